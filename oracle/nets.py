@@ -1,0 +1,168 @@
+"""Functional CPU restatement of the reference forward passes (eval and train mode).
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  Each function takes a
+``state_dict`` with the reference's key names and computes what the reference
+``nn.Module`` computes, citing the file:line it follows (paths relative to
+/root/reference).  dtype follows the input (fp32 or fp64).
+"""
+import torch
+import torch.nn.functional as F
+
+
+class SD:
+    """state_dict view with a key prefix; casts to the working dtype."""
+
+    def __init__(self, sd, prefix="", dtype=torch.float32, train=False, stats=None):
+        self.sd, self.prefix, self.dtype, self.train = sd, prefix, dtype, train
+        self.stats = stats if stats is not None else {}
+
+    def sub(self, name):
+        return SD(self.sd, self.prefix + name + ".", self.dtype, self.train, self.stats)
+
+    def __getitem__(self, k):
+        return self.sd[self.prefix + k].to(self.dtype)
+
+    def has(self, k):
+        return (self.prefix + k) in self.sd
+
+
+def bn(p, x, eps):
+    """nn.BatchNorm2d: eval uses running stats; train uses biased batch var
+    (torch semantics).  Batch stats are recorded in p.stats."""
+    if p.train:
+        mean = x.mean(dim=(0, 2, 3))
+        var = x.var(dim=(0, 2, 3), unbiased=False)
+        p.stats[p.prefix] = (mean.detach(), var.detach())
+    else:
+        mean, var = p["running_mean"], p["running_var"]
+    scale = p["weight"] / torch.sqrt(var + eps)
+    return x * scale.view(1, -1, 1, 1) + (p["bias"] - mean * scale).view(1, -1, 1, 1)
+
+
+def prelu(x, alpha):
+    return torch.clamp(x, min=0) + alpha.view(1, -1, 1, 1) * torch.clamp(x, max=0)
+
+
+# --------------------------------------------------------------------------- ERFNet
+def erf_downsampler(p, x):
+    """DownsamplerBlock, model/ERFNet.py:16-27."""
+    y = torch.cat([F.conv2d(x, p["conv.weight"], p["conv.bias"], stride=2, padding=1),
+                   F.max_pool2d(x, 2, 2)], 1)
+    return F.relu(bn(p.sub("bn"), y, 1e-3))
+
+
+def erf_nb1d(p, x, d):
+    """non_bottleneck_1d (dropout p=0 / eval), model/ERFNet.py:30-65."""
+    y = F.relu(F.conv2d(x, p["conv3x1_1.weight"], p["conv3x1_1.bias"], padding=(1, 0)))
+    y = F.conv2d(y, p["conv1x3_1.weight"], p["conv1x3_1.bias"], padding=(0, 1))
+    y = F.relu(bn(p.sub("bn1"), y, 1e-3))
+    y = F.relu(F.conv2d(y, p["conv3x1_2.weight"], p["conv3x1_2.bias"], padding=(d, 0), dilation=(d, 1)))
+    y = F.conv2d(y, p["conv1x3_2.weight"], p["conv1x3_2.bias"], padding=(0, d), dilation=(1, d))
+    y = bn(p.sub("bn2"), y, 1e-3)
+    return F.relu(y + x)
+
+
+def erf_upsampler(p, x):
+    """UpsamplerBlock, model/ERFNet.py:103-112."""
+    y = F.conv_transpose2d(x, p["conv.weight"], p["conv.bias"], stride=2, padding=1, output_padding=1)
+    return F.relu(bn(p.sub("bn"), y, 1e-3))
+
+
+ERF_ENC_DILATIONS = [None, 1, 1, 1, 1, 1, None, 2, 4, 8, 16, 2, 4, 8, 16]  # ERFNet.py:75-86
+ERF_DEC_LAYERS = ["up", 1, 1, "up", 1, 1]                                   # ERFNet.py:120-126
+
+
+def erfnet(sd, x, train=False, stats=None):
+    """ERFNet.forward (only_encode=False), model/ERFNet.py:151-156."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = erf_downsampler(p.sub("encoder.initial_block"), x)
+    for i, d in enumerate(ERF_ENC_DILATIONS):
+        q = p.sub("encoder.layers.%d" % i)
+        y = erf_downsampler(q, y) if d is None else erf_nb1d(q, y, d)
+    for i, d in enumerate(ERF_DEC_LAYERS):
+        q = p.sub("decoder.layers.%d" % i)
+        y = erf_upsampler(q, y) if d == "up" else erf_nb1d(q, y, d)
+    return F.conv_transpose2d(y, p["decoder.output_conv.weight"], p["decoder.output_conv.bias"], stride=2)
+
+
+# --------------------------------------------------------------------------- DABNet
+def dab_bnprelu(p, x):
+    """BNPReLU, model/DABNet.py:38-48."""
+    return prelu(bn(p.sub("bn"), x, 1e-3), p["acti.weight"])
+
+
+def dab_conv(p, x, stride=1, padding=0, dilation=1, groups=1, bn_acti=False):
+    """Conv (bias=False), model/DABNet.py:16-35."""
+    y = F.conv2d(x, p["conv.weight"], None, stride, padding, dilation, groups)
+    return dab_bnprelu(p.sub("bn_prelu"), y) if bn_acti else y
+
+
+def dab_module(p, x, d):
+    """DABModule, model/DABNet.py:51-83."""
+    c = x.shape[1] // 2
+    y = dab_bnprelu(p.sub("bn_relu_1"), x)
+    y = dab_conv(p.sub("conv3x3"), y, 1, 1, bn_acti=True)
+    b1 = dab_conv(p.sub("dconv3x1"), y, 1, (1, 0), 1, c, True)
+    b1 = dab_conv(p.sub("dconv1x3"), b1, 1, (0, 1), 1, c, True)
+    b2 = dab_conv(p.sub("ddconv3x1"), y, 1, (d, 0), (d, 1), c, True)
+    b2 = dab_conv(p.sub("ddconv1x3"), b2, 1, (0, d), (1, d), c, True)
+    y = dab_bnprelu(p.sub("bn_relu_2"), b1 + b2)
+    y = dab_conv(p.sub("conv1x1"), y)
+    return y + x
+
+
+def dab_down(p, x, n_in, n_out):
+    """DownSamplingBlock, model/DABNet.py:86-110."""
+    y = dab_conv(p.sub("conv3x3"), x, 2, 1)
+    if n_in < n_out:
+        y = torch.cat([y, F.max_pool2d(x, 2, 2)], 1)
+    return dab_bnprelu(p.sub("bn_prelu"), y)
+
+
+def dab_inject(x, ratio):
+    """InputInjection, model/DABNet.py:113-124 (AvgPool2d(3,2,1), count_include_pad)."""
+    for _ in range(ratio):
+        x = F.avg_pool2d(x, 3, 2, 1)
+    return x
+
+
+DAB_D1 = [2, 2, 2]                 # DABNet.py:145-147
+DAB_D2 = [4, 4, 8, 8, 16, 16]      # DABNet.py:151
+
+
+def dabnet(sd, x, train=False, stats=None, upsample=True):
+    """DABNet.forward, model/DABNet.py:160-183."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = dab_conv(p.sub("init_conv.0"), x, 2, 1, bn_acti=True)
+    y = dab_conv(p.sub("init_conv.1"), y, 1, 1, bn_acti=True)
+    y = dab_conv(p.sub("init_conv.2"), y, 1, 1, bn_acti=True)
+    d1, d2, d3 = dab_inject(x, 1), dab_inject(x, 2), dab_inject(x, 3)
+    y0 = dab_bnprelu(p.sub("bn_prelu_1"), torch.cat([y, d1], 1))
+    y10 = dab_down(p.sub("downsample_1"), y0, 35, 64)
+    y = y10
+    for i, d in enumerate(DAB_D1):
+        y = dab_module(p.sub("DAB_Block_1.DAB_Module_1_%d" % i), y, d)
+    y1 = dab_bnprelu(p.sub("bn_prelu_2"), torch.cat([y, y10, d2], 1))
+    y20 = dab_down(p.sub("downsample_2"), y1, 131, 128)
+    y = y20
+    for i, d in enumerate(DAB_D2):
+        y = dab_module(p.sub("DAB_Block_2.DAB_Module_2_%d" % i), y, d)
+    y2 = dab_bnprelu(p.sub("bn_prelu_3"), torch.cat([y, y20, d3], 1))
+    out = dab_conv(p.sub("classifier.0"), y2)
+    if upsample:
+        out = F.interpolate(out, x.shape[2:], mode="bilinear", align_corners=False)
+    return out
+
+
+FORWARD = {"ERFNet": erfnet, "DABNet": dabnet}
+
+
+def forward(name, sd, x, **kw):
+    return FORWARD[name](sd, x, **kw)
+
+
+def argmax_mask(logits):
+    """test.py:79-82 / predict.py:52-54: numpy argmax over classes, uint8 (first max wins)."""
+    a = logits.detach().cpu().numpy()
+    import numpy as np
+    return np.asarray(np.argmax(a, axis=1), dtype=np.uint8)

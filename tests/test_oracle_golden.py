@@ -1,0 +1,78 @@
+"""Pin the CPU oracle (oracle/) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tools/make_golden.py in the build container)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import spec_state_dict
+from oracle import fixture, loss as oloss, nets
+
+
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
+def test_eval_forward_matches_reference(name, spec, golden):
+    sd = spec_state_dict(spec, name)
+    g = golden(name)
+    with torch.no_grad():
+        y = nets.forward(name, sd, fixture.make_input(1, 64, 128))
+    ref = torch.from_numpy(g["eval_1x64x128_logits"])
+    assert y.shape == ref.shape
+    rel = (y - ref).norm() / ref.norm()
+    assert rel < 1e-5, rel  # fp32 re-association noise (BN as scale+shift)
+    assert (nets.argmax_mask(y) == g["eval_1x64x128_argmax"]).mean() > 0.9999
+    with torch.no_grad():
+        y = nets.forward(name, sd, fixture.make_input(2, 128, 256))
+    ref = torch.from_numpy(g["eval_2x128x256_logits_s4"])
+    rel = (y[:, :, ::4, ::4] - ref).norm() / ref.norm()
+    assert rel < 1e-5, rel  # fp32 re-association noise (BN as scale+shift)
+    s = g["eval_2x128x256_sum"]
+    assert abs(y.double().abs().sum().item() - s[1]) / s[1] < 1e-6
+    assert (nets.argmax_mask(y) == g["eval_2x128x256_argmax"]).mean() > 0.9999
+
+
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
+def test_train_forward_backward_matches_reference_fp64(name, spec, golden):
+    sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v)
+          for k, v in spec_state_dict(spec, name).items()}
+    g = golden(name)
+    x = fixture.make_input(2, 64, 128).double()
+    lab = fixture.make_labels(2, 64, 128, 19)
+    y = nets.forward(name, sd, x, train=True)
+    l, _, _ = oloss.weighted_ce(y, lab, torch.tensor(fixture.CLASS_WEIGHTS, dtype=torch.float64))
+    assert abs(l.item() - g["train_2x64x128_loss"][0]) < 1e-9 * max(1.0, abs(l.item()))
+    ref = torch.from_numpy(g["train_2x64x128_logits_s4"]).double()
+    assert ((y.detach()[:, :, ::4, ::4] - ref).norm() / ref.norm()) < 1e-6
+    l.backward()
+    stats = json.loads(bytes(g["train_2x64x128_gradstats"]).decode())
+    checked = 0
+    for k, (gnorm, gsum, wnorm) in stats.items():
+        gr = sd[k].grad
+        assert gr is not None, k
+        if gnorm < 1e-10 * max(wnorm, 1e-30):   # mathematically-zero grads (bias feeding train-mode BN), SURVEY H8
+            continue
+        assert abs(gr.norm().item() - gnorm) / gnorm < 1e-6, k
+        checked += 1
+    assert checked > 20
+    for key in g.files:
+        if key.startswith("train_2x64x128_grad::"):
+            k = key.split("::")[1]
+            ref = torch.from_numpy(g[key]).double()
+            assert ((sd[k].grad - ref).norm() / ref.norm()) < 1e-5, k
+
+
+def test_state_dict_spec_counts(spec):
+    # parameter counts published by the reference (usage.txt:91-109)
+    assert spec["ERFNet"]["n_params"] == 2066642
+    assert spec["DABNet"]["n_params"] == 756643
+
+
+def test_weighted_ce_matches_reference(golden):
+    g = golden("loss")
+    logits = torch.from_numpy(g["logits"])
+    lab = torch.from_numpy(g["labels"])
+    w = torch.tensor(fixture.CLASS_WEIGHTS, dtype=torch.float64)
+    l, swl, sw = oloss.weighted_ce(logits, lab, w)
+    assert abs(l.item() - g["loss"][0]) < 1e-12
+    gr = oloss.weighted_ce_grad(logits, lab, w)
+    assert np.abs(gr.numpy() - g["grad"]).max() < 1e-14
