@@ -1,0 +1,24 @@
+"""build_model(model_name, num_classes) -- same signature and names as the reference's
+builders/model_builder.py:21-59.  Models on the B200 hot path are built from the CUDA-backed
+modules under model/; names of the reference zoo that are outside the hot-path scope raise
+NotImplementedError (the reference silently returns None for unknown names; there is no CPU or
+eager fallback here, so the failure is explicit).
+"""
+from model.ERFNet import ERFNet
+from model.DABNet import DABNet
+
+_HOT_PATH = {
+    "ERFNet": ERFNet,
+    "DABNet": DABNet,
+}
+_REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
+                    "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")
+
+
+def build_model(model_name, num_classes):
+    if model_name in _HOT_PATH:
+        return _HOT_PATH[model_name](classes=num_classes)
+    if model_name in _REFERENCE_NAMES:
+        raise NotImplementedError("%s is not (yet) on the B200 hot path; available: %s"
+                                  % (model_name, ", ".join(sorted(_HOT_PATH))))
+    raise NotImplementedError("unknown model name %r" % (model_name,))

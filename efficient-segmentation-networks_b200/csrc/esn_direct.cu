@@ -1,0 +1,242 @@
+// CUDA-core direct convolution (fp32 accumulate), NHWC, with the fused epilogue of esn.h.
+// This is the exact-arithmetic path (fp32 parity against the reference) and the path for the
+// shapes the tcgen05 kernel does not take: Cin = 3 stems read straight from the caller's NCHW
+// fp32 image, depthwise convs, odd channel counts.
+#include "esn_common.cuh"
+
+namespace {
+
+struct DirectArgs {
+  const void* x;
+  void* y;
+  const float* w;
+  int N, Hi, Wi, Cin, x_cs;
+  int Ho, Wo, Cout, y_cs;
+  int kh, kw, stride, pad_h, pad_w, dil_h, dil_w, transposed, dw, x_nchw;
+  EpiArgs ep;
+};
+
+template <typename TI, typename TO, int COV, int CIV>
+__global__ void __launch_bounds__(256) conv_direct_kernel(const DirectArgs a) {
+  const int ncog = (a.Cout + COV - 1) / COV;
+  const long long total = (long long)a.N * a.Ho * a.Wo * ncog;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cog = (int)(idx % ncog);
+  const long long pix = idx / ncog;
+  const int wo = (int)(pix % a.Wo);
+  const int ho = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const int co = cog * COV;
+  const TI* __restrict__ x = reinterpret_cast<const TI*>(a.x);
+
+  float acc[COV];
+#pragma unroll
+  for (int j = 0; j < COV; ++j) acc[j] = 0.f;
+
+  for (int r = 0; r < a.kh; ++r) {
+    int hi;
+    if (!a.transposed) {
+      hi = ho * a.stride - a.pad_h + r * a.dil_h;
+    } else {
+      const int t = ho + a.pad_h - r * a.dil_h;
+      if (t < 0 || (t % a.stride) != 0) continue;
+      hi = t / a.stride;
+    }
+    if (hi < 0 || hi >= a.Hi) continue;
+    for (int s = 0; s < a.kw; ++s) {
+      int wi;
+      if (!a.transposed) {
+        wi = wo * a.stride - a.pad_w + s * a.dil_w;
+      } else {
+        const int t = wo + a.pad_w - s * a.dil_w;
+        if (t < 0 || (t % a.stride) != 0) continue;
+        wi = t / a.stride;
+      }
+      if (wi < 0 || wi >= a.Wi) continue;
+      const int tap = r * a.kw + s;
+      if (a.dw) {
+        const float* wt = a.w + (size_t)tap * a.Cout + co;
+        const TI* xp = x + ((size_t)((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs + co;
+        if (COV == 4) {
+          const float4 xv = ld4<TI>(xp);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wt));
+          acc[0] += xv.x * wv.x;
+          acc[1 % COV] += xv.y * wv.y;
+          acc[2 % COV] += xv.z * wv.z;
+          acc[3 % COV] += xv.w * wv.w;
+        } else {
+          acc[0] += ld1<TI>(xp) * __ldg(wt);
+        }
+      } else {
+        const float* wt = a.w + (size_t)tap * a.Cin * a.Cout + co;
+        if (a.x_nchw) {
+          for (int ci = 0; ci < a.Cin; ++ci) {
+            const float xv = ld1<TI>(x + ((size_t)((size_t)n * a.Cin + ci) * a.Hi + hi) * a.Wi + wi);
+            const float* wr = wt + (size_t)ci * a.Cout;
+#pragma unroll
+            for (int j = 0; j < COV; ++j)
+              if (co + j < a.Cout) acc[j] += xv * __ldg(wr + j);
+          }
+        } else {
+          const TI* xp = x + ((size_t)((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs;
+          for (int ci = 0; ci < a.Cin; ci += CIV) {
+            float xv[CIV];
+            if (CIV == 4) {
+              const float4 t = ld4<TI>(xp + ci);
+              xv[0] = t.x;
+              xv[1 % CIV] = t.y;
+              xv[2 % CIV] = t.z;
+              xv[3 % CIV] = t.w;
+            } else {
+              xv[0] = ld1<TI>(xp + ci);
+            }
+#pragma unroll
+            for (int i = 0; i < CIV; ++i) {
+              const float* wr = wt + (size_t)(ci + i) * a.Cout;
+              if (COV == 4) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr));
+                acc[0] += xv[i] * wv.x;
+                acc[1 % COV] += xv[i] * wv.y;
+                acc[2 % COV] += xv[i] * wv.z;
+                acc[3 % COV] += xv[i] * wv.w;
+              } else {
+                acc[0] += xv[i] * __ldg(wr);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- fused epilogue
+  const size_t opix = ((size_t)((size_t)n * a.Ho + ho) * a.Wo + wo);
+  float v[COV];
+#pragma unroll
+  for (int j = 0; j < COV; ++j) {
+    const int c = co + j;
+    if (c < a.Cout) {
+      const float sc = a.ep.scale ? __ldg(a.ep.scale + c) : 1.f;
+      const float sh = a.ep.shift ? __ldg(a.ep.shift + c) : 0.f;
+      float t = acc[j] * sc + sh;
+      if (a.ep.res) {
+        const size_t ri = opix * a.ep.res_cstride + c;
+        t += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
+                                           : reinterpret_cast<const float*>(a.ep.res)[ri];
+      }
+      const float al = (a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + c) : 0.f;
+      v[j] = apply_act(t, a.ep.act, al);
+    } else {
+      v[j] = 0.f;
+    }
+  }
+  TO* yp = reinterpret_cast<TO*>(a.y) + opix * a.y_cs + co;
+  if (COV == 4) {
+    st4<TO>(yp, make_float4(v[0], v[1 % COV], v[2 % COV], v[3 % COV]));
+  } else {
+    st1<TO>(yp, v[0]);
+  }
+}
+
+template <typename TI, typename TO>
+int launch_direct(const DirectArgs& a, bool cov4, bool civ4, cudaStream_t st) {
+  const int cov = cov4 ? 4 : 1;
+  const long long total = (long long)a.N * a.Ho * a.Wo * ((a.Cout + cov - 1) / cov);
+  const int block = 256;
+  const int grid = esn_cdiv(total, block);
+  if (cov4 && civ4)
+    conv_direct_kernel<TI, TO, 4, 4><<<grid, block, 0, st>>>(a);
+  else if (cov4)
+    conv_direct_kernel<TI, TO, 4, 1><<<grid, block, 0, st>>>(a);
+  else if (civ4)
+    conv_direct_kernel<TI, TO, 1, 4><<<grid, block, 0, st>>>(a);
+  else
+    conv_direct_kernel<TI, TO, 1, 1><<<grid, block, 0, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+}  // namespace
+
+int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y) {
+  if (e.act < ESN_ACT_NONE || e.act > ESN_ACT_PRELU) return ESN_ERR_BAD_ARG;
+  if (e.act == ESN_ACT_PRELU && !e.alpha) return ESN_ERR_BAD_ARG;
+  if (e.residual.ptr) {
+    const EsnTensor& r = e.residual;
+    if (!esn_valid_nhwc(r)) return ESN_ERR_BAD_ARG;
+    if (r.n != y.n || r.h != y.h || r.w != y.w || r.c != y.c) return ESN_ERR_BAD_SHAPE;
+  }
+  return ESN_OK;
+}
+
+extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
+  if (!p || !p->w) return ESN_ERR_BAD_ARG;
+  const EsnTensor& x = p->x;
+  const EsnTensor& y = p->y;
+  if (!esn_valid_nhwc(y)) return ESN_ERR_BAD_ARG;
+  const bool nchw = x.layout == ESN_NCHW;
+  if (nchw) {
+    if (!x.ptr || x.dtype != ESN_F32) return ESN_ERR_BAD_ARG;
+  } else if (!esn_valid_nhwc(x)) {
+    return ESN_ERR_BAD_ARG;
+  }
+  if (p->kh < 1 || p->kw < 1 || p->stride < 1 || p->dil_h < 1 || p->dil_w < 1) return ESN_ERR_BAD_ARG;
+  const bool dw = p->groups != 1;
+  if (dw && (p->groups != x.c || x.c != y.c || nchw)) return ESN_ERR_UNSUPPORTED;
+  if (x.n != y.n) return ESN_ERR_BAD_SHAPE;
+  int eh, ew;
+  if (!p->transposed) {
+    eh = (x.h + 2 * p->pad_h - p->dil_h * (p->kh - 1) - 1) / p->stride + 1;
+    ew = (x.w + 2 * p->pad_w - p->dil_w * (p->kw - 1) - 1) / p->stride + 1;
+    if (eh != y.h || ew != y.w) return ESN_ERR_BAD_SHAPE;
+  } else {
+    eh = (x.h - 1) * p->stride - 2 * p->pad_h + p->dil_h * (p->kh - 1) + 1;
+    ew = (x.w - 1) * p->stride - 2 * p->pad_w + p->dil_w * (p->kw - 1) + 1;
+    if (y.h < eh || y.h >= eh + p->stride || y.w < ew || y.w >= ew + p->stride) return ESN_ERR_BAD_SHAPE;
+  }
+  int rc = esn_check_epilogue(p->ep, y);
+  if (rc) return rc;
+
+  DirectArgs a;
+  a.x = x.ptr;
+  a.y = y.ptr;
+  a.w = reinterpret_cast<const float*>(p->w);
+  a.N = x.n;
+  a.Hi = x.h;
+  a.Wi = x.w;
+  a.Cin = x.c;
+  a.x_cs = nchw ? 0 : x.c_stride;
+  a.Ho = y.h;
+  a.Wo = y.w;
+  a.Cout = y.c;
+  a.y_cs = y.c_stride;
+  a.kh = p->kh;
+  a.kw = p->kw;
+  a.stride = p->stride;
+  a.pad_h = p->pad_h;
+  a.pad_w = p->pad_w;
+  a.dil_h = p->dil_h;
+  a.dil_w = p->dil_w;
+  a.transposed = p->transposed;
+  a.dw = dw;
+  a.x_nchw = nchw;
+  a.ep = make_epi(p->ep);
+
+  const size_t ysz = y.dtype == ESN_F32 ? 4 : 2, xsz = x.dtype == ESN_F32 ? 4 : 2;
+  const bool scale_al = (!p->ep.scale || ((uintptr_t)p->ep.scale % 16) == 0);
+  bool cov4 = (y.c % 4 == 0) && (y.c_stride % 4 == 0) && ((uintptr_t)y.ptr % (4 * ysz) == 0) &&
+              ((uintptr_t)p->w % 16 == 0) && scale_al;
+  bool civ4 = !nchw && !dw && (x.c % 4 == 0) && (x.c_stride % 4 == 0) && ((uintptr_t)x.ptr % (4 * xsz) == 0);
+  if (dw) {  // depthwise reads x with the same vector width as it writes y
+    cov4 = cov4 && (x.c_stride % 4 == 0) && ((uintptr_t)x.ptr % (4 * xsz) == 0);
+    civ4 = false;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x.dtype == ESN_F32 && y.dtype == ESN_F32) return launch_direct<float, float>(a, cov4, civ4, st);
+  if (x.dtype == ESN_F32 && y.dtype == ESN_BF16) return launch_direct<float, __nv_bfloat16>(a, cov4, civ4, st);
+  if (x.dtype == ESN_BF16 && y.dtype == ESN_BF16)
+    return launch_direct<__nv_bfloat16, __nv_bfloat16>(a, cov4, civ4, st);
+  if (x.dtype == ESN_BF16 && y.dtype == ESN_F32) return launch_direct<__nv_bfloat16, float>(a, cov4, civ4, st);
+  return ESN_ERR_BAD_ARG;
+}

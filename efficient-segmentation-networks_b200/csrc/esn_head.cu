@@ -1,0 +1,336 @@
+// Segmentation heads (logits in the caller's NCHW layout and/or the uint8 argmax mask) and the
+// weighted cross-entropy loss.  All are HBM-bound: one thread per (low-res or output) pixel,
+// stores coalesced along W inside each class plane.
+#include "esn_common.cuh"
+
+namespace {
+
+constexpr int kMaxClasses = 32;
+
+template <typename T> __device__ __forceinline__ void st2(T* p, float a, float b);
+template <> __device__ __forceinline__ void st2<float>(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <> __device__ __forceinline__ void st2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// ---------------------------------------------------------------- ConvTranspose2d(Cin, classes, 2, stride 2)
+struct ConvtHeadArgs {
+  const void* x;
+  const float* w;     // [2][2][Cin][32]
+  const float* bias;  // [classes]
+  void* logits;       // NCHW or null
+  uint8_t* mask;      // or null
+  int N, Hi, Wi, Cin, x_cs, classes;
+};
+
+template <typename TI, typename TL, int CIN>
+__global__ void __launch_bounds__(128) convt2x2_head_kernel(const ConvtHeadArgs a) {
+  extern __shared__ float sw[];  // [4][CIN][32] + bias[32]
+  float* sb = sw + 4 * CIN * 32;
+  for (int i = threadIdx.x; i < 4 * CIN * 32; i += blockDim.x) sw[i] = a.w[i];
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) sb[i] = i < a.classes ? a.bias[i] : 0.f;
+  __syncthreads();
+  const long long total = (long long)a.N * a.Hi * a.Wi;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % a.Wi);
+  const int i = (int)((idx / a.Wi) % a.Hi);
+  const int n = (int)(idx / ((long long)a.Wi * a.Hi));
+  float f[CIN];
+  const TI* xp = reinterpret_cast<const TI*>(a.x) + (size_t)idx * a.x_cs;
+#pragma unroll
+  for (int c = 0; c < CIN; c += 4) {
+    const float4 t = ld4<TI>(xp + c);
+    f[c] = t.x;
+    f[c + 1] = t.y;
+    f[c + 2] = t.z;
+    f[c + 3] = t.w;
+  }
+  const int Ho = 2 * a.Hi, Wo = 2 * a.Wi;
+  const int ncls4 = (a.classes + 3) / 4;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float acc[2][kMaxClasses];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+      for (int q = 0; q < kMaxClasses / 4; ++q) {
+        if (q < ncls4) {
+          float4 v = *reinterpret_cast<const float4*>(sb + 4 * q);
+          const float* wp = sw + (size_t)((r * 2 + s) * CIN) * 32 + 4 * q;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const float4 wv = *reinterpret_cast<const float4*>(wp + c * 32);
+            v.x += f[c] * wv.x;
+            v.y += f[c] * wv.y;
+            v.z += f[c] * wv.z;
+            v.w += f[c] * wv.w;
+          }
+          acc[s][4 * q] = v.x;
+          acc[s][4 * q + 1] = v.y;
+          acc[s][4 * q + 2] = v.z;
+          acc[s][4 * q + 3] = v.w;
+        }
+      }
+    }
+    const int ho = 2 * i + r;
+    if (a.logits) {
+      TL* lp = reinterpret_cast<TL*>(a.logits);
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < a.classes)
+          st2<TL>(lp + ((size_t)((size_t)n * a.classes + k) * Ho + ho) * Wo + 2 * j, acc[0][k], acc[1][k]);
+    }
+    if (a.mask) {
+      int b0 = 0, b1 = 0;
+      float m0 = acc[0][0], m1 = acc[1][0];
+#pragma unroll
+      for (int k = 1; k < kMaxClasses; ++k)
+        if (k < a.classes) {
+          if (acc[0][k] > m0) { m0 = acc[0][k]; b0 = k; }
+          if (acc[1][k] > m1) { m1 = acc[1][k]; b1 = k; }
+        }
+      *reinterpret_cast<uchar2*>(a.mask + ((size_t)n * Ho + ho) * Wo + 2 * j) = make_uchar2((uint8_t)b0, (uint8_t)b1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- bilinear (align_corners=False) head
+struct BilinearHeadArgs {
+  const void* x;  // NHWC low-res scores
+  void* logits;
+  uint8_t* mask;
+  int N, Hi, Wi, x_cs, classes, Ho, Wo;
+  float sh, sw;   // in/out
+};
+
+template <typename TI, typename TL>
+__global__ void __launch_bounds__(256) bilinear_head_kernel(const BilinearHeadArgs a) {
+  const long long total = (long long)a.N * a.Ho * a.Wo;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wo = (int)(idx % a.Wo);
+  const int ho = (int)((idx / a.Wo) % a.Ho);
+  const int n = (int)(idx / ((long long)a.Wo * a.Ho));
+  // torch area_pixel_compute_source_index, align_corners=False, cubic=False
+  float fh = a.sh * (ho + 0.5f) - 0.5f;
+  fh = fh < 0.f ? 0.f : fh;
+  float fw = a.sw * (wo + 0.5f) - 0.5f;
+  fw = fw < 0.f ? 0.f : fw;
+  const int h0 = (int)fh, w0 = (int)fw;
+  const int hp = (h0 < a.Hi - 1) ? 1 : 0, wp = (w0 < a.Wi - 1) ? 1 : 0;
+  const float lh1 = fh - h0, lh0 = 1.f - lh1, lw1 = fw - w0, lw0 = 1.f - lw1;
+  const TI* x = reinterpret_cast<const TI*>(a.x);
+  const TI* p00 = x + ((size_t)((size_t)n * a.Hi + h0) * a.Wi + w0) * a.x_cs;
+  const TI* p01 = p00 + (size_t)wp * a.x_cs;
+  const TI* p10 = p00 + (size_t)hp * a.Wi * a.x_cs;
+  const TI* p11 = p10 + (size_t)wp * a.x_cs;
+  float best = 0.f;
+  int bi = 0;
+  TL* lp = reinterpret_cast<TL*>(a.logits);
+  for (int k = 0; k < a.classes; ++k) {
+    const float v = lh0 * (lw0 * ld1<TI>(p00 + k) + lw1 * ld1<TI>(p01 + k)) +
+                    lh1 * (lw0 * ld1<TI>(p10 + k) + lw1 * ld1<TI>(p11 + k));
+    if (lp) st1<TL>(lp + ((size_t)((size_t)n * a.classes + k) * a.Ho + ho) * a.Wo + wo, v);
+    if (k == 0 || v > best) { best = v; bi = k; }
+  }
+  if (a.mask) a.mask[idx] = (uint8_t)bi;
+}
+
+// ---------------------------------------------------------------- weighted cross-entropy on NCHW logits
+struct CEArgs {
+  const void* logits;
+  const long long* target;
+  const float* weight;
+  float* sums;
+  void* dlogits;
+  int N, C, H, W, ignore;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) weighted_ce_kernel(const CEArgs a) {
+  const long long hw = (long long)a.H * a.W;
+  const long long total = (long long)a.N * hw;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float wl = 0.f, wsum = 0.f;
+  if (idx < total) {
+    const int n = (int)(idx / hw);
+    const long long px = idx % hw;
+    const T* lp = reinterpret_cast<const T*>(a.logits) + (size_t)n * a.C * hw + px;
+    const long long y = a.target[idx];
+    const bool valid = (y != a.ignore) && y >= 0 && y < a.C;
+    float v[kMaxClasses];
+    float m = -INFINITY, xy = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < a.C) {
+        v[k] = ld1<T>(lp + (size_t)k * hw);
+        m = fmaxf(m, v[k]);
+        if (k == (int)y) xy = v[k];
+      }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < a.C) {
+        v[k] = __expf(v[k] - m);
+        s += v[k];
+      }
+    const float wy = valid ? (a.weight ? __ldg(a.weight + y) : 1.f) : 0.f;
+    if (valid) {
+      wl = wy * (m + logf(s) - xy);  // w * (lse - x_y)
+      wsum = wy;
+    }
+    if (a.dlogits) {
+      T* gp = reinterpret_cast<T*>(a.dlogits) + (size_t)n * a.C * hw + px;
+      const float inv = wy / s;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < a.C) st1<T>(gp + (size_t)k * hw, v[k] * inv - ((valid && k == (int)y) ? wy : 0.f));
+    }
+  }
+  // block reduction: warp shuffle -> smem -> one atomic pair per CTA
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wl += __shfl_xor_sync(0xffffffffu, wl, o);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = wl;
+    red[1][warp] = wsum;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    wl = lane < 8 ? red[0][lane] : 0.f;
+    wsum = lane < 8 ? red[1][lane] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      wl += __shfl_xor_sync(0xffffffffu, wl, o);
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if (lane == 0) {
+      atomicAdd(a.sums, wl);
+      atomicAdd(a.sums + 1, wsum);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int esn_head_convt2x2(const EsnHead* p, void* stream) {
+  if (!p || !p->w || !p->bias || !esn_valid_nhwc(p->x)) return ESN_ERR_BAD_ARG;
+  if (!p->logits.ptr && !p->mask) return ESN_ERR_BAD_ARG;
+  if (p->classes < 1 || p->classes > kMaxClasses) return ESN_ERR_UNSUPPORTED;
+  const EsnTensor& x = p->x;
+  if (p->out_h != 2 * x.h || p->out_w != 2 * x.w) return ESN_ERR_BAD_SHAPE;
+  if (x.c != 16 || x.c_stride % 4) return ESN_ERR_UNSUPPORTED;
+  if ((uintptr_t)x.ptr % 16) return ESN_ERR_ALIGN;
+  int ldt = ESN_F32;
+  if (p->logits.ptr) {
+    const EsnTensor& l = p->logits;
+    if (l.layout != ESN_NCHW || (l.dtype != ESN_F32 && l.dtype != ESN_BF16)) return ESN_ERR_BAD_ARG;
+    if (l.n != x.n || l.c != p->classes || l.h != p->out_h || l.w != p->out_w) return ESN_ERR_BAD_SHAPE;
+    ldt = l.dtype;
+  }
+  ConvtHeadArgs a;
+  a.x = x.ptr;
+  a.w = p->w;
+  a.bias = p->bias;
+  a.logits = p->logits.ptr;
+  a.mask = p->mask;
+  a.N = x.n;
+  a.Hi = x.h;
+  a.Wi = x.w;
+  a.Cin = x.c;
+  a.x_cs = x.c_stride;
+  a.classes = p->classes;
+  const long long total = (long long)x.n * x.h * x.w;
+  const int block = 128, grid = esn_cdiv(total, block);
+  const size_t smem = (4 * 16 * 32 + 32) * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x.dtype == ESN_F32 && ldt == ESN_F32)
+    convt2x2_head_kernel<float, float, 16><<<grid, block, smem, st>>>(a);
+  else if (x.dtype == ESN_F32)
+    convt2x2_head_kernel<float, __nv_bfloat16, 16><<<grid, block, smem, st>>>(a);
+  else if (ldt == ESN_F32)
+    convt2x2_head_kernel<__nv_bfloat16, float, 16><<<grid, block, smem, st>>>(a);
+  else
+    convt2x2_head_kernel<__nv_bfloat16, __nv_bfloat16, 16><<<grid, block, smem, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_head_bilinear(const EsnHead* p, void* stream) {
+  if (!p || !esn_valid_nhwc(p->x)) return ESN_ERR_BAD_ARG;
+  if (!p->logits.ptr && !p->mask) return ESN_ERR_BAD_ARG;
+  const EsnTensor& x = p->x;
+  if (p->classes != x.c || p->out_h < 1 || p->out_w < 1) return ESN_ERR_BAD_SHAPE;
+  int ldt = ESN_F32;
+  if (p->logits.ptr) {
+    const EsnTensor& l = p->logits;
+    if (l.layout != ESN_NCHW || (l.dtype != ESN_F32 && l.dtype != ESN_BF16)) return ESN_ERR_BAD_ARG;
+    if (l.n != x.n || l.c != p->classes || l.h != p->out_h || l.w != p->out_w) return ESN_ERR_BAD_SHAPE;
+    ldt = l.dtype;
+  }
+  BilinearHeadArgs a;
+  a.x = x.ptr;
+  a.logits = p->logits.ptr;
+  a.mask = p->mask;
+  a.N = x.n;
+  a.Hi = x.h;
+  a.Wi = x.w;
+  a.x_cs = x.c_stride;
+  a.classes = p->classes;
+  a.Ho = p->out_h;
+  a.Wo = p->out_w;
+  a.sh = (float)x.h / (float)p->out_h;
+  a.sw = (float)x.w / (float)p->out_w;
+  const long long total = (long long)x.n * p->out_h * p->out_w;
+  const int block = 256, grid = esn_cdiv(total, block);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x.dtype == ESN_F32 && ldt == ESN_F32)
+    bilinear_head_kernel<float, float><<<grid, block, 0, st>>>(a);
+  else if (x.dtype == ESN_F32)
+    bilinear_head_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(a);
+  else if (ldt == ESN_F32)
+    bilinear_head_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(a);
+  else
+    bilinear_head_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_weighted_ce(const EsnCE* p, void* stream) {
+  if (!p || !p->logits.ptr || !p->target || !p->sums) return ESN_ERR_BAD_ARG;
+  const EsnTensor& l = p->logits;
+  if (l.layout != ESN_NCHW || (l.dtype != ESN_F32 && l.dtype != ESN_BF16)) return ESN_ERR_BAD_ARG;
+  if (l.c < 1 || l.c > kMaxClasses) return ESN_ERR_UNSUPPORTED;
+  if (p->dlogits.ptr) {
+    const EsnTensor& g = p->dlogits;
+    if (g.layout != ESN_NCHW || g.dtype != l.dtype) return ESN_ERR_BAD_ARG;
+    if (g.n != l.n || g.c != l.c || g.h != l.h || g.w != l.w) return ESN_ERR_BAD_SHAPE;
+  }
+  CEArgs a;
+  a.logits = l.ptr;
+  a.target = reinterpret_cast<const long long*>(p->target);
+  a.weight = p->weight;
+  a.sums = p->sums;
+  a.dlogits = p->dlogits.ptr;
+  a.N = l.n;
+  a.C = l.c;
+  a.H = l.h;
+  a.W = l.w;
+  a.ignore = p->ignore_label;
+  const long long total = (long long)l.n * l.h * l.w;
+  const int block = 256, grid = esn_cdiv(total, block);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (l.dtype == ESN_F32)
+    weighted_ce_kernel<float><<<grid, block, 0, st>>>(a);
+  else
+    weighted_ce_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}

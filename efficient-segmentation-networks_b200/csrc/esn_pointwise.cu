@@ -1,0 +1,234 @@
+// Memory-bound NHWC kernels: pools, per-channel affine + activation, layout conversion.
+// One thread handles one pixel x 4 channels (128-bit fp32 / 64-bit bf16 accesses) when the view
+// is 4-aligned, else one pixel x 1 channel.
+#include "esn_common.cuh"
+
+namespace {
+
+struct PwArgs {
+  const void* x;
+  void* y;
+  int N, Hi, Wi, C, x_cs, x_nchw;
+  int Ho, Wo, y_cs;
+  EpiArgs ep;
+};
+
+enum { OP_MAXPOOL2 = 0, OP_AVGPOOL3S2 = 1, OP_AFFINE = 2 };
+
+template <typename TI, int V>
+__device__ __forceinline__ void load_px(const PwArgs& a, const TI* x, int n, int h, int w, int c, float* v) {
+  if (a.x_nchw) {
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      v[j] = (c + j < a.C) ? ld1<TI>(x + ((size_t)((size_t)n * a.C + c + j) * a.Hi + h) * a.Wi + w) : 0.f;
+  } else {
+    const TI* p = x + ((size_t)((size_t)n * a.Hi + h) * a.Wi + w) * a.x_cs + c;
+    if (V == 4) {
+      const float4 t = ld4<TI>(p);
+      v[0] = t.x;
+      v[1 % V] = t.y;
+      v[2 % V] = t.z;
+      v[3 % V] = t.w;
+    } else {
+      v[0] = ld1<TI>(p);
+    }
+  }
+}
+
+template <typename TI, typename TO, int V, int OP>
+__global__ void __launch_bounds__(256) pw_kernel(const PwArgs a) {
+  const int ncg = (a.C + V - 1) / V;
+  const long long total = (long long)a.N * a.Ho * a.Wo * ncg;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = (int)(idx % ncg);
+  const long long pix = idx / ncg;
+  const int wo = (int)(pix % a.Wo);
+  const int ho = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const int c = cg * V;
+  const TI* __restrict__ x = reinterpret_cast<const TI*>(a.x);
+  float v[V];
+  if (OP == OP_MAXPOOL2) {
+    float t[V];
+    load_px<TI, V>(a, x, n, 2 * ho, 2 * wo, c, v);
+    load_px<TI, V>(a, x, n, 2 * ho, 2 * wo + 1, c, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], t[j]);
+    load_px<TI, V>(a, x, n, 2 * ho + 1, 2 * wo, c, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], t[j]);
+    load_px<TI, V>(a, x, n, 2 * ho + 1, 2 * wo + 1, c, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], t[j]);
+  } else if (OP == OP_AVGPOOL3S2) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = 0.f;
+    for (int r = -1; r <= 1; ++r) {
+      const int hi = 2 * ho + r;
+      if (hi < 0 || hi >= a.Hi) continue;
+      for (int s = -1; s <= 1; ++s) {
+        const int wi = 2 * wo + s;
+        if (wi < 0 || wi >= a.Wi) continue;
+        float t[V];
+        load_px<TI, V>(a, x, n, hi, wi, c, t);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] += t[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] *= (1.f / 9.f);  // count_include_pad=True: always /9
+  } else {
+    load_px<TI, V>(a, x, n, ho, wo, c, v);
+  }
+  const size_t opix = ((size_t)((size_t)n * a.Ho + ho) * a.Wo + wo);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int cc = c + j;
+    if (cc < a.C) {
+      const float sc = a.ep.scale ? __ldg(a.ep.scale + cc) : 1.f;
+      const float sh = a.ep.shift ? __ldg(a.ep.shift + cc) : 0.f;
+      float t = v[j] * sc + sh;
+      if (a.ep.res) {
+        const size_t ri = opix * a.ep.res_cstride + cc;
+        t += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
+                                           : reinterpret_cast<const float*>(a.ep.res)[ri];
+      }
+      const float al = (a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + cc) : 0.f;
+      v[j] = apply_act(t, a.ep.act, al);
+    }
+  }
+  TO* yp = reinterpret_cast<TO*>(a.y) + opix * a.y_cs + c;
+  if (V == 4)
+    st4<TO>(yp, make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]));
+  else
+    st1<TO>(yp, v[0]);
+}
+
+template <int OP>
+int run_pw(const EsnPool* p, void* stream) {
+  if (!p) return ESN_ERR_BAD_ARG;
+  const EsnTensor& x = p->x;
+  const EsnTensor& y = p->y;
+  if (!esn_valid_nhwc(y)) return ESN_ERR_BAD_ARG;
+  const bool nchw = x.layout == ESN_NCHW;
+  if (nchw ? (!x.ptr || x.dtype != ESN_F32) : !esn_valid_nhwc(x)) return ESN_ERR_BAD_ARG;
+  if (x.n != y.n || x.c != y.c) return ESN_ERR_BAD_SHAPE;
+  if (OP == OP_MAXPOOL2 && (y.h != x.h / 2 || y.w != x.w / 2)) return ESN_ERR_BAD_SHAPE;
+  if (OP == OP_AVGPOOL3S2 && (y.h != (x.h - 1) / 2 + 1 || y.w != (x.w - 1) / 2 + 1)) return ESN_ERR_BAD_SHAPE;
+  if (OP == OP_AFFINE && (y.h != x.h || y.w != x.w)) return ESN_ERR_BAD_SHAPE;
+  int rc = esn_check_epilogue(p->ep, y);
+  if (rc) return rc;
+  PwArgs a;
+  a.x = x.ptr;
+  a.y = y.ptr;
+  a.N = x.n;
+  a.Hi = x.h;
+  a.Wi = x.w;
+  a.C = x.c;
+  a.x_cs = nchw ? 0 : x.c_stride;
+  a.x_nchw = nchw;
+  a.Ho = y.h;
+  a.Wo = y.w;
+  a.y_cs = y.c_stride;
+  a.ep = make_epi(p->ep);
+  const size_t ysz = y.dtype == ESN_F32 ? 4 : 2, xsz = x.dtype == ESN_F32 ? 4 : 2;
+  const bool v4 = (y.c % 4 == 0) && (y.c_stride % 4 == 0) && ((uintptr_t)y.ptr % (4 * ysz) == 0) &&
+                  (nchw || ((x.c_stride % 4 == 0) && ((uintptr_t)x.ptr % (4 * xsz) == 0)));
+  const int V = v4 ? 4 : 1;
+  const long long total = (long long)y.n * y.h * y.w * ((y.c + V - 1) / V);
+  const int block = 256, grid = esn_cdiv(total, block);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ESN_PW_LAUNCH(TI, TO)                                    \
+  do {                                                           \
+    if (v4)                                                      \
+      pw_kernel<TI, TO, 4, OP><<<grid, block, 0, st>>>(a);       \
+    else                                                         \
+      pw_kernel<TI, TO, 1, OP><<<grid, block, 0, st>>>(a);       \
+  } while (0)
+  if (x.dtype == ESN_F32 && y.dtype == ESN_F32)
+    ESN_PW_LAUNCH(float, float);
+  else if (x.dtype == ESN_F32 && y.dtype == ESN_BF16)
+    ESN_PW_LAUNCH(float, __nv_bfloat16);
+  else if (x.dtype == ESN_BF16 && y.dtype == ESN_BF16)
+    ESN_PW_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (x.dtype == ESN_BF16 && y.dtype == ESN_F32)
+    ESN_PW_LAUNCH(__nv_bfloat16, float);
+  else
+    return ESN_ERR_BAD_ARG;
+#undef ESN_PW_LAUNCH
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+// ---- NCHW f32/bf16 <-> NHWC f32/bf16 through a 32x32 smem transpose over (C, W) per (n,h)
+template <typename TI, typename TO>
+__global__ void nchw_to_nhwc_kernel(const TI* __restrict__ x, TO* __restrict__ y, int N, int C, int H, int W, int y_cs) {
+  __shared__ float tile[32][33];
+  const int nh = blockIdx.z;
+  const int n = nh / H, h = nh % H;
+  const int c0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, w = w0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && w < W) ? ld1<TI>(x + ((size_t)((size_t)n * C + c) * H + h) * W + w) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int w = w0 + i, c = c0 + threadIdx.x;
+    if (w < W && c < C) st1<TO>(y + ((size_t)((size_t)n * H + h) * W + w) * y_cs + c, tile[threadIdx.x][i]);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, TO* __restrict__ y, int N, int C, int H, int W, int x_cs) {
+  __shared__ float tile[32][33];
+  const int nh = blockIdx.z;
+  const int n = nh / H, h = nh % H;
+  const int c0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int w = w0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && w < W) ? ld1<TI>(x + ((size_t)((size_t)n * H + h) * W + w) * x_cs + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, w = w0 + threadIdx.x;
+    if (w < W && c < C) st1<TO>(y + ((size_t)((size_t)n * C + c) * H + h) * W + w, tile[threadIdx.x][i]);
+  }
+}
+
+}  // namespace
+
+extern "C" int esn_maxpool2x2_affine_act(const EsnPool* p, void* stream) { return run_pw<OP_MAXPOOL2>(p, stream); }
+extern "C" int esn_avgpool3x3s2_affine_act(const EsnPool* p, void* stream) { return run_pw<OP_AVGPOOL3S2>(p, stream); }
+extern "C" int esn_affine_act(const EsnPool* p, void* stream) { return run_pw<OP_AFFINE>(p, stream); }
+
+extern "C" int esn_convert_layout(const EsnTensor* x, const EsnTensor* y, void* stream) {
+  if (!x || !y || !x->ptr || !y->ptr) return ESN_ERR_BAD_ARG;
+  if (x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return ESN_ERR_BAD_SHAPE;
+  if ((x->dtype != ESN_F32 && x->dtype != ESN_BF16) || (y->dtype != ESN_F32 && y->dtype != ESN_BF16))
+    return ESN_ERR_BAD_ARG;
+  const int N = x->n, C = x->c, H = x->h, W = x->w;
+  if ((long long)N * H > 65535LL * 32768) return ESN_ERR_UNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 block(32, 8), grid(esn_cdiv(W, 32), esn_cdiv(C, 32), N * H);
+  if (grid.z > 65535) {  // fold rows: the kernels only need (n,h) as one index
+    return ESN_ERR_UNSUPPORTED;
+  }
+#define ESN_CVT(K, TI, TO, CS) K<TI, TO><<<grid, block, 0, st>>>((const TI*)x->ptr, (TO*)y->ptr, N, C, H, W, CS)
+  if (x->layout == ESN_NCHW && y->layout == ESN_NHWC) {
+    if (x->dtype == ESN_F32 && y->dtype == ESN_F32) ESN_CVT(nchw_to_nhwc_kernel, float, float, y->c_stride);
+    else if (x->dtype == ESN_F32) ESN_CVT(nchw_to_nhwc_kernel, float, __nv_bfloat16, y->c_stride);
+    else if (y->dtype == ESN_F32) ESN_CVT(nchw_to_nhwc_kernel, __nv_bfloat16, float, y->c_stride);
+    else ESN_CVT(nchw_to_nhwc_kernel, __nv_bfloat16, __nv_bfloat16, y->c_stride);
+  } else if (x->layout == ESN_NHWC && y->layout == ESN_NCHW) {
+    if (x->dtype == ESN_F32 && y->dtype == ESN_F32) ESN_CVT(nhwc_to_nchw_kernel, float, float, x->c_stride);
+    else if (x->dtype == ESN_F32) ESN_CVT(nhwc_to_nchw_kernel, float, __nv_bfloat16, x->c_stride);
+    else if (y->dtype == ESN_F32) ESN_CVT(nhwc_to_nchw_kernel, __nv_bfloat16, float, x->c_stride);
+    else ESN_CVT(nhwc_to_nchw_kernel, __nv_bfloat16, __nv_bfloat16, x->c_stride);
+  } else {
+    return ESN_ERR_UNSUPPORTED;
+  }
+#undef ESN_CVT
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}

@@ -1,0 +1,105 @@
+// DABNet depthwise asymmetric pair: both branches, their four BN+PReLU stages, the branch add and
+// bn_relu_2 in ONE pass over the tensor (DABNet.py:73-80).  HBM-bound: 1 read + 1 write of a
+// C x h x w tensor; the 17 neighbour reads per output come from L1/L2.
+//
+// Parameter block prm, fp32 [27][C]:
+//   rows  0-2  dconv3x1 taps      3-5  dconv1x3 taps      (branch 1, dilation 1)
+//   rows  6-8  ddconv3x1 taps     9-11 ddconv1x3 taps     (branch 2, dilation d)
+//   rows 12-14 scale,shift,alpha after dconv3x1   15-17 after dconv1x3
+//   rows 18-20 after ddconv3x1    21-23 after ddconv1x3   24-26 bn_relu_2 (after the add)
+#include "esn_common.cuh"
+
+namespace {
+
+struct DabArgs {
+  const void* x;
+  void* y;
+  const float* prm;
+  int N, H, W, C, x_cs, y_cs, d;
+};
+
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float prelu1(float v, float al) { return v >= 0.f ? v : v * al; }
+__device__ __forceinline__ float4 affine_prelu(float4 v, float4 sc, float4 sh, float4 al) {
+  return make_float4(prelu1(fmaf(v.x, sc.x, sh.x), al.x), prelu1(fmaf(v.y, sc.y, sh.y), al.y),
+                     prelu1(fmaf(v.z, sc.z, sh.z), al.z), prelu1(fmaf(v.w, sc.w, sh.w), al.w));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) dab_dw_pair_kernel(const DabArgs a) {
+  const int ncg = a.C / 4;
+  const long long total = (long long)a.N * a.H * a.W * ncg;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % ncg) * 4;
+  const long long pix = idx / ncg;
+  const int w = (int)(pix % a.W);
+  const int h = (int)((pix / a.W) % a.H);
+  const int n = (int)(pix / ((long long)a.W * a.H));
+  const TI* __restrict__ x = reinterpret_cast<const TI*>(a.x) + (size_t)n * a.H * a.W * a.x_cs + c;
+  auto P = [&](int row) { return __ldg(reinterpret_cast<const float4*>(a.prm + (size_t)row * a.C + c)); };
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // one branch: taps at rows wbase..wbase+2 (3x1) and wbase+3..wbase+5 (1x3), affines at abase..abase+5
+  auto branch = [&](int wbase, int abase, int d) -> float4 {
+    const float4 wa0 = P(wbase), wa1 = P(wbase + 1), wa2 = P(wbase + 2);
+    const float4 sa = P(abase), ba = P(abase + 1), aa = P(abase + 2);
+    float4 acc = zero;
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+      const int ww = w + s * d;
+      if (ww < 0 || ww >= a.W) continue;  // zero padding applies to the intermediate tensor
+      float4 t = zero;
+      if (h - d >= 0) t = f4_fma(ld4<TI>(x + ((size_t)(h - d) * a.W + ww) * a.x_cs), wa0, t);
+      t = f4_fma(ld4<TI>(x + ((size_t)h * a.W + ww) * a.x_cs), wa1, t);
+      if (h + d < a.H) t = f4_fma(ld4<TI>(x + ((size_t)(h + d) * a.W + ww) * a.x_cs), wa2, t);
+      t = affine_prelu(t, sa, ba, aa);
+      acc = f4_fma(t, P(wbase + 4 + s), acc);
+    }
+    return affine_prelu(acc, P(abase + 3), P(abase + 4), P(abase + 5));
+  };
+  const float4 b1 = branch(0, 12, 1);
+  const float4 b2 = branch(6, 18, a.d);
+  const float4 sum = make_float4(b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w);
+  const float4 out = affine_prelu(sum, P(24), P(25), P(26));
+  st4<TO>(reinterpret_cast<TO*>(a.y) + (size_t)pix * a.y_cs + c, out);
+}
+
+}  // namespace
+
+extern "C" int esn_dab_dw_pair(const EsnDabPair* p, void* stream) {
+  if (!p || !p->prm || !esn_valid_nhwc(p->x) || !esn_valid_nhwc(p->y)) return ESN_ERR_BAD_ARG;
+  const EsnTensor& x = p->x;
+  const EsnTensor& y = p->y;
+  if (x.n != y.n || x.h != y.h || x.w != y.w || x.c != y.c) return ESN_ERR_BAD_SHAPE;
+  if (p->dilation < 1) return ESN_ERR_BAD_ARG;
+  if (x.c % 4 || x.c_stride % 4 || y.c_stride % 4) return ESN_ERR_UNSUPPORTED;
+  const size_t xsz = x.dtype == ESN_F32 ? 4 : 2, ysz = y.dtype == ESN_F32 ? 4 : 2;
+  if (((uintptr_t)x.ptr % (4 * xsz)) || ((uintptr_t)y.ptr % (4 * ysz)) || ((uintptr_t)p->prm % 16)) return ESN_ERR_ALIGN;
+  DabArgs a;
+  a.x = x.ptr;
+  a.y = y.ptr;
+  a.prm = p->prm;
+  a.N = x.n;
+  a.H = x.h;
+  a.W = x.w;
+  a.C = x.c;
+  a.x_cs = x.c_stride;
+  a.y_cs = y.c_stride;
+  a.d = p->dilation;
+  const long long total = (long long)x.n * x.h * x.w * (x.c / 4);
+  const int block = 256, grid = esn_cdiv(total, block);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x.dtype == ESN_F32 && y.dtype == ESN_F32)
+    dab_dw_pair_kernel<float, float><<<grid, block, 0, st>>>(a);
+  else if (x.dtype == ESN_BF16 && y.dtype == ESN_BF16)
+    dab_dw_pair_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(a);
+  else if (x.dtype == ESN_F32)
+    dab_dw_pair_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(a);
+  else
+    dab_dw_pair_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}

@@ -1,0 +1,98 @@
+"""ctypes binding of libesn_sm100.so (C ABI: include/esn.h).
+
+The library is the product: if it is missing this module raises at import
+time -- there is no CPU or eager-PyTorch fallback behind it.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libesn_sm100.so")
+
+ESN_F32, ESN_BF16, ESN_U8, ESN_I64, ESN_I32 = 0, 1, 2, 3, 4
+ESN_NHWC, ESN_NCHW = 0, 1
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+ERR_UNSUPPORTED = -3
+
+
+class EsnTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("layout", C.c_int32),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("c_stride", C.c_int32), ("_pad", C.c_int32)]
+
+
+class EsnEpilogue(C.Structure):
+    _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("alpha", C.c_void_p),
+                ("act", C.c_int32), ("_pad", C.c_int32), ("residual", EsnTensor)]
+
+
+class EsnConv(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("w", C.c_void_p),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32),
+                ("pad_h", C.c_int32), ("pad_w", C.c_int32), ("dil_h", C.c_int32), ("dil_w", C.c_int32),
+                ("groups", C.c_int32), ("transposed", C.c_int32), ("cout_pad", C.c_int32),
+                ("ep", EsnEpilogue)]
+
+
+class EsnPool(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("ep", EsnEpilogue)]
+
+
+class EsnDabPair(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("prm", C.c_void_p),
+                ("dilation", C.c_int32), ("_pad", C.c_int32)]
+
+
+class EsnHead(C.Structure):
+    _fields_ = [("x", EsnTensor), ("w", C.c_void_p), ("bias", C.c_void_p), ("logits", EsnTensor),
+                ("mask", C.c_void_p), ("classes", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class EsnCE(C.Structure):
+    _fields_ = [("logits", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
+                ("dlogits", EsnTensor), ("ignore_label", C.c_int32), ("_pad", C.c_int32)]
+
+
+# every symbol include/esn.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "esn_conv2d_direct": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_conv2d_umma": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_maxpool2x2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
+    "esn_avgpool3x3s2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
+    "esn_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
+    "esn_convert_layout": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
+    "esn_dab_dw_pair": (C.c_int, [C.POINTER(EsnDabPair), C.c_void_p]),
+    "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
+    "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
+    "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
+    "esn_version": (C.c_int, []),
+    "esn_strerror": (C.c_char_p, [C.c_int]),
+    "esn_launch_count": (C.c_int64, []),
+    "esn_launch_count_reset": (None, []),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libesn_sm100.so not found at %s -- build it with `python __graft_entry__.py build` "
+            "(or `make -C efficient-segmentation-networks_b200/csrc`). There is no fallback path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class EsnError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise EsnError("%s failed: %s (code %d)" % (what, lib.esn_strerror(rc).decode(), rc))

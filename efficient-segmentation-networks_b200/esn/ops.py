@@ -1,0 +1,289 @@
+"""Host-side wrappers: torch tensors in, C-ABI calls out (no torch compute on the path).
+
+Internal activations are torch tensors of logical shape (N,C,H,W) whose memory
+is NHWC ("channels_last"), possibly a channel slice of a wider concat buffer.
+PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.ESN_F32, torch.bfloat16: L.ESN_BF16, torch.uint8: L.ESN_U8, torch.int64: L.ESN_I64}
+_NULL = L.EsnTensor()
+UMMA_ENABLED = os.environ.get("ESN_DISABLE_UMMA", "0") != "1"
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("%s: tensors must live on a CUDA device; this framework has no CPU path" % what)
+
+
+def is_nhwc(t):
+    if t.dim() != 4:
+        return False
+    n, c, h, w = t.shape
+    s = t.stride()
+    return s[1] == 1 and s[3] >= c and s[2] == w * s[3] and s[0] == h * s[2] and (c > 1 or s[3] == 1)
+
+
+def tdesc(t):
+    """EsnTensor view of a 4-D torch tensor (NHWC-strided or NCHW-contiguous)."""
+    n, c, h, w = t.shape
+    d = L.EsnTensor()
+    d.ptr = t.data_ptr()
+    d.dtype = _DT[t.dtype]
+    d.n, d.c, d.h, d.w = n, c, h, w
+    if is_nhwc(t):
+        d.layout, d.c_stride = L.ESN_NHWC, t.stride(3)
+    elif t.is_contiguous():
+        d.layout, d.c_stride = L.ESN_NCHW, 0
+    else:
+        raise RuntimeError("tensor is neither NHWC-strided nor NCHW-contiguous: shape %s stride %s" % (tuple(t.shape), t.stride()))
+    return d
+
+
+def new_act(n, c, h, w, dtype, device, c_alloc=None):
+    """Fresh NHWC activation with logical shape (N,C,H,W); c_alloc pads the pixel stride."""
+    ca = c if c_alloc is None else c_alloc
+    buf = torch.empty((n, h, w, ca), dtype=dtype, device=device)
+    t = buf.permute(0, 3, 1, 2)
+    return t if ca == c else t[:, :c]
+
+
+def compute_dtype(x):
+    """fp32 unless bf16 autocast is active, ESN_COMPUTE=bf16, or the activations already are bf16."""
+    if x.dtype == torch.bfloat16:
+        return torch.bfloat16
+    if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+        return torch.bfloat16
+    if os.environ.get("ESN_COMPUTE", "").lower() == "bf16":
+        return torch.bfloat16
+    return torch.float32
+
+
+def as_act(x, dtype=None):
+    """Accept the caller's NCHW tensor or an internal NHWC one; return NHWC in `dtype`."""
+    require_cuda(x, "forward")
+    dtype = dtype or compute_dtype(x)
+    if is_nhwc(x) and x.dtype == dtype:
+        return x
+    if not x.is_contiguous() and not is_nhwc(x):
+        x = x.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    n, c, h, w = x.shape
+    y = new_act(n, c, h, w, dtype, x.device, c_alloc=(c + 7) // 8 * 8 if c % 8 else None)
+    dx, dy = tdesc(x), tdesc(y)
+    if dx.layout == L.ESN_NHWC:  # NHWC but other dtype: elementwise copy through the affine kernel
+        return affine_act(x, None, None, None, L.ACT_NONE, out=y)
+    L.check(L.lib.esn_convert_layout(C.byref(dx), C.byref(dy), stream()), "esn_convert_layout")
+    return y
+
+
+def to_nchw(x, dtype=None):
+    """NHWC internal activation -> NCHW-contiguous tensor (what the reference returns)."""
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, h, w), dtype=dtype or x.dtype, device=x.device)
+    dx, dy = tdesc(x), tdesc(y)
+    if dx.layout == L.ESN_NCHW:
+        return x if dtype in (None, x.dtype) else x.to(dtype)
+    L.check(L.lib.esn_convert_layout(C.byref(dx), C.byref(dy), stream()), "esn_convert_layout")
+    return y
+
+
+# --------------------------------------------------------------------------- prepared (packed) parameters
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def bn_affine(bn, device):
+    """Eval-mode BatchNorm2d as y = x*scale + shift (reads bn.eps: SURVEY H11)."""
+    w, b = _f32(bn.weight, device), _f32(bn.bias, device)
+    m, v = _f32(bn.running_mean, device), _f32(bn.running_var, device)
+    scale = w / torch.sqrt(v + bn.eps)
+    return scale, b - m * scale
+
+
+class ConvPrep:
+    """Packed weights + folded epilogue of one conv (+BN slice) (+activation)."""
+
+    def __init__(self, conv, scale=None, shift=None, act=L.ACT_NONE, alpha=None, device=None):
+        device = device or conv.weight.device
+        transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+        w = _f32(conv.weight, device)
+        if transposed:          # (Cin, Cout, kh, kw) -> (Cout, Cin, kh, kw)
+            w = w.permute(1, 0, 2, 3).contiguous()
+        self.cout, cin_g, self.kh, self.kw = w.shape
+        self.groups = conv.groups
+        self.cin = cin_g * conv.groups
+        if self.groups != 1 and not (self.groups == self.cin == self.cout):
+            raise NotImplementedError("only dense and depthwise convs are supported, got groups=%d" % self.groups)
+        self.transposed = int(transposed)
+        self.stride = conv.stride[0]
+        self.pad_h, self.pad_w = conv.padding
+        self.dil_h, self.dil_w = conv.dilation
+        self.out_pad = conv.output_padding[0] if transposed else 0
+        taps = self.kh * self.kw
+        # direct layout: [tap][Cin/groups][Cout]
+        self.w_direct = w.permute(2, 3, 1, 0).reshape(taps, cin_g, self.cout).contiguous()
+        self._w_umma = None
+        self._w_src = w
+        self.cout_pad = (self.cout + 15) // 16 * 16
+        sc = torch.ones(self.cout, device=device) if scale is None else scale.clone()
+        sh = torch.zeros(self.cout, device=device) if shift is None else shift.clone()
+        if conv.bias is not None:
+            sh = sh + _f32(conv.bias, device) * sc
+        self.scale, self.shift = sc.contiguous(), sh.contiguous()
+        self.act = act
+        self.alpha = None if alpha is None else _f32(alpha, device)
+
+    @property
+    def w_umma(self):
+        if self._w_umma is None:     # bf16 [tap][Cout_pad][Cin]
+            w = self._w_src
+            taps = self.kh * self.kw
+            p = torch.zeros((taps, self.cout_pad, self.cin), dtype=torch.bfloat16, device=w.device)
+            p[:, :self.cout] = w.permute(2, 3, 0, 1).reshape(taps, self.cout, self.cin).to(torch.bfloat16)
+            self._w_umma = p.contiguous()
+        return self._w_umma
+
+    def out_hw(self, h, w):
+        if self.transposed:
+            return ((h - 1) * self.stride - 2 * self.pad_h + self.dil_h * (self.kh - 1) + self.out_pad + 1,
+                    (w - 1) * self.stride - 2 * self.pad_w + self.dil_w * (self.kw - 1) + self.out_pad + 1)
+        return ((h + 2 * self.pad_h - self.dil_h * (self.kh - 1) - 1) // self.stride + 1,
+                (w + 2 * self.pad_w - self.dil_w * (self.kw - 1) - 1) // self.stride + 1)
+
+
+def _epilogue(ep, scale, shift, alpha, act, residual):
+    ep.scale = scale.data_ptr() if scale is not None else None
+    ep.shift = shift.data_ptr() if shift is not None else None
+    ep.alpha = alpha.data_ptr() if alpha is not None else None
+    ep.act = act
+    ep.residual = tdesc(residual) if residual is not None else _NULL
+
+
+def conv2d(x, prep, out=None, residual=None, force_direct=False):
+    """y = act(conv(x)*scale + shift (+ residual)); routes to tcgen05 when the shape allows."""
+    n, c, h, w = x.shape
+    assert c == prep.cin, (c, prep.cin)
+    ho, wo = prep.out_hw(h, w)
+    if out is None:
+        odt = x.dtype if x.dtype == torch.bfloat16 else torch.float32
+        out = new_act(n, prep.cout, ho, wo, odt, x.device)
+    p = L.EsnConv()
+    p.x, p.y = tdesc(x), tdesc(out)
+    p.kh, p.kw, p.stride = prep.kh, prep.kw, prep.stride
+    p.pad_h, p.pad_w, p.dil_h, p.dil_w = prep.pad_h, prep.pad_w, prep.dil_h, prep.dil_w
+    p.groups, p.transposed, p.cout_pad = prep.groups, prep.transposed, prep.cout_pad
+    _epilogue(p.ep, prep.scale, prep.shift, prep.alpha, prep.act, residual)
+    if (UMMA_ENABLED and not force_direct and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+            and prep.groups == 1 and p.x.layout == L.ESN_NHWC):
+        p.w = prep.w_umma.data_ptr()
+        rc = L.lib.esn_conv2d_umma(C.byref(p), stream())
+        if rc == 0:
+            return out
+        if rc != L.ERR_UNSUPPORTED and rc != -5:
+            L.check(rc, "esn_conv2d_umma")
+    p.w = prep.w_direct.data_ptr()
+    L.check(L.lib.esn_conv2d_direct(C.byref(p), stream()), "esn_conv2d_direct")
+    return out
+
+
+def _pool_call(fn, name, x, out, scale, shift, alpha, act, residual=None):
+    p = L.EsnPool()
+    p.x, p.y = tdesc(x), tdesc(out)
+    _epilogue(p.ep, scale, shift, alpha, act, residual)
+    L.check(fn(C.byref(p), stream()), name)
+    return out
+
+
+def maxpool2x2(x, out, scale=None, shift=None, alpha=None, act=L.ACT_NONE):
+    return _pool_call(L.lib.esn_maxpool2x2_affine_act, "esn_maxpool2x2_affine_act", x, out, scale, shift, alpha, act)
+
+
+def avgpool3x3s2(x, out, scale=None, shift=None, alpha=None, act=L.ACT_NONE):
+    return _pool_call(L.lib.esn_avgpool3x3s2_affine_act, "esn_avgpool3x3s2_affine_act", x, out, scale, shift, alpha, act)
+
+
+def affine_act(x, scale, shift, alpha, act, out=None, residual=None):
+    if out is None:
+        n, c, h, w = x.shape
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    return _pool_call(L.lib.esn_affine_act, "esn_affine_act", x, out, scale, shift, alpha, act, residual)
+
+
+def dab_dw_pair(x, prm, dilation, out=None):
+    if out is None:
+        n, c, h, w = x.shape
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    p = L.EsnDabPair()
+    p.x, p.y, p.prm, p.dilation = tdesc(x), tdesc(out), prm.data_ptr(), dilation
+    L.check(L.lib.esn_dab_dw_pair(C.byref(p), stream()), "esn_dab_dw_pair")
+    return out
+
+
+def _head(fn, name, x, w, bias, classes, out_h, out_w, want_logits, want_mask, logits_dtype):
+    n = x.shape[0]
+    p = L.EsnHead()
+    p.x = tdesc(x)
+    p.w = w.data_ptr() if w is not None else None
+    p.bias = bias.data_ptr() if bias is not None else None
+    logits = mask = None
+    if want_logits:
+        logits = torch.empty((n, classes, out_h, out_w), dtype=logits_dtype, device=x.device)
+        p.logits = tdesc(logits)
+        p.logits.layout, p.logits.c_stride = L.ESN_NCHW, 0
+    if want_mask:
+        mask = torch.empty((n, out_h, out_w), dtype=torch.uint8, device=x.device)
+        p.mask = mask.data_ptr()
+    p.classes, p.out_h, p.out_w = classes, out_h, out_w
+    L.check(fn(C.byref(p), stream()), name)
+    return logits, mask
+
+
+def head_convt2x2(x, w, bias, classes, want_logits=True, want_mask=False, logits_dtype=torch.float32):
+    return _head(L.lib.esn_head_convt2x2, "esn_head_convt2x2", x, w, bias, classes, 2 * x.shape[2], 2 * x.shape[3],
+                 want_logits, want_mask, logits_dtype)
+
+
+def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, logits_dtype=torch.float32):
+    return _head(L.lib.esn_head_bilinear, "esn_head_bilinear", x, None, None, classes, out_h, out_w,
+                 want_logits, want_mask, logits_dtype)
+
+
+def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False):
+    """Returns (sums[2] = [sum w*nll, sum w], unnormalised dlogits or None)."""
+    require_cuda(logits, "weighted_ce")
+    logits = logits.contiguous()
+    target = target.contiguous()
+    sums = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    p = L.EsnCE()
+    p.logits = tdesc(logits)
+    p.logits.layout, p.logits.c_stride = L.ESN_NCHW, 0
+    p.target = target.data_ptr()
+    p.weight = weight.data_ptr() if weight is not None else None
+    p.sums = sums.data_ptr()
+    g = None
+    if want_grad:
+        g = torch.empty_like(logits)
+        p.dlogits = tdesc(g)
+        p.dlogits.layout, p.dlogits.c_stride = L.ESN_NCHW, 0
+    p.ignore_label = ignore_label
+    L.check(L.lib.esn_weighted_ce(C.byref(p), stream()), "esn_weighted_ce")
+    return sums, g
+
+
+def launch_count():
+    return int(L.lib.esn_launch_count())
+
+
+def launch_count_reset():
+    L.lib.esn_launch_count_reset()

@@ -1,0 +1,255 @@
+"""DABNet on B200 kernels -- drop-in for the reference's model/DABNet.py.
+
+Same class names, constructor signatures and attribute names (identical
+``state_dict`` keys) as /root/reference/model/DABNet.py:16-183.  Launch plan:
+
+* Conv (+BNPReLU) (DABNet.py:16-35): one conv launch, BN + PReLU in the epilogue
+* DABModule (DABNet.py:51-83): 4 launches instead of 22 ATen kernels --
+  bn_relu_1 (affine+PReLU), conv3x3+BNPReLU (tcgen05), the fused depthwise
+  asymmetric pair kernel (both branches, 4 BNPReLUs, add, bn_relu_2), and
+  conv1x1 + residual (tcgen05)
+* DownSamplingBlock (DABNet.py:86-110): conv and max-pool branches write their
+  channel slices of the output with the BNPReLU slice folded in
+* concats (DABNet.py:166,171,176) are never materialised by a copy: producers
+  write into channel slices of one pre-allocated NHWC buffer, BNPReLU runs in place
+* classifier + F.interpolate (DABNet.py:179-181): 1x1 conv at 1/8 resolution and
+  one fused bilinear kernel that writes NCHW logits and/or the argmax mask.
+"""
+import torch
+import torch.nn as nn
+
+from esn import ops
+from esn._lib import ACT_NONE, ACT_PRELU
+from esn.prep import PrepMixin
+
+__all__ = ["DABNet"]
+
+
+def _no_train(mod):
+    if mod.training:
+        raise NotImplementedError(
+            "%s: training-mode kernels (batch-stat BN, backward) are not built yet for this model; "
+            "call .eval(). There is no eager-PyTorch fallback." % type(mod).__name__)
+
+
+def _bnprelu_affine(bnp, device):
+    scale, shift = ops.bn_affine(bnp.bn, device)
+    alpha = bnp.acti.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+    return scale.contiguous(), shift.contiguous(), alpha
+
+
+class Conv(PrepMixin, nn.Module):
+    def __init__(self, nIn, nOut, kSize, stride, padding, dilation=(1, 1), groups=1, bn_acti=False, bias=False):
+        super().__init__()
+        self.bn_acti = bn_acti
+        self.conv = nn.Conv2d(nIn, nOut, kernel_size=kSize, stride=stride, padding=padding,
+                              dilation=dilation, groups=groups, bias=bias)
+        if self.bn_acti:
+            self.bn_prelu = BNPReLU(nOut)
+
+    def _build_prep(self, device):
+        if self.bn_acti:
+            s, b, a = _bnprelu_affine(self.bn_prelu, device)
+            return ops.ConvPrep(self.conv, s, b, ACT_PRELU, a, device=device)
+        return ops.ConvPrep(self.conv, device=device)
+
+    def forward(self, input, out=None, residual=None):
+        _no_train(self)
+        n_in = input.shape[1]
+        x = input if (n_in < 8 and input.is_contiguous() and input.dtype == torch.float32
+                      and not ops.is_nhwc(input)) else ops.as_act(input)
+        prep = self.prep(x.device)
+        if out is None and x.dtype == torch.float32 and ops.compute_dtype(x) == torch.bfloat16:
+            n, c, h, w = x.shape
+            ho, wo = prep.out_hw(h, w)
+            out = ops.new_act(n, prep.cout, ho, wo, torch.bfloat16, x.device)
+        return ops.conv2d(x, prep, out=out, residual=residual)
+
+
+class BNPReLU(PrepMixin, nn.Module):
+    def __init__(self, nIn):
+        super().__init__()
+        self.bn = nn.BatchNorm2d(nIn, eps=1e-3)
+        self.acti = nn.PReLU(nIn)
+
+    def _build_prep(self, device):
+        return _bnprelu_affine(self, device)
+
+    def forward(self, input, out=None):
+        _no_train(self)
+        x = ops.as_act(input)
+        s, b, a = self.prep(x.device)
+        return ops.affine_act(x, s, b, a, ACT_PRELU, out=out)
+
+
+class DABModule(PrepMixin, nn.Module):
+    def __init__(self, nIn, d=1, kSize=3, dkSize=3):
+        super().__init__()
+        self.bn_relu_1 = BNPReLU(nIn)
+        self.conv3x3 = Conv(nIn, nIn // 2, kSize, 1, padding=1, bn_acti=True)
+        self.dconv3x1 = Conv(nIn // 2, nIn // 2, (dkSize, 1), 1, padding=(1, 0), groups=nIn // 2, bn_acti=True)
+        self.dconv1x3 = Conv(nIn // 2, nIn // 2, (1, dkSize), 1, padding=(0, 1), groups=nIn // 2, bn_acti=True)
+        self.ddconv3x1 = Conv(nIn // 2, nIn // 2, (dkSize, 1), 1, padding=(1 * d, 0), dilation=(d, 1),
+                              groups=nIn // 2, bn_acti=True)
+        self.ddconv1x3 = Conv(nIn // 2, nIn // 2, (1, dkSize), 1, padding=(0, 1 * d), dilation=(1, d),
+                              groups=nIn // 2, bn_acti=True)
+        self.bn_relu_2 = BNPReLU(nIn // 2)
+        self.conv1x1 = Conv(nIn // 2, nIn, 1, 1, padding=0, bn_acti=False)
+        self._d = d
+        self._dk = dkSize
+
+    def _build_prep(self, device):
+        """[27][C] parameter block of esn_dab_dw_pair (layout: csrc/esn_stencil.cu)."""
+        if self._dk != 3:
+            raise NotImplementedError("fused depthwise pair kernel is built for dkSize=3")
+        rows = []
+        for m in (self.dconv3x1, self.dconv1x3, self.ddconv3x1, self.ddconv1x3):
+            w = m.conv.weight.detach().to(device=device, dtype=torch.float32)  # (C,1,3,1) or (C,1,1,3)
+            rows.append(w.reshape(w.shape[0], 3).t())
+        for m in (self.dconv3x1, self.dconv1x3, self.ddconv3x1, self.ddconv1x3):
+            rows.append(torch.stack(_bnprelu_affine(m.bn_prelu, device)))
+        rows.append(torch.stack(_bnprelu_affine(self.bn_relu_2, device)))
+        return torch.cat(rows, 0).contiguous()
+
+    def forward(self, input, out=None):
+        _no_train(self)
+        x = ops.as_act(input)
+        prm = self.prep(x.device)
+        y = self.bn_relu_1(x)
+        y = self.conv3x3(y)
+        y = ops.dab_dw_pair(y, prm, self._d)
+        return self.conv1x1(y, out=out, residual=x)     # output + input
+
+
+class DownSamplingBlock(PrepMixin, nn.Module):
+    def __init__(self, nIn, nOut):
+        super().__init__()
+        self.nIn = nIn
+        self.nOut = nOut
+        if self.nIn < self.nOut:
+            nConv = nOut - nIn
+        else:
+            nConv = nOut
+        self.conv3x3 = Conv(nIn, nConv, kSize=3, stride=2, padding=1)
+        self.max_pool = nn.MaxPool2d(2, stride=2)
+        self.bn_prelu = BNPReLU(nOut)
+
+    def _build_prep(self, device):
+        s, b, a = _bnprelu_affine(self.bn_prelu, device)
+        nc = self.conv3x3.conv.out_channels
+        conv = ops.ConvPrep(self.conv3x3.conv, s[:nc], b[:nc], ACT_PRELU, a[:nc], device=device)
+        return conv, s[nc:].contiguous(), b[nc:].contiguous(), a[nc:].contiguous()
+
+    def forward(self, input, out=None):
+        _no_train(self)
+        x = ops.as_act(input)
+        conv, ps, pb, pa = self.prep(x.device)
+        n, c, h, w = x.shape
+        if out is None:
+            out = ops.new_act(n, self.nOut, h // 2, w // 2, x.dtype, x.device)
+        nc = conv.cout
+        ops.conv2d(x, conv, out=out[:, :nc])
+        if self.nIn < self.nOut:
+            ops.maxpool2x2(x, out[:, nc:], ps, pb, pa, ACT_PRELU)
+        return out
+
+
+class InputInjection(nn.Module):
+    def __init__(self, ratio):
+        super().__init__()
+        self.pool = nn.ModuleList()
+        for i in range(0, ratio):
+            self.pool.append(nn.AvgPool2d(3, stride=2, padding=1))
+
+    def forward(self, input):
+        ops.require_cuda(input, "InputInjection")
+        x = input
+        for _ in self.pool:
+            n, c, h, w = x.shape
+            y = ops.new_act(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, torch.float32, x.device, c_alloc=4)
+            x = ops.avgpool3x3s2(x if (ops.is_nhwc(x) or x.is_contiguous()) else x.contiguous(), y)
+        return x
+
+
+class DABNet(nn.Module):
+    def __init__(self, classes=19, block_1=3, block_2=6):
+        super().__init__()
+        self.init_conv = nn.Sequential(
+            Conv(3, 32, 3, 2, padding=1, bn_acti=True),
+            Conv(32, 32, 3, 1, padding=1, bn_acti=True),
+            Conv(32, 32, 3, 1, padding=1, bn_acti=True),
+        )
+        self.down_1 = InputInjection(1)
+        self.down_2 = InputInjection(2)
+        self.down_3 = InputInjection(3)
+        self.bn_prelu_1 = BNPReLU(32 + 3)
+        self.downsample_1 = DownSamplingBlock(32 + 3, 64)
+        self.DAB_Block_1 = nn.Sequential()
+        for i in range(0, block_1):
+            self.DAB_Block_1.add_module("DAB_Module_1_" + str(i), DABModule(64, d=2))
+        self.bn_prelu_2 = BNPReLU(128 + 3)
+        dilation_block_2 = [4, 4, 8, 8, 16, 16]
+        self.downsample_2 = DownSamplingBlock(128 + 3, 128)
+        self.DAB_Block_2 = nn.Sequential()
+        for i in range(0, block_2):
+            self.DAB_Block_2.add_module("DAB_Module_2_" + str(i), DABModule(128, d=dilation_block_2[i]))
+        self.bn_prelu_3 = BNPReLU(256 + 3)
+        self.classifier = nn.Sequential(Conv(259, classes, 1, 1, padding=0))
+
+    def _scores(self, input):
+        """Everything up to the 1/8-resolution class scores (NHWC fp32)."""
+        ops.require_cuda(input, "DABNet")
+        if input.dtype != torch.float32 or not input.is_contiguous():
+            input = input.float().contiguous()
+        dt = ops.compute_dtype(input)
+        dev = input.device
+        n, _, h, w = input.shape
+
+        # input-injection pyramid, computed once (the reference recomputes it 3x: DABNet.py:160-165)
+        d1 = self.down_1(input)
+        d2 = self.down_1(d1)
+        d3 = self.down_1(d2)
+
+        h1, w1 = d1.shape[2:]
+        cat0 = ops.new_act(n, 35, h1, w1, dt, dev, c_alloc=40)
+        y = self.init_conv[0](input)
+        y = self.init_conv[1](y)
+        self.init_conv[2](y, out=cat0[:, :32])
+        ops.affine_act(d1, None, None, None, ACT_NONE, out=cat0[:, 32:35])
+        self.bn_prelu_1(cat0, out=cat0)
+
+        h2, w2 = d2.shape[2:]
+        cat1 = ops.new_act(n, 131, h2, w2, dt, dev, c_alloc=136)
+        y = self.downsample_1(cat0, out=cat1[:, 64:128])
+        blocks = list(self.DAB_Block_1)
+        for i, blk in enumerate(blocks):
+            y = blk(y, out=cat1[:, 0:64] if i == len(blocks) - 1 else None)
+        ops.affine_act(d2, None, None, None, ACT_NONE, out=cat1[:, 128:131])
+        self.bn_prelu_2(cat1, out=cat1)
+
+        h3, w3 = d3.shape[2:]
+        cat2 = ops.new_act(n, 259, h3, w3, dt, dev, c_alloc=264)
+        y = self.downsample_2(cat1, out=cat2[:, 128:256])
+        blocks = list(self.DAB_Block_2)
+        for i, blk in enumerate(blocks):
+            y = blk(y, out=cat2[:, 0:128] if i == len(blocks) - 1 else None)
+        ops.affine_act(d3, None, None, None, ACT_NONE, out=cat2[:, 256:259])
+        self.bn_prelu_3(cat2, out=cat2)
+
+        classes = self.classifier[0].conv.out_channels
+        scores = ops.new_act(n, classes, h3, w3, torch.float32, dev, c_alloc=32)
+        self.classifier[0](cat2, out=scores)
+        return scores, (h, w), dt
+
+    def forward(self, input):
+        scores, (h, w), dt = self._scores(input)
+        ldt = torch.bfloat16 if dt == torch.bfloat16 else torch.float32
+        return ops.head_bilinear(scores, scores.shape[1], h, w, True, False, ldt)[0]
+
+    @torch.no_grad()
+    def predict_mask(self, input, with_logits=False):
+        """uint8 (N,H,W) argmax mask computed inside the upsampling kernel (test.py:79-82 on GPU)."""
+        scores, (h, w), dt = self._scores(input)
+        ldt = torch.bfloat16 if dt == torch.bfloat16 else torch.float32
+        logits, mask = ops.head_bilinear(scores, scores.shape[1], h, w, with_logits, True, ldt)
+        return (logits, mask) if with_logits else mask

@@ -1,0 +1,191 @@
+/*
+ * esn.h -- C ABI of libesn_sm100.so: B200 (sm_100a) kernels for the
+ * convolutional encoder-decoder hot path of the lightweight segmentation zoo.
+ *
+ * The reference (Ethan-ye/Efficient-Segmentation-Networks) has no FFI boundary
+ * of its own: every op on the path is an ATen call made from the nn.Module
+ * forwards under model/ (SURVEY.md section 8b).  Each entry point below therefore
+ * cites the reference nn.Module lines whose ATen calls it replaces.  The host
+ * side (efficient-segmentation-networks_b200/esn/_lib.py) binds these with
+ * ctypes; INTEGRATION.md shows the binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    the name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *  - no allocation, no synchronisation, no exceptions across the ABI.
+ *  - return 0 on success, a negative ESN_ERR_* otherwise (esn_strerror()).
+ *  - activations are NHWC ("channels last"): element (n,h,w,c) of a tensor
+ *    view lives at ptr[((n*H + h)*W + w)*c_stride + c]; c_stride >= c lets a
+ *    kernel read or write a channel slice of a wider concat buffer.  The only
+ *    NCHW tensors are the network input (fp32, as the reference's Dataset
+ *    yields it, dataset/cityscapes.py:58-106) and the logits returned to the
+ *    caller (N,classes,H,W), as `model(images)` returns them (train.py:351).
+ */
+#ifndef ESN_H_
+#define ESN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESN_VERSION 100
+
+enum {
+  ESN_OK = 0,
+  ESN_ERR_BAD_ARG = -1,      /* null pointer, bad dtype/layout combination      */
+  ESN_ERR_BAD_SHAPE = -2,    /* shapes inconsistent with the op                 */
+  ESN_ERR_UNSUPPORTED = -3,  /* valid op, but this kernel family cannot run it  */
+  ESN_ERR_CUDA = -4,         /* a CUDA runtime/driver call failed               */
+  ESN_ERR_ALIGN = -5         /* pointer / stride alignment requirement not met  */
+};
+
+enum { ESN_F32 = 0, ESN_BF16 = 1, ESN_U8 = 2, ESN_I64 = 3, ESN_I32 = 4 };
+enum { ESN_NHWC = 0, ESN_NCHW = 1 };
+enum { ESN_ACT_NONE = 0, ESN_ACT_RELU = 1, ESN_ACT_PRELU = 2 };
+
+/* A 4-D activation view. */
+typedef struct EsnTensor {
+  void* ptr;        /* device pointer to element (0,0,0,0) of the view */
+  int32_t dtype;    /* ESN_F32 / ESN_BF16 / ...                          */
+  int32_t layout;   /* ESN_NHWC (c_stride used) or ESN_NCHW (contiguous) */
+  int32_t n, h, w, c;
+  int32_t c_stride; /* NHWC only: elements between consecutive pixels    */
+  int32_t _pad;
+} EsnTensor;
+
+/* Fused epilogue shared by the conv kernels:
+ *   v = acc * scale[c] + shift[c]        (conv bias and eval-mode BN folded here)
+ *   v += residual[n,h,w,c]               (optional)
+ *   v = act(v)                           (none / ReLU / per-channel PReLU)
+ */
+typedef struct EsnEpilogue {
+  const float* scale;  /* [Cout] or NULL (=1) */
+  const float* shift;  /* [Cout] or NULL (=0) */
+  const float* alpha;  /* [Cout] PReLU slopes, used when act == ESN_ACT_PRELU */
+  int32_t act;
+  int32_t _pad;
+  EsnTensor residual;  /* ptr == NULL: none; else same N,H,W,C as the output */
+} EsnEpilogue;
+
+/* 2-D convolution / transposed convolution, NHWC, stride/dilation/groups as
+ * torch.nn.Conv2d / ConvTranspose2d (cross-correlation, zero padding).
+ * Replaces the aten::convolution (+ native_batch_norm eval + relu/prelu + add)
+ * sequences of:
+ *   ERFNet.py:24-27,49-65,109-112,128,136   (DownsamplerBlock conv, non_bottleneck_1d,
+ *                                            UpsamplerBlock, output_conv)
+ *   DABNet.py:27-35,69-83,101-110,132-136,158,179  (Conv, DABModule, DownSamplingBlock, stem, classifier)
+ * Weight packing (done once by the host at plan-build time):
+ *   direct kernels : fp32 [kh*kw][Cin/groups][Cout]      (Cout contiguous)
+ *   umma kernels   : bf16 [kh*kw][Cout_pad][Cin]         (Cin contiguous, K-major B operand)
+ * For transposed convs the packed tap (kh,kw) holds W[ci][co][kh][kw].
+ */
+typedef struct EsnConv {
+  EsnTensor x;   /* input  view (NHWC f32/bf16, or NCHW f32 for the network input) */
+  EsnTensor y;   /* output view (NHWC f32/bf16)                                    */
+  const void* w; /* packed weights, see above                                      */
+  int32_t kh, kw;
+  int32_t stride;
+  int32_t pad_h, pad_w;
+  int32_t dil_h, dil_w;
+  int32_t groups;      /* 1 or Cin (depthwise) */
+  int32_t transposed;  /* 0 / 1 (ConvTranspose2d; output_padding implied by y.h/y.w) */
+  int32_t cout_pad;    /* umma only: padded Cout rows per tap in w                    */
+  EsnEpilogue ep;
+} EsnConv;
+
+/* CUDA-core direct convolution (fp32 accumulate; f32 or bf16 activations).
+ * The exact-arithmetic path (fp32 parity) and the path for shapes the tensor
+ * core kernel does not take (Cin = 3 stem, depthwise). */
+int esn_conv2d_direct(const EsnConv* p, void* stream);
+
+/* tcgen05 implicit-GEMM convolution: bf16 operands staged by TMA, fp32
+ * accumulators in TMEM, fused epilogue.  Requires bf16 NHWC x/y, groups == 1,
+ * Cin in {16,32,64,128,...multiple of 64}, Cout <= 256.  Returns
+ * ESN_ERR_UNSUPPORTED for anything else (the host then calls esn_conv2d_direct). */
+int esn_conv2d_umma(const EsnConv* p, void* stream);
+
+/* MaxPool2d(2, stride 2) followed by the per-channel affine + activation of
+ * the BatchNorm slice it is concatenated into.
+ * Replaces the pool branch of ERFNet.py:24-27 (DownsamplerBlock) and
+ * DABNet.py:104-108 (DownSamplingBlock): y[..., c] = act(max2x2(x)[c]*scale[c]+shift[c]). */
+typedef struct EsnPool {
+  EsnTensor x, y;
+  EsnEpilogue ep;
+} EsnPool;
+int esn_maxpool2x2_affine_act(const EsnPool* p, void* stream);
+
+/* AvgPool2d(3, stride 2, padding 1, count_include_pad=True) applied `ratio`
+ * times (DABNet.py:113-124 InputInjection), then affine+act, written into a
+ * channel slice.  x may be NCHW f32 (network input) or NHWC. */
+int esn_avgpool3x3s2_affine_act(const EsnPool* p, void* stream);
+
+/* Elementwise per-channel affine + activation (+ residual) on an NHWC view:
+ * standalone BNPReLU on concat tensors (DABNet.py:38-48,166,171,176). */
+int esn_affine_act(const EsnPool* p, void* stream);
+
+/* Layout / dtype conversion between NCHW f32 and NHWC f32|bf16 views. */
+int esn_convert_layout(const EsnTensor* x, const EsnTensor* y, void* stream);
+
+/* DABNet depthwise asymmetric pair, both branches fused (DABNet.py:73-78):
+ *   br1 = BNPReLU(dw1x3(BNPReLU(dw3x1(x))))           dilation 1
+ *   br2 = BNPReLU(dw1x3_d(BNPReLU(dw3x1_d(x))))       dilation d
+ *   y   = PReLU(BN(br1 + br2))                        (bn_relu_2)
+ * Per-channel parameter block `prm`, fp32 [15][C]:
+ *   rows 0-2  w3x1 taps, 3 scale, 4 shift, 5 alpha      (branch 1, first conv)   -- see esn/plan.py
+ *   ... (layout documented in DESIGN.md section 4) */
+typedef struct EsnDabPair {
+  EsnTensor x, y;
+  const float* prm;    /* [27][C] fp32 */
+  int32_t dilation;
+  int32_t _pad;
+} EsnDabPair;
+int esn_dab_dw_pair(const EsnDabPair* p, void* stream);
+
+/* Segmentation heads.
+ * esn_head_convt2x2: ConvTranspose2d(Cin, classes, 2, stride 2, bias) (ERFNet.py:128,136)
+ *   fused with either NCHW logits output (f32/bf16) and/or the uint8 argmax mask
+ *   (test.py:79-82: np.argmax over classes, first maximum wins).
+ * esn_head_bilinear: F.interpolate(bilinear, align_corners=False) of NHWC low-res
+ *   class scores (DABNet.py:181) fused the same way. */
+typedef struct EsnHead {
+  EsnTensor x;          /* NHWC input features (convt) or low-res scores (bilinear) */
+  const float* w;       /* convt: fp32 [2][2][Cin][classes_pad(32)]; bilinear: unused */
+  const float* bias;    /* convt: [classes] */
+  EsnTensor logits;     /* optional (ptr may be NULL): NCHW f32/bf16 (N,classes,H,W) */
+  uint8_t* mask;        /* optional: (N,H,W) uint8 argmax */
+  int32_t classes;
+  int32_t out_h, out_w;
+  int32_t _pad;
+} EsnHead;
+int esn_head_convt2x2(const EsnHead* p, void* stream);
+int esn_head_bilinear(const EsnHead* p, void* stream);
+
+/* Weighted cross-entropy over NCHW logits (utils/losses/loss.py:15-32):
+ *   sums[0] += sum_i w[y_i]*nll_i,  sums[1] += sum_i w[y_i]   (fp32 atomics per CTA)
+ * and, if dlogits != NULL, the UNNORMALISED gradient w[y_i]*(softmax - onehot);
+ * the caller scales by 1/sums[1] (after the cross-rank all-reduce of sums). */
+typedef struct EsnCE {
+  EsnTensor logits;       /* NCHW f32/bf16 */
+  const int64_t* target;  /* (N,H,W) */
+  const float* weight;    /* [classes] or NULL */
+  float* sums;            /* [2], zeroed by the caller */
+  EsnTensor dlogits;      /* optional NCHW, same dtype as logits */
+  int32_t ignore_label;
+  int32_t _pad;
+} EsnCE;
+int esn_weighted_ce(const EsnCE* p, void* stream);
+
+/* Library / device queries (host-side, no stream). */
+int esn_version(void);
+const char* esn_strerror(int code);
+/* Number of kernels this library has launched in this process (bench.py's
+ * `gpu_launches`), and reset. */
+int64_t esn_launch_count(void);
+void esn_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESN_H_ */

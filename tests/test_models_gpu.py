@@ -1,0 +1,131 @@
+"""Model-level parity (GPU): CUDA path vs the reference's golden outputs and vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import spec_state_dict
+from oracle import fixture, nets
+
+pytestmark = pytest.mark.gpu
+
+FP32_LOGIT_TOL = 1e-3     # north_star: logits within 1e-3 relative in fp32
+BF16_LOGIT_TOL = 5e-2     # north_star: 5e-2 in bf16
+ARGMAX_MIN = 0.999        # north_star: argmax masks >= 99.9 % pixel-identical (fp32)
+
+
+def _model(name, spec):
+    from builders.model_builder import build_model
+    m = build_model(name, 19)
+    m.load_state_dict(spec_state_dict(spec, name))
+    return m.cuda().eval()
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def _margin_mask(ref_logits, tol):
+    top2 = torch.topk(ref_logits.double(), 2, dim=1).values
+    return (top2[:, 0] - top2[:, 1]) > tol * top2[:, 0].abs().clamp_min(1e-6)
+
+
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
+def test_fp32_matches_reference_golden(name, spec, golden):
+    m = _model(name, spec)
+    g = golden(name)
+    for (n, h, w) in ((1, 64, 128), (2, 128, 256)):
+        x = fixture.make_input(n, h, w).cuda()
+        with torch.no_grad():
+            y = m(x)
+            logits, mask = m.predict_mask(x, with_logits=True)
+        assert y.shape == (n, 19, h, w) and y.dtype == torch.float32 and y.is_contiguous()
+        assert torch.equal(y, logits)
+        tag = "eval_%dx%dx%d" % (n, h, w)
+        if h == 64:
+            ref = torch.from_numpy(g[tag + "_logits"])
+            assert _rel(y.cpu(), ref) < FP32_LOGIT_TOL
+            assert ((y.cpu() - ref).abs().max() / ref.abs().max()).item() < FP32_LOGIT_TOL
+        else:
+            ref = torch.from_numpy(g[tag + "_logits_s4"])
+            assert _rel(y.cpu()[:, :, ::4, ::4], ref) < FP32_LOGIT_TOL
+        ref_mask = g[tag + "_argmax"]
+        agree = (mask.cpu().numpy() == ref_mask).mean()
+        assert agree >= ARGMAX_MIN, agree
+        assert (mask.cpu().numpy() == nets.argmax_mask(y)).all()       # fused argmax == numpy argmax of our logits
+
+
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
+def test_bf16_matches_oracle(name, spec):
+    m = _model(name, spec)
+    sd = spec_state_dict(spec, name)
+    x = fixture.make_input(2, 128, 256)
+    with torch.no_grad():
+        ref = nets.forward(name, sd, x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m(x.cuda())
+            mask = m.predict_mask(x.cuda())
+    assert y.dtype == torch.bfloat16
+    rel = _rel(y.float().cpu(), ref)
+    assert rel < BF16_LOGIT_TOL, rel
+    # raw and margin-aware argmax agreement (random-init logits have tiny top-2 margins)
+    ref_mask = torch.from_numpy(nets.argmax_mask(ref))
+    raw = (mask.cpu() == ref_mask).float().mean().item()
+    safe = _margin_mask(ref, BF16_LOGIT_TOL)
+    aware = (mask.cpu() == ref_mask)[safe].float().mean().item()
+    print("%s bf16: logits rel-L2 %.3e  argmax raw %.4f  margin-aware %.4f (%.1f%% of pixels)" %
+          (name, rel, raw, aware, 100 * safe.float().mean().item()))
+    assert aware >= ARGMAX_MIN, aware
+    assert raw > 0.9, raw
+
+
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
+def test_blocks_are_drop_in(name, spec):
+    """Blocks keep the reference signatures and work stand-alone on NCHW tensors."""
+    sd = spec_state_dict(spec, name)
+    if name == "ERFNet":
+        from model.ERFNet import non_bottleneck_1d, DownsamplerBlock, UpsamplerBlock
+        blk = non_bottleneck_1d(128, 0.3, 8)
+        pre = "encoder.layers.9."
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, 128, 24, 40)
+        ref = nets.erf_nb1d(nets.SD(sd, pre), x, 8)
+        y = blk.cuda().eval()(x.cuda())
+        assert _rel(y.float().cpu(), ref) < 1e-4
+        blk = DownsamplerBlock(64, 128)
+        pre = "encoder.layers.6."
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, 64, 24, 40)
+        ref = nets.erf_downsampler(nets.SD(sd, pre), x)
+        assert _rel(blk.cuda().eval()(x.cuda()).float().cpu(), ref) < 1e-4
+        blk = UpsamplerBlock(128, 64)
+        pre = "decoder.layers.0."
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, 128, 12, 20)
+        ref = nets.erf_upsampler(nets.SD(sd, pre), x)
+        assert _rel(blk.cuda().eval()(x.cuda()).float().cpu(), ref) < 1e-4
+    else:
+        from model.DABNet import DABModule
+        blk = DABModule(128, d=8)
+        pre = "DAB_Block_2.DAB_Module_2_2."
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, 128, 24, 40)
+        ref = nets.dab_module(nets.SD(sd, pre), x, 8)
+        y = blk.cuda().eval()(x.cuda())
+        assert y.shape == ref.shape
+        assert _rel(y.float().cpu(), ref) < 1e-4
+
+
+def test_full_size_properties_erfnet(spec):
+    """At BASELINE.json's full size the CPU oracle is too slow; check size-independent properties:
+    batch-permutation equivariance, fused argmax == argmax of the logits, bf16 close to fp32."""
+    m = _model("ERFNet", spec)
+    x = fixture.make_input(2, 512, 1024).cuda()
+    with torch.no_grad():
+        y = m(x)
+        y_sw = m(x.flip(0))
+        assert torch.equal(y, y_sw.flip(0))
+        logits, mask = m.predict_mask(x, with_logits=True)
+        assert torch.equal(mask.long(), logits.argmax(1))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yb = m(x)
+    assert _rel(yb.float(), y) < BF16_LOGIT_TOL

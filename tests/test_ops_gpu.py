@@ -1,0 +1,179 @@
+"""Kernel-level parity: each C-ABI op against the same op in plain torch fp32 (GPU tests)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from esn import ops as o
+    return o
+
+
+def _rand_conv(cin, cout, k, stride=1, pad=0, dil=1, groups=1, bias=True, transposed=False, out_pad=0, seed=0):
+    torch.manual_seed(seed)
+    if transposed:
+        m = nn.ConvTranspose2d(cin, cout, k, stride=stride, padding=pad, output_padding=out_pad, bias=bias)
+    else:
+        m = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, dilation=dil, groups=groups, bias=bias)
+    return m.cuda().float()
+
+
+def _nhwc(x, dtype, ops, c_alloc=None):
+    n, c, h, w = x.shape
+    y = ops.new_act(n, c, h, w, dtype, x.device, c_alloc=c_alloc)
+    y.copy_(x)
+    return y
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, pad, dil, groups, transposed, out_pad, H, W
+    (16, 16, (3, 1), 1, (1, 0), (1, 1), 1, False, 0, 20, 36),
+    (64, 64, (1, 3), 1, (0, 2), (1, 2), 1, False, 0, 17, 40),
+    (128, 128, (3, 1), 1, (16, 0), (16, 1), 1, False, 0, 24, 32),
+    (16, 48, 3, 2, 1, 1, 1, False, 0, 32, 48),
+    (64, 64, 3, 2, 1, 1, 1, False, 0, 16, 32),
+    (35, 29, 3, 2, 1, 1, 1, False, 0, 16, 32),
+    (128, 64, 3, 2, 1, 1, 1, True, 1, 9, 14),
+    (64, 16, 3, 2, 1, 1, 1, True, 1, 12, 20),
+    (32, 32, (3, 1), 1, (4, 0), (4, 1), 32, False, 0, 20, 24),   # depthwise dilated
+    (64, 32, 3, 1, 1, 1, 1, False, 0, 16, 24),
+    (32, 64, 1, 1, 0, 1, 1, False, 0, 16, 24),
+    (259, 19, 1, 1, 0, 1, 1, False, 0, 8, 16),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_direct_matches_torch(ops, case, dtype):
+    from esn._lib import ACT_PRELU
+    cin, cout, k, stride, pad, dil, groups, tr, op, H, W = case
+    m = _rand_conv(cin, cout, k, stride, pad, dil, groups, True, tr, op)
+    torch.manual_seed(1)
+    x = torch.randn(2, cin, H, W, device="cuda")
+    scale = torch.rand(cout, device="cuda") + 0.5
+    shift = torch.randn(cout, device="cuda") * 0.1
+    alpha = torch.rand(cout, device="cuda") * 0.4
+    xa = _nhwc(x, dtype, ops)
+    with torch.no_grad():
+        ref = m(xa.float())
+        res = torch.randn_like(ref)
+        resa = _nhwc(res, dtype, ops)
+        ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + resa.float()
+        ref = torch.where(ref >= 0, ref, ref * alpha.view(1, -1, 1, 1))
+    prep = ops.ConvPrep(m, scale, shift, ACT_PRELU, alpha)
+    y = ops.conv2d(xa, prep, residual=resa, force_direct=True)
+    assert y.shape == ref.shape
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    err = (y.float() - ref).abs().max() / ref.abs().max()
+    assert err < tol, err
+
+
+def test_conv_direct_nchw_input_and_slice_output(ops):
+    from esn._lib import ACT_RELU
+    m = _rand_conv(3, 13, 3, 2, 1)
+    x = torch.randn(2, 3, 32, 48, device="cuda") * 50
+    prep = ops.ConvPrep(m, act=ACT_RELU)
+    y = ops.new_act(2, 16, 16, 24, torch.float32, x.device)
+    y.zero_()
+    ops.conv2d(x, prep, out=y[:, :13])
+    scale = torch.rand(3, device="cuda") + 0.5
+    shift = torch.randn(3, device="cuda")
+    ops.maxpool2x2(x, y[:, 13:], scale, shift, None, ACT_RELU)
+    with torch.no_grad():
+        ref = torch.cat([F.relu(m(x)), F.relu(F.max_pool2d(x, 2, 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))], 1)
+    assert (y - ref).abs().max() / ref.abs().max() < 1e-5
+
+
+def test_pools_affine_convert(ops):
+    from esn._lib import ACT_NONE, ACT_PRELU
+    x = torch.randn(2, 35, 16, 24, device="cuda")
+    xa = _nhwc(x, torch.float32, ops, c_alloc=40)
+    s, b, a = torch.rand(35, device="cuda") + 0.5, torch.randn(35, device="cuda"), torch.rand(35, device="cuda") * 0.3
+    out = ops.affine_act(xa, s, b, a, ACT_PRELU)
+    ref = x * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+    ref = torch.where(ref >= 0, ref, ref * a.view(1, -1, 1, 1))
+    assert torch.allclose(out, ref, atol=1e-6, rtol=1e-5)
+    # in place
+    ops.affine_act(xa, s, b, a, ACT_PRELU, out=xa)
+    assert torch.allclose(xa, ref, atol=1e-6, rtol=1e-5)
+    # avg pool 3x3 s2 p1 (count_include_pad) on NCHW input, odd sizes
+    img = torch.randn(2, 3, 33, 47, device="cuda") * 30
+    y = ops.new_act(2, 3, 17, 24, torch.float32, img.device, c_alloc=4)
+    ops.avgpool3x3s2(img, y)
+    assert torch.allclose(y, F.avg_pool2d(img, 3, 2, 1), atol=1e-4, rtol=1e-5)
+    y2 = ops.new_act(2, 3, 9, 12, torch.float32, img.device, c_alloc=4)
+    ops.avgpool3x3s2(y, y2)
+    assert torch.allclose(y2, F.avg_pool2d(F.avg_pool2d(img, 3, 2, 1), 3, 2, 1), atol=1e-4, rtol=1e-5)
+    # max pool on NHWC bf16
+    xb = _nhwc(x, torch.bfloat16, ops, c_alloc=40)
+    yb = ops.new_act(2, 35, 8, 12, torch.bfloat16, x.device, c_alloc=40)
+    ops.maxpool2x2(xb, yb)
+    assert torch.equal(yb.float(), F.max_pool2d(xb.float(), 2, 2))
+    # layout round trip
+    for dt in (torch.float32, torch.bfloat16):
+        t = ops.as_act(x, dt)
+        assert ops.is_nhwc(t) and t.dtype == dt
+        back = ops.to_nchw(t, torch.float32)
+        assert back.is_contiguous()
+        assert torch.allclose(back, x.to(dt).float())
+
+
+def test_dab_pair_matches_torch(ops):
+    torch.manual_seed(3)
+    from model.DABNet import DABModule
+    from oracle import fixture
+    for c, d in ((64, 2), (128, 16)):
+        m = DABModule(c, d=d)
+        m.load_state_dict(fixture.randomize_state_dict(m.state_dict(), 5))
+        m = m.cuda().eval()
+        x = torch.randn(2, c // 2, 20, 28, device="cuda")
+        with torch.no_grad():
+            def cbr(conv, t, pad, dil):
+                y = F.conv2d(t, conv.conv.weight, None, 1, pad, dil, c // 2)
+                y = F.batch_norm(y, conv.bn_prelu.bn.running_mean, conv.bn_prelu.bn.running_var,
+                                 conv.bn_prelu.bn.weight, conv.bn_prelu.bn.bias, False, 0.0, 1e-3)
+                return F.prelu(y, conv.bn_prelu.acti.weight)
+            b1 = cbr(m.dconv1x3, cbr(m.dconv3x1, x, (1, 0), 1), (0, 1), 1)
+            b2 = cbr(m.ddconv1x3, cbr(m.ddconv3x1, x, (d, 0), (d, 1)), (0, d), (1, d))
+            s = b1 + b2
+            s = F.batch_norm(s, m.bn_relu_2.bn.running_mean, m.bn_relu_2.bn.running_var, m.bn_relu_2.bn.weight,
+                             m.bn_relu_2.bn.bias, False, 0.0, 1e-3)
+            ref = F.prelu(s, m.bn_relu_2.acti.weight)
+        y = ops.dab_dw_pair(ops.as_act(x, torch.float32), m.prep(x.device), d)
+        assert (y - ref).abs().max() / ref.abs().max() < 1e-5
+
+
+def test_heads_and_ce(ops):
+    from oracle import fixture, loss as oloss
+    torch.manual_seed(0)
+    # convT 2x2 head
+    m = nn.ConvTranspose2d(16, 19, 2, stride=2).cuda()
+    x = torch.randn(2, 16, 12, 20, device="cuda")
+    w = torch.zeros(2, 2, 16, 32, device="cuda")
+    w[:, :, :, :19] = m.weight.detach().permute(2, 3, 0, 1)
+    logits, mask = ops.head_convt2x2(ops.as_act(x, torch.float32), w.contiguous(), m.bias.detach().contiguous(), 19, True, True)
+    with torch.no_grad():
+        ref = m(x)
+    assert torch.allclose(logits, ref, atol=1e-5, rtol=1e-5)
+    assert (mask.long() == ref.argmax(1)).float().mean() > 0.999
+    # bilinear head (align_corners=False), x8
+    s = torch.randn(2, 19, 8, 16, device="cuda")
+    sa = ops.new_act(2, 19, 8, 16, torch.float32, s.device, c_alloc=32)
+    sa.copy_(s)
+    logits, mask = ops.head_bilinear(sa, 19, 64, 128, True, True)
+    ref = F.interpolate(s, (64, 128), mode="bilinear", align_corners=False)
+    assert torch.allclose(logits, ref, atol=1e-5, rtol=1e-5)
+    assert (mask.long() == ref.argmax(1)).float().mean() > 0.999
+    # weighted CE fwd + grad vs the CPU oracle
+    lg = torch.randn(2, 19, 16, 32) * 3
+    lab = fixture.make_labels(2, 16, 32, 19, seed=5)
+    wt = torch.tensor(fixture.CLASS_WEIGHTS)
+    sums, g = ops.weighted_ce(lg.cuda(), lab.cuda(), wt.cuda(), 255, want_grad=True)
+    l, swl, sw = oloss.weighted_ce(lg.double(), lab, wt.double())
+    assert abs(sums[0].item() / sums[1].item() - l.item()) < 1e-5 * abs(l.item())
+    gref = oloss.weighted_ce_grad(lg.double(), lab, wt.double())
+    assert ((g.cpu().double() / sums[1].item()) - gref).abs().max() < 1e-6
