@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the segmentation hot path on B200 (driver contract in the task brief).
+
+Default workload = BASELINE.json configs[1]: ERFNet (19 classes), bf16, inference, batch 16 per GPU,
+3x1024x2048 synthetic Cityscapes-shaped input, fused argmax head (uint8 mask out).
+A "step" is one forward of one batch.  N>1 shards images across ranks with no data-path
+collective (inference; "weak" scaling: 16 images per GPU).
+
+    python bench.py                                   # N=1
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference                  # the reference's CPU path (oracle port) on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "efficient-segmentation-networks_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, batch per GPU, H, W, mode)
+    "erfnet_infer_bf16_b16_1024x2048": ("ERFNet", 16, 1024, 2048),
+    "dabnet_infer_bf16_b16_1024x2048": ("DABNet", 16, 1024, 2048),
+    "erfnet_infer_bf16_b16_512x1024": ("ERFNet", 16, 512, 1024),
+    "dabnet_infer_bf16_b16_512x1024": ("DABNet", 16, 512, 1024),
+}
+# block-fused algorithmic elements per input pixel (forward), bf16 storage; the
+# logits term (19 elements/pixel) is replaced by the 1-byte argmax mask because the head is fused.
+ALG_ELEMS_PER_PX = {"ERFNet": 162.0, "DABNet": 189.5}
+GMAC_512x1024 = {"ERFNet": 26.60, "DABNet": 10.22}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def fixture_state_dict(name):
+    from oracle import fixture
+    spec = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_spec.json")))
+    proto = {k: torch.empty(shape, dtype=getattr(torch, dt.split(".")[1])) for k, shape, dt in spec[name]["keys"]}
+    return fixture.randomize_state_dict(proto, 1234)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_leg(model, h, w, steps, warmup, budget_s=25.0):
+    """The reference's CPU path (oracle port of model/*.py, fp32, eval, all host threads) on a
+    bounded sample of the workload: one image of the workload's resolution per step."""
+    from oracle import fixture, nets
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = fixture_state_dict(model)
+    x = fixture.make_input(1, h, w)
+    times = []
+    with torch.no_grad():
+        t_start = time.perf_counter()
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            y = nets.forward(model, sd, x)
+            nets.argmax_mask(y)
+            t1 = time.perf_counter()
+            if i >= warmup:
+                times.append(t1 - t0)
+            if i >= warmup and (t1 - t_start) > budget_s and len(times) >= 2:
+                break
+    mean = sum(times) / len(times)
+    return {"value": 1.0 / mean, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "%d x (1 image 3x%dx%d fp32, forward + numpy argmax), oracle/nets.py on %d host threads"
+                      % (len(times), h, w, threads)}, mean, len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="erfnet_infer_bf16_b16_1024x2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    args = ap.parse_args()
+    model_name, batch, H, W = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": args.workload, "net": model_name, "classes": 19, "batch_per_gpu": batch,
+              "input": "3x%dx%d fp32 NCHW" % (H, W), "mode": "inference", "head": "argmax fused (uint8 mask)",
+              "sharding": "images across ranks, no collective",
+              "l2": "no flush: per-step working set (input %.0f MB + activations) >> 126 MB L2" % (batch * 3 * H * W * 4 / 1e6)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, max(1, min(args.warmup, 2)))
+        line = {"impl": "reference", "metric": "images/s", "value": base["value"], "unit": "images/s",
+                "n_gpus": args.gpus, "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, mode="inference (CPU, reference arithmetic)", batch_per_gpu=1),
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from builders.model_builder import build_model
+    from esn import ops
+    from oracle import fixture
+
+    m = build_model(model_name, 19)
+    m.load_state_dict(fixture_state_dict(model_name))
+    m = m.cuda().eval()
+    x_host = fixture.make_input(batch, H, W, seed=1234 + rank).pin_memory()
+    x = x_host.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def step(inp):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return m.predict_mask(inp)
+
+    # ---- warm-up (also builds the packed-weight caches), then optional CUDA-graph capture
+    for _ in range(max(args.warmup, 3)):
+        mask = step(x)
+    torch.cuda.synchronize()
+    ops.launch_count_reset()
+    step(x)
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count()
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step(x)
+            with torch.cuda.graph(graph, stream=s):
+                mask = step(x)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return mask
+        return step(x)
+
+    # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+    except Exception:
+        gpu_id = str(local_rank)
+    sampler = ClockSampler(gpu_id)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([elapsed_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = t.item()
+    ms_per_step = elapsed_ms / args.steps
+    value = world * batch / (ms_per_step / 1e3)
+
+    # ---- e2e: pinned host images -> H2D -> forward -> D2H uint8 masks, every step, double-buffered
+    h2d = x_host.numel() * 4
+    d2h = batch * H * W
+    mask_host = [torch.empty((batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    xin = [torch.empty_like(x), torch.empty_like(x)]
+    copy_s = torch.cuda.Stream()
+    main_s = torch.cuda.current_stream()
+
+    def e2e_loop(k):
+        ready = [None, None]
+        done = [None, None]
+        for i in range(k + 1):
+            b = i & 1
+            if i < k:
+                with torch.cuda.stream(copy_s):
+                    if done[b] is not None:
+                        copy_s.wait_event(done[b])      # buffer b free (its compute finished)
+                    xin[b].copy_(x_host, non_blocking=True)
+                    ready[b] = torch.cuda.Event()
+                    ready[b].record(copy_s)
+            if i >= 1:
+                pb = (i - 1) & 1
+                main_s.wait_event(ready[pb])
+                mk = step(xin[pb])
+                mask_host[pb].copy_(mk, non_blocking=True)
+                done[pb] = torch.cuda.Event()
+                done[pb].record(main_s)
+        main_s.wait_stream(copy_s)
+
+    e2e_loop(2)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    e2e_loop(k_e2e)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_ms = (t1 - t0) * 1e3 / k_e2e
+    if dist:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_value = world * batch / (e2e_ms / 1e3)
+
+    # ---- per-kernel roofline: one instrumented eager step, CUDA events around every launch
+    hbm_peak, tc_peak, peak_src = peaks()
+    roofline, kernels = None, None
+    if rank == 0:
+        for _ in range(2):
+            ops.PROFILE = []
+            step(x)
+            torch.cuda.synchronize()
+            prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for r in prof:
+            ms = r["ev"][0].elapsed_time(r["ev"][1])
+            a = agg.setdefault(r["kernel"], {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            a["launches"] += 1
+            a["ms"] += ms
+            a["bytes"] += r["bytes"]
+            a["flops"] += r["flops"]
+        tot_ms = sum(a["ms"] for a in agg.values())
+        kernels = {k: {"launches": a["launches"], "ms": round(a["ms"], 4), "share": round(a["ms"] / tot_ms, 4),
+                       "alg_GBps": round(a["bytes"] / a["ms"] / 1e6, 1), "TFLOPs": round(a["flops"] / a["ms"] / 1e9, 2)}
+                   for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        achieved = top[1]["bytes"] / (top[1]["ms"] / 1e3) / 1e9
+        roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": top[1]["launches"], "share_of_step": round(top[1]["ms"] / tot_ms, 4),
+                    "tensor_TFLOPs": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12, 1),
+                    "tensor_frac_of_bf16_peak": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12 / tc_peak, 4),
+                    "definition": "sum over the step's launches of (|x|+|y|+|residual| bytes) / sum of their CUDA-event durations"}
+        # whole-network figure against SURVEY 8(d)'s block-fused algorithmic bytes
+        px = batch * H * W
+        alg_bytes = px * ((ALG_ELEMS_PER_PX[model_name] - 19.0) * 2 + 1 + 3 * 4 - 3 * 2)
+        flops = 2 * GMAC_512x1024[model_name] * 1e9 * (H * W) / (512 * 1024) * batch
+        model_roof = {"alg_bytes_per_step": int(alg_bytes), "hbm_frac": round(alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak, 4),
+                      "tensor_frac": round(flops / (ms_per_step / 1e3) / 1e12 / tc_peak, 4),
+                      "note": "block-fused algorithmic bytes (SURVEY 8d) and conv FLOPs of the whole forward / step time"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    line = {"metric": "images/s", "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(config, cuda_graph=graph is not None),
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms, 3), "steps": k_e2e,
+                    "note": "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "model_roofline": model_roof, "kernels": kernels}
+    if not args.no_cpu_baseline and world >= 1:
+        base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0)
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

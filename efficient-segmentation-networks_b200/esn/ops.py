@@ -20,6 +20,27 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional per-launch profile (bench.py's roofline leg): when PROFILE is a list every C-ABI call is
+# bracketed by CUDA events on the launching stream and (kernel, algorithmic bytes, flops, events)
+# is appended.  None (the default) adds no work to the hot path.
+PROFILE = None
+
+
+def _nbytes(t):
+    return 0 if t is None else t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3] * t.element_size()
+
+
+def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag=""):
+    if PROFILE is None:
+        L.check(fn(*arg_refs, stream()), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(fn(*arg_refs, stream()), name)
+    e1.record()
+    PROFILE.append({"kernel": name, "tag": tag, "bytes": int(alg_bytes), "flops": int(flops), "ev": (e0, e1)})
+
+
 def require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError("%s: tensors must live on a CUDA device; this framework has no CPU path" % what)
@@ -61,7 +82,7 @@ def compute_dtype(x):
     """fp32 unless bf16 autocast is active, ESN_COMPUTE=bf16, or the activations already are bf16."""
     if x.dtype == torch.bfloat16:
         return torch.bfloat16
-    if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+    if torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16:
         return torch.bfloat16
     if os.environ.get("ESN_COMPUTE", "").lower() == "bf16":
         return torch.bfloat16
@@ -83,7 +104,7 @@ def as_act(x, dtype=None):
     dx, dy = tdesc(x), tdesc(y)
     if dx.layout == L.ESN_NHWC:  # NHWC but other dtype: elementwise copy through the affine kernel
         return affine_act(x, None, None, None, L.ACT_NONE, out=y)
-    L.check(L.lib.esn_convert_layout(C.byref(dx), C.byref(dy), stream()), "esn_convert_layout")
+    _call(L.lib.esn_convert_layout, "esn_convert_layout", (C.byref(dx), C.byref(dy)), _nbytes(x) + _nbytes(y))
     return y
 
 
@@ -184,24 +205,49 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
     p.pad_h, p.pad_w, p.dil_h, p.dil_w = prep.pad_h, prep.pad_w, prep.dil_h, prep.dil_w
     p.groups, p.transposed, p.cout_pad = prep.groups, prep.transposed, prep.cout_pad
     _epilogue(p.ep, prep.scale, prep.shift, prep.alpha, prep.act, residual)
+    alg = _nbytes(x) + _nbytes(out) + _nbytes(residual)
+    flops = 2 * n * ho * wo * prep.cout * (prep.cin // prep.groups) * prep.kh * prep.kw
+    if prep.transposed:
+        flops = 2 * n * h * w * prep.cout * prep.cin * prep.kh * prep.kw
+    tag = "%dx%d c%d-%d s%d d%d%s" % (prep.kh, prep.kw, prep.cin, prep.cout, prep.stride,
+                                       max(prep.dil_h, prep.dil_w), "T" if prep.transposed else "")
     if (UMMA_ENABLED and not force_direct and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
-            and prep.groups == 1 and p.x.layout == L.ESN_NHWC):
+            and prep.groups == 1 and p.x.layout == L.ESN_NHWC and umma_supported(prep, p)):
         p.w = prep.w_umma.data_ptr()
-        rc = L.lib.esn_conv2d_umma(C.byref(p), stream())
-        if rc == 0:
-            return out
-        if rc != L.ERR_UNSUPPORTED and rc != -5:
-            L.check(rc, "esn_conv2d_umma")
+        _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag)
+        return out
     p.w = prep.w_direct.data_ptr()
-    L.check(L.lib.esn_conv2d_direct(C.byref(p), stream()), "esn_conv2d_direct")
+    _call(L.lib.esn_conv2d_direct, "esn_conv2d_direct", (C.byref(p),), alg, flops, tag)
     return out
+
+
+def umma_supported(prep, p):
+    """Mirror of esn_conv2d_umma's shape gate (csrc/esn_umma.cu) so routing costs no failed call."""
+    cin = prep.cin
+    if not (cin in (16, 32, 64) or cin % 64 == 0) or prep.cout_pad > 256:
+        return False
+    if prep.kh * prep.kw > 9 or prep.stride not in (1, 2):
+        return False
+    if prep.transposed and (prep.stride != 2 or prep.dil_h != 1 or prep.dil_w != 1 or p.y.h != 2 * p.x.h):
+        return False
+    if not prep.transposed and prep.stride == 2 and ((p.x.h | p.x.w) & 1):
+        return False
+    if p.x.c_stride % 8 or p.y.c_stride % 8 or p.x.ptr % 16 or p.y.ptr % 16:
+        return False
+    if p.ep.residual.ptr and (p.ep.residual.c_stride % 8 or p.ep.residual.ptr % 16 or p.ep.residual.dtype != L.ESN_BF16):
+        return False
+    taps = prep.kh * prep.kw if not prep.transposed else 4
+    kb = min(cin, 64)
+    if taps * cin * prep.cout_pad * 2 + 2 * 128 * kb * 2 + 4096 > 227 * 1024:
+        return False
+    return True
 
 
 def _pool_call(fn, name, x, out, scale, shift, alpha, act, residual=None):
     p = L.EsnPool()
     p.x, p.y = tdesc(x), tdesc(out)
     _epilogue(p.ep, scale, shift, alpha, act, residual)
-    L.check(fn(C.byref(p), stream()), name)
+    _call(fn, name, (C.byref(p),), _nbytes(x) + _nbytes(out) + _nbytes(residual))
     return out
 
 
@@ -226,7 +272,7 @@ def dab_dw_pair(x, prm, dilation, out=None):
         out = new_act(n, c, h, w, x.dtype, x.device)
     p = L.EsnDabPair()
     p.x, p.y, p.prm, p.dilation = tdesc(x), tdesc(out), prm.data_ptr(), dilation
-    L.check(L.lib.esn_dab_dw_pair(C.byref(p), stream()), "esn_dab_dw_pair")
+    _call(L.lib.esn_dab_dw_pair, "esn_dab_dw_pair", (C.byref(p),), _nbytes(x) + _nbytes(out), 0, "d%d" % dilation)
     return out
 
 
@@ -245,7 +291,9 @@ def _head(fn, name, x, w, bias, classes, out_h, out_w, want_logits, want_mask, l
         mask = torch.empty((n, out_h, out_w), dtype=torch.uint8, device=x.device)
         p.mask = mask.data_ptr()
     p.classes, p.out_h, p.out_w = classes, out_h, out_w
-    L.check(fn(C.byref(p), stream()), name)
+    alg = _nbytes(x) + (logits.numel() * logits.element_size() if logits is not None else 0) + \
+        (mask.numel() if mask is not None else 0)
+    _call(fn, name, (C.byref(p),), alg)
     return logits, mask
 
 

@@ -12,6 +12,10 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 GOLD = os.path.join(ROOT, "tests", "golden")
+# torch's GPU fp32 convs default to TF32 (10-bit mantissa); the torch reference ops used by the
+# kernel-level tests must be true fp32
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_configure(config):
