@@ -302,6 +302,17 @@ def main():
         kernels = {k: {"launches": a["launches"], "ms": round(a["ms"], 4), "share": round(a["ms"] / tot_ms, 4),
                        "alg_GBps": round(a["bytes"] / a["ms"] / 1e6, 1), "TFLOPs": round(a["flops"] / a["ms"] / 1e9, 2)}
                    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        by_tag = {}
+        for r in prof:
+            ms = r["ev"][0].elapsed_time(r["ev"][1])
+            a = by_tag.setdefault(r["kernel"].replace("esn_", "") + " " + r["tag"], [0, 0.0, 0, 0])
+            a[0] += 1
+            a[1] += ms
+            a[2] += r["bytes"]
+            a[3] += r["flops"]
+        layers = {k: {"n": v[0], "ms": round(v[1], 3), "alg_GBps": round(v[2] / v[1] / 1e6, 1),
+                      "TFLOPs": round(v[3] / v[1] / 1e9, 1)}
+                  for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][1])[:24]}
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         achieved = top[1]["bytes"] / (top[1]["ms"] / 1e3) / 1e9
         roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
@@ -332,7 +343,7 @@ def main():
                     "note": "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "model_roofline": model_roof, "kernels": kernels}
+            "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}
     if not args.no_cpu_baseline and world >= 1:
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0)
         line["cpu_baseline"] = base

@@ -24,22 +24,27 @@
 namespace {
 
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 192;
+constexpr int kThreads = 352;   // 11 warps: TMA-A, MMA, TMA-residual, 8 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kEpiWarp0 = 3;
 constexpr int kTileM = 128;
 constexpr long long kSpinLimitCycles = 4000000000LL;  // ~2 s
 
 struct alignas(64) UmmaArgs {
-  CUtensorMap tmA;
-  CUtensorMap tmB;
-  int ntaps, nkb, kb_elems, N, cout;
+  CUtensorMap tmA;  // activations, 5-D
+  CUtensorMap tmB;  // weights, 2-D
+  CUtensorMap tmY;  // output, 4-D   (staged epilogue only)
+  CUtensorMap tmR;  // residual, 4-D (staged epilogue with residual only)
+  int ntaps, nkb, kb_elems, N, cout, MT;
   int bw, bh, tiles_w, tiles_h, ntiles, gh, gw;
   int tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_par[kMaxTaps], tap_coff[kMaxTaps], tap_wrow[kMaxTaps];
   __nv_bfloat16* y;
   int Hy, Wy, y_cs, sy, oy, sx, ox;
   EpiArgs ep;
-  int stages;
-  uint32_t stage_bytes, wblock_bytes, w_region_bytes;
-  uint32_t idesc, desc_hi;  // instruction descriptor; upper 32 bits of the smem descriptors
+  int staged, has_res, stages, NS;
+  int cbo, ncb;                      // staged epilogue: channels per 128B-wide column block, #blocks
+  uint32_t stage_bytes, wblock_bytes, w_region_bytes, out_block_bytes, out_buf_bytes, out_swz_mask;
+  uint32_t idesc, desc_hi;           // instruction descriptor; upper 32 bits of the smem descriptors
   uint32_t tmem_cols;
 };
 
@@ -89,6 +94,39 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -126,28 +164,38 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t desc_
 }
 
 // ------------------------------------------------------------------ kernel
+// Shared memory map (base aligned to 1024 B):
+//   [ weights: ntaps*nkb blocks of N x KB ]  [ A ring: stages x (MT*128 x KB) ]
+//   [ staging: NS x (ncb blocks of MT*128 x cbo) -- residual lands here, output leaves from here ]
+//   [ epilogue params: scale|shift|alpha, N floats each ]  [ mbarriers ]
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
+  const int S = a.stages, NS = a.NS;
   const uint32_t w_base = base;
   const uint32_t a_base = base + a.w_region_bytes;
-  const uint32_t bar_base = a_base + (uint32_t)a.stages * a.stage_bytes;
-  const int S = a.stages;
+  const uint32_t o_base = a_base + (uint32_t)S * a.stage_bytes;
+  const uint32_t prm_base = o_base + (uint32_t)NS * a.out_buf_bytes;
+  const uint32_t bar_base = prm_base + 3u * 256u * 4u;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   const uint32_t wfull_bar = bar_base + 8u * (2 * S);
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + 1 + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 3 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 5);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * S + 5 + b); };
+  auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * S + 9 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 13);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* prm = reinterpret_cast<float*>(smem_raw + (prm_base - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
+    if (a.staged) tma_prefetch_desc(&a.tmY);
+    if (a.has_res && a.staged) tma_prefetch_desc(&a.tmR);
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -155,7 +203,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     mbar_init(wfull_bar, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), kEpiThreads);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(sfull_bar(b), 1);
+      mbar_init(sfree_bar(b), 1);
     }
     fence_barrier_init();
   }
@@ -164,12 +216,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // per-channel epilogue parameters -> smem (read back as broadcast LDS.128)
+  for (int i = threadIdx.x; i < a.N; i += kThreads) {
+    const bool in = i < a.cout;
+    prm[i] = (in && a.ep.scale) ? a.ep.scale[i] : 1.f;
+    prm[256 + i] = (in && a.ep.shift) ? a.ep.shift[i] : 0.f;
+    prm[512 + i] = (in && a.ep.act == ESN_ACT_PRELU) ? a.ep.alpha[i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kiters = a.ntaps * a.nkb;  // smem stages consumed per tile
+  const uint32_t acc_cols = (uint32_t)(a.MT * a.N);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -204,12 +264,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
       const int ksteps = a.kb_elems / 16;
+      const uint32_t sub_bytes = (uint32_t)kTileM * a.kb_elems * 2u;  // one 128-row M sub-tile of a stage
       uint32_t it = 0, tc = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tc) {
         const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
         mbar_wait(tempty_bar(acc), aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.N;
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int ki = 0; ki < kiters; ++ki, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
@@ -217,88 +278,145 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           tc_fence_after();
           const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
           const uint32_t b_addr = w_base + (uint32_t)ki * a.wblock_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_desc(a_addr + 32u * k, a.desc_hi);
-            const uint64_t bd = make_desc(b_addr + 32u * k, a.desc_hi);
-            umma_bf16(d_tmem, ad, bd, a.idesc, (ki | k) != 0 ? 1u : 0u);
+          for (int m = 0; m < a.MT; ++m) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_desc(a_addr + m * sub_bytes + 32u * k, a.desc_hi);
+              const uint64_t bd = make_desc(b_addr + 32u * k, a.desc_hi);
+              umma_bf16(d_tmem + (uint32_t)(m * a.N), ad, bd, a.idesc, (ki | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
         }
-        umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        umma_commit(tfull_bar(acc));  // accumulators ready for the epilogue
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0 && a.staged && a.has_res) {
+      // ---------------- residual producer: the residual tile lands in the staging buffer the
+      // epilogue will overwrite in place with the output tile
+      uint32_t tc = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tc) {
+        const int tw = tile % a.tiles_w;
+        const int th = (tile / a.tiles_w) % a.tiles_h;
+        const int n = tile / (a.tiles_w * a.tiles_h);
+        const int b = tc % NS;
+        const uint32_t u = tc / NS;
+        mbar_wait(sfree_bar(b), (u & 1u) ^ 1u);
+        mbar_expect_tx(sfull_bar(b), a.out_buf_bytes);
+        for (int cb = 0; cb < a.ncb; ++cb)
+          tma_load_4d(o_base + (uint32_t)b * a.out_buf_bytes + (uint32_t)cb * a.out_block_bytes, &a.tmR, sfull_bar(b),
+                      cb * a.cbo, tw * a.bw, th * a.bh, n);
       }
     }
   } else {
-    // ---------------- epilogue warps: TMEM -> registers -> bf16 NHWC
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int ri = row / a.bw, rj = row % a.bw;
+    // ---------------- epilogue warps: TMEM -> registers -> (staging smem -> TMA store | global)
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;     // TMEM lane quadrant this warp may access
+    const int grp = ew >> 2;    // two warps per quadrant split the (sub-tile, 16-column) units
+    const int nchunk = a.N / 16;
+    const int units = a.MT * nchunk;
+    const uint32_t row_bytes = (uint32_t)a.cbo * 2u;
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tc) {
       const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
       const int tw = tile % a.tiles_w;
       const int th = (tile / a.tiles_w) % a.tiles_h;
       const int n = tile / (a.tiles_w * a.tiles_h);
-      const int gi = th * a.bh + ri, gj = tw * a.bw + rj;
-      const bool valid = gi < a.gh && gj < a.gw;
-      const size_t opix = ((size_t)n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
-      __nv_bfloat16* yp = a.y + opix * a.y_cs;
+      const int b = a.staged ? (int)(tc % NS) : 0;
+      const uint32_t u = a.staged ? tc / NS : 0;
+      const uint32_t obuf = o_base + (uint32_t)b * a.out_buf_bytes;
+      if (a.staged) {
+        if (a.has_res)
+          mbar_wait(sfull_bar(b), u & 1u);           // residual tile landed
+        else
+          mbar_wait(sfree_bar(b), (u & 1u) ^ 1u);    // previous store out of this buffer drained
+      }
       mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.N;
-      for (int c0 = 0; c0 < a.N; c0 += 16) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
+      for (int un = grp; un < units; un += 2) {
+        const int m = un / nchunk;
+        const int c0 = (un % nchunk) * 16;
         uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
+        tmem_ld16(taddr + (uint32_t)(m * a.N + c0), r);
         tmem_ld_wait();
-        if (valid) {
+        if (c0 >= a.cout) continue;
+        const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cb = c0 + 8 * h;
-            if (cb < a.cout) {
-              float f[8];
+        for (int h = 0; h < 2; ++h) {
+          const int cb8 = c0 + 8 * h;
+          if (cb8 >= a.cout) continue;
+          float f[8];
+          {
+            const float4 s0 = lds_f4(prm_base + 4u * cb8), s1 = lds_f4(prm_base + 4u * cb8 + 16u);
+            const float4 h0 = lds_f4(prm_base + 1024u + 4u * cb8), h1 = lds_f4(prm_base + 1024u + 4u * cb8 + 16u);
+            f[0] = fmaf(__uint_as_float(r[8 * h + 0]), s0.x, h0.x);
+            f[1] = fmaf(__uint_as_float(r[8 * h + 1]), s0.y, h0.y);
+            f[2] = fmaf(__uint_as_float(r[8 * h + 2]), s0.z, h0.z);
+            f[3] = fmaf(__uint_as_float(r[8 * h + 3]), s0.w, h0.w);
+            f[4] = fmaf(__uint_as_float(r[8 * h + 4]), s1.x, h1.x);
+            f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
+            f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
+            f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
+          }
+          if (a.staged) {
+            const int blk = cb8 / a.cbo;
+            uint32_t off = (uint32_t)R * row_bytes + (uint32_t)(cb8 - blk * a.cbo) * 2u;
+            off ^= ((off >> 7) & a.out_swz_mask) << 4;
+            const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
+            if (a.has_res) {
+              float g[8];
+              bf16x8_to_float(lds128(saddr), g);
 #pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += g[j];
+            }
+            if (a.ep.act == ESN_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            } else if (a.ep.act == ESN_ACT_PRELU) {
+              const float4 a0 = lds_f4(prm_base + 2048u + 4u * cb8), a1 = lds_f4(prm_base + 2048u + 4u * cb8 + 16u);
+              const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
+            }
+            sts128(saddr, float_to_bf16x8(f));
+          } else {
+            // fallback: per-thread global stores (output channel count not a multiple of 8)
+            const int ri = R / a.bw, rj = R % a.bw;
+            const int gi = th * a.bh + ri, gj = tw * a.bw + rj;
+            if (gi < a.gh && gj < a.gw) {
+              const size_t opix = ((size_t)n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
+              __nv_bfloat16* yp = a.y + opix * a.y_cs;
               for (int j = 0; j < 8; ++j) {
-                const int c = min(cb + j, a.cout - 1);
-                const float sc = a.ep.scale ? __ldg(a.ep.scale + c) : 1.f;
-                const float sh = a.ep.shift ? __ldg(a.ep.shift + c) : 0.f;
-                f[j] = __uint_as_float(r[8 * h + j]) * sc + sh;
-              }
-              const bool full8 = cb + 8 <= a.cout;
-              if (a.ep.res) {
-                const __nv_bfloat16* rp =
-                    reinterpret_cast<const __nv_bfloat16*>(a.ep.res) + opix * a.ep.res_cstride + cb;
-                if (full8) {
-                  float g[8];
-                  bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(rp)), g);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] += g[j];
-                } else {
-                  for (int j = 0; j < 8; ++j)
-                    if (cb + j < a.cout) f[j] += __bfloat162float(rp[j]);
+                const int c = cb8 + j;
+                if (c < a.cout) {
+                  float v = f[j];
+                  if (a.ep.res)
+                    v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
+                  v = apply_act(v, a.ep.act, prm[512 + c]);
+                  yp[c] = __float2bfloat16_rn(v);
                 }
-              }
-              if (a.ep.act == ESN_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-              } else if (a.ep.act == ESN_ACT_PRELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float al = __ldg(a.ep.alpha + min(cb + j, a.cout - 1));
-                  f[j] = f[j] >= 0.f ? f[j] : f[j] * al;
-                }
-              }
-              if (full8) {
-                *reinterpret_cast<uint4*>(yp + cb) = float_to_bf16x8(f);
-              } else {
-                for (int j = 0; j < 8; ++j)
-                  if (cb + j < a.cout) yp[cb + j] = __float2bfloat16_rn(f[j]);
               }
             }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      mbar_arrive(tempty_bar(acc));   // accumulators drained (count = 256)
+      if (a.staged) {
+        fence_proxy_async();          // my st.shared writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (threadIdx.x == kEpiWarp0 * 32) {
+          for (int cb = 0; cb < a.ncb; ++cb)
+            tma_store_4d(&a.tmY, obuf + (uint32_t)cb * a.out_block_bytes, cb * a.cbo, tw * a.bw, th * a.bh, n);
+          tma_store_commit();
+          // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
+          if (NS == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>();
+          if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree_bar((tc + 1) % NS));
+        }
+      }
     }
+    if (a.staged && threadIdx.x == kEpiWarp0 * 32) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -355,7 +473,8 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   const EsnTensor& y = p->y;
   if (!esn_valid_nhwc(x) || !esn_valid_nhwc(y)) return ESN_ERR_BAD_ARG;
   if (x.dtype != ESN_BF16 || y.dtype != ESN_BF16 || p->groups != 1) return ESN_ERR_UNSUPPORTED;
-  if (p->ep.residual.ptr && p->ep.residual.dtype != ESN_BF16) return ESN_ERR_UNSUPPORTED;
+  const EsnTensor& res = p->ep.residual;
+  if (res.ptr && res.dtype != ESN_BF16) return ESN_ERR_UNSUPPORTED;
   int rc = esn_check_epilogue(p->ep, y);
   if (rc) return rc;
   const int Cin = x.c, Cout = y.c, N = p->cout_pad;
@@ -371,7 +490,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   if (x.c_stride % 8 || y.c_stride % 8 || ((uintptr_t)x.ptr % 16) || ((uintptr_t)y.ptr % 16) ||
       ((uintptr_t)p->w % 16))
     return ESN_ERR_ALIGN;
-  if (p->ep.residual.ptr && (p->ep.residual.c_stride % 8 || ((uintptr_t)p->ep.residual.ptr % 16))) return ESN_ERR_ALIGN;
+  if (res.ptr && (res.c_stride % 8 || ((uintptr_t)res.ptr % 16))) return ESN_ERR_ALIGN;
   if (x.n != y.n) return ESN_ERR_BAD_SHAPE;
   const int ntaps_all = p->kh * p->kw;
   if (ntaps_all > kMaxTaps) return ESN_ERR_UNSUPPORTED;
@@ -403,18 +522,30 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   a.nkb = nkb;
   a.N = N;
   a.cout = Cout;
-  a.stage_bytes = kTileM * row_bytes;
+
+  // M sub-tiles per pipeline stage: keep every stage 16 KB so small-C layers amortise the
+  // per-tile barrier round trips over 4x (C=16) / 2x (C=32) more pixels
+  int MT = 64 / KB;
+  while (MT > 1 && MT * N > 256) MT >>= 1;
+  a.MT = MT;
+  const int rows = MT * kTileM;
+  a.stage_bytes = rows * row_bytes;
   a.wblock_bytes = N * row_bytes;
 
   // iteration grid: output positions (conv) or input positions (one transposed-conv phase)
   const int gh = p->transposed ? x.h : y.h, gw = p->transposed ? x.w : y.w;
-  int bw = 128;
-  if (gw <= 64) {
+  int bw;
+  if (gw > 128 && MT >= 2) {
+    bw = 256;
+  } else if (gw > 64) {
+    bw = 128;
+  } else {
     bw = 8;
     while (bw < gw) bw <<= 1;
   }
   a.bw = bw;
-  a.bh = kTileM / bw;
+  a.bh = rows / bw;
+  if (a.bh > 256) return ESN_ERR_UNSUPPORTED;
   a.gh = gh;
   a.gw = gw;
   a.tiles_w = esn_cdiv(gw, a.bw);
@@ -425,6 +556,26 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   a.Wy = y.w;
   a.y_cs = y.c_stride;
   a.ep = make_epi(p->ep);
+
+  // staged epilogue (swizzled smem tile + TMA store, residual prefetched by TMA into the same tile)
+  a.staged = (Cout % 8 == 0) && (Cout <= 64 || Cout % 64 == 0);
+  a.has_res = res.ptr != nullptr;
+  CUtensorMapSwizzle oswz = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (a.staged) {
+    a.cbo = Cout <= 64 ? Cout : 64;
+    a.ncb = Cout / a.cbo;
+    a.out_block_bytes = (uint32_t)rows * a.cbo * 2;
+    a.out_buf_bytes = a.ncb * a.out_block_bytes;
+    const int rb = a.cbo * 2;
+    if (rb == 128) { oswz = CU_TENSOR_MAP_SWIZZLE_128B; a.out_swz_mask = 7; }
+    else if (rb == 64) { oswz = CU_TENSOR_MAP_SWIZZLE_64B; a.out_swz_mask = 3; }
+    else if (rb == 32) { oswz = CU_TENSOR_MAP_SWIZZLE_32B; a.out_swz_mask = 1; }
+    else { a.out_swz_mask = 0; }
+    a.NS = a.out_buf_bytes <= 16384 ? 4 : 2;
+  } else {
+    a.cbo = 8;  // unused
+    a.NS = 0;
+  }
 
   // ---- activation tensor map (5-D)
   {
@@ -494,21 +645,42 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     a.sx = a.sy;
     a.oy = p->transposed ? pa : 0;
     a.ox = p->transposed ? pb : 0;
+
+    if (a.staged) {  // output / residual maps over this phase's (strided) output positions
+      for (int which = 0; which < (a.has_res ? 2 : 1); ++which) {
+        const EsnTensor& t = which ? res : y;
+        const cuuint64_t cs = (cuuint64_t)t.c_stride;
+        const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)x.n};
+        const cuuint64_t strides[3] = {cs * 2 * a.sx, (cuuint64_t)y.w * cs * 2 * a.sy, (cuuint64_t)y.h * y.w * cs * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)a.cbo, (cuuint32_t)a.bw, (cuuint32_t)a.bh, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        void* bp = reinterpret_cast<uint8_t*>(t.ptr) + ((size_t)a.oy * y.w + a.ox) * cs * 2;
+        if (encode(which ? &a.tmR : &a.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bp, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return ESN_ERR_CUDA;
+      }
+    }
+
     const uint32_t wbytes = (uint32_t)nt * nkb * a.wblock_bytes;
     a.w_region_bytes = (wbytes + 1023u) & ~1023u;
-    // shared memory plan: resident weights + A ring + barriers (+1 KB alignment slack)
-    const uint32_t fixed = a.w_region_bytes + 1024u + 256u;
-    const bool two_ctas = (fixed + 4u * a.stage_bytes <= 100u * 1024u) && (2 * N <= 256);
-    const uint32_t budget = two_ctas ? 110u * 1024u : (uint32_t)lim.max_smem;
-    if (fixed + 2u * a.stage_bytes > budget) return ESN_ERR_UNSUPPORTED;
-    int stages = (int)((budget - fixed) / a.stage_bytes);
-    if (stages > 8) stages = 8;
-    a.stages = stages;
+    // shared memory plan: resident weights + A ring + staging + params + barriers (+1 KB alignment slack)
+    for (;;) {
+      const uint32_t fixed = a.w_region_bytes + (uint32_t)a.NS * a.out_buf_bytes + 3072u + 256u + 1024u;
+      if (fixed + 2u * a.stage_bytes <= (uint32_t)lim.max_smem) {
+        int stages = (int)(((uint32_t)lim.max_smem - fixed) / a.stage_bytes);
+        a.stages = stages > 8 ? 8 : stages;
+        break;
+      }
+      if (a.NS == 4) { a.NS = 2; continue; }
+      return ESN_ERR_UNSUPPORTED;
+    }
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * N)) cols <<= 1;
+    while (cols < (uint32_t)(2 * MT * N)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t smem = fixed + (size_t)stages * a.stage_bytes;
-    int grid = lim.sms * (two_ctas ? 2 : 1);
+    const size_t smem = a.w_region_bytes + (size_t)a.NS * a.out_buf_bytes + 3072u + 256u + 1024u +
+                        (size_t)a.stages * a.stage_bytes;
+    int grid = lim.sms;
     if (grid > a.ntiles) grid = a.ntiles;
     conv_umma_kernel<<<grid, kThreads, smem, st>>>(a);
     ESN_CHECK_LAUNCH();

@@ -38,6 +38,11 @@ class EsnPool(C.Structure):
     _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("ep", EsnEpilogue)]
 
 
+class EsnStem(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("w", C.c_void_p), ("cconv", C.c_int32),
+                ("with_pool", C.c_int32), ("ep", EsnEpilogue)]
+
+
 class EsnDabPair(C.Structure):
     _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("prm", C.c_void_p),
                 ("dilation", C.c_int32), ("_pad", C.c_int32)]
@@ -58,6 +63,7 @@ class EsnCE(C.Structure):
 SYMBOLS = {
     "esn_conv2d_direct": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
     "esn_conv2d_umma": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_stem_conv3x3s2": (C.c_int, [C.POINTER(EsnStem), C.c_void_p]),
     "esn_maxpool2x2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
     "esn_avgpool3x3s2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
     "esn_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),

@@ -238,9 +238,25 @@ def umma_supported(prep, p):
         return False
     taps = prep.kh * prep.kw if not prep.transposed else 4
     kb = min(cin, 64)
-    if taps * cin * prep.cout_pad * 2 + 2 * 128 * kb * 2 + 4096 > 227 * 1024:
+    mt = 64 // kb
+    while mt > 1 and mt * prep.cout_pad > 256:
+        mt //= 2
+    staged = prep.cout % 8 == 0 and (prep.cout <= 64 or prep.cout % 64 == 0)
+    staging = 2 * mt * 128 * prep.cout * 2 if staged else 0
+    if taps * cin * prep.cout_pad * 2 + staging + 2 * mt * 128 * kb * 2 + 6144 > 226 * 1024:
         return False
     return True
+
+
+def stem_conv3x3s2(x, w_direct, cconv, with_pool, out, scale, shift, alpha, act):
+    """3x3/s2 stem conv (+ 2x2 max-pool concat) on the NCHW fp32 image -> NHWC `out`."""
+    p = L.EsnStem()
+    p.x, p.y = tdesc(x), tdesc(out)
+    p.w, p.cconv, p.with_pool = w_direct.data_ptr(), cconv, int(with_pool)
+    _epilogue(p.ep, scale, shift, alpha, act, None)
+    flops = 2 * out.shape[0] * out.shape[2] * out.shape[3] * cconv * 27
+    _call(L.lib.esn_stem_conv3x3s2, "esn_stem_conv3x3s2", (C.byref(p),), _nbytes(x) + _nbytes(out), flops)
+    return out
 
 
 def _pool_call(fn, name, x, out, scale, shift, alpha, act, residual=None):

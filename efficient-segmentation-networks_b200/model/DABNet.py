@@ -63,6 +63,16 @@ class Conv(PrepMixin, nn.Module):
             n, c, h, w = x.shape
             ho, wo = prep.out_hw(h, w)
             out = ops.new_act(n, prep.cout, ho, wo, torch.bfloat16, x.device)
+        c = self.conv
+        if (n_in == 3 and x is input and not ops.is_nhwc(x) and residual is None and c.kernel_size == (3, 3)
+                and c.stride == (2, 2) and c.padding == (1, 1) and c.dilation == (1, 1) and c.groups == 1
+                and prep.cout % 4 == 0 and prep.cout <= 32):
+            if out is None:
+                n, _, h, w = x.shape
+                ho, wo = prep.out_hw(h, w)
+                out = ops.new_act(n, prep.cout, ho, wo, ops.compute_dtype(x), x.device)
+            return ops.stem_conv3x3s2(x, prep.w_direct, prep.cout, False, out, prep.scale, prep.shift, prep.alpha,
+                                      prep.act)
         return ops.conv2d(x, prep, out=out, residual=residual)
 
 

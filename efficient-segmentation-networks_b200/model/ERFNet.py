@@ -42,7 +42,8 @@ class DownsamplerBlock(PrepMixin, nn.Module):
         scale, shift = ops.bn_affine(self.bn, device)
         nc = self.conv.out_channels
         conv = ops.ConvPrep(self.conv, scale[:nc], shift[:nc], ACT_RELU, device=device)
-        return conv, scale[nc:].contiguous(), shift[nc:].contiguous()
+        ps, pb = scale[nc:].contiguous(), shift[nc:].contiguous()
+        return conv, ps, pb, torch.cat([conv.scale, ps]).contiguous(), torch.cat([conv.shift, pb]).contiguous()
 
     def forward(self, input):
         _no_train(self)
@@ -51,10 +52,13 @@ class DownsamplerBlock(PrepMixin, nn.Module):
         x = input if (input.shape[1] < 8 and input.is_contiguous() and input.dtype == torch.float32
                       and not ops.is_nhwc(input)) else ops.as_act(input, dtype)
         ops.require_cuda(x, "DownsamplerBlock")
-        conv, pscale, pshift = self.prep(x.device)
+        conv, pscale, pshift, fscale, fshift = self.prep(x.device)
         n, c, h, w = x.shape
         nc = conv.cout
         y = ops.new_act(n, nc + c, h // 2, w // 2, dtype, x.device)
+        if c == 3 and not ops.is_nhwc(x) and (h | w) % 2 == 0 and (nc + c) % 4 == 0 and nc + c <= 32:
+            # network stem: conv + pool + BN + ReLU in one pass over the NCHW image
+            return ops.stem_conv3x3s2(x, conv.w_direct, nc, True, y, fscale, fshift, None, ACT_RELU)
         ops.conv2d(x, conv, out=y[:, :nc])
         ops.maxpool2x2(x, y[:, nc:], pscale, pshift, None, ACT_RELU)
         return y

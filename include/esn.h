@@ -106,6 +106,19 @@ int esn_conv2d_direct(const EsnConv* p, void* stream);
  * ESN_ERR_UNSUPPORTED for anything else (the host then calls esn_conv2d_direct). */
 int esn_conv2d_umma(const EsnConv* p, void* stream);
 
+/* Network stem on the caller's NCHW fp32 image (Cin = 3): Conv2d(3, cconv, 3, stride 2, pad 1)
+ * [ || MaxPool2d(2,2) -> concat ] -> per-channel affine (bias + eval BN) -> activation -> NHWC.
+ * Replaces ERFNet.py:24-27 for DownsamplerBlock(3,16) (cconv 13 + 3 pooled channels) and
+ * DABNet.py:132 Conv(3,32,3,2)+BNPReLU.  w: fp32 [9][3][cconv]; ep.scale/shift/alpha: [y.c]. */
+typedef struct EsnStem {
+  EsnTensor x, y;
+  const float* w;
+  int32_t cconv;
+  int32_t with_pool;
+  EsnEpilogue ep;
+} EsnStem;
+int esn_stem_conv3x3s2(const EsnStem* p, void* stream);
+
 /* MaxPool2d(2, stride 2) followed by the per-channel affine + activation of
  * the BatchNorm slice it is concatenated into.
  * Replaces the pool branch of ERFNet.py:24-27 (DownsamplerBlock) and
