@@ -31,19 +31,24 @@ constexpr int kTileM = 128;
 constexpr long long kSpinLimitCycles = 4000000000LL;  // ~2 s
 
 struct alignas(64) UmmaArgs {
-  CUtensorMap tmA;  // activations, 5-D
-  CUtensorMap tmB;  // weights, 2-D
-  CUtensorMap tmY;  // output, 4-D   (staged epilogue only)
-  CUtensorMap tmR;  // residual, 4-D (staged epilogue with residual only)
+  CUtensorMap tmA;   // activations, 5-D, main box
+  CUtensorMap tmAh;  // activations, 5-D, tail box of the horizontal-reuse window
+  CUtensorMap tmB;   // weights, 2-D
+  CUtensorMap tmY;   // output, 4-D   (staged epilogue only)
+  CUtensorMap tmR;   // residual, 4-D (staged epilogue with residual only)
+  int mode, nunits;
   int ntaps, nkb, kb_elems, N, cout, MT;
-  int bw, bh, tiles_w, tiles_h, ntiles, gh, gw;
+  int bw, bh, tiles_w, tiles_h, gh, gw;
+  int a_boxw, a_nbox, o_boxw, o_nbox;
+  int hs_d, hs_pad;                  // MODE_HREUSE: tap spacing / left padding in pixels
+  int vr_d, vr_pad, vr_L, vr_nseg;   // MODE_VREUSE: row stride, top padding, outputs per unit, segments
   int tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_par[kMaxTaps], tap_coff[kMaxTaps], tap_wrow[kMaxTaps];
   __nv_bfloat16* y;
   int Hy, Wy, y_cs, sy, oy, sx, ox;
   EpiArgs ep;
   int staged, has_res, stages, NS;
   int cbo, ncb;                      // staged epilogue: channels per 128B-wide column block, #blocks
-  uint32_t stage_bytes, wblock_bytes, w_region_bytes, out_block_bytes, out_buf_bytes, out_swz_mask;
+  uint32_t load_bytes, stage_bytes, wblock_bytes, w_region_bytes, out_block_bytes, out_buf_bytes, out_swz_mask;
   uint32_t idesc, desc_hi;           // instruction descriptor; upper 32 bits of the smem descriptors
   uint32_t tmem_cols;
 };
@@ -164,10 +169,53 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t desc_
 }
 
 // ------------------------------------------------------------------ kernel
+// Work decomposition.  A "unit" is what one CTA walks before moving on:
+//   MODE_GENERIC : one output tile (bh x bw positions), one TMA box per (tap, K block)
+//   MODE_HREUSE  : one output row tile (1 x bw); ONE box of bw+2d pixels per K block, the 1xk taps
+//                  read it through row-shifted UMMA descriptors (swizzle is a function of absolute
+//                  smem address bits, so any whole-row shift of the start address is legal)
+//   MODE_VREUSE  : L output row tiles h0, h0+d, h0+2d, ... of one column strip; input rows go
+//                  through the smem ring once each and serve as tap 0/1/2 of three outputs
 // Shared memory map (base aligned to 1024 B):
-//   [ weights: ntaps*nkb blocks of N x KB ]  [ A ring: stages x (MT*128 x KB) ]
-//   [ staging: NS x (ncb blocks of MT*128 x cbo) -- residual lands here, output leaves from here ]
-//   [ epilogue params: scale|shift|alpha, N floats each ]  [ mbarriers ]
+//   [ weights: ntaps*nkb blocks of N x KB ]  [ A ring: stages x stage_bytes ]
+//   [ staging: NS x (ncb blocks of rows x cbo) -- residual lands here, output leaves from here ]
+//   [ epilogue params: scale|shift|alpha ]  [ mbarriers ]
+enum { MODE_GENERIC = 0, MODE_HREUSE = 1, MODE_VREUSE = 2 };
+
+struct Unit {
+  int n, w0, h0, hstep, len;
+};
+
+__device__ __forceinline__ Unit decode_unit(const UmmaArgs& a, int u) {
+  Unit r;
+  if (a.mode == MODE_VREUSE) {
+    // u -> (n, tw, residue, segment); outputs h = res + (seg*L + i)*d
+    const int seg = u % a.vr_nseg;
+    int t = u / a.vr_nseg;
+    const int res = t % a.vr_d;
+    t /= a.vr_d;
+    const int tw = t % a.tiles_w;
+    r.n = t / a.tiles_w;
+    r.w0 = tw * a.bw;
+    const int cnt = (a.gh - res + a.vr_d - 1) / a.vr_d;  // outputs in this residue class
+    const int first = seg * a.vr_L;
+    r.len = cnt - first;
+    if (r.len > a.vr_L) r.len = a.vr_L;
+    if (r.len < 0) r.len = 0;
+    r.h0 = res + first * a.vr_d;
+    r.hstep = a.vr_d;
+  } else {
+    const int tw = u % a.tiles_w;
+    const int th = (u / a.tiles_w) % a.tiles_h;
+    r.n = u / (a.tiles_w * a.tiles_h);
+    r.w0 = tw * a.bw;
+    r.h0 = th * a.bh;
+    r.hstep = 0;
+    r.len = 1;
+  }
+  return r;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -194,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
+    if (a.mode == MODE_HREUSE) tma_prefetch_desc(&a.tmAh);
     if (a.staged) tma_prefetch_desc(&a.tmY);
     if (a.has_res && a.staged) tma_prefetch_desc(&a.tmR);
     for (int s = 0; s < S; ++s) {
@@ -228,32 +277,57 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int kiters = a.ntaps * a.nkb;  // smem stages consumed per tile
   const uint32_t acc_cols = (uint32_t)(a.MT * a.N);
+  const uint32_t rb = (uint32_t)a.kb_elems * 2u;  // bytes per A/B smem row
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: weights once, then the A ring
-      mbar_expect_tx(wfull_bar, (uint32_t)kiters * a.wblock_bytes);
+      mbar_expect_tx(wfull_bar, (uint32_t)(a.ntaps * a.nkb) * a.wblock_bytes);
       for (int t = 0; t < a.ntaps; ++t)
         for (int kb = 0; kb < a.nkb; ++kb)
           tma_load_2d(w_base + (uint32_t)(t * a.nkb + kb) * a.wblock_bytes, &a.tmB, wfull_bar, kb * a.kb_elems,
                       a.tap_wrow[t]);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const int tw = tile % a.tiles_w;
-        const int th = (tile / a.tiles_w) % a.tiles_h;
-        const int n = tile / (a.tiles_w * a.tiles_h);
-        for (int t = 0; t < a.ntaps; ++t) {
-          const int cw = tw * a.bw + a.tap_dx[t];
-          const int ch = th * a.bh + a.tap_dy[t];
+      for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        const Unit un = decode_unit(a, u);
+        if (un.len <= 0) continue;
+        if (a.mode == MODE_VREUSE) {
+          // rows h0-pad + j*d, j = 0..len+ntaps-2: one ring slot each, each row loaded exactly once
+          for (int j = 0; j < un.len + a.ntaps - 1; ++j, ++it) {
+            const int s = it % S;
+            mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+            mbar_expect_tx(full_bar(s), a.load_bytes);
+            const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
+            const int row = un.h0 + j * un.hstep - a.vr_pad;
+            for (int q = 0; q < a.a_nbox; ++q)
+              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * rb, &a.tmA, full_bar(s), 0, un.w0 + q * a.a_boxw, 0, row,
+                          un.n);
+          }
+        } else if (a.mode == MODE_HREUSE) {
           for (int kb = 0; kb < a.nkb; ++kb, ++it) {
             const int s = it % S;
-            const uint32_t ph = (it / S) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_expect_tx(full_bar(s), a.stage_bytes);
-            tma_load_5d(a_base + (uint32_t)s * a.stage_bytes, &a.tmA, full_bar(s), a.tap_coff[t] + kb * a.kb_elems, cw,
-                        a.tap_par[t], ch, n);
+            mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+            mbar_expect_tx(full_bar(s), a.load_bytes);
+            const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
+            const int c0 = kb * a.kb_elems;
+            const int wl = un.w0 - a.hs_pad;   // window [w0 - pad, w0 + bw + (k-1)d - pad)
+            for (int q = 0; q < a.a_nbox; ++q)
+              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * rb, &a.tmA, full_bar(s), c0, wl + q * a.a_boxw, 0, un.h0,
+                          un.n);
+            tma_load_5d(dst + (uint32_t)a.bw * rb, &a.tmAh, full_bar(s), c0, wl + a.bw, 0, un.h0, un.n);
+          }
+        } else {
+          for (int t = 0; t < a.ntaps; ++t) {
+            const int cw = un.w0 + a.tap_dx[t];
+            const int ch = un.h0 + a.tap_dy[t];
+            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+              const int s = it % S;
+              mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+              mbar_expect_tx(full_bar(s), a.load_bytes);
+              tma_load_5d(a_base + (uint32_t)s * a.stage_bytes, &a.tmA, full_bar(s), a.tap_coff[t] + kb * a.kb_elems,
+                          cw, a.tap_par[t], ch, un.n);
+            }
           }
         }
       }
@@ -264,30 +338,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
       const int ksteps = a.kb_elems / 16;
-      const uint32_t sub_bytes = (uint32_t)kTileM * a.kb_elems * 2u;  // one 128-row M sub-tile of a stage
+      const uint32_t sub_bytes = (uint32_t)kTileM * rb;  // one 128-row M sub-tile
       uint32_t it = 0, tc = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tc) {
-        const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), aph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_cols;
-        for (int ki = 0; ki < kiters; ++ki, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          mbar_wait(full_bar(s), ph);
+      for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        const Unit un = decode_unit(a, u);
+        if (un.len <= 0) continue;
+        for (int i = 0; i < un.len; ++i, ++tc) {
+          const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+          mbar_wait(tempty_bar(acc), aph ^ 1u);
           tc_fence_after();
-          const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
-          const uint32_t b_addr = w_base + (uint32_t)ki * a.wblock_bytes;
-          for (int m = 0; m < a.MT; ++m) {
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = make_desc(a_addr + m * sub_bytes + 32u * k, a.desc_hi);
-              const uint64_t bd = make_desc(b_addr + 32u * k, a.desc_hi);
-              umma_bf16(d_tmem + (uint32_t)(m * a.N), ad, bd, a.idesc, (ki | k) != 0 ? 1u : 0u);
+          const uint32_t d_tmem = tmem_base + acc * acc_cols;
+          if (a.mode == MODE_VREUSE) {
+            // tap t of output i lives in ring slot it+i+t
+            for (int t = 0; t < a.ntaps; ++t) {
+              const uint32_t jt = it + (uint32_t)(i + t);
+              const int s = jt % S;
+              if (i == 0 || t == a.ntaps - 1) {
+                mbar_wait(full_bar(s), (jt / S) & 1u);
+                tc_fence_after();
+              }
+              const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
+              const uint32_t b_addr = w_base + (uint32_t)t * a.wblock_bytes;
+              for (int m = 0; m < a.MT; ++m)
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(d_tmem + (uint32_t)(m * a.N), make_desc(a_addr + m * sub_bytes + 32u * k, a.desc_hi),
+                            make_desc(b_addr + 32u * k, a.desc_hi), a.idesc, (t | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar((it + (uint32_t)i) % S));  // oldest row is done once these MMAs retire
+            if (i == un.len - 1)
+              for (int t = 1; t < a.ntaps; ++t) umma_commit(empty_bar((it + (uint32_t)(i + t)) % S));
+          } else if (a.mode == MODE_HREUSE) {
+            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+              const int s = it % S;
+              mbar_wait(full_bar(s), (it / S) & 1u);
+              tc_fence_after();
+              const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
+              for (int t = 0; t < a.ntaps; ++t) {
+                const uint32_t a_t = a_addr + (uint32_t)(t * a.hs_d) * rb;   // row-shifted window
+                const uint32_t b_t = w_base + (uint32_t)(t * a.nkb + kb) * a.wblock_bytes;
+                for (int m = 0; m < a.MT; ++m)
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(d_tmem + (uint32_t)(m * a.N), make_desc(a_t + m * sub_bytes + 32u * k, a.desc_hi),
+                              make_desc(b_t + 32u * k, a.desc_hi), a.idesc, (kb | t | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(empty_bar(s));
+            }
+          } else {
+            const int kiters = a.ntaps * a.nkb;
+            for (int ki = 0; ki < kiters; ++ki, ++it) {
+              const int s = it % S;
+              mbar_wait(full_bar(s), (it / S) & 1u);
+              tc_fence_after();
+              const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
+              const uint32_t b_addr = w_base + (uint32_t)ki * a.wblock_bytes;
+              for (int m = 0; m < a.MT; ++m)
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(d_tmem + (uint32_t)(m * a.N), make_desc(a_addr + m * sub_bytes + 32u * k, a.desc_hi),
+                            make_desc(b_addr + 32u * k, a.desc_hi), a.idesc, (ki | k) != 0 ? 1u : 0u);
+              umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
             }
           }
-          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          umma_commit(tfull_bar(acc));  // accumulators ready for the epilogue
         }
-        umma_commit(tfull_bar(acc));  // accumulators ready for the epilogue
+        if (a.mode == MODE_VREUSE) it += (uint32_t)(un.len + a.ntaps - 1);
       }
     }
   } else if (warp == 2) {
@@ -295,17 +408,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       // ---------------- residual producer: the residual tile lands in the staging buffer the
       // epilogue will overwrite in place with the output tile
       uint32_t tc = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tc) {
-        const int tw = tile % a.tiles_w;
-        const int th = (tile / a.tiles_w) % a.tiles_h;
-        const int n = tile / (a.tiles_w * a.tiles_h);
-        const int b = tc % NS;
-        const uint32_t u = tc / NS;
-        mbar_wait(sfree_bar(b), (u & 1u) ^ 1u);
-        mbar_expect_tx(sfull_bar(b), a.out_buf_bytes);
-        for (int cb = 0; cb < a.ncb; ++cb)
-          tma_load_4d(o_base + (uint32_t)b * a.out_buf_bytes + (uint32_t)cb * a.out_block_bytes, &a.tmR, sfull_bar(b),
-                      cb * a.cbo, tw * a.bw, th * a.bh, n);
+      for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        const Unit un = decode_unit(a, u);
+        for (int i = 0; i < un.len; ++i, ++tc) {
+          const int b = tc % NS;
+          const uint32_t use = tc / NS;
+          mbar_wait(sfree_bar(b), (use & 1u) ^ 1u);
+          mbar_expect_tx(sfull_bar(b), a.out_buf_bytes);
+          const int h = un.h0 + i * un.hstep;
+          for (int cb = 0; cb < a.ncb; ++cb)
+            for (int q = 0; q < a.o_nbox; ++q)
+              tma_load_4d(o_base + (uint32_t)b * a.out_buf_bytes + (uint32_t)cb * a.out_block_bytes +
+                              (uint32_t)(q * a.o_boxw) * (uint32_t)a.cbo * 2u,
+                          &a.tmR, sfull_bar(b), cb * a.cbo, un.w0 + q * a.o_boxw, h, un.n);
+        }
       }
     }
   } else {
@@ -314,105 +430,111 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int q = warp & 3;     // TMEM lane quadrant this warp may access
     const int grp = ew >> 2;    // two warps per quadrant split the (sub-tile, 16-column) units
     const int nchunk = a.N / 16;
-    const int units = a.MT * nchunk;
+    const int nwork = a.MT * nchunk;
     const uint32_t row_bytes = (uint32_t)a.cbo * 2u;
     uint32_t tc = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tc) {
-      const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-      const int tw = tile % a.tiles_w;
-      const int th = (tile / a.tiles_w) % a.tiles_h;
-      const int n = tile / (a.tiles_w * a.tiles_h);
-      const int b = a.staged ? (int)(tc % NS) : 0;
-      const uint32_t u = a.staged ? tc / NS : 0;
-      const uint32_t obuf = o_base + (uint32_t)b * a.out_buf_bytes;
-      if (a.staged) {
-        if (a.has_res)
-          mbar_wait(sfull_bar(b), u & 1u);           // residual tile landed
-        else
-          mbar_wait(sfree_bar(b), (u & 1u) ^ 1u);    // previous store out of this buffer drained
-      }
-      mbar_wait(tfull_bar(acc), aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
-      for (int un = grp; un < units; un += 2) {
-        const int m = un / nchunk;
-        const int c0 = (un % nchunk) * 16;
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(m * a.N + c0), r);
-        tmem_ld_wait();
-        if (c0 >= a.cout) continue;
-        const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
+    for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+      const Unit un = decode_unit(a, u);
+      for (int i = 0; i < un.len; ++i, ++tc) {
+        const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+        const int th0 = un.h0 + i * un.hstep;
+        const int b = a.staged ? (int)(tc % NS) : 0;
+        const uint32_t use = a.staged ? tc / NS : 0;
+        const uint32_t obuf = o_base + (uint32_t)b * a.out_buf_bytes;
+        if (a.staged) {
+          if (a.has_res)
+            mbar_wait(sfull_bar(b), use & 1u);           // residual tile landed
+          else
+            mbar_wait(sfree_bar(b), (use & 1u) ^ 1u);    // previous store out of this buffer drained
+        }
+        mbar_wait(tfull_bar(acc), aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
+        for (int wk = grp; wk < nwork; wk += 2) {
+          const int m = wk / nchunk;
+          const int c0 = (wk % nchunk) * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)(m * a.N + c0), r);
+          tmem_ld_wait();
+          if (c0 >= a.cout) continue;
+          const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cb8 = c0 + 8 * h;
-          if (cb8 >= a.cout) continue;
-          float f[8];
-          {
-            const float4 s0 = lds_f4(prm_base + 4u * cb8), s1 = lds_f4(prm_base + 4u * cb8 + 16u);
-            const float4 h0 = lds_f4(prm_base + 1024u + 4u * cb8), h1 = lds_f4(prm_base + 1024u + 4u * cb8 + 16u);
-            f[0] = fmaf(__uint_as_float(r[8 * h + 0]), s0.x, h0.x);
-            f[1] = fmaf(__uint_as_float(r[8 * h + 1]), s0.y, h0.y);
-            f[2] = fmaf(__uint_as_float(r[8 * h + 2]), s0.z, h0.z);
-            f[3] = fmaf(__uint_as_float(r[8 * h + 3]), s0.w, h0.w);
-            f[4] = fmaf(__uint_as_float(r[8 * h + 4]), s1.x, h1.x);
-            f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
-            f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
-            f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
-          }
-          if (a.staged) {
-            const int blk = cb8 / a.cbo;
-            uint32_t off = (uint32_t)R * row_bytes + (uint32_t)(cb8 - blk * a.cbo) * 2u;
-            off ^= ((off >> 7) & a.out_swz_mask) << 4;
-            const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
-            if (a.has_res) {
-              float g[8];
-              bf16x8_to_float(lds128(saddr), g);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += g[j];
+          for (int h = 0; h < 2; ++h) {
+            const int cb8 = c0 + 8 * h;
+            if (cb8 >= a.cout) continue;
+            float f[8];
+            {
+              const float4 s0 = lds_f4(prm_base + 4u * cb8), s1 = lds_f4(prm_base + 4u * cb8 + 16u);
+              const float4 h0 = lds_f4(prm_base + 1024u + 4u * cb8), h1 = lds_f4(prm_base + 1024u + 4u * cb8 + 16u);
+              f[0] = fmaf(__uint_as_float(r[8 * h + 0]), s0.x, h0.x);
+              f[1] = fmaf(__uint_as_float(r[8 * h + 1]), s0.y, h0.y);
+              f[2] = fmaf(__uint_as_float(r[8 * h + 2]), s0.z, h0.z);
+              f[3] = fmaf(__uint_as_float(r[8 * h + 3]), s0.w, h0.w);
+              f[4] = fmaf(__uint_as_float(r[8 * h + 4]), s1.x, h1.x);
+              f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
+              f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
+              f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
             }
-            if (a.ep.act == ESN_ACT_RELU) {
+            if (a.staged) {
+              const int blk = cb8 / a.cbo;
+              uint32_t off = (uint32_t)R * row_bytes + (uint32_t)(cb8 - blk * a.cbo) * 2u;
+              off ^= ((off >> 7) & a.out_swz_mask) << 4;
+              const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
+              if (a.has_res) {
+                float g[8];
+                bf16x8_to_float(lds128(saddr), g);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else if (a.ep.act == ESN_ACT_PRELU) {
-              const float4 a0 = lds_f4(prm_base + 2048u + 4u * cb8), a1 = lds_f4(prm_base + 2048u + 4u * cb8 + 16u);
-              const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                for (int j = 0; j < 8; ++j) f[j] += g[j];
+              }
+              if (a.ep.act == ESN_ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
-            }
-            sts128(saddr, float_to_bf16x8(f));
-          } else {
-            // fallback: per-thread global stores (output channel count not a multiple of 8)
-            const int ri = R / a.bw, rj = R % a.bw;
-            const int gi = th * a.bh + ri, gj = tw * a.bw + rj;
-            if (gi < a.gh && gj < a.gw) {
-              const size_t opix = ((size_t)n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
-              __nv_bfloat16* yp = a.y + opix * a.y_cs;
-              for (int j = 0; j < 8; ++j) {
-                const int c = cb8 + j;
-                if (c < a.cout) {
-                  float v = f[j];
-                  if (a.ep.res)
-                    v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
-                  v = apply_act(v, a.ep.act, prm[512 + c]);
-                  yp[c] = __float2bfloat16_rn(v);
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              } else if (a.ep.act == ESN_ACT_PRELU) {
+                const float4 a0 = lds_f4(prm_base + 2048u + 4u * cb8), a1 = lds_f4(prm_base + 2048u + 4u * cb8 + 16u);
+                const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
+              }
+              sts128(saddr, float_to_bf16x8(f));
+            } else {
+              // fallback: per-thread global stores (output channel count not a multiple of 8)
+              const int ri = R / a.bw, rj = R % a.bw;
+              const int gi = th0 + ri, gj = un.w0 + rj;
+              if (gi < a.gh && gj < a.gw) {
+                const size_t opix =
+                    ((size_t)un.n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
+                __nv_bfloat16* yp = a.y + opix * a.y_cs;
+                for (int j = 0; j < 8; ++j) {
+                  const int c = cb8 + j;
+                  if (c < a.cout) {
+                    float v = f[j];
+                    if (a.ep.res)
+                      v += __bfloat162float(
+                          reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
+                    v = apply_act(v, a.ep.act, prm[512 + c]);
+                    yp[c] = __float2bfloat16_rn(v);
+                  }
                 }
               }
             }
           }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));   // accumulators drained (count = 256)
-      if (a.staged) {
-        fence_proxy_async();          // my st.shared writes -> visible to the TMA (async proxy)
-        epi_bar_sync();
-        if (threadIdx.x == kEpiWarp0 * 32) {
-          for (int cb = 0; cb < a.ncb; ++cb)
-            tma_store_4d(&a.tmY, obuf + (uint32_t)cb * a.out_block_bytes, cb * a.cbo, tw * a.bw, th * a.bh, n);
-          tma_store_commit();
-          // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
-          if (NS == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>();
-          if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree_bar((tc + 1) % NS));
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));   // accumulators drained (count = 256)
+        if (a.staged) {
+          fence_proxy_async();          // my st.shared writes -> visible to the TMA (async proxy)
+          epi_bar_sync();
+          if (threadIdx.x == kEpiWarp0 * 32) {
+            for (int cb = 0; cb < a.ncb; ++cb)
+              for (int qb = 0; qb < a.o_nbox; ++qb)
+                tma_store_4d(&a.tmY,
+                             obuf + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
+                             cb * a.cbo, un.w0 + qb * a.o_boxw, th0, un.n);
+            tma_store_commit();
+            // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
+            if (NS == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>();
+            if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree_bar((tc + 1) % NS));
+          }
         }
       }
     }
@@ -523,34 +645,76 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   a.N = N;
   a.cout = Cout;
 
-  // M sub-tiles per pipeline stage: keep every stage 16 KB so small-C layers amortise the
+  // iteration grid: output positions (conv) or input positions (one transposed-conv phase)
+  const int gh = p->transposed ? x.h : y.h, gw = p->transposed ? x.w : y.w;
+  a.gh = gh;
+  a.gw = gw;
+
+  // M sub-tiles per pipeline stage: keep every stage ~16 KB so small-C layers amortise the
   // per-tile barrier round trips over 4x (C=16) / 2x (C=32) more pixels
   int MT = 64 / KB;
   while (MT > 1 && MT * N > 256) MT >>= 1;
+
+  // ---- mode: tap reuse needs row tiles (one image row segment per tile)
+  static const bool no_reuse = getenv("ESN_UMMA_NOREUSE") != nullptr;
+  const bool rowable = !no_reuse && gw >= 128 && !p->transposed && p->stride == 1;
+  a.mode = MODE_GENERIC;
+  if (rowable && p->kh == 1 && p->kw >= 2 && (p->kw - 1) * p->dil_w <= 256)
+    a.mode = MODE_HREUSE;
+  else if (rowable && p->kw == 1 && p->kh >= 2 && nkb == 1)
+    a.mode = MODE_VREUSE;
+  if (a.mode != MODE_GENERIC) {
+    while (MT > 1 && MT * kTileM > gw) MT >>= 1;
+    a.bw = MT * kTileM;
+    a.bh = 1;
+    a.a_boxw = a.bw > 256 ? 256 : a.bw;
+    a.a_nbox = a.bw / a.a_boxw;
+  } else {
+    int bw;
+    if (gw > 128 && MT >= 2) {
+      bw = 256;
+    } else if (gw > 64) {
+      bw = 128;
+    } else {
+      bw = 8;
+      while (bw < gw) bw <<= 1;
+    }
+    a.bw = bw;
+    a.bh = MT * kTileM / bw;
+    if (a.bh > 256) return ESN_ERR_UNSUPPORTED;
+    a.a_boxw = a.bw;
+    a.a_nbox = 1;
+  }
+  a.o_boxw = a.a_boxw;
+  a.o_nbox = a.a_nbox;
   a.MT = MT;
   const int rows = MT * kTileM;
-  a.stage_bytes = rows * row_bytes;
   a.wblock_bytes = N * row_bytes;
-
-  // iteration grid: output positions (conv) or input positions (one transposed-conv phase)
-  const int gh = p->transposed ? x.h : y.h, gw = p->transposed ? x.w : y.w;
-  int bw;
-  if (gw > 128 && MT >= 2) {
-    bw = 256;
-  } else if (gw > 64) {
-    bw = 128;
-  } else {
-    bw = 8;
-    while (bw < gw) bw <<= 1;
-  }
-  a.bw = bw;
-  a.bh = rows / bw;
-  if (a.bh > 256) return ESN_ERR_UNSUPPORTED;
-  a.gh = gh;
-  a.gw = gw;
   a.tiles_w = esn_cdiv(gw, a.bw);
   a.tiles_h = esn_cdiv(gh, a.bh);
-  a.ntiles = x.n * a.tiles_w * a.tiles_h;
+  if (a.mode == MODE_HREUSE) {
+    a.hs_d = p->dil_w;
+    a.hs_pad = p->pad_w;
+    const int extra = (p->kw - 1) * p->dil_w;
+    a.load_bytes = (uint32_t)(a.bw + extra) * row_bytes;
+    a.stage_bytes = (a.load_bytes + 1023u) & ~1023u;
+    a.nunits = x.n * a.tiles_w * a.tiles_h;
+  } else if (a.mode == MODE_VREUSE) {
+    a.vr_d = p->dil_h;
+    a.vr_pad = p->pad_h;
+    const int cnt = esn_cdiv(gh, a.vr_d);
+    int L = 32;
+    while (L > 4 && (long long)x.n * a.tiles_w * a.vr_d * esn_cdiv(cnt, L) < 3LL * lim.sms) L >>= 1;
+    a.vr_L = L;
+    a.vr_nseg = esn_cdiv(cnt, L);
+    a.load_bytes = (uint32_t)rows * row_bytes;
+    a.stage_bytes = a.load_bytes;
+    a.nunits = x.n * a.tiles_w * a.vr_d * a.vr_nseg;
+  } else {
+    a.load_bytes = (uint32_t)rows * row_bytes;
+    a.stage_bytes = a.load_bytes;
+    a.nunits = x.n * a.tiles_w * a.tiles_h;
+  }
   a.y = reinterpret_cast<__nv_bfloat16*>(y.ptr);
   a.Hy = y.h;
   a.Wy = y.w;
@@ -577,8 +741,8 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     a.NS = 0;
   }
 
-  // ---- activation tensor map (5-D)
-  {
+  // ---- activation tensor maps (5-D): main box, and the (k-1)*d-pixel tail box of the hreuse window
+  for (int which = 0; which < (a.mode == MODE_HREUSE ? 2 : 1); ++which) {
     const cuuint64_t cs = (cuuint64_t)x.c_stride;
     cuuint64_t dims[5], strides[4];
     if (!p->transposed && p->stride == 2) {
@@ -590,10 +754,12 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
       strides[0] = cs * 2; strides[1] = (cuuint64_t)x.w * cs * 2; strides[2] = (cuuint64_t)x.w * cs * 2;
       strides[3] = (cuuint64_t)x.h * x.w * cs * 2;
     }
-    const cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, 1};
+    const cuuint32_t bwid = which ? (cuuint32_t)((p->kw - 1) * p->dil_w) : (cuuint32_t)a.a_boxw;
+    const cuuint32_t box[5] = {(cuuint32_t)KB, bwid, 1, (cuuint32_t)a.bh, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    if (encode(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (encode(which ? &a.tmAh : &a.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x.ptr, dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ESN_ERR_CUDA;
   }
   // ---- weight tensor map (2-D): rows = tap*N + cout index, cols = Cin
@@ -652,7 +818,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
         const cuuint64_t cs = (cuuint64_t)t.c_stride;
         const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)x.n};
         const cuuint64_t strides[3] = {cs * 2 * a.sx, (cuuint64_t)y.w * cs * 2 * a.sy, (cuuint64_t)y.h * y.w * cs * 2};
-        const cuuint32_t box[4] = {(cuuint32_t)a.cbo, (cuuint32_t)a.bw, (cuuint32_t)a.bh, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)a.cbo, (cuuint32_t)a.o_boxw, (cuuint32_t)a.bh, 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         void* bp = reinterpret_cast<uint8_t*>(t.ptr) + ((size_t)a.oy * y.w + a.ox) * cs * 2;
         if (encode(which ? &a.tmR : &a.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bp, dims, strides, box, es,
@@ -665,9 +831,10 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     const uint32_t wbytes = (uint32_t)nt * nkb * a.wblock_bytes;
     a.w_region_bytes = (wbytes + 1023u) & ~1023u;
     // shared memory plan: resident weights + A ring + staging + params + barriers (+1 KB alignment slack)
+    const int min_stages = a.mode == MODE_VREUSE ? nt + 1 : 2;
     for (;;) {
       const uint32_t fixed = a.w_region_bytes + (uint32_t)a.NS * a.out_buf_bytes + 3072u + 256u + 1024u;
-      if (fixed + 2u * a.stage_bytes <= (uint32_t)lim.max_smem) {
+      if (fixed + (uint32_t)min_stages * a.stage_bytes <= (uint32_t)lim.max_smem) {
         int stages = (int)(((uint32_t)lim.max_smem - fixed) / a.stage_bytes);
         a.stages = stages > 8 ? 8 : stages;
         break;
@@ -681,7 +848,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     const size_t smem = a.w_region_bytes + (size_t)a.NS * a.out_buf_bytes + 3072u + 256u + 1024u +
                         (size_t)a.stages * a.stage_bytes;
     int grid = lim.sms;
-    if (grid > a.ntiles) grid = a.ntiles;
+    if (grid > a.nunits) grid = a.nunits;
     conv_umma_kernel<<<grid, kThreads, smem, st>>>(a);
     ESN_CHECK_LAUNCH();
   }

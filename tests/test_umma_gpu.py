@@ -17,6 +17,11 @@ CASES = [
     ("1x3_64", 64, 64, (1, 3), 1, (0, 1), (1, 1), False, 0, 2, 32, 128),
     ("3x1_128_d16", 128, 128, (3, 1), 1, (16, 0), (16, 1), False, 0, 2, 40, 64),
     ("1x3_128_d8", 128, 128, (1, 3), 1, (0, 8), (1, 8), False, 0, 2, 24, 72),
+    ("1x3_64_w256", 64, 64, (1, 3), 1, (0, 1), (1, 1), False, 0, 2, 8, 256),
+    ("1x3_64_d2_w256", 64, 64, (1, 3), 1, (0, 2), (1, 2), False, 0, 2, 8, 256),
+    ("1x3_128_d4_w256", 128, 128, (1, 3), 1, (0, 4), (1, 4), False, 0, 2, 8, 256),
+    ("1x3_128_d8_w256", 128, 128, (1, 3), 1, (0, 8), (1, 8), False, 0, 2, 8, 256),
+    ("1x3_128_d16_w256", 128, 128, (1, 3), 1, (0, 16), (1, 16), False, 0, 2, 8, 256),
     ("3x3_64_32", 64, 32, 3, 1, 1, 1, False, 0, 2, 20, 48),
     ("3x3_128_64", 128, 64, 3, 1, 1, 1, False, 0, 1, 16, 32),
     ("3x3_32_32", 32, 32, 3, 1, 1, 1, False, 0, 2, 32, 64),
@@ -25,6 +30,17 @@ CASES = [
     ("convT_128_64", 128, 64, 3, 2, 1, 1, True, 1, 2, 8, 24),
     ("convT_64_16", 64, 16, 3, 2, 1, 1, True, 1, 2, 12, 130),
     ("1x1_64_29", 64, 29, 1, 1, 0, 1, False, 0, 2, 9, 33),
+    # tap-reuse modes (row tiles): shifted-window descriptors on 32B / 64B / 128B swizzled tiles
+    ("h_1x3_16_w512", 16, 16, (1, 3), 1, (0, 1), (1, 1), False, 0, 2, 6, 512),
+    ("h_1x3_16_w640", 16, 16, (1, 3), 1, (0, 1), (1, 1), False, 0, 1, 5, 640),
+    ("h_1x3_32_w256", 32, 32, (1, 3), 1, (0, 2), (1, 2), False, 0, 2, 6, 256),
+    ("h_1x5_32_w128", 32, 32, (1, 5), 1, (0, 2), (1, 1), False, 0, 2, 6, 128),
+    ("h_1x3_128_w200", 128, 128, (1, 3), 1, (0, 4), (1, 4), False, 0, 2, 5, 200),
+    ("v_3x1_64_h70", 64, 64, (3, 1), 1, (1, 0), (1, 1), False, 0, 2, 70, 128),
+    ("v_3x1_64_d2", 64, 64, (3, 1), 1, (2, 0), (2, 1), False, 0, 2, 37, 256),
+    ("v_3x1_16_w512", 16, 16, (3, 1), 1, (1, 0), (1, 1), False, 0, 2, 19, 512),
+    ("v_5x1_32", 32, 32, (5, 1), 1, (2, 0), (1, 1), False, 0, 2, 21, 128),
+    ("v_3x1_64_d16", 64, 64, (3, 1), 1, (16, 0), (16, 1), False, 0, 1, 40, 128),
 ]
 
 
