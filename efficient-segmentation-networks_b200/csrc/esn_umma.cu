@@ -42,6 +42,7 @@ struct alignas(64) UmmaArgs {
   int a_boxw, a_nbox, o_boxw, o_nbox;
   int hs_d, hs_pad;                  // MODE_HREUSE: tap spacing / left padding in pixels
   int vr_d, vr_pad, vr_L, vr_nseg;   // MODE_VREUSE: row stride, top padding, outputs per unit, segments
+  int vr_cnt, vr_rem;                // rows of the longest residue class; residues >= vr_rem have one less
   int tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_par[kMaxTaps], tap_coff[kMaxTaps], tap_wrow[kMaxTaps];
   __nv_bfloat16* y;
   int Hy, Wy, y_cs, sy, oy, sx, ox;
@@ -171,52 +172,92 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t desc_
 // ------------------------------------------------------------------ kernel
 // Work decomposition.  A "unit" is what one CTA walks before moving on:
 //   MODE_GENERIC : one output tile (bh x bw positions), one TMA box per (tap, K block)
-//   MODE_HREUSE  : one output row tile (1 x bw); ONE box of bw+2d pixels per K block, the 1xk taps
-//                  read it through row-shifted UMMA descriptors (swizzle is a function of absolute
-//                  smem address bits, so any whole-row shift of the start address is legal)
+//   MODE_HREUSE  : one output row tile (1 x bw); ONE box of bw+(k-1)d pixels per K block, the 1xk
+//                  taps read it through row-shifted UMMA descriptors (the swizzle is a function of
+//                  absolute smem address bits, so any whole-row shift of the start address is legal
+//                  with base_offset = 0 -- measured on B200)
 //   MODE_VREUSE  : L output row tiles h0, h0+d, h0+2d, ... of one column strip; input rows go
 //                  through the smem ring once each and serve as tap 0/1/2 of three outputs
+// Every CTA owns a contiguous range of units and walks it with an incremental iterator (no
+// divisions on the hot path); stage / phase counters are running registers.
 // Shared memory map (base aligned to 1024 B):
 //   [ weights: ntaps*nkb blocks of N x KB ]  [ A ring: stages x stage_bytes ]
 //   [ staging: NS x (ncb blocks of rows x cbo) -- residual lands here, output leaves from here ]
 //   [ epilogue params: scale|shift|alpha ]  [ mbarriers ]
 enum { MODE_GENERIC = 0, MODE_HREUSE = 1, MODE_VREUSE = 2 };
 
-struct Unit {
-  int n, w0, h0, hstep, len;
+template <int MODE>
+struct UnitIter {
+  int n, tw, th, res, seg;   // th: generic/hreuse tile row index; res/seg: vreuse residue and segment
+  int w0, h0, hstep, len;
+  __device__ __forceinline__ void set(const UmmaArgs& a) {
+    w0 = tw * a.bw;
+    if (MODE == MODE_VREUSE) {
+      const int cnt = a.vr_cnt - (res >= a.vr_rem ? 1 : 0);
+      const int first = seg * a.vr_L;
+      len = min(cnt - first, a.vr_L);
+      h0 = res + first * a.vr_d;
+      hstep = a.vr_d;
+    } else {
+      h0 = th * a.bh;
+      hstep = 0;
+      len = 1;
+    }
+  }
+  __device__ __forceinline__ void init(const UmmaArgs& a, int u) {
+    th = res = seg = 0;
+    if (MODE == MODE_VREUSE) {
+      seg = u % a.vr_nseg;
+      int t = u / a.vr_nseg;
+      res = t % a.vr_d;
+      t /= a.vr_d;
+      tw = t % a.tiles_w;
+      n = t / a.tiles_w;
+    } else {
+      tw = u % a.tiles_w;
+      const int t = u / a.tiles_w;
+      th = t % a.tiles_h;
+      n = t / a.tiles_h;
+    }
+    set(a);
+  }
+  __device__ __forceinline__ void next(const UmmaArgs& a) {
+    if (MODE == MODE_VREUSE) {
+      if (++seg == a.vr_nseg) {
+        seg = 0;
+        if (++res == a.vr_d) {
+          res = 0;
+          if (++tw == a.tiles_w) { tw = 0; ++n; }
+        }
+      }
+    } else {
+      if (++tw == a.tiles_w) {
+        tw = 0;
+        if (++th == a.tiles_h) { th = 0; ++n; }
+      }
+    }
+    set(a);
+  }
 };
 
-__device__ __forceinline__ Unit decode_unit(const UmmaArgs& a, int u) {
-  Unit r;
-  if (a.mode == MODE_VREUSE) {
-    // u -> (n, tw, residue, segment); outputs h = res + (seg*L + i)*d
-    const int seg = u % a.vr_nseg;
-    int t = u / a.vr_nseg;
-    const int res = t % a.vr_d;
-    t /= a.vr_d;
-    const int tw = t % a.tiles_w;
-    r.n = t / a.tiles_w;
-    r.w0 = tw * a.bw;
-    const int cnt = (a.gh - res + a.vr_d - 1) / a.vr_d;  // outputs in this residue class
-    const int first = seg * a.vr_L;
-    r.len = cnt - first;
-    if (r.len > a.vr_L) r.len = a.vr_L;
-    if (r.len < 0) r.len = 0;
-    r.h0 = res + first * a.vr_d;
-    r.hstep = a.vr_d;
-  } else {
-    const int tw = u % a.tiles_w;
-    const int th = (u / a.tiles_w) % a.tiles_h;
-    r.n = u / (a.tiles_w * a.tiles_h);
-    r.w0 = tw * a.bw;
-    r.h0 = th * a.bh;
-    r.hstep = 0;
-    r.len = 1;
-  }
-  return r;
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 
+template <int KB, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
+  constexpr int KSTEPS = KB / 16;
+  constexpr uint32_t RB = KB * 2u;                 // bytes per A/B smem row
+  constexpr uint32_t SUB16 = (kTileM * RB) >> 4;   // one 128-row M sub-tile, in 16 B descriptor units
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -226,13 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const uint32_t o_base = a_base + (uint32_t)S * a.stage_bytes;
   const uint32_t prm_base = o_base + (uint32_t)NS * a.out_buf_bytes;
   const uint32_t bar_base = prm_base + 3u * 256u * 4u;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8u * S;
   const uint32_t wfull_bar = bar_base + 8u * (2 * S);
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + 1 + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 3 + b); };
-  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * S + 5 + b); };
-  auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * S + 9 + b); };
+  const uint32_t tfull0 = bar_base + 8u * (2 * S + 1), tempty0 = bar_base + 8u * (2 * S + 3);
+  const uint32_t sfull0 = bar_base + 8u * (2 * S + 5), sfree0 = bar_base + 8u * (2 * S + 9);
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 13);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* prm = reinterpret_cast<float*>(smem_raw + (prm_base - raw));
@@ -242,21 +280,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
-    if (a.mode == MODE_HREUSE) tma_prefetch_desc(&a.tmAh);
+    if (MODE == MODE_HREUSE) tma_prefetch_desc(&a.tmAh);
     if (a.staged) tma_prefetch_desc(&a.tmY);
     if (a.has_res && a.staged) tma_prefetch_desc(&a.tmR);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full0 + 8u * s, 1);
+      mbar_init(empty0 + 8u * s, 1);
     }
     mbar_init(wfull_bar, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), kEpiThreads);
+      mbar_init(tfull0 + 8u * b, 1);
+      mbar_init(tempty0 + 8u * b, kEpiThreads / 32);
     }
     for (int b = 0; b < 4; ++b) {
-      mbar_init(sfull_bar(b), 1);
-      mbar_init(sfree_bar(b), 1);
+      mbar_init(sfull0 + 8u * b, 1);
+      mbar_init(sfree0 + 8u * b, 1);
     }
     fence_barrier_init();
   }
@@ -277,268 +315,300 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // contiguous unit range of this CTA
+  const int u_begin = (int)(((long long)a.nunits * blockIdx.x) / gridDim.x);
+  const int u_end = (int)(((long long)a.nunits * (blockIdx.x + 1)) / gridDim.x);
   const uint32_t acc_cols = (uint32_t)(a.MT * a.N);
-  const uint32_t rb = (uint32_t)a.kb_elems * 2u;  // bytes per A/B smem row
+  const int ntaps = a.ntaps, nkb = a.nkb, MT = a.MT;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && u_begin < u_end) {
       // ---------------- TMA producer: weights once, then the A ring
-      mbar_expect_tx(wfull_bar, (uint32_t)(a.ntaps * a.nkb) * a.wblock_bytes);
-      for (int t = 0; t < a.ntaps; ++t)
-        for (int kb = 0; kb < a.nkb; ++kb)
-          tma_load_2d(w_base + (uint32_t)(t * a.nkb + kb) * a.wblock_bytes, &a.tmB, wfull_bar, kb * a.kb_elems,
-                      a.tap_wrow[t]);
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-        const Unit un = decode_unit(a, u);
+      mbar_expect_tx(wfull_bar, (uint32_t)(ntaps * nkb) * a.wblock_bytes);
+      for (int t = 0; t < ntaps; ++t)
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(w_base + (uint32_t)(t * nkb + kb) * a.wblock_bytes, &a.tmB, wfull_bar, kb * KB, a.tap_wrow[t]);
+      int s = 0;
+      uint32_t ph = 0;   // parity of the phase the consumer completes next on stage s
+      UnitIter<MODE> un;
+      un.init(a, u_begin);
+      for (int u = u_begin; u < u_end; ++u, un.next(a)) {
         if (un.len <= 0) continue;
-        if (a.mode == MODE_VREUSE) {
+        if (MODE == MODE_VREUSE) {
           // rows h0-pad + j*d, j = 0..len+ntaps-2: one ring slot each, each row loaded exactly once
-          for (int j = 0; j < un.len + a.ntaps - 1; ++j, ++it) {
-            const int s = it % S;
-            mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
-            mbar_expect_tx(full_bar(s), a.load_bytes);
+          int row = un.h0 - a.vr_pad;
+          for (int j = 0; j < un.len + ntaps - 1; ++j, row += un.hstep) {
+            mbar_wait(empty0 + 8u * s, ph ^ 1u);
+            mbar_expect_tx(full0 + 8u * s, a.load_bytes);
             const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
-            const int row = un.h0 + j * un.hstep - a.vr_pad;
             for (int q = 0; q < a.a_nbox; ++q)
-              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * rb, &a.tmA, full_bar(s), 0, un.w0 + q * a.a_boxw, 0, row,
+              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, 0, un.w0 + q * a.a_boxw, 0, row,
                           un.n);
+            if (++s == S) { s = 0; ph ^= 1u; }
           }
-        } else if (a.mode == MODE_HREUSE) {
-          for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-            const int s = it % S;
-            mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
-            mbar_expect_tx(full_bar(s), a.load_bytes);
+        } else if (MODE == MODE_HREUSE) {
+          const int wl = un.w0 - a.hs_pad;   // window [w0 - pad, w0 + bw + (k-1)d - pad)
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(empty0 + 8u * s, ph ^ 1u);
+            mbar_expect_tx(full0 + 8u * s, a.load_bytes);
             const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
-            const int c0 = kb * a.kb_elems;
-            const int wl = un.w0 - a.hs_pad;   // window [w0 - pad, w0 + bw + (k-1)d - pad)
             for (int q = 0; q < a.a_nbox; ++q)
-              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * rb, &a.tmA, full_bar(s), c0, wl + q * a.a_boxw, 0, un.h0,
-                          un.n);
-            tma_load_5d(dst + (uint32_t)a.bw * rb, &a.tmAh, full_bar(s), c0, wl + a.bw, 0, un.h0, un.n);
+              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, kb * KB, wl + q * a.a_boxw, 0,
+                          un.h0, un.n);
+            tma_load_5d(dst + (uint32_t)a.bw * RB, &a.tmAh, full0 + 8u * s, kb * KB, wl + a.bw, 0, un.h0, un.n);
+            if (++s == S) { s = 0; ph ^= 1u; }
           }
         } else {
-          for (int t = 0; t < a.ntaps; ++t) {
+          for (int t = 0; t < ntaps; ++t) {
             const int cw = un.w0 + a.tap_dx[t];
             const int ch = un.h0 + a.tap_dy[t];
-            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-              const int s = it % S;
-              mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
-              mbar_expect_tx(full_bar(s), a.load_bytes);
-              tma_load_5d(a_base + (uint32_t)s * a.stage_bytes, &a.tmA, full_bar(s), a.tap_coff[t] + kb * a.kb_elems,
-                          cw, a.tap_par[t], ch, un.n);
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(empty0 + 8u * s, ph ^ 1u);
+              mbar_expect_tx(full0 + 8u * s, a.load_bytes);
+              tma_load_5d(a_base + (uint32_t)s * a.stage_bytes, &a.tmA, full0 + 8u * s, a.tap_coff[t] + kb * KB, cw,
+                          a.tap_par[t], ch, un.n);
+              if (++s == S) { s = 0; ph ^= 1u; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
+    if (lane == 0 && u_begin < u_end) {
+      // ---------------- MMA issuer (single thread): descriptors advanced with 32-bit adds
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
-      const int ksteps = a.kb_elems / 16;
-      const uint32_t sub_bytes = (uint32_t)kTileM * rb;  // one 128-row M sub-tile
-      uint32_t it = 0, tc = 0;
-      for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-        const Unit un = decode_unit(a, u);
+      const uint32_t dhi = a.desc_hi, idesc = a.idesc;
+      const uint32_t w_lo = desc_lo(w_base), wblk16 = a.wblock_bytes >> 4;
+      const uint32_t a_lo0 = desc_lo(a_base), stage16 = a.stage_bytes >> 4;
+      const uint32_t N = (uint32_t)a.N;
+      int s = 0;
+      uint32_t ph = 0, acc = 0, aph = 0;
+      UnitIter<MODE> un;
+      un.init(a, u_begin);
+      for (int u = u_begin; u < u_end; ++u, un.next(a)) {
         if (un.len <= 0) continue;
-        for (int i = 0; i < un.len; ++i, ++tc) {
-          const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-          mbar_wait(tempty_bar(acc), aph ^ 1u);
+        for (int i = 0; i < un.len; ++i) {
+          mbar_wait(tempty0 + 8u * acc, aph ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * acc_cols;
-          if (a.mode == MODE_VREUSE) {
-            // tap t of output i lives in ring slot it+i+t
-            for (int t = 0; t < a.ntaps; ++t) {
-              const uint32_t jt = it + (uint32_t)(i + t);
-              const int s = jt % S;
-              if (i == 0 || t == a.ntaps - 1) {
-                mbar_wait(full_bar(s), (jt / S) & 1u);
+          if (MODE == MODE_VREUSE) {
+            // tap t of this output lives in ring slot s+t (s = slot of the oldest live row)
+            int st = s;
+            uint32_t pt = ph;
+            for (int t = 0; t < ntaps; ++t) {
+              if (i == 0 || t == ntaps - 1) {
+                mbar_wait(full0 + 8u * st, pt);
                 tc_fence_after();
               }
-              const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
-              const uint32_t b_addr = w_base + (uint32_t)t * a.wblock_bytes;
-              for (int m = 0; m < a.MT; ++m)
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d_tmem + (uint32_t)(m * a.N), make_desc(a_addr + m * sub_bytes + 32u * k, a.desc_hi),
-                            make_desc(b_addr + 32u * k, a.desc_hi), a.idesc, (t | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(empty_bar((it + (uint32_t)i) % S));  // oldest row is done once these MMAs retire
-            if (i == un.len - 1)
-              for (int t = 1; t < a.ntaps; ++t) umma_commit(empty_bar((it + (uint32_t)(i + t)) % S));
-          } else if (a.mode == MODE_HREUSE) {
-            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-              const int s = it % S;
-              mbar_wait(full_bar(s), (it / S) & 1u);
-              tc_fence_after();
-              const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
-              for (int t = 0; t < a.ntaps; ++t) {
-                const uint32_t a_t = a_addr + (uint32_t)(t * a.hs_d) * rb;   // row-shifted window
-                const uint32_t b_t = w_base + (uint32_t)(t * a.nkb + kb) * a.wblock_bytes;
-                for (int m = 0; m < a.MT; ++m)
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(d_tmem + (uint32_t)(m * a.N), make_desc(a_t + m * sub_bytes + 32u * k, a.desc_hi),
-                              make_desc(b_t + 32u * k, a.desc_hi), a.idesc, (kb | t | k) != 0 ? 1u : 0u);
+              const uint32_t al = a_lo0 + (uint32_t)st * stage16, bl = w_lo + (uint32_t)t * wblk16;
+              for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
+                               (t | k) != 0 ? 1u : 0u);
               }
-              umma_commit(empty_bar(s));
+              if (++st == S) { st = 0; pt ^= 1u; }
+            }
+            umma_commit(empty0 + 8u * s);   // the oldest row is dead once these MMAs retire
+            if (++s == S) { s = 0; ph ^= 1u; }
+            if (i == un.len - 1) {          // unit done: release the ntaps-1 rows still held
+              for (int t = 1; t < ntaps; ++t) {
+                umma_commit(empty0 + 8u * s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+              }
+            }
+          } else if (MODE == MODE_HREUSE) {
+            const uint32_t shift16 = ((uint32_t)a.hs_d * RB) >> 4;   // tap spacing in descriptor units
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(full0 + 8u * s, ph);
+              tc_fence_after();
+              uint32_t al = a_lo0 + (uint32_t)s * stage16;
+              uint32_t bl = w_lo + (uint32_t)kb * wblk16;
+              for (int t = 0; t < ntaps; ++t, al += shift16, bl += (uint32_t)nkb * wblk16) {
+                for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
+                                 (kb | t | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(empty0 + 8u * s);
+              if (++s == S) { s = 0; ph ^= 1u; }
             }
           } else {
-            const int kiters = a.ntaps * a.nkb;
-            for (int ki = 0; ki < kiters; ++ki, ++it) {
-              const int s = it % S;
-              mbar_wait(full_bar(s), (it / S) & 1u);
+            const int kiters = ntaps * nkb;
+            uint32_t bl = w_lo;
+            for (int ki = 0; ki < kiters; ++ki, bl += wblk16) {
+              mbar_wait(full0 + 8u * s, ph);
               tc_fence_after();
-              const uint32_t a_addr = a_base + (uint32_t)s * a.stage_bytes;
-              const uint32_t b_addr = w_base + (uint32_t)ki * a.wblock_bytes;
-              for (int m = 0; m < a.MT; ++m)
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d_tmem + (uint32_t)(m * a.N), make_desc(a_addr + m * sub_bytes + 32u * k, a.desc_hi),
-                            make_desc(b_addr + 32u * k, a.desc_hi), a.idesc, (ki | k) != 0 ? 1u : 0u);
-              umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+              const uint32_t al = a_lo0 + (uint32_t)s * stage16;
+              for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
+                               (ki | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(empty0 + 8u * s);  // frees the smem stage when these MMAs retire
+              if (++s == S) { s = 0; ph ^= 1u; }
             }
           }
-          umma_commit(tfull_bar(acc));  // accumulators ready for the epilogue
+          umma_commit(tfull0 + 8u * acc);  // accumulators ready for the epilogue
+          acc ^= 1u;
+          if (acc == 0) aph ^= 1u;
         }
-        if (a.mode == MODE_VREUSE) it += (uint32_t)(un.len + a.ntaps - 1);
       }
     }
   } else if (warp == 2) {
     if (lane == 0 && a.staged && a.has_res) {
       // ---------------- residual producer: the residual tile lands in the staging buffer the
       // epilogue will overwrite in place with the output tile
+      const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : 1u;
       uint32_t tc = 0;
-      for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-        const Unit un = decode_unit(a, u);
-        for (int i = 0; i < un.len; ++i, ++tc) {
-          const int b = tc % NS;
-          const uint32_t use = tc / NS;
-          mbar_wait(sfree_bar(b), (use & 1u) ^ 1u);
-          mbar_expect_tx(sfull_bar(b), a.out_buf_bytes);
-          const int h = un.h0 + i * un.hstep;
+      UnitIter<MODE> un;
+      if (u_begin < u_end) un.init(a, u_begin);
+      for (int u = u_begin; u < u_end; ++u, un.next(a)) {
+        int h = un.h0;
+        for (int i = 0; i < un.len; ++i, ++tc, h += un.hstep) {
+          const uint32_t b = tc & nsmask, use = tc >> nsshift;
+          mbar_wait(sfree0 + 8u * b, (use & 1u) ^ 1u);
+          mbar_expect_tx(sfull0 + 8u * b, a.out_buf_bytes);
+          const uint32_t dst = o_base + b * a.out_buf_bytes;
           for (int cb = 0; cb < a.ncb; ++cb)
             for (int q = 0; q < a.o_nbox; ++q)
-              tma_load_4d(o_base + (uint32_t)b * a.out_buf_bytes + (uint32_t)cb * a.out_block_bytes +
-                              (uint32_t)(q * a.o_boxw) * (uint32_t)a.cbo * 2u,
-                          &a.tmR, sfull_bar(b), cb * a.cbo, un.w0 + q * a.o_boxw, h, un.n);
+              tma_load_4d(dst + (uint32_t)cb * a.out_block_bytes + (uint32_t)(q * a.o_boxw * a.cbo) * 2u, &a.tmR,
+                          sfull0 + 8u * b, cb * a.cbo, un.w0 + q * a.o_boxw, h, un.n);
         }
       }
     }
   } else {
     // ---------------- epilogue warps: TMEM -> registers -> (staging smem -> TMA store | global)
-    const int ew = warp - kEpiWarp0;
-    const int q = warp & 3;     // TMEM lane quadrant this warp may access
-    const int grp = ew >> 2;    // two warps per quadrant split the (sub-tile, 16-column) units
-    const int nchunk = a.N / 16;
-    const int nwork = a.MT * nchunk;
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int grp = (warp - kEpiWarp0) >> 2;    // two warps per quadrant split the (sub-tile, 16-column) work
+    const int nchunk = a.N >> 4;
     const uint32_t row_bytes = (uint32_t)a.cbo * 2u;
-    uint32_t tc = 0;
-    for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-      const Unit un = decode_unit(a, u);
-      for (int i = 0; i < un.len; ++i, ++tc) {
-        const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-        const int th0 = un.h0 + i * un.hstep;
-        const int b = a.staged ? (int)(tc % NS) : 0;
-        const uint32_t use = a.staged ? tc / NS : 0;
-        const uint32_t obuf = o_base + (uint32_t)b * a.out_buf_bytes;
-        if (a.staged) {
-          if (a.has_res)
-            mbar_wait(sfull_bar(b), use & 1u);           // residual tile landed
+    const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : 1u;
+    const int staged = a.staged, has_res = a.has_res, act = a.ep.act, cout = a.cout;
+    const uint32_t swz = a.out_swz_mask;
+    const bool wide = a.cbo == 64 && a.ncb > 1;  // column blocks of 64 channels
+    uint32_t tc = 0, acc = 0, aph = 0;
+    UnitIter<MODE> un;
+    if (u_begin < u_end) un.init(a, u_begin);
+    for (int u = u_begin; u < u_end; ++u, un.next(a)) {
+      int th0 = un.h0;
+      for (int i = 0; i < un.len; ++i, ++tc, th0 += un.hstep) {
+        const uint32_t b = staged ? (tc & nsmask) : 0u;
+        const uint32_t use = staged ? (tc >> nsshift) : 0u;
+        const uint32_t obuf = o_base + b * a.out_buf_bytes;
+        if (staged) {
+          if (has_res)
+            mbar_wait(sfull0 + 8u * b, use & 1u);           // residual tile landed
           else
-            mbar_wait(sfree_bar(b), (use & 1u) ^ 1u);    // previous store out of this buffer drained
+            mbar_wait(sfree0 + 8u * b, (use & 1u) ^ 1u);    // previous store out of this buffer drained
         }
-        mbar_wait(tfull_bar(acc), aph);
+        mbar_wait(tfull0 + 8u * acc, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
-        for (int wk = grp; wk < nwork; wk += 2) {
-          const int m = wk / nchunk;
-          const int c0 = (wk % nchunk) * 16;
+        // work items (m, chunk) are dealt round-robin to the two warps of a quadrant
+        int m = 0, chn = grp;
+        while (chn >= nchunk) { chn -= nchunk; ++m; }
+        while (m < MT) {
+          const int c0 = chn << 4;
           uint32_t r[16];
           tmem_ld16(taddr + (uint32_t)(m * a.N + c0), r);
           tmem_ld_wait();
-          if (c0 >= a.cout) continue;
-          const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
+          if (c0 < cout) {
+            const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cb8 = c0 + 8 * h;
-            if (cb8 >= a.cout) continue;
-            float f[8];
-            {
-              const float4 s0 = lds_f4(prm_base + 4u * cb8), s1 = lds_f4(prm_base + 4u * cb8 + 16u);
-              const float4 h0 = lds_f4(prm_base + 1024u + 4u * cb8), h1 = lds_f4(prm_base + 1024u + 4u * cb8 + 16u);
-              f[0] = fmaf(__uint_as_float(r[8 * h + 0]), s0.x, h0.x);
-              f[1] = fmaf(__uint_as_float(r[8 * h + 1]), s0.y, h0.y);
-              f[2] = fmaf(__uint_as_float(r[8 * h + 2]), s0.z, h0.z);
-              f[3] = fmaf(__uint_as_float(r[8 * h + 3]), s0.w, h0.w);
-              f[4] = fmaf(__uint_as_float(r[8 * h + 4]), s1.x, h1.x);
-              f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
-              f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
-              f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
-            }
-            if (a.staged) {
-              const int blk = cb8 / a.cbo;
-              uint32_t off = (uint32_t)R * row_bytes + (uint32_t)(cb8 - blk * a.cbo) * 2u;
-              off ^= ((off >> 7) & a.out_swz_mask) << 4;
-              const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
-              if (a.has_res) {
-                float g[8];
-                bf16x8_to_float(lds128(saddr), g);
+            for (int h = 0; h < 2; ++h) {
+              const int cb8 = c0 + 8 * h;
+              if (cb8 < cout) {
+                float f[8];
+                {
+                  const uint32_t pa = prm_base + 4u * (uint32_t)cb8;
+                  const float4 s0 = lds_f4(pa), s1 = lds_f4(pa + 16u);
+                  const float4 h0 = lds_f4(pa + 1024u), h1 = lds_f4(pa + 1040u);
+                  f[0] = fmaf(__uint_as_float(r[8 * h + 0]), s0.x, h0.x);
+                  f[1] = fmaf(__uint_as_float(r[8 * h + 1]), s0.y, h0.y);
+                  f[2] = fmaf(__uint_as_float(r[8 * h + 2]), s0.z, h0.z);
+                  f[3] = fmaf(__uint_as_float(r[8 * h + 3]), s0.w, h0.w);
+                  f[4] = fmaf(__uint_as_float(r[8 * h + 4]), s1.x, h1.x);
+                  f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
+                  f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
+                  f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
+                }
+                if (staged) {
+                  const int blk = wide ? (cb8 >> 6) : 0;
+                  const int cin_blk = wide ? (cb8 & 63) : cb8;
+                  uint32_t off = (uint32_t)R * row_bytes + (uint32_t)cin_blk * 2u;
+                  off ^= ((off >> 7) & swz) << 4;
+                  const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
+                  if (has_res) {
+                    float g[8];
+                    bf16x8_to_float(lds128(saddr), g);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += g[j];
-              }
-              if (a.ep.act == ESN_ACT_RELU) {
+                    for (int j = 0; j < 8; ++j) f[j] += g[j];
+                  }
+                  if (act == ESN_ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-              } else if (a.ep.act == ESN_ACT_PRELU) {
-                const float4 a0 = lds_f4(prm_base + 2048u + 4u * cb8), a1 = lds_f4(prm_base + 2048u + 4u * cb8 + 16u);
-                const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                  } else if (act == ESN_ACT_PRELU) {
+                    const uint32_t pa = prm_base + 2048u + 4u * (uint32_t)cb8;
+                    const float4 a0 = lds_f4(pa), a1 = lds_f4(pa + 16u);
+                    const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
-              }
-              sts128(saddr, float_to_bf16x8(f));
-            } else {
-              // fallback: per-thread global stores (output channel count not a multiple of 8)
-              const int ri = R / a.bw, rj = R % a.bw;
-              const int gi = th0 + ri, gj = un.w0 + rj;
-              if (gi < a.gh && gj < a.gw) {
-                const size_t opix =
-                    ((size_t)un.n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
-                __nv_bfloat16* yp = a.y + opix * a.y_cs;
-                for (int j = 0; j < 8; ++j) {
-                  const int c = cb8 + j;
-                  if (c < a.cout) {
-                    float v = f[j];
-                    if (a.ep.res)
-                      v += __bfloat162float(
-                          reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
-                    v = apply_act(v, a.ep.act, prm[512 + c]);
-                    yp[c] = __float2bfloat16_rn(v);
+                    for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
+                  }
+                  sts128(saddr, float_to_bf16x8(f));
+                } else {
+                  // fallback: per-thread global stores (output channel count not a multiple of 8)
+                  const int ri = R / a.bw, rj = R - ri * a.bw;
+                  const int gi = th0 + ri, gj = un.w0 + rj;
+                  if (gi < a.gh && gj < a.gw) {
+                    const size_t opix =
+                        ((size_t)un.n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
+                    __nv_bfloat16* yp = a.y + opix * a.y_cs;
+                    for (int j = 0; j < 8; ++j) {
+                      const int c = cb8 + j;
+                      if (c < cout) {
+                        float v = f[j];
+                        if (a.ep.res)
+                          v += __bfloat162float(
+                              reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
+                        v = apply_act(v, act, prm[512 + c]);
+                        yp[c] = __float2bfloat16_rn(v);
+                      }
+                    }
                   }
                 }
               }
             }
           }
+          chn += 2;
+          while (chn >= nchunk) { chn -= nchunk; ++m; }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));   // accumulators drained (count = 256)
-        if (a.staged) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);   // accumulators drained (one arrival per warp)
+        acc ^= 1u;
+        if (acc == 0) aph ^= 1u;
+        if (staged) {
           fence_proxy_async();          // my st.shared writes -> visible to the TMA (async proxy)
           epi_bar_sync();
           if (threadIdx.x == kEpiWarp0 * 32) {
             for (int cb = 0; cb < a.ncb; ++cb)
               for (int qb = 0; qb < a.o_nbox; ++qb)
-                tma_store_4d(&a.tmY,
-                             obuf + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
+                tma_store_4d(&a.tmY, obuf + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
                              cb * a.cbo, un.w0 + qb * a.o_boxw, th0, un.n);
             tma_store_commit();
             // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
             if (NS == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>();
-            if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree_bar((tc + 1) % NS));
+            if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree0 + 8u * ((tc + 1) & nsmask));
           }
         }
       }
     }
-    if (a.staged && threadIdx.x == kEpiWarp0 * 32) tma_store_wait_all();
+    if (staged && threadIdx.x == kEpiWarp0 * 32) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -581,8 +651,12 @@ const DeviceLimits& limits() {
     cudaDeviceGetAttribute(&l.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&l.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, conv_umma_kernel) == cudaSuccess) l.max_smem -= (int)fa.sharedSizeBytes;
-    cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.max_smem);
+    if (cudaFuncGetAttributes(&fa, conv_umma_kernel<64, MODE_GENERIC>) == cudaSuccess) l.max_smem -= (int)fa.sharedSizeBytes;
+#define ESN_SET_SMEM(KBv, Mv) cudaFuncSetAttribute(conv_umma_kernel<KBv, Mv>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.max_smem)
+    ESN_SET_SMEM(16, MODE_GENERIC); ESN_SET_SMEM(16, MODE_HREUSE); ESN_SET_SMEM(16, MODE_VREUSE);
+    ESN_SET_SMEM(32, MODE_GENERIC); ESN_SET_SMEM(32, MODE_HREUSE); ESN_SET_SMEM(32, MODE_VREUSE);
+    ESN_SET_SMEM(64, MODE_GENERIC); ESN_SET_SMEM(64, MODE_HREUSE); ESN_SET_SMEM(64, MODE_VREUSE);
+#undef ESN_SET_SMEM
   });
   return l;
 }
@@ -707,6 +781,8 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     while (L > 4 && (long long)x.n * a.tiles_w * a.vr_d * esn_cdiv(cnt, L) < 3LL * lim.sms) L >>= 1;
     a.vr_L = L;
     a.vr_nseg = esn_cdiv(cnt, L);
+    a.vr_cnt = cnt;
+    a.vr_rem = gh - (cnt - 1) * a.vr_d;
     a.load_bytes = (uint32_t)rows * row_bytes;
     a.stage_bytes = a.load_bytes;
     a.nunits = x.n * a.tiles_w * a.vr_d * a.vr_nseg;
@@ -849,7 +925,18 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
                         (size_t)a.stages * a.stage_bytes;
     int grid = lim.sms;
     if (grid > a.nunits) grid = a.nunits;
-    conv_umma_kernel<<<grid, kThreads, smem, st>>>(a);
+#define ESN_LAUNCH(KBv, Mv) conv_umma_kernel<KBv, Mv><<<grid, kThreads, smem, st>>>(a)
+#define ESN_LAUNCH_KB(KBv)                                                   \
+  do {                                                                       \
+    if (a.mode == MODE_HREUSE) ESN_LAUNCH(KBv, MODE_HREUSE);                 \
+    else if (a.mode == MODE_VREUSE) ESN_LAUNCH(KBv, MODE_VREUSE);            \
+    else ESN_LAUNCH(KBv, MODE_GENERIC);                                      \
+  } while (0)
+    if (KB == 64) ESN_LAUNCH_KB(64);
+    else if (KB == 32) ESN_LAUNCH_KB(32);
+    else ESN_LAUNCH_KB(16);
+#undef ESN_LAUNCH_KB
+#undef ESN_LAUNCH
     ESN_CHECK_LAUNCH();
   }
   return ESN_OK;
