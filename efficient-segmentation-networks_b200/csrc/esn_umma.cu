@@ -24,8 +24,8 @@
 namespace {
 
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 352;   // 11 warps: TMA-A, MMA, TMA-residual, 8 epilogue
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 512;   // 16 epilogue warps (4 per TMEM lane quadrant)
+constexpr int kThreads = 96 + kEpiThreads;   // + TMA-A, MMA, TMA-residual warps
 constexpr int kEpiWarp0 = 3;
 constexpr int kTileM = 128;
 constexpr long long kSpinLimitCycles = 4000000000LL;  // ~2 s
@@ -118,7 +118,7 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -251,6 +251,11 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uin
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 
 template <int KB, int MODE>
@@ -322,12 +327,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const int ntaps = a.ntaps, nkb = a.nkb, MT = a.MT;
 
   if (warp == 0) {
-    if (lane == 0 && u_begin < u_end) {
-      // ---------------- TMA producer: weights once, then the A ring
-      mbar_expect_tx(wfull_bar, (uint32_t)(ntaps * nkb) * a.wblock_bytes);
-      for (int t = 0; t < ntaps; ++t)
-        for (int kb = 0; kb < nkb; ++kb)
-          tma_load_2d(w_base + (uint32_t)(t * nkb + kb) * a.wblock_bytes, &a.tmB, wfull_bar, kb * KB, a.tap_wrow[t]);
+    if (u_begin < u_end) {
+      // ---------------- TMA producer (warp-uniform control flow; one elected lane issues):
+      // weights once, then the A ring
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(wfull_bar, (uint32_t)(ntaps * nkb) * a.wblock_bytes);
+        for (int t = 0; t < ntaps; ++t)
+          for (int kb = 0; kb < nkb; ++kb)
+            tma_load_2d(w_base + (uint32_t)(t * nkb + kb) * a.wblock_bytes, &a.tmB, wfull_bar, kb * KB, a.tap_wrow[t]);
+      }
       int s = 0;
       uint32_t ph = 0;   // parity of the phase the consumer completes next on stage s
       UnitIter<MODE> un;
@@ -339,23 +348,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           int row = un.h0 - a.vr_pad;
           for (int j = 0; j < un.len + ntaps - 1; ++j, row += un.hstep) {
             mbar_wait(empty0 + 8u * s, ph ^ 1u);
-            mbar_expect_tx(full0 + 8u * s, a.load_bytes);
-            const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
-            for (int q = 0; q < a.a_nbox; ++q)
-              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, 0, un.w0 + q * a.a_boxw, 0, row,
-                          un.n);
+            if (leader) {
+              mbar_expect_tx(full0 + 8u * s, a.load_bytes);
+              const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
+              for (int q = 0; q < a.a_nbox; ++q)
+                tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, 0, un.w0 + q * a.a_boxw, 0,
+                            row, un.n);
+            }
             if (++s == S) { s = 0; ph ^= 1u; }
           }
         } else if (MODE == MODE_HREUSE) {
           const int wl = un.w0 - a.hs_pad;   // window [w0 - pad, w0 + bw + (k-1)d - pad)
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(empty0 + 8u * s, ph ^ 1u);
-            mbar_expect_tx(full0 + 8u * s, a.load_bytes);
-            const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
-            for (int q = 0; q < a.a_nbox; ++q)
-              tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, kb * KB, wl + q * a.a_boxw, 0,
-                          un.h0, un.n);
-            tma_load_5d(dst + (uint32_t)a.bw * RB, &a.tmAh, full0 + 8u * s, kb * KB, wl + a.bw, 0, un.h0, un.n);
+            if (leader) {
+              mbar_expect_tx(full0 + 8u * s, a.load_bytes);
+              const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
+              for (int q = 0; q < a.a_nbox; ++q)
+                tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, kb * KB, wl + q * a.a_boxw, 0,
+                            un.h0, un.n);
+              tma_load_5d(dst + (uint32_t)a.bw * RB, &a.tmAh, full0 + 8u * s, kb * KB, wl + a.bw, 0, un.h0, un.n);
+            }
             if (++s == S) { s = 0; ph ^= 1u; }
           }
         } else {
@@ -364,9 +377,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             const int ch = un.h0 + a.tap_dy[t];
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(empty0 + 8u * s, ph ^ 1u);
-              mbar_expect_tx(full0 + 8u * s, a.load_bytes);
-              tma_load_5d(a_base + (uint32_t)s * a.stage_bytes, &a.tmA, full0 + 8u * s, a.tap_coff[t] + kb * KB, cw,
-                          a.tap_par[t], ch, un.n);
+              if (leader) {
+                mbar_expect_tx(full0 + 8u * s, a.load_bytes);
+                tma_load_5d(a_base + (uint32_t)s * a.stage_bytes, &a.tmA, full0 + 8u * s, a.tap_coff[t] + kb * KB, cw,
+                            a.tap_par[t], ch, un.n);
+              }
               if (++s == S) { s = 0; ph ^= 1u; }
             }
           }
@@ -374,8 +389,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && u_begin < u_end) {
-      // ---------------- MMA issuer (single thread): descriptors advanced with 32-bit adds
+    if (u_begin < u_end) {
+      // ---------------- MMA issuer: warp-uniform loops (operands stay in uniform registers), one
+      // elected lane issues tcgen05.mma / tcgen05.commit; descriptors advance with 32-bit adds
+      const bool leader = elect_one();
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
       const uint32_t dhi = a.desc_hi, idesc = a.idesc;
@@ -405,16 +422,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
-                               (t | k) != 0 ? 1u : 0u);
+                  if (leader)
+                    umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
+                                 (t | k) != 0 ? 1u : 0u);
               }
               if (++st == S) { st = 0; pt ^= 1u; }
             }
-            umma_commit(empty0 + 8u * s);   // the oldest row is dead once these MMAs retire
+            if (leader) umma_commit(empty0 + 8u * s);   // the oldest row is dead once these MMAs retire
             if (++s == S) { s = 0; ph ^= 1u; }
             if (i == un.len - 1) {          // unit done: release the ntaps-1 rows still held
               for (int t = 1; t < ntaps; ++t) {
-                umma_commit(empty0 + 8u * s);
+                if (leader) umma_commit(empty0 + 8u * s);
                 if (++s == S) { s = 0; ph ^= 1u; }
               }
             }
@@ -429,11 +447,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 for (int m = 0; m < MT; ++m) {
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k)
-                    umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
-                                 (kb | t | k) != 0 ? 1u : 0u);
+                    if (leader)
+                      umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi,
+                                   idesc, (kb | t | k) != 0 ? 1u : 0u);
                 }
               }
-              umma_commit(empty0 + 8u * s);
+              if (leader) umma_commit(empty0 + 8u * s);
               if (++s == S) { s = 0; ph ^= 1u; }
             }
           } else {
@@ -446,14 +465,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
-                               (ki | k) != 0 ? 1u : 0u);
+                  if (leader)
+                    umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
+                                 (ki | k) != 0 ? 1u : 0u);
               }
-              umma_commit(empty0 + 8u * s);  // frees the smem stage when these MMAs retire
+              if (leader) umma_commit(empty0 + 8u * s);  // frees the smem stage when these MMAs retire
               if (++s == S) { s = 0; ph ^= 1u; }
             }
           }
-          umma_commit(tfull0 + 8u * acc);  // accumulators ready for the epilogue
+          if (leader) umma_commit(tfull0 + 8u * acc);  // accumulators ready for the epilogue
+          __syncwarp();
           acc ^= 1u;
           if (acc == 0) aph ^= 1u;
         }
@@ -484,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   } else {
     // ---------------- epilogue warps: TMEM -> registers -> (staging smem -> TMA store | global)
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-    const int grp = (warp - kEpiWarp0) >> 2;    // two warps per quadrant split the (sub-tile, 16-column) work
+    const int grp = (warp - kEpiWarp0) >> 2;    // 4 warps per quadrant split the (sub-tile, 16-column) work
     const int nchunk = a.N >> 4;
     const uint32_t row_bytes = (uint32_t)a.cbo * 2u;
     const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : 1u;
@@ -509,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         mbar_wait(tfull0 + 8u * acc, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
-        // work items (m, chunk) are dealt round-robin to the two warps of a quadrant
+        // work items (m, chunk) are dealt round-robin to the warps of a quadrant
         int m = 0, chn = grp;
         while (chn >= nchunk) { chn -= nchunk; ++m; }
         while (m < MT) {
@@ -584,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               }
             }
           }
-          chn += 2;
+          chn += kEpiThreads / 128;
           while (chn >= nchunk) { chn -= nchunk; ++m; }
         }
         tc_fence_before();
@@ -738,6 +759,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   else if (rowable && p->kw == 1 && p->kh >= 2 && nkb == 1)
     a.mode = MODE_VREUSE;
   if (a.mode != MODE_GENERIC) {
+    if (a.mode == MODE_HREUSE && KB == 64 && nkb == 1 && N <= 64) MT = 2;   // 256-pixel row tiles for C=64
     while (MT > 1 && MT * kTileM > gw) MT >>= 1;
     a.bw = MT * kTileM;
     a.bh = 1;
