@@ -47,7 +47,7 @@ struct alignas(64) UmmaArgs {
   __nv_bfloat16* y;
   int Hy, Wy, y_cs, sy, oy, sx, ox;
   EpiArgs ep;
-  int staged, has_res, stages, NS;
+  int staged, has_res, stages, NS, NA;   // NS staging buffers, NA TMEM accumulator buffers
   int cbo, ncb;                      // staged epilogue: channels per 128B-wide column block, #blocks
   uint32_t load_bytes, stage_bytes, wblock_bytes, w_region_bytes, out_block_bytes, out_buf_bytes, out_swz_mask;
   uint32_t idesc, desc_hi;           // instruction descriptor; upper 32 bits of the smem descriptors
@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const uint32_t bar_base = prm_base + 3u * 256u * 4u;
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * S;
   const uint32_t wfull_bar = bar_base + 8u * (2 * S);
-  const uint32_t tfull0 = bar_base + 8u * (2 * S + 1), tempty0 = bar_base + 8u * (2 * S + 3);
-  const uint32_t sfull0 = bar_base + 8u * (2 * S + 5), sfree0 = bar_base + 8u * (2 * S + 9);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 13);
+  const uint32_t tfull0 = bar_base + 8u * (2 * S + 1), tempty0 = bar_base + 8u * (2 * S + 5);
+  const uint32_t sfull0 = bar_base + 8u * (2 * S + 9), sfree0 = bar_base + 8u * (2 * S + 13);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 17);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* prm = reinterpret_cast<float*>(smem_raw + (prm_base - raw));
 
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       mbar_init(empty0 + 8u * s, 1);
     }
     mbar_init(wfull_bar, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(tfull0 + 8u * b, 1);
       mbar_init(tempty0 + 8u * b, kEpiThreads / 32);
     }
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const int u_end = (int)(((long long)a.nunits * (blockIdx.x + 1)) / gridDim.x);
   const uint32_t acc_cols = (uint32_t)(a.MT * a.N);
   const int ntaps = a.ntaps, nkb = a.nkb, MT = a.MT;
+  const uint32_t NA = (uint32_t)a.NA;
 
   if (warp == 0) {
     if (u_begin < u_end) {
@@ -475,8 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           }
           if (leader) umma_commit(tfull0 + 8u * acc);  // accumulators ready for the epilogue
           __syncwarp();
-          acc ^= 1u;
-          if (acc == 0) aph ^= 1u;
+          if (++acc == NA) { acc = 0; aph ^= 1u; }
         }
       }
     }
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (lane == 0 && a.staged && a.has_res) {
       // ---------------- residual producer: the residual tile lands in the staging buffer the
       // epilogue will overwrite in place with the output tile
-      const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : 1u;
+      const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : (NS == 2 ? 1u : 0u);
       uint32_t tc = 0;
       UnitIter<MODE> un;
       if (u_begin < u_end) un.init(a, u_begin);
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int grp = (warp - kEpiWarp0) >> 2;    // 4 warps per quadrant split the (sub-tile, 16-column) work
     const int nchunk = a.N >> 4;
     const uint32_t row_bytes = (uint32_t)a.cbo * 2u;
-    const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : 1u;
+    const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : (NS == 2 ? 1u : 0u);
     const int staged = a.staged, has_res = a.has_res, act = a.ep.act, cout = a.cout;
     const uint32_t swz = a.out_swz_mask;
     const bool wide = a.cbo == 64 && a.ncb > 1;  // column blocks of 64 channels
@@ -611,8 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);   // accumulators drained (one arrival per warp)
-        acc ^= 1u;
-        if (acc == 0) aph ^= 1u;
+        if (++acc == NA) { acc = 0; aph ^= 1u; }
         if (staged) {
           fence_proxy_async();          // my st.shared writes -> visible to the TMA (async proxy)
           epi_bar_sync();
@@ -623,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                              cb * a.cbo, un.w0 + qb * a.o_boxw, th0, un.n);
             tma_store_commit();
             // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
-            if (NS == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>();
+            if (NS == 4) tma_store_wait_read<3>(); else if (NS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
             if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree0 + 8u * ((tc + 1) & nsmask));
           }
         }
@@ -929,21 +928,32 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     const uint32_t wbytes = (uint32_t)nt * nkb * a.wblock_bytes;
     a.w_region_bytes = (wbytes + 1023u) & ~1023u;
     // shared memory plan: resident weights + A ring + staging + params + barriers (+1 KB alignment slack)
+    // trade staging buffers for A stages until the load pipeline is deep enough to cover ~2 tiles
     const int min_stages = a.mode == MODE_VREUSE ? nt + 1 : 2;
+    const int per_tile = a.mode == MODE_VREUSE ? 1 : (a.mode == MODE_HREUSE ? nkb : nt * nkb);
+    int want = a.mode == MODE_VREUSE ? nt + 3 : 2 * per_tile + 1;
+    if (want > 8) want = 8;
+    int ns = a.staged ? (a.out_buf_bytes <= 16384 ? 4 : 2) : 0;
     for (;;) {
-      const uint32_t fixed = a.w_region_bytes + (uint32_t)a.NS * a.out_buf_bytes + 3072u + 256u + 1024u;
-      if (fixed + (uint32_t)min_stages * a.stage_bytes <= (uint32_t)lim.max_smem) {
-        int stages = (int)(((uint32_t)lim.max_smem - fixed) / a.stage_bytes);
-        a.stages = stages > 8 ? 8 : stages;
+      const uint32_t fixed = a.w_region_bytes + (uint32_t)ns * a.out_buf_bytes + 3072u + 512u + 1024u;
+      int stages = fixed < (uint32_t)lim.max_smem ? (int)(((uint32_t)lim.max_smem - fixed) / a.stage_bytes) : 0;
+      if (stages > 8) stages = 8;
+      if (stages >= want || ns <= 1) {
+        if (stages < min_stages) return ESN_ERR_UNSUPPORTED;
+        a.stages = stages;
+        a.NS = ns;
         break;
       }
-      if (a.NS == 4) { a.NS = 2; continue; }
-      return ESN_ERR_UNSUPPORTED;
+      ns >>= 1;
     }
+    int na = 4;
+    while (na > 2 && na * MT * N > 512) na >>= 1;
+    if (na * MT * N > 512) return ESN_ERR_UNSUPPORTED;
+    a.NA = na;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * MT * N)) cols <<= 1;
+    while (cols < (uint32_t)(na * MT * N)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t smem = a.w_region_bytes + (size_t)a.NS * a.out_buf_bytes + 3072u + 256u + 1024u +
+    const size_t smem = a.w_region_bytes + (size_t)a.NS * a.out_buf_bytes + 3072u + 512u + 1024u +
                         (size_t)a.stages * a.stage_bytes;
     int grid = lim.sms;
     if (grid > a.nunits) grid = a.nunits;
