@@ -931,7 +931,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     // trade staging buffers for A stages until the load pipeline is deep enough to cover ~2 tiles
     const int min_stages = a.mode == MODE_VREUSE ? nt + 1 : 2;
     const int per_tile = a.mode == MODE_VREUSE ? 1 : (a.mode == MODE_HREUSE ? nkb : nt * nkb);
-    int want = a.mode == MODE_VREUSE ? nt + 3 : 2 * per_tile + 1;
+    int want = a.mode == MODE_VREUSE ? nt + 3 : (a.mode == MODE_HREUSE ? per_tile + 1 : 2 * per_tile + 1);
     if (want > 8) want = 8;
     int ns = a.staged ? (a.out_buf_bytes <= 16384 ? 4 : 2) : 0;
     for (;;) {
