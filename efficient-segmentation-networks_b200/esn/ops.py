@@ -46,6 +46,14 @@ def require_cuda(t, what):
         raise RuntimeError("%s: tensors must live on a CUDA device; this framework has no CPU path" % what)
 
 
+def widen(t, c):
+    """The same NHWC buffer seen with `c` logical channels (c <= pixel stride): used to run
+    vectorised / tensor-core kernels over zero-padded channel tails of concat buffers."""
+    assert is_nhwc(t) and c <= t.stride(3)
+    n, _, h, w = t.shape
+    return t.as_strided((n, c, h, w), t.stride(), t.storage_offset())
+
+
 def is_nhwc(t):
     if t.dim() != 4:
         return False
@@ -70,10 +78,10 @@ def tdesc(t):
     return d
 
 
-def new_act(n, c, h, w, dtype, device, c_alloc=None):
+def new_act(n, c, h, w, dtype, device, c_alloc=None, zero=False):
     """Fresh NHWC activation with logical shape (N,C,H,W); c_alloc pads the pixel stride."""
     ca = c if c_alloc is None else c_alloc
-    buf = torch.empty((n, h, w, ca), dtype=dtype, device=device)
+    buf = (torch.zeros if zero else torch.empty)((n, h, w, ca), dtype=dtype, device=device)
     t = buf.permute(0, 3, 1, 2)
     return t if ca == c else t[:, :c]
 
@@ -135,12 +143,31 @@ def bn_affine(bn, device):
 class ConvPrep:
     """Packed weights + folded epilogue of one conv (+BN slice) (+activation)."""
 
-    def __init__(self, conv, scale=None, shift=None, act=L.ACT_NONE, alpha=None, device=None):
+    def __init__(self, conv, scale=None, shift=None, act=L.ACT_NONE, alpha=None, device=None, cin_pad=None,
+                 cout_pad=None):
+        """cin_pad / cout_pad: zero-extend the weight so the kernel sees a channel-padded NHWC view
+        (padded input channels must hold finite values; padded outputs evaluate to act(0))."""
         device = device or conv.weight.device
         transposed = isinstance(conv, torch.nn.ConvTranspose2d)
         w = _f32(conv.weight, device)
         if transposed:          # (Cin, Cout, kh, kw) -> (Cout, Cin, kh, kw)
             w = w.permute(1, 0, 2, 3).contiguous()
+        bias = None if conv.bias is None else _f32(conv.bias, device)
+        if cin_pad is not None and cin_pad > w.shape[1]:
+            assert conv.groups == 1
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
+        if cout_pad is not None and cout_pad > w.shape[0]:
+            assert conv.groups == 1
+            extra = cout_pad - w.shape[0]
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, extra))
+            zeros = torch.zeros(extra, device=device)
+            scale = torch.cat([torch.ones(w.shape[0] - extra, device=device) if scale is None else scale, zeros + 1])
+            shift = torch.cat([torch.zeros(w.shape[0] - extra, device=device) if shift is None else shift, zeros])
+            if alpha is not None:
+                alpha = torch.cat([_f32(alpha, device), zeros])
+            if bias is not None:
+                bias = torch.cat([bias, zeros])
+        w = w.contiguous()
         self.cout, cin_g, self.kh, self.kw = w.shape
         self.groups = conv.groups
         self.cin = cin_g * conv.groups
@@ -159,11 +186,34 @@ class ConvPrep:
         self.cout_pad = (self.cout + 15) // 16 * 16
         sc = torch.ones(self.cout, device=device) if scale is None else scale.clone()
         sh = torch.zeros(self.cout, device=device) if shift is None else shift.clone()
-        if conv.bias is not None:
-            sh = sh + _f32(conv.bias, device) * sc
+        if bias is not None:
+            sh = sh + bias * sc
         self.scale, self.shift = sc.contiguous(), sh.contiguous()
         self.act = act
         self.alpha = None if alpha is None else _f32(alpha, device)
+
+    def cin_split(self):
+        """Sub-convs over 64-channel-multiple input slices: scale on every part, shift + activation on the last."""
+        if getattr(self, "_parts", None) is None:
+            import copy
+            taps = self.kh * self.kw
+            per = max(64, (200 * 1024 // (taps * self.cout_pad * 2)) // 64 * 64)
+            parts, lo = [], 0
+            while lo < self.cin:
+                hi = min(self.cin, lo + per)
+                q = copy.copy(self)
+                q._parts, q._w_umma = None, None
+                q._w_src = self._w_src[:, lo:hi].contiguous()
+                q.cin, q.cin_lo = hi - lo, lo // 64
+                q.w_direct = q._w_src.permute(2, 3, 1, 0).reshape(taps, hi - lo, self.cout).contiguous()
+                last = hi == self.cin
+                if not last:
+                    q.shift = torch.zeros_like(self.shift)
+                    q.act, q.alpha = L.ACT_NONE, None
+                parts.append(q)
+                lo = hi
+            self._parts = parts
+        return self._parts
 
     @property
     def w_umma(self):
@@ -211,11 +261,25 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
         flops = 2 * n * h * w * prep.cout * prep.cin * prep.kh * prep.kw
     tag = "%dx%d c%d-%d s%d d%d%s" % (prep.kh, prep.kw, prep.cin, prep.cout, prep.stride,
                                        max(prep.dil_h, prep.dil_w), "T" if prep.transposed else "")
-    if (UMMA_ENABLED and not force_direct and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
-            and prep.groups == 1 and p.x.layout == L.ESN_NHWC and umma_supported(prep, p)):
+    tc_ok = (UMMA_ENABLED and not force_direct and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+             and prep.groups == 1 and p.x.layout == L.ESN_NHWC)
+    if tc_ok and umma_supported(prep, p):
         p.w = prep.w_umma.data_ptr()
         _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag)
         return out
+    if tc_ok and prep.cin % 64 == 0 and prep.cin > 64 and not prep.transposed:
+        # all taps of the full-Cin weight do not fit in shared memory: run the conv as a sum over
+        # 64-channel input slices, carrying the scaled partial sum through the residual operand
+        parts = prep.cin_split()
+        if parts is not None and all(umma_supported(q, p) for q in parts):
+            acc = residual
+            for i, q in enumerate(parts):
+                last = i == len(parts) - 1
+                xi = x[:, 64 * q.cin_lo:64 * q.cin_lo + q.cin]
+                yi = out if last else new_act(n, prep.cout, ho, wo, out.dtype, x.device)
+                conv2d(xi, q, out=yi, residual=acc)
+                acc = yi
+            return out
     p.w = prep.w_direct.data_ptr()
     _call(L.lib.esn_conv2d_direct, "esn_conv2d_direct", (C.byref(p),), alg, flops, tag)
     return out

@@ -83,12 +83,21 @@ class BNPReLU(PrepMixin, nn.Module):
         self.acti = nn.PReLU(nIn)
 
     def _build_prep(self, device):
-        return _bnprelu_affine(self, device)
+        s, b, a = _bnprelu_affine(self, device)
+        pad = (-s.numel()) % 8      # zero scale/shift/alpha tail: padded channels of a concat buffer stay 0
+        z = torch.zeros(pad, device=device)
+        return s, b, a, torch.cat([s, z]), torch.cat([b, z]), torch.cat([a, z])
 
     def forward(self, input, out=None):
         _no_train(self)
         x = ops.as_act(input)
-        s, b, a = self.prep(x.device)
+        s, b, a, sp, bp, ap = self.prep(x.device)
+        c = x.shape[1]
+        if c % 4 and out is x and x.stride(3) >= sp.numel():
+            # in-place BNPReLU of a channel-padded concat buffer: run the vector path over the padded width
+            xw = ops.widen(x, sp.numel())
+            ops.affine_act(xw, sp, bp, ap, ACT_PRELU, out=xw)
+            return x
         return ops.affine_act(x, s, b, a, ACT_PRELU, out=out)
 
 
@@ -144,22 +153,40 @@ class DownSamplingBlock(PrepMixin, nn.Module):
         self.max_pool = nn.MaxPool2d(2, stride=2)
         self.bn_prelu = BNPReLU(nOut)
 
+    @staticmethod
+    def _tc_channels(c):
+        """Smallest channel count >= c the tcgen05 conv takes as Cin (16/32/64 or a multiple of 64)."""
+        for v in (16, 32, 64):
+            if c <= v:
+                return v
+        return (c + 63) // 64 * 64
+
     def _build_prep(self, device):
         s, b, a = _bnprelu_affine(self.bn_prelu, device)
         nc = self.conv3x3.conv.out_channels
         conv = ops.ConvPrep(self.conv3x3.conv, s[:nc], b[:nc], ACT_PRELU, a[:nc], device=device)
-        return conv, s[nc:].contiguous(), b[nc:].contiguous(), a[nc:].contiguous()
+        # tensor-core variant for channel-padded concat inputs: Cin zero-extended, Cout rounded up to 8
+        # (the extra output channels land where the max-pool branch writes afterwards)
+        conv_tc = ops.ConvPrep(self.conv3x3.conv, s[:nc], b[:nc], ACT_PRELU, a[:nc], device=device,
+                               cin_pad=self._tc_channels(self.nIn), cout_pad=(nc + 7) // 8 * 8)
+        return conv, conv_tc, s[nc:].contiguous(), b[nc:].contiguous(), a[nc:].contiguous()
 
     def forward(self, input, out=None):
         _no_train(self)
         x = ops.as_act(input)
-        conv, ps, pb, pa = self.prep(x.device)
+        conv, conv_tc, ps, pb, pa = self.prep(x.device)
         n, c, h, w = x.shape
         if out is None:
             out = ops.new_act(n, self.nOut, h // 2, w // 2, x.dtype, x.device)
         nc = conv.cout
-        ops.conv2d(x, conv, out=out[:, :nc])
-        if self.nIn < self.nOut:
+        pooled = self.nIn < self.nOut
+        if (x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.stride(3) >= conv_tc.cin
+                and (conv_tc.cout == nc or (pooled and conv_tc.cout <= self.nOut)) and (h | w) % 2 == 0):
+            # x is a zero-padded concat buffer: read it at its padded width on the tensor cores
+            ops.conv2d(ops.widen(x, conv_tc.cin), conv_tc, out=out[:, :conv_tc.cout])
+        else:
+            ops.conv2d(x, conv, out=out[:, :nc])
+        if pooled:
             ops.maxpool2x2(x, out[:, nc:], ps, pb, pa, ACT_PRELU)
         return out
 
@@ -221,7 +248,7 @@ class DABNet(nn.Module):
         d3 = self.down_1(d2)
 
         h1, w1 = d1.shape[2:]
-        cat0 = ops.new_act(n, 35, h1, w1, dt, dev, c_alloc=40)
+        cat0 = ops.new_act(n, 35, h1, w1, dt, dev, c_alloc=64, zero=True)
         y = self.init_conv[0](input)
         y = self.init_conv[1](y)
         self.init_conv[2](y, out=cat0[:, :32])
@@ -229,7 +256,7 @@ class DABNet(nn.Module):
         self.bn_prelu_1(cat0, out=cat0)
 
         h2, w2 = d2.shape[2:]
-        cat1 = ops.new_act(n, 131, h2, w2, dt, dev, c_alloc=136)
+        cat1 = ops.new_act(n, 131, h2, w2, dt, dev, c_alloc=192, zero=True)
         y = self.downsample_1(cat0, out=cat1[:, 64:128])
         blocks = list(self.DAB_Block_1)
         for i, blk in enumerate(blocks):
@@ -238,7 +265,7 @@ class DABNet(nn.Module):
         self.bn_prelu_2(cat1, out=cat1)
 
         h3, w3 = d3.shape[2:]
-        cat2 = ops.new_act(n, 259, h3, w3, dt, dev, c_alloc=264)
+        cat2 = ops.new_act(n, 259, h3, w3, dt, dev, c_alloc=320, zero=True)
         y = self.downsample_2(cat1, out=cat2[:, 128:256])
         blocks = list(self.DAB_Block_2)
         for i, blk in enumerate(blocks):
@@ -247,9 +274,24 @@ class DABNet(nn.Module):
         self.bn_prelu_3(cat2, out=cat2)
 
         classes = self.classifier[0].conv.out_channels
-        scores = ops.new_act(n, classes, h3, w3, torch.float32, dev, c_alloc=32)
-        self.classifier[0](cat2, out=scores)
+        if dt == torch.bfloat16:
+            # 1x1 classifier on the tensor cores over the padded 320-channel view (zero weights on the tail)
+            scores = ops.new_act(n, classes, h3, w3, torch.bfloat16, dev, c_alloc=32)
+            cls = self._cls_prep(dev)
+            ops.conv2d(ops.widen(cat2, cls.cin), cls, out=ops.widen(scores, cls.cout))
+        else:
+            scores = ops.new_act(n, classes, h3, w3, torch.float32, dev, c_alloc=32)
+            self.classifier[0](cat2, out=scores)
         return scores, (h, w), dt
+
+    def _cls_prep(self, device):
+        m = self.classifier[0]
+        key = (str(device), m.conv.weight.data_ptr(), m.conv.weight._version)
+        cached = self.__dict__.get("_esn_cls")
+        if cached is None or cached[0] != key:
+            cached = (key, ops.ConvPrep(m.conv, device=device, cin_pad=320, cout_pad=32))
+            self.__dict__["_esn_cls"] = cached
+        return cached[1]
 
     def forward(self, input):
         scores, (h, w), dt = self._scores(input)
