@@ -306,7 +306,7 @@ def umma_supported(prep, p):
     while mt > 1 and mt * prep.cout_pad > 256:
         mt //= 2
     staged = prep.cout % 8 == 0 and (prep.cout <= 64 or prep.cout % 64 == 0)
-    staging = 2 * mt * 128 * prep.cout * 2 if staged else 0
+    staging = mt * 128 * prep.cout * 2 if staged else 0     # the planner can go down to one staging buffer
     if taps * cin * prep.cout_pad * 2 + staging + 2 * mt * 128 * kb * 2 + 6144 > 226 * 1024:
         return False
     return True
