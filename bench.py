@@ -315,8 +315,22 @@ def main():
                   for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][1])[:24]}
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         achieved = top[1]["bytes"] / (top[1]["ms"] / 1e3) / 1e9
+        # DRAM traffic of the same kernel family from the committed ncu launch list (separate run)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % model_name.lower())
+        fam_names = {"esn_conv2d_umma": "conv_umma_kernel", "esn_conv2d_direct": "conv_direct_kernel",
+                     "esn_dab_dw_pair": "dab_dw_pair_kernel", "esn_affine_act": "pw_kernel"}
+        if os.path.exists(tpath) and top[0] in fam_names:
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload:
+                fams = [v for k, v in tj["families"].items() if k.startswith(fam_names[top[0]])]
+                n_l = sum(v["launches"] for v in fams)
+                if n_l:
+                    traffic = {"dram_bytes_per_launch": int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in fams) / n_l),
+                               "alg_bytes_per_launch": int(top[1]["bytes"] / top[1]["launches"]), "kernel_launches": n_l,
+                               "source": tj["source"]}
         roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": top[1]["launches"], "share_of_step": round(top[1]["ms"] / tot_ms, 4),
                     "tensor_TFLOPs": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12, 1),
                     "tensor_frac_of_bf16_peak": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12 / tc_peak, 4),

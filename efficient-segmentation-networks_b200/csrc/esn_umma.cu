@@ -37,6 +37,7 @@ struct alignas(64) UmmaArgs {
   CUtensorMap tmY;   // output, 4-D   (staged epilogue only)
   CUtensorMap tmR;   // residual, 4-D (staged epilogue with residual only)
   int mode, nunits;
+  int g_dw, g_dh, g_dn;              // MODE_GENERIC: (tw, th, n) increment of one grid stride (interleaved tiles)
   int ntaps, nkb, kb_elems, N, cout, MT;
   int bw, bh, tiles_w, tiles_h, gh, gw;
   int a_boxw, a_nbox, o_boxw, o_nbox;
@@ -230,11 +231,19 @@ struct UnitIter {
           if (++tw == a.tiles_w) { tw = 0; ++n; }
         }
       }
-    } else {
+    } else if (MODE == MODE_HREUSE) {
       if (++tw == a.tiles_w) {
         tw = 0;
         if (++th == a.tiles_h) { th = 0; ++n; }
       }
+    } else {
+      // interleaved assignment (unit += gridDim.x): tiles in flight on different SMs are neighbours in
+      // memory, so the halo rows of multi-row taps are shared through L2 instead of re-read from HBM
+      tw += a.g_dw;
+      if (tw >= a.tiles_w) { tw -= a.tiles_w; ++th; }
+      th += a.g_dh;
+      if (th >= a.tiles_h) { th -= a.tiles_h; ++n; }
+      n += a.g_dn;
     }
     set(a);
   }
@@ -321,8 +330,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // contiguous unit range of this CTA
-  const int u_begin = (int)(((long long)a.nunits * blockIdx.x) / gridDim.x);
-  const int u_end = (int)(((long long)a.nunits * (blockIdx.x + 1)) / gridDim.x);
+  const int u_step = MODE == MODE_GENERIC ? (int)gridDim.x : 1;
+  const int u_begin = MODE == MODE_GENERIC ? (int)blockIdx.x : (int)(((long long)a.nunits * blockIdx.x) / gridDim.x);
+  const int u_end = MODE == MODE_GENERIC ? a.nunits : (int)(((long long)a.nunits * (blockIdx.x + 1)) / gridDim.x);
   const uint32_t acc_cols = (uint32_t)(a.MT * a.N);
   const int ntaps = a.ntaps, nkb = a.nkb, MT = a.MT;
   const uint32_t NA = (uint32_t)a.NA;
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       uint32_t ph = 0;   // parity of the phase the consumer completes next on stage s
       UnitIter<MODE> un;
       un.init(a, u_begin);
-      for (int u = u_begin; u < u_end; ++u, un.next(a)) {
+      for (int u = u_begin; u < u_end; u += u_step, un.next(a)) {
         if (un.len <= 0) continue;
         if (MODE == MODE_VREUSE) {
           // rows h0-pad + j*d, j = 0..len+ntaps-2: one ring slot each, each row loaded exactly once
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       uint32_t ph = 0, acc = 0, aph = 0;
       UnitIter<MODE> un;
       un.init(a, u_begin);
-      for (int u = u_begin; u < u_end; ++u, un.next(a)) {
+      for (int u = u_begin; u < u_end; u += u_step, un.next(a)) {
         if (un.len <= 0) continue;
         for (int i = 0; i < un.len; ++i) {
           mbar_wait(tempty0 + 8u * acc, aph ^ 1u);
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       uint32_t tc = 0;
       UnitIter<MODE> un;
       if (u_begin < u_end) un.init(a, u_begin);
-      for (int u = u_begin; u < u_end; ++u, un.next(a)) {
+      for (int u = u_begin; u < u_end; u += u_step, un.next(a)) {
         int h = un.h0;
         for (int i = 0; i < un.len; ++i, ++tc, h += un.hstep) {
           const uint32_t b = tc & nsmask, use = tc >> nsshift;
@@ -515,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     uint32_t tc = 0, acc = 0, aph = 0;
     UnitIter<MODE> un;
     if (u_begin < u_end) un.init(a, u_begin);
-    for (int u = u_begin; u < u_end; ++u, un.next(a)) {
+    for (int u = u_begin; u < u_end; u += u_step, un.next(a)) {
       int th0 = un.h0;
       for (int i = 0; i < un.len; ++i, ++tc, th0 += un.hstep) {
         const uint32_t b = staged ? (tc & nsmask) : 0u;
@@ -957,6 +967,9 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
                         (size_t)a.stages * a.stage_bytes;
     int grid = lim.sms;
     if (grid > a.nunits) grid = a.nunits;
+    a.g_dw = grid % a.tiles_w;
+    a.g_dh = (grid / a.tiles_w) % a.tiles_h;
+    a.g_dn = grid / (a.tiles_w * a.tiles_h);
 #define ESN_LAUNCH(KBv, Mv) conv_umma_kernel<KBv, Mv><<<grid, kThreads, smem, st>>>(a)
 #define ESN_LAUNCH_KB(KBv)                                                   \
   do {                                                                       \
