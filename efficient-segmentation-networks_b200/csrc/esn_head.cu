@@ -147,6 +147,8 @@ struct CEArgs {
   float* sums;
   void* dlogits;
   int N, C, H, W, ignore;
+  const float* gnorm;
+  const float* gout;
 };
 
 template <typename T>
@@ -184,10 +186,11 @@ __global__ void __launch_bounds__(256) weighted_ce_kernel(const CEArgs a) {
     }
     if (a.dlogits) {
       T* gp = reinterpret_cast<T*>(a.dlogits) + (size_t)n * a.C * hw + px;
-      const float inv = wy / s;
+      const float gs = (a.gout ? __ldg(a.gout) : 1.f) / (a.gnorm ? __ldg(a.gnorm) : 1.f);
+      const float inv = wy / s * gs;
 #pragma unroll
       for (int k = 0; k < kMaxClasses; ++k)
-        if (k < a.C) st1<T>(gp + (size_t)k * hw, v[k] * inv - ((valid && k == (int)y) ? wy : 0.f));
+        if (k < a.C) st1<T>(gp + (size_t)k * hw, v[k] * inv - ((valid && k == (int)y) ? wy * gs : 0.f));
     }
   }
   // block reduction: warp shuffle -> smem -> one atomic pair per CTA
@@ -324,6 +327,8 @@ extern "C" int esn_weighted_ce(const EsnCE* p, void* stream) {
   a.H = l.h;
   a.W = l.w;
   a.ignore = p->ignore_label;
+  a.gnorm = p->gnorm;
+  a.gout = p->gout;
   const long long total = (long long)l.n * l.h * l.w;
   const int block = 256, grid = esn_cdiv(total, block);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

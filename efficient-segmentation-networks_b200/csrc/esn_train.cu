@@ -1,0 +1,630 @@
+// Training-path kernels (round 1: correct first, CUDA cores; the tensor-core wgrad is next):
+//   * per-channel batch statistics (sum, sum of squares) for train-mode BatchNorm
+//   * BatchNorm finalize (scale/shift for the apply pass, running-stat update as torch does it)
+//   * BN + activation backward: reduction pass (sum dz, sum dz*xhat, sum for d alpha) and apply pass
+//   * weight gradient of dense / depthwise convolutions
+//   * max-pool 2x2 backward, bilinear (align_corners=False) backward
+// All reductions: fp32 inside a CTA (warp shuffle -> smem), fp64 atomics across CTAs.
+#include "esn_common.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ void ldv4(const T* p, bool vec, int c, int C, float* v) {
+  if (vec) {
+    const float4 t = ld4<T>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (c + j < C) ? ld1<T>(p + j) : 0.f;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void stv4(T* p, bool vec, int c, int C, const float* v) {
+  if (vec) {
+    st4<T>(p, make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < C) st1<T>(p + j, v[j]);
+  }
+}
+
+// ---------------------------------------------------------------- channel statistics
+// block = 256 threads = (256/CG) pixel lanes x CG channel groups of 4; grid.x pixel chunks, grid.y channel blocks
+constexpr int kStatThreads = 256;
+
+template <typename T, int NQ>
+__global__ void __launch_bounds__(kStatThreads) channel_stats_kernel(const T* __restrict__ x, long long M, int C, int cs,
+                                                                     double* __restrict__ sums, long long px_per_cta) {
+  // NQ quantities per channel: 1 -> sum; 2 -> sum, sum of squares
+  __shared__ float red[NQ][kStatThreads][4];
+  const int CG = min((C + 3) / 4, 64);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.y * 64 + cg) * 4;
+  const bool vec = (cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(x) % (4 * sizeof(T))) == 0);
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const long long p0 = blockIdx.x * px_per_cta, p1 = min(M, p0 + px_per_cta);
+  if (pl < lanes && c < C) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      float v[4];
+      ldv4<T>(x + p * cs + c, vec, c, C, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += v[j];
+        if (NQ > 1) q[j] += v[j] * v[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x][j] = s[j];
+    if (NQ > 1) red[NQ - 1][threadIdx.x][j] = q[j];
+  }
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += red[0][l * CG + cg][j];
+        if (NQ > 1) q[j] += red[NQ - 1][l * CG + cg][j];
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < C) {
+        atomicAdd(sums + c + j, (double)s[j]);
+        if (NQ > 1) atomicAdd(sums + C + c + j, (double)q[j]);
+      }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* scale, float* shift, float* mean, float* invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;   // biased variance normalises (torch semantics)
+  if (var < 0) var = 0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * is;
+  scale[c] = sc;
+  shift[c] = b - (float)m * sc;
+  mean[c] = (float)m;
+  invstd[c] = is;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+  if (running_var) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------- BN + activation backward
+struct BnBwdArgs {
+  const void* x;
+  const void* dy;
+  void* dx;
+  const void* extra;
+  long long M;
+  int C, x_cs, dy_cs, dx_cs, extra_cs, act, train_stats;
+  const float *scale, *shift, *alpha, *mean, *invstd;
+  double* sums;  // [3][C]: sum dz, sum dz*xhat, sum dy*z*[z<0]
+  float *dgamma, *dbeta, *dalpha;
+  long long px_per_cta;
+};
+
+__device__ __forceinline__ float act_grad(float z, float dy, int act, float alpha) {
+  if (act == ESN_ACT_RELU) return z > 0.f ? dy : 0.f;
+  if (act == ESN_ACT_PRELU) return z >= 0.f ? dy : dy * alpha;
+  return dy;
+}
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kStatThreads) bn_act_bwd_reduce_kernel(const BnBwdArgs a) {
+  __shared__ float red[3][kStatThreads][4];
+  const int C = a.C;
+  const int CG = min((C + 3) / 4, 64);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.y * 64 + cg) * 4;
+  const TX* x = reinterpret_cast<const TX*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy);
+  const bool vx = (a.x_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(x) % (4 * sizeof(TX))) == 0);
+  const bool vg = (a.dy_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(dy) % (4 * sizeof(TG))) == 0);
+  float sc[4], sh[4], al[4], mu[4], is[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = min(c + j, C - 1);
+    sc[j] = a.scale ? a.scale[cc] : 1.f;
+    sh[j] = a.shift ? a.shift[cc] : 0.f;
+    al[j] = (a.act == ESN_ACT_PRELU) ? a.alpha[cc] : 0.f;
+    mu[j] = a.mean ? a.mean[cc] : 0.f;
+    is[j] = a.invstd ? a.invstd[cc] : 1.f;
+  }
+  float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(a.M, p0 + a.px_per_cta);
+  if (pl < lanes && c < C) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      float xv[4], gv[4];
+      ldv4<TX>(x + p * a.x_cs + c, vx, c, C, xv);
+      ldv4<TG>(dy + p * a.dy_cs + c, vg, c, C, gv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = fmaf(xv[j], sc[j], sh[j]);
+        const float dz = act_grad(z, gv[j], a.act, al[j]);
+        s0[j] += dz;
+        s1[j] += dz * (xv[j] - mu[j]) * is[j];
+        s2[j] += (z < 0.f) ? gv[j] * z : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x][j] = s0[j];
+    red[1][threadIdx.x][j] = s1[j];
+    red[2][threadIdx.x][j] = s2[j];
+  }
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s0[j] += red[0][l * CG + cg][j];
+        s1[j] += red[1][l * CG + cg][j];
+        s2[j] += red[2][l * CG + cg][j];
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < C) {
+        atomicAdd(a.sums + c + j, (double)s0[j]);
+        atomicAdd(a.sums + C + c + j, (double)s1[j]);
+        atomicAdd(a.sums + 2 * C + c + j, (double)s2[j]);
+      }
+  }
+}
+
+template <typename TX, typename TG, typename TD>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnBwdArgs a) {
+  const int C = a.C;
+  const int ncg = (C + 3) / 4;
+  const long long total = a.M * ncg;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // parameter gradients: written once by the first threads of the grid
+  if (idx < C) {
+    const int c = (int)idx;
+    if (a.dbeta) a.dbeta[c] = (float)a.sums[c];
+    if (a.dgamma) a.dgamma[c] = (float)a.sums[C + c];
+    if (a.dalpha && a.act == ESN_ACT_PRELU) a.dalpha[c] = (float)a.sums[2 * C + c];
+  }
+  if (idx >= total) return;
+  const int c = (int)(idx % ncg) * 4;
+  const long long p = idx / ncg;
+  const TX* x = reinterpret_cast<const TX*>(a.x) + p * a.x_cs + c;
+  const TG* dy = reinterpret_cast<const TG*>(a.dy) + p * a.dy_cs + c;
+  TD* dx = reinterpret_cast<TD*>(a.dx) + p * a.dx_cs + c;
+  const bool vx = (a.x_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(a.x) % (4 * sizeof(TX))) == 0);
+  const bool vg = (a.dy_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(a.dy) % (4 * sizeof(TG))) == 0);
+  const bool vd = (a.dx_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(a.dx) % (4 * sizeof(TD))) == 0);
+  float xv[4], gv[4], ev[4] = {0, 0, 0, 0}, out[4];
+  ldv4<TX>(x, vx, c, C, xv);
+  ldv4<TG>(dy, vg, c, C, gv);
+  if (a.extra) {
+    const TD* e = reinterpret_cast<const TD*>(a.extra) + p * a.extra_cs + c;
+    const bool ve = (a.extra_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(a.extra) % (4 * sizeof(TD))) == 0);
+    ldv4<TD>(e, ve, c, C, ev);
+  }
+  const float invM = (float)(1.0 / (double)a.M);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = min(c + j, C - 1);
+    const float sc = a.scale ? a.scale[cc] : 1.f, sh = a.shift ? a.shift[cc] : 0.f;
+    const float al = (a.act == ESN_ACT_PRELU) ? a.alpha[cc] : 0.f;
+    const float z = fmaf(xv[j], sc, sh);
+    const float dz = act_grad(z, gv[j], a.act, al);
+    float g;
+    if (a.train_stats) {
+      const float xhat = (xv[j] - a.mean[cc]) * a.invstd[cc];
+      g = sc * (dz - (float)a.sums[cc] * invM - xhat * (float)a.sums[C + cc] * invM);
+    } else {
+      g = sc * dz;
+    }
+    out[j] = g + ev[j];
+  }
+  stv4<TD>(dx, vd, c, C, out);
+}
+
+// ---------------------------------------------------------------- dense conv weight gradient
+// dW[tap][ci][co] += sum_p X[p + delta_tap, ci] * dY[p, co]; block computes a 64(ci) x 64(co) tile for one
+// tap over a chunk of output pixels; thread = 4x4 register tile; smem stages of 16 pixels.
+struct WgradArgs {
+  const void* x;
+  const void* dy;
+  float* dw;
+  int N, Hi, Wi, Cin, x_cs, x_nchw;
+  int Ho, Wo, Cout, dy_cs;
+  int kh, kw, stride, pad_h, pad_w, dil_h, dil_w;
+  long long px_per_cta;
+};
+
+constexpr int kWgPix = 16;
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(256) wgrad_dense_kernel(const WgradArgs a) {
+  __shared__ float xs[kWgPix][64 + 1];
+  __shared__ float gs[kWgPix][64 + 1];
+  const int tap = blockIdx.y;
+  const int r = tap / a.kw, s = tap % a.kw;
+  const int nci = (a.Cin + 63) / 64, nco = (a.Cout + 63) / 64;
+  const int ci0 = (blockIdx.z % nci) * 64, co0 = (blockIdx.z / nci) * 64;
+  (void)nco;
+  const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;   // thread tile: ci = ti*4.., co = tj*4..
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const long long M = (long long)a.N * a.Ho * a.Wo;
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(M, p0 + a.px_per_cta);
+  const TX* x = reinterpret_cast<const TX*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy);
+  for (long long pb = p0; pb < p1; pb += kWgPix) {
+    // stage kWgPix pixels x 64 channels of X (shifted by the tap) and of dY
+    for (int e = threadIdx.x; e < kWgPix * 64; e += 256) {
+      const int pp = e / 64, ch = e % 64;
+      const long long p = pb + pp;
+      float xv = 0.f, gv = 0.f;
+      if (p < p1) {
+        const int wo = (int)(p % a.Wo);
+        const int ho = (int)((p / a.Wo) % a.Ho);
+        const int n = (int)(p / ((long long)a.Wo * a.Ho));
+        const int hi = ho * a.stride - a.pad_h + r * a.dil_h, wi = wo * a.stride - a.pad_w + s * a.dil_w;
+        if (co0 + ch < a.Cout) gv = ld1<TG>(dy + p * a.dy_cs + co0 + ch);
+        if (ci0 + ch < a.Cin && hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) {
+          if (a.x_nchw)
+            xv = ld1<TX>(x + ((size_t)((size_t)n * a.Cin + ci0 + ch) * a.Hi + hi) * a.Wi + wi);
+          else
+            xv = ld1<TX>(x + ((size_t)((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs + ci0 + ch);
+        }
+      }
+      xs[pp][ch] = xv;
+      gs[pp][ch] = gv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < kWgPix; ++pp) {
+      float xv[4], gv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xv[i] = xs[pp][ti * 4 + i];
+        gv[i] = gs[pp][tj * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + ti * 4 + i, co = co0 + tj * 4 + j;
+      if (ci < a.Cin && co < a.Cout && acc[i][j] != 0.f)
+        atomicAdd(a.dw + ((size_t)tap * a.Cin + ci) * a.Cout + co, acc[i][j]);
+    }
+}
+
+// depthwise: dW[tap][c] += sum_p X[p+delta, c] * dY[p, c]
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kStatThreads) wgrad_dw_kernel(const WgradArgs a) {
+  __shared__ float red[kStatThreads][4];
+  const int tap = blockIdx.y;
+  const int r = tap / a.kw, s = tap % a.kw;
+  const int C = a.Cout;
+  const int CG = min((C + 3) / 4, 64);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.z * 64 + cg) * 4;
+  const TX* x = reinterpret_cast<const TX*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy);
+  const bool vx = (a.x_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(x) % (4 * sizeof(TX))) == 0);
+  const bool vg = (a.dy_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(dy) % (4 * sizeof(TG))) == 0);
+  float acc[4] = {0, 0, 0, 0};
+  const long long M = (long long)a.N * a.Ho * a.Wo;
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(M, p0 + a.px_per_cta);
+  if (pl < lanes && c < C) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      const int wo = (int)(p % a.Wo);
+      const int ho = (int)((p / a.Wo) % a.Ho);
+      const int n = (int)(p / ((long long)a.Wo * a.Ho));
+      const int hi = ho * a.stride - a.pad_h + r * a.dil_h, wi = wo * a.stride - a.pad_w + s * a.dil_w;
+      if (hi < 0 || hi >= a.Hi || wi < 0 || wi >= a.Wi) continue;
+      float xv[4], gv[4];
+      ldv4<TX>(x + ((size_t)((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs + c, vx, c, C, xv);
+      ldv4<TG>(dy + p * a.dy_cs + c, vg, c, C, gv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv[j], gv[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += red[l * CG + cg][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < C) atomicAdd(a.dw + (size_t)tap * C + c + j, acc[j]);
+  }
+}
+
+// ---------------------------------------------------------------- max-pool 2x2 backward (gather form)
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const TX* __restrict__ x, const TG* __restrict__ dy,
+                                                             TG* __restrict__ dx, int N, int Hi, int Wi, int C, int x_cs,
+                                                             int dy_cs, int dx_cs, int accumulate) {
+  const long long total = (long long)N * Hi * Wi * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long p = idx / C;
+  const int wi = (int)(p % Wi), hi = (int)((p / Wi) % Hi), n = (int)(p / ((long long)Wi * Hi));
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const int ho = hi / 2, wo = wi / 2;
+  float g = 0.f;
+  if (ho < Ho && wo < Wo) {
+    // first maximum in raster order wins (torch max_pool2d_with_indices)
+    float best = -INFINITY;
+    int bi = 0;
+    for (int k = 0; k < 4; ++k) {
+      const float v = ld1<TX>(x + ((size_t)((size_t)n * Hi + 2 * ho + (k >> 1)) * Wi + 2 * wo + (k & 1)) * x_cs + c);
+      if (v > best) { best = v; bi = k; }
+    }
+    if (bi == ((hi & 1) << 1 | (wi & 1))) g = ld1<TG>(dy + ((size_t)((size_t)n * Ho + ho) * Wo + wo) * dy_cs + c);
+  }
+  TG* o = dx + p * dx_cs + c;
+  st1<TG>(o, accumulate ? ld1<TG>(o) + g : g);
+}
+
+// ---------------------------------------------------------------- bilinear backward (align_corners=False)
+// d low[n,h,w,c] = sum over output pixels of d logits * weight; gather over the <= (2*ceil(1/s)+1)^2 window
+template <typename TL, typename TO>
+__global__ void __launch_bounds__(128) bilinear_bwd_kernel(const TL* __restrict__ dl, TO* __restrict__ dlow, int N, int C,
+                                                           int Hi, int Wi, int Ho, int Wo, int low_cs, float sh, float sw,
+                                                           float gscale) {
+  const long long total = (long long)N * C * Hi * Wi;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % Wi);
+  const int h = (int)((idx / Wi) % Hi);
+  const int c = (int)((idx / ((long long)Wi * Hi)) % C);
+  const int n = (int)(idx / ((long long)Wi * Hi * C));
+  // output rows whose source index floor is h-1 or h (or clamps onto h)
+  const float rh = 1.f / sh, rw = 1.f / sw;
+  int ho0 = (int)floorf(((float)h - 1.f + 0.5f) * rh - 0.5f) - 1, ho1 = (int)ceilf(((float)h + 1.f + 0.5f) * rh - 0.5f) + 1;
+  int wo0 = (int)floorf(((float)w - 1.f + 0.5f) * rw - 0.5f) - 1, wo1 = (int)ceilf(((float)w + 1.f + 0.5f) * rw - 0.5f) + 1;
+  ho0 = max(ho0, 0); ho1 = min(ho1, Ho - 1);
+  wo0 = max(wo0, 0); wo1 = min(wo1, Wo - 1);
+  const TL* plane = dl + ((size_t)n * C + c) * Ho * Wo;
+  float acc = 0.f;
+  for (int ho = ho0; ho <= ho1; ++ho) {
+    float fh = sh * (ho + 0.5f) - 0.5f;
+    fh = fh < 0.f ? 0.f : fh;
+    const int h0 = (int)fh;
+    const int h1 = h0 + ((h0 < Hi - 1) ? 1 : 0);
+    const float l1 = fh - h0, l0 = 1.f - l1;
+    const float wh = (h0 == h ? l0 : 0.f) + (h1 == h ? l1 : 0.f);
+    if (wh == 0.f) continue;
+    float rowacc = 0.f;
+    for (int wo = wo0; wo <= wo1; ++wo) {
+      float fw = sw * (wo + 0.5f) - 0.5f;
+      fw = fw < 0.f ? 0.f : fw;
+      const int w0 = (int)fw;
+      const int w1 = w0 + ((w0 < Wi - 1) ? 1 : 0);
+      const float m1 = fw - w0, m0 = 1.f - m1;
+      const float ww = (w0 == w ? m0 : 0.f) + (w1 == w ? m1 : 0.f);
+      if (ww != 0.f) rowacc += ww * ld1<TL>(plane + (size_t)ho * Wo + wo);
+    }
+    acc += wh * rowacc;
+  }
+  st1<TO>(dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c, acc * gscale);
+}
+
+inline long long pick_chunk(long long M, int other_ctas) {
+  // ~4 CTAs per SM in total
+  long long want = (4LL * 148 + other_ctas - 1) / other_ctas;
+  if (want < 1) want = 1;
+  long long chunk = (M + want - 1) / want;
+  if (chunk < 256) chunk = 256;
+  return chunk;
+}
+
+}  // namespace
+
+extern "C" int esn_channel_stats(const EsnTensor* x, double* sums, int32_t with_squares, void* stream) {
+  if (!x || !sums || !esn_valid_nhwc(*x)) return ESN_ERR_BAD_ARG;
+  const long long M = (long long)x->n * x->h * x->w;
+  const int cblocks = esn_cdiv(esn_cdiv(x->c, 4), 64);
+  const long long chunk = pick_chunk(M, cblocks);
+  dim3 grid(esn_cdiv(M, chunk), cblocks);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x->dtype == ESN_F32) {
+    if (with_squares) channel_stats_kernel<float, 2><<<grid, kStatThreads, 0, st>>>((const float*)x->ptr, M, x->c, x->c_stride, sums, chunk);
+    else channel_stats_kernel<float, 1><<<grid, kStatThreads, 0, st>>>((const float*)x->ptr, M, x->c, x->c_stride, sums, chunk);
+  } else {
+    if (with_squares) channel_stats_kernel<__nv_bfloat16, 2><<<grid, kStatThreads, 0, st>>>((const __nv_bfloat16*)x->ptr, M, x->c, x->c_stride, sums, chunk);
+    else channel_stats_kernel<__nv_bfloat16, 1><<<grid, kStatThreads, 0, st>>>((const __nv_bfloat16*)x->ptr, M, x->c, x->c_stride, sums, chunk);
+  }
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_bn_finalize(const EsnBnFinalize* p, void* stream) {
+  if (!p || !p->sums || !p->scale || !p->shift || !p->mean || !p->invstd || p->channels < 1 || p->count < 1)
+    return ESN_ERR_BAD_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  bn_finalize_kernel<<<esn_cdiv(p->channels, 128), 128, 0, st>>>(p->sums, (double)p->count, p->gamma, p->beta, p->eps,
+                                                                 p->momentum, p->running_mean, p->running_var, p->scale,
+                                                                 p->shift, p->mean, p->invstd, p->channels);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+static int fill_bn_bwd(const EsnBnBwd* p, BnBwdArgs& a) {
+  if (!p || !esn_valid_nhwc(p->x) || !esn_valid_nhwc(p->dy) || !p->sums) return ESN_ERR_BAD_ARG;
+  if (p->x.n != p->dy.n || p->x.h != p->dy.h || p->x.w != p->dy.w || p->x.c != p->dy.c) return ESN_ERR_BAD_SHAPE;
+  if (p->act == ESN_ACT_PRELU && !p->alpha) return ESN_ERR_BAD_ARG;
+  if (p->train_stats && (!p->mean || !p->invstd)) return ESN_ERR_BAD_ARG;
+  a.x = p->x.ptr;
+  a.dy = p->dy.ptr;
+  a.dx = p->dx.ptr;
+  a.extra = p->extra.ptr;
+  a.M = (long long)p->x.n * p->x.h * p->x.w;
+  a.C = p->x.c;
+  a.x_cs = p->x.c_stride;
+  a.dy_cs = p->dy.c_stride;
+  a.dx_cs = p->dx.c_stride;
+  a.extra_cs = p->extra.c_stride;
+  a.act = p->act;
+  a.train_stats = p->train_stats;
+  a.scale = p->scale;
+  a.shift = p->shift;
+  a.alpha = p->alpha;
+  a.mean = p->mean;
+  a.invstd = p->invstd;
+  a.sums = p->sums;
+  a.dgamma = p->dgamma;
+  a.dbeta = p->dbeta;
+  a.dalpha = p->dalpha;
+  return ESN_OK;
+}
+
+extern "C" int esn_bn_act_bwd_reduce(const EsnBnBwd* p, void* stream) {
+  BnBwdArgs a;
+  int rc = fill_bn_bwd(p, a);
+  if (rc) return rc;
+  const int cblocks = esn_cdiv(esn_cdiv(a.C, 4), 64);
+  a.px_per_cta = pick_chunk(a.M, cblocks);
+  dim3 grid(esn_cdiv(a.M, a.px_per_cta), cblocks);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool xf = p->x.dtype == ESN_F32, gf = p->dy.dtype == ESN_F32;
+  if (xf && gf) bn_act_bwd_reduce_kernel<float, float><<<grid, kStatThreads, 0, st>>>(a);
+  else if (xf) bn_act_bwd_reduce_kernel<float, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+  else if (gf) bn_act_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, kStatThreads, 0, st>>>(a);
+  else bn_act_bwd_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream) {
+  BnBwdArgs a;
+  int rc = fill_bn_bwd(p, a);
+  if (rc) return rc;
+  if (!esn_valid_nhwc(p->dx) || p->dx.c != p->x.c || p->dx.dtype != p->dy.dtype) return ESN_ERR_BAD_ARG;
+  if (p->extra.ptr && (!esn_valid_nhwc(p->extra) || p->extra.dtype != p->dx.dtype)) return ESN_ERR_BAD_ARG;
+  const long long total = a.M * ((a.C + 3) / 4);
+  const int grid = esn_cdiv(total > a.C ? total : a.C, 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool xf = p->x.dtype == ESN_F32, gf = p->dy.dtype == ESN_F32;
+  if (xf && gf) bn_act_bwd_apply_kernel<float, float, float><<<grid, 256, 0, st>>>(a);
+  else if (xf) bn_act_bwd_apply_kernel<float, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  else if (gf) bn_act_bwd_apply_kernel<__nv_bfloat16, float, float><<<grid, 256, 0, st>>>(a);
+  else bn_act_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
+  // p->x: forward input, p->y: gradient of the conv output, p->w: fp32 dW accumulator
+  // [kh*kw][Cin/groups][Cout] (same layout as the direct kernel's weights), accumulated with atomics.
+  if (!p || !p->w || !esn_valid_nhwc(p->y)) return ESN_ERR_BAD_ARG;
+  const EsnTensor& x = p->x;
+  const EsnTensor& dy = p->y;
+  const bool nchw = x.layout == ESN_NCHW;
+  if (nchw ? (!x.ptr || x.dtype != ESN_F32) : !esn_valid_nhwc(x)) return ESN_ERR_BAD_ARG;
+  if (p->transposed) return ESN_ERR_UNSUPPORTED;
+  const bool dw = p->groups != 1;
+  if (dw && (p->groups != x.c || x.c != dy.c || nchw)) return ESN_ERR_UNSUPPORTED;
+  const int eh = (x.h + 2 * p->pad_h - p->dil_h * (p->kh - 1) - 1) / p->stride + 1;
+  const int ew = (x.w + 2 * p->pad_w - p->dil_w * (p->kw - 1) - 1) / p->stride + 1;
+  if (eh != dy.h || ew != dy.w || x.n != dy.n) return ESN_ERR_BAD_SHAPE;
+  WgradArgs a;
+  a.x = x.ptr;
+  a.dy = dy.ptr;
+  a.dw = reinterpret_cast<float*>(const_cast<void*>(p->w));
+  a.N = x.n; a.Hi = x.h; a.Wi = x.w; a.Cin = x.c; a.x_cs = nchw ? 0 : x.c_stride; a.x_nchw = nchw;
+  a.Ho = dy.h; a.Wo = dy.w; a.Cout = dy.c; a.dy_cs = dy.c_stride;
+  a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
+  a.dil_h = p->dil_h; a.dil_w = p->dil_w;
+  const long long M = (long long)dy.n * dy.h * dy.w;
+  const int taps = p->kh * p->kw;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool xf = x.dtype == ESN_F32, gf = dy.dtype == ESN_F32;
+  if (dw) {
+    const int cblocks = esn_cdiv(esn_cdiv(dy.c, 4), 64);
+    a.px_per_cta = pick_chunk(M, taps * cblocks);
+    dim3 grid(esn_cdiv(M, a.px_per_cta), taps, cblocks);
+    if (xf && gf) wgrad_dw_kernel<float, float><<<grid, kStatThreads, 0, st>>>(a);
+    else if (xf) wgrad_dw_kernel<float, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+    else if (gf) wgrad_dw_kernel<__nv_bfloat16, float><<<grid, kStatThreads, 0, st>>>(a);
+    else wgrad_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+  } else {
+    const int tiles = esn_cdiv(x.c, 64) * esn_cdiv(dy.c, 64);
+    a.px_per_cta = pick_chunk(M, taps * tiles);
+    a.px_per_cta = (a.px_per_cta + kWgPix - 1) / kWgPix * kWgPix;
+    dim3 grid(esn_cdiv(M, a.px_per_cta), taps, tiles);
+    if (xf && gf) wgrad_dense_kernel<float, float><<<grid, 256, 0, st>>>(a);
+    else if (xf) wgrad_dense_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
+    else if (gf) wgrad_dense_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(a);
+    else wgrad_dense_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  }
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_maxpool2x2_bwd(const EsnTensor* x, const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate,
+                                  void* stream) {
+  if (!x || !dy || !dx || !esn_valid_nhwc(*x) || !esn_valid_nhwc(*dy) || !esn_valid_nhwc(*dx)) return ESN_ERR_BAD_ARG;
+  if (dy->h != x->h / 2 || dy->w != x->w / 2 || dy->c != x->c || dx->h != x->h || dx->w != x->w || dx->c != x->c ||
+      dx->dtype != dy->dtype)
+    return ESN_ERR_BAD_SHAPE;
+  const long long total = (long long)x->n * x->h * x->w * x->c;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = esn_cdiv(total, 256);
+  const bool xf = x->dtype == ESN_F32, gf = dy->dtype == ESN_F32;
+#define ESN_MPB(TX, TG)                                                                                              \
+  maxpool2x2_bwd_kernel<TX, TG><<<grid, 256, 0, st>>>((const TX*)x->ptr, (const TG*)dy->ptr, (TG*)dx->ptr, x->n, x->h, \
+                                                      x->w, x->c, x->c_stride, dy->c_stride, dx->c_stride, accumulate)
+  if (xf && gf) ESN_MPB(float, float);
+  else if (xf) ESN_MPB(float, __nv_bfloat16);
+  else if (gf) ESN_MPB(__nv_bfloat16, float);
+  else ESN_MPB(__nv_bfloat16, __nv_bfloat16);
+#undef ESN_MPB
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_bilinear_bwd(const EsnTensor* dlogits, const EsnTensor* dlow, float gscale, void* stream) {
+  if (!dlogits || !dlow || !dlogits->ptr || !esn_valid_nhwc(*dlow)) return ESN_ERR_BAD_ARG;
+  if (dlogits->layout != ESN_NCHW || dlogits->n != dlow->n || dlogits->c != dlow->c) return ESN_ERR_BAD_SHAPE;
+  const long long total = (long long)dlow->n * dlow->c * dlow->h * dlow->w;
+  const int grid = esn_cdiv(total, 128);
+  const float sh = (float)dlow->h / (float)dlogits->h, sw = (float)dlow->w / (float)dlogits->w;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool lf = dlogits->dtype == ESN_F32, of = dlow->dtype == ESN_F32;
+#define ESN_BLB(TL, TO)                                                                                            \
+  bilinear_bwd_kernel<TL, TO><<<grid, 128, 0, st>>>((const TL*)dlogits->ptr, (TO*)dlow->ptr, dlow->n, dlow->c,      \
+                                                    dlow->h, dlow->w, dlogits->h, dlogits->w, dlow->c_stride, sh, sw, \
+                                                    gscale)
+  if (lf && of) ESN_BLB(float, float);
+  else if (lf) ESN_BLB(float, __nv_bfloat16);
+  else if (of) ESN_BLB(__nv_bfloat16, float);
+  else ESN_BLB(__nv_bfloat16, __nv_bfloat16);
+#undef ESN_BLB
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}

@@ -43,6 +43,20 @@ class EsnStem(C.Structure):
                 ("with_pool", C.c_int32), ("ep", EsnEpilogue)]
 
 
+class EsnBnFinalize(C.Structure):
+    _fields_ = [("sums", C.c_void_p), ("count", C.c_int64), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("eps", C.c_float), ("momentum", C.c_float), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("channels", C.c_int32), ("_pad", C.c_int32)]
+
+
+class EsnBnBwd(C.Structure):
+    _fields_ = [("x", EsnTensor), ("dy", EsnTensor), ("dx", EsnTensor), ("extra", EsnTensor),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("alpha", C.c_void_p), ("mean", C.c_void_p),
+                ("invstd", C.c_void_p), ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("dalpha", C.c_void_p), ("act", C.c_int32), ("train_stats", C.c_int32)]
+
+
 class EsnDabPair(C.Structure):
     _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("prm", C.c_void_p),
                 ("dilation", C.c_int32), ("_pad", C.c_int32)]
@@ -56,7 +70,8 @@ class EsnHead(C.Structure):
 
 class EsnCE(C.Structure):
     _fields_ = [("logits", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
-                ("dlogits", EsnTensor), ("ignore_label", C.c_int32), ("_pad", C.c_int32)]
+                ("dlogits", EsnTensor), ("ignore_label", C.c_int32), ("_pad", C.c_int32),
+                ("gnorm", C.c_void_p), ("gout", C.c_void_p)]
 
 
 # every symbol include/esn.h declares: name -> (restype, argtypes)
@@ -72,6 +87,13 @@ SYMBOLS = {
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
+    "esn_channel_stats": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_int32, C.c_void_p]),
+    "esn_bn_finalize": (C.c_int, [C.POINTER(EsnBnFinalize), C.c_void_p]),
+    "esn_bn_act_bwd_reduce": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
+    "esn_bn_act_bwd_apply": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
+    "esn_conv2d_wgrad": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_maxpool2x2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
+    "esn_bilinear_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_float, C.c_void_p]),
     "esn_version": (C.c_int, []),
     "esn_strerror": (C.c_char_p, [C.c_int]),
     "esn_launch_count": (C.c_int64, []),

@@ -149,15 +149,28 @@ class ConvPrep:
         (padded input channels must hold finite values; padded outputs evaluate to act(0))."""
         device = device or conv.weight.device
         transposed = isinstance(conv, torch.nn.ConvTranspose2d)
-        w = _f32(conv.weight, device)
+        self._init(_f32(conv.weight, device), None if conv.bias is None else _f32(conv.bias, device), conv.stride[0],
+                   conv.padding, conv.dilation, conv.groups, transposed,
+                   conv.output_padding[0] if transposed else 0, scale, shift, act, alpha, device, cin_pad, cout_pad)
+
+    @classmethod
+    def from_weight(cls, w, stride=1, padding=(0, 0), dilation=(1, 1), groups=1, transposed=False, out_pad=0,
+                    bias=None, scale=None, shift=None, act=L.ACT_NONE, alpha=None):
+        """Build from a raw weight tensor: (Cout, Cin/groups, kh, kw), or (Cin, Cout, kh, kw) if transposed."""
+        self = cls.__new__(cls)
+        self._init(w.detach().float(), bias, stride, tuple(padding), tuple(dilation), groups, transposed, out_pad,
+                   scale, shift, act, alpha, w.device, None, None)
+        return self
+
+    def _init(self, w, bias, stride, padding, dilation, groups, transposed, out_pad, scale, shift, act, alpha, device,
+              cin_pad, cout_pad):
         if transposed:          # (Cin, Cout, kh, kw) -> (Cout, Cin, kh, kw)
             w = w.permute(1, 0, 2, 3).contiguous()
-        bias = None if conv.bias is None else _f32(conv.bias, device)
         if cin_pad is not None and cin_pad > w.shape[1]:
-            assert conv.groups == 1
+            assert groups == 1
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
         if cout_pad is not None and cout_pad > w.shape[0]:
-            assert conv.groups == 1
+            assert groups == 1
             extra = cout_pad - w.shape[0]
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, extra))
             zeros = torch.zeros(extra, device=device)
@@ -169,15 +182,15 @@ class ConvPrep:
                 bias = torch.cat([bias, zeros])
         w = w.contiguous()
         self.cout, cin_g, self.kh, self.kw = w.shape
-        self.groups = conv.groups
-        self.cin = cin_g * conv.groups
+        self.groups = groups
+        self.cin = cin_g * groups
         if self.groups != 1 and not (self.groups == self.cin == self.cout):
             raise NotImplementedError("only dense and depthwise convs are supported, got groups=%d" % self.groups)
         self.transposed = int(transposed)
-        self.stride = conv.stride[0]
-        self.pad_h, self.pad_w = conv.padding
-        self.dil_h, self.dil_w = conv.dilation
-        self.out_pad = conv.output_padding[0] if transposed else 0
+        self.stride = stride
+        self.pad_h, self.pad_w = padding
+        self.dil_h, self.dil_w = dilation
+        self.out_pad = out_pad
         taps = self.kh * self.kw
         # direct layout: [tap][Cin/groups][Cout]
         self.w_direct = w.permute(2, 3, 1, 0).reshape(taps, cin_g, self.cout).contiguous()
@@ -387,13 +400,17 @@ def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, l
                  want_logits, want_mask, logits_dtype)
 
 
-def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False):
-    """Returns (sums[2] = [sum w*nll, sum w], unnormalised dlogits or None)."""
+def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, sums=None, gnorm=None, gout=None):
+    """Returns (sums[2] = [sum w*nll, sum w], dlogits or None); dlogits are scaled by gout/gnorm
+    (device scalars) when given, unnormalised otherwise."""
     require_cuda(logits, "weighted_ce")
     logits = logits.contiguous()
     target = target.contiguous()
-    sums = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float32, device=logits.device)
     p = L.EsnCE()
+    p.gnorm = gnorm.data_ptr() if gnorm is not None else None
+    p.gout = gout.data_ptr() if gout is not None else None
     p.logits = tdesc(logits)
     p.logits.layout, p.logits.c_stride = L.ESN_NCHW, 0
     p.target = target.data_ptr()
@@ -405,7 +422,7 @@ def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False):
         p.dlogits = tdesc(g)
         p.dlogits.layout, p.dlogits.c_stride = L.ESN_NCHW, 0
     p.ignore_label = ignore_label
-    L.check(L.lib.esn_weighted_ce(C.byref(p), stream()), "esn_weighted_ce")
+    _call(L.lib.esn_weighted_ce, "esn_weighted_ce", (C.byref(p),), logits.numel() * logits.element_size() * (2 if want_grad else 1))
     return sums, g
 
 

@@ -1,0 +1,341 @@
+"""Training path: forward kernels + hand-written backward on a tiny tape.
+
+No torch.autograd inside the model: every activation-sized computation (forward and backward) is
+a C-ABI kernel call.  The model's train-mode ``forward`` records backward closures on a `Tape`; one
+`torch.autograd.Function` around the whole network hands the parameter gradients back to
+PyTorch, so the reference's ``output = model(images); loss = criterion(output, labels);
+loss.backward(); optimizer.step()`` (train.py:351-355) works unchanged.
+
+Semantics follow torch: train-mode BatchNorm normalises with the biased batch
+variance and updates running_var with the unbiased one; PReLU per channel; MaxPool2d(2,2) routes
+the gradient to the first maximum; bilinear align_corners=False.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+class V:
+    """An activation and its gradient slot.  A V may be a channel slice of a wider (concat) V, in
+    which case its gradient is the same slice of the parent's gradient buffer."""
+    __slots__ = ("t", "_g", "parent", "lo", "hi")
+
+    def __init__(self, t, parent=None, lo=0, hi=0):
+        self.t, self._g, self.parent, self.lo, self.hi = t, None, parent, lo, hi
+
+    @property
+    def g(self):
+        if self.parent is not None:
+            pg = self.parent.g
+            return None if pg is None else pg[:, self.lo:self.hi]
+        return self._g
+
+    def slice(self, lo, hi):
+        return V(self.t[:, lo:hi], self, lo, hi)
+
+    def add_grad(self, fn):
+        """fn(existing) -> tensor holding existing + this consumer's contribution.  For slices the
+        contribution is accumulated in place into the parent's buffer."""
+        if self.parent is not None:
+            root = self.parent
+            while root.parent is not None:
+                root = root.parent
+            if root._g is None:     # gradient buffer of the whole concat tensor, zero-filled once
+                n, c, h, w = root.t.shape
+                root._g = ops.new_act(n, c, h, w, root.t.dtype, root.t.device, c_alloc=root.t.stride(3), zero=True)
+            view = self.g
+            out = fn(view, view)
+            assert out.data_ptr() == view.data_ptr()
+        else:
+            self._g = fn(self._g, None)
+
+
+class Tape:
+    def __init__(self):
+        self.steps = []
+        self.param_grads = {}     # parameter -> fp32 gradient tensor
+
+    def push(self, fn):
+        self.steps.append(fn)
+
+    def add_param_grad(self, p, g):
+        g = g.to(p.dtype) if g.dtype != p.dtype else g
+        self.param_grads[p] = g if p not in self.param_grads else self.param_grads[p] + g
+
+    def backward(self):
+        for fn in reversed(self.steps):
+            fn()
+        self.steps = []
+        return self.param_grads
+
+
+def _f64zeros(n, device):
+    return torch.zeros(n, dtype=torch.float64, device=device)
+
+
+# --------------------------------------------------------------------------- convolution
+class ConvT:
+    """nn.Conv2d (dense or depthwise) for training: forward = raw conv (+bias); backward = input
+    gradient through the (tensor-core) conv kernels with flipped / transposed weights, weight
+    gradient through esn_conv2d_wgrad."""
+
+    def __init__(self, conv):
+        self.conv = conv
+        self._key = None
+
+    def preps(self):
+        c = self.conv
+        w = c.weight
+        key = (w.data_ptr(), w._version, None if c.bias is None else c.bias._version)
+        if self._key != key:
+            wd = w.detach().float()
+            bias = None if c.bias is None else c.bias.detach().float()
+            s, pad, dil, g = c.stride[0], tuple(c.padding), tuple(c.dilation), c.groups
+            kh, kw = wd.shape[2:]
+            self.fwd_prep = ops.ConvPrep.from_weight(wd, s, pad, dil, g, bias=bias)
+            if s == 1:
+                wf = wd.flip(2, 3) if g != 1 else wd.permute(1, 0, 2, 3).flip(2, 3)
+                self.dgrad_prep = ops.ConvPrep.from_weight(wf.contiguous(), 1,
+                                                           (dil[0] * (kh - 1) - pad[0], dil[1] * (kw - 1) - pad[1]), dil, g)
+            else:   # conv_transpose2d(dy, W): W (Cout, Cin, kh, kw) read as (in=Cout, out=Cin)
+                if g != 1:
+                    raise NotImplementedError("strided depthwise conv backward")
+                self.dgrad_prep = ops.ConvPrep.from_weight(wd, s, pad, dil, 1, transposed=True)
+            self._key = key
+        return self.fwd_prep, self.dgrad_prep
+
+    def forward(self, tape, x, out=None, residual=None, need_dx=True, dtype=None):
+        """x: V (or a raw NCHW input tensor wrapped in V with need_dx=False)."""
+        fwd_prep, dgrad_prep = self.preps()
+        xt = x.t
+        if out is None:
+            n, _, h, w = xt.shape
+            ho, wo = fwd_prep.out_hw(h, w)
+            out = ops.new_act(n, fwd_prep.cout, ho, wo, dtype or (xt.dtype if ops.is_nhwc(xt) else torch.float32), xt.device)
+        y = out if isinstance(out, V) else V(out)      # `out` may be a channel slice (V) of a concat buffer
+        ops.conv2d(xt, fwd_prep, out=y.t, residual=None if residual is None else residual.t)
+        conv = self.conv
+
+        def bwd():
+            dy = y.g
+            # weight gradient [tap][Cin/g][Cout] -> (Cout, Cin/g, kh, kw)
+            kh, kw = fwd_prep.kh, fwd_prep.kw
+            cin_g = fwd_prep.cin // fwd_prep.groups
+            dwbuf = torch.zeros((kh * kw, cin_g, fwd_prep.cout), dtype=torch.float32, device=dy.device)
+            p = L.EsnConv()
+            p.x, p.y = ops.tdesc(xt), ops.tdesc(dy)
+            p.w = dwbuf.data_ptr()
+            p.kh, p.kw, p.stride = kh, kw, fwd_prep.stride
+            p.pad_h, p.pad_w, p.dil_h, p.dil_w = fwd_prep.pad_h, fwd_prep.pad_w, fwd_prep.dil_h, fwd_prep.dil_w
+            p.groups, p.transposed, p.cout_pad = fwd_prep.groups, 0, fwd_prep.cout_pad
+            flops = 2 * dy.shape[0] * dy.shape[2] * dy.shape[3] * fwd_prep.cout * cin_g * kh * kw
+            ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy), flops)
+            tape.add_param_grad(conv.weight, dwbuf.view(kh, kw, cin_g, fwd_prep.cout).permute(3, 2, 0, 1))
+            if conv.bias is not None:
+                sums = _f64zeros(fwd_prep.cout, dy.device)
+                d = ops.tdesc(dy)
+                ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 0),
+                          ops._nbytes(dy))
+                tape.add_param_grad(conv.bias, sums.float())
+            if residual is not None:
+                residual.add_grad(lambda ex, dst: dy if ex is None else ops.affine_act(dy, None, None, None, L.ACT_NONE,
+                                                                                        out=dst, residual=ex))
+            if need_dx:
+                if dgrad_prep.transposed:
+                    h = xt.shape[2]
+                    dgrad_prep.out_pad = h - ((dy.shape[2] - 1) * dgrad_prep.stride - 2 * dgrad_prep.pad_h
+                                              + dgrad_prep.dil_h * (dgrad_prep.kh - 1) + 1)
+                x.add_grad(lambda ex, dst: ops.conv2d(dy, dgrad_prep, out=dst, residual=ex))
+
+        tape.push(bwd)
+        return y
+
+
+# --------------------------------------------------------------------------- BatchNorm (+ activation)
+class BNActT:
+    """Train-mode nn.BatchNorm2d followed by PReLU / ReLU / nothing; or, with bn=None, the
+    activation alone (its backward then also yields sum(dz) = the bias gradient of a preceding conv)."""
+
+    def __init__(self, bn, act, prelu=None):
+        self.bn, self.act, self.prelu = bn, act, prelu
+
+    def forward(self, tape, x, out=None):
+        xt = x.t
+        n, c, h, w = xt.shape
+        dev = xt.device
+        bn = self.bn
+        alpha = None if self.prelu is None else self.prelu.weight.detach()
+        scale = shift = mean = invstd = None
+        if bn is not None:
+            sums = _f64zeros(2 * c, dev)
+            d = ops.tdesc(xt)
+            ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 1),
+                      ops._nbytes(xt))
+            scale, shift, mean, invstd = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
+            f = L.EsnBnFinalize()
+            f.sums, f.count = sums.data_ptr(), n * h * w
+            f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+            f.eps, f.momentum = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
+            f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            f.scale, f.shift, f.mean, f.invstd = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr()
+            f.channels = c
+            ops._call(L.lib.esn_bn_finalize, "esn_bn_finalize", (C.byref(f),))
+            bn.num_batches_tracked += 1
+        if isinstance(out, V):
+            y = out
+            ops.affine_act(xt, scale, shift, alpha, self.act, out=y.t)
+        else:
+            y = V(ops.affine_act(xt, scale, shift, alpha, self.act, out=out))
+        act, prelu = self.act, self.prelu
+
+        def bwd():
+            dy = y.g
+            sums3 = _f64zeros(3 * c, dev)
+            dgamma = torch.empty(c, dtype=torch.float32, device=dev) if bn is not None else None
+            dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+            dalpha = torch.empty(c, dtype=torch.float32, device=dev) if prelu is not None else None
+
+            def run(ex, dst):
+                dx = dst if dst is not None else ops.new_act(n, c, h, w, dy.dtype, dev)
+                p = L.EsnBnBwd()
+                p.x, p.dy, p.dx = ops.tdesc(xt), ops.tdesc(dy), ops.tdesc(dx)
+                if ex is not None:
+                    p.extra = ops.tdesc(ex)
+                p.scale = scale.data_ptr() if scale is not None else None
+                p.shift = shift.data_ptr() if shift is not None else None
+                p.alpha = alpha.data_ptr() if alpha is not None else None
+                p.mean = mean.data_ptr() if mean is not None else None
+                p.invstd = invstd.data_ptr() if invstd is not None else None
+                p.sums = sums3.data_ptr()
+                p.dgamma = dgamma.data_ptr() if dgamma is not None else None
+                p.dbeta = dbeta.data_ptr()
+                p.dalpha = dalpha.data_ptr() if dalpha is not None else None
+                p.act, p.train_stats = act, int(bn is not None)
+                nb = ops._nbytes(xt) + ops._nbytes(dy)
+                ops._call(L.lib.esn_bn_act_bwd_reduce, "esn_bn_act_bwd_reduce", (C.byref(p),), nb)
+                ops._call(L.lib.esn_bn_act_bwd_apply, "esn_bn_act_bwd_apply", (C.byref(p),), nb + ops._nbytes(dx))
+                return dx
+
+            x.add_grad(run)
+            if bn is not None:
+                tape.add_param_grad(bn.weight, dgamma)
+                tape.add_param_grad(bn.bias, dbeta)
+            if prelu is not None:
+                tape.add_param_grad(prelu.weight, dalpha)
+
+        tape.push(bwd)
+        return y
+
+
+def add(tape, a, b):
+    """y = a + b (branch merge)."""
+    y = V(ops.affine_act(a.t, None, None, None, L.ACT_NONE, residual=b.t))
+
+    def bwd():
+        dy = y.g
+        for v in (a, b):
+            v.add_grad(lambda ex, dst: dy if (ex is None and dst is None) else
+                       ops.affine_act(dy, None, None, None, L.ACT_NONE, out=dst, residual=ex))
+    tape.push(bwd)
+    return y
+
+
+def maxpool2x2(tape, x, out):
+    """MaxPool2d(2,2) of x written into `out` (a channel slice of a concat buffer)."""
+    y = out
+    ops.maxpool2x2(x.t, out.t)
+
+    def bwd():
+        dy = y.g
+
+        def run(ex, dst):
+            n, c, h, w = x.t.shape
+            dx = dst if dst is not None else (ex if ex is not None else ops.new_act(n, c, h, w, dy.dtype, dy.device))
+            dxd, dyd, xd = ops.tdesc(dx), ops.tdesc(dy), ops.tdesc(x.t)
+            ops._call(L.lib.esn_maxpool2x2_bwd, "esn_maxpool2x2_bwd", (C.byref(xd), C.byref(dyd), C.byref(dxd),
+                                                                      int(ex is not None)), 2 * ops._nbytes(dx))
+            return dx
+        x.add_grad(run)
+    tape.push(bwd)
+    return y
+
+
+def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32):
+    """F.interpolate(scores, (H, W), bilinear, align_corners=False) -> NCHW logits; backward gathers."""
+    classes = scores.t.shape[1]
+    logits, _ = ops.head_bilinear(scores.t, classes, out_h, out_w, True, False, logits_dtype)
+    holder = {}
+
+    def bwd():
+        dl = holder["dlogits"]
+
+        def run(ex, dst):
+            assert ex is None
+            n, c, h, w = scores.t.shape
+            dlow = ops.new_act(n, c, h, w, scores.t.dtype, dl.device, c_alloc=scores.t.stride(3))
+            a, b = ops.tdesc(dl), ops.tdesc(dlow)
+            a.layout, a.c_stride = L.ESN_NCHW, 0
+            ops._call(L.lib.esn_bilinear_bwd, "esn_bilinear_bwd", (C.byref(a), C.byref(b), C.c_float(1.0)),
+                      dl.numel() * dl.element_size())
+            return dlow
+        scores.add_grad(run)
+    tape.push(bwd)
+    return logits, holder
+
+
+# --------------------------------------------------------------------------- autograd glue
+class _NetFn(torch.autograd.Function):
+    """One autograd node for the whole network: forward runs the kernels and records the tape,
+    backward replays it and returns the parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, run_forward, x, *params):
+        logits, tape, holder = run_forward(x)
+        ctx.tape, ctx.holder, ctx.params = tape, holder, params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.holder["dlogits"] = dlogits.contiguous()
+        grads = ctx.tape.backward()
+        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def run_network(model, run_forward, x):
+    params = [p for p in model.parameters() if p.requires_grad]
+    return _NetFn.apply(run_forward, x, *params)
+
+
+class _CEFn(torch.autograd.Function):
+    """CrossEntropyLoss2d (utils/losses/loss.py:15-32): weighted mean over non-ignored pixels of the
+    GLOBAL batch -- under torch.distributed the two sums are all-reduced before the division so the
+    loss and its gradient equal the reference's gathered-batch value."""
+
+    @staticmethod
+    def forward(ctx, logits, target, weight, ignore_label):
+        lg = logits.detach().contiguous()
+        sums, _ = ops.weighted_ce(lg, target, weight, ignore_label, want_grad=False)
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(sums)
+            ctx.world = torch.distributed.get_world_size()
+        else:
+            ctx.world = 1
+        ctx.save_for_backward(lg, target, sums)
+        ctx.weight, ctx.ignore = weight, ignore_label
+        return sums[0] / sums[1]
+
+    @staticmethod
+    def backward(ctx, gout):
+        lg, target, sums = ctx.saved_tensors
+        gout = gout.detach().float().reshape(1).contiguous()
+        scratch = torch.zeros(2, dtype=torch.float32, device=lg.device)
+        _, g = ops.weighted_ce(lg, target, ctx.weight, ctx.ignore, want_grad=True, sums=scratch, gnorm=sums[1:2],
+                               gout=gout)
+        return g, None, None, None
+
+
+def cross_entropy(logits, target, weight=None, ignore_label=255):
+    return _CEFn.apply(logits, target, weight, ignore_label)

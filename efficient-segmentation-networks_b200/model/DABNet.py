@@ -294,6 +294,11 @@ class DABNet(nn.Module):
         return cached[1]
 
     def forward(self, input):
+        if self.training:
+            # batch-statistics BatchNorm + recorded backward (esn/train.py); one autograd node for the net
+            from esn import train as T
+            from model._dabnet_train import dabnet_train_forward
+            return T.run_network(self, lambda x: dabnet_train_forward(self, x), input)
         scores, (h, w), dt = self._scores(input)
         ldt = torch.bfloat16 if dt == torch.bfloat16 else torch.float32
         return ops.head_bilinear(scores, scores.shape[1], h, w, True, False, ldt)[0]

@@ -1,0 +1,100 @@
+"""Train-mode forward of DABNet on the training kernels (esn/train.py): same graph as the
+reference's DABNet.forward (model/DABNet.py:160-183) with batch-statistics BatchNorm, recording the
+backward on a tape.  Concats are channel slices of one buffer (forward and gradient)."""
+import torch
+
+from esn import ops
+from esn import train as T
+from esn._lib import ACT_NONE, ACT_PRELU
+
+
+def _convT(conv):
+    t = conv.__dict__.get("_esn_T")
+    if t is None:
+        t = T.ConvT(conv)
+        conv.__dict__["_esn_T"] = t
+    return t
+
+
+def _bnprelu(tape, m, x, out=None):
+    return T.BNActT(m.bn, ACT_PRELU, m.acti).forward(tape, x, out=out)
+
+
+def _conv(tape, m, x, out=None, need_dx=True, dtype=None):
+    """DABNet `Conv` wrapper: conv (bias=False) [+ BNPReLU]."""
+    if not m.bn_acti:
+        return _convT(m.conv).forward(tape, x, out=out, need_dx=need_dx, dtype=dtype)
+    y = _convT(m.conv).forward(tape, x, need_dx=need_dx, dtype=dtype)
+    return _bnprelu(tape, m.bn_prelu, y, out=out)
+
+
+def _dab_module(tape, m, xin, out=None):
+    b = _bnprelu(tape, m.bn_relu_1, xin)
+    t = _conv(tape, m.conv3x3, b)
+    v1 = _conv(tape, m.dconv1x3, _conv(tape, m.dconv3x1, t))
+    v2 = _conv(tape, m.ddconv1x3, _conv(tape, m.ddconv3x1, t))
+    s = T.add(tape, v1, v2)
+    w = _bnprelu(tape, m.bn_relu_2, s)
+    return _convT(m.conv1x1.conv).forward(tape, w, out=out, residual=xin)      # output + input
+
+
+def _down(tape, m, x, out, dt):
+    """DownSamplingBlock: conv3x3 s2 [|| maxpool] -> BNPReLU, written into `out` (a V slice)."""
+    n, _, h, w = x.t.shape
+    pre = T.V(ops.new_act(n, m.nOut, h // 2, w // 2, dt, x.t.device))
+    nc = m.conv3x3.conv.out_channels
+    if m.nIn < m.nOut:
+        _convT(m.conv3x3.conv).forward(tape, x, out=pre.slice(0, nc))
+        T.maxpool2x2(tape, x, pre.slice(nc, m.nOut))
+    else:
+        _convT(m.conv3x3.conv).forward(tape, x, out=pre)
+    return _bnprelu(tape, m.bn_prelu, pre, out=out)
+
+
+def dabnet_train_forward(model, input):
+    ops.require_cuda(input, "DABNet")
+    if input.dtype != torch.float32 or not input.is_contiguous():
+        input = input.float().contiguous()
+    dt = ops.compute_dtype(input)
+    dev = input.device
+    n, _, H, W = input.shape
+    tape = T.Tape()
+
+    d1 = model.down_1(input)          # input-injection pyramid: no parameters, no gradient needed
+    d2 = model.down_1(d1)
+    d3 = model.down_1(d2)
+
+    def cat_buffer(c, like):
+        hh, ww = like.shape[2:]
+        return T.V(ops.new_act(n, c, hh, ww, dt, dev, c_alloc=(c + 7) // 8 * 8, zero=True))
+
+    x = T.V(input)
+    y = _conv(tape, model.init_conv[0], x, need_dx=False, dtype=dt)
+    y = _conv(tape, model.init_conv[1], y)
+    cat0 = cat_buffer(35, d1)
+    _conv(tape, model.init_conv[2], y, out=cat0.slice(0, 32))
+    ops.affine_act(d1, None, None, None, ACT_NONE, out=cat0.t[:, 32:35])
+    c0 = _bnprelu(tape, model.bn_prelu_1, cat0)
+
+    cat1 = cat_buffer(131, d2)
+    y = _down(tape, model.downsample_1, c0, cat1.slice(64, 128), dt)
+    blocks = list(model.DAB_Block_1)
+    for i, blk in enumerate(blocks):
+        y = _dab_module(tape, blk, y, out=cat1.slice(0, 64) if i == len(blocks) - 1 else None)
+    ops.affine_act(d2, None, None, None, ACT_NONE, out=cat1.t[:, 128:131])
+    c1 = _bnprelu(tape, model.bn_prelu_2, cat1)
+
+    cat2 = cat_buffer(259, d3)
+    y = _down(tape, model.downsample_2, c1, cat2.slice(128, 256), dt)
+    blocks = list(model.DAB_Block_2)
+    for i, blk in enumerate(blocks):
+        y = _dab_module(tape, blk, y, out=cat2.slice(0, 128) if i == len(blocks) - 1 else None)
+    ops.affine_act(d3, None, None, None, ACT_NONE, out=cat2.t[:, 256:259])
+    c2 = _bnprelu(tape, model.bn_prelu_3, cat2)
+
+    classes = model.classifier[0].conv.out_channels
+    hh, ww = d3.shape[2:]
+    scores = T.V(ops.new_act(n, classes, hh, ww, dt, dev, c_alloc=32))
+    _conv(tape, model.classifier[0], c2, out=scores)
+    logits, holder = T.bilinear_logits(tape, scores, H, W, torch.float32)
+    return logits, tape, holder

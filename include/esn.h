@@ -177,8 +177,9 @@ int esn_head_bilinear(const EsnHead* p, void* stream);
 
 /* Weighted cross-entropy over NCHW logits (utils/losses/loss.py:15-32):
  *   sums[0] += sum_i w[y_i]*nll_i,  sums[1] += sum_i w[y_i]   (fp32 atomics per CTA)
- * and, if dlogits != NULL, the UNNORMALISED gradient w[y_i]*(softmax - onehot);
- * the caller scales by 1/sums[1] (after the cross-rank all-reduce of sums). */
+ * and, if dlogits != NULL, the gradient w[y_i]*(softmax - onehot) * (*gout) / (*gnorm); gnorm is the
+ * device scalar holding sum_i w[y_i] AFTER the cross-rank all-reduce (so data-parallel training
+ * reproduces the reference's gathered-batch weighted mean), NULL = unnormalised. */
 typedef struct EsnCE {
   EsnTensor logits;       /* NCHW f32/bf16 */
   const int64_t* target;  /* (N,H,W) */
@@ -187,8 +188,76 @@ typedef struct EsnCE {
   EsnTensor dlogits;      /* optional NCHW, same dtype as logits */
   int32_t ignore_label;
   int32_t _pad;
+  const float* gnorm;     /* optional device scalar: dlogits are divided by *gnorm (the global sum of weights) */
+  const float* gout;      /* optional device scalar: upstream gradient of the loss */
 } EsnCE;
 int esn_weighted_ce(const EsnCE* p, void* stream);
+
+/* ------------------------------------------------------------------ training path
+ * Train-mode BatchNorm2d (torch semantics: biased batch variance normalises, running_var is updated
+ * with the unbiased one, momentum as given) is split the way the fused inference epilogue wants it:
+ *   esn_channel_stats  : sums[0..C) += sum_x, sums[C..2C) += sum_x^2 over N*H*W (fp64 atomics)
+ *   esn_bn_finalize    : scale = gamma*invstd, shift = beta - mean*scale (consumed by esn_affine_act /
+ *                        the conv epilogues), saves mean / invstd, updates the running statistics
+ * Replaces aten::native_batch_norm(training=True) of every nn.BatchNorm2d on the path
+ * (ERFNet.py:21,38,45,107; DABNet.py:41). */
+int esn_channel_stats(const EsnTensor* x, double* sums, int32_t with_squares, void* stream);
+
+typedef struct EsnBnFinalize {
+  const double* sums;      /* [2][C] from esn_channel_stats */
+  int64_t count;           /* N*H*W */
+  const float* gamma;      /* [C] or NULL */
+  const float* beta;       /* [C] or NULL */
+  float eps, momentum;
+  float* running_mean;     /* [C] updated in place, or NULL */
+  float* running_var;      /* [C] updated in place, or NULL */
+  float* scale;            /* out [C] */
+  float* shift;            /* out [C] */
+  float* mean;             /* out [C] */
+  float* invstd;           /* out [C] */
+  int32_t channels;
+  int32_t _pad;
+} EsnBnFinalize;
+int esn_bn_finalize(const EsnBnFinalize* p, void* stream);
+
+/* Backward of y = act(x*scale + shift) where (scale, shift) come from train-mode BN (train_stats=1)
+ * or are constants (train_stats=0: conv bias + ReLU, eval BN).  dz = dy * act'(z).
+ *   esn_bn_act_bwd_reduce: sums[0..C) += sum dz, [C..2C) += sum dz*xhat, [2C..3C) += sum dy*z*[z<0]
+ *   esn_bn_act_bwd_apply : dx = scale*(dz - mean(dz) - xhat*mean(dz*xhat)) (+ extra), and writes
+ *                          dbeta = sum dz, dgamma = sum dz*xhat, dalpha = sum dy*z*[z<0]
+ * Replaces native_batch_norm_backward + _prelu_kernel_backward / threshold_backward (+ the add of a
+ * second consumer's gradient, passed as `extra`). */
+typedef struct EsnBnBwd {
+  EsnTensor x;        /* BN input (= conv output), saved by the forward */
+  EsnTensor dy;       /* gradient w.r.t. the activation output */
+  EsnTensor dx;       /* out: gradient w.r.t. x (same dtype as dy) */
+  EsnTensor extra;    /* optional: added to dx (ptr NULL = none) */
+  const float* scale; /* [C] as used by the forward (NULL = 1) */
+  const float* shift; /* [C] (NULL = 0) */
+  const float* alpha; /* [C] PReLU slopes */
+  const float* mean;  /* [C] batch mean   (train_stats) */
+  const float* invstd;/* [C] 1/sqrt(var+eps) (train_stats) */
+  double* sums;       /* [3][C], zeroed by the caller before the reduce pass */
+  float* dgamma;      /* out [C] or NULL */
+  float* dbeta;       /* out [C] or NULL */
+  float* dalpha;      /* out [C] or NULL */
+  int32_t act;
+  int32_t train_stats;
+} EsnBnBwd;
+int esn_bn_act_bwd_reduce(const EsnBnBwd* p, void* stream);
+int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream);
+
+/* Weight gradient of a dense or depthwise Conv2d: p->x = forward input, p->y = gradient of the conv
+ * output, p->w = fp32 accumulator [kh*kw][Cin/groups][Cout] (zeroed by the caller; atomics).
+ * Replaces the weight branch of aten::convolution_backward.  The input gradient is the transposed /
+ * flipped convolution and runs through esn_conv2d_umma / esn_conv2d_direct. */
+int esn_conv2d_wgrad(const EsnConv* p, void* stream);
+
+/* MaxPool2d(2,2) backward (first maximum wins, as max_pool2d_with_indices), optionally accumulating
+ * into dx; bilinear (align_corners=False) backward from NCHW d logits to NHWC low-res scores,
+ * scaled by gscale (1 / sum of class weights: the loss normalisation). */
+int esn_maxpool2x2_bwd(const EsnTensor* x, const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);
+int esn_bilinear_bwd(const EsnTensor* dlogits, const EsnTensor* dlow, float gscale, void* stream);
 
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);

@@ -1,0 +1,194 @@
+"""Training path (GPU): kernel-level backward parity against torch autograd (fp32, TF32 off) and
+model-level parity of DABNet's loss / gradients against the reference's fp64 golden values."""
+import ctypes as C
+import json
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from conftest import spec_state_dict
+from oracle import fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(x, dtype, ops, c_alloc=None):
+    n, c, h, w = x.shape
+    y = ops.new_act(n, c, h, w, dtype, x.device, c_alloc=c_alloc)
+    y.copy_(x)
+    return y
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("c,act", [(64, "prelu"), (35, "prelu"), (16, "relu")])
+def test_bn_act_forward_backward_matches_torch(c, act):
+    from esn import ops, train as T
+    from esn._lib import ACT_PRELU, ACT_RELU
+    torch.manual_seed(0)
+    bn = nn.BatchNorm2d(c, eps=1e-3).cuda()
+    bn_ref = nn.BatchNorm2d(c, eps=1e-3).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1)
+        bn_ref.load_state_dict(bn.state_dict())
+    prelu = nn.PReLU(c).cuda() if act == "prelu" else None
+    if prelu is not None:
+        with torch.no_grad():
+            prelu.weight.uniform_(0.05, 0.45)
+    x = (torch.randn(2, c, 12, 20, device="cuda") * 3 + 1).requires_grad_(True)
+    ref = bn_ref(x)
+    ref = F.prelu(ref, prelu.weight) if prelu is not None else F.relu(ref)
+    gy = torch.randn_like(ref)
+    extra = torch.randn_like(ref)
+    params = [bn_ref.weight, bn_ref.bias] + ([prelu.weight] if prelu is not None else [])
+    grads = torch.autograd.grad(ref, [x] + params, gy)
+    tape = T.Tape()
+    xv = T.V(_nhwc(x.detach(), torch.float32, ops, c_alloc=(c + 7) // 8 * 8))
+    xv._g = _nhwc(extra, torch.float32, ops)              # a second consumer's gradient, already present
+    y = T.BNActT(bn, ACT_PRELU if prelu is not None else ACT_RELU, prelu).forward(tape, xv)
+    assert torch.allclose(y.t, ref.detach(), atol=2e-5, rtol=1e-5)
+    assert torch.allclose(bn.running_mean, bn_ref.running_mean, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(bn.running_var, bn_ref.running_var, atol=1e-6, rtol=1e-5)
+    y._g = _nhwc(gy, torch.float32, ops)
+    pg = tape.backward()
+    assert _rel(xv.g, grads[0] + extra) < 1e-4
+    assert _rel(pg[bn.weight], grads[1]) < 1e-4
+    assert _rel(pg[bn.bias], grads[2]) < 1e-4
+    if prelu is not None:
+        assert _rel(pg[prelu.weight], grads[3]) < 1e-4
+
+
+WG_CASES = [
+    # cin, cout, k, stride, pad, dil, groups, H, W
+    (64, 32, 3, 1, 1, 1, 1, 12, 20),
+    (32, 64, 1, 1, 0, 1, 1, 12, 20),
+    (35, 29, 3, 2, 1, 1, 1, 12, 20),
+    (131, 128, 3, 2, 1, 1, 1, 8, 12),
+    (32, 32, (3, 1), 1, (4, 0), (4, 1), 32, 16, 20),
+    (64, 64, (1, 3), 1, (0, 2), (1, 2), 64, 10, 24),
+    (16, 16, (3, 1), 1, (1, 0), (1, 1), 1, 12, 20),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_backward_matches_torch(case, dtype):
+    from esn import ops, train as T
+    cin, cout, k, stride, pad, dil, groups, H, W = case
+    torch.manual_seed(1)
+    conv = nn.Conv2d(cin, cout, k, stride, pad, dil, groups, bias=True).cuda()
+    x = torch.randn(2, cin, H, W, device="cuda")
+    xa = _nhwc(x, dtype, ops, c_alloc=(cin + 7) // 8 * 8)
+    xr = xa.float().detach().clone().requires_grad_(True)
+    ref = conv(xr)
+    gy = torch.randn_like(ref)
+    gya = _nhwc(gy, dtype, ops, c_alloc=(cout + 7) // 8 * 8)
+    gx, gw, gb = torch.autograd.grad(ref, [xr, conv.weight, conv.bias], gya.float())
+    tape = T.Tape()
+    xv = T.V(xa)
+    y = T.ConvT(conv).forward(tape, xv)
+    tol = 1e-4 if dtype == torch.float32 else 1.2e-2
+    assert _rel(y.t.float(), ref.detach()) < tol
+    y._g = gya
+    pg = tape.backward()
+    assert _rel(xv.g.float(), gx) < tol
+    assert _rel(pg[conv.weight], gw) < (1e-4 if dtype == torch.float32 else 3e-3)
+    assert _rel(pg[conv.bias], gb) < (1e-4 if dtype == torch.float32 else 3e-3)
+
+
+def test_pool_bilinear_ce_backward():
+    from esn import ops, train as T
+    torch.manual_seed(2)
+    # max pool into a concat slice, gradient accumulated on top of an existing one
+    x = torch.randn(2, 35, 8, 12, device="cuda").requires_grad_(True)
+    ref = F.max_pool2d(x, 2, 2)
+    gy = torch.randn_like(ref)
+    gx, = torch.autograd.grad(ref, x, gy)
+    tape = T.Tape()
+    xv = T.V(_nhwc(x.detach(), torch.float32, ops, c_alloc=40))
+    buf = T.V(ops.new_act(2, 64, 4, 6, torch.float32, x.device, zero=True))
+    out = buf.slice(29, 64)
+    T.maxpool2x2(tape, xv, out)
+    assert torch.equal(out.t, ref.detach())
+    buf._g = ops.new_act(2, 64, 4, 6, torch.float32, x.device, zero=True)
+    buf._g[:, 29:64].copy_(gy)
+    tape.backward()
+    assert torch.allclose(xv.g, gx)
+    # bilinear x8 backward
+    s = torch.randn(2, 19, 8, 16, device="cuda").requires_grad_(True)
+    ref = F.interpolate(s, (64, 128), mode="bilinear", align_corners=False)
+    gl = torch.randn_like(ref)
+    gs, = torch.autograd.grad(ref, s, gl)
+    tape = T.Tape()
+    sv = T.V(_nhwc(s.detach(), torch.float32, ops, c_alloc=32))
+    logits, holder = T.bilinear_logits(tape, sv, 64, 128)
+    assert torch.allclose(logits, ref.detach(), atol=1e-5, rtol=1e-5)
+    holder["dlogits"] = gl
+    tape.backward()
+    assert _rel(sv.g, gs) < 1e-5
+    # weighted CE through the autograd Function (normalised gradient)
+    lg = (torch.randn(2, 19, 16, 32, device="cuda") * 3).requires_grad_(True)
+    lab = fixture.make_labels(2, 16, 32, 19, seed=5).cuda()
+    wt = torch.tensor(fixture.CLASS_WEIGHTS, device="cuda")
+    ref = F.cross_entropy(lg, lab, wt, ignore_index=255)
+    gref, = torch.autograd.grad(ref, lg)
+    lg2 = lg.detach().clone().requires_grad_(True)
+    loss = T.cross_entropy(lg2, lab, wt, 255)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert _rel(lg2.grad, gref) < 1e-5
+
+
+def _train_step(name, spec, dtype):
+    from builders.model_builder import build_model
+    from utils.losses.loss import CrossEntropyLoss2d
+    m = build_model(name, 19)
+    m.load_state_dict(spec_state_dict(spec, name))
+    m = m.cuda().train()
+    x = fixture.make_input(2, 64, 128).cuda()
+    lab = fixture.make_labels(2, 64, 128, 19).cuda()
+    crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
+    if dtype == torch.bfloat16:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x)
+            loss = crit(out, lab)
+    else:
+        out = m(x)
+        loss = crit(out, lab)
+    loss.backward()
+    return m, out, loss
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dabnet_training_matches_reference_fp64(spec, golden, dtype):
+    """loss / logits / every parameter gradient against the reference's fp64 run (tests/golden)."""
+    g = golden("DABNet")
+    m, out, loss = _train_step("DABNet", spec, dtype)
+    ref_loss = float(g["train_2x64x128_loss"][0])
+    ltol, gtol = (1e-4, 2e-2) if dtype == torch.float32 else (2e-2, 1e-1)   # fp32-vs-fp64 noise is ~1e-2 per tensor
+    assert abs(loss.item() - ref_loss) / ref_loss < ltol, (loss.item(), ref_loss)
+    ref = torch.from_numpy(g["train_2x64x128_logits_s4"])
+    assert _rel(out.detach().float().cpu()[:, :, ::4, ::4], ref) < (1e-4 if dtype == torch.float32 else 5e-2)
+    stats = json.loads(bytes(g["train_2x64x128_gradstats"]).decode())
+    named = dict(m.named_parameters())
+    worst, checked = 0.0, 0
+    for k, (gnorm, gsum, wnorm) in stats.items():
+        assert named[k].grad is not None, k
+        if gnorm < 1e-10 * max(wnorm, 1e-30):
+            continue
+        err = abs(named[k].grad.double().norm().item() - gnorm) / gnorm
+        worst = max(worst, err)
+        checked += 1
+    print("DABNet %s: loss %.6f (ref %.6f), worst per-tensor grad-norm error %.3e over %d tensors" %
+          (dtype, loss.item(), ref_loss, worst, checked))
+    assert worst < gtol, worst
+    for key in g.files:
+        if key.startswith("train_2x64x128_grad::"):
+            k = key.split("::")[1]
+            err = _rel(named[k].grad.cpu(), torch.from_numpy(g[key]))
+            print("   full-tensor rel-L2 %-50s %.3e" % (k, err))
+            assert err < gtol, (k, err)
