@@ -28,10 +28,12 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (model, batch per GPU, H, W, mode)
-    "erfnet_infer_bf16_b16_1024x2048": ("ERFNet", 16, 1024, 2048),
-    "dabnet_infer_bf16_b16_1024x2048": ("DABNet", 16, 1024, 2048),
-    "erfnet_infer_bf16_b16_512x1024": ("ERFNet", 16, 512, 1024),
-    "dabnet_infer_bf16_b16_512x1024": ("DABNet", 16, 512, 1024),
+    "erfnet_infer_bf16_b16_1024x2048": ("ERFNet", 16, 1024, 2048, "infer"),
+    "dabnet_infer_bf16_b16_1024x2048": ("DABNet", 16, 1024, 2048, "infer"),
+    "erfnet_infer_bf16_b16_512x1024": ("ERFNet", 16, 512, 1024, "infer"),
+    "dabnet_infer_bf16_b16_512x1024": ("DABNet", 16, 512, 1024, "infer"),
+    # BASELINE.json configs[2]: DABNet bf16 training, batch 8/GPU, 512x1024, weighted CE, Adam, data parallel
+    "dabnet_train_bf16_b8_512x1024": ("DABNet", 8, 512, 1024, "train"),
 }
 # block-fused algorithmic elements per input pixel (forward), bf16 storage; the
 # logits term (19 elements/pixel) is replaced by the 1-byte argmax mask because the head is fused.
@@ -98,21 +100,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_leg(model, h, w, steps, warmup, budget_s=25.0):
-    """The reference's CPU path (oracle port of model/*.py, fp32, eval, all host threads) on a
-    bounded sample of the workload: one image of the workload's resolution per step."""
-    from oracle import fixture, nets
+def cpu_reference_leg(model, h, w, steps, warmup, budget_s=25.0, train=False):
+    """The reference's CPU path (oracle port of model/*.py, fp32, all host threads) on a bounded
+    sample of the workload: one image of the workload's resolution per step (inference: forward +
+    numpy argmax; training: train-mode forward + weighted CE + backward through torch autograd)."""
+    from oracle import fixture, nets, loss as oloss
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = fixture_state_dict(model)
     x = fixture.make_input(1, h, w)
     times = []
-    with torch.no_grad():
+    if train:
+        sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+        lab = fixture.make_labels(1, h, w, 19)
+        wt = torch.tensor(fixture.CLASS_WEIGHTS)
+    with torch.set_grad_enabled(train):
         t_start = time.perf_counter()
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            y = nets.forward(model, sd, x)
-            nets.argmax_mask(y)
+            if train:
+                l, _, _ = oloss.weighted_ce(nets.forward(model, sd, x, train=True), lab, wt)
+                l.backward()
+                for v in sd.values():
+                    v.grad = None
+            else:
+                y = nets.forward(model, sd, x)
+                nets.argmax_mask(y)
             t1 = time.perf_counter()
             if i >= warmup:
                 times.append(t1 - t0)
@@ -120,8 +133,9 @@ def cpu_reference_leg(model, h, w, steps, warmup, budget_s=25.0):
                 break
     mean = sum(times) / len(times)
     return {"value": 1.0 / mean, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "%d x (1 image 3x%dx%d fp32, forward + numpy argmax), oracle/nets.py on %d host threads"
-                      % (len(times), h, w, threads)}, mean, len(times)
+            "sample": "%d x (1 image 3x%dx%d fp32, %s), oracle/nets.py on %d host threads"
+                      % (len(times), h, w, "train-mode forward + weighted CE + backward" if train else "forward + numpy argmax",
+                         threads)}, mean, len(times)
 
 
 def main():
@@ -134,19 +148,23 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
-    model_name, batch, H, W = WORKLOADS[args.workload]
+    model_name, batch, H, W, mode = WORKLOADS[args.workload]
+    train = mode == "train"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": args.workload, "net": model_name, "classes": 19, "batch_per_gpu": batch,
-              "input": "3x%dx%d fp32 NCHW" % (H, W), "mode": "inference", "head": "argmax fused (uint8 mask)",
-              "sharding": "images across ranks, no collective",
+              "input": "3x%dx%d fp32 NCHW" % (H, W),
+              "mode": "training step: forward + weighted CE + backward + Adam" if train else "inference",
+              "head": "bilinear -> fp32 logits -> fused weighted-CE kernel" if train else "argmax fused (uint8 mask)",
+              "sharding": ("data parallel: flat fp32 gradient buckets all-reduced (NCCL) from inside the backward tape, "
+                           "2-scalar loss all-reduce, per-GPU BatchNorm") if train else "images across ranks, no collective",
               "l2": "no flush: per-step working set (input %.0f MB + activations) >> 126 MB L2" % (batch * 3 * H * W * 4 / 1e6)}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, max(1, min(args.warmup, 2)))
+        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, max(1, min(args.warmup, 2)), train=train)
         line = {"impl": "reference", "metric": "images/s", "value": base["value"], "unit": "images/s",
                 "n_gpus": args.gpus, "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -169,12 +187,33 @@ def main():
 
     m = build_model(model_name, 19)
     m.load_state_dict(fixture_state_dict(model_name))
-    m = m.cuda().eval()
+    m = m.cuda()
     x_host = fixture.make_input(batch, H, W, seed=1234 + rank).pin_memory()
     x = x_host.cuda(non_blocking=True)
+    y_host = y = None
+    if train:
+        from esn import parallel
+        from utils.losses.loss import CrossEntropyLoss2d
+        m.train()
+        if world > 1:
+            parallel.data_parallel(m)
+        crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
+        opt = torch.optim.Adam(m.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True)  # train.py:212-215
+        y_host = fixture.make_labels(batch, H, W, 19, seed=1234 + rank).pin_memory()
+        y = y_host.cuda(non_blocking=True)
+        args.no_graph = True
+    else:
+        m.eval()
     torch.cuda.synchronize()
 
-    def step(inp):
+    def step(inp, lab=None):
+        if train:
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = crit(m(inp), y if lab is None else lab)
+            loss.backward()
+            opt.step()
+            return loss.detach()
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             return m.predict_mask(inp)
 
@@ -237,10 +276,12 @@ def main():
     value = world * batch / (ms_per_step / 1e3)
 
     # ---- e2e: pinned host images -> H2D -> forward -> D2H uint8 masks, every step, double-buffered
-    h2d = x_host.numel() * 4
-    d2h = batch * H * W
-    mask_host = [torch.empty((batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h2d = x_host.numel() * 4 + (y_host.numel() * 8 if train else 0)
+    d2h = 4 if train else batch * H * W
+    mask_host = [(torch.empty((), dtype=torch.float32) if train else torch.empty((batch, H, W), dtype=torch.uint8)).pin_memory()
+                 for _ in range(2)]
     xin = [torch.empty_like(x), torch.empty_like(x)]
+    yin = [torch.empty_like(y), torch.empty_like(y)] if train else [None, None]
     copy_s = torch.cuda.Stream()
     main_s = torch.cuda.current_stream()
 
@@ -254,12 +295,14 @@ def main():
                     if done[b] is not None:
                         copy_s.wait_event(done[b])      # buffer b free (its compute finished)
                     xin[b].copy_(x_host, non_blocking=True)
+                    if train:
+                        yin[b].copy_(y_host, non_blocking=True)
                     ready[b] = torch.cuda.Event()
                     ready[b].record(copy_s)
             if i >= 1:
                 pb = (i - 1) & 1
                 main_s.wait_event(ready[pb])
-                mk = step(xin[pb])
+                mk = step(xin[pb], yin[pb])
                 mask_host[pb].copy_(mk, non_blocking=True)
                 done[pb] = torch.cuda.Event()
                 done[pb].record(main_s)
@@ -339,6 +382,9 @@ def main():
         px = batch * H * W
         alg_bytes = px * ((ALG_ELEMS_PER_PX[model_name] - 19.0) * 2 + 1 + 3 * 4 - 3 * 2)
         flops = 2 * GMAC_512x1024[model_name] * 1e9 * (H * W) / (512 * 1024) * batch
+        if train:   # ~3.5x the forward block-fused traffic (saved activations + gradients), 3x the FLOPs
+            alg_bytes = px * 3.5 * ALG_ELEMS_PER_PX[model_name] * 2
+            flops *= 3
         model_roof = {"alg_bytes_per_step": int(alg_bytes), "hbm_frac": round(alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak, 4),
                       "tensor_frac": round(flops / (ms_per_step / 1e3) / 1e12 / tc_peak, 4),
                       "note": "block-fused algorithmic bytes (SURVEY 8d) and conv FLOPs of the whole forward / step time"}
@@ -359,7 +405,7 @@ def main():
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}
     if not args.no_cpu_baseline and world >= 1:
-        base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0)
+        base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
     print(json.dumps(line))
     if dist:

@@ -1,0 +1,96 @@
+"""Batch-sharded data parallelism: one process per GPU, NCCL all-reduce of flat gradient buckets
+launched from inside the backward tape (as soon as the last gradient of a bucket exists) on a side
+stream, so communication overlaps the remaining backward kernels.
+
+Replaces the reference's single-process nn.DataParallel (train.py:166-168): no per-step parameter
+broadcast (replicas stay identical by construction), no logits gather (the loss is local; only the
+two scalars sum(w*nll), sum(w) are all-reduced inside CrossEntropyLoss2d), BatchNorm statistics stay
+per-GPU as in the reference.  Gradients are SUMMED: every rank's loss is already divided by the
+global sum of class weights.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    """Flat fp32 buckets over the model's parameters in REVERSE registration order (the order the
+    backward tape produces gradients in), ~bucket_bytes each."""
+
+    def __init__(self, model, bucket_bytes=1 << 20, process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in model.parameters() if p.requires_grad][::-1]
+        self.buckets, cur, size = [], [], 0
+        for p in params:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {p: i for i, b in enumerate(self.buckets) for p in b}
+        dev = params[0].device
+        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=dev) for b in self.buckets]
+        self.views = []
+        for b, f in zip(self.buckets, self.flat):
+            off, vs = 0, {}
+            for p in b:
+                vs[p] = f[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            self.views.append(vs)
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.reset()
+
+    def reset(self):
+        self.pending = [len(b) for b in self.buckets]
+        self.seen = set()
+        self.works = []
+
+    def grad_ready(self, p, g):
+        """Called by the tape when parameter p's gradient is final: copy into the flat bucket and
+        launch the bucket's all-reduce once it is full.  Returns the bucket view (the gradient)."""
+        i = self.bucket_of[p]
+        view = self.views[i][p]
+        view.copy_(g)
+        if p not in self.seen:
+            self.seen.add(p)
+            self.pending[i] -= 1
+            if self.pending[i] == 0:
+                self._launch(i)
+        return view
+
+    def _launch(self, i):
+        if self.world == 1:
+            return
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self.works.append(dist.all_reduce(self.flat[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.works.append(dist.all_reduce(self.flat[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Parameters that produced no gradient this step count as zeros; wait for all reductions."""
+        for i, b in enumerate(self.buckets):
+            if self.pending[i] > 0:
+                for p in b:
+                    if p not in self.seen:
+                        self.views[i][p].zero_()
+                self.pending[i] = 0
+                self._launch(i)
+        for w in self.works:
+            w.wait()
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.reset()
+
+
+def data_parallel(model, bucket_bytes=1 << 20, process_group=None):
+    """Attach gradient buckets to a model built by build_model(); its train-mode forward/backward then
+    all-reduces gradients across the process group.  Parameters are broadcast once from rank 0."""
+    if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0, group=process_group)
+    model.__dict__["_esn_buckets"] = GradBuckets(model, bucket_bytes, process_group)
+    return model

@@ -54,21 +54,28 @@ class V:
 
 
 class Tape:
-    def __init__(self):
+    def __init__(self, buckets=None):
         self.steps = []
         self.param_grads = {}     # parameter -> fp32 gradient tensor
+        self.buckets = buckets    # esn.parallel.GradBuckets or None
 
     def push(self, fn):
         self.steps.append(fn)
 
     def add_param_grad(self, p, g):
         g = g.to(p.dtype) if g.dtype != p.dtype else g
-        self.param_grads[p] = g if p not in self.param_grads else self.param_grads[p] + g
+        if p in self.param_grads:
+            g = self.param_grads[p] + g
+        # every parameter of the hot-path nets is used exactly once per step, so its gradient is final
+        # here: hand it to the data-parallel buckets (flat copy + all-reduce launch, overlapped)
+        self.param_grads[p] = self.buckets.grad_ready(p, g) if self.buckets is not None else g
 
     def backward(self):
         for fn in reversed(self.steps):
             fn()
         self.steps = []
+        if self.buckets is not None:
+            self.buckets.finish()
         return self.param_grads
 
 
