@@ -538,6 +538,8 @@ extern "C" int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream) {
   return ESN_OK;
 }
 
+bool esn_wgrad_mma_try(const EsnConv* p, void* stream, int* rc);   // esn_wgrad_mma.cu
+
 extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   // p->x: forward input, p->y: gradient of the conv output, p->w: fp32 dW accumulator
   // [kh*kw][Cin/groups][Cout] (same layout as the direct kernel's weights), accumulated with atomics.
@@ -552,6 +554,10 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   const int eh = (x.h + 2 * p->pad_h - p->dil_h * (p->kh - 1) - 1) / p->stride + 1;
   const int ew = (x.w + 2 * p->pad_w - p->dil_w * (p->kw - 1) - 1) / p->stride + 1;
   if (eh != dy.h || ew != dy.w || x.n != dy.n) return ESN_ERR_BAD_SHAPE;
+  {
+    int rc = ESN_OK;   // bf16 dense convs: tensor-core path
+    if (!dw && !nchw && esn_wgrad_mma_try(p, stream, &rc)) return rc;
+  }
   WgradArgs a;
   a.x = x.ptr;
   a.dy = dy.ptr;
