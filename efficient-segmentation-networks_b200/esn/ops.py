@@ -155,11 +155,11 @@ class ConvPrep:
 
     @classmethod
     def from_weight(cls, w, stride=1, padding=(0, 0), dilation=(1, 1), groups=1, transposed=False, out_pad=0,
-                    bias=None, scale=None, shift=None, act=L.ACT_NONE, alpha=None):
+                    bias=None, scale=None, shift=None, act=L.ACT_NONE, alpha=None, cin_pad=None, cout_pad=None):
         """Build from a raw weight tensor: (Cout, Cin/groups, kh, kw), or (Cin, Cout, kh, kw) if transposed."""
         self = cls.__new__(cls)
         self._init(w.detach().float(), bias, stride, tuple(padding), tuple(dilation), groups, transposed, out_pad,
-                   scale, shift, act, alpha, w.device, None, None)
+                   scale, shift, act, alpha, w.device, cin_pad, cout_pad)
         return self
 
     def _init(self, w, bias, stride, padding, dilation, groups, transposed, out_pad, scale, shift, act, alpha, device,
@@ -280,7 +280,7 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
         p.w = prep.w_umma.data_ptr()
         _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag)
         return out
-    if tc_ok and prep.cin % 64 == 0 and prep.cin > 64 and not prep.transposed:
+    if tc_ok and prep.cin % 64 == 0 and prep.cin > 64:
         # all taps of the full-Cin weight do not fit in shared memory: run the conv as a sum over
         # 64-channel input slices, carrying the scaled partial sum through the residual operand
         parts = prep.cin_split()

@@ -89,8 +89,12 @@ class ConvT:
     gradient through the (tensor-core) conv kernels with flipped / transposed weights, weight
     gradient through esn_conv2d_wgrad."""
 
-    def __init__(self, conv):
+    def __init__(self, conv, cin_pad=None, cout_pad=None):
+        """cin_pad / cout_pad: run the kernels over zero-padded channel counts (tensor-core friendly);
+        the input buffer must then be at least cin_pad wide with zeros in the tail, and the caller's
+        output slice cout_pad wide (the tail is overwritten or ignored by the caller)."""
         self.conv = conv
+        self.cin_pad, self.cout_pad = cin_pad, cout_pad
         self._key = None
 
     def preps(self):
@@ -102,6 +106,10 @@ class ConvT:
             bias = None if c.bias is None else c.bias.detach().float()
             s, pad, dil, g = c.stride[0], tuple(c.padding), tuple(c.dilation), c.groups
             kh, kw = wd.shape[2:]
+            if self.cin_pad or self.cout_pad:      # zero-extend (Cout, Cin, kh, kw)
+                assert g == 1 and bias is None
+                wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, (self.cin_pad or wd.shape[1]) - wd.shape[1],
+                                                  0, (self.cout_pad or wd.shape[0]) - wd.shape[0]))
             self.fwd_prep = ops.ConvPrep.from_weight(wd, s, pad, dil, g, bias=bias)
             if s == 1:
                 wf = wd.flip(2, 3) if g != 1 else wd.permute(1, 0, 2, 3).flip(2, 3)
@@ -117,7 +125,8 @@ class ConvT:
     def forward(self, tape, x, out=None, residual=None, need_dx=True, dtype=None):
         """x: V (or a raw NCHW input tensor wrapped in V with need_dx=False)."""
         fwd_prep, dgrad_prep = self.preps()
-        xt = x.t
+        xt = x.t if not self.cin_pad else ops.widen(x.t, self.cin_pad)
+        cin_real, cout_real = self.conv.in_channels, self.conv.out_channels
         if out is None:
             n, _, h, w = xt.shape
             ho, wo = fwd_prep.out_hw(h, w)
@@ -139,8 +148,12 @@ class ConvT:
             p.pad_h, p.pad_w, p.dil_h, p.dil_w = fwd_prep.pad_h, fwd_prep.pad_w, fwd_prep.dil_h, fwd_prep.dil_w
             p.groups, p.transposed, p.cout_pad = fwd_prep.groups, 0, fwd_prep.cout_pad
             flops = 2 * dy.shape[0] * dy.shape[2] * dy.shape[3] * fwd_prep.cout * cin_g * kh * kw
-            ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy), flops)
-            tape.add_param_grad(conv.weight, dwbuf.view(kh, kw, cin_g, fwd_prep.cout).permute(3, 2, 0, 1))
+            ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy), flops,
+                      "%dx%d c%d-%d s%d g%d" % (kh, kw, fwd_prep.cin, fwd_prep.cout, fwd_prep.stride, fwd_prep.groups))
+            dw4 = dwbuf.view(kh, kw, cin_g, fwd_prep.cout).permute(3, 2, 0, 1)
+            if fwd_prep.groups == 1:
+                dw4 = dw4[:cout_real, :cin_real]        # drop the zero-padded channels
+            tape.add_param_grad(conv.weight, dw4)
             if conv.bias is not None:
                 sums = _f64zeros(fwd_prep.cout, dy.device)
                 d = ops.tdesc(dy)
@@ -155,7 +168,14 @@ class ConvT:
                     h = xt.shape[2]
                     dgrad_prep.out_pad = h - ((dy.shape[2] - 1) * dgrad_prep.stride - 2 * dgrad_prep.pad_h
                                               + dgrad_prep.dil_h * (dgrad_prep.kh - 1) + 1)
-                x.add_grad(lambda ex, dst: ops.conv2d(dy, dgrad_prep, out=dst, residual=ex))
+                if not self.cin_pad:
+                    x.add_grad(lambda ex, dst: ops.conv2d(dy, dgrad_prep, out=dst, residual=ex))
+                else:
+                    def run(ex, dst):
+                        assert dst is None
+                        g = ops.conv2d(dy, dgrad_prep)[:, :cin_real]     # computed over the padded width
+                        return g if ex is None else ops.affine_act(g, None, None, None, L.ACT_NONE, out=g, residual=ex)
+                    x.add_grad(run)
 
         tape.push(bwd)
         return y

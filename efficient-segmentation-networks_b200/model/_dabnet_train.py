@@ -8,12 +8,20 @@ from esn import train as T
 from esn._lib import ACT_NONE, ACT_PRELU
 
 
-def _convT(conv):
-    t = conv.__dict__.get("_esn_T")
+def _convT(conv, cin_pad=None, cout_pad=None):
+    key = "_esn_T%s_%s" % (cin_pad, cout_pad)
+    t = conv.__dict__.get(key)
     if t is None:
-        t = T.ConvT(conv)
-        conv.__dict__["_esn_T"] = t
+        t = T.ConvT(conv, cin_pad, cout_pad)
+        conv.__dict__[key] = t
     return t
+
+
+def _tc_channels(c):
+    for v in (16, 32, 64):
+        if c <= v:
+            return v
+    return (c + 63) // 64 * 64
 
 
 def _bnprelu(tape, m, x, out=None):
@@ -43,11 +51,17 @@ def _down(tape, m, x, out, dt):
     n, _, h, w = x.t.shape
     pre = T.V(ops.new_act(n, m.nOut, h // 2, w // 2, dt, x.t.device))
     nc = m.conv3x3.conv.out_channels
+    # bf16: run the strided conv (odd channel counts 35->29, 131->128) on the tensor cores over the
+    # zero-padded width of the concat buffer; extra output channels are overwritten by the pool branch
+    cin_p, cout_p = _tc_channels(m.nIn), (nc + 7) // 8 * 8
+    padded = (dt == torch.bfloat16 and x.t.stride(3) >= cin_p and (cin_p != m.nIn or cout_p != nc)
+              and (cout_p == nc or m.nIn < m.nOut) and (h | w) % 2 == 0)
+    ct = _convT(m.conv3x3.conv, cin_p, cout_p) if padded else _convT(m.conv3x3.conv)
     if m.nIn < m.nOut:
-        _convT(m.conv3x3.conv).forward(tape, x, out=pre.slice(0, nc))
+        ct.forward(tape, x, out=pre.slice(0, cout_p if padded else nc))
         T.maxpool2x2(tape, x, pre.slice(nc, m.nOut))
     else:
-        _convT(m.conv3x3.conv).forward(tape, x, out=pre)
+        ct.forward(tape, x, out=pre)
     return _bnprelu(tape, m.bn_prelu, pre, out=out)
 
 
@@ -74,7 +88,8 @@ def dabnet_train_forward(model, input):
     cat0 = cat_buffer(35, d1)
     _conv(tape, model.init_conv[2], y, out=cat0.slice(0, 32))
     ops.affine_act(d1, None, None, None, ACT_NONE, out=cat0.t[:, 32:35])
-    c0 = _bnprelu(tape, model.bn_prelu_1, cat0)
+    c0 = _bnprelu(tape, model.bn_prelu_1, cat0, out=T.V(ops.new_act(n, 35, d1.shape[2], d1.shape[3], dt, dev,
+                                                                       c_alloc=64, zero=True)))
 
     cat1 = cat_buffer(131, d2)
     y = _down(tape, model.downsample_1, c0, cat1.slice(64, 128), dt)
@@ -82,7 +97,8 @@ def dabnet_train_forward(model, input):
     for i, blk in enumerate(blocks):
         y = _dab_module(tape, blk, y, out=cat1.slice(0, 64) if i == len(blocks) - 1 else None)
     ops.affine_act(d2, None, None, None, ACT_NONE, out=cat1.t[:, 128:131])
-    c1 = _bnprelu(tape, model.bn_prelu_2, cat1)
+    c1 = _bnprelu(tape, model.bn_prelu_2, cat1, out=T.V(ops.new_act(n, 131, d2.shape[2], d2.shape[3], dt, dev,
+                                                                       c_alloc=192, zero=True)))
 
     cat2 = cat_buffer(259, d3)
     y = _down(tape, model.downsample_2, c1, cat2.slice(128, 256), dt)
