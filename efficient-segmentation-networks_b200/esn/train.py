@@ -142,7 +142,20 @@ class ConvT:
             cin_g = fwd_prep.cin // fwd_prep.groups
             dwbuf = torch.zeros((kh * kw, cin_g, fwd_prep.cout), dtype=torch.float32, device=dy.device)
             p = L.EsnConv()
-            p.x, p.y = ops.tdesc(xt), ops.tdesc(dy)
+            xw = xt
+            if not ops.is_nhwc(xt) and dy.dtype == torch.bfloat16 and fwd_prep.groups == 1 and fwd_prep.cin < 8:
+                # network stem (NCHW fp32 image, Cin=3): give the tensor-core wgrad an NHWC bf16 copy
+                # padded to 8 channels; the padded rows of dW are dropped below
+                n_, c_, h_, w_ = xt.shape
+                x8 = ops.new_act(n_, c_, h_, w_, torch.bfloat16, xt.device, c_alloc=8, zero=True)
+                dxs, dx8 = ops.tdesc(xt), ops.tdesc(x8)
+                ops._call(L.lib.esn_convert_layout, "esn_convert_layout", (C.byref(dxs), C.byref(dx8)),
+                          ops._nbytes(xt) + ops._nbytes(x8))
+                xw = ops.widen(x8, 8)
+                cin_g = 8
+                dwbuf = torch.zeros((kh * kw, cin_g, fwd_prep.cout), dtype=torch.float32, device=dy.device)
+                p.w = dwbuf.data_ptr()
+            p.x, p.y = ops.tdesc(xw), ops.tdesc(dy)
             p.w = dwbuf.data_ptr()
             p.kh, p.kw, p.stride = kh, kw, fwd_prep.stride
             p.pad_h, p.pad_w, p.dil_h, p.dil_w = fwd_prep.pad_h, fwd_prep.pad_w, fwd_prep.dil_h, fwd_prep.dil_w
@@ -342,10 +355,11 @@ class _CEFn(torch.autograd.Function):
     loss and its gradient equal the reference's gathered-batch value."""
 
     @staticmethod
-    def forward(ctx, logits, target, weight, ignore_label):
+    def forward(ctx, logits, target, weight, ignore_label, distributed=True):
         lg = logits.detach().contiguous()
         sums, _ = ops.weighted_ce(lg, target, weight, ignore_label, want_grad=False)
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        if (distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1):
             torch.distributed.all_reduce(sums)
             ctx.world = torch.distributed.get_world_size()
         else:
@@ -361,8 +375,8 @@ class _CEFn(torch.autograd.Function):
         scratch = torch.zeros(2, dtype=torch.float32, device=lg.device)
         _, g = ops.weighted_ce(lg, target, ctx.weight, ctx.ignore, want_grad=True, sums=scratch, gnorm=sums[1:2],
                                gout=gout)
-        return g, None, None, None
+        return g, None, None, None, None
 
 
-def cross_entropy(logits, target, weight=None, ignore_label=255):
-    return _CEFn.apply(logits, target, weight, ignore_label)
+def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=True):
+    return _CEFn.apply(logits, target, weight, ignore_label, distributed)

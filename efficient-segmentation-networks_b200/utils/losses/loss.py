@@ -11,8 +11,9 @@ __all__ = ["CrossEntropyLoss2d"]
 
 
 class CrossEntropyLoss2d(nn.Module):
-    def __init__(self, weight=None, ignore_label=255, reduction='mean'):
+    def __init__(self, weight=None, ignore_label=255, reduction='mean', distributed=True):
         super().__init__()
+        self.distributed = distributed   # all-reduce the two loss sums over the default process group
         if reduction != 'mean':
             raise NotImplementedError("only reduction='mean' (the reference's default) is on the hot path")
         self.ignore_label = ignore_label
@@ -27,4 +28,4 @@ class CrossEntropyLoss2d(nn.Module):
         w = self.weight
         if w is not None and w.device != output.device:
             w = w.to(output.device)
-        return T.cross_entropy(output, target.long(), w, self.ignore_label)
+        return T.cross_entropy(output, target.long(), w, self.ignore_label, self.distributed)
