@@ -327,12 +327,13 @@ def main():
     # ---- per-kernel roofline: one instrumented eager step, CUDA events around every launch
     hbm_peak, tc_peak, peak_src = peaks()
     roofline, kernels = None, None
+    # (every rank runs the step -- a training step contains collectives -- only rank 0 keeps the profile)
+    for _ in range(2):
+        ops.PROFILE = []
+        step(x)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
-        for _ in range(2):
-            ops.PROFILE = []
-            step(x)
-            torch.cuda.synchronize()
-            prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         for r in prof:
             ms = r["ev"][0].elapsed_time(r["ev"][1])
