@@ -148,6 +148,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are
+    # redirected to stderr for the duration of the run; the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        _real_stdout.write(json.dumps(obj) + "\n")
+        _real_stdout.flush()
     model_name, batch, H, W, mode = WORKLOADS[args.workload]
     train = mode == "train"
     rank = int(os.environ.get("RANK", "0"))
@@ -172,7 +181,7 @@ def main():
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -408,7 +417,7 @@ def main():
     if not args.no_cpu_baseline and world >= 1:
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
