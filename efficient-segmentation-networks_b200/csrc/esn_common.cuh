@@ -90,6 +90,7 @@ struct EpiArgs {
   int res_cstride;
   int res_dtype;
   int act;
+  int pre_act;   // ESN_EP_ACT_BEFORE_RESIDUAL
 };
 
 static inline EpiArgs make_epi(const EsnEpilogue& e) {
@@ -101,6 +102,7 @@ static inline EpiArgs make_epi(const EsnEpilogue& e) {
   a.res_cstride = e.residual.c_stride;
   a.res_dtype = e.residual.dtype;
   a.act = e.act;
+  a.pre_act = (e.flags & ESN_EP_ACT_BEFORE_RESIDUAL) ? 1 : 0;
   return a;
 }
 

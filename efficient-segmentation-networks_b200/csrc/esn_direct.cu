@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectArgs a) {
       const float sh = a.ep.shift ? __ldg(a.ep.shift + c) : 0.f;
       float t = acc[j] * sc + sh;
       if (a.ep.res) {
+        if (a.ep.pre_act) t = apply_act(t, a.ep.act, (a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + c) : 0.f);
         const size_t ri = opix * a.ep.res_cstride + c;
         t += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
                                            : reinterpret_cast<const float*>(a.ep.res)[ri];

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) pw_kernel(const PwArgs a) {
       const float sh = a.ep.shift ? __ldg(a.ep.shift + cc) : 0.f;
       float t = v[j] * sc + sh;
       if (a.ep.res) {
+        if (a.ep.pre_act) t = apply_act(t, a.ep.act, (a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + cc) : 0.f);
         const size_t ri = opix * a.ep.res_cstride + cc;
         t += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
                                            : reinterpret_cast<const float*>(a.ep.res)[ri];

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
   const float* xb = a.x + (size_t)n * 3 * plane;
 
   float v[27];
+  unsigned okmask = 0;   // bit (r*3+s): tap inside the image (needed by the 3x3 pool: padding is -inf there)
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int hi = 2 * ho - 1 + r;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
     for (int s = 0; s < 3; ++s) {
       const int wi = 2 * wo - 1 + s;
       const bool ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+      okmask |= (ok ? 1u : 0u) << (r * 3 + s);
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(xb + c * plane + (size_t)hi * a.W + wi) : 0.f;
     }
@@ -66,11 +68,19 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
       acc[c4 + 3] = fmaf(v[t], wv.w, acc[c4 + 3]);
     }
   }
-  if (a.with_pool) {  // taps (1,1),(1,2),(2,1),(2,2) of the 3x3 window are the 2x2 pooling window
+  if (a.with_pool) {  // 1: taps (1,1),(1,2),(2,1),(2,2) = the 2x2 window; 2: all valid taps = MaxPool2d(3,2,1)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float m = fmaxf(fmaxf(v[(1 * 3 + 1) * 3 + c], v[(1 * 3 + 2) * 3 + c]),
-                            fmaxf(v[(2 * 3 + 1) * 3 + c], v[(2 * 3 + 2) * 3 + c]));
+      float m;
+      if (a.with_pool == 2) {
+        m = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          if (okmask & (1u << t)) m = fmaxf(m, v[t * 3 + c]);
+      } else {
+        m = fmaxf(fmaxf(v[(1 * 3 + 1) * 3 + c], v[(1 * 3 + 2) * 3 + c]),
+                  fmaxf(v[(2 * 3 + 1) * 3 + c], v[(2 * 3 + 2) * 3 + c]));
+      }
 #pragma unroll
       for (int k = 0; k < CPAD; ++k)
         if (k == a.cconv + c) acc[k] = m;
@@ -95,7 +105,7 @@ extern "C" int esn_stem_conv3x3s2(const EsnStem* p, void* stream) {
   const EsnTensor& y = p->y;
   if (x.layout != ESN_NCHW || x.dtype != ESN_F32 || x.c != 3) return ESN_ERR_UNSUPPORTED;
   if (x.n != y.n || y.h != (x.h - 1) / 2 + 1 || y.w != (x.w - 1) / 2 + 1) return ESN_ERR_BAD_SHAPE;
-  if (p->with_pool && ((x.h | x.w) & 1)) return ESN_ERR_UNSUPPORTED;
+  if (p->with_pool == 1 && ((x.h | x.w) & 1)) return ESN_ERR_UNSUPPORTED;
   const int ctot = p->cconv + (p->with_pool ? 3 : 0);
   if (y.c != ctot || ctot > 32 || ctot % 4 || y.c_stride % 4) return ESN_ERR_UNSUPPORTED;
   const size_t ysz = y.dtype == ESN_F32 ? 4 : 2;

@@ -575,6 +575,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   off ^= ((off >> 7) & swz) << 4;
                   const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
                   if (has_res) {
+                    if (a.ep.pre_act) {   // ext = act(BN(conv)) before "main + ext" (ENet bottlenecks)
+                      if (act == ESN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                      } else if (act == ESN_ACT_PRELU) {
+                        const uint32_t pa = prm_base + 2048u + 4u * (uint32_t)cb8;
+                        const float4 a0 = lds_f4(pa), a1 = lds_f4(pa + 16u);
+                        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
+                      }
+                    }
                     float g[8];
                     bf16x8_to_float(lds128(saddr), g);
 #pragma unroll
@@ -603,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                       const int c = cb8 + j;
                       if (c < cout) {
                         float v = f[j];
+                        if (a.ep.res && a.ep.pre_act) v = apply_act(v, act, prm[512 + c]);
                         if (a.ep.res)
                           v += __bfloat162float(
                               reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);

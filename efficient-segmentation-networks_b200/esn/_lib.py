@@ -23,7 +23,7 @@ class EsnTensor(C.Structure):
 
 class EsnEpilogue(C.Structure):
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("alpha", C.c_void_p),
-                ("act", C.c_int32), ("_pad", C.c_int32), ("residual", EsnTensor)]
+                ("act", C.c_int32), ("flags", C.c_int32), ("residual", EsnTensor)]
 
 
 class EsnConv(C.Structure):
@@ -55,6 +55,11 @@ class EsnBnBwd(C.Structure):
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("alpha", C.c_void_p), ("mean", C.c_void_p),
                 ("invstd", C.c_void_p), ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
                 ("dalpha", C.c_void_p), ("act", C.c_int32), ("train_stats", C.c_int32)]
+
+
+class EsnUnpool(C.Structure):
+    _fields_ = [("v", EsnTensor), ("idx", C.c_void_p), ("ext", EsnTensor), ("y", EsnTensor), ("alpha", C.c_void_p),
+                ("act", C.c_int32), ("_pad", C.c_int32)]
 
 
 class EsnDabPair(C.Structure):
@@ -94,6 +99,8 @@ SYMBOLS = {
     "esn_conv2d_wgrad": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
     "esn_maxpool2x2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
     "esn_bilinear_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_float, C.c_void_p]),
+    "esn_maxpool3x3s2_idx": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
+    "esn_max_unpool2x2": (C.c_int, [C.POINTER(EsnUnpool), C.c_void_p]),
     "esn_version": (C.c_int, []),
     "esn_strerror": (C.c_char_p, [C.c_int]),
     "esn_launch_count": (C.c_int64, []),

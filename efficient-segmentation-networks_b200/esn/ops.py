@@ -246,7 +246,8 @@ class ConvPrep:
                 (w + 2 * self.pad_w - self.dil_w * (self.kw - 1) - 1) // self.stride + 1)
 
 
-def _epilogue(ep, scale, shift, alpha, act, residual):
+def _epilogue(ep, scale, shift, alpha, act, residual, flags=0):
+    ep.flags = flags
     ep.scale = scale.data_ptr() if scale is not None else None
     ep.shift = shift.data_ptr() if shift is not None else None
     ep.alpha = alpha.data_ptr() if alpha is not None else None
@@ -267,7 +268,7 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
     p.kh, p.kw, p.stride = prep.kh, prep.kw, prep.stride
     p.pad_h, p.pad_w, p.dil_h, p.dil_w = prep.pad_h, prep.pad_w, prep.dil_h, prep.dil_w
     p.groups, p.transposed, p.cout_pad = prep.groups, prep.transposed, prep.cout_pad
-    _epilogue(p.ep, prep.scale, prep.shift, prep.alpha, prep.act, residual)
+    _epilogue(p.ep, prep.scale, prep.shift, prep.alpha, prep.act, residual, getattr(prep, "ep_flags", 0))
     alg = _nbytes(x) + _nbytes(out) + _nbytes(residual)
     flops = 2 * n * ho * wo * prep.cout * (prep.cin // prep.groups) * prep.kh * prep.kw
     if prep.transposed:
@@ -336,10 +337,10 @@ def stem_conv3x3s2(x, w_direct, cconv, with_pool, out, scale, shift, alpha, act)
     return out
 
 
-def _pool_call(fn, name, x, out, scale, shift, alpha, act, residual=None):
+def _pool_call(fn, name, x, out, scale, shift, alpha, act, residual=None, flags=0):
     p = L.EsnPool()
     p.x, p.y = tdesc(x), tdesc(out)
-    _epilogue(p.ep, scale, shift, alpha, act, residual)
+    _epilogue(p.ep, scale, shift, alpha, act, residual, flags)
     _call(fn, name, (C.byref(p),), _nbytes(x) + _nbytes(out) + _nbytes(residual))
     return out
 
@@ -352,11 +353,37 @@ def avgpool3x3s2(x, out, scale=None, shift=None, alpha=None, act=L.ACT_NONE):
     return _pool_call(L.lib.esn_avgpool3x3s2_affine_act, "esn_avgpool3x3s2_affine_act", x, out, scale, shift, alpha, act)
 
 
-def affine_act(x, scale, shift, alpha, act, out=None, residual=None):
+def affine_act(x, scale, shift, alpha, act, out=None, residual=None, flags=0):
     if out is None:
         n, c, h, w = x.shape
         out = new_act(n, c, h, w, x.dtype, x.device)
-    return _pool_call(L.lib.esn_affine_act, "esn_affine_act", x, out, scale, shift, alpha, act, residual)
+    return _pool_call(L.lib.esn_affine_act, "esn_affine_act", x, out, scale, shift, alpha, act, residual, flags)
+
+
+def maxpool3x3s2_idx(x):
+    """MaxPool2d(3, 2, 1, return_indices=True) on NHWC -> (pooled, int32 indices [N,Ho,Wo,C])."""
+    n, c, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = new_act(n, c, ho, wo, x.dtype, x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.int32, device=x.device)
+    dx, dy = tdesc(x), tdesc(y)
+    _call(L.lib.esn_maxpool3x3s2_idx, "esn_maxpool3x3s2_idx", (C.byref(dx), C.byref(dy), C.c_void_p(idx.data_ptr())),
+          _nbytes(x) + _nbytes(y) + idx.numel() * 4)
+    return y, idx
+
+
+def max_unpool2x2(v, idx, ext=None, act=L.ACT_NONE, alpha=None):
+    """y = act(MaxUnpool2d(2)(v, idx) + ext): deterministic gather (last writer in raster order wins)."""
+    n, c, h, w = v.shape
+    y = new_act(n, c, 2 * h, 2 * w, v.dtype, v.device)
+    p = L.EsnUnpool()
+    p.v, p.y, p.idx = tdesc(v), tdesc(y), idx.data_ptr()
+    if ext is not None:
+        p.ext = tdesc(ext)
+    p.alpha = alpha.data_ptr() if alpha is not None else None
+    p.act = act
+    _call(L.lib.esn_max_unpool2x2, "esn_max_unpool2x2", (C.byref(p),), _nbytes(v) + idx.numel() * 4 + _nbytes(ext) + _nbytes(y))
+    return y
 
 
 def dab_dw_pair(x, prm, dilation, out=None):

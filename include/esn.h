@@ -65,9 +65,11 @@ typedef struct EsnEpilogue {
   const float* shift;  /* [Cout] or NULL (=0) */
   const float* alpha;  /* [Cout] PReLU slopes, used when act == ESN_ACT_PRELU */
   int32_t act;
-  int32_t _pad;
+  int32_t flags;       /* ESN_EP_ACT_BEFORE_RESIDUAL: v = act(act(acc*scale+shift) + residual), the
+                          "ext = act(BN(conv)); out = act(main + ext)" pattern of ENet.py:93-100 */
   EsnTensor residual;  /* ptr == NULL: none; else same N,H,W,C as the output */
 } EsnEpilogue;
+enum { ESN_EP_ACT_BEFORE_RESIDUAL = 1 };
 
 /* 2-D convolution / transposed convolution, NHWC, stride/dilation/groups as
  * torch.nn.Conv2d / ConvTranspose2d (cross-correlation, zero padding).
@@ -114,7 +116,7 @@ typedef struct EsnStem {
   EsnTensor x, y;
   const float* w;
   int32_t cconv;
-  int32_t with_pool;
+  int32_t with_pool;   /* 0 none, 1 MaxPool2d(2,2) (ERFNet), 2 MaxPool2d(3, stride 2, padding 1) (ENet.py:33) */
   EsnEpilogue ep;
 } EsnStem;
 int esn_stem_conv3x3s2(const EsnStem* p, void* stream);
@@ -133,6 +135,22 @@ int esn_maxpool2x2_affine_act(const EsnPool* p, void* stream);
  * times (DABNet.py:113-124 InputInjection), then affine+act, written into a
  * channel slice.  x may be NCHW f32 (network input) or NHWC. */
 int esn_avgpool3x3s2_affine_act(const EsnPool* p, void* stream);
+
+/* ENet pooling pair (ENet.py:126-130,225,262).  esn_maxpool3x3s2_idx: MaxPool2d(3,2,1,return_indices) on
+ * NHWC, idx int32 [N,Ho,Wo,C] = h*W+w of the first maximum.  esn_max_unpool2x2: MaxUnpool2d(2) as a
+ * deterministic gather (last writer in raster order wins, as the CPU reference), fused with
+ * y = act(unpool(v, idx) + ext). */
+int esn_maxpool3x3s2_idx(const EsnTensor* x, const EsnTensor* y, int32_t* idx, void* stream);
+typedef struct EsnUnpool {
+  EsnTensor v;          /* pooled-resolution values */
+  const int32_t* idx;   /* [N,Hp,Wp,C] */
+  EsnTensor ext;        /* optional addend at output resolution (ptr NULL = none) */
+  EsnTensor y;          /* output [N,2Hp,2Wp,C] */
+  const float* alpha;
+  int32_t act;
+  int32_t _pad;
+} EsnUnpool;
+int esn_max_unpool2x2(const EsnUnpool* p, void* stream);
 
 /* Elementwise per-channel affine + activation (+ residual) on an NHWC view:
  * standalone BNPReLU on concat tensors (DABNet.py:38-48,166,171,176). */

@@ -166,3 +166,86 @@ def argmax_mask(logits):
     a = logits.detach().cpu().numpy()
     import numpy as np
     return np.asarray(np.argmax(a, axis=1), dtype=np.uint8)
+
+
+# --------------------------------------------------------------------------- ENet
+def _enet_act(p, x):
+    """The block's shared activation module: nn.PReLU() (one alpha, encoder) or nn.ReLU (decoder),
+    model/ENet.py:18-21,53-56.  All aliases of the shared PReLU load last from `out_prelu.weight`."""
+    if p.has("out_prelu.weight"):
+        a = p["out_prelu.weight"]
+        return torch.clamp(x, min=0) + a.view(1, 1, 1, 1) * torch.clamp(x, max=0)
+    return F.relu(x)
+
+
+def _enet_cba(p, q, x, idx_conv, **kw):
+    """conv -> BN(eps 1e-5) -> shared activation inside an nn.Sequential `q` (conv at idx_conv)."""
+    y = F.conv2d(x, p["%s.%d.weight" % (q, idx_conv)], None, **kw)
+    return _enet_act(p, bn(p.sub("%s.%d" % (q, idx_conv + 1)), y, 1e-5))
+
+
+def enet_initial(p, x):
+    """InitialBlock, model/ENet.py:14-44."""
+    y = torch.cat([F.conv2d(x, p["main_branch.weight"], None, stride=2, padding=1), F.max_pool2d(x, 3, 2, 1)], 1)
+    return _enet_act(p, bn(p.sub("batch_norm"), y, 1e-5))
+
+
+def enet_regular(p, x, k=3, pad=0, dil=1, asym=False):
+    """RegularBottleneck, model/ENet.py:46-100 (eval: Dropout2d is the identity)."""
+    e = _enet_cba(p, "ext_conv1", x, 0)
+    if asym:
+        e = _enet_cba(p, "ext_conv2", e, 0, padding=(pad, 0), dilation=dil)
+        e = _enet_cba(p, "ext_conv2", e, 3, padding=(0, pad), dilation=dil)
+    else:
+        e = _enet_cba(p, "ext_conv2", e, 0, padding=pad, dilation=dil)
+    e = _enet_cba(p, "ext_conv3", e, 0)
+    return _enet_act(p, x + e)
+
+
+def enet_down(p, x):
+    """DownsamplingBottleneck, model/ENet.py:102-197."""
+    main, idx = F.max_pool2d(x, 3, 2, 1, return_indices=True)
+    e = _enet_cba(p, "ext_conv1", x, 0, stride=2)
+    e = _enet_cba(p, "ext_conv2", e, 0, padding=1)
+    e = _enet_cba(p, "ext_conv3", e, 0)
+    n, ce, h, w = e.shape
+    main = torch.cat([main, torch.zeros(n, ce - main.shape[1], h, w, dtype=x.dtype)], 1)
+    return _enet_act(p, main + e), idx
+
+
+def enet_up(p, x, idx):
+    """UpsamplingBottleneck, model/ENet.py:199-272 (MaxUnpool2d on the CPU: raster order, last writer wins)."""
+    main = bn(p.sub("main_conv1.1"), F.conv2d(x, p["main_conv1.0.weight"]), 1e-5)
+    main = F.max_unpool2d(main.contiguous(), idx, 2)
+    e = _enet_cba(p, "ext_conv1", x, 0)
+    e = F.conv_transpose2d(e, p["ext_conv2.0.weight"], None, stride=2, padding=1, output_padding=1)
+    e = _enet_act(p, bn(p.sub("ext_conv2.1"), e, 1e-5))
+    e = _enet_cba(p, "ext_conv3", e, 0)
+    return _enet_act(p, main + e)
+
+
+ENET_STAGE23 = [("regular", 1, 1), ("dilated", 2, 2), ("asymmetric", 2, 1), ("dilated", 4, 4),
+                ("regular", 1, 1), ("dilated", 8, 8), ("asymmetric", 2, 1), ("dilated", 16, 16)]   # ENet.py:307-360
+
+
+def enet(sd, x, train=False, stats=None):
+    """ENet.forward, model/ENet.py:386-432."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = enet_initial(p.sub("initial_block"), x)
+    y, i1 = enet_down(p.sub("downsample1_0"), y)
+    for i in range(1, 5):
+        y = enet_regular(p.sub("regular1_%d" % i), y, 3, 1, 1)
+    y, i2 = enet_down(p.sub("downsample2_0"), y)
+    for stage, first in ((2, 1), (3, 0)):
+        for j, (kind, pad, dil) in enumerate(ENET_STAGE23):
+            q = p.sub("%s%d_%d" % (kind, stage, first + j))
+            y = enet_regular(q, y, 5 if kind == "asymmetric" else 3, pad, dil, kind == "asymmetric")
+    y = enet_up(p.sub("upsample4_0"), y, i2)
+    y = enet_regular(p.sub("regular4_1"), y, 3, 1, 1)
+    y = enet_regular(p.sub("regular4_2"), y, 3, 1, 1)
+    y = enet_up(p.sub("upsample5_0"), y, i1)
+    y = enet_regular(p.sub("regular5_1"), y, 3, 1, 1)
+    return F.conv_transpose2d(y, p["transposed_conv.weight"], None, stride=2, padding=1, output_padding=1)
+
+
+FORWARD["ENet"] = enet

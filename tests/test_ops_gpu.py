@@ -177,3 +177,23 @@ def test_heads_and_ce(ops):
     assert abs(sums[0].item() / sums[1].item() - l.item()) < 1e-5 * abs(l.item())
     gref = oloss.weighted_ce_grad(lg.double(), lab, wt.double())
     assert ((g.cpu().double() / sums[1].item()) - gref).abs().max() < 1e-6
+
+
+def test_enet_pool_unpool_matches_cpu_reference(ops):
+    """MaxPool2d(3,2,1,return_indices) and the gather-form MaxUnpool2d against torch on the CPU
+    (NCHW, sequential raster order: last writer wins -- SURVEY.md H5), with duplicate indices present."""
+    from esn._lib import ACT_RELU
+    torch.manual_seed(4)
+    x = torch.randn(2, 16, 12, 20).round()        # rounding creates ties -> exercises first-max / duplicate paths
+    ref_y, ref_i = F.max_pool2d(x, 3, 2, 1, return_indices=True)
+    xa = _nhwc(x.cuda(), torch.float32, ops)
+    y, idx = ops.maxpool3x3s2_idx(xa)
+    assert torch.equal(y.cpu(), ref_y)
+    assert torch.equal(idx.permute(0, 3, 1, 2).cpu().long(), ref_i)
+    v = torch.randn(2, 16, 6, 10)
+    ext = torch.randn(2, 16, 12, 20)
+    ref = F.relu(F.max_unpool2d(v.contiguous(), ref_i, 2) + ext)
+    out = ops.max_unpool2x2(_nhwc(v.cuda(), torch.float32, ops), idx, ext=_nhwc(ext.cuda(), torch.float32, ops), act=ACT_RELU)
+    assert torch.equal(out.cpu(), ref)
+    dup = (ref_i.flatten(2).sort(dim=2).values.diff(dim=2) == 0).float().mean().item()
+    assert dup > 0.05, "test input must contain duplicate indices"

@@ -10,7 +10,7 @@ from conftest import spec_state_dict
 from oracle import fixture, loss as oloss, nets
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet"])
 def test_eval_forward_matches_reference(name, spec, golden):
     sd = spec_state_dict(spec, name)
     g = golden(name)
@@ -65,6 +65,7 @@ def test_state_dict_spec_counts(spec):
     # parameter counts published by the reference (usage.txt:91-109)
     assert spec["ERFNet"]["n_params"] == 2066642
     assert spec["DABNet"]["n_params"] == 756643
+    assert spec["ENet"]["n_params"] == 360422
 
 
 def test_weighted_ce_matches_reference(golden):

@@ -51,7 +51,7 @@ def main():
         torch.manual_seed(1234)
         m = build_model(name, 19)
         sd = fixture.randomize_state_dict(m.state_dict(), 1234)
-        m.load_state_dict(sd)
+        m.load_state_dict(sd)      # aliased parameters (ENet's shared PReLU): the last key loaded wins
         spec[name] = {"keys": [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()],
                       "n_params": int(sum(p.numel() for p in m.parameters()))}
         out = {}
@@ -68,6 +68,10 @@ def main():
                     out[tag + "_logits_s4"] = y[:, :, ::4, ::4].contiguous().numpy()
                     out[tag + "_sum"] = np.array([y.double().sum().item(), y.double().abs().sum().item()])
                 out[tag + "_argmax"] = np.argmax(y.numpy(), axis=1).astype(np.uint8)
+        if name not in ("ERFNet", "DABNet"):          # inference-only nets so far: no training golden
+            np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+            print(name, "golden written:", {k: v.shape for k, v in out.items()})
+            continue
         # ---- train-mode forward + weighted CE + backward, fp64 (dropout off)
         m64 = build_model(name, 19).double()
         m64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
