@@ -209,7 +209,7 @@ def enet_down(p, x):
     e = _enet_cba(p, "ext_conv2", e, 0, padding=1)
     e = _enet_cba(p, "ext_conv3", e, 0)
     n, ce, h, w = e.shape
-    main = torch.cat([main, torch.zeros(n, ce - main.shape[1], h, w, dtype=x.dtype)], 1)
+    main = torch.cat([main, torch.zeros(n, ce - main.shape[1], h, w, dtype=x.dtype, device=x.device)], 1)
     return _enet_act(p, main + e), idx
 
 
