@@ -360,6 +360,27 @@ def affine_act(x, scale, shift, alpha, act, out=None, residual=None, flags=0):
     return _pool_call(L.lib.esn_affine_act, "esn_affine_act", x, out, scale, shift, alpha, act, residual, flags)
 
 
+def fglo_gate(x, w1, b1, w2, b2, out=None, residual=None):
+    """CGNet FGlo: y = x * sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2) (+ residual)."""
+    n, c, h, w = x.shape
+    sums = torch.zeros((n, c), dtype=torch.float32, device=x.device)
+    gate = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    dx = tdesc(x)
+    _call(L.lib.esn_global_avgpool, "esn_global_avgpool", (C.byref(dx), C.c_void_p(sums.data_ptr())), _nbytes(x))
+    p = L.EsnFGlo()
+    p.sums, p.w1, p.b1, p.w2, p.b2, p.gate = (sums.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                              gate.data_ptr())
+    p.n, p.channels, p.hidden, p.hw = n, c, w1.shape[0], h * w
+    _call(L.lib.esn_fglo_gate, "esn_fglo_gate", (C.byref(p),))
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    dy = tdesc(out)
+    dr = tdesc(residual) if residual is not None else _NULL
+    _call(L.lib.esn_scale_nc, "esn_scale_nc", (C.byref(dx), C.c_void_p(gate.data_ptr()), C.byref(dr), C.byref(dy)),
+          _nbytes(x) + _nbytes(out) + _nbytes(residual))
+    return out
+
+
 def maxpool3x3s2_idx(x):
     """MaxPool2d(3, 2, 1, return_indices=True) on NHWC -> (pooled, int32 indices [N,Ho,Wo,C])."""
     n, c, h, w = x.shape

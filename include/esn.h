@@ -152,6 +152,23 @@ typedef struct EsnUnpool {
 } EsnUnpool;
 int esn_max_unpool2x2(const EsnUnpool* p, void* stream);
 
+/* CGNet global-context gate FGlo (CGNet.py:173-191): x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2), and the
+ * block's residual (CGNet.py:258-260).  esn_global_avgpool: sums[n][c] += sum over H*W (fp32 atomics, caller
+ * zeroes); esn_fglo_gate: gate[n][c] from the sums and the two nn.Linear layers (row-major weights);
+ * esn_scale_nc: y = x * gate[n][c] (+ residual). */
+int esn_global_avgpool(const EsnTensor* x, float* sums, void* stream);
+typedef struct EsnFGlo {
+  const float* sums;   /* [N][C] */
+  const float* w1;     /* [hidden][C]  (fc.0.weight) */
+  const float* b1;     /* [hidden] */
+  const float* w2;     /* [C][hidden]  (fc.2.weight) */
+  const float* b2;     /* [C] */
+  float* gate;         /* out [N][C] */
+  int32_t n, channels, hidden, hw;
+} EsnFGlo;
+int esn_fglo_gate(const EsnFGlo* p, void* stream);
+int esn_scale_nc(const EsnTensor* x, const float* gate, const EsnTensor* residual, const EsnTensor* y, void* stream);
+
 /* Elementwise per-channel affine + activation (+ residual) on an NHWC view:
  * standalone BNPReLU on concat tensors (DABNet.py:38-48,166,171,176). */
 int esn_affine_act(const EsnPool* p, void* stream);

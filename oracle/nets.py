@@ -249,3 +249,69 @@ def enet(sd, x, train=False, stats=None):
 
 
 FORWARD["ENet"] = enet
+
+
+# --------------------------------------------------------------------------- CGNet
+def _cg_bnprelu(p, x, bn_key="bn", act_key="act"):
+    return prelu(bn(p.sub(bn_key), x, 1e-3), p[act_key + ".weight"])
+
+
+def _cg_conv_bn_prelu(p, x, stride=1):
+    """ConvBNPReLU, model/CGNet.py:13-36 (pad = (k-1)/2)."""
+    w = p["conv.weight"]
+    return _cg_bnprelu(p, F.conv2d(x, w, None, stride, (w.shape[2] - 1) // 2))
+
+
+def _cg_fglo(p, x):
+    """FGlo, model/CGNet.py:173-191: x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2)."""
+    y = x.mean(dim=(2, 3))
+    y = F.relu(F.linear(y, p["fc.0.weight"], p["fc.0.bias"]))
+    y = torch.sigmoid(F.linear(y, p["fc.2.weight"], p["fc.2.bias"]))
+    return x * y.view(y.shape[0], -1, 1, 1)
+
+
+def _cg_joint(p, x, d):
+    c = x.shape[1]
+    loc = F.conv2d(x, p["F_loc.conv.weight"], None, 1, 1, 1, c)
+    sur = F.conv2d(x, p["F_sur.conv.weight"], None, 1, d, d, c)
+    return torch.cat([loc, sur], 1)
+
+
+def cg_block_down(p, x, d):
+    """ContextGuidedBlock_Down, model/CGNet.py:193-227."""
+    y = _cg_conv_bn_prelu(p.sub("conv1x1"), x, 2)
+    j = _cg_bnprelu(p, _cg_joint(p, y, d))
+    j = F.conv2d(j, p["reduce.conv.weight"])
+    return _cg_fglo(p.sub("F_glo"), j)
+
+
+def cg_block(p, x, d):
+    """ContextGuidedBlock (add=True), model/CGNet.py:230-260."""
+    y = _cg_conv_bn_prelu(p.sub("conv1x1"), x)
+    j = _cg_bnprelu(p.sub("bn_prelu"), _cg_joint(p, y, d))
+    return x + _cg_fglo(p.sub("F_glo"), j)
+
+
+def cgnet(sd, x, train=False, stats=None):
+    """CGNet.forward (M=3, N=21), model/CGNet.py:274-367."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = _cg_conv_bn_prelu(p.sub("level1_0"), x, 2)
+    y = _cg_conv_bn_prelu(p.sub("level1_1"), y)
+    y = _cg_conv_bn_prelu(p.sub("level1_2"), y)
+    i1, i2 = dab_inject(x, 1), dab_inject(x, 2)
+    y0 = _cg_bnprelu(p.sub("b1"), torch.cat([y, i1], 1))
+    y10 = cg_block_down(p.sub("level2_0"), y0, 2)
+    y = y10
+    for i in range(2):
+        y = cg_block(p.sub("level2.%d" % i), y, 2)
+    y1 = _cg_bnprelu(p.sub("bn_prelu_2"), torch.cat([y, y10, i2], 1))
+    y20 = cg_block_down(p.sub("level3_0"), y1, 4)
+    y = y20
+    for i in range(20):
+        y = cg_block(p.sub("level3.%d" % i), y, 4)
+    y2 = _cg_bnprelu(p.sub("bn_prelu_3"), torch.cat([y20, y], 1))
+    out = F.conv2d(y2, p["classifier.0.conv.weight"])
+    return F.interpolate(out, x.shape[2:], mode="bilinear", align_corners=False)
+
+
+FORWARD["CGNet"] = cgnet
