@@ -171,6 +171,8 @@ int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y) {
   return ESN_OK;
 }
 
+bool esn_dwconv_try(const EsnConv* p, void* stream, int* rc);   // esn_stencil.cu: vectorised depthwise path
+
 extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
   if (!p || !p->w) return ESN_ERR_BAD_ARG;
   const EsnTensor& x = p->x;
@@ -198,6 +200,7 @@ extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
   }
   int rc = esn_check_epilogue(p->ep, y);
   if (rc) return rc;
+  if (dw && esn_dwconv_try(p, stream, &rc)) return rc;
 
   DirectArgs a;
   a.x = x.ptr;

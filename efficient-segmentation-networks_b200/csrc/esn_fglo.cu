@@ -42,19 +42,23 @@ __global__ void __launch_bounds__(kGapThreads) global_sum_kernel(const T* __rest
       for (int j = 0; j < 4; ++j) s[j] += red[l * CG + cg][j];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (c + j < C) atomicAdd(sums + (size_t)n * C + c + j, s[j]);
+      if (c + j < C) sums[((size_t)blockIdx.x * gridDim.z + n) * C + c + j] = s[j];   // partial of this chunk (deterministic)
   }
 }
 
 // one CTA per image: hidden = relu(W1 (sum/HW) + b1), gate = sigmoid(W2 hidden + b2)
-__global__ void fglo_gate_kernel(const float* __restrict__ sums, float inv_hw, const float* __restrict__ w1,
+__global__ void fglo_gate_kernel(const float* __restrict__ sums, int chunks, int N, float inv_hw, const float* __restrict__ w1,
                                  const float* __restrict__ b1, const float* __restrict__ w2,
                                  const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
   extern __shared__ float sm[];   // mean[C] | hidden[R]
   float* mean = sm;
   float* hid = sm + C;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[(size_t)n * C + c] * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < chunks; ++k) t += sums[((size_t)k * N + n) * C + c];   // fixed order: run-to-run identical
+    mean[c] = t * inv_hw;
+  }
   __syncthreads();
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
     float acc = b1[r];
@@ -92,15 +96,31 @@ __global__ void __launch_bounds__(256) scale_nc_kernel(const T* __restrict__ x, 
 
 }  // namespace
 
+static void gap_plan(const EsnTensor* x, int* per, int* chunks) {
+  const int HW = x->h * x->w;
+  const int cblocks = esn_cdiv(esn_cdiv(x->c, 4), 64);
+  int want = esn_cdiv(4 * 148, x->n * cblocks);
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  *per = esn_cdiv(HW, want);
+  if (*per < 256) *per = 256;
+  *chunks = esn_cdiv(HW, *per);
+}
+
+extern "C" int esn_global_avgpool_chunks(const EsnTensor* x) {
+  if (!x || x->h < 1 || x->w < 1 || x->c < 1 || x->n < 1) return ESN_ERR_BAD_ARG;
+  int per, chunks;
+  gap_plan(x, &per, &chunks);
+  return chunks;
+}
+
 extern "C" int esn_global_avgpool(const EsnTensor* x, float* sums, void* stream) {
   if (!x || !sums || !esn_valid_nhwc(*x)) return ESN_ERR_BAD_ARG;
   const int HW = x->h * x->w;
   const int cblocks = esn_cdiv(esn_cdiv(x->c, 4), 64);
-  int chunks = esn_cdiv(4 * 148, x->n * cblocks);
-  if (chunks < 1) chunks = 1;
-  int per = esn_cdiv(HW, chunks);
-  if (per < 256) per = 256;
-  dim3 grid(esn_cdiv(HW, per), cblocks, x->n);
+  int per, chunks;
+  gap_plan(x, &per, &chunks);
+  dim3 grid(chunks, cblocks, x->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x->dtype == ESN_F32)
     global_sum_kernel<float><<<grid, kGapThreads, 0, st>>>((const float*)x->ptr, HW, x->c, x->c_stride, sums, per);
@@ -112,11 +132,11 @@ extern "C" int esn_global_avgpool(const EsnTensor* x, float* sums, void* stream)
 
 extern "C" int esn_fglo_gate(const EsnFGlo* p, void* stream) {
   if (!p || !p->sums || !p->w1 || !p->b1 || !p->w2 || !p->b2 || !p->gate || p->n < 1 || p->channels < 1 || p->hidden < 1 ||
-      p->hw < 1)
+      p->hw < 1 || p->chunks < 1)
     return ESN_ERR_BAD_ARG;
   if (p->channels > 4096 || p->hidden > 1024) return ESN_ERR_UNSUPPORTED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  fglo_gate_kernel<<<p->n, 128, (p->channels + p->hidden) * sizeof(float), st>>>(p->sums, 1.f / (float)p->hw, p->w1, p->b1, p->w2,
+  fglo_gate_kernel<<<p->n, 128, (p->channels + p->hidden) * sizeof(float), st>>>(p->sums, p->chunks, p->n, 1.f / (float)p->hw, p->w1, p->b1, p->w2,
                                                                                  p->b2, p->gate, p->channels, p->hidden);
   ESN_CHECK_LAUNCH();
   return ESN_OK;

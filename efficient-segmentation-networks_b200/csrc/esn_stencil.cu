@@ -103,3 +103,125 @@ extern "C" int esn_dab_dw_pair(const EsnDabPair* p, void* stream) {
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise k_h x k_w convolution (k <= 3, any dilation, stride 1 or 2), NHWC, 128-bit accesses:
+// one thread = one output pixel x 8 channels (bf16) or 4 channels (fp32); per-channel taps and the
+// fused epilogue parameters come from shared memory.  HBM-bound: 1 read + 1 write of the tensor, the
+// neighbour re-reads hit L1/L2.  Used by CGNet (F_loc / F_sur, CGNet.py:106-171), DABNet's training path,
+// Fast-SCNN / ESPNetv2 depthwise layers.
+namespace {
+
+struct DwArgs {
+  const void* x;
+  void* y;
+  const float* w;   // [taps][C]
+  int N, Hi, Wi, C, x_cs, Ho, Wo, y_cs;
+  int kh, kw, stride, pad_h, pad_w, dil_h, dil_w;
+  EpiArgs ep;
+};
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* f) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p)), f);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+    *reinterpret_cast<uint4*>(p) = float_to_bf16x8(f);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sm[];   // w[taps][C] | scale[C] | shift[C] | alpha[C]
+  const int taps = a.kh * a.kw;
+  float* sw = sm;
+  float* sp = sm + taps * a.C;
+  for (int i = threadIdx.x; i < taps * a.C; i += blockDim.x) sw[i] = a.w[i];
+  for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
+    sp[i] = a.ep.scale ? a.ep.scale[i] : 1.f;
+    sp[a.C + i] = a.ep.shift ? a.ep.shift[i] : 0.f;
+    sp[2 * a.C + i] = (a.ep.act == ESN_ACT_PRELU) ? a.ep.alpha[i] : 0.f;
+  }
+  __syncthreads();
+  const int ncg = a.C / V;
+  const long long total = (long long)a.N * a.Ho * a.Wo * ncg;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % ncg) * V;
+  const long long pix = idx / ncg;
+  const int wo = (int)(pix % a.Wo);
+  const int ho = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const T* x = reinterpret_cast<const T*>(a.x) + (size_t)n * a.Hi * a.Wi * a.x_cs + c;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  for (int r = 0; r < a.kh; ++r) {
+    const int hi = ho * a.stride - a.pad_h + r * a.dil_h;
+    if (hi < 0 || hi >= a.Hi) continue;
+    for (int s = 0; s < a.kw; ++s) {
+      const int wi = wo * a.stride - a.pad_w + s * a.dil_w;
+      if (wi < 0 || wi >= a.Wi) continue;
+      float xv[V];
+      Vec<T>::load(x + ((size_t)hi * a.Wi + wi) * a.x_cs, xv);
+      const float* wt = sw + (r * a.kw + s) * a.C + c;
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = fmaf(xv[j], wt[j], acc[j]);
+    }
+  }
+  float res[V];
+  if (a.ep.res) Vec<T>::load(reinterpret_cast<const T*>(a.ep.res) + (size_t)pix * a.ep.res_cstride + c, res);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float t = fmaf(acc[j], sp[c + j], sp[a.C + c + j]);
+    if (a.ep.res) {
+      if (a.ep.pre_act) t = apply_act(t, a.ep.act, sp[2 * a.C + c + j]);
+      t += res[j];
+    }
+    acc[j] = apply_act(t, a.ep.act, sp[2 * a.C + c + j]);
+  }
+  Vec<T>::store(reinterpret_cast<T*>(a.y) + (size_t)pix * a.y_cs + c, acc);
+}
+
+}  // namespace
+
+// Called by esn_conv2d_direct for depthwise convs whose views are 16-byte vectorisable; returns false if not.
+bool esn_dwconv_try(const EsnConv* p, void* stream, int* rc) {
+  const EsnTensor& x = p->x;
+  const EsnTensor& y = p->y;
+  if (x.layout != ESN_NHWC || x.dtype != y.dtype || p->transposed || p->groups != x.c || x.c != y.c) return false;
+  const int V = x.dtype == ESN_BF16 ? 8 : 4;
+  if (x.c % V || x.c_stride % V || y.c_stride % V || ((uintptr_t)x.ptr % 16) || ((uintptr_t)y.ptr % 16)) return false;
+  if (p->ep.residual.ptr && (p->ep.residual.dtype != x.dtype || p->ep.residual.c_stride % V || ((uintptr_t)p->ep.residual.ptr % 16)))
+    return false;
+  const int taps = p->kh * p->kw;
+  const size_t smem = (size_t)(taps + 3) * x.c * sizeof(float);
+  if (smem > 48 * 1024) return false;
+  DwArgs a;
+  a.x = x.ptr; a.y = y.ptr; a.w = reinterpret_cast<const float*>(p->w);
+  a.N = x.n; a.Hi = x.h; a.Wi = x.w; a.C = x.c; a.x_cs = x.c_stride; a.Ho = y.h; a.Wo = y.w; a.y_cs = y.c_stride;
+  a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w; a.dil_h = p->dil_h; a.dil_w = p->dil_w;
+  a.ep = make_epi(p->ep);
+  const long long total = (long long)y.n * y.h * y.w * (x.c / V);
+  const int grid = esn_cdiv(total, 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x.dtype == ESN_BF16) dwconv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
+  else dwconv_kernel<float><<<grid, 256, smem, st>>>(a);
+  g_esn_launches.fetch_add(1, std::memory_order_relaxed);
+  *rc = (cudaPeekAtLastError() == cudaSuccess) ? ESN_OK : ESN_ERR_CUDA;
+  if (*rc != ESN_OK) cudaGetLastError();
+  return true;
+}

@@ -64,7 +64,8 @@ class EsnUnpool(C.Structure):
 
 class EsnFGlo(C.Structure):
     _fields_ = [("sums", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
-                ("gate", C.c_void_p), ("n", C.c_int32), ("channels", C.c_int32), ("hidden", C.c_int32), ("hw", C.c_int32)]
+                ("gate", C.c_void_p), ("n", C.c_int32), ("channels", C.c_int32), ("hidden", C.c_int32), ("hw", C.c_int32),
+                ("chunks", C.c_int32), ("_pad", C.c_int32)]
 
 
 class EsnDabPair(C.Structure):
@@ -106,6 +107,7 @@ SYMBOLS = {
     "esn_bilinear_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_float, C.c_void_p]),
     "esn_maxpool3x3s2_idx": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
     "esn_max_unpool2x2": (C.c_int, [C.POINTER(EsnUnpool), C.c_void_p]),
+    "esn_global_avgpool_chunks": (C.c_int, [C.POINTER(EsnTensor)]),
     "esn_global_avgpool": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
     "esn_fglo_gate": (C.c_int, [C.POINTER(EsnFGlo), C.c_void_p]),
     "esn_scale_nc": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),

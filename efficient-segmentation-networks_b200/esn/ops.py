@@ -363,14 +363,15 @@ def affine_act(x, scale, shift, alpha, act, out=None, residual=None, flags=0):
 def fglo_gate(x, w1, b1, w2, b2, out=None, residual=None):
     """CGNet FGlo: y = x * sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2) (+ residual)."""
     n, c, h, w = x.shape
-    sums = torch.zeros((n, c), dtype=torch.float32, device=x.device)
-    gate = torch.empty((n, c), dtype=torch.float32, device=x.device)
     dx = tdesc(x)
+    chunks = L.lib.esn_global_avgpool_chunks(C.byref(dx))
+    sums = torch.empty((chunks, n, c), dtype=torch.float32, device=x.device)
+    gate = torch.empty((n, c), dtype=torch.float32, device=x.device)
     _call(L.lib.esn_global_avgpool, "esn_global_avgpool", (C.byref(dx), C.c_void_p(sums.data_ptr())), _nbytes(x))
     p = L.EsnFGlo()
     p.sums, p.w1, p.b1, p.w2, p.b2, p.gate = (sums.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                               gate.data_ptr())
-    p.n, p.channels, p.hidden, p.hw = n, c, w1.shape[0], h * w
+    p.n, p.channels, p.hidden, p.hw, p.chunks = n, c, w1.shape[0], h * w, chunks
     _call(L.lib.esn_fglo_gate, "esn_fglo_gate", (C.byref(p),))
     if out is None:
         out = new_act(n, c, h, w, x.dtype, x.device)

@@ -153,18 +153,20 @@ typedef struct EsnUnpool {
 int esn_max_unpool2x2(const EsnUnpool* p, void* stream);
 
 /* CGNet global-context gate FGlo (CGNet.py:173-191): x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2), and the
- * block's residual (CGNet.py:258-260).  esn_global_avgpool: sums[n][c] += sum over H*W (fp32 atomics, caller
- * zeroes); esn_fglo_gate: gate[n][c] from the sums and the two nn.Linear layers (row-major weights);
+ * block's residual (CGNet.py:258-260).  esn_global_avgpool: per-chunk partial sums over H*W;
+ * esn_fglo_gate: gate[n][c] from the sums and the two nn.Linear layers (row-major weights);
  * esn_scale_nc: y = x * gate[n][c] (+ residual). */
-int esn_global_avgpool(const EsnTensor* x, float* sums, void* stream);
+int esn_global_avgpool_chunks(const EsnTensor* x);   /* host query: number of partial-sum chunks K for this view */
+int esn_global_avgpool(const EsnTensor* x, float* sums /* [K][N][C] partial sums, no atomics */, void* stream);
 typedef struct EsnFGlo {
-  const float* sums;   /* [N][C] */
+  const float* sums;   /* [chunks][N][C] partial sums, reduced in fixed order (deterministic) */
   const float* w1;     /* [hidden][C]  (fc.0.weight) */
   const float* b1;     /* [hidden] */
   const float* w2;     /* [C][hidden]  (fc.2.weight) */
   const float* b2;     /* [C] */
   float* gate;         /* out [N][C] */
   int32_t n, channels, hidden, hw;
+  int32_t chunks, _pad;
 } EsnFGlo;
 int esn_fglo_gate(const EsnFGlo* p, void* stream);
 int esn_scale_nc(const EsnTensor* x, const float* gate, const EsnTensor* residual, const EsnTensor* y, void* stream);
