@@ -8,12 +8,14 @@ from model.ERFNet import ERFNet
 from model.DABNet import DABNet
 from model.ENet import ENet
 from model.CGNet import CGNet
+from model.FastSCNN import FastSCNN
 
 _HOT_PATH = {
     "ERFNet": ERFNet,
     "DABNet": DABNet,
     "ENet": ENet,
     "CGNet": CGNet,
+    "FastSCNN": FastSCNN,
 }
 _REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
                     "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")

@@ -103,7 +103,8 @@ struct BilinearHeadArgs {
   void* logits;
   uint8_t* mask;
   int N, Hi, Wi, x_cs, classes, Ho, Wo;
-  float sh, sw;   // in/out
+  float sh, sw;   // in/out  (align_corners: (in-1)/(out-1))
+  int align;
 };
 
 template <typename TI, typename TL>
@@ -115,11 +116,17 @@ __global__ void __launch_bounds__(256) bilinear_head_kernel(const BilinearHeadAr
   const int ho = (int)((idx / a.Wo) % a.Ho);
   const int n = (int)(idx / ((long long)a.Wo * a.Ho));
   // torch area_pixel_compute_source_index, align_corners=False, cubic=False
-  float fh = a.sh * (ho + 0.5f) - 0.5f;
-  fh = fh < 0.f ? 0.f : fh;
-  float fw = a.sw * (wo + 0.5f) - 0.5f;
-  fw = fw < 0.f ? 0.f : fw;
-  const int h0 = (int)fh, w0 = (int)fw;
+  float fh, fw;
+  if (a.align) {
+    fh = a.sh * ho;
+    fw = a.sw * wo;
+  } else {
+    fh = a.sh * (ho + 0.5f) - 0.5f;
+    fh = fh < 0.f ? 0.f : fh;
+    fw = a.sw * (wo + 0.5f) - 0.5f;
+    fw = fw < 0.f ? 0.f : fw;
+  }
+  const int h0 = min((int)fh, a.Hi - 1), w0 = min((int)fw, a.Wi - 1);
   const int hp = (h0 < a.Hi - 1) ? 1 : 0, wp = (w0 < a.Wi - 1) ? 1 : 0;
   const float lh1 = fh - h0, lh0 = 1.f - lh1, lw1 = fw - w0, lw0 = 1.f - lw1;
   const TI* x = reinterpret_cast<const TI*>(a.x);
@@ -289,8 +296,14 @@ extern "C" int esn_head_bilinear(const EsnHead* p, void* stream) {
   a.classes = p->classes;
   a.Ho = p->out_h;
   a.Wo = p->out_w;
-  a.sh = (float)x.h / (float)p->out_h;
-  a.sw = (float)x.w / (float)p->out_w;
+  a.align = p->align_corners;
+  if (a.align) {
+    a.sh = p->out_h > 1 ? (float)(x.h - 1) / (float)(p->out_h - 1) : 0.f;
+    a.sw = p->out_w > 1 ? (float)(x.w - 1) / (float)(p->out_w - 1) : 0.f;
+  } else {
+    a.sh = (float)x.h / (float)p->out_h;
+    a.sw = (float)x.w / (float)p->out_w;
+  }
   const long long total = (long long)x.n * p->out_h * p->out_w;
   const int block = 256, grid = esn_cdiv(total, block);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -12,7 +12,7 @@ struct StemArgs {
   const float* x;
   void* y;
   const float* w;  // [9][3][cconv]
-  int N, H, W, Ho, Wo, cconv, ctot, y_cs, with_pool;
+  int N, H, W, Ho, Wo, cconv, ctot, y_cs, with_pool, pad;
   EpiArgs ep;
 };
 
@@ -44,10 +44,10 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
   unsigned okmask = 0;   // bit (r*3+s): tap inside the image (needed by the 3x3 pool: padding is -inf there)
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const int hi = 2 * ho - 1 + r;
+    const int hi = 2 * ho - a.pad + r;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      const int wi = 2 * wo - 1 + s;
+      const int wi = 2 * wo - a.pad + s;
       const bool ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
       okmask |= (ok ? 1u : 0u) << (r * 3 + s);
 #pragma unroll
@@ -104,9 +104,12 @@ extern "C" int esn_stem_conv3x3s2(const EsnStem* p, void* stream) {
   const EsnTensor& x = p->x;
   const EsnTensor& y = p->y;
   if (x.layout != ESN_NCHW || x.dtype != ESN_F32 || x.c != 3) return ESN_ERR_UNSUPPORTED;
-  if (x.n != y.n || y.h != (x.h - 1) / 2 + 1 || y.w != (x.w - 1) / 2 + 1) return ESN_ERR_BAD_SHAPE;
-  if (p->with_pool == 1 && ((x.h | x.w) & 1)) return ESN_ERR_UNSUPPORTED;
-  const int ctot = p->cconv + (p->with_pool ? 3 : 0);
+  const int pad = (p->with_pool & ESN_STEM_PAD0) ? 0 : 1;
+  const int pool = p->with_pool & 3;
+  if (x.n != y.n || y.h != (x.h + 2 * pad - 3) / 2 + 1 || y.w != (x.w + 2 * pad - 3) / 2 + 1) return ESN_ERR_BAD_SHAPE;
+  if (pool == 1 && ((x.h | x.w) & 1)) return ESN_ERR_UNSUPPORTED;
+  if (pool && !pad) return ESN_ERR_UNSUPPORTED;
+  const int ctot = p->cconv + (pool ? 3 : 0);
   if (y.c != ctot || ctot > 32 || ctot % 4 || y.c_stride % 4) return ESN_ERR_UNSUPPORTED;
   const size_t ysz = y.dtype == ESN_F32 ? 4 : 2;
   if ((uintptr_t)y.ptr % (4 * ysz)) return ESN_ERR_ALIGN;
@@ -125,7 +128,8 @@ extern "C" int esn_stem_conv3x3s2(const EsnStem* p, void* stream) {
   a.cconv = p->cconv;
   a.ctot = ctot;
   a.y_cs = y.c_stride;
-  a.with_pool = p->with_pool;
+  a.with_pool = pool;
+  a.pad = pad;
   a.ep = make_epi(p->ep);
   const long long total = (long long)y.n * y.h * y.w;
   const int block = 128, grid = esn_cdiv(total, block);

@@ -158,8 +158,9 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a) {
   __syncthreads();
   const int ncg = a.C / V;
   const long long total = (long long)a.N * a.Ho * a.Wo * ncg;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  // grid-stride loop: the per-CTA parameter staging above is amortised over many pixels
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
   const int c = (int)(idx % ncg) * V;
   const long long pix = idx / ncg;
   const int wo = (int)(pix % a.Wo);
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a) {
     acc[j] = apply_act(t, a.ep.act, sp[2 * a.C + c + j]);
   }
   Vec<T>::store(reinterpret_cast<T*>(a.y) + (size_t)pix * a.y_cs + c, acc);
+  }
 }
 
 }  // namespace
@@ -216,7 +218,8 @@ bool esn_dwconv_try(const EsnConv* p, void* stream, int* rc) {
   a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w; a.dil_h = p->dil_h; a.dil_w = p->dil_w;
   a.ep = make_epi(p->ep);
   const long long total = (long long)y.n * y.h * y.w * (x.c / V);
-  const int grid = esn_cdiv(total, 256);
+  int grid = esn_cdiv(total, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x.dtype == ESN_BF16) dwconv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
   else dwconv_kernel<float><<<grid, 256, smem, st>>>(a);

@@ -76,7 +76,7 @@ class EsnDabPair(C.Structure):
 class EsnHead(C.Structure):
     _fields_ = [("x", EsnTensor), ("w", C.c_void_p), ("bias", C.c_void_p), ("logits", EsnTensor),
                 ("mask", C.c_void_p), ("classes", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("align_corners", C.c_int32)]
 
 
 class EsnCE(C.Structure):
@@ -111,6 +111,8 @@ SYMBOLS = {
     "esn_global_avgpool": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
     "esn_fglo_gate": (C.c_int, [C.POINTER(EsnFGlo), C.c_void_p]),
     "esn_scale_nc": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
+    "esn_adaptive_avgpool": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
+    "esn_bilinear_nhwc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
     "esn_version": (C.c_int, []),
     "esn_strerror": (C.c_char_p, [C.c_int]),
     "esn_launch_count": (C.c_int64, []),

@@ -210,7 +210,7 @@ class ConvPrep:
         if getattr(self, "_parts", None) is None:
             import copy
             taps = self.kh * self.kw
-            per = max(64, (200 * 1024 // (taps * self.cout_pad * 2)) // 64 * 64)
+            per = max(64, (128 * 1024 // (taps * self.cout_pad * 2)) // 64 * 64)
             parts, lo = [], 0
             while lo < self.cin:
                 hi = min(self.cin, lo + per)
@@ -227,6 +227,26 @@ class ConvPrep:
                 lo = hi
             self._parts = parts
         return self._parts
+
+    def cout_split(self):
+        """Sub-convs over <=256-output-channel slices (each with its slice of the epilogue parameters)."""
+        if getattr(self, "_oparts", None) is None:
+            import copy
+            taps = self.kh * self.kw
+            parts, lo = [], 0
+            while lo < self.cout:
+                hi = min(self.cout, lo + 256)
+                q = copy.copy(self)
+                q._oparts, q._parts, q._w_umma = None, None, None
+                q._w_src = self._w_src[lo:hi].contiguous()
+                q.cout, q.cout_lo, q.cout_pad = hi - lo, lo, (hi - lo + 15) // 16 * 16
+                q.w_direct = q._w_src.permute(2, 3, 1, 0).reshape(taps, self.cin // self.groups, hi - lo).contiguous()
+                q.scale, q.shift = self.scale[lo:hi].contiguous(), self.shift[lo:hi].contiguous()
+                q.alpha = None if self.alpha is None else self.alpha[lo:hi].contiguous()
+                parts.append(q)
+                lo = hi
+            self._oparts = parts
+        return self._oparts
 
     @property
     def w_umma(self):
@@ -280,6 +300,12 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
     if tc_ok and umma_supported(prep, p):
         p.w = prep.w_umma.data_ptr()
         _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag)
+        return out
+    if tc_ok and prep.cout_pad > 256:
+        # more output channels than one UMMA N tile: run 256-channel slices of the weight
+        for q in prep.cout_split():
+            conv2d(x, q, out=out[:, q.cout_lo:q.cout_lo + q.cout],
+                   residual=None if residual is None else residual[:, q.cout_lo:q.cout_lo + q.cout])
         return out
     if tc_ok and prep.cin % 64 == 0 and prep.cin > 64:
         # all taps of the full-Cin weight do not fit in shared memory: run the conv as a sum over
@@ -418,9 +444,28 @@ def dab_dw_pair(x, prm, dilation, out=None):
     return out
 
 
-def _head(fn, name, x, w, bias, classes, out_h, out_w, want_logits, want_mask, logits_dtype):
+def adaptive_avgpool(x, size, dtype=None):
+    n, c, h, w = x.shape
+    y = new_act(n, c, size, size, dtype or x.dtype, x.device)
+    dx, dy = tdesc(x), tdesc(y)
+    _call(L.lib.esn_adaptive_avgpool, "esn_adaptive_avgpool", (C.byref(dx), C.byref(dy)), _nbytes(x) + _nbytes(y))
+    return y
+
+
+def bilinear(x, out_h, out_w, align_corners, out=None):
+    n, c, h, w = x.shape
+    if out is None:
+        out = new_act(n, c, out_h, out_w, x.dtype, x.device)
+    dx, dy = tdesc(x), tdesc(out)
+    _call(L.lib.esn_bilinear_nhwc, "esn_bilinear_nhwc", (C.byref(dx), C.byref(dy), int(bool(align_corners))),
+          _nbytes(x) + _nbytes(out))
+    return out
+
+
+def _head(fn, name, x, w, bias, classes, out_h, out_w, want_logits, want_mask, logits_dtype, align_corners=False):
     n = x.shape[0]
     p = L.EsnHead()
+    p.align_corners = int(bool(align_corners))
     p.x = tdesc(x)
     p.w = w.data_ptr() if w is not None else None
     p.bias = bias.data_ptr() if bias is not None else None
@@ -444,9 +489,10 @@ def head_convt2x2(x, w, bias, classes, want_logits=True, want_mask=False, logits
                  want_logits, want_mask, logits_dtype)
 
 
-def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, logits_dtype=torch.float32):
+def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, logits_dtype=torch.float32,
+                  align_corners=False):
     return _head(L.lib.esn_head_bilinear, "esn_head_bilinear", x, None, None, classes, out_h, out_w,
-                 want_logits, want_mask, logits_dtype)
+                 want_logits, want_mask, logits_dtype, align_corners)
 
 
 def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, sums=None, gnorm=None, gout=None):

@@ -70,6 +70,7 @@ typedef struct EsnEpilogue {
   EsnTensor residual;  /* ptr == NULL: none; else same N,H,W,C as the output */
 } EsnEpilogue;
 enum { ESN_EP_ACT_BEFORE_RESIDUAL = 1 };
+enum { ESN_STEM_PAD0 = 256 };
 
 /* 2-D convolution / transposed convolution, NHWC, stride/dilation/groups as
  * torch.nn.Conv2d / ConvTranspose2d (cross-correlation, zero padding).
@@ -116,7 +117,8 @@ typedef struct EsnStem {
   EsnTensor x, y;
   const float* w;
   int32_t cconv;
-  int32_t with_pool;   /* 0 none, 1 MaxPool2d(2,2) (ERFNet), 2 MaxPool2d(3, stride 2, padding 1) (ENet.py:33) */
+  int32_t with_pool;   /* bits 0-1: 0 none, 1 MaxPool2d(2,2) (ERFNet), 2 MaxPool2d(3, stride 2, padding 1) (ENet.py:33);
+                          bit 8 (ESN_STEM_PAD0): the conv has padding 0 instead of 1 (FastSCNN.py:120) */
   EsnEpilogue ep;
 } EsnStem;
 int esn_stem_conv3x3s2(const EsnStem* p, void* stream);
@@ -171,6 +173,11 @@ typedef struct EsnFGlo {
 int esn_fglo_gate(const EsnFGlo* p, void* stream);
 int esn_scale_nc(const EsnTensor* x, const float* gate, const EsnTensor* residual, const EsnTensor* y, void* stream);
 
+/* nn.AdaptiveAvgPool2d (FastSCNN.py:97-99) and NHWC->NHWC F.interpolate(bilinear, align_corners 0/1)
+ * (FastSCNN.py:101-102,174), y may be a channel slice of a concat buffer. */
+int esn_adaptive_avgpool(const EsnTensor* x, const EsnTensor* y, void* stream);
+int esn_bilinear_nhwc(const EsnTensor* x, const EsnTensor* y, int32_t align_corners, void* stream);
+
 /* Elementwise per-channel affine + activation (+ residual) on an NHWC view:
  * standalone BNPReLU on concat tensors (DABNet.py:38-48,166,171,176). */
 int esn_affine_act(const EsnPool* p, void* stream);
@@ -207,7 +214,7 @@ typedef struct EsnHead {
   uint8_t* mask;        /* optional: (N,H,W) uint8 argmax */
   int32_t classes;
   int32_t out_h, out_w;
-  int32_t _pad;
+  int32_t align_corners; /* bilinear head only: 0 (DABNet/CGNet) or 1 (FastSCNN.py:229, ESPNetv2) */
 } EsnHead;
 int esn_head_convt2x2(const EsnHead* p, void* stream);
 int esn_head_bilinear(const EsnHead* p, void* stream);

@@ -315,3 +315,78 @@ def cgnet(sd, x, train=False, stats=None):
 
 
 FORWARD["CGNet"] = cgnet
+
+
+# --------------------------------------------------------------------------- Fast-SCNN
+def _fs_bn(p, key, x):
+    return bn(p.sub(key), x, 1e-5)        # nn.BatchNorm2d default eps (FastSCNN.py:20)
+
+
+def _fs_cbr(p, x, stride=1, padding=0):
+    """_ConvBNReLU, model/FastSCNN.py:15-27."""
+    return F.relu(_fs_bn(p, "conv.1", F.conv2d(x, p["conv.0.weight"], None, stride, padding)))
+
+
+def _fs_dsconv(p, x, stride=1):
+    """_DSConv, model/FastSCNN.py:30-45."""
+    c = x.shape[1]
+    y = F.relu(_fs_bn(p, "conv.1", F.conv2d(x, p["conv.0.weight"], None, stride, 1, 1, c)))
+    return F.relu(_fs_bn(p, "conv.4", F.conv2d(y, p["conv.3.weight"])))
+
+
+def _fs_dwconv(p, x, stride=1):
+    """_DWConv, model/FastSCNN.py:48-59."""
+    return F.relu(_fs_bn(p, "conv.1", F.conv2d(x, p["conv.0.weight"], None, stride, 1, 1, x.shape[1])))
+
+
+def _fs_bottleneck(p, x, stride, shortcut):
+    """LinearBottleneck, model/FastSCNN.py:62-82."""
+    y = _fs_cbr(p.sub("block.0"), x)
+    y = _fs_dwconv(p.sub("block.1"), y, stride)
+    y = _fs_bn(p, "block.3", F.conv2d(y, p["block.2.weight"]))
+    return x + y if shortcut else y
+
+
+def _fs_ppm(p, x):
+    """PyramidPooling, model/FastSCNN.py:85-112."""
+    size = x.shape[2:]
+    feats = [x]
+    for i, s in enumerate((1, 2, 3, 6)):
+        f = _fs_cbr(p.sub("conv%d" % (i + 1)), F.adaptive_avg_pool2d(x, s))
+        feats.append(F.interpolate(f, size, mode="bilinear", align_corners=True))
+    return _fs_cbr(p.sub("out"), torch.cat(feats, 1))
+
+
+def _fs_ffm(p, hi, lo):
+    """FeatureFusionModule, model/FastSCNN.py:157-182."""
+    lo = F.interpolate(lo, hi.shape[2:], mode="bilinear", align_corners=True)
+    lo = _fs_dwconv(p.sub("dwconv"), lo)
+    lo = _fs_bn(p, "conv_lower_res.1", F.conv2d(lo, p["conv_lower_res.0.weight"], p["conv_lower_res.0.bias"]))
+    hi = _fs_bn(p, "conv_higher_res.1", F.conv2d(hi, p["conv_higher_res.0.weight"], p["conv_higher_res.0.bias"]))
+    return F.relu(hi + lo)
+
+
+def fastscnn(sd, x, train=False, stats=None):
+    """FastSCNN.forward (aux=False, eval: Dropout is the identity), model/FastSCNN.py:204-235."""
+    p = SD(sd, "", x.dtype, train, stats)
+    q = p.sub("learning_to_downsample")
+    hi = _fs_cbr(q.sub("conv"), x, 2, 0)
+    hi = _fs_dsconv(q.sub("dsconv1"), hi, 2)
+    hi = _fs_dsconv(q.sub("dsconv2"), hi, 2)
+    g = p.sub("global_feature_extractor")
+    y = hi
+    for name, cin, cout, stride in (("bottleneck1", 64, 64, 2), ("bottleneck2", 64, 96, 2), ("bottleneck3", 96, 128, 1)):
+        for i in range(3):
+            s = stride if i == 0 else 1
+            ci = cin if i == 0 else cout
+            y = _fs_bottleneck(g.sub("%s.%d" % (name, i)), y, s, s == 1 and ci == cout)
+    y = _fs_ppm(g.sub("ppm"), y)
+    y = _fs_ffm(p.sub("feature_fusion"), hi, y)
+    c = p.sub("classifier")
+    y = _fs_dsconv(c.sub("dsconv1"), y)
+    y = _fs_dsconv(c.sub("dsconv2"), y)
+    y = F.conv2d(y, c["conv.1.weight"], c["conv.1.bias"])
+    return F.interpolate(y, x.shape[2:], mode="bilinear", align_corners=True)
+
+
+FORWARD["FastSCNN"] = fastscnn
