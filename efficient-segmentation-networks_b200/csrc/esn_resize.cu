@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const TI* __restrict
 
 extern "C" int esn_adaptive_avgpool(const EsnTensor* x, const EsnTensor* y, void* stream) {
   if (!x || !y || !esn_valid_nhwc(*x) || !esn_valid_nhwc(*y)) return ESN_ERR_BAD_ARG;
-  if (x->n != y->n || x->c != y->c || y->h > x->h || y->w > x->w) return ESN_ERR_BAD_SHAPE;
+  if (x->n != y->n || x->c != y->c) return ESN_ERR_BAD_SHAPE;   // output may exceed the input (windows then repeat)
   const long long total = (long long)y->n * y->h * y->w * y->c;
   const int grid = esn_cdiv(total, 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -145,7 +145,7 @@ template <> struct Vec<__nv_bfloat16> {
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a) {
   constexpr int V = Vec<T>::N;
-  extern __shared__ float sm[];   // w[taps][C] | scale[C] | shift[C] | alpha[C]
+  extern __shared__ __align__(16) float sm[];   // w[taps][C] | scale[C] | shift[C] | alpha[C]
   const int taps = a.kh * a.kw;
   float* sw = sm;
   float* sp = sm + taps * a.C;
@@ -179,20 +179,36 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwArgs a) {
       float xv[V];
       Vec<T>::load(x + ((size_t)hi * a.Wi + wi) * a.x_cs, xv);
       const float* wt = sw + (r * a.kw + s) * a.C + c;
+      float wv[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = fmaf(xv[j], wt[j], acc[j]);
+      for (int j = 0; j < V; j += 4) {     // 128-bit shared-memory reads of the per-channel taps
+        const float4 t = *reinterpret_cast<const float4*>(wt + j);
+        wv[j] = t.x; wv[j + 1] = t.y; wv[j + 2] = t.z; wv[j + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = fmaf(xv[j], wv[j], acc[j]);
     }
   }
   float res[V];
   if (a.ep.res) Vec<T>::load(reinterpret_cast<const T*>(a.ep.res) + (size_t)pix * a.ep.res_cstride + c, res);
+  float psc[V], psh[V], pal[V];
+#pragma unroll
+  for (int j = 0; j < V; j += 4) {
+    const float4 t0 = *reinterpret_cast<const float4*>(sp + c + j);
+    const float4 t1 = *reinterpret_cast<const float4*>(sp + a.C + c + j);
+    const float4 t2 = *reinterpret_cast<const float4*>(sp + 2 * a.C + c + j);
+    psc[j] = t0.x; psc[j + 1] = t0.y; psc[j + 2] = t0.z; psc[j + 3] = t0.w;
+    psh[j] = t1.x; psh[j + 1] = t1.y; psh[j + 2] = t1.z; psh[j + 3] = t1.w;
+    pal[j] = t2.x; pal[j + 1] = t2.y; pal[j + 2] = t2.z; pal[j + 3] = t2.w;
+  }
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    float t = fmaf(acc[j], sp[c + j], sp[a.C + c + j]);
+    float t = fmaf(acc[j], psc[j], psh[j]);
     if (a.ep.res) {
-      if (a.ep.pre_act) t = apply_act(t, a.ep.act, sp[2 * a.C + c + j]);
+      if (a.ep.pre_act) t = apply_act(t, a.ep.act, pal[j]);
       t += res[j];
     }
-    acc[j] = apply_act(t, a.ep.act, sp[2 * a.C + c + j]);
+    acc[j] = apply_act(t, a.ep.act, pal[j]);
   }
   Vec<T>::store(reinterpret_cast<T*>(a.y) + (size_t)pix * a.y_cs + c, acc);
   }
