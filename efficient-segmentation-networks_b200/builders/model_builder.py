@@ -9,6 +9,7 @@ from model.DABNet import DABNet
 from model.ENet import ENet
 from model.CGNet import CGNet
 from model.FastSCNN import FastSCNN
+from model.ESPNet_v2.SegmentationModel import EESPNet_Seg
 
 _HOT_PATH = {
     "ERFNet": ERFNet,
@@ -16,6 +17,7 @@ _HOT_PATH = {
     "ENet": ENet,
     "CGNet": CGNet,
     "FastSCNN": FastSCNN,
+    "ESPNet_v2": EESPNet_Seg,
 }
 _REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
                     "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")

@@ -184,8 +184,10 @@ class ConvPrep:
         self.cout, cin_g, self.kh, self.kw = w.shape
         self.groups = groups
         self.cin = cin_g * groups
-        if self.groups != 1 and not (self.groups == self.cin == self.cout):
-            raise NotImplementedError("only dense and depthwise convs are supported, got groups=%d" % self.groups)
+        self.depthwise = self.groups > 1 and self.groups == self.cin == self.cout
+        self.grouped = self.groups > 1 and not self.depthwise
+        if self.grouped and (transposed or self.cout % groups):
+            raise NotImplementedError("grouped transposed convs are not supported")
         self.transposed = int(transposed)
         self.stride = stride
         self.pad_h, self.pad_w = padding
@@ -227,6 +229,27 @@ class ConvPrep:
                 lo = hi
             self._parts = parts
         return self._parts
+
+    def group_split(self):
+        """A grouped conv as `groups` dense sub-convs over channel slices of the input and output."""
+        if getattr(self, "_gparts", None) is None:
+            import copy
+            taps = self.kh * self.kw
+            cg, og = self.cin // self.groups, self.cout // self.groups
+            parts = []
+            for g in range(self.groups):
+                q = copy.copy(self)
+                q._gparts, q._oparts, q._parts, q._w_umma = None, None, None, None
+                q.groups, q.grouped, q.depthwise = 1, False, False
+                q._w_src = self._w_src[g * og:(g + 1) * og].contiguous()
+                q.cin, q.cout, q.cout_pad = cg, og, (og + 15) // 16 * 16
+                q.cin_lo_g, q.cout_lo = g * cg, g * og
+                q.w_direct = q._w_src.permute(2, 3, 1, 0).reshape(taps, cg, og).contiguous()
+                q.scale, q.shift = self.scale[g * og:(g + 1) * og].clone(), self.shift[g * og:(g + 1) * og].clone()
+                q.alpha = None if self.alpha is None else self.alpha[g * og:(g + 1) * og].clone()
+                parts.append(q)
+            self._gparts = parts
+        return self._gparts
 
     def cout_split(self):
         """Sub-convs over <=256-output-channel slices (each with its slice of the epilogue parameters)."""
@@ -283,6 +306,12 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
     if out is None:
         odt = x.dtype if x.dtype == torch.bfloat16 else torch.float32
         out = new_act(n, prep.cout, ho, wo, odt, x.device)
+    if prep.grouped:
+        for q in prep.group_split():
+            conv2d(x[:, q.cin_lo_g:q.cin_lo_g + q.cin], q, out=out[:, q.cout_lo:q.cout_lo + q.cout],
+                   residual=None if residual is None else residual[:, q.cout_lo:q.cout_lo + q.cout],
+                   force_direct=force_direct)
+        return out
     p = L.EsnConv()
     p.x, p.y = tdesc(x), tdesc(out)
     p.kh, p.kw, p.stride = prep.kh, prep.kw, prep.stride

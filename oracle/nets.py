@@ -390,3 +390,101 @@ def fastscnn(sd, x, train=False, stats=None):
 
 
 FORWARD["FastSCNN"] = fastscnn
+
+
+# --------------------------------------------------------------------------- ESPNetv2 (EESPNet_Seg, s=2)
+def _e2_bn(p, key, x):
+    return bn(p.sub(key), x, 1e-5)
+
+
+def _e2_cbr(p, x, stride=1, groups=1):
+    """CBR, model/ESPNet_v2/cnn_utils.py:27-49."""
+    w = p["conv.weight"]
+    y = F.conv2d(x, w, None, stride, (w.shape[2] - 1) // 2, 1, groups)
+    return prelu(_e2_bn(p, "bn", y), p["act.weight"])
+
+
+def _e2_cb(p, x, stride=1, groups=1):
+    """CB, cnn_utils.py:66-89."""
+    w = p["conv.weight"]
+    return _e2_bn(p, "bn", F.conv2d(x, w, None, stride, (w.shape[2] - 1) // 2, 1, groups))
+
+
+def _e2_br(p, x):
+    """BR, cnn_utils.py:45-64."""
+    return prelu(_e2_bn(p, "bn", x), p["act.weight"])
+
+
+def _e2_dilations(k, r_lim):
+    ks = sorted((3 + 2 * i) if (3 + 2 * i) <= r_lim else 3 for i in range(k))
+    return [{3: 1, 5: 2, 7: 3, 9: 4, 11: 5, 13: 6, 15: 7, 17: 8}[s] for s in ks]   # Model.py:40-49
+
+
+def e2_eesp(p, x, stride, r_lim, down_avg=False, k=4):
+    """EESP, model/ESPNet_v2/Model.py:15-99."""
+    o1 = _e2_cbr(p.sub("proj_1x1"), x, 1, k)
+    n = o1.shape[1]
+    outs = []
+    for i, d in enumerate(_e2_dilations(k, r_lim)):
+        o = F.conv2d(o1, p["spp_dw.%d.conv.weight" % i], None, stride, d, d, n)
+        outs.append(o if i == 0 else o + outs[-1])
+    e = _e2_cb(p.sub("conv_1x1_exp"), _e2_br(p.sub("br_after_cat"), torch.cat(outs, 1)), 1, k)
+    if stride == 2 and down_avg:
+        return e
+    if e.shape == x.shape:
+        e = e + x
+    return prelu(e, p["module_act.weight"])
+
+
+def e2_down(p, x, img, r_lim):
+    """DownSampler (reinf=True), Model.py:102-147."""
+    avg = F.avg_pool2d(x, 3, 2, 1)
+    out = torch.cat([avg, e2_eesp(p.sub("eesp"), x, 2, r_lim, True)], 1)
+    if img is not None:
+        while True:
+            img = F.avg_pool2d(img, 3, 2, 1)
+            if img.shape[2] == avg.shape[2]:
+                break
+        out = out + _e2_cb(p.sub("inp_reinf.1"), _e2_cbr(p.sub("inp_reinf.0"), img))
+    return prelu(out, p["act.weight"])
+
+
+def _e2_psp(p, x):
+    """PSPModule, cnn_utils.py:11-25."""
+    h, w = x.shape[2:]
+    out, f = [x], x
+    for i in range(4):
+        f = F.avg_pool2d(f, 3, 2, 1)
+        s = F.conv2d(f, p["stages.%d.conv.weight" % i], None, 1, 1, 1, f.shape[1])
+        out.append(F.interpolate(s, (h, w), mode="bilinear", align_corners=True))
+    return _e2_cbr(p.sub("project"), torch.cat(out, 1))
+
+
+def _e2_up2(x):
+    return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+
+
+def espnetv2(sd, x, train=False, stats=None):
+    """EESPNet_Seg.forward (s=2; eval: Dropout2d is the identity), SegmentationModel.py:20-77; encoder
+    EESPNet.forward(seg=True), Model.py:236-287."""
+    p = SD(sd, "", x.dtype, train, stats)
+    q = p.sub("net")
+    l1 = _e2_cbr(q.sub("level1"), x, 2)
+    l2 = e2_down(q.sub("level2_0"), l1, x, 13)
+    l3 = e2_down(q.sub("level3_0"), l2, x, 11)
+    for i in range(3):
+        l3 = e2_eesp(q.sub("level3.%d" % i), l3, 1, 9)
+    l4 = e2_down(q.sub("level4_0"), l3, x, 9)
+    for i in range(7):
+        l4 = e2_eesp(q.sub("level4.%d" % i), l4, 1, 7)
+    l4p = _e2_cbr(p.sub("proj_L4_C"), l4)
+    up = F.interpolate(l4p, l3.shape[2:], mode="bilinear", align_corners=True)
+    m3 = e2_eesp(p.sub("pspMod.0"), torch.cat([l3, up], 1), 1, 7)
+    m3 = _e2_psp(p.sub("pspMod.1"), m3)
+    s3 = _e2_br(p.sub("act_l3"), F.conv2d(m3, p["project_l3.1.conv.weight"]))
+    m2 = _e2_cbr(p.sub("project_l2"), torch.cat([l2, _e2_up2(s3)], 1))
+    m1 = F.conv2d(torch.cat([l1, _e2_up2(m2)], 1), p["project_l1.1.conv.weight"])
+    return _e2_up2(m1)
+
+
+FORWARD["ESPNet_v2"] = espnetv2

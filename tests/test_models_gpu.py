@@ -29,7 +29,7 @@ def _margin_mask(ref_logits, tol):
     return (top2[:, 0] - top2[:, 1]) > tol * top2[:, 0].abs().clamp_min(1e-6)
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2"])
 def test_fp32_matches_reference_golden(name, spec, golden):
     m = _model(name, spec)
     g = golden(name)
@@ -54,7 +54,7 @@ def test_fp32_matches_reference_golden(name, spec, golden):
         assert (mask.cpu().numpy() == nets.argmax_mask(y)).all()       # fused argmax == numpy argmax of our logits
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2"])
 def test_bf16_matches_oracle(name, spec):
     m = _model(name, spec)
     sd = spec_state_dict(spec, name)

@@ -43,6 +43,9 @@ CONV_CASES = [
     (64, 32, 3, 1, 1, 1, 1, False, 0, 16, 24),
     (32, 64, 1, 1, 0, 1, 1, False, 0, 16, 24),
     (259, 19, 1, 1, 0, 1, 1, False, 0, 8, 16),
+    (32, 24, 1, 1, 0, 1, 4, False, 0, 16, 24),      # grouped 1x1 (ESPNetv2 reduce: 8 -> 6 per group)
+    (96, 96, 1, 1, 0, 1, 4, False, 0, 12, 20),      # grouped 1x1 expand
+    (24, 24, 3, 2, 6, 6, 24, False, 0, 20, 28),     # depthwise, stride 2, dilation 6
 ]
 
 
@@ -70,6 +73,32 @@ def test_conv_direct_matches_torch(ops, case, dtype):
     tol = 2e-5 if dtype == torch.float32 else 1.5e-2
     err = (y.float() - ref).abs().max() / ref.abs().max()
     assert err < tol, err
+
+
+@pytest.mark.parametrize("cin,cout", [(256, 64), (512, 512), (256, 256)])
+def test_grouped_1x1_on_tensor_cores(ops, cin, cout):
+    """Grouped (g=4) 1x1 conv as per-group tcgen05 convs over channel slices, bf16, residual + PReLU epilogue."""
+    from esn._lib import ACT_PRELU
+    m = _rand_conv(cin, cout, 1, groups=4, bias=False)
+    torch.manual_seed(2)
+    x = torch.randn(2, cin, 24, 40, device="cuda")
+    scale = torch.rand(cout, device="cuda") + 0.5
+    shift = torch.randn(cout, device="cuda") * 0.1
+    alpha = torch.rand(cout, device="cuda") * 0.4
+    xa = _nhwc(x, torch.bfloat16, ops)
+    with torch.no_grad():
+        mb = nn.Conv2d(cin, cout, 1, groups=4, bias=False).cuda()
+        mb.weight.copy_(m.weight.to(torch.bfloat16).float())
+        ref = mb(xa.float())
+        resa = _nhwc(torch.randn_like(ref), torch.bfloat16, ops)
+        ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + resa.float()
+        ref = torch.where(ref >= 0, ref, ref * alpha.view(1, -1, 1, 1))
+    prep = ops.ConvPrep(m, scale, shift, ACT_PRELU, alpha)
+    ops.launch_count_reset()
+    y = ops.conv2d(xa, prep, residual=resa)
+    assert ops.launch_count() == 4
+    err = (y.float() - ref).abs().max() / ref.abs().max()
+    assert err < 1e-2, err
 
 
 def test_conv_direct_nchw_input_and_slice_output(ops):
