@@ -36,13 +36,17 @@ WORKLOADS = {
     "enet_infer_bf16_b32_1024x2048": ("ENet", 32, 1024, 2048, "infer"),
     "cgnet_infer_bf16_b32_1024x2048": ("CGNet", 32, 1024, 2048, "infer"),
     "fastscnn_infer_bf16_b16_1024x2048": ("FastSCNN", 16, 1024, 2048, "infer"),
+    "espnet_infer_bf16_b16_1024x2048": ("ESPNet", 16, 1024, 2048, "infer"),
+    "espnetv2_infer_bf16_b16_1024x2048": ("ESPNet_v2", 16, 1024, 2048, "infer"),
     # BASELINE.json configs[2]: DABNet bf16 training, batch 8/GPU, 512x1024, weighted CE, Adam, data parallel
     "dabnet_train_bf16_b8_512x1024": ("DABNet", 8, 512, 1024, "train"),
 }
 # block-fused algorithmic elements per input pixel (forward), bf16 storage; the
 # logits term (19 elements/pixel) is replaced by the 1-byte argmax mask because the head is fused.
-ALG_ELEMS_PER_PX = {"ERFNet": 162.0, "DABNet": 189.5, "ENet": 178.0, "CGNet": 234.3, "FastSCNN": 54.6}
-GMAC_512x1024 = {"ERFNet": 26.60, "DABNet": 10.22, "ENet": 4.12, "CGNet": 6.76, "FastSCNN": 1.68}
+ALG_ELEMS_PER_PX = {"ERFNet": 162.0, "DABNet": 189.5, "ENet": 178.0, "CGNet": 234.3, "FastSCNN": 54.6,
+                    "ESPNet": 141.2, "ESPNet_v2": 186.9}
+GMAC_512x1024 = {"ERFNet": 26.60, "DABNet": 10.22, "ENet": 4.12, "CGNet": 6.76, "FastSCNN": 1.68, "ESPNet": 3.36,
+                 "ESPNet_v2": 5.65}
 
 
 def peaks():

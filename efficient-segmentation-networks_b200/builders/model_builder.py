@@ -9,6 +9,7 @@ from model.DABNet import DABNet
 from model.ENet import ENet
 from model.CGNet import CGNet
 from model.FastSCNN import FastSCNN
+from model.ESPNet import ESPNet
 from model.ESPNet_v2.SegmentationModel import EESPNet_Seg
 
 _HOT_PATH = {
@@ -18,6 +19,7 @@ _HOT_PATH = {
     "CGNet": CGNet,
     "FastSCNN": FastSCNN,
     "ESPNet_v2": EESPNet_Seg,
+    "ESPNet": ESPNet,
 }
 _REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
                     "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")

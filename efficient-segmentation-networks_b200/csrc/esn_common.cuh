@@ -91,6 +91,7 @@ struct EpiArgs {
   int res_dtype;
   int act;
   int pre_act;   // ESN_EP_ACT_BEFORE_RESIDUAL
+  int res_first; // ESN_EP_RESIDUAL_FIRST
 };
 
 static inline EpiArgs make_epi(const EsnEpilogue& e) {
@@ -103,6 +104,7 @@ static inline EpiArgs make_epi(const EsnEpilogue& e) {
   a.res_dtype = e.residual.dtype;
   a.act = e.act;
   a.pre_act = (e.flags & ESN_EP_ACT_BEFORE_RESIDUAL) ? 1 : 0;
+  a.res_first = (e.flags & ESN_EP_RESIDUAL_FIRST) ? 1 : 0;
   return a;
 }
 
@@ -111,4 +113,4 @@ static inline bool esn_valid_nhwc(const EsnTensor& t) {
          t.w > 0 && t.c > 0 && t.c_stride >= t.c;
 }
 
-int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y);
+int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y, bool allow_residual_first = false);

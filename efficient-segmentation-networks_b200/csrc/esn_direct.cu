@@ -140,6 +140,64 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectArgs a) {
   }
 }
 
+// ConvTranspose2d(k=2, stride 2, pad 0), Cout <= 32: every input pixel owns its 2x2 output block, so one
+// thread reads its Cin values once per tap (L1) against shared-memory weights and writes four NHWC pixels
+// through the fused epilogue.  (ESPNet's up_l3 / up_l2, ESPNet.py:346-350.)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128) convt2x2_nhwc_kernel(const DirectArgs a, const int cp) {
+  extern __shared__ float sw[];  // [4][Cin][cp]
+  for (int i = threadIdx.x; i < 4 * a.Cin * cp; i += blockDim.x) {
+    const int co = i % cp, tc = i / cp;
+    sw[i] = co < a.Cout ? a.w[(size_t)tc * a.Cout + co] : 0.f;
+  }
+  __syncthreads();
+  const long long total = (long long)a.N * a.Hi * a.Wi;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % a.Wi);
+  const int i = (int)((idx / a.Wi) % a.Hi);
+  const int n = (int)(idx / ((long long)a.Wi * a.Hi));
+  const TI* xp = reinterpret_cast<const TI*>(a.x) + (size_t)idx * a.x_cs;
+  const int nq = cp / 4;
+#pragma unroll 1
+  for (int tap = 0; tap < 4; ++tap) {
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    const float* wt = sw + (size_t)tap * a.Cin * cp;
+    for (int c = 0; c < a.Cin; ++c) {
+      const float v = ld1<TI>(xp + c);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < nq) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)c * cp + 4 * q);
+          acc[4 * q] = fmaf(v, w4.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        }
+    }
+    const int ho = 2 * i + (tap >> 1), wo = 2 * j + (tap & 1);
+    const size_t opix = ((size_t)((size_t)n * a.Ho + ho) * a.Wo + wo);
+    TO* yp = reinterpret_cast<TO*>(a.y) + opix * a.y_cs;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < a.Cout) {
+        const float sc = a.ep.scale ? __ldg(a.ep.scale + k) : 1.f;
+        const float sh = a.ep.shift ? __ldg(a.ep.shift + k) : 0.f;
+        const float al = (a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + k) : 0.f;
+        float t = acc[k] * sc + sh;
+        if (a.ep.res) {
+          if (a.ep.pre_act) t = apply_act(t, a.ep.act, al);
+          const size_t ri = opix * a.ep.res_cstride + k;
+          t += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
+                                             : reinterpret_cast<const float*>(a.ep.res)[ri];
+        }
+        st1<TO>(yp + k, apply_act(t, a.ep.act, al));
+      }
+  }
+}
+
 template <typename TI, typename TO>
 int launch_direct(const DirectArgs& a, bool cov4, bool civ4, cudaStream_t st) {
   const int cov = cov4 ? 4 : 1;
@@ -160,8 +218,9 @@ int launch_direct(const DirectArgs& a, bool cov4, bool civ4, cudaStream_t st) {
 
 }  // namespace
 
-int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y) {
+int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y, bool allow_residual_first) {
   if (e.act < ESN_ACT_NONE || e.act > ESN_ACT_PRELU) return ESN_ERR_BAD_ARG;
+  if ((e.flags & ESN_EP_RESIDUAL_FIRST) && !allow_residual_first) return ESN_ERR_UNSUPPORTED;
   if (e.act == ESN_ACT_PRELU && !e.alpha) return ESN_ERR_BAD_ARG;
   if (e.residual.ptr) {
     const EsnTensor& r = e.residual;
@@ -237,6 +296,20 @@ extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
     civ4 = false;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->transposed && !dw && !nchw && p->kh == 2 && p->kw == 2 && p->stride == 2 && p->pad_h == 0 && p->pad_w == 0 &&
+      p->dil_h == 1 && p->dil_w == 1 && y.c <= 32 && y.h == 2 * x.h && y.w == 2 * x.w) {
+    const int cp = (y.c + 3) / 4 * 4;
+    const size_t smem = (size_t)4 * x.c * cp * sizeof(float);
+    if (smem <= 48 * 1024) {
+      const int grid = esn_cdiv((long long)x.n * x.h * x.w, 128);
+      if (x.dtype == ESN_F32 && y.dtype == ESN_F32) convt2x2_nhwc_kernel<float, float><<<grid, 128, smem, st>>>(a, cp);
+      else if (x.dtype == ESN_F32) convt2x2_nhwc_kernel<float, __nv_bfloat16><<<grid, 128, smem, st>>>(a, cp);
+      else if (y.dtype == ESN_F32) convt2x2_nhwc_kernel<__nv_bfloat16, float><<<grid, 128, smem, st>>>(a, cp);
+      else convt2x2_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 128, smem, st>>>(a, cp);
+      ESN_CHECK_LAUNCH();
+      return ESN_OK;
+    }
+  }
   if (x.dtype == ESN_F32 && y.dtype == ESN_F32) return launch_direct<float, float>(a, cov4, civ4, st);
   if (x.dtype == ESN_F32 && y.dtype == ESN_BF16) return launch_direct<float, __nv_bfloat16>(a, cov4, civ4, st);
   if (x.dtype == ESN_BF16 && y.dtype == ESN_BF16)

@@ -97,6 +97,94 @@ __global__ void __launch_bounds__(128) convt2x2_head_kernel(const ConvtHeadArgs 
   }
 }
 
+// Vector variant: one thread = 4 consecutive input pixels -> 8 consecutive outputs in each of the two output
+// rows, so every class plane gets 16-byte (bf16) / 2x16-byte (fp32) stores and each shared-memory weight
+// vector feeds 16 FMAs instead of 4.
+template <typename TL> __device__ __forceinline__ void store8(TL* p, const float* v);
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+  *reinterpret_cast<uint4*>(p) = float_to_bf16x8(v);
+}
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <typename TI, typename TL, int CIN>
+__global__ void __launch_bounds__(128) convt2x2_head_vec_kernel(const ConvtHeadArgs a) {
+  extern __shared__ float sw[];  // [4][CIN][32] + bias[32]
+  float* sb = sw + 4 * CIN * 32;
+  for (int i = threadIdx.x; i < 4 * CIN * 32; i += blockDim.x) sw[i] = a.w[i];
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) sb[i] = i < a.classes ? a.bias[i] : 0.f;
+  __syncthreads();
+  const int wq = a.Wi / 4;
+  const long long total = (long long)a.N * a.Hi * wq;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j0 = (int)(idx % wq) * 4;
+  const int i = (int)((idx / wq) % a.Hi);
+  const int n = (int)(idx / ((long long)wq * a.Hi));
+  float f[4][CIN];
+  const TI* xp = reinterpret_cast<const TI*>(a.x) + ((size_t)((size_t)n * a.Hi + i) * a.Wi + j0) * a.x_cs;
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < CIN; c += 4) {
+      const float4 t = ld4<TI>(xp + (size_t)p * a.x_cs + c);
+      f[p][c] = t.x; f[p][c + 1] = t.y; f[p][c + 2] = t.z; f[p][c + 3] = t.w;
+    }
+  const int Ho = 2 * a.Hi, Wo = 2 * a.Wi;
+  const int ncls4 = (a.classes + 3) / 4;
+#pragma unroll 1
+  for (int r = 0; r < 2; ++r) {
+    const int ho = 2 * i + r;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) { best[o] = -INFINITY; bi[o] = 0; }
+#pragma unroll 1
+    for (int q = 0; q < ncls4; ++q) {
+      float acc[4][8];  // [class in quad][output pixel = 2*p + s]
+      const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { acc[0][o] = b.x; acc[1][o] = b.y; acc[2][o] = b.z; acc[3][o] = b.w; }
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + (size_t)((r * 2 + 0) * CIN + c) * 32 + 4 * q);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + (size_t)((r * 2 + 1) * CIN + c) * 32 + 4 * q);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float v = f[p][c];
+          acc[0][2 * p] = fmaf(v, w0.x, acc[0][2 * p]);
+          acc[1][2 * p] = fmaf(v, w0.y, acc[1][2 * p]);
+          acc[2][2 * p] = fmaf(v, w0.z, acc[2][2 * p]);
+          acc[3][2 * p] = fmaf(v, w0.w, acc[3][2 * p]);
+          acc[0][2 * p + 1] = fmaf(v, w1.x, acc[0][2 * p + 1]);
+          acc[1][2 * p + 1] = fmaf(v, w1.y, acc[1][2 * p + 1]);
+          acc[2][2 * p + 1] = fmaf(v, w1.z, acc[2][2 * p + 1]);
+          acc[3][2 * p + 1] = fmaf(v, w1.w, acc[3][2 * p + 1]);
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = 4 * q + kk;
+        if (k < a.classes) {
+          if (a.logits)
+            store8<TL>(reinterpret_cast<TL*>(a.logits) + ((size_t)((size_t)n * a.classes + k) * Ho + ho) * Wo + 2 * j0, acc[kk]);
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (acc[kk][o] > best[o]) { best[o] = acc[kk][o]; bi[o] = k; }
+        }
+      }
+    }
+    if (a.mask) {
+      uint8_t m[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) m[o] = (uint8_t)bi[o];
+      *reinterpret_cast<uint2*>(a.mask + ((size_t)n * Ho + ho) * Wo + 2 * j0) = *reinterpret_cast<const uint2*>(m);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- bilinear (align_corners=False) head
 struct BilinearHeadArgs {
   const void* x;  // NHWC low-res scores
@@ -144,6 +232,127 @@ __global__ void __launch_bounds__(256) bilinear_head_kernel(const BilinearHeadAr
     if (k == 0 || v > best) { best = v; bi = k; }
   }
   if (a.mask) a.mask[idx] = (uint8_t)bi;
+}
+
+// Vector variant: one thread = PX consecutive output pixels of one row (16-byte stores into every class
+// plane, PX bytes of mask).  The two source rows are blended once per source column and the column pair is
+// rolled along the row, so an 8x upsample reads 3 class vectors per 8 outputs instead of 32.
+template <typename TI, int NC> __device__ __forceinline__ void load_classes(const TI* p, float* f);
+template <int NC> __device__ __forceinline__ void load_classes_f32(const float* p, float* f) {
+#pragma unroll
+  for (int k = 0; k < NC; k += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + k));
+    f[k] = t.x; f[k + 1] = t.y; f[k + 2] = t.z; f[k + 3] = t.w;
+  }
+}
+template <int NC> __device__ __forceinline__ void load_classes_bf16(const __nv_bfloat16* p, float* f) {
+#pragma unroll
+  for (int k = 0; k < NC; k += 4) {
+    const float4 t = ld4<__nv_bfloat16>(p + k);
+    f[k] = t.x; f[k + 1] = t.y; f[k + 2] = t.z; f[k + 3] = t.w;
+  }
+}
+template <int NC> struct ClsLoad {
+  static __device__ __forceinline__ void ld(const float* p, float* f) { load_classes_f32<NC>(p, f); }
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) { load_classes_bf16<NC>(p, f); }
+};
+
+template <typename TL, int PX> struct RowStore;
+template <> struct RowStore<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) { *reinterpret_cast<uint4*>(p) = float_to_bf16x8(v); }
+};
+template <> struct RowStore<float, 4> {
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <typename TI, typename TL, int NC, int PX>
+__global__ void __launch_bounds__(128) bilinear_head_vec_kernel(const BilinearHeadArgs a) {
+  const int wo0 = (blockIdx.x * 128 + threadIdx.x) * PX;
+  if (wo0 >= a.Wo) return;
+  const int ho = blockIdx.y, n = blockIdx.z;
+  float fh;
+  if (a.align) {
+    fh = a.sh * ho;
+  } else {
+    fh = a.sh * (ho + 0.5f) - 0.5f;
+    fh = fh < 0.f ? 0.f : fh;
+  }
+  const int h0 = min((int)fh, a.Hi - 1);
+  const int hp = (h0 < a.Hi - 1) ? 1 : 0;
+  const float lh1 = fh - h0, lh0 = 1.f - lh1;
+  const TI* r0 = reinterpret_cast<const TI*>(a.x) + ((size_t)((size_t)n * a.Hi + h0) * a.Wi) * a.x_cs;
+  const TI* r1 = r0 + (size_t)hp * a.Wi * a.x_cs;
+  float c0[NC], c1[NC];
+  float out[NC][PX];
+  int curw = -2;
+  auto blend = [&](int w, float* c) {
+    float t[NC], b[NC];
+    ClsLoad<NC>::ld(r0 + (size_t)w * a.x_cs, t);
+    ClsLoad<NC>::ld(r1 + (size_t)w * a.x_cs, b);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c[k] = lh0 * t[k] + lh1 * b[k];
+  };
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    const int wo = wo0 + j;
+    float fw;
+    if (a.align) {
+      fw = a.sw * wo;
+    } else {
+      fw = a.sw * (wo + 0.5f) - 0.5f;
+      fw = fw < 0.f ? 0.f : fw;
+    }
+    const int w0 = min((int)fw, a.Wi - 1);
+    const int wp = (w0 < a.Wi - 1) ? 1 : 0;
+    const float lw1 = fw - w0, lw0 = 1.f - lw1;
+    if (w0 != curw) {
+      if (w0 == curw + 1) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) c0[k] = c1[k];
+      } else {
+        blend(w0, c0);
+      }
+      if (wp) {
+        blend(w0 + 1, c1);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) c1[k] = c0[k];
+      }
+      curw = w0;
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) out[k][j] = lw0 * c0[k] + lw1 * c1[k];
+  }
+  if (a.logits) {
+    TL* lp = reinterpret_cast<TL*>(a.logits) + ((size_t)n * a.classes * a.Ho + ho) * a.Wo + wo0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+      if (k < a.classes) RowStore<TL, PX>::st(lp + (size_t)k * a.Ho * a.Wo, out[k]);
+  }
+  if (a.mask) {
+    uint8_t m[PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      float best = out[0][j];
+      int bi = 0;
+#pragma unroll
+      for (int k = 1; k < NC; ++k)
+        if (k < a.classes && out[k][j] > best) { best = out[k][j]; bi = k; }
+      m[j] = (uint8_t)bi;
+    }
+    uint8_t* mp = a.mask + ((size_t)n * a.Ho + ho) * a.Wo + wo0;
+    if (PX == 8) *reinterpret_cast<uint2*>(mp) = *reinterpret_cast<const uint2*>(m);
+    else *reinterpret_cast<uint32_t*>(mp) = *reinterpret_cast<const uint32_t*>(m);
+  }
+}
+
+template <typename TI, typename TL, int PX>
+void launch_bilinear_vec(const BilinearHeadArgs& a, cudaStream_t st) {
+  dim3 grid((unsigned)((a.Wo / PX + 127) / 128), (unsigned)a.Ho, (unsigned)a.N);
+  if (a.classes <= 20) bilinear_head_vec_kernel<TI, TL, 20, PX><<<grid, 128, 0, st>>>(a);
+  else bilinear_head_vec_kernel<TI, TL, 32, PX><<<grid, 128, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------- weighted cross-entropy on NCHW logits
@@ -236,7 +445,7 @@ extern "C" int esn_head_convt2x2(const EsnHead* p, void* stream) {
   if (p->classes < 1 || p->classes > kMaxClasses) return ESN_ERR_UNSUPPORTED;
   const EsnTensor& x = p->x;
   if (p->out_h != 2 * x.h || p->out_w != 2 * x.w) return ESN_ERR_BAD_SHAPE;
-  if (x.c != 16 || x.c_stride % 4) return ESN_ERR_UNSUPPORTED;
+  if ((x.c != 16 && x.c != 20) || x.c_stride % 4) return ESN_ERR_UNSUPPORTED;   // 20 = 19 classes + one zero channel
   if ((uintptr_t)x.ptr % 16) return ESN_ERR_ALIGN;
   int ldt = ESN_F32;
   if (p->logits.ptr) {
@@ -259,16 +468,42 @@ extern "C" int esn_head_convt2x2(const EsnHead* p, void* stream) {
   a.classes = p->classes;
   const long long total = (long long)x.n * x.h * x.w;
   const int block = 128, grid = esn_cdiv(total, block);
-  const size_t smem = (4 * 16 * 32 + 32) * sizeof(float);
+  const size_t smem = (4 * (size_t)x.c * 32 + 32) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (x.dtype == ESN_F32 && ldt == ESN_F32)
-    convt2x2_head_kernel<float, float, 16><<<grid, block, smem, st>>>(a);
-  else if (x.dtype == ESN_F32)
-    convt2x2_head_kernel<float, __nv_bfloat16, 16><<<grid, block, smem, st>>>(a);
-  else if (ldt == ESN_F32)
-    convt2x2_head_kernel<__nv_bfloat16, float, 16><<<grid, block, smem, st>>>(a);
-  else
-    convt2x2_head_kernel<__nv_bfloat16, __nv_bfloat16, 16><<<grid, block, smem, st>>>(a);
+#define ESN_HEAD_LAUNCH(CIN)                                                                   \
+  do {                                                                                         \
+    if (x.dtype == ESN_F32 && ldt == ESN_F32)                                                  \
+      convt2x2_head_kernel<float, float, CIN><<<grid, block, smem, st>>>(a);                   \
+    else if (x.dtype == ESN_F32)                                                               \
+      convt2x2_head_kernel<float, __nv_bfloat16, CIN><<<grid, block, smem, st>>>(a);           \
+    else if (ldt == ESN_F32)                                                                   \
+      convt2x2_head_kernel<__nv_bfloat16, float, CIN><<<grid, block, smem, st>>>(a);           \
+    else                                                                                       \
+      convt2x2_head_kernel<__nv_bfloat16, __nv_bfloat16, CIN><<<grid, block, smem, st>>>(a);   \
+  } while (0)
+  const bool vec = x.w % 4 == 0 && (!p->logits.ptr || (uintptr_t)p->logits.ptr % 16 == 0) && (!p->mask || (uintptr_t)p->mask % 8 == 0);
+  if (vec) {
+    const int vgrid = esn_cdiv(total / 4, block);
+#define ESN_HEADV_LAUNCH(CIN)                                                                       \
+  do {                                                                                              \
+    if (x.dtype == ESN_F32 && ldt == ESN_F32)                                                       \
+      convt2x2_head_vec_kernel<float, float, CIN><<<vgrid, block, smem, st>>>(a);                   \
+    else if (x.dtype == ESN_F32)                                                                    \
+      convt2x2_head_vec_kernel<float, __nv_bfloat16, CIN><<<vgrid, block, smem, st>>>(a);           \
+    else if (ldt == ESN_F32)                                                                        \
+      convt2x2_head_vec_kernel<__nv_bfloat16, float, CIN><<<vgrid, block, smem, st>>>(a);           \
+    else                                                                                            \
+      convt2x2_head_vec_kernel<__nv_bfloat16, __nv_bfloat16, CIN><<<vgrid, block, smem, st>>>(a);   \
+  } while (0)
+    if (x.c == 16) ESN_HEADV_LAUNCH(16);
+    else ESN_HEADV_LAUNCH(20);
+#undef ESN_HEADV_LAUNCH
+  } else if (x.c == 16) {
+    ESN_HEAD_LAUNCH(16);
+  } else {
+    ESN_HEAD_LAUNCH(20);
+  }
+#undef ESN_HEAD_LAUNCH
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }
@@ -307,6 +542,22 @@ extern "C" int esn_head_bilinear(const EsnHead* p, void* stream) {
   const long long total = (long long)x.n * p->out_h * p->out_w;
   const int block = 256, grid = esn_cdiv(total, block);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {  // vector path: class vectors readable as whole 4-channel groups, rows storable as 16-byte pieces
+    const int nc = p->classes <= 20 ? 20 : 32;
+    const int px = ldt == ESN_BF16 ? 8 : 4;
+    const size_t xsz = x.dtype == ESN_F32 ? 4 : 2;
+    const bool ok = p->classes <= 32 && x.c_stride >= nc && x.c_stride % 4 == 0 && (uintptr_t)x.ptr % (4 * xsz) == 0 &&
+                    p->out_w % px == 0 && p->out_h <= 65535 && x.n <= 65535 &&
+                    (!p->logits.ptr || (uintptr_t)p->logits.ptr % 16 == 0) && (!p->mask || (uintptr_t)p->mask % 8 == 0);
+    if (ok) {
+      if (x.dtype == ESN_F32 && ldt == ESN_F32) launch_bilinear_vec<float, float, 4>(a, st);
+      else if (x.dtype == ESN_F32) launch_bilinear_vec<float, __nv_bfloat16, 8>(a, st);
+      else if (ldt == ESN_F32) launch_bilinear_vec<__nv_bfloat16, float, 4>(a, st);
+      else launch_bilinear_vec<__nv_bfloat16, __nv_bfloat16, 8>(a, st);
+      ESN_CHECK_LAUNCH();
+      return ESN_OK;
+    }
+  }
   if (x.dtype == ESN_F32 && ldt == ESN_F32)
     bilinear_head_kernel<float, float><<<grid, block, 0, st>>>(a);
   else if (x.dtype == ESN_F32)

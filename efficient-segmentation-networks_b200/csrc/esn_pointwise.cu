@@ -88,8 +88,13 @@ __global__ void __launch_bounds__(256) pw_kernel(const PwArgs a) {
     if (cc < a.C) {
       const float sc = a.ep.scale ? __ldg(a.ep.scale + cc) : 1.f;
       const float sh = a.ep.shift ? __ldg(a.ep.shift + cc) : 0.f;
+      if (a.ep.res && a.ep.res_first) {
+        const size_t ri = opix * a.ep.res_cstride + cc;
+        v[j] += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
+                                              : reinterpret_cast<const float*>(a.ep.res)[ri];
+      }
       float t = v[j] * sc + sh;
-      if (a.ep.res) {
+      if (a.ep.res && !a.ep.res_first) {
         if (a.ep.pre_act) t = apply_act(t, a.ep.act, (a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + cc) : 0.f);
         const size_t ri = opix * a.ep.res_cstride + cc;
         t += (a.ep.res_dtype == ESN_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[ri])
@@ -106,6 +111,138 @@ __global__ void __launch_bounds__(256) pw_kernel(const PwArgs a) {
     st1<TO>(yp, v[0]);
 }
 
+// ---- vector path: NHWC in, NHWC out, 16-byte accesses.  A thread owns one group of V channels (its
+// scale / shift / slope live in registers) and walks pixels of one output row; the threads of a CTA cover
+// ncg channel groups x ppb pixels per step, channel groups fastest, so a warp touches whole pixels.
+// Channel counts that are not a multiple of V (35, 131, 259 ... concat slices) load the full vector -- it
+// stays inside the pixel stride -- and store the valid lanes one by one.
+template <typename T, int V> struct PwVec;
+template <> struct PwVec<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float* f) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct PwVec<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
+    const float4 t = ld4<__nv_bfloat16>(p);
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
+    st4<__nv_bfloat16>(p, make_float4(f[0], f[1], f[2], f[3]));
+  }
+};
+template <> struct PwVec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    bf16x8_to_float(r, f);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
+    *reinterpret_cast<uint4*>(p) = float_to_bf16x8(f);
+  }
+};
+
+template <typename TI, typename TO, int V, int OP>
+__global__ void __launch_bounds__(256) pw_vec_kernel(const PwArgs a, const int ncg, const int ppb, const int wpb) {
+  const int pl = threadIdx.x / ncg;
+  if (pl >= ppb) return;
+  const int c = (threadIdx.x - pl * ncg) * V;
+  const int row = blockIdx.x;
+  const int n = row / a.Ho, ho = row - n * a.Ho;
+  float sc[V], sh[V], al[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const bool ok = c + j < a.C;
+    sc[j] = (ok && a.ep.scale) ? __ldg(a.ep.scale + c + j) : 1.f;
+    sh[j] = (ok && a.ep.shift) ? __ldg(a.ep.shift + c + j) : 0.f;
+    al[j] = (ok && a.ep.act == ESN_ACT_PRELU) ? __ldg(a.ep.alpha + c + j) : 0.f;
+  }
+  const bool full = c + V <= a.C;
+  const int act = a.ep.act;
+  const TI* __restrict__ x = reinterpret_cast<const TI*>(a.x) + (size_t)n * a.Hi * a.Wi * a.x_cs + c;
+  TO* __restrict__ y = reinterpret_cast<TO*>(a.y) + (size_t)row * a.Wo * a.y_cs + c;
+  const int w_end = min(a.Wo, (int)(blockIdx.y + 1) * wpb);
+  for (int wo = blockIdx.y * wpb + pl; wo < w_end; wo += ppb) {
+    float v[V];
+    if (OP == OP_MAXPOOL2) {
+      float t[V];
+      const TI* p0 = x + ((size_t)(2 * ho) * a.Wi + 2 * wo) * a.x_cs;
+      PwVec<TI, V>::ld(p0, v);
+      PwVec<TI, V>::ld(p0 + a.x_cs, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], t[j]);
+      PwVec<TI, V>::ld(p0 + (size_t)a.Wi * a.x_cs, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], t[j]);
+      PwVec<TI, V>::ld(p0 + (size_t)a.Wi * a.x_cs + a.x_cs, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], t[j]);
+    } else if (OP == OP_AVGPOOL3S2) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = 0.f;
+#pragma unroll
+      for (int r = -1; r <= 1; ++r) {
+        const int hi = 2 * ho + r;
+        if (hi < 0 || hi >= a.Hi) continue;
+#pragma unroll
+        for (int q = -1; q <= 1; ++q) {
+          const int wi = 2 * wo + q;
+          if (wi < 0 || wi >= a.Wi) continue;
+          float t[V];
+          PwVec<TI, V>::ld(x + ((size_t)hi * a.Wi + wi) * a.x_cs, t);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] += t[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] *= (1.f / 9.f);
+    } else {
+      PwVec<TI, V>::ld(x + ((size_t)ho * a.Wi + wo) * a.x_cs, v);
+    }
+    if (a.ep.res) {
+      float r[V];
+      const size_t ri = ((size_t)row * a.Wo + wo) * a.ep.res_cstride + c;
+      if (a.ep.res_dtype == ESN_BF16) PwVec<__nv_bfloat16, V>::ld(reinterpret_cast<const __nv_bfloat16*>(a.ep.res) + ri, r);
+      else if (V == 4) PwVec<float, 4>::ld(reinterpret_cast<const float*>(a.ep.res) + ri, r);
+      if (a.ep.res_first) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = apply_act(fmaf(v[j] + r[j], sc[j], sh[j]), act, al[j]);
+      } else if (a.ep.pre_act) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = apply_act(apply_act(fmaf(v[j], sc[j], sh[j]), act, al[j]) + r[j], act, al[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = apply_act(fmaf(v[j], sc[j], sh[j]) + r[j], act, al[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = apply_act(fmaf(v[j], sc[j], sh[j]), act, al[j]);
+    }
+    TO* yp = y + (size_t)wo * a.y_cs;
+    if (full) {
+      PwVec<TO, V>::st(yp, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (c + j < a.C) st1<TO>(yp + j, v[j]);
+    }
+  }
+}
+
+template <typename TI, typename TO, int V, int OP>
+void launch_pw_vec(const PwArgs& a, cudaStream_t st) {
+  const int ncg = (a.C + V - 1) / V;
+  const int ppb = 256 / ncg;
+  int iters = 4;
+  while (iters > 1 && (long long)a.N * a.Ho * ((a.Wo + ppb * iters - 1) / (ppb * iters)) < 148 * 8) iters >>= 1;
+  const int wpb = ppb * iters;
+  dim3 grid((unsigned)(a.N * a.Ho), (unsigned)((a.Wo + wpb - 1) / wpb));
+  pw_vec_kernel<TI, TO, V, OP><<<grid, 256, 0, st>>>(a, ncg, ppb, wpb);
+}
+
 template <int OP>
 int run_pw(const EsnPool* p, void* stream) {
   if (!p) return ESN_ERR_BAD_ARG;
@@ -118,7 +255,7 @@ int run_pw(const EsnPool* p, void* stream) {
   if (OP == OP_MAXPOOL2 && (y.h != x.h / 2 || y.w != x.w / 2)) return ESN_ERR_BAD_SHAPE;
   if (OP == OP_AVGPOOL3S2 && (y.h != (x.h - 1) / 2 + 1 || y.w != (x.w - 1) / 2 + 1)) return ESN_ERR_BAD_SHAPE;
   if (OP == OP_AFFINE && (y.h != x.h || y.w != x.w)) return ESN_ERR_BAD_SHAPE;
-  int rc = esn_check_epilogue(p->ep, y);
+  int rc = esn_check_epilogue(p->ep, y, OP == OP_AFFINE);
   if (rc) return rc;
   PwArgs a;
   a.x = x.ptr;
@@ -134,12 +271,28 @@ int run_pw(const EsnPool* p, void* stream) {
   a.y_cs = y.c_stride;
   a.ep = make_epi(p->ep);
   const size_t ysz = y.dtype == ESN_F32 ? 4 : 2, xsz = x.dtype == ESN_F32 ? 4 : 2;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!nchw) {
+    const bool all16 = x.dtype == ESN_BF16 && y.dtype == ESN_BF16 && (!p->ep.residual.ptr || p->ep.residual.dtype == ESN_BF16);
+    const int V = all16 ? 8 : 4;
+    const EsnTensor& r = p->ep.residual;
+    const bool res_ok = !r.ptr || (r.c_stride % V == 0 && (uintptr_t)r.ptr % (V * (r.dtype == ESN_F32 ? 4 : 2)) == 0);
+    if (x.c_stride % V == 0 && y.c_stride % V == 0 && (uintptr_t)x.ptr % (V * xsz) == 0 && (uintptr_t)y.ptr % (V * ysz) == 0 &&
+        res_ok && (y.c + V - 1) / V <= 256) {
+      if (all16) launch_pw_vec<__nv_bfloat16, __nv_bfloat16, 8, OP>(a, st);
+      else if (x.dtype == ESN_F32 && y.dtype == ESN_F32) launch_pw_vec<float, float, 4, OP>(a, st);
+      else if (x.dtype == ESN_F32) launch_pw_vec<float, __nv_bfloat16, 4, OP>(a, st);
+      else if (y.dtype == ESN_F32) launch_pw_vec<__nv_bfloat16, float, 4, OP>(a, st);
+      else launch_pw_vec<__nv_bfloat16, __nv_bfloat16, 4, OP>(a, st);
+      ESN_CHECK_LAUNCH();
+      return ESN_OK;
+    }
+  }
   const bool v4 = (y.c % 4 == 0) && (y.c_stride % 4 == 0) && ((uintptr_t)y.ptr % (4 * ysz) == 0) &&
                   (nchw || ((x.c_stride % 4 == 0) && ((uintptr_t)x.ptr % (4 * xsz) == 0)));
   const int V = v4 ? 4 : 1;
   const long long total = (long long)y.n * y.h * y.w * ((y.c + V - 1) / V);
   const int block = 256, grid = esn_cdiv(total, block);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define ESN_PW_LAUNCH(TI, TO)                                    \
   do {                                                           \
     if (v4)                                                      \

@@ -212,7 +212,10 @@ class ConvPrep:
         if getattr(self, "_parts", None) is None:
             import copy
             taps = self.kh * self.kw
-            per = max(64, (128 * 1024 // (taps * self.cout_pad * 2)) // 64 * 64)
+            # weights of one part stay resident in shared memory next to the A ring and the output staging
+            staging = 128 * self.cout * 2 if (self.cout % 8 == 0 and (self.cout <= 64 or self.cout % 64 == 0)) else 0
+            budget = 226 * 1024 - 6144 - 2 * 128 * 64 * 2 - staging
+            per = max(64, (budget // (taps * self.cout_pad * 2)) // 64 * 64)
             parts, lo = [], 0
             while lo < self.cin:
                 hi = min(self.cin, lo + per)

@@ -69,7 +69,11 @@ typedef struct EsnEpilogue {
                           "ext = act(BN(conv)); out = act(main + ext)" pattern of ENet.py:93-100 */
   EsnTensor residual;  /* ptr == NULL: none; else same N,H,W,C as the output */
 } EsnEpilogue;
-enum { ESN_EP_ACT_BEFORE_RESIDUAL = 1 };
+enum {
+  ESN_EP_ACT_BEFORE_RESIDUAL = 1,
+  ESN_EP_RESIDUAL_FIRST = 2 /* v = act((x + residual)*scale + shift): "BN(input + combine)" of ESPNet.py:221-224;
+                               esn_affine_act only, the conv entry points answer ESN_ERR_UNSUPPORTED */
+};
 enum { ESN_STEM_PAD0 = 256 };
 
 /* 2-D convolution / transposed convolution, NHWC, stride/dilation/groups as

@@ -488,3 +488,73 @@ def espnetv2(sd, x, train=False, stats=None):
 
 
 FORWARD["ESPNet_v2"] = espnetv2
+
+
+# --------------------------------------------------------------------------- ESPNet (v1, ESPNet-A decoder)
+def _esp_br(p, x):
+    """BR, model/ESPNet.py:43-62 (eps 1e-3)."""
+    return prelu(bn(p.sub("bn"), x, 1e-3), p["act.weight"])
+
+
+def _esp_branches(p, o1):
+    """The five dilated 3x3 branches + hierarchical sums shared by DownSamplerB / the ESP block, ESPNet.py:155-169."""
+    outs = []
+    for name, d in (("d1", 1), ("d2", 2), ("d4", 4), ("d8", 8), ("d16", 16)):
+        outs.append(F.conv2d(o1, p[name + ".conv.weight"], None, 1, d, d))
+    d1, add = outs[0], outs[1]
+    cat = [d1, add]
+    for o in outs[2:]:
+        add = add + o
+        cat.append(add)
+    return torch.cat(cat, 1)
+
+
+def esp_down(p, x):
+    """DownSamplerB, ESPNet.py:138-173."""
+    o1 = F.conv2d(x, p["c1.conv.weight"], None, 2, 1)
+    return prelu(bn(p.sub("bn"), _esp_branches(p, o1), 1e-3), p["act.weight"])
+
+
+def esp_block(p, x, add=True):
+    """DilatedParllelResidualBlockB, ESPNet.py:176-226."""
+    c = _esp_branches(p, F.conv2d(x, p["c1.conv.weight"]))
+    if add:
+        c = x + c
+    return _esp_br(p.sub("bn"), c)
+
+
+def _esp_encoder(q, x, p_rep, q_rep):
+    """ESPNet_Encoder.forward up to the three concat stages, ESPNet.py:283-318."""
+    o0 = prelu(bn(q.sub("level1.bn"), F.conv2d(x, q["level1.conv.weight"], None, 2, 1), 1e-3), q["level1.act.weight"])
+    inp1 = F.avg_pool2d(x, 3, 2, 1)
+    inp2 = F.avg_pool2d(inp1, 3, 2, 1)
+    o0_cat = _esp_br(q.sub("b1"), torch.cat([o0, inp1], 1))
+    o1_0 = esp_down(q.sub("level2_0"), o0_cat)
+    o1 = o1_0
+    for i in range(p_rep):
+        o1 = esp_block(q.sub("level2.%d" % i), o1)
+    o1_cat = _esp_br(q.sub("b2"), torch.cat([o1, o1_0, inp2], 1))
+    o2_0 = esp_down(q.sub("level3_0"), o1_cat)
+    o2 = o2_0
+    for i in range(q_rep):
+        o2 = esp_block(q.sub("level3.%d" % i), o2)
+    o2_cat = _esp_br(q.sub("b3"), torch.cat([o2_0, o2], 1))
+    return o0_cat, o1_cat, o2_cat
+
+
+def espnet(sd, x, train=False, stats=None):
+    """ESPNet.forward (classes from the weights, p=2, q=3), ESPNet.py:355-385."""
+    p = SD(sd, "", x.dtype, train, stats)
+    q = p.sub("encoder")
+    o0_cat, o1_cat, o2_cat = _esp_encoder(q, x, 2, 3)
+    s = bn(p.sub("br"), F.conv2d(o2_cat, q["classifier.conv.weight"]), 1e-3)
+    o2_c = F.conv_transpose2d(s, p["up_l3.0.weight"], None, 2)
+    o1_c = F.conv2d(o1_cat, p["level3_C.conv.weight"])
+    comb = esp_block(p.sub("combine_l2_l3.1"), _esp_br(p.sub("combine_l2_l3.0"), torch.cat([o1_c, o2_c], 1)), add=False)
+    comb = _esp_br(p.sub("up_l2.1"), F.conv_transpose2d(comb, p["up_l2.0.weight"], None, 2))
+    y = torch.cat([comb, o0_cat], 1)
+    y = prelu(bn(p.sub("conv.bn"), F.conv2d(y, p["conv.conv.weight"], None, 1, 1), 1e-3), p["conv.act.weight"])
+    return F.conv_transpose2d(y, p["classifier.weight"], None, 2)
+
+
+FORWARD["ESPNet"] = espnet

@@ -29,7 +29,7 @@ def _margin_mask(ref_logits, tol):
     return (top2[:, 0] - top2[:, 1]) > tol * top2[:, 0].abs().clamp_min(1e-6)
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet"])
 def test_fp32_matches_reference_golden(name, spec, golden):
     m = _model(name, spec)
     g = golden(name)
@@ -54,7 +54,7 @@ def test_fp32_matches_reference_golden(name, spec, golden):
         assert (mask.cpu().numpy() == nets.argmax_mask(y)).all()       # fused argmax == numpy argmax of our logits
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet"])
 def test_bf16_matches_oracle(name, spec):
     m = _model(name, spec)
     sd = spec_state_dict(spec, name)
@@ -122,6 +122,41 @@ def test_blocks_are_drop_in(name, spec):
         y = blk.cuda().eval()(x.cuda())
         assert y.shape == ref.shape
         assert _rel(y.float().cpu(), ref) < 1e-4
+
+
+def test_esp_blocks_are_drop_in(spec):
+    """ESPNet / ESPNetv2 blocks called on their own take and return ordinary (logical-channel) tensors."""
+    from model.ESPNet import DilatedParllelResidualBlockB, DownSamplerB
+    from model.ESPNet_v2.Model import EESP, DownSampler
+    sd = spec_state_dict(spec, "ESPNet")
+    torch.manual_seed(0)
+    for cls, args, pre, fn, cin in ((DilatedParllelResidualBlockB, (64, 64), "encoder.level2.1.", nets.esp_block, 64),
+                                    (DilatedParllelResidualBlockB, (128, 128), "encoder.level3.0.", nets.esp_block, 128),
+                                    (DownSamplerB, (131, 128), "encoder.level3_0.", nets.esp_down, 131)):
+        blk = cls(*args)
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, cin, 24, 40)
+        ref = fn(nets.SD(sd, pre), x)
+        y = blk.cuda().eval()(x.cuda())
+        assert y.shape == ref.shape
+        assert _rel(y.float().cpu(), ref) < 1e-4, (cls.__name__, args)
+    sd = spec_state_dict(spec, "ESPNet_v2")
+    blk = EESP(256, 256, stride=1, k=4, r_lim=9)
+    pre = "net.level3.1."
+    blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    x = torch.randn(2, 256, 24, 40)
+    ref = nets.e2_eesp(nets.SD(sd, pre), x, 1, 9)
+    assert _rel(blk.cuda().eval()(x.cuda()).float().cpu(), ref) < 1e-4
+    blk = DownSampler(128, 256, k=4, r_lim=11, reinf=True)
+    pre = "net.level3_0."
+    blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    x, img = torch.randn(2, 128, 24, 40), torch.randn(2, 3, 96, 160)
+    ref = nets.e2_down(nets.SD(sd, pre), x, img, 11)
+    y = blk.cuda().eval()(x.cuda(), img.cuda())
+    assert y.shape == ref.shape
+    assert _rel(y.float().cpu(), ref) < 1e-4
+    ref = nets.e2_down(nets.SD(sd, pre), x, None, 11)          # without input reinforcement
+    assert _rel(blk(x.cuda()).float().cpu(), ref) < 1e-4
 
 
 def test_full_size_properties_erfnet(spec):

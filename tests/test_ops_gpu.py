@@ -46,6 +46,8 @@ CONV_CASES = [
     (32, 24, 1, 1, 0, 1, 4, False, 0, 16, 24),      # grouped 1x1 (ESPNetv2 reduce: 8 -> 6 per group)
     (96, 96, 1, 1, 0, 1, 4, False, 0, 12, 20),      # grouped 1x1 expand
     (24, 24, 3, 2, 6, 6, 24, False, 0, 20, 28),     # depthwise, stride 2, dilation 6
+    (40, 19, 2, 2, 0, 1, 1, True, 0, 12, 20),       # ESPNet 2x2/s2 transposed convs
+    (19, 19, 2, 2, 0, 1, 1, True, 0, 9, 14),
 ]
 
 

@@ -10,7 +10,7 @@ from conftest import spec_state_dict
 from oracle import fixture, loss as oloss, nets
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet"])
 def test_eval_forward_matches_reference(name, spec, golden):
     sd = spec_state_dict(spec, name)
     g = golden(name)
