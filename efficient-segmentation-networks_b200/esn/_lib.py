@@ -34,6 +34,11 @@ class EsnConv(C.Structure):
                 ("ep", EsnEpilogue)]
 
 
+class EsnConvPair(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("w1", C.c_void_p), ("w2", C.c_void_p),
+                ("taps", C.c_int32), ("dilation", C.c_int32), ("ep1", EsnEpilogue), ("ep2", EsnEpilogue)]
+
+
 class EsnPool(C.Structure):
     _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("ep", EsnEpilogue)]
 
@@ -89,6 +94,7 @@ class EsnCE(C.Structure):
 SYMBOLS = {
     "esn_conv2d_direct": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
     "esn_conv2d_umma": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_conv_pair_umma": (C.c_int, [C.POINTER(EsnConvPair), C.c_void_p]),
     "esn_stem_conv3x3s2": (C.c_int, [C.POINTER(EsnStem), C.c_void_p]),
     "esn_maxpool2x2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
     "esn_avgpool3x3s2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),

@@ -14,6 +14,7 @@ from . import _lib as L
 _DT = {torch.float32: L.ESN_F32, torch.bfloat16: L.ESN_BF16, torch.uint8: L.ESN_U8, torch.int64: L.ESN_I64}
 _NULL = L.EsnTensor()
 UMMA_ENABLED = os.environ.get("ESN_DISABLE_UMMA", "0") != "1"
+PAIR_DISABLED = os.environ.get("ESN_DISABLE_PAIR", "0") == "1"
 
 
 def stream():
@@ -354,6 +355,51 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
             return out
     p.w = prep.w_direct.data_ptr()
     _call(L.lib.esn_conv2d_direct, "esn_conv2d_direct", (C.byref(p),), alg, flops, tag)
+    return out
+
+
+def pair_supported(x, p1, p2, out, residual):
+    """Mirror of esn_conv_pair_umma's gate (csrc/esn_umma_pair.cu)."""
+    if not UMMA_ENABLED or PAIR_DISABLED or x.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        return False
+    n, c, h, w = x.shape
+    if c not in (16, 64) or p1.cout != c or p2.cout != c or p1.cin != c or p2.cin != c:
+        return False
+    if (p1.kh, p1.kw, p2.kh, p2.kw) != (3, 1, 1, 3) or p1.stride != 1 or p2.stride != 1 or p1.groups != 1 or p2.groups != 1:
+        return False
+    d = p1.dil_h
+    if d != p2.dil_w or d < 1 or d > 8 or p1.pad_h != d or p2.pad_w != d or p1.pad_w != 0 or p2.pad_h != 0:
+        return False
+    if p1.act not in (L.ACT_NONE, L.ACT_RELU) or getattr(p1, "ep_flags", 0) or getattr(p2, "ep_flags", 0):
+        return False
+    bw = 128 * (64 // c)
+    if w % bw or w // bw > 8:
+        return False
+    rb = 2 * c
+    inter = ((w + 16) * rb + 1023) // 1024 * 1024
+    wreg = (2 * 3 * c * rb + 1023) // 1024 * 1024
+    if 1024 + wreg + inter + 2 * bw * rb + 1280 + 1024 + 4 * bw * rb > 226 * 1024:
+        return False
+    for t in (x, out) + ((residual,) if residual is not None else ()):
+        if not is_nhwc(t) or t.stride(3) % 8 or t.data_ptr() % 16 or t.dtype != torch.bfloat16:
+            return False
+    return True
+
+
+def conv_pair(x, p1, p2, out=None, residual=None):
+    """Fused k x 1 -> act -> 1 x k -> affine (+residual) -> act on the tcgen05 pair kernel (caller checked pair_supported)."""
+    n, c, h, w = x.shape
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    p = L.EsnConvPair()
+    p.x, p.y = tdesc(x), tdesc(out)
+    p.w1, p.w2 = p1.w_umma.data_ptr(), p2.w_umma.data_ptr()
+    p.taps, p.dilation = 3, p1.dil_h
+    _epilogue(p.ep1, p1.scale, p1.shift, p1.alpha, p1.act, None)
+    _epilogue(p.ep2, p2.scale, p2.shift, p2.alpha, p2.act, residual)
+    alg = _nbytes(x) + _nbytes(out) + _nbytes(residual)
+    flops = 2 * 2 * n * h * w * c * c * 3
+    _call(L.lib.esn_conv_pair_umma, "esn_conv_pair_umma", (C.byref(p),), alg, flops, "3x1+1x3 c%d d%d" % (c, p1.dil_h))
     return out
 
 

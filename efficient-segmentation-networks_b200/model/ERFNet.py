@@ -89,6 +89,18 @@ class non_bottleneck_1d(PrepMixin, nn.Module):
         _no_train(self)   # eval: Dropout2d is the identity (ERFNet.py:62-63)
         x = ops.as_act(input)
         c1, c2, c3, c4 = self.prep(x.device)
+        n, c, h, w = x.shape
+        # each factorized pair is one kernel when the shape allows (intermediate row kept in shared memory)
+        if x.dtype == torch.bfloat16:
+            y = ops.new_act(n, c, h, w, x.dtype, x.device)
+            if ops.pair_supported(x, c1, c2, y, None):
+                ops.conv_pair(x, c1, c2, out=y)
+            else:
+                y = ops.conv2d(ops.conv2d(x, c1), c2, out=y)
+            out = ops.new_act(n, c, h, w, x.dtype, x.device)
+            if ops.pair_supported(y, c3, c4, out, x):
+                return ops.conv_pair(y, c3, c4, out=out, residual=x)
+            return ops.conv2d(ops.conv2d(y, c3), c4, out=out, residual=x)
         y = ops.conv2d(x, c1)
         y = ops.conv2d(y, c2)
         y = ops.conv2d(y, c3)

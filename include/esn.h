@@ -113,6 +113,23 @@ int esn_conv2d_direct(const EsnConv* p, void* stream);
  * ESN_ERR_UNSUPPORTED for anything else (the host then calls esn_conv2d_direct). */
 int esn_conv2d_umma(const EsnConv* p, void* stream);
 
+/* Fused factorized pair: y = act2( conv_1xk( act1( conv_kx1(x)*s1 + b1 ) )*s2 + b2 (+ residual) ), both convs
+ * dense C -> C with `taps` taps, padding (taps-1)/2 * dilation, the same dilation.  One half of the reference's
+ * non_bottleneck_1d (ERFNet.py:44-65: conv3x1 -> ReLU -> conv1x3 -> BN -> ReLU, and the dilated second pair
+ * + residual); the intermediate tensor stays in shared memory.  bf16 NHWC, C in {16, 64}, taps == 3,
+ * dilation <= 8, W a multiple of 128 (C=64) / 512 (C=16), shared memory for one intermediate row; anything
+ * else answers ESN_ERR_UNSUPPORTED and the host runs two esn_conv2d_umma calls.
+ * w1 / w2: bf16 [tap][C][C] (tap-major, Cin contiguous), as for esn_conv2d_umma. */
+typedef struct EsnConvPair {
+  EsnTensor x, y;
+  const void* w1;
+  const void* w2;
+  int32_t taps, dilation;
+  EsnEpilogue ep1;     /* scale/shift + none|ReLU; no residual */
+  EsnEpilogue ep2;     /* scale/shift, optional residual, none|ReLU|PReLU */
+} EsnConvPair;
+int esn_conv_pair_umma(const EsnConvPair* p, void* stream);
+
 /* Network stem on the caller's NCHW fp32 image (Cin = 3): Conv2d(3, cconv, 3, stride 2, pad 1)
  * [ || MaxPool2d(2,2) -> concat ] -> per-channel affine (bias + eval BN) -> activation -> NHWC.
  * Replaces ERFNet.py:24-27 for DownsamplerBlock(3,16) (cconv 13 + 3 pooled channels) and

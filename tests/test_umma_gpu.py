@@ -106,3 +106,62 @@ def test_umma_large_persistent_grid():
     assert err < 1.5e-2, err
     err, _, _ = run_case(("big_1x3_128", 128, 128, (1, 3), 1, (0, 2), (1, 2), False, 0, 4, 128, 256), True)
     assert err < 1.5e-2, err
+
+
+PAIR_CASES = [
+    # C, dilation, N, H, W, residual, act2
+    (64, 1, 2, 9, 128, True, "relu"),
+    (64, 1, 2, 40, 512, True, "relu"),
+    (64, 1, 1, 300, 256, False, "relu"),      # more rows than CTAs: several rows per CTA, TR = 2
+    (64, 2, 2, 17, 384, True, "prelu"),
+    (64, 8, 1, 33, 256, True, "none"),
+    (16, 1, 2, 11, 512, True, "relu"),
+    (16, 1, 1, 200, 1024, False, "relu"),
+    (16, 3, 1, 21, 1536, True, "relu"),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
+def test_fused_pair_equals_two_convs(case):
+    """esn_conv_pair_umma (intermediate row in shared memory) must reproduce the two-kernel path bit for bit:
+    same operands, same accumulation order, same bf16 rounding of the intermediate."""
+    from esn import ops
+    from esn._lib import ACT_NONE, ACT_RELU, ACT_PRELU
+    C_, d, N, H, W, with_res, act2 = case
+    torch.manual_seed(3)
+    m1 = nn.Conv2d(C_, C_, (3, 1), padding=(d, 0), dilation=(d, 1)).cuda()
+    m2 = nn.Conv2d(C_, C_, (1, 3), padding=(0, d), dilation=(1, d)).cuda()
+    scale = torch.rand(C_, device="cuda") + 0.5
+    shift = torch.randn(C_, device="cuda") * 0.1
+    alpha = torch.rand(C_, device="cuda") * 0.4
+    act = {"relu": ACT_RELU, "prelu": ACT_PRELU, "none": ACT_NONE}[act2]
+    p1 = ops.ConvPrep(m1, act=ACT_RELU)
+    p2 = ops.ConvPrep(m2, scale, shift, act, alpha if act == ACT_PRELU else None)
+    x = ops.new_act(N, C_, H, W, torch.bfloat16, "cuda")
+    x.copy_(torch.randn(N, C_, H, W, device="cuda"))
+    res = None
+    if with_res:
+        res = ops.new_act(N, C_, H, W, torch.bfloat16, "cuda")
+        res.copy_(torch.randn(N, C_, H, W, device="cuda"))
+    ref = ops.conv2d(ops.conv2d(x, p1), p2, residual=res)
+    out = ops.new_act(N, C_, H, W, torch.bfloat16, "cuda")
+    assert ops.pair_supported(x, p1, p2, out, res)
+    ops.launch_count_reset()
+    y = ops.conv_pair(x, p1, p2, out=out, residual=res)
+    torch.cuda.synchronize()
+    assert ops.launch_count() == 1
+    assert torch.equal(y, ref), (y.float() - ref.float()).abs().max().item()
+    # and against torch fp32 on the same bf16 operands (bf16-rounded intermediate)
+    with torch.no_grad():
+        w1, w2 = m1.weight.to(torch.bfloat16).float(), m2.weight.to(torch.bfloat16).float()
+        t = torch.relu(torch.nn.functional.conv2d(x.float(), w1, m1.bias, 1, (d, 0), (d, 1))).to(torch.bfloat16).float()
+        t = torch.nn.functional.conv2d(t, w2, None, 1, (0, d), (1, d))
+        t = (t + m2.bias.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        if with_res:
+            t = t + res.float()
+        if act == ACT_RELU:
+            t = torch.relu(t)
+        elif act == ACT_PRELU:
+            t = torch.where(t >= 0, t, t * alpha.view(1, -1, 1, 1))
+    err = (y.float() - t).abs().max() / t.abs().max()
+    assert err < 1.5e-2, err
