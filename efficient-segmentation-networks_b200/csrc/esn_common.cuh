@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <atomic>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "esn.h"
 
 extern std::atomic<long long> g_esn_launches;
@@ -13,7 +16,9 @@ extern std::atomic<long long> g_esn_launches;
   do {                                                       \
     g_esn_launches.fetch_add(1, std::memory_order_relaxed);  \
     if (cudaPeekAtLastError() != cudaSuccess) {              \
-      cudaGetLastError();                                    \
+      const cudaError_t e_ = cudaGetLastError();             \
+      if (getenv("ESN_DEBUG"))                               \
+        fprintf(stderr, "esn: %s:%d: %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); \
       return ESN_ERR_CUDA;                                   \
     }                                                        \
   } while (0)

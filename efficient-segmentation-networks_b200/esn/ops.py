@@ -285,6 +285,18 @@ class ConvPrep:
             self._w_umma = p.contiguous()
         return self._w_umma
 
+    @property
+    def w_umma_scaled(self):
+        """bf16 [tap][Cout_pad][Cin] with the epilogue scale folded into the output channels (the fused pair
+        kernel adds the residual inside the accumulator, so the scale cannot be applied afterwards)."""
+        if getattr(self, "_w_umma_s", None) is None:
+            w = self._w_src * self.scale.view(-1, 1, 1, 1)
+            taps = self.kh * self.kw
+            p = torch.zeros((taps, self.cout_pad, self.cin), dtype=torch.bfloat16, device=w.device)
+            p[:, :self.cout] = w.permute(2, 3, 0, 1).reshape(taps, self.cout, self.cin).to(torch.bfloat16)
+            self._w_umma_s = p.contiguous()
+        return self._w_umma_s
+
     def out_hw(self, h, w):
         if self.transposed:
             return ((h - 1) * self.stride - 2 * self.pad_h + self.dil_h * (self.kh - 1) + self.out_pad + 1,
@@ -393,10 +405,10 @@ def conv_pair(x, p1, p2, out=None, residual=None):
         out = new_act(n, c, h, w, x.dtype, x.device)
     p = L.EsnConvPair()
     p.x, p.y = tdesc(x), tdesc(out)
-    p.w1, p.w2 = p1.w_umma.data_ptr(), p2.w_umma.data_ptr()
+    p.w1, p.w2 = p1.w_umma.data_ptr(), p2.w_umma_scaled.data_ptr()
     p.taps, p.dilation = 3, p1.dil_h
     _epilogue(p.ep1, p1.scale, p1.shift, p1.alpha, p1.act, None)
-    _epilogue(p.ep2, p2.scale, p2.shift, p2.alpha, p2.act, residual)
+    _epilogue(p.ep2, None, p2.shift, p2.alpha, p2.act, residual)      # scale2 lives in w2
     alg = _nbytes(x) + _nbytes(out) + _nbytes(residual)
     flops = 2 * 2 * n * h * w * c * c * 3
     _call(L.lib.esn_conv_pair_umma, "esn_conv_pair_umma", (C.byref(p),), alg, flops, "3x1+1x3 c%d d%d" % (c, p1.dil_h))

@@ -123,8 +123,7 @@ PAIR_CASES = [
 
 @pytest.mark.parametrize("case", PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
 def test_fused_pair_equals_two_convs(case):
-    """esn_conv_pair_umma (intermediate row in shared memory) must reproduce the two-kernel path bit for bit:
-    same operands, same accumulation order, same bf16 rounding of the intermediate."""
+    """esn_conv_pair_umma (intermediate row in shared memory) against the two-kernel path and torch fp32."""
     from esn import ops
     from esn._lib import ACT_NONE, ACT_RELU, ACT_PRELU
     C_, d, N, H, W, with_res, act2 = case
@@ -150,7 +149,9 @@ def test_fused_pair_equals_two_convs(case):
     y = ops.conv_pair(x, p1, p2, out=out, residual=res)
     torch.cuda.synchronize()
     assert ops.launch_count() == 1
-    assert torch.equal(y, ref), (y.float() - ref.float()).abs().max().item()
+    # same operands and accumulation order as the two-kernel path, except that the BN scale is folded into the
+    # bf16 weights of the second conv (the residual is added inside the accumulator by an identity MMA)
+    assert ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item() < 1.5e-2
     # and against torch fp32 on the same bf16 operands (bf16-rounded intermediate)
     with torch.no_grad():
         w1, w2 = m1.weight.to(torch.bfloat16).float(), m2.weight.to(torch.bfloat16).float()
