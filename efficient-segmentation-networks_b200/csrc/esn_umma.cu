@@ -285,7 +285,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             for (int t = 0; t < ntaps; ++t) {
               if (i == 0 || t == ntaps - 1) {
                 mbar_wait(full0 + 8u * st, pt);
-                tc_fence_after();
               }
               const uint32_t al = a_lo0 + (uint32_t)st * stage16, bl = w_lo + (uint32_t)t * wblk16;
               for (int m = 0; m < MT; ++m) {
@@ -309,7 +308,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             const uint32_t shift16 = ((uint32_t)a.hs_d * RB) >> 4;   // tap spacing in descriptor units
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(full0 + 8u * s, ph);
-              tc_fence_after();
               uint32_t al = a_lo0 + (uint32_t)s * stage16;
               uint32_t bl = w_lo + (uint32_t)kb * wblk16;
               for (int t = 0; t < ntaps; ++t, al += shift16, bl += (uint32_t)nkb * wblk16) {
@@ -329,7 +327,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             uint32_t bl = w_lo;
             for (int ki = 0; ki < kiters; ++ki, bl += wblk16) {
               mbar_wait(full0 + 8u * s, ph);
-              tc_fence_after();
               const uint32_t al = a_lo0 + (uint32_t)s * stage16;
               for (int m = 0; m < MT; ++m) {
 #pragma unroll

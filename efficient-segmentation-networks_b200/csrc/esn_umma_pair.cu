@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
           uint32_t al1 = 0;
           if (has1) {
             TWAIT(3, mbar_wait(full0 + 8u * s, ph));
-            tc_fence_after();
             al1 = a_lo0 + (uint32_t)s * stage16;
           }
           const uint32_t bl1 = w1_lo + (uint32_t)t * wblk16, bl2 = w2_lo + (uint32_t)t * wblk16;
@@ -290,7 +289,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
         if (has2 && a.has_res) {
           // + residual: D += R . I, R = the residual tile in the next ring slot
           TWAIT(3, mbar_wait(full0 + 8u * s, ph));
-          tc_fence_after();
           const uint32_t alr = a_lo0 + (uint32_t)s * stage16;
           for (int m = 0; m < MT; ++m) {
 #pragma unroll
