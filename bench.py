@@ -379,7 +379,7 @@ def main():
         # DRAM traffic of the same kernel family from the committed ncu launch list (separate run)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % model_name.lower())
-        fam_names = {"esn_conv2d_umma": "conv_umma_kernel", "esn_conv2d_direct": "conv_direct_kernel",
+        fam_names = {"esn_conv2d_umma": "conv_umma_kernel", "esn_conv_pair_umma": "conv_pair_kernel", "esn_conv2d_direct": "conv_direct_kernel",
                      "esn_dab_dw_pair": "dab_dw_pair_kernel", "esn_affine_act": "pw_kernel"}
         if os.path.exists(tpath) and top[0] in fam_names:
             tj = json.load(open(tpath))
