@@ -1,0 +1,171 @@
+// Backward kernels of the resize / pooling / dropout ops of the pointwise-heavy nets (Fast-SCNN, ESPNetv2):
+// gather-form (deterministic, no atomics), NHWC, one thread per (pixel, channel) of the gradient it produces.
+// All are HBM-bound and small (they run at 1/8 ... 1/32 resolution, or on the 19-class logits).
+#include "esn_common.cuh"
+
+namespace {
+
+// ---- bilinear backward, align_corners = False / True, upstream gradient in NCHW (logits) or NHWC
+template <typename TG, typename TO>
+__global__ void __launch_bounds__(128) bilinear_bwd2_kernel(const TG* __restrict__ dy, TO* __restrict__ dx, int N, int C, int Hi,
+                                                            int Wi, int Ho, int Wo, int dy_nchw, int dy_cs, int dx_cs, float sh,
+                                                            float sw, int align, int accumulate) {
+  const long long total = (long long)N * Hi * Wi * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int w = (int)((idx / C) % Wi);
+  const int h = (int)((idx / ((long long)C * Wi)) % Hi);
+  const int n = (int)(idx / ((long long)C * Wi * Hi));
+  // candidate outputs: source index within (h-1, h+1)
+  const float rh = sh > 0.f ? 1.f / sh : 0.f, rw = sw > 0.f ? 1.f / sw : 0.f;
+  const float off = align ? 0.f : 0.5f;
+  int ho0 = sh > 0.f ? (int)floorf(((float)h - 1.f + off) * rh - off) - 1 : 0;
+  int ho1 = sh > 0.f ? (int)ceilf(((float)h + 1.f + off) * rh - off) + 1 : Ho - 1;
+  int wo0 = sw > 0.f ? (int)floorf(((float)w - 1.f + off) * rw - off) - 1 : 0;
+  int wo1 = sw > 0.f ? (int)ceilf(((float)w + 1.f + off) * rw - off) + 1 : Wo - 1;
+  ho0 = max(ho0, 0); ho1 = min(ho1, Ho - 1);
+  wo0 = max(wo0, 0); wo1 = min(wo1, Wo - 1);
+  float acc = 0.f;
+  for (int ho = ho0; ho <= ho1; ++ho) {
+    float fh = align ? sh * ho : sh * (ho + 0.5f) - 0.5f;
+    fh = fh < 0.f ? 0.f : fh;
+    const int h0 = min((int)fh, Hi - 1);
+    const int h1 = h0 + ((h0 < Hi - 1) ? 1 : 0);
+    const float l1 = fh - h0, l0 = 1.f - l1;
+    const float wh = (h0 == h ? l0 : 0.f) + (h1 == h ? l1 : 0.f);
+    if (wh == 0.f) continue;
+    float rowacc = 0.f;
+    for (int wo = wo0; wo <= wo1; ++wo) {
+      float fw = align ? sw * wo : sw * (wo + 0.5f) - 0.5f;
+      fw = fw < 0.f ? 0.f : fw;
+      const int w0 = min((int)fw, Wi - 1);
+      const int w1 = w0 + ((w0 < Wi - 1) ? 1 : 0);
+      const float m1 = fw - w0, m0 = 1.f - m1;
+      const float ww = (w0 == w ? m0 : 0.f) + (w1 == w ? m1 : 0.f);
+      if (ww != 0.f) {
+        const size_t gi = dy_nchw ? (((size_t)n * C + c) * Ho + ho) * Wo + wo : (((size_t)n * Ho + ho) * Wo + wo) * dy_cs + c;
+        rowacc += ww * ld1<TG>(dy + gi);
+      }
+    }
+    acc += wh * rowacc;
+  }
+  TO* p = dx + ((size_t)((size_t)n * Hi + h) * Wi + w) * dx_cs + c;
+  if (accumulate) acc += ld1<TO>(p);
+  st1<TO>(p, acc);
+}
+
+// ---- adaptive average pool backward: dx[h,w] = sum over windows containing (h,w) of dy / |window|
+template <typename T>
+__global__ void __launch_bounds__(128) adaptive_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int C, int H,
+                                                                   int W, int S, int dy_cs, int dx_cs, int accumulate) {
+  const long long total = (long long)N * H * W * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int w = (int)((idx / C) % W);
+  const int h = (int)((idx / ((long long)C * W)) % H);
+  const int n = (int)(idx / ((long long)C * W * H));
+  float acc = 0.f;
+  for (int i = 0; i < S; ++i) {
+    const int hs = (i * H) / S, he = ((i + 1) * H + S - 1) / S;
+    if (h < hs || h >= he) continue;
+    for (int j = 0; j < S; ++j) {
+      const int ws = (j * W) / S, we = ((j + 1) * W + S - 1) / S;
+      if (w < ws || w >= we) continue;
+      acc += ld1<T>(dy + (((size_t)n * S + i) * S + j) * dy_cs + c) / (float)((he - hs) * (we - ws));
+    }
+  }
+  T* p = dx + ((size_t)((size_t)n * H + h) * W + w) * dx_cs + c;
+  if (accumulate) acc += ld1<T>(p);
+  st1<T>(p, acc);
+}
+
+// ---- dropout (element-wise nn.Dropout or per-(n, c) nn.Dropout2d): counter-based hash, so the backward
+// pass regenerates the mask from the seed instead of storing it
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int C, int H, int W, int x_cs,
+                                                      int y_cs, uint64_t seed, uint32_t thresh, float scale, int per_channel) {
+  const long long total = (long long)N * H * W * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long pix = idx / C;
+  const int n = (int)(pix / ((long long)H * W));
+  const uint64_t key = per_channel ? ((uint64_t)n * C + c) : (uint64_t)idx;
+  const bool keep = mix32(seed + 0x9e3779b97f4a7c15ULL * (key + 1)) >= thresh;
+  st1<T>(y + (size_t)pix * y_cs + c, keep ? ld1<T>(x + (size_t)pix * x_cs + c) * scale : 0.f);
+}
+
+}  // namespace
+
+extern "C" int esn_bilinear_bwd_nhwc(const EsnTensor* dy, const EsnTensor* dx, int32_t align_corners, int32_t accumulate,
+                                     void* stream) {
+  if (!dy || !dx || !dy->ptr || !esn_valid_nhwc(*dx)) return ESN_ERR_BAD_ARG;
+  const bool nchw = dy->layout == ESN_NCHW;
+  if (!nchw && !esn_valid_nhwc(*dy)) return ESN_ERR_BAD_ARG;
+  if (dy->n != dx->n || dy->c != dx->c) return ESN_ERR_BAD_SHAPE;
+  float sh, sw;
+  if (align_corners) {
+    sh = dy->h > 1 ? (float)(dx->h - 1) / (float)(dy->h - 1) : 0.f;
+    sw = dy->w > 1 ? (float)(dx->w - 1) / (float)(dy->w - 1) : 0.f;
+  } else {
+    sh = (float)dx->h / (float)dy->h;
+    sw = (float)dx->w / (float)dy->w;
+  }
+  const long long total = (long long)dx->n * dx->h * dx->w * dx->c;
+  const int grid = esn_cdiv(total, 128);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool gf = dy->dtype == ESN_F32, of = dx->dtype == ESN_F32;
+#define ESN_BB2(TG, TO)                                                                                                  \
+  bilinear_bwd2_kernel<TG, TO><<<grid, 128, 0, st>>>((const TG*)dy->ptr, (TO*)dx->ptr, dx->n, dx->c, dx->h, dx->w, dy->h, \
+                                                     dy->w, nchw ? 1 : 0, dy->c_stride, dx->c_stride, sh, sw,             \
+                                                     align_corners ? 1 : 0, accumulate)
+  if (gf && of) ESN_BB2(float, float);
+  else if (gf) ESN_BB2(float, __nv_bfloat16);
+  else if (of) ESN_BB2(__nv_bfloat16, float);
+  else ESN_BB2(__nv_bfloat16, __nv_bfloat16);
+#undef ESN_BB2
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_adaptive_avgpool_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream) {
+  if (!dy || !dx || !esn_valid_nhwc(*dy) || !esn_valid_nhwc(*dx)) return ESN_ERR_BAD_ARG;
+  if (dy->n != dx->n || dy->c != dx->c || dy->h != dy->w || dy->dtype != dx->dtype) return ESN_ERR_BAD_SHAPE;
+  const long long total = (long long)dx->n * dx->h * dx->w * dx->c;
+  const int grid = esn_cdiv(total, 128);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dx->dtype == ESN_F32)
+    adaptive_avgpool_bwd_kernel<float><<<grid, 128, 0, st>>>((const float*)dy->ptr, (float*)dx->ptr, dx->n, dx->c, dx->h, dx->w,
+                                                             dy->h, dy->c_stride, dx->c_stride, accumulate);
+  else
+    adaptive_avgpool_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy->ptr, (__nv_bfloat16*)dx->ptr, dx->n,
+                                                                     dx->c, dx->h, dx->w, dy->h, dy->c_stride, dx->c_stride,
+                                                                     accumulate);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, int32_t per_channel, void* stream) {
+  if (!x || !y || !esn_valid_nhwc(*x) || !esn_valid_nhwc(*y)) return ESN_ERR_BAD_ARG;
+  if (x->n != y->n || x->c != y->c || x->h != y->h || x->w != y->w || x->dtype != y->dtype) return ESN_ERR_BAD_SHAPE;
+  if (!(p >= 0.f) || p >= 1.f) return ESN_ERR_BAD_ARG;
+  const long long total = (long long)x->n * x->h * x->w * x->c;
+  const int grid = esn_cdiv(total, 256);
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  const float scale = 1.f / (1.f - p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x->dtype == ESN_F32)
+    dropout_kernel<float><<<grid, 256, 0, st>>>((const float*)x->ptr, (float*)y->ptr, x->n, x->c, x->h, x->w, x->c_stride,
+                                                y->c_stride, seed, thresh, scale, per_channel);
+  else
+    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, (__nv_bfloat16*)y->ptr, x->n, x->c, x->h, x->w,
+                                                        x->c_stride, y->c_stride, seed, thresh, scale, per_channel);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}

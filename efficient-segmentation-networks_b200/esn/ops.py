@@ -165,8 +165,8 @@ class ConvPrep:
 
     def _init(self, w, bias, stride, padding, dilation, groups, transposed, out_pad, scale, shift, act, alpha, device,
               cin_pad, cout_pad):
-        if transposed:          # (Cin, Cout, kh, kw) -> (Cout, Cin, kh, kw)
-            w = w.permute(1, 0, 2, 3).contiguous()
+        if transposed and not (groups > 1 and groups == w.shape[0] and w.shape[1] == 1):
+            w = w.permute(1, 0, 2, 3).contiguous()          # (Cin, Cout, kh, kw) -> (Cout, Cin, kh, kw); depthwise: (C, 1, kh, kw) as is
         if cin_pad is not None and cin_pad > w.shape[1]:
             assert groups == 1
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))

@@ -116,9 +116,9 @@ class ConvT:
                 self.dgrad_prep = ops.ConvPrep.from_weight(wf.contiguous(), 1,
                                                            (dil[0] * (kh - 1) - pad[0], dil[1] * (kw - 1) - pad[1]), dil, g)
             else:   # conv_transpose2d(dy, W): W (Cout, Cin, kh, kw) read as (in=Cout, out=Cin)
-                if g != 1:
-                    raise NotImplementedError("strided depthwise conv backward")
-                self.dgrad_prep = ops.ConvPrep.from_weight(wd, s, pad, dil, 1, transposed=True)
+                if g != 1 and not (g == wd.shape[0] and wd.shape[1] == 1):
+                    raise NotImplementedError("strided grouped conv backward")
+                self.dgrad_prep = ops.ConvPrep.from_weight(wd, s, pad, dil, g, transposed=True)
             self._key = key
         return self.fwd_prep, self.dgrad_prep
 
@@ -303,10 +303,10 @@ def maxpool2x2(tape, x, out):
     return y
 
 
-def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32):
-    """F.interpolate(scores, (H, W), bilinear, align_corners=False) -> NCHW logits; backward gathers."""
+def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32, align_corners=False):
+    """F.interpolate(scores, (H, W), bilinear, align_corners) -> NCHW logits; backward gathers."""
     classes = scores.t.shape[1]
-    logits, _ = ops.head_bilinear(scores.t, classes, out_h, out_w, True, False, logits_dtype)
+    logits, _ = ops.head_bilinear(scores.t, classes, out_h, out_w, True, False, logits_dtype, align_corners=align_corners)
     holder = {}
 
     def bwd():
@@ -318,12 +318,109 @@ def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32):
             dlow = ops.new_act(n, c, h, w, scores.t.dtype, dl.device, c_alloc=scores.t.stride(3))
             a, b = ops.tdesc(dl), ops.tdesc(dlow)
             a.layout, a.c_stride = L.ESN_NCHW, 0
-            ops._call(L.lib.esn_bilinear_bwd, "esn_bilinear_bwd", (C.byref(a), C.byref(b), C.c_float(1.0)),
-                      dl.numel() * dl.element_size())
+            if align_corners:
+                ops._call(L.lib.esn_bilinear_bwd_nhwc, "esn_bilinear_bwd_nhwc", (C.byref(a), C.byref(b), 1, 0),
+                          dl.numel() * dl.element_size())
+            else:
+                ops._call(L.lib.esn_bilinear_bwd, "esn_bilinear_bwd", (C.byref(a), C.byref(b), C.c_float(1.0)),
+                          dl.numel() * dl.element_size())
             return dlow
         scores.add_grad(run)
     tape.push(bwd)
     return logits, holder
+
+
+def _accumulating(fn_into):
+    """add_grad adapter for kernels with an `accumulate` flag: fn_into(dx, accumulate) fills / adds into dx."""
+    def run(ex, dst, alloc):
+        if dst is not None:           # slice of a concat gradient buffer (zero-filled at creation): add in place
+            fn_into(dst, 1)
+            return dst
+        if ex is not None:
+            fn_into(ex, 1)
+            return ex
+        dx = alloc()
+        fn_into(dx, 0)
+        return dx
+    return run
+
+
+def bilinear(tape, x, out_h, out_w, align_corners, out=None):
+    """F.interpolate(x, (out_h, out_w), bilinear, align_corners) on NHWC activations (optionally into a concat slice)."""
+    y = out if isinstance(out, V) else V(ops.bilinear(x.t, out_h, out_w, align_corners, out=out))
+    if isinstance(out, V):
+        ops.bilinear(x.t, out_h, out_w, align_corners, out=out.t)
+    n, c, h, w = x.t.shape
+
+    def bwd():
+        dy = y.g
+
+        def into(dx, acc):
+            a, b = ops.tdesc(dy), ops.tdesc(dx)
+            ops._call(L.lib.esn_bilinear_bwd_nhwc, "esn_bilinear_bwd_nhwc", (C.byref(a), C.byref(b), int(bool(align_corners)), acc),
+                      ops._nbytes(dy) + ops._nbytes(dx))
+        run = _accumulating(into)
+        x.add_grad(lambda ex, dst: run(ex, dst, lambda: ops.new_act(n, c, h, w, dy.dtype, dy.device)))
+    tape.push(bwd)
+    return y
+
+
+def adaptive_avgpool(tape, x, size):
+    """F.adaptive_avg_pool2d(x, size)."""
+    y = V(ops.adaptive_avgpool(x.t, size))
+    n, c, h, w = x.t.shape
+
+    def bwd():
+        dy = y.g
+
+        def into(dx, acc):
+            a, b = ops.tdesc(dy), ops.tdesc(dx)
+            ops._call(L.lib.esn_adaptive_avgpool_bwd, "esn_adaptive_avgpool_bwd", (C.byref(a), C.byref(b), acc),
+                      ops._nbytes(dy) + ops._nbytes(dx))
+        run = _accumulating(into)
+        x.add_grad(lambda ex, dst: run(ex, dst, lambda: ops.new_act(n, c, h, w, dy.dtype, dy.device)))
+    tape.push(bwd)
+    return y
+
+
+def copy_into(tape, x, out):
+    """out (a channel slice of a concat buffer) = x; the slice's gradient flows back to x."""
+    ops.affine_act(x.t, None, None, None, L.ACT_NONE, out=out.t)
+
+    def bwd():
+        dy = out.g
+        x.add_grad(lambda ex, dst: ops.affine_act(dy, None, None, None, L.ACT_NONE, out=dst, residual=ex)
+                   if (ex is not None or dst is not None) else ops.affine_act(dy, None, None, None, L.ACT_NONE))
+    tape.push(bwd)
+    return out
+
+
+_DROPOUT_CALLS = [0]
+
+
+def dropout(tape, x, p, per_channel=False, training=True):
+    """nn.Dropout (element-wise) / nn.Dropout2d (per (n, c) plane): keep mask regenerated from the seed in backward.
+    The seed is drawn from torch's CPU generator, so torch.manual_seed makes runs repeatable."""
+    if not training or p <= 0.0:
+        return x
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) + _DROPOUT_CALLS[0]
+    _DROPOUT_CALLS[0] += 1
+    n, c, h, w = x.t.shape
+
+    def apply(src):
+        dst = ops.new_act(n, c, h, w, src.dtype, src.device)
+        a, b = ops.tdesc(src), ops.tdesc(dst)
+        ops._call(L.lib.esn_dropout, "esn_dropout", (C.byref(a), C.byref(b), C.c_uint64(seed), C.c_float(p), int(per_channel)),
+                  ops._nbytes(src) + ops._nbytes(dst))
+        return dst
+    y = V(apply(x.t))
+
+    def bwd():
+        g = apply(y.g)
+        x.add_grad(lambda ex, dst: g if (ex is None and dst is None) else
+                   ops.affine_act(g, None, None, None, L.ACT_NONE, out=dst, residual=ex))
+    tape.push(bwd)
+    return y
 
 
 # --------------------------------------------------------------------------- autograd glue

@@ -292,6 +292,13 @@ class FastSCNN(nn.Module):
         return self.classifier(y), x.shape[2:]
 
     def forward(self, x):
+        if self.training:
+            # batch-statistics BatchNorm + Dropout + recorded backward (esn/train.py); one autograd node for the net
+            from esn import train as T
+            from model._fastscnn_train import fastscnn_train_forward
+            if self.aux:
+                raise NotImplementedError("FastSCNN(aux=True): the auxiliary head is never used by the reference's forward")
+            return T.run_network(self, lambda inp: fastscnn_train_forward(self, inp), x)
         scores, (h, w) = self._scores(x)
         ldt = torch.bfloat16 if scores.dtype == torch.bfloat16 else torch.float32
         return ops.head_bilinear(scores, scores.shape[1], h, w, True, False, ldt, align_corners=True)[0]

@@ -324,6 +324,14 @@ int esn_conv2d_wgrad(const EsnConv* p, void* stream);
 int esn_maxpool2x2_bwd(const EsnTensor* x, const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);
 int esn_bilinear_bwd(const EsnTensor* dlogits, const EsnTensor* dlow, float gscale, void* stream);
 
+/* Backward of F.interpolate(bilinear, align_corners 0/1) with the upstream gradient in NCHW (logits) or
+ * NHWC, of F.adaptive_avg_pool2d (FastSCNN.py:96-105: dy is (N,C,S,S)), and nn.Dropout / nn.Dropout2d
+ * (forward and backward are the same call: the keep mask is a counter-based hash of (seed, element) or
+ * (seed, n, c), scaled by 1/(1-p); FastSCNN.py:193, SegmentationModel.py:50-53).  `accumulate` adds to dx. */
+int esn_bilinear_bwd_nhwc(const EsnTensor* dy, const EsnTensor* dx, int32_t align_corners, int32_t accumulate, void* stream);
+int esn_adaptive_avgpool_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);
+int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, int32_t per_channel, void* stream);
+
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);
 const char* esn_strerror(int code);

@@ -71,6 +71,11 @@ WG_CASES = [
     (32, 32, (3, 1), 1, (4, 0), (4, 1), 32, 16, 20),
     (64, 64, (1, 3), 1, (0, 2), (1, 2), 64, 10, 24),
     (16, 16, (3, 1), 1, (1, 0), (1, 1), 1, 12, 20),
+    (32, 32, 3, 2, 1, 1, 32, 15, 31),       # Fast-SCNN strided depthwise (odd input from the pad-0 stem)
+    (48, 48, 3, 2, 1, 1, 48, 16, 32),
+    (384, 64, 1, 1, 0, 1, 1, 8, 16),        # linear-bottleneck projection / expansion
+    (96, 576, 1, 1, 0, 1, 1, 4, 8),
+    (128, 128, 3, 1, 1, 1, 128, 8, 16),
 ]
 
 
@@ -149,6 +154,9 @@ def _train_step(name, spec, dtype):
     m = build_model(name, 19)
     m.load_state_dict(spec_state_dict(spec, name))
     m = m.cuda().train()
+    for mod in m.modules():           # the golden gradients were produced with dropout off
+        if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
+            mod.p = 0.0
     x = fixture.make_input(2, 64, 128).cuda()
     lab = fixture.make_labels(2, 64, 128, 19).cuda()
     crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
@@ -164,15 +172,32 @@ def _train_step(name, spec, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_dabnet_training_matches_reference_fp64(spec, golden, dtype):
-    """loss / logits / every parameter gradient against the reference's fp64 run (tests/golden)."""
-    g = golden("DABNet")
-    m, out, loss = _train_step("DABNet", spec, dtype)
+@pytest.mark.parametrize("net", ["DABNet", "FastSCNN"])
+def test_training_matches_reference_fp64(spec, golden, dtype, net):
+    """loss / logits / every parameter gradient against the reference's fp64 run (tests/golden; dropout off)."""
+    g = golden(net)
+    m, out, loss = _train_step(net, spec, dtype)
     ref_loss = float(g["train_2x64x128_loss"][0])
     ltol, gtol = (1e-4, 2e-2) if dtype == torch.float32 else (2e-2, 1e-1)   # SURVEY H8: fp32-vs-fp64 noise is ~1e-2 per tensor
-    assert abs(loss.item() - ref_loss) / ref_loss < ltol, (loss.item(), ref_loss)
     ref = torch.from_numpy(g["train_2x64x128_logits_s4"])
-    assert _rel(out.detach().float().cpu()[:, :, ::4, ::4], ref) < (1e-4 if dtype == torch.float32 else 5e-2)
+    logit_tol = 1e-4 if dtype == torch.float32 else 5e-2
+    if dtype == torch.bfloat16:
+        # bf16 noise floor of THIS graph: the reference arithmetic (oracle port) under torch bf16 autocast.  Batch-
+        # statistics BatchNorm over a handful of values (Fast-SCNN's 1x1 ... 6x6 pyramid levels at batch 2)
+        # amplifies rounding noise far beyond 5e-2, for torch exactly as for us.
+        from oracle import nets
+        sd0 = {k: v.cuda() for k, v in spec_state_dict(spec, net).items()}
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            y_ac = nets.forward(net, sd0, fixture.make_input(2, 64, 128).cuda(), train=True)
+            l_ac = F.cross_entropy(y_ac.float(), fixture.make_labels(2, 64, 128, 19).cuda(),
+                                   torch.tensor(fixture.CLASS_WEIGHTS, device="cuda"), ignore_index=255)
+        r_log = _rel(y_ac.float().cpu()[:, :, ::4, ::4], ref)
+        r_loss = abs(l_ac.item() - ref_loss) / ref_loss
+        print("   torch bf16-autocast of the same graph: logits rel-L2 %.3e, loss error %.3e" % (r_log, r_loss))
+        logit_tol = max(logit_tol, 1.5 * r_log)
+        ltol = max(ltol, 1.5 * r_loss)
+    assert abs(loss.item() - ref_loss) / ref_loss < ltol, (loss.item(), ref_loss)
+    assert _rel(out.detach().float().cpu()[:, :, ::4, ::4], ref) < logit_tol
     stats = json.loads(bytes(g["train_2x64x128_gradstats"]).decode())
     named = dict(m.named_parameters())
     errs = []
@@ -183,8 +208,8 @@ def test_dabnet_training_matches_reference_fp64(spec, golden, dtype):
         errs.append(abs(named[k].grad.double().norm().item() - gnorm) / gnorm)
     errs.sort()
     worst, p90, med = errs[-1], errs[int(0.9 * len(errs))], errs[len(errs) // 2]
-    print("DABNet %s: loss %.6f (ref %.6f); per-tensor grad-norm error vs fp64: median %.3e p90 %.3e worst %.3e (%d tensors)"
-          % (dtype, loss.item(), ref_loss, med, p90, worst, len(errs)))
+    print("%s %s: loss %.6f (ref %.6f); per-tensor grad-norm error vs fp64: median %.3e p90 %.3e worst %.3e (%d tensors)"
+          % (net, dtype, loss.item(), ref_loss, med, p90, worst, len(errs)))
     if dtype == torch.float32:
         assert worst < gtol, worst
         for key in g.files:
@@ -198,11 +223,11 @@ def test_dabnet_training_matches_reference_fp64(spec, golden, dtype):
     # under torch bf16 autocast on the same fixture and require our error distribution to be no worse.
     from oracle import nets
     sd = {k: (v.cuda().requires_grad_(True) if v.is_floating_point() else v.cuda())
-          for k, v in spec_state_dict(spec, "DABNet").items()}
+          for k, v in spec_state_dict(spec, net).items()}
     x = fixture.make_input(2, 64, 128).cuda()
     lab = fixture.make_labels(2, 64, 128, 19).cuda()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        y = nets.forward("DABNet", sd, x, train=True)
+        y = nets.forward(net, sd, x, train=True)
         l = F.cross_entropy(y.float(), lab, torch.tensor(fixture.CLASS_WEIGHTS, device="cuda"), ignore_index=255)
     l.backward()
     ref_errs = sorted(abs(sd[k].grad.double().norm().item() - gn) / gn
@@ -211,3 +236,50 @@ def test_dabnet_training_matches_reference_fp64(spec, golden, dtype):
     print("   torch bf16-autocast on the same graph: median %.3e p90 %.3e worst %.3e" % (r_med, r_p90, ref_errs[-1]))
     assert med < 1.5 * r_med + 1e-3, (med, r_med)
     assert p90 < 1.5 * r_p90 + 1e-3, (p90, r_p90)
+
+
+def test_resize_pool_dropout_backward():
+    """Fast-SCNN's extra ops: bilinear (align_corners 0/1, NHWC), adaptive average pool, dropout, strided depthwise conv."""
+    from esn import ops, train as T
+    torch.manual_seed(5)
+    for align, (hi, wi, ho, wo) in ((True, (4, 8, 16, 32)), (False, (5, 7, 13, 20)), (True, (1, 1, 4, 8)), (True, (6, 6, 4, 8))):
+        x = torch.randn(2, 24, hi, wi, device="cuda").requires_grad_(True)
+        ref = F.interpolate(x, (ho, wo), mode="bilinear", align_corners=align)
+        gy = torch.randn_like(ref)
+        gx, = torch.autograd.grad(ref, x, gy)
+        tape = T.Tape()
+        xv = T.V(_nhwc(x.detach(), torch.float32, ops))
+        y = T.bilinear(tape, xv, ho, wo, align)
+        assert torch.allclose(y.t, ref.detach(), atol=1e-5, rtol=1e-5)
+        y._g = _nhwc(gy, torch.float32, ops)
+        tape.backward()
+        assert _rel(xv.g, gx) < 1e-5, (align, hi, wi)
+    for size, (h, w) in ((1, (4, 8)), (2, (4, 8)), (3, (4, 8)), (6, (4, 8)), (3, (7, 10))):
+        x = torch.randn(2, 16, h, w, device="cuda").requires_grad_(True)
+        ref = F.adaptive_avg_pool2d(x, size)
+        gy = torch.randn_like(ref)
+        gx, = torch.autograd.grad(ref, x, gy)
+        tape = T.Tape()
+        xv = T.V(_nhwc(x.detach(), torch.float32, ops))
+        y = T.adaptive_avgpool(tape, xv, size)
+        assert torch.allclose(y.t, ref.detach(), atol=1e-5, rtol=1e-5)
+        y._g = _nhwc(gy, torch.float32, ops)
+        tape.backward()
+        assert _rel(xv.g, gx) < 1e-5, (size, h, w)
+    # dropout: ~p of the elements dropped, survivors scaled by 1/(1-p), backward uses the same mask
+    x = torch.randn(4, 32, 16, 16, device="cuda")
+    for per_channel in (False, True):
+        tape = T.Tape()
+        xv = T.V(_nhwc(x, torch.float32, ops))
+        y = T.dropout(tape, xv, 0.25, per_channel=per_channel)
+        kept = y.t != 0
+        frac = 1.0 - kept.float().mean().item()
+        assert abs(frac - 0.25) < (0.02 if not per_channel else 0.15), frac
+        assert torch.allclose(y.t[kept], x[kept] / 0.75, rtol=1e-6)
+        if per_channel:
+            planes = kept.float().mean(dim=(2, 3))
+            assert ((planes == 0) | (planes == 1)).all()
+        y._g = _nhwc(torch.ones_like(x), torch.float32, ops)
+        tape.backward()
+        assert torch.equal(xv.g != 0, kept)
+        assert torch.allclose(xv.g[kept], torch.full_like(xv.g[kept], 1 / 0.75))
