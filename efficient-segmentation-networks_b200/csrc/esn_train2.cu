@@ -81,6 +81,31 @@ __global__ void __launch_bounds__(128) adaptive_avgpool_bwd_kernel(const T* __re
   st1<T>(p, acc);
 }
 
+// ---- AvgPool2d(3, stride 2, pad 1, count_include_pad) backward: every window divides by 9
+template <typename T>
+__global__ void __launch_bounds__(128) avgpool3x3s2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int C, int H, int W,
+                                                               int Ho, int Wo, int dy_cs, int dx_cs, int accumulate) {
+  const long long total = (long long)N * H * W * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int w = (int)((idx / C) % W);
+  const int h = (int)((idx / ((long long)C * W)) % H);
+  const int n = (int)(idx / ((long long)C * W * H));
+  float acc = 0.f;
+  for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {          // windows [2ho-1, 2ho+1] containing h
+    if (ho >= Ho) continue;
+    for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+      if (wo >= Wo) continue;
+      acc += ld1<T>(dy + (((size_t)n * Ho + ho) * Wo + wo) * dy_cs + c);
+    }
+  }
+  acc *= (1.f / 9.f);
+  T* p = dx + ((size_t)((size_t)n * H + h) * W + w) * dx_cs + c;
+  if (accumulate) acc += ld1<T>(p);
+  st1<T>(p, acc);
+}
+
 // ---- dropout (element-wise nn.Dropout or per-(n, c) nn.Dropout2d): counter-based hash, so the backward
 // pass regenerates the mask from the seed instead of storing it
 __device__ __forceinline__ uint32_t mix32(uint64_t x) {
@@ -147,6 +172,23 @@ extern "C" int esn_adaptive_avgpool_bwd(const EsnTensor* dy, const EsnTensor* dx
     adaptive_avgpool_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy->ptr, (__nv_bfloat16*)dx->ptr, dx->n,
                                                                      dx->c, dx->h, dx->w, dy->h, dy->c_stride, dx->c_stride,
                                                                      accumulate);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_avgpool3x3s2_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream) {
+  if (!dy || !dx || !esn_valid_nhwc(*dy) || !esn_valid_nhwc(*dx)) return ESN_ERR_BAD_ARG;
+  if (dy->n != dx->n || dy->c != dx->c || dy->h != (dx->h - 1) / 2 + 1 || dy->w != (dx->w - 1) / 2 + 1 || dy->dtype != dx->dtype)
+    return ESN_ERR_BAD_SHAPE;
+  const long long total = (long long)dx->n * dx->h * dx->w * dx->c;
+  const int grid = esn_cdiv(total, 128);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dx->dtype == ESN_F32)
+    avgpool3x3s2_bwd_kernel<float><<<grid, 128, 0, st>>>((const float*)dy->ptr, (float*)dx->ptr, dx->n, dx->c, dx->h, dx->w, dy->h,
+                                                         dy->w, dy->c_stride, dx->c_stride, accumulate);
+  else
+    avgpool3x3s2_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)dy->ptr, (__nv_bfloat16*)dx->ptr, dx->n, dx->c,
+                                                                 dx->h, dx->w, dy->h, dy->w, dy->c_stride, dx->c_stride, accumulate);
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }

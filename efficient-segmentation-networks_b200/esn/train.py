@@ -270,9 +270,13 @@ class BNActT:
         return y
 
 
-def add(tape, a, b):
-    """y = a + b (branch merge)."""
-    y = V(ops.affine_act(a.t, None, None, None, L.ACT_NONE, residual=b.t))
+def add(tape, a, b, out=None):
+    """y = a + b (branch merge), optionally written into `out` (a V, e.g. a channel slice of a concat buffer)."""
+    if out is not None:
+        y = out
+        ops.affine_act(a.t, None, None, None, L.ACT_NONE, out=y.t, residual=b.t)
+    else:
+        y = V(ops.affine_act(a.t, None, None, None, L.ACT_NONE, residual=b.t))
 
     def bwd():
         dy = y.g
@@ -381,6 +385,81 @@ def adaptive_avgpool(tape, x, size):
         x.add_grad(lambda ex, dst: run(ex, dst, lambda: ops.new_act(n, c, h, w, dy.dtype, dy.device)))
     tape.push(bwd)
     return y
+
+
+def avgpool3x3s2(tape, x, out=None):
+    """AvgPool2d(3, stride 2, pad 1) (count_include_pad), optionally into a concat slice."""
+    n, c, h, w = x.t.shape
+    if out is None:
+        out = V(ops.new_act(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.t.dtype, x.t.device))
+    y = out
+    ops.avgpool3x3s2(x.t, y.t)
+
+    def bwd():
+        dy = y.g
+
+        def into(dx, acc):
+            a, b = ops.tdesc(dy), ops.tdesc(dx)
+            ops._call(L.lib.esn_avgpool3x3s2_bwd, "esn_avgpool3x3s2_bwd", (C.byref(a), C.byref(b), acc),
+                      ops._nbytes(dy) + ops._nbytes(dx))
+        run = _accumulating(into)
+        x.add_grad(lambda ex, dst: run(ex, dst, lambda: ops.new_act(n, c, h, w, dy.dtype, dy.device)))
+    tape.push(bwd)
+    return y
+
+
+class _SubConv:
+    """One group of a grouped nn.Conv2d, seen as a dense conv over channel slices (weight is a view)."""
+
+    def __init__(self, conv, g):
+        og, cg = conv.out_channels // conv.groups, conv.in_channels // conv.groups
+        self.weight = conv.weight.detach()[g * og:(g + 1) * og]
+        self.bias = None
+        self.stride, self.padding, self.dilation, self.groups = conv.stride, conv.padding, conv.dilation, 1
+        self.in_channels, self.out_channels = cg, og
+
+
+class _GradCollector:
+    """Stands in for the tape while the groups of a grouped conv run their backward."""
+
+    def __init__(self, tape):
+        self.tape, self.grads = tape, {}
+
+    def push(self, fn):
+        self.tape.push(fn)
+
+    def add_param_grad(self, p, g):
+        self.grads[id(p)] = g
+
+
+class GroupedConvT:
+    """nn.Conv2d with 1 < groups < channels (ESPNetv2's g=4 1x1 convs, cnn_utils.py:27-110): one dense ConvT per
+    group over channel slices of the input / output; the weight gradient is assembled once all groups are done."""
+
+    def __init__(self, conv):
+        assert conv.bias is None
+        self.conv = conv
+        self.subs = [_SubConv(conv, g) for g in range(conv.groups)]
+        self.convts = [ConvT(sc) for sc in self.subs]
+        self._ptr = conv.weight.data_ptr()
+
+    def forward(self, tape, x, out=None):
+        conv = self.conv
+        if conv.weight.data_ptr() != self._ptr:          # parameter storage replaced (.to(), load): rebuild the views
+            self.__init__(conv)
+        n, _, h, w = x.t.shape
+        if out is None:
+            ho, wo = self.convts[0].preps()[0].out_hw(h, w)
+            out = V(ops.new_act(n, conv.out_channels, ho, wo, x.t.dtype, x.t.device))
+        coll = _GradCollector(tape)
+        og, cg = conv.out_channels // conv.groups, conv.in_channels // conv.groups
+
+        def assemble():      # pushed first => runs after every group's backward
+            tape.add_param_grad(conv.weight, torch.cat([coll.grads[id(sc.weight)] for sc in self.subs], 0))
+        tape.push(assemble)
+        for g, ct in enumerate(self.convts):
+            ct.forward(coll, x.slice(g * cg, (g + 1) * cg), out=out.slice(g * og, (g + 1) * og))
+        return out
 
 
 def copy_into(tape, x, out):

@@ -116,6 +116,11 @@ class EESPNet_Seg(PrepMixin, nn.Module):
         return m1, (h, w)
 
     def forward(self, input):
+        if self.training:
+            # batch-statistics BatchNorm + Dropout2d + recorded backward (esn/train.py); one autograd node for the net
+            from esn import train as T
+            from model.ESPNet_v2._train import espnetv2_train_forward
+            return T.run_network(self, lambda inp: espnetv2_train_forward(self, inp), input)
         scores, (h, w) = self._scores(input)
         ldt = torch.bfloat16 if scores.dtype == torch.bfloat16 else torch.float32
         return ops.head_bilinear(scores, scores.shape[1], h, w, True, False, ldt, align_corners=True)[0]

@@ -330,6 +330,7 @@ int esn_bilinear_bwd(const EsnTensor* dlogits, const EsnTensor* dlow, float gsca
  * (seed, n, c), scaled by 1/(1-p); FastSCNN.py:193, SegmentationModel.py:50-53).  `accumulate` adds to dx. */
 int esn_bilinear_bwd_nhwc(const EsnTensor* dy, const EsnTensor* dx, int32_t align_corners, int32_t accumulate, void* stream);
 int esn_adaptive_avgpool_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);
+int esn_avgpool3x3s2_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);   /* AvgPool2d(3,2,1): /9 always */
 int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, int32_t per_channel, void* stream);
 
 /* Library / device queries (host-side, no stream). */

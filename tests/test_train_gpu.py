@@ -172,7 +172,7 @@ def _train_step(name, spec, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("net", ["DABNet", "FastSCNN"])
+@pytest.mark.parametrize("net", ["DABNet", "FastSCNN", "ESPNet_v2"])
 def test_training_matches_reference_fp64(spec, golden, dtype, net):
     """loss / logits / every parameter gradient against the reference's fp64 run (tests/golden; dropout off)."""
     g = golden(net)
@@ -283,3 +283,34 @@ def test_resize_pool_dropout_backward():
         tape.backward()
         assert torch.equal(xv.g != 0, kept)
         assert torch.allclose(xv.g[kept], torch.full_like(xv.g[kept], 1 / 0.75))
+
+
+def test_grouped_conv_and_avgpool_backward():
+    """ESPNetv2's extra ops: grouped (g=4) 1x1 conv as per-group convs, AvgPool2d(3,2,1) backward."""
+    from esn import ops, train as T
+    torch.manual_seed(6)
+    conv = nn.Conv2d(64, 32, 1, groups=4, bias=False).cuda()
+    x = torch.randn(2, 64, 9, 14, device="cuda", requires_grad=True)
+    ref = conv(x)
+    gy = torch.randn_like(ref)
+    gx, gw = torch.autograd.grad(ref, [x, conv.weight], gy)
+    tape = T.Tape()
+    xv = T.V(_nhwc(x.detach(), torch.float32, ops))
+    y = T.GroupedConvT(conv).forward(tape, xv)
+    assert _rel(y.t, ref.detach()) < 1e-5
+    y._g = _nhwc(gy, torch.float32, ops)
+    pg = tape.backward()
+    assert _rel(xv.g, gx) < 1e-5
+    assert _rel(pg[conv.weight], gw) < 1e-5
+    for (h, w) in ((8, 12), (7, 11), (1, 2)):
+        x = torch.randn(2, 16, h, w, device="cuda", requires_grad=True)
+        ref = F.avg_pool2d(x, 3, 2, 1)
+        gy = torch.randn_like(ref)
+        gx, = torch.autograd.grad(ref, x, gy)
+        tape = T.Tape()
+        xv = T.V(_nhwc(x.detach(), torch.float32, ops))
+        y = T.avgpool3x3s2(tape, xv)
+        assert torch.allclose(y.t, ref.detach(), atol=1e-6)
+        y._g = _nhwc(gy, torch.float32, ops)
+        tape.backward()
+        assert _rel(xv.g, gx) < 1e-5, (h, w)
