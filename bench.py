@@ -42,6 +42,7 @@ WORKLOADS = {
     "dabnet_train_bf16_b8_512x1024": ("DABNet", 8, 512, 1024, "train"),
     # BASELINE.json configs[4] (first half): Fast-SCNN bf16 training, batch 16/GPU, 1024x2048
     "fastscnn_train_bf16_b16_1024x2048": ("FastSCNN", 16, 1024, 2048, "train"),
+    "espnetv2_train_bf16_b16_1024x2048": ("ESPNet_v2", 16, 1024, 2048, "train"),
 }
 # block-fused algorithmic elements per input pixel (forward), bf16 storage; the
 # logits term (19 elements/pixel) is replaced by the 1-byte argmax mask because the head is fused.

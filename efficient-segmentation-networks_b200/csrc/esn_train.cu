@@ -250,6 +250,38 @@ struct WgradArgs {
 
 constexpr int kWgPix = 16;
 
+// Tiny dense convs (taps*Cin*Cout <= 128: ESPNetv2's 8->6 grouped slices and 3->3 input-reinforcement conv):
+// one thread per weight element, walking a pixel strip; the few channels of a pixel are L1 broadcasts.
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(128) wgrad_small_kernel(const WgradArgs a) {
+  const int P = a.kh * a.kw * a.Cin * a.Cout;
+  const int t = threadIdx.x;
+  if (t >= P) return;
+  const int co = t % a.Cout;
+  const int ci = (t / a.Cout) % a.Cin;
+  const int tap = t / (a.Cout * a.Cin);
+  const int r = tap / a.kw, q = tap - r * a.kw;
+  const long long M = (long long)a.N * a.Ho * a.Wo;
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(M, p0 + a.px_per_cta);
+  if (p0 >= p1) return;
+  int wo = (int)(p0 % a.Wo);
+  int ho = (int)((p0 / a.Wo) % a.Ho);
+  int n = (int)(p0 / ((long long)a.Wo * a.Ho));
+  const TX* x = reinterpret_cast<const TX*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy) + co;
+  float acc = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const int hi = ho * a.stride - a.pad_h + r * a.dil_h, wi = wo * a.stride - a.pad_w + q * a.dil_w;
+    if (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) {
+      const float xv = a.x_nchw ? ld1<TX>(x + (((size_t)n * a.Cin + ci) * a.Hi + hi) * a.Wi + wi)
+                                : ld1<TX>(x + (((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs + ci);
+      acc = fmaf(xv, ld1<TG>(dy + (size_t)p * a.dy_cs), acc);
+    }
+    if (++wo == a.Wo) { wo = 0; if (++ho == a.Ho) { ho = 0; ++n; } }
+  }
+  atomicAdd(a.dw + t, acc);      // t == (tap*Cin + ci)*Cout + co: the [tap][Cin][Cout] layout
+}
+
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(256) wgrad_dense_kernel(const WgradArgs a) {
   __shared__ float xs[kWgPix][64 + 1];
@@ -578,6 +610,14 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
     else if (xf) wgrad_dw_kernel<float, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
     else if (gf) wgrad_dw_kernel<__nv_bfloat16, float><<<grid, kStatThreads, 0, st>>>(a);
     else wgrad_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+  } else if (taps * x.c * dy.c <= 128) {
+    a.px_per_cta = (M + 148 * 16 - 1) / (148 * 16);
+    if (a.px_per_cta < 64) a.px_per_cta = 64;
+    const int grid = esn_cdiv(M, a.px_per_cta);
+    if (xf && gf) wgrad_small_kernel<float, float><<<grid, 128, 0, st>>>(a);
+    else if (xf) wgrad_small_kernel<float, __nv_bfloat16><<<grid, 128, 0, st>>>(a);
+    else if (gf) wgrad_small_kernel<__nv_bfloat16, float><<<grid, 128, 0, st>>>(a);
+    else wgrad_small_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, st>>>(a);
   } else {
     const int tiles = esn_cdiv(x.c, 64) * esn_cdiv(dy.c, 64);
     a.px_per_cta = pick_chunk(M, taps * tiles);
