@@ -235,6 +235,192 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnBwdArgs a
   stv4<TD>(dx, vd, c, C, out);
 }
 
+// ---------------------------------------------------------------- 16-byte (8 x bf16) variants
+// Same decomposition -- a thread owns one 8-channel group and walks a pixel chunk, channel groups fastest across
+// the threads so a warp reads whole pixels -- with 128-bit accesses and the per-channel constants in registers.
+// Channel counts that are not a multiple of 8 (35, 131, 259 ...) read the full vector (it stays inside the pixel
+// stride) and simply never publish / store the lanes past C.
+constexpr int kV8Groups = 32;     // channel groups per block (256 channels per blockIdx.y)
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* f) { bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p)), f); }
+
+template <int NQ>
+__global__ void __launch_bounds__(kStatThreads) channel_stats_v8_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int cs,
+                                                                        double* __restrict__ sums, long long px_per_cta) {
+  __shared__ float red[NQ][kStatThreads][9];
+  const int ng = (C + 7) / 8;
+  const int CG = min(ng - (int)blockIdx.y * kV8Groups, kV8Groups);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.y * kV8Groups + cg) * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const long long p0 = blockIdx.x * px_per_cta, p1 = min(M, p0 + px_per_cta);
+  if (pl < lanes) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      float v[8];
+      ld8(x + p * cs + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        if (NQ > 1) q[j] = fmaf(v[j], v[j], q[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = s[j];
+    if (NQ > 1) red[NQ - 1][threadIdx.x][j] = q[j];
+  }
+  __syncthreads();
+  // thread t < CG*8 publishes channel (t / 8 group, t % 8 lane): sum over the pixel lanes
+  if ((int)threadIdx.x < CG * 8) {
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int cc = (blockIdx.y * kV8Groups + g) * 8 + j;
+    if (cc < C) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        a0 += red[0][l * CG + g][j];
+        if (NQ > 1) a1 += red[NQ - 1][l * CG + g][j];
+      }
+      atomicAdd(sums + cc, (double)a0);
+      if (NQ > 1) atomicAdd(sums + C + cc, (double)a1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kStatThreads) bn_act_bwd_reduce_v8_kernel(const BnBwdArgs a) {
+  __shared__ float red[3][kStatThreads][9];
+  const int C = a.C;
+  const int ng = (C + 7) / 8;
+  const int CG = min(ng - (int)blockIdx.y * kV8Groups, kV8Groups);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.y * kV8Groups + cg) * 8;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
+  float sc[8], sh[8], al[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cc = min(c + j, C - 1);
+    sc[j] = a.scale ? a.scale[cc] : 1.f;
+    sh[j] = a.shift ? a.shift[cc] : 0.f;
+    al[j] = (a.act == ESN_ACT_PRELU) ? a.alpha[cc] : 0.f;
+    mu[j] = a.mean ? a.mean[cc] : 0.f;
+    is[j] = a.invstd ? a.invstd[cc] : 1.f;
+  }
+  float s0[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(a.M, p0 + a.px_per_cta);
+  if (pl < lanes) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      float xv[8], gv[8];
+      ld8(x + p * a.x_cs + c, xv);
+      ld8(dy + p * a.dy_cs + c, gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], sc[j], sh[j]);
+        const float dz = act_grad(z, gv[j], a.act, al[j]);
+        s0[j] += dz;
+        s1[j] = fmaf(dz, (xv[j] - mu[j]) * is[j], s1[j]);
+        s2[j] += (z < 0.f) ? gv[j] * z : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = s0[j];
+    red[1][threadIdx.x][j] = s1[j];
+    red[2][threadIdx.x][j] = s2[j];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < CG * 8) {
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int cc = (blockIdx.y * kV8Groups + g) * 8 + j;
+    if (cc < C) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        a0 += red[0][l * CG + g][j];
+        a1 += red[1][l * CG + g][j];
+        a2 += red[2][l * CG + g][j];
+      }
+      atomicAdd(a.sums + cc, (double)a0);
+      atomicAdd(a.sums + C + cc, (double)a1);
+      atomicAdd(a.sums + 2 * C + cc, (double)a2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kStatThreads) bn_act_bwd_apply_v8_kernel(const BnBwdArgs a) {
+  const int C = a.C;
+  const int ng = (C + 7) / 8;
+  const int CG = min(ng - (int)blockIdx.y * kV8Groups, kV8Groups);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.y * kV8Groups + cg) * 8;
+  // parameter gradients: written once by the first pixel block
+  if (blockIdx.x == 0 && (int)threadIdx.x < CG * 8) {
+    const int cc = (blockIdx.y * kV8Groups) * 8 + threadIdx.x;
+    if (cc < C) {
+      if (a.dbeta) a.dbeta[cc] = (float)a.sums[cc];
+      if (a.dgamma) a.dgamma[cc] = (float)a.sums[C + cc];
+      if (a.dalpha && a.act == ESN_ACT_PRELU) a.dalpha[cc] = (float)a.sums[2 * C + cc];
+    }
+  }
+  if (pl >= lanes) return;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
+  const __nv_bfloat16* ex = reinterpret_cast<const __nv_bfloat16*>(a.extra);
+  __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx);
+  const float invM = (float)(1.0 / (double)a.M);
+  float sc[8], sh[8], al[8], k0[8], k1[8], mu[8];   // g = sc*dz - k0 - (x - mu)*k1
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cc = min(c + j, C - 1);
+    sc[j] = a.scale ? a.scale[cc] : 1.f;
+    sh[j] = a.shift ? a.shift[cc] : 0.f;
+    al[j] = (a.act == ESN_ACT_PRELU) ? a.alpha[cc] : 0.f;
+    if (a.train_stats) {
+      mu[j] = a.mean[cc];
+      k0[j] = sc[j] * (float)a.sums[cc] * invM;
+      k1[j] = sc[j] * a.invstd[cc] * (float)a.sums[C + cc] * invM;
+    } else {
+      mu[j] = k0[j] = k1[j] = 0.f;
+    }
+  }
+  const bool full = c + 8 <= C;
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(a.M, p0 + a.px_per_cta);
+  for (long long p = p0 + pl; p < p1; p += lanes) {
+    float xv[8], gv[8], out[8];
+    ld8(x + p * a.x_cs + c, xv);
+    ld8(dy + p * a.dy_cs + c, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(xv[j], sc[j], sh[j]);
+      const float dz = act_grad(z, gv[j], a.act, al[j]);
+      out[j] = sc[j] * dz - k0[j] - (xv[j] - mu[j]) * k1[j];
+    }
+    if (ex) {
+      float ev[8];
+      ld8(ex + p * a.extra_cs + c, ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] += ev[j];
+    }
+    __nv_bfloat16* o = dx + p * a.dx_cs + c;
+    if (full) {
+      *reinterpret_cast<uint4*>(o) = float_to_bf16x8(out);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j < C) o[j] = __float2bfloat16_rn(out[j]);
+    }
+  }
+}
+
+static inline bool v8_ok(const void* p, int cs) { return p && cs % 8 == 0 && (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
+
 // ---------------------------------------------------------------- dense conv weight gradient
 // dW[tap][ci][co] += sum_p X[p + delta_tap, ci] * dY[p, co]; block computes a 64(ci) x 64(co) tile for one
 // tap over a chunk of output pixels; thread = 4x4 register tile; smem stages of 16 pixels.
@@ -484,6 +670,15 @@ extern "C" int esn_channel_stats(const EsnTensor* x, double* sums, int32_t with_
   const long long chunk = pick_chunk(M, cblocks);
   dim3 grid(esn_cdiv(M, chunk), cblocks);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x->dtype == ESN_BF16 && v8_ok(x->ptr, x->c_stride)) {
+    const int cb = esn_cdiv(esn_cdiv(x->c, 8), kV8Groups);
+    const long long ch = pick_chunk(M, cb);
+    dim3 g8(esn_cdiv(M, ch), cb);
+    if (with_squares) channel_stats_v8_kernel<2><<<g8, kStatThreads, 0, st>>>((const __nv_bfloat16*)x->ptr, M, x->c, x->c_stride, sums, ch);
+    else channel_stats_v8_kernel<1><<<g8, kStatThreads, 0, st>>>((const __nv_bfloat16*)x->ptr, M, x->c, x->c_stride, sums, ch);
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
+  }
   if (x->dtype == ESN_F32) {
     if (with_squares) channel_stats_kernel<float, 2><<<grid, kStatThreads, 0, st>>>((const float*)x->ptr, M, x->c, x->c_stride, sums, chunk);
     else channel_stats_kernel<float, 1><<<grid, kStatThreads, 0, st>>>((const float*)x->ptr, M, x->c, x->c_stride, sums, chunk);
@@ -539,11 +734,19 @@ extern "C" int esn_bn_act_bwd_reduce(const EsnBnBwd* p, void* stream) {
   BnBwdArgs a;
   int rc = fill_bn_bwd(p, a);
   if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool xf = p->x.dtype == ESN_F32, gf = p->dy.dtype == ESN_F32;
+  if (!xf && !gf && v8_ok(a.x, a.x_cs) && v8_ok(a.dy, a.dy_cs)) {
+    const int cb = esn_cdiv(esn_cdiv(a.C, 8), kV8Groups);
+    a.px_per_cta = pick_chunk(a.M, cb);
+    dim3 g8(esn_cdiv(a.M, a.px_per_cta), cb);
+    bn_act_bwd_reduce_v8_kernel<<<g8, kStatThreads, 0, st>>>(a);
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
+  }
   const int cblocks = esn_cdiv(esn_cdiv(a.C, 4), 64);
   a.px_per_cta = pick_chunk(a.M, cblocks);
   dim3 grid(esn_cdiv(a.M, a.px_per_cta), cblocks);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool xf = p->x.dtype == ESN_F32, gf = p->dy.dtype == ESN_F32;
   if (xf && gf) bn_act_bwd_reduce_kernel<float, float><<<grid, kStatThreads, 0, st>>>(a);
   else if (xf) bn_act_bwd_reduce_kernel<float, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
   else if (gf) bn_act_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, kStatThreads, 0, st>>>(a);
@@ -558,10 +761,20 @@ extern "C" int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream) {
   if (rc) return rc;
   if (!esn_valid_nhwc(p->dx) || p->dx.c != p->x.c || p->dx.dtype != p->dy.dtype) return ESN_ERR_BAD_ARG;
   if (p->extra.ptr && (!esn_valid_nhwc(p->extra) || p->extra.dtype != p->dx.dtype)) return ESN_ERR_BAD_ARG;
-  const long long total = a.M * ((a.C + 3) / 4);
-  const int grid = esn_cdiv(total > a.C ? total : a.C, 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool xf = p->x.dtype == ESN_F32, gf = p->dy.dtype == ESN_F32;
+  if (!xf && !gf && v8_ok(a.x, a.x_cs) && v8_ok(a.dy, a.dy_cs) && v8_ok(a.dx, a.dx_cs) && (!a.extra || v8_ok(a.extra, a.extra_cs))) {
+    const int cb = esn_cdiv(esn_cdiv(a.C, 8), kV8Groups);
+    long long want = (8LL * 148 + cb - 1) / cb;
+    a.px_per_cta = (a.M + want - 1) / want;
+    if (a.px_per_cta < 64) a.px_per_cta = 64;
+    dim3 g8(esn_cdiv(a.M, a.px_per_cta), cb);
+    bn_act_bwd_apply_v8_kernel<<<g8, kStatThreads, 0, st>>>(a);
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
+  }
+  const long long total = a.M * ((a.C + 3) / 4);
+  const int grid = esn_cdiv(total > a.C ? total : a.C, 256);
   if (xf && gf) bn_act_bwd_apply_kernel<float, float, float><<<grid, 256, 0, st>>>(a);
   else if (xf) bn_act_bwd_apply_kernel<float, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
   else if (gf) bn_act_bwd_apply_kernel<__nv_bfloat16, float, float><<<grid, 256, 0, st>>>(a);
