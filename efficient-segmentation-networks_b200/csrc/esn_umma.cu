@@ -35,6 +35,7 @@ struct alignas(64) UmmaArgs {
   int hs_d, hs_pad;                  // MODE_HREUSE: tap spacing / left padding in pixels
   int vr_d, vr_pad, vr_L, vr_nseg;   // MODE_VREUSE: row stride, top padding, outputs per unit, segments
   int vr_cnt, vr_rem;                // rows of the longest residue class; residues >= vr_rem have one less
+  int vr_kh, vr_kw;                  // MODE_VREUSE: tap rows (ring slots per output) x taps per row (shifted windows of one slot)
   int tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_par[kMaxTaps], tap_coff[kMaxTaps], tap_wrow[kMaxTaps];
   __nv_bfloat16* y;
   int Hy, Wy, y_cs, sy, oy, sx, ox;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
-    if (MODE == MODE_HREUSE) tma_prefetch_desc(&a.tmAh);
+    if (MODE == MODE_HREUSE || (MODE == MODE_VREUSE && a.vr_kw > 1)) tma_prefetch_desc(&a.tmAh);
     if (a.staged) tma_prefetch_desc(&a.tmY);
     if (a.has_res && a.staged) tma_prefetch_desc(&a.tmR);
     for (int s = 0; s < S; ++s) {
@@ -215,14 +216,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         if (MODE == MODE_VREUSE) {
           // rows h0-pad + j*d, j = 0..len+ntaps-2: one ring slot each, each row loaded exactly once
           int row = un.h0 - a.vr_pad;
-          for (int j = 0; j < un.len + ntaps - 1; ++j, row += un.hstep) {
+          const int wl = un.w0 - a.hs_pad;     // k_h x k_w convs: each slot holds the row window [w0-pad, w0+bw+(k_w-1)d-pad)
+          for (int j = 0; j < un.len + a.vr_kh - 1; ++j, row += un.hstep) {
             mbar_wait(empty0 + 8u * s, ph ^ 1u);
             if (leader) {
               mbar_expect_tx(full0 + 8u * s, a.load_bytes);
               const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
               for (int q = 0; q < a.a_nbox; ++q)
-                tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, 0, un.w0 + q * a.a_boxw, 0,
+                tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, 0, wl + q * a.a_boxw, 0,
                             row, un.n);
+              if (a.vr_kw > 1) tma_load_5d(dst + (uint32_t)a.bw * RB, &a.tmAh, full0 + 8u * s, 0, wl + a.bw, 0, row, un.n);
             }
             if (++s == S) { s = 0; ph ^= 1u; }
           }
@@ -282,24 +285,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             // tap t of this output lives in ring slot s+t (s = slot of the oldest live row)
             int st = s;
             uint32_t pt = ph;
-            for (int t = 0; t < ntaps; ++t) {
-              if (i == 0 || t == ntaps - 1) {
+            const int kh = a.vr_kh, kw = a.vr_kw;
+            const uint32_t shift16 = ((uint32_t)a.hs_d * RB) >> 4;   // horizontal tap spacing in descriptor units
+            uint32_t bl = w_lo;
+            for (int t = 0; t < kh; ++t) {
+              if (i == 0 || t == kh - 1) {
                 mbar_wait(full0 + 8u * st, pt);
               }
-              const uint32_t al = a_lo0 + (uint32_t)st * stage16, bl = w_lo + (uint32_t)t * wblk16;
-              for (int m = 0; m < MT; ++m) {
+              uint32_t al = a_lo0 + (uint32_t)st * stage16;
+              for (int q = 0; q < kw; ++q, al += shift16, bl += wblk16) {
+                for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  if (leader)
-                    umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
-                                 (t | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < KSTEPS; ++k)
+                    if (leader)
+                      umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi, idesc,
+                                   (t | q | k) != 0 ? 1u : 0u);
+                }
               }
               if (++st == S) { st = 0; pt ^= 1u; }
             }
             if (leader) umma_commit(empty0 + 8u * s);   // the oldest row is dead once these MMAs retire
             if (++s == S) { s = 0; ph ^= 1u; }
-            if (i == un.len - 1) {          // unit done: release the ntaps-1 rows still held
-              for (int t = 1; t < ntaps; ++t) {
+            if (i == un.len - 1) {          // unit done: release the kh-1 rows still held
+              for (int t = 1; t < kh; ++t) {
                 if (leader) umma_commit(empty0 + 8u * s);
                 if (++s == S) { s = 0; ph ^= 1u; }
               }
@@ -616,8 +624,8 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   a.mode = MODE_GENERIC;
   if (rowable && p->kh == 1 && p->kw >= 2 && (p->kw - 1) * p->dil_w <= 256)
     a.mode = MODE_HREUSE;
-  else if (rowable && p->kw == 1 && p->kh >= 2 && nkb == 1)
-    a.mode = MODE_VREUSE;
+  else if (rowable && p->kh >= 2 && nkb == 1 && (p->kw - 1) * p->dil_w <= 64 && !getenv("ESN_UMMA_NOHV") )
+    a.mode = MODE_VREUSE;     // k x 1, and k_h x k_w (3x3): row ring x shifted windows, every input row loaded once
   if (a.mode != MODE_GENERIC) {
     if (a.mode == MODE_HREUSE && KB == 64 && nkb == 1 && N <= 64) MT = 2;   // 256-pixel row tiles for C=64
     while (MT > 1 && MT * kTileM > gw) MT >>= 1;
@@ -665,8 +673,12 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     a.vr_nseg = esn_cdiv(cnt, L);
     a.vr_cnt = cnt;
     a.vr_rem = gh - (cnt - 1) * a.vr_d;
-    a.load_bytes = (uint32_t)rows * row_bytes;
-    a.stage_bytes = a.load_bytes;
+    a.vr_kh = p->kh;
+    a.vr_kw = p->kw;
+    a.hs_d = p->dil_w;
+    a.hs_pad = p->pad_w;
+    a.load_bytes = (uint32_t)(rows + (p->kw - 1) * p->dil_w) * row_bytes;
+    a.stage_bytes = (a.load_bytes + 1023u) & ~1023u;
     a.nunits = x.n * a.tiles_w * a.vr_d * a.vr_nseg;
   } else {
     a.load_bytes = (uint32_t)rows * row_bytes;
@@ -700,7 +712,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   }
 
   // ---- activation tensor maps (5-D): main box, and the (k-1)*d-pixel tail box of the hreuse window
-  for (int which = 0; which < (a.mode == MODE_HREUSE ? 2 : 1); ++which) {
+  for (int which = 0; which < ((a.mode == MODE_HREUSE || (a.mode == MODE_VREUSE && p->kw > 1)) ? 2 : 1); ++which) {
     const cuuint64_t cs = (cuuint64_t)x.c_stride;
     cuuint64_t dims[5], strides[4];
     if (!p->transposed && p->stride == 2) {
@@ -790,9 +802,9 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     a.w_region_bytes = (wbytes + 1023u) & ~1023u;
     // shared memory plan: resident weights + A ring + staging + params + barriers (+1 KB alignment slack)
     // trade staging buffers for A stages until the load pipeline is deep enough to cover ~2 tiles
-    const int min_stages = a.mode == MODE_VREUSE ? nt + 1 : 2;
+    const int min_stages = a.mode == MODE_VREUSE ? p->kh + 1 : 2;
     const int per_tile = a.mode == MODE_VREUSE ? 1 : (a.mode == MODE_HREUSE ? nkb : nt * nkb);
-    int want = a.mode == MODE_VREUSE ? nt + 3 : (a.mode == MODE_HREUSE ? per_tile + 1 : 2 * per_tile + 1);
+    int want = a.mode == MODE_VREUSE ? p->kh + 3 : (a.mode == MODE_HREUSE ? per_tile + 1 : 2 * per_tile + 1);
     if (want > 8) want = 8;
     int ns = a.staged ? (a.out_buf_bytes <= 16384 ? 4 : 2) : 0;
     for (;;) {

@@ -41,6 +41,13 @@ CASES = [
     ("v_3x1_16_w512", 16, 16, (3, 1), 1, (1, 0), (1, 1), False, 0, 2, 19, 512),
     ("v_5x1_32", 32, 32, (5, 1), 1, (2, 0), (1, 1), False, 0, 2, 21, 128),
     ("v_3x1_64_d16", 64, 64, (3, 1), 1, (16, 0), (16, 1), False, 0, 1, 40, 128),
+    # k_h x k_w convs on the row ring: every input row loaded once, 9 taps = 3 slots x 3 shifted windows
+    ("hv_3x3_32_32_w256", 32, 32, 3, 1, 1, 1, False, 0, 2, 20, 256),
+    ("hv_3x3_64_32_w384", 64, 32, 3, 1, 1, 1, False, 0, 2, 17, 384),
+    ("hv_3x3_32_d4_w128", 32, 32, 3, 1, 4, 4, False, 0, 2, 24, 128),
+    ("hv_3x3_16_48_w512", 16, 48, 3, 1, 1, 1, False, 0, 1, 9, 512),
+    ("hv_3x3_64_64_d2_w200", 64, 64, 3, 1, 2, 2, False, 0, 2, 21, 200),
+    ("hv_3x3_32_d16_w256", 32, 32, 3, 1, 16, 16, False, 0, 1, 40, 256),
 ]
 
 
