@@ -385,6 +385,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int staged = a.staged, has_res = a.has_res, act = a.ep.act, cout = a.cout;
     const uint32_t swz = a.out_swz_mask;
     const bool wide = a.cbo == 64 && a.ncb > 1;  // column blocks of 64 channels
+    // this thread's work items: (sub-tile m, 16-column chunk) pairs dealt round-robin to the 4 warps of a quadrant
+    int nitems = 0, it_c0[4] = {0, 0, 0, 0};
+    uint32_t it_toff[4] = {0, 0, 0, 0}, it_soff[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    {
+      int m = 0, chn = grp;
+      while (chn >= nchunk) { chn -= nchunk; ++m; }
+      while (m < MT && nitems < 4) {
+        const int c0 = chn << 4;
+        it_c0[nitems] = c0;
+        it_toff[nitems] = (uint32_t)(m * a.N + c0);
+        const int R = m * kTileM + q * 32 + lane;
+        for (int h = 0; h < 2; ++h) {
+          const int cb8 = c0 + 8 * h;
+          const int blk = wide ? (cb8 >> 6) : 0;
+          const int cin_blk = wide ? (cb8 & 63) : cb8;
+          uint32_t off = (uint32_t)R * row_bytes + (uint32_t)cin_blk * 2u;
+          off ^= ((off >> 7) & swz) << 4;
+          it_soff[nitems][h] = (uint32_t)blk * a.out_block_bytes + off;
+        }
+        ++nitems;
+        chn += kEpiThreads / 128;
+        while (chn >= nchunk) { chn -= nchunk; ++m; }
+      }
+    }
     uint32_t tc = 0, acc = 0, aph = 0;
     UnitIter<MODE> un;
     if (u_begin < u_end) un.init(a, u_begin);
@@ -403,22 +427,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         mbar_wait(tfull0 + 8u * acc, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
-        // work items (m, chunk) are dealt round-robin to the warps of a quadrant
-        int m = 0, chn = grp;
-        while (chn >= nchunk) { chn -= nchunk; ++m; }
-        while (m < MT) {
-          const int c0 = chn << 4;
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)(m * a.N + c0), r);
-          tmem_ld_wait();
-          if (c0 < cout) {
-            const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
+        if (staged) {
+          // ---- staged path: every thread's (sub-tile, 16-column) items are fixed for the whole kernel, so their
+          // TMEM offsets, swizzled staging offsets and parameter addresses were computed once (it_*)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int cb8 = c0 + 8 * h;
-              if (cb8 < cout) {
-                float f[8];
-                {
+          for (int k = 0; k < 4; ++k) {
+            if (k < nitems) {
+              uint32_t r[16];
+              tmem_ld16(taddr + it_toff[k], r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int cb8 = it_c0[k] + 8 * h;
+                if (cb8 < cout) {
+                  float f[8];
                   const uint32_t pa = prm_base + 4u * (uint32_t)cb8;
                   const float4 s0 = lds_f4(pa), s1 = lds_f4(pa + 16u);
                   const float4 h0 = lds_f4(pa + 1024u), h1 = lds_f4(pa + 1040u);
@@ -430,21 +452,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
                   f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
                   f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
-                }
-                if (staged) {
-                  const int blk = wide ? (cb8 >> 6) : 0;
-                  const int cin_blk = wide ? (cb8 & 63) : cb8;
-                  uint32_t off = (uint32_t)R * row_bytes + (uint32_t)cin_blk * 2u;
-                  off ^= ((off >> 7) & swz) << 4;
-                  const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
+                  const uint32_t saddr = obuf + it_soff[k][h];
                   if (has_res) {
                     if (a.ep.pre_act) {   // ext = act(BN(conv)) before "main + ext" (ENet bottlenecks)
                       if (act == ESN_ACT_RELU) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                       } else if (act == ESN_ACT_PRELU) {
-                        const uint32_t pa = prm_base + 2048u + 4u * (uint32_t)cb8;
-                        const float4 a0 = lds_f4(pa), a1 = lds_f4(pa + 16u);
+                        const float4 a0 = lds_f4(pa + 2048u), a1 = lds_f4(pa + 2064u);
                         const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
@@ -459,40 +474,108 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                   } else if (act == ESN_ACT_PRELU) {
-                    const uint32_t pa = prm_base + 2048u + 4u * (uint32_t)cb8;
-                    const float4 a0 = lds_f4(pa), a1 = lds_f4(pa + 16u);
+                    const float4 a0 = lds_f4(pa + 2048u), a1 = lds_f4(pa + 2064u);
                     const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
                   }
                   sts128(saddr, float_to_bf16x8(f));
-                } else {
-                  // fallback: per-thread global stores (output channel count not a multiple of 8)
-                  const int ri = R / a.bw, rj = R - ri * a.bw;
-                  const int gi = th0 + ri, gj = un.w0 + rj;
-                  if (gi < a.gh && gj < a.gw) {
-                    const size_t opix =
-                        ((size_t)un.n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
-                    __nv_bfloat16* yp = a.y + opix * a.y_cs;
-                    for (int j = 0; j < 8; ++j) {
-                      const int c = cb8 + j;
-                      if (c < cout) {
-                        float v = f[j];
-                        if (a.ep.res && a.ep.pre_act) v = apply_act(v, act, prm[512 + c]);
-                        if (a.ep.res)
-                          v += __bfloat162float(
-                              reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
-                        v = apply_act(v, act, prm[512 + c]);
-                        yp[c] = __float2bfloat16_rn(v);
+                }
+              }
+            }
+          }
+        } else {
+          // work items (m, chunk) are dealt round-robin to the warps of a quadrant
+          int m = 0, chn = grp;
+          while (chn >= nchunk) { chn -= nchunk; ++m; }
+          while (m < MT) {
+            const int c0 = chn << 4;
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)(m * a.N + c0), r);
+            tmem_ld_wait();
+            if (c0 < cout) {
+              const int R = m * kTileM + q * 32 + lane;   // row of the (MT*128)-row tile
+  #pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int cb8 = c0 + 8 * h;
+                if (cb8 < cout) {
+                  float f[8];
+                  {
+                    const uint32_t pa = prm_base + 4u * (uint32_t)cb8;
+                    const float4 s0 = lds_f4(pa), s1 = lds_f4(pa + 16u);
+                    const float4 h0 = lds_f4(pa + 1024u), h1 = lds_f4(pa + 1040u);
+                    f[0] = fmaf(__uint_as_float(r[8 * h + 0]), s0.x, h0.x);
+                    f[1] = fmaf(__uint_as_float(r[8 * h + 1]), s0.y, h0.y);
+                    f[2] = fmaf(__uint_as_float(r[8 * h + 2]), s0.z, h0.z);
+                    f[3] = fmaf(__uint_as_float(r[8 * h + 3]), s0.w, h0.w);
+                    f[4] = fmaf(__uint_as_float(r[8 * h + 4]), s1.x, h1.x);
+                    f[5] = fmaf(__uint_as_float(r[8 * h + 5]), s1.y, h1.y);
+                    f[6] = fmaf(__uint_as_float(r[8 * h + 6]), s1.z, h1.z);
+                    f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
+                  }
+                  if (staged) {
+                    const int blk = wide ? (cb8 >> 6) : 0;
+                    const int cin_blk = wide ? (cb8 & 63) : cb8;
+                    uint32_t off = (uint32_t)R * row_bytes + (uint32_t)cin_blk * 2u;
+                    off ^= ((off >> 7) & swz) << 4;
+                    const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
+                    if (has_res) {
+                      if (a.ep.pre_act) {   // ext = act(BN(conv)) before "main + ext" (ENet bottlenecks)
+                        if (act == ESN_ACT_RELU) {
+  #pragma unroll
+                          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                        } else if (act == ESN_ACT_PRELU) {
+                          const uint32_t pa = prm_base + 2048u + 4u * (uint32_t)cb8;
+                          const float4 a0 = lds_f4(pa), a1 = lds_f4(pa + 16u);
+                          const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  #pragma unroll
+                          for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
+                        }
+                      }
+                      float g[8];
+                      bf16x8_to_float(lds128(saddr), g);
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) f[j] += g[j];
+                    }
+                    if (act == ESN_ACT_RELU) {
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                    } else if (act == ESN_ACT_PRELU) {
+                      const uint32_t pa = prm_base + 2048u + 4u * (uint32_t)cb8;
+                      const float4 a0 = lds_f4(pa), a1 = lds_f4(pa + 16u);
+                      const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
+                    }
+                    sts128(saddr, float_to_bf16x8(f));
+                  } else {
+                    // fallback: per-thread global stores (output channel count not a multiple of 8)
+                    const int ri = R / a.bw, rj = R - ri * a.bw;
+                    const int gi = th0 + ri, gj = un.w0 + rj;
+                    if (gi < a.gh && gj < a.gw) {
+                      const size_t opix =
+                          ((size_t)un.n * a.Hy + (size_t)(gi * a.sy + a.oy)) * a.Wy + (size_t)(gj * a.sx + a.ox);
+                      __nv_bfloat16* yp = a.y + opix * a.y_cs;
+                      for (int j = 0; j < 8; ++j) {
+                        const int c = cb8 + j;
+                        if (c < cout) {
+                          float v = f[j];
+                          if (a.ep.res && a.ep.pre_act) v = apply_act(v, act, prm[512 + c]);
+                          if (a.ep.res)
+                            v += __bfloat162float(
+                                reinterpret_cast<const __nv_bfloat16*>(a.ep.res)[opix * a.ep.res_cstride + c]);
+                          v = apply_act(v, act, prm[512 + c]);
+                          yp[c] = __float2bfloat16_rn(v);
+                        }
                       }
                     }
                   }
                 }
               }
             }
+            chn += kEpiThreads / 128;
+            while (chn >= nchunk) { chn -= nchunk; ++m; }
           }
-          chn += kEpiThreads / 128;
-          while (chn >= nchunk) { chn -= nchunk; ++m; }
         }
         tc_fence_before();
         __syncwarp();
