@@ -228,3 +228,10 @@ def test_enet_pool_unpool_matches_cpu_reference(ops):
     assert torch.equal(out.cpu(), ref)
     dup = (ref_i.flatten(2).sort(dim=2).values.diff(dim=2) == 0).float().mean().item()
     assert dup > 0.05, "test input must contain duplicate indices"
+    # bf16: the 16-byte (8-channel) pool / unpool paths, values exactly representable
+    yb, idxb = ops.maxpool3x3s2_idx(_nhwc(x.cuda(), torch.bfloat16, ops))
+    assert torch.equal(yb.float().cpu(), ref_y) and torch.equal(idxb.permute(0, 3, 1, 2).cpu().long(), ref_i)
+    vb, eb = v.round(), ext.round()
+    refb = F.relu(F.max_unpool2d(vb.contiguous(), ref_i, 2) + eb)
+    outb = ops.max_unpool2x2(_nhwc(vb.cuda(), torch.bfloat16, ops), idx, ext=_nhwc(eb.cuda(), torch.bfloat16, ops), act=ACT_RELU)
+    assert outb.dtype == torch.bfloat16 and torch.equal(outb.float().cpu(), refb)
