@@ -43,6 +43,7 @@ struct alignas(64) PairArgs {
   int N, has_res, act1, act2, stages, NI, NS;   // NI: intermediate row buffers (1 or 2); NS: output staging buffers
   const __nv_bfloat16* res;
   int res_cs, W, pf;   // pf: L2 prefetch distance in tiles
+  int issuers;         // 1: one MMA-issuing warp; 2: conv1 (+ residual MMA) on warp 1, conv2 on warp 2
   uint32_t stage_bytes, wblock_bytes, inter_bytes, out_buf_bytes, swz_mask;
   uint32_t idesc, desc_hi, tmem_cols;
   const float *scale1, *shift1, *scale2, *shift2, *alpha2;
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
   const uint32_t t2full0 = t1empty0 + 8u * NA, t2empty0 = t2full0 + 8u * NA;
   const uint32_t ifull0 = t2empty0 + 8u * NA, ifree0 = ifull0 + 8u * 2 * kMaxTR;   // [buffer][tile]
   const uint32_t sfree0 = ifree0 + 8u * 2 * kMaxTR;
-  const uint32_t tmem_slot = sfree0 + 8u * 2;
+  const uint32_t rres0 = sfree0 + 8u * 2;          // residual MMA issued into accumulator slot (two-issuer mode)
+  const uint32_t tmem_slot = rres0 + 8u * NA;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* prm = reinterpret_cast<float*>(smem_raw + (prm_base - raw));
 
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       mbar_init(ifree0 + 8u * j, 1);
     }
     for (int b = 0; b < 2; ++b) mbar_init(sfree0 + 8u * b, 1);
+    for (int b = 0; b < NA; ++b) mbar_init(rres0 + 8u * b, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -226,9 +229,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     // row) of tile g-3 interleaved tap by tap -- two independent accumulator chains in flight -- then
     // "+ residual" as one more MMA against the identity.  conv2 trails by three tiles: its inputs (epilogue 1
     // of tiles <= g-2) never depend on MMAs that were only just issued.
-    // (Splitting the two chains over two issuing warps measured 25 % faster per launch but hit a rare
-    // "unspecified launch failure" on B200 with the residual path; one issuer is what ships.)
-    if (G > 0) {
+    // This single-issuer loop is the fallback (ESN_PAIR_ISSUERS=1).  The default splits the work over two issuing
+    // warps (below): ~20 % faster per launch because the issue stream itself -- waits, tcgen05.mma, ~100-cycle
+    // tcgen05.commits -- was the critical path.  The split that works keeps ONE consumer on the TMA ring (warp 1 also
+    // issues the residual MMA); letting warp 2 consume ring slots as well produced a rare "unspecified launch failure".
+    if (G > 0 && a.issuers == 2) {
+      // ---- two-issuer mode, warp 1: conv1 of tile g from the ring, then (residual pairs) the residual tile of
+      // g-3 as the FIRST MMA of conv2's accumulator (accumulate = 0); warp 2 adds the 1 x k taps on top once
+      // rres[slot] says that MMA has been issued.  The ring has a single consumer.
+      const bool leader = elect_one();
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      const uint32_t dhi = a.desc_hi, idesc = a.idesc;
+      const uint32_t w1_lo = desc_lo(w1_base), wblk16 = a.wblock_bytes >> 4;
+      const uint32_t a_lo0 = desc_lo(a_base), stage16 = a.stage_bytes >> 4, id_lo = desc_lo(id_base);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int g = 0; g < G + 3; ++g) {
+        if (g < G) {
+          const uint32_t slot1 = (uint32_t)g & (NA - 1);
+          mbar_wait(t1empty0 + 8u * slot1, ((((uint32_t)g / NA) & 1u) ^ 1u));
+          tc_fence_after();
+          const uint32_t d1 = tmem_base + slot1 * acc_cols;
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(full0 + 8u * s, ph);
+            const uint32_t al1 = a_lo0 + (uint32_t)s * stage16, bl1 = w1_lo + (uint32_t)t * wblk16;
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                if (leader)
+                  umma_bf16_lo(d1 + (uint32_t)m * N, al1 + (uint32_t)m * SUB16 + 2u * k, bl1 + 2u * k, dhi, idesc,
+                               (t | k) != 0 ? 1u : 0u);
+            }
+            if (leader) umma_commit(empty0 + 8u * s);
+            if (++s == S) { s = 0; ph ^= 1u; }
+          }
+          if (leader) umma_commit(t1full0 + 8u * slot1);
+        }
+        if (g >= 3 && a.has_res) {
+          const int gg = g - 3;
+          const uint32_t slot2 = (uint32_t)gg & (NA - 1);
+          mbar_wait(t2empty0 + 8u * slot2, ((((uint32_t)gg / NA) & 1u) ^ 1u));
+          tc_fence_after();
+          mbar_wait(full0 + 8u * s, ph);
+          const uint32_t d2 = tmem_base + (NA + slot2) * acc_cols, alr = a_lo0 + (uint32_t)s * stage16;
+          for (int m = 0; m < MT; ++m) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              if (leader) umma_bf16_lo(d2 + (uint32_t)m * N, alr + (uint32_t)m * SUB16 + 2u * k, id_lo + 2u * k, dhi, idesc, k != 0 ? 1u : 0u);
+          }
+          if (leader) {
+            umma_commit(empty0 + 8u * s);
+            mbar_arrive(rres0 + 8u * slot2);
+          }
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        __syncwarp();
+      }
+    } else if (G > 0) {
       const bool leader = elect_one();
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
@@ -309,7 +367,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       }
     }
   } else if (warp == 2) {
-    // idle
+    if (G > 0 && a.issuers == 2) {
+      // ---- two-issuer mode, warp 2: conv2 (1 x k) of tile g-3 from the intermediate row
+      const bool leader = elect_one();
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      const uint32_t dhi = a.desc_hi, idesc = a.idesc;
+      const uint32_t w2_lo = desc_lo(w2_base), wblk16 = a.wblock_bytes >> 4;
+      const uint32_t i_lo0 = desc_lo(i_base);
+      const uint32_t tap16 = ((uint32_t)a.d * RB) >> 4;
+      int r2m = 0, j2m = 0;
+      for (int gg = 0; gg < G; ++gg) {
+        const int r = r2m, j = j2m;
+        if (++j2m == TR) { j2m = 0; ++r2m; }
+        const int jn = j + 1 < TR ? j + 1 : j;
+        const uint32_t ib = (uint32_t)r & (uint32_t)(a.NI - 1);
+        mbar_wait(ifull0 + 8u * (ib * kMaxTR + jn), (uint32_t)(r >> nishift) & 1u);
+        const uint32_t slot2 = (uint32_t)gg & (NA - 1), use = (uint32_t)gg / NA;
+        if (a.has_res)
+          mbar_wait(rres0 + 8u * slot2, use & 1u);               // accumulator holds the residual (issued by warp 1)
+        else
+          mbar_wait(t2empty0 + 8u * slot2, (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d2 = tmem_base + (NA + slot2) * acc_cols;
+        const uint32_t i_lo = i_lo0 + ((ib * a.inter_bytes + (uint32_t)(kPadPx + j * a.BW - (ntaps >> 1) * a.d) * RB) >> 4);
+        const uint32_t acc0 = a.has_res ? 1u : 0u;
+        for (int t = 0; t < ntaps; ++t) {
+          const uint32_t bl2 = w2_lo + (uint32_t)t * wblk16, al2 = i_lo + (uint32_t)t * tap16;
+          for (int m = 0; m < MT; ++m) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              if (leader)
+                umma_bf16_lo(d2 + (uint32_t)m * N, al2 + (uint32_t)m * SUB16 + 2u * k, bl2 + 2u * k, dhi, idesc,
+                             (t | k) != 0 ? 1u : acc0);
+          }
+        }
+        if (leader) {
+          umma_commit(t2full0 + 8u * slot2);
+          umma_commit(ifree0 + 8u * (ib * kMaxTR + j));
+        }
+        __syncwarp();
+      }
+    }
   } else {
     // ---------------- epilogue warps.  Every thread owns ONE (sub-tile, 16-channel) item of each tile -- row
     // R of the tile, channels c0..c0+15 -- so all of its addresses are loop constants: the swizzled offsets
@@ -583,6 +682,8 @@ extern "C" int esn_conv_pair_umma(const EsnConvPair* p, void* stream) {
   }
   static const int pf_env = getenv("ESN_PAIR_PF") ? atoi(getenv("ESN_PAIR_PF")) : 0;
   a.pf = pf_env;
+  static const int issuers_env = getenv("ESN_PAIR_ISSUERS") ? atoi(getenv("ESN_PAIR_ISSUERS")) : 2;
+  a.issuers = issuers_env == 1 ? 1 : 2;
   for (int which = 0; which < (a.has_res ? 2 : 1); ++which) {  // output, residual (prefetch only): (C, W, H, N)
     const EsnTensor& t = which ? res : y;
     const cuuint64_t cs = (cuuint64_t)t.c_stride;
