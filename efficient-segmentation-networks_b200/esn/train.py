@@ -194,6 +194,79 @@ class ConvT:
         return y
 
 
+class ConvTransposeT:
+    """nn.ConvTranspose2d (dense, stride 2: ERFNet's UpsamplerBlock 3x3/p1/op1 and its 2x2 output conv) for training.
+    Forward = the transposed-conv kernels; input gradient = the strided conv with the same weight (the adjoint);
+    weight gradient = esn_conv2d_wgrad with the roles of input and output gradient swapped."""
+
+    def __init__(self, conv):
+        self.conv = conv
+        self._key = None
+
+    def preps(self):
+        c = self.conv
+        w = c.weight
+        key = (w.data_ptr(), w._version, None if c.bias is None else c.bias._version)
+        if self._key != key:
+            self.fwd_prep = ops.ConvPrep(c)
+            # (Cin, Cout, kh, kw) read as a conv weight (out = Cin, in = Cout): conv2d(dy, W, stride, padding) = dx
+            self.dgrad_prep = ops.ConvPrep.from_weight(w.detach().float(), c.stride[0], tuple(c.padding), (1, 1), 1)
+            self._key = key
+        return self.fwd_prep, self.dgrad_prep
+
+    def backward_from(self, tape, x, dy):
+        """dy: NHWC gradient of the output (channels = conv.out_channels, possibly in a zero-padded wider buffer)."""
+        conv = self.conv
+        fwd_prep, dgrad_prep = self.preps()
+        kh, kw = conv.kernel_size
+        cin, cout = conv.in_channels, conv.out_channels
+        xt = x.t
+        dwbuf = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=dy.device)   # [tap][Cout][Cin]
+        p = L.EsnConv()
+        p.x, p.y, p.w = ops.tdesc(dy), ops.tdesc(xt), dwbuf.data_ptr()
+        p.kh, p.kw, p.stride = kh, kw, conv.stride[0]
+        p.pad_h, p.pad_w, p.dil_h, p.dil_w = conv.padding[0], conv.padding[1], 1, 1
+        p.groups, p.transposed, p.cout_pad = 1, 0, (cin + 15) // 16 * 16
+        ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy),
+                  2 * xt.shape[0] * xt.shape[2] * xt.shape[3] * cin * cout * kh * kw, "%dx%dT c%d-%d" % (kh, kw, cin, cout))
+        tape.add_param_grad(conv.weight, dwbuf.view(kh, kw, cout, cin).permute(3, 2, 0, 1))
+        if conv.bias is not None:
+            sums = _f64zeros(cout, dy.device)
+            d = ops.tdesc(dy)
+            ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 0), ops._nbytes(dy))
+            tape.add_param_grad(conv.bias, sums.float())
+        x.add_grad(lambda ex, dst: ops.conv2d(dy, dgrad_prep, out=dst, residual=ex))
+
+    def forward(self, tape, x, out=None):
+        fwd_prep, _ = self.preps()
+        n, _, h, w = x.t.shape
+        if out is None:
+            ho, wo = fwd_prep.out_hw(h, w)
+            out = V(ops.new_act(n, fwd_prep.cout, ho, wo, x.t.dtype, x.t.device))
+        y = out
+        ops.conv2d(x.t, fwd_prep, out=y.t)
+        tape.push(lambda: self.backward_from(tape, x, y.g))
+        return y
+
+
+def convt2x2_logits(tape, convt, x, w_packed, bias, classes):
+    """ERFNet's output conv (ConvTranspose2d(16, classes, 2, stride 2), ERFNet.py:128) -> NCHW fp32 logits through the
+    fused head kernel; backward converts d logits to NHWC once and reuses ConvTransposeT's gradients."""
+    logits, _ = ops.head_convt2x2(x.t, w_packed, bias, classes, True, False, torch.float32)
+    holder = {}
+
+    def bwd():
+        dl = holder["dlogits"]
+        n, c, h, w = dl.shape
+        dy = ops.new_act(n, c, h, w, x.t.dtype, dl.device, c_alloc=(c + 7) // 8 * 8, zero=True)
+        a, b = ops.tdesc(dl), ops.tdesc(dy)
+        a.layout, a.c_stride = L.ESN_NCHW, 0
+        ops._call(L.lib.esn_convert_layout, "esn_convert_layout", (C.byref(a), C.byref(b)), ops._nbytes(dl) + ops._nbytes(dy))
+        convt.backward_from(tape, x, dy)
+    tape.push(bwd)
+    return logits, holder
+
+
 # --------------------------------------------------------------------------- BatchNorm (+ activation)
 class BNActT:
     """Train-mode nn.BatchNorm2d followed by PReLU / ReLU / nothing; or, with bn=None, the
@@ -287,10 +360,12 @@ def add(tape, a, b, out=None):
     return y
 
 
-def maxpool2x2(tape, x, out):
+def maxpool2x2(tape, x, out, need_dx=True):
     """MaxPool2d(2,2) of x written into `out` (a channel slice of a concat buffer)."""
     y = out
     ops.maxpool2x2(x.t, out.t)
+    if not need_dx:          # the network input: no gradient wanted
+        return y
 
     def bwd():
         dy = y.g

@@ -195,6 +195,12 @@ class ERFNet(nn.Module):
 
     def forward(self, input, only_encode=False):
         ops.require_cuda(input, "ERFNet")
+        if self.training and not only_encode:
+            # batch-statistics BatchNorm + Dropout2d + recorded backward (esn/train.py); one autograd node for the net.
+            # encoder.output_conv takes no part (ERFNet.py:88-89: predict=False), so it gets no gradient -- as in the reference.
+            from esn import train as T
+            from model._erfnet_train import erfnet_train_forward
+            return T.run_network(self, lambda inp: erfnet_train_forward(self, inp), input)
         if only_encode:
             return self.encoder.forward(input, predict=True)
         output = self.encoder(input)

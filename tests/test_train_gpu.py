@@ -174,7 +174,7 @@ def _train_step(name, spec, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("net", ["DABNet", "FastSCNN", "ESPNet_v2"])
+@pytest.mark.parametrize("net", ["DABNet", "FastSCNN", "ESPNet_v2", "ERFNet"])
 def test_training_matches_reference_fp64(spec, golden, dtype, net):
     """loss / logits / every parameter gradient against the reference's fp64 run (tests/golden; dropout off)."""
     g = golden(net)
@@ -198,6 +198,15 @@ def test_training_matches_reference_fp64(spec, golden, dtype, net):
         print("   torch bf16-autocast of the same graph: logits rel-L2 %.3e, loss error %.3e" % (r_log, r_loss))
         logit_tol = max(logit_tol, 1.5 * r_log)
         ltol = max(ltol, 1.5 * r_loss)
+    else:
+        # fp32 noise floor of this graph against the fp64 golden: the oracle port run in fp32 on the CPU (deep nets with
+        # batch-statistics BatchNorm -- ERFNet's 23 blocks -- sit at a few 1e-4, above the 1e-4 the shallow nets meet)
+        from oracle import nets
+        with torch.no_grad():
+            y32 = nets.forward(net, spec_state_dict(spec, net), fixture.make_input(2, 64, 128), train=True)
+        r_log = _rel(y32[:, :, ::4, ::4], ref)
+        print("   oracle in fp32 (CPU) vs the fp64 golden: logits rel-L2 %.3e" % r_log)
+        logit_tol = max(logit_tol, 3.0 * r_log)
     assert abs(loss.item() - ref_loss) / ref_loss < ltol, (loss.item(), ref_loss)
     assert _rel(out.detach().float().cpu()[:, :, ::4, ::4], ref) < logit_tol
     stats = json.loads(bytes(g["train_2x64x128_gradstats"]).decode())
@@ -214,12 +223,21 @@ def test_training_matches_reference_fp64(spec, golden, dtype, net):
           % (net, dtype, loss.item(), ref_loss, med, p90, worst, len(errs)))
     if dtype == torch.float32:
         assert worst < gtol, worst
+        # full tensors: fp32-vs-fp64 noise grows with depth -- torch's own fp32 autograd of the same graph is
+        # 3e-2 off on ERFNet's first conv -- so the bound is 2e-2 or twice what torch fp32 shows for that tensor
+        from oracle import nets
+        sd32 = {k: (v.cuda().requires_grad_(True) if v.is_floating_point() else v.cuda())
+                for k, v in spec_state_dict(spec, net).items()}
+        y32 = nets.forward(net, sd32, fixture.make_input(2, 64, 128).cuda(), train=True)
+        F.cross_entropy(y32, fixture.make_labels(2, 64, 128, 19).cuda(), torch.tensor(fixture.CLASS_WEIGHTS, device="cuda"),
+                        ignore_index=255).backward()
         for key in g.files:
             if key.startswith("train_2x64x128_grad::"):
                 k = key.split("::")[1]
-                err = _rel(named[k].grad.cpu(), torch.from_numpy(g[key]))
-                print("   full-tensor rel-L2 %-50s %.3e" % (k, err))
-                assert err < gtol, (k, err)
+                gold = torch.from_numpy(g[key])
+                err, err_t = _rel(named[k].grad.cpu(), gold), _rel(sd32[k].grad.cpu(), gold)
+                print("   full-tensor rel-L2 %-50s %.3e   (torch fp32 autograd: %.3e)" % (k, err, err_t))
+                assert err < max(gtol, 2.0 * err_t), (k, err, err_t)
         return
     # bf16: the tolerance is the reference's own bf16 noise.  Run the reference arithmetic (oracle port)
     # under torch bf16 autocast on the same fixture and require our error distribution to be no worse.
