@@ -40,6 +40,7 @@ WORKLOADS = {
     "espnetv2_infer_bf16_b16_1024x2048": ("ESPNet_v2", 16, 1024, 2048, "infer"),
     # BASELINE.json configs[2]: DABNet bf16 training, batch 8/GPU, 512x1024, weighted CE, Adam, data parallel
     "dabnet_train_bf16_b8_512x1024": ("DABNet", 8, 512, 1024, "train"),
+    "erfnet_train_bf16_b8_512x1024": ("ERFNet", 8, 512, 1024, "train"),
     # BASELINE.json configs[4] (first half): Fast-SCNN bf16 training, batch 16/GPU, 1024x2048
     "fastscnn_train_bf16_b16_1024x2048": ("FastSCNN", 16, 1024, 2048, "train"),
     "espnetv2_train_bf16_b16_1024x2048": ("ESPNet_v2", 16, 1024, 2048, "train"),

@@ -707,8 +707,17 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   a.mode = MODE_GENERIC;
   if (rowable && p->kh == 1 && p->kw >= 2 && (p->kw - 1) * p->dil_w <= 256)
     a.mode = MODE_HREUSE;
-  else if (rowable && p->kh >= 2 && nkb == 1 && (p->kw - 1) * p->dil_w <= 64 && !getenv("ESN_UMMA_NOHV") )
-    a.mode = MODE_VREUSE;     // k x 1, and k_h x k_w (3x3): row ring x shifted windows, every input row loaded once
+  else if (rowable && p->kh >= 2 && nkb == 1 && (p->kw - 1) * p->dil_w <= 64 && !getenv("ESN_UMMA_NOHV")) {
+    // k x 1, and k_h x k_w (3x3): row ring x shifted windows, every input row loaded once -- if the ring (k_h + 1
+    // row windows) fits next to the resident weights and one staging tile; otherwise one box per tap (generic)
+    int mt = MT;
+    while (mt > 1 && mt * kTileM > gw) mt >>= 1;
+    const uint32_t stage = ((uint32_t)(mt * kTileM + (p->kw - 1) * p->dil_w) * (uint32_t)(KB * 2) + 1023u) & ~1023u;
+    const uint32_t wreg = ((uint32_t)ntaps_all * N * KB * 2 + 1023u) & ~1023u;
+    const bool stg = (Cout % 8 == 0) && (Cout <= 64 || Cout % 64 == 0);
+    const uint32_t need = wreg + (uint32_t)(p->kh + 1) * stage + (stg ? (uint32_t)mt * kTileM * Cout * 2 : 0u) + 3072u + 512u + 1024u;
+    if (need <= (uint32_t)lim.max_smem) a.mode = MODE_VREUSE;
+  }
   if (a.mode != MODE_GENERIC) {
     if (a.mode == MODE_HREUSE && KB == 64 && nkb == 1 && N <= 64) MT = 2;   // 256-pixel row tiles for C=64
     while (MT > 1 && MT * kTileM > gw) MT >>= 1;

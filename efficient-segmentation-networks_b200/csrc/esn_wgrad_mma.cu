@@ -23,7 +23,7 @@ struct WgMmaArgs {
   long long px_per_cta;
 };
 
-constexpr int kKT = 32;       // pixels per smem stage
+constexpr int kKT = 64;       // pixels per smem stage
 constexpr int kWgThreads = 256;
 
 // CO_T x CI_T output tile per CTA (multiples of 16), one filter tap per blockIdx.y
@@ -46,49 +46,75 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_mma_kernel(const WgMmaArgs a
   const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(M, p0 + a.px_per_cta);
   const bool va = (a.dy_cs % 8 == 0) && (co0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.dy) & 15) == 0);
   const bool vb = (a.x_cs % 8 == 0) && (ci0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
-  for (long long pb = p0; pb < p1; pb += kKT) {
-    // ---- stage kKT pixels: dY[p, co0..co0+CO_T) and X[p+delta, ci0..ci0+CI_T), 8 channels per thread-iteration
-    for (int e = threadIdx.x; e < kKT * (CO_T / 8); e += kWgThreads) {
-      const int pp = e / (CO_T / 8), c8 = (e % (CO_T / 8)) * 8;
-      const long long p = pb + pp;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (p < p1) {
-        const __nv_bfloat16* src = a.dy + p * a.dy_cs + co0 + c8;
-        if (va && co0 + c8 + 8 <= a.Cout) {
-          v = __ldg(reinterpret_cast<const uint4*>(src));
-        } else {
-          __nv_bfloat16 t[8];
+  // Software pipeline: the global loads of pixel block k+1 are issued into registers before the MMAs of block k,
+  // so their latency hides behind the tensor work (one __syncthreads pair per block as before).
+  constexpr int EA = (kKT * (CO_T / 8) + kWgThreads - 1) / kWgThreads;
+  constexpr int EB = (kKT * (CI_T / 8) + kWgThreads - 1) / kWgThreads;
+  uint4 ra[EA], rb[EB];
+  auto fetch = [&](const long long pb) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = (co0 + c8 + j < a.Cout) ? src[j] : __float2bfloat16(0.f);
-          v = *reinterpret_cast<uint4*>(t);
-        }
-      }
-      *reinterpret_cast<uint4*>(&sA[pp][c8]) = v;
-    }
-    for (int e = threadIdx.x; e < kKT * (CI_T / 8); e += kWgThreads) {
-      const int pp = e / (CI_T / 8), c8 = (e % (CI_T / 8)) * 8;
-      const long long p = pb + pp;
+    for (int i = 0; i < EA; ++i) {
+      const int e = threadIdx.x + i * kWgThreads;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (p < p1) {
-        const int wo = (int)(p % a.Wo);
-        const int ho = (int)((p / a.Wo) % a.Ho);
-        const int n = (int)(p / ((long long)a.Wo * a.Ho));
-        const int hi = ho * a.stride - a.pad_h + r * a.dil_h, wi = wo * a.stride - a.pad_w + s * a.dil_w;
-        if (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) {
-          const __nv_bfloat16* src = a.x + ((size_t)((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs + ci0 + c8;
-          if (vb && ci0 + c8 + 8 <= a.Cin) {
+      if (e < kKT * (CO_T / 8)) {
+        const int pp = e / (CO_T / 8), c8 = (e % (CO_T / 8)) * 8;
+        const long long p = pb + pp;
+        if (p < p1) {
+          const __nv_bfloat16* src = a.dy + p * a.dy_cs + co0 + c8;
+          if (va && co0 + c8 + 8 <= a.Cout) {
             v = __ldg(reinterpret_cast<const uint4*>(src));
           } else {
             __nv_bfloat16 t[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = (ci0 + c8 + j < a.Cin) ? src[j] : __float2bfloat16(0.f);
+            for (int j = 0; j < 8; ++j) t[j] = (co0 + c8 + j < a.Cout) ? src[j] : __float2bfloat16(0.f);
             v = *reinterpret_cast<uint4*>(t);
           }
         }
       }
-      *reinterpret_cast<uint4*>(&sB[pp][c8]) = v;
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      const int e = threadIdx.x + i * kWgThreads;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (e < kKT * (CI_T / 8)) {
+        const int pp = e / (CI_T / 8), c8 = (e % (CI_T / 8)) * 8;
+        const long long p = pb + pp;
+        if (p < p1) {
+          const int wo = (int)(p % a.Wo);
+          const int ho = (int)((p / a.Wo) % a.Ho);
+          const int n = (int)(p / ((long long)a.Wo * a.Ho));
+          const int hi = ho * a.stride - a.pad_h + r * a.dil_h, wi = wo * a.stride - a.pad_w + s * a.dil_w;
+          if (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) {
+            const __nv_bfloat16* src = a.x + ((size_t)((size_t)n * a.Hi + hi) * a.Wi + wi) * a.x_cs + ci0 + c8;
+            if (vb && ci0 + c8 + 8 <= a.Cin) {
+              v = __ldg(reinterpret_cast<const uint4*>(src));
+            } else {
+              __nv_bfloat16 t[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) t[j] = (ci0 + c8 + j < a.Cin) ? src[j] : __float2bfloat16(0.f);
+              v = *reinterpret_cast<uint4*>(t);
+            }
+          }
+        }
+      }
+      rb[i] = v;
+    }
+  };
+  if (p0 < p1) fetch(p0);
+  for (long long pb = p0; pb < p1; pb += kKT) {
+#pragma unroll
+    for (int i = 0; i < EA; ++i) {
+      const int e = threadIdx.x + i * kWgThreads;
+      if (e < kKT * (CO_T / 8)) *reinterpret_cast<uint4*>(&sA[e / (CO_T / 8)][(e % (CO_T / 8)) * 8]) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      const int e = threadIdx.x + i * kWgThreads;
+      if (e < kKT * (CI_T / 8)) *reinterpret_cast<uint4*>(&sB[e / (CI_T / 8)][(e % (CI_T / 8)) * 8]) = rb[i];
     }
     __syncthreads();
+    if (pb + kKT < p1) fetch(pb + kKT);
 #pragma unroll
     for (int kk = 0; kk < kKT; kk += 16) {
 #pragma unroll

@@ -48,6 +48,7 @@ CASES = [
     ("hv_3x3_16_48_w512", 16, 48, 3, 1, 1, 1, False, 0, 1, 9, 512),
     ("hv_3x3_64_64_d2_w200", 64, 64, 3, 1, 2, 2, False, 0, 2, 21, 200),
     ("hv_3x3_32_d16_w256", 32, 32, 3, 1, 16, 16, False, 0, 1, 40, 256),
+    ("hv_fallback_3x3_64_128_w256", 64, 128, 3, 1, 1, 1, False, 0, 1, 10, 256),   # ring + 147 KB of weights do not fit: generic mode
 ]
 
 
