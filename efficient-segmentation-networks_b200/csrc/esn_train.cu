@@ -436,6 +436,55 @@ struct WgradArgs {
 
 constexpr int kWgPix = 16;
 
+// Network stem (NCHW fp32 image, Cin = 3, 3x3, Cout <= 32): lane = output channel, 27 accumulators per lane.  A warp
+// walks output pixels: the 27 image values of a pixel are warp-uniform (broadcast) loads, dY is one coalesced load.
+template <typename TG>
+__global__ void __launch_bounds__(256) wgrad_stem_kernel(const WgradArgs a) {
+  __shared__ float red[8][27][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long M = (long long)a.N * a.Ho * a.Wo;
+  const long long p0 = blockIdx.x * a.px_per_cta, p1 = min(M, p0 + a.px_per_cta);
+  const float* x = reinterpret_cast<const float*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy);
+  const size_t plane = (size_t)a.Hi * a.Wi;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  const bool act = lane < a.Cout;
+  for (long long p = p0 + warp; p < p1; p += 8) {
+    const int wo = (int)(p % a.Wo);
+    const int ho = (int)((p / a.Wo) % a.Ho);
+    const int n = (int)(p / ((long long)a.Wo * a.Ho));
+    const float g = act ? ld1<TG>(dy + (size_t)p * a.dy_cs + lane) : 0.f;
+    const float* xn = x + (size_t)n * 3 * plane;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = ho * a.stride - a.pad_h + r * a.dil_h;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int wi = wo * a.stride - a.pad_w + q * a.dil_w;
+        if (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) {
+          const size_t o = (size_t)hi * a.Wi + wi;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) acc[(r * 3 + q) * 3 + ci] = fmaf(__ldg(xn + ci * plane + o), g, acc[(r * 3 + q) * 3 + ci]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 27; ++t) red[warp][t][lane] = acc[t];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 27 * 32; e += 256) {
+    const int t = e >> 5, co = e & 31;
+    if (co < a.Cout) {
+      float v = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) v += red[wv][t][co];
+      atomicAdd(a.dw + (size_t)t * a.Cout + co, v);     // t = (tap*3 + ci): the [tap][Cin][Cout] layout
+    }
+  }
+}
+
 // Tiny dense convs (taps*Cin*Cout <= 128: ESPNetv2's 8->6 grouped slices and 3->3 input-reinforcement conv):
 // one thread per weight element, walking a pixel strip; the few channels of a pixel are L1 broadcasts.
 template <typename TX, typename TG>
@@ -823,6 +872,12 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
     else if (xf) wgrad_dw_kernel<float, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
     else if (gf) wgrad_dw_kernel<__nv_bfloat16, float><<<grid, kStatThreads, 0, st>>>(a);
     else wgrad_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+  } else if (nchw && x.c == 3 && p->kh == 3 && p->kw == 3 && dy.c <= 32) {
+    a.px_per_cta = (M + 148 * 8 - 1) / (148 * 8);
+    if (a.px_per_cta < 256) a.px_per_cta = 256;
+    const int grid = esn_cdiv(M, a.px_per_cta);
+    if (gf) wgrad_stem_kernel<float><<<grid, 256, 0, st>>>(a);
+    else wgrad_stem_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
   } else if (taps * x.c * dy.c <= 128) {
     a.px_per_cta = (M + 148 * 16 - 1) / (148 * 16);
     if (a.px_per_cta < 64) a.px_per_cta = 64;

@@ -13,10 +13,18 @@ __global__ void __launch_bounds__(128) bilinear_bwd2_kernel(const TG* __restrict
   const long long total = (long long)N * Hi * Wi * C;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % C);
-  const int w = (int)((idx / C) % Wi);
-  const int h = (int)((idx / ((long long)C * Wi)) % Hi);
-  const int n = (int)(idx / ((long long)C * Wi * Hi));
+  int c, w, h, n;
+  if (dy_nchw) {      // upstream gradient in class planes: consecutive threads walk along w (coalesced plane reads)
+    w = (int)(idx % Wi);
+    h = (int)((idx / Wi) % Hi);
+    c = (int)((idx / ((long long)Wi * Hi)) % C);
+    n = (int)(idx / ((long long)Wi * Hi * C));
+  } else {
+    c = (int)(idx % C);
+    w = (int)((idx / C) % Wi);
+    h = (int)((idx / ((long long)C * Wi)) % Hi);
+    n = (int)(idx / ((long long)C * Wi * Hi));
+  }
   // candidate outputs: source index within (h-1, h+1)
   const float rh = sh > 0.f ? 1.f / sh : 0.f, rw = sw > 0.f ? 1.f / sw : 0.f;
   const float off = align ? 0.f : 0.5f;

@@ -132,7 +132,15 @@ class ConvT:
             ho, wo = fwd_prep.out_hw(h, w)
             out = ops.new_act(n, fwd_prep.cout, ho, wo, dtype or (xt.dtype if ops.is_nhwc(xt) else torch.float32), xt.device)
         y = out if isinstance(out, V) else V(out)      # `out` may be a channel slice (V) of a concat buffer
-        ops.conv2d(xt, fwd_prep, out=y.t, residual=None if residual is None else residual.t)
+        if (not ops.is_nhwc(xt) and xt.dtype == torch.float32 and xt.is_contiguous() and fwd_prep.cin == 3 and residual is None
+                and (fwd_prep.kh, fwd_prep.kw, fwd_prep.stride) == (3, 3, 2) and (fwd_prep.pad_h, fwd_prep.pad_w) in ((0, 0), (1, 1))
+                and fwd_prep.cout % 4 == 0 and fwd_prep.cout <= 32 and y.t.shape[1] == fwd_prep.cout and y.t.stride(3) % 4 == 0
+                and (fwd_prep.pad_h == 0 or not ((xt.shape[2] | xt.shape[3]) & 1))):
+            # network stem on the NCHW image: the dedicated kernel (bias as the epilogue shift)
+            ops.stem_conv3x3s2(xt, fwd_prep.w_direct, fwd_prep.cout, 256 if fwd_prep.pad_h == 0 else 0, y.t,
+                               fwd_prep.scale, fwd_prep.shift, None, L.ACT_NONE)
+        else:
+            ops.conv2d(xt, fwd_prep, out=y.t, residual=None if residual is None else residual.t)
         conv = self.conv
 
         def bwd():
@@ -143,7 +151,9 @@ class ConvT:
             dwbuf = torch.zeros((kh * kw, cin_g, fwd_prep.cout), dtype=torch.float32, device=dy.device)
             p = L.EsnConv()
             xw = xt
-            if not ops.is_nhwc(xt) and dy.dtype == torch.bfloat16 and fwd_prep.groups == 1 and fwd_prep.cin < 8:
+            stem = (not ops.is_nhwc(xt) and fwd_prep.cin == 3 and (kh, kw) == (3, 3) and fwd_prep.cout <= 32
+                    and xt.dtype == torch.float32)          # esn_conv2d_wgrad has a kernel for the NCHW fp32 image
+            if not stem and not ops.is_nhwc(xt) and dy.dtype == torch.bfloat16 and fwd_prep.groups == 1 and fwd_prep.cin < 8:
                 # network stem (NCHW fp32 image, Cin=3): give the tensor-core wgrad an NHWC bf16 copy
                 # padded to 8 channels; the padded rows of dW are dropped below
                 n_, c_, h_, w_ = xt.shape
