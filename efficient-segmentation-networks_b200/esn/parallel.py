@@ -46,19 +46,40 @@ class GradBuckets:
         self.pending = [len(b) for b in self.buckets]
         self.seen = set()
         self.works = []
+        self.staged = [dict() for _ in self.buckets]     # parameter -> gradient waiting to be packed
 
     def grad_ready(self, p, g):
-        """Called by the tape when parameter p's gradient is final: copy into the flat bucket and
-        launch the bucket's all-reduce once it is full.  Returns the bucket view (the gradient)."""
+        """Called by the tape when parameter p's gradient is final.  The copy into the flat bucket is deferred until
+        the bucket is complete and then done with ONE multi-tensor copy for all dense gradients (a few hundred tiny
+        copy kernels per step otherwise), followed by the bucket's all-reduce.  Returns the bucket view (the gradient;
+        valid once the tape's backward has finished)."""
         i = self.bucket_of[p]
         view = self.views[i][p]
-        view.copy_(g)
+        self.staged[i][p] = g          # a second contribution replaces the first (the tape has already summed them)
         if p not in self.seen:
             self.seen.add(p)
             self.pending[i] -= 1
             if self.pending[i] == 0:
+                self._pack(i)
                 self._launch(i)
+        elif self.pending[i] == 0:        # bucket already reduced: late extra contribution (not on the hot-path nets)
+            raise RuntimeError("gradient for %r arrived after its bucket was all-reduced" % (tuple(p.shape),))
         return view
+
+    def _pack(self, i):
+        dense_v, dense_g = [], []
+        for p, g in self.staged[i].items():
+            v = self.views[i][p]
+            if g is v:
+                continue
+            if g.dtype == v.dtype and g.is_contiguous() and g.shape == v.shape:
+                dense_v.append(v)
+                dense_g.append(g)
+            else:
+                v.copy_(g)
+        if dense_v:
+            torch._foreach_copy_(dense_v, dense_g)
+        self.staged[i] = dict()
 
     def _launch(self, i):
         if self.world == 1:
@@ -77,6 +98,7 @@ class GradBuckets:
                 for p in b:
                     if p not in self.seen:
                         self.views[i][p].zero_()
+                self._pack(i)
                 self.pending[i] = 0
                 self._launch(i)
         for w in self.works:

@@ -65,7 +65,10 @@ class Tape:
     def add_param_grad(self, p, g):
         g = g.to(p.dtype) if g.dtype != p.dtype else g
         if p in self.param_grads:
-            g = self.param_grads[p] + g
+            prev = self.param_grads[p]
+            if self.buckets is not None:       # the bucket view is only filled when its bucket is packed
+                prev = self.buckets.staged[self.buckets.bucket_of[p]].get(p, prev)
+            g = prev + g
         # every parameter of the hot-path nets is used exactly once per step, so its gradient is final
         # here: hand it to the data-parallel buckets (flat copy + all-reduce launch, overlapped)
         self.param_grads[p] = self.buckets.grad_ready(p, g) if self.buckets is not None else g
