@@ -26,6 +26,8 @@ struct alignas(64) UmmaArgs {
   CUtensorMap tmAh;  // activations, 5-D, tail box of the horizontal-reuse window
   CUtensorMap tmB;   // weights, 2-D
   CUtensorMap tmY;   // output, 4-D   (staged epilogue only)
+  CUtensorMap tmY2;  // phase-fused transposed conv: output rows 2i+1 (tmY: rows 2i)
+
   CUtensorMap tmR;   // residual, 4-D (staged epilogue with residual only)
   int mode, nunits;
   int g_dw, g_dh, g_dn;              // MODE_GENERIC: (tw, th, n) increment of one grid stride (interleaved tiles)
@@ -41,6 +43,7 @@ struct alignas(64) UmmaArgs {
   int Hy, Wy, y_cs, sy, oy, sx, ox;
   EpiArgs ep;
   int staged, has_res, stages, NS, NA;   // NS staging buffers, NA TMEM accumulator buffers
+  int shuf_bpa;                      // phase-fused transposed conv: column blocks per output-row parity (0 = off)
   int cbo, ncb;                      // staged epilogue: channels per 128B-wide column block, #blocks
   uint32_t load_bytes, stage_bytes, wblock_bytes, w_region_bytes, out_block_bytes, out_buf_bytes, out_swz_mask;
   uint32_t idesc, desc_hi;           // instruction descriptor; upper 32 bits of the smem descriptors
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     tma_prefetch_desc(&a.tmB);
     if (MODE == MODE_HREUSE || (MODE == MODE_VREUSE && a.vr_kw > 1)) tma_prefetch_desc(&a.tmAh);
     if (a.staged) tma_prefetch_desc(&a.tmY);
+    if (a.staged && a.shuf_bpa) tma_prefetch_desc(&a.tmY2);
     if (a.has_res && a.staged) tma_prefetch_desc(&a.tmR);
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8u * s, 1);
@@ -384,7 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : (NS == 2 ? 1u : 0u);
     const int staged = a.staged, has_res = a.has_res, act = a.ep.act, cout = a.cout;
     const uint32_t swz = a.out_swz_mask;
-    const bool wide = a.cbo == 64 && a.ncb > 1;  // column blocks of 64 channels
+    const bool wide = a.ncb > 1;                 // several column blocks of cbo (16 / 32 / 64) channels
+    const int cbo_shift = a.cbo == 64 ? 6 : (a.cbo == 32 ? 5 : 4);
     // this thread's work items: (sub-tile m, 16-column chunk) pairs dealt round-robin to the 4 warps of a quadrant
     int nitems = 0, it_c0[4] = {0, 0, 0, 0};
     uint32_t it_toff[4] = {0, 0, 0, 0}, it_soff[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
@@ -398,8 +403,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int R = m * kTileM + q * 32 + lane;
         for (int h = 0; h < 2; ++h) {
           const int cb8 = c0 + 8 * h;
-          const int blk = wide ? (cb8 >> 6) : 0;
-          const int cin_blk = wide ? (cb8 & 63) : cb8;
+          const int blk = wide ? (cb8 >> cbo_shift) : 0;
+          const int cin_blk = wide ? (cb8 & (a.cbo - 1)) : cb8;
           uint32_t off = (uint32_t)R * row_bytes + (uint32_t)cin_blk * 2u;
           off ^= ((off >> 7) & swz) << 4;
           it_soff[nitems][h] = (uint32_t)blk * a.out_block_bytes + off;
@@ -514,8 +519,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     f[7] = fmaf(__uint_as_float(r[8 * h + 7]), s1.w, h1.w);
                   }
                   if (staged) {
-                    const int blk = wide ? (cb8 >> 6) : 0;
-                    const int cin_blk = wide ? (cb8 & 63) : cb8;
+                    const int blk = wide ? (cb8 >> cbo_shift) : 0;
+                    const int cin_blk = wide ? (cb8 & (a.cbo - 1)) : cb8;
                     uint32_t off = (uint32_t)R * row_bytes + (uint32_t)cin_blk * 2u;
                     off ^= ((off >> 7) & swz) << 4;
                     const uint32_t saddr = obuf + (uint32_t)blk * a.out_block_bytes + off;
@@ -585,10 +590,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           fence_proxy_async();          // my st.shared writes -> visible to the TMA (async proxy)
           epi_bar_sync();
           if (threadIdx.x == kEpiWarp0 * 32) {
-            for (int cb = 0; cb < a.ncb; ++cb)
+            for (int cb = 0; cb < a.ncb; ++cb) {
+              // phase-fused transposed conv: column blocks [0, bpa) are output rows 2i, [bpa, 2 bpa) rows 2i+1
+              const bool odd = a.shuf_bpa && cb >= a.shuf_bpa;
+              const int cc = (a.shuf_bpa ? (cb - (odd ? a.shuf_bpa : 0)) : cb) * a.cbo;
               for (int qb = 0; qb < a.o_nbox; ++qb)
-                tma_store_4d(&a.tmY, obuf + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
-                             cb * a.cbo, un.w0 + qb * a.o_boxw, th0, un.n);
+                tma_store_4d(odd ? &a.tmY2 : &a.tmY, obuf + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
+                             cc, un.w0 + qb * a.o_boxw, th0, un.n);
+            }
             tma_store_commit();
             // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
             if (NS == 4) tma_store_wait_read<3>(); else if (NS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
@@ -645,7 +654,9 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   if (res.ptr && res.dtype != ESN_BF16) return ESN_ERR_UNSUPPORTED;
   int rc = esn_check_epilogue(p->ep, y);
   if (rc) return rc;
-  const int Cin = x.c, Cout = y.c, N = p->cout_pad;
+  const bool fused = p->transposed == 2;   // phase-fused ConvTranspose2d(3, s2, p1, op1): 2x2 taps, 4*C outputs, pixel-shuffle store
+  const bool tr = p->transposed == 1;
+  const int Cin = x.c, Cout = fused ? 4 * y.c : y.c, N = p->cout_pad;
   if (N % 16 || N < 16 || N > 256 || N < Cout) return ESN_ERR_UNSUPPORTED;
   int KB;
   if (Cin == 16 || Cin == 32 || Cin == 64)
@@ -663,8 +674,12 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   const int ntaps_all = p->kh * p->kw;
   if (ntaps_all > kMaxTaps) return ESN_ERR_UNSUPPORTED;
   if (p->stride != 1 && p->stride != 2) return ESN_ERR_UNSUPPORTED;
-  if (p->transposed && (p->stride != 2 || p->dil_h != 1 || p->dil_w != 1)) return ESN_ERR_UNSUPPORTED;
-  if (!p->transposed) {
+  if (tr && (p->stride != 2 || p->dil_h != 1 || p->dil_w != 1)) return ESN_ERR_UNSUPPORTED;
+  if (fused) {
+    if (p->kh != 2 || p->kw != 2 || p->stride != 1 || p->pad_h || p->pad_w || p->dil_h != 1 || p->dil_w != 1 || res.ptr ||
+        y.h != 2 * x.h || y.w != 2 * x.w || y.c_stride != y.c || N != Cout || (y.c != 8 && y.c != 16 && y.c != 32 && y.c != 64))
+      return ESN_ERR_UNSUPPORTED;
+  } else if (!tr) {
     const int eh = (x.h + 2 * p->pad_h - p->dil_h * (p->kh - 1) - 1) / p->stride + 1;
     const int ew = (x.w + 2 * p->pad_w - p->dil_w * (p->kw - 1) - 1) / p->stride + 1;
     if (eh != y.h || ew != y.w) return ESN_ERR_BAD_SHAPE;
@@ -692,7 +707,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   a.cout = Cout;
 
   // iteration grid: output positions (conv) or input positions (one transposed-conv phase)
-  const int gh = p->transposed ? x.h : y.h, gw = p->transposed ? x.w : y.w;
+  const int gh = (tr || fused) ? x.h : y.h, gw = (tr || fused) ? x.w : y.w;
   a.gh = gh;
   a.gw = gw;
 
@@ -703,7 +718,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
 
   // ---- mode: tap reuse needs row tiles (one image row segment per tile)
   static const bool no_reuse = getenv("ESN_UMMA_NOREUSE") != nullptr;
-  const bool rowable = !no_reuse && gw >= 128 && !p->transposed && p->stride == 1;
+  const bool rowable = !no_reuse && gw >= 128 && !tr && p->stride == 1;
   a.mode = MODE_GENERIC;
   if (rowable && p->kh == 1 && p->kw >= 2 && (p->kw - 1) * p->dil_w <= 256)
     a.mode = MODE_HREUSE;
@@ -789,7 +804,9 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   CUtensorMapSwizzle oswz = CU_TENSOR_MAP_SWIZZLE_NONE;
   if (a.staged) {
     a.cbo = Cout <= 64 ? Cout : 64;
+    if (fused) a.cbo = 2 * y.c <= 64 ? 2 * y.c : 64;      // one column block never straddles the two output-row parities
     a.ncb = Cout / a.cbo;
+    a.shuf_bpa = fused ? (2 * y.c) / a.cbo : 0;
     a.out_block_bytes = (uint32_t)rows * a.cbo * 2;
     a.out_buf_bytes = a.ncb * a.out_block_bytes;
     const int rb = a.cbo * 2;
@@ -799,6 +816,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     else { a.out_swz_mask = 0; }
     a.NS = a.out_buf_bytes <= 16384 ? 4 : 2;
   } else {
+    if (fused) return ESN_ERR_UNSUPPORTED;
     a.cbo = 8;  // unused
     a.NS = 0;
   }
@@ -807,7 +825,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   for (int which = 0; which < ((a.mode == MODE_HREUSE || (a.mode == MODE_VREUSE && p->kw > 1)) ? 2 : 1); ++which) {
     const cuuint64_t cs = (cuuint64_t)x.c_stride;
     cuuint64_t dims[5], strides[4];
-    if (!p->transposed && p->stride == 2) {
+    if (!tr && p->stride == 2) {
       dims[0] = 2 * cs; dims[1] = x.w / 2; dims[2] = 2; dims[3] = x.h / 2; dims[4] = x.n;
       strides[0] = 2 * cs * 2; strides[1] = (cuuint64_t)x.w * cs * 2; strides[2] = 2 * (cuuint64_t)x.w * cs * 2;
       strides[3] = (cuuint64_t)x.h * x.w * cs * 2;
@@ -837,14 +855,14 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nphase = p->transposed ? 4 : 1;
+  const int nphase = tr ? 4 : 1;
   for (int ph = 0; ph < nphase; ++ph) {
     const int pa = ph >> 1, pb = ph & 1;
     int nt = 0;
     for (int r = 0; r < p->kh; ++r)
       for (int s = 0; s < p->kw; ++s) {
         int dy, dx, par = 0, coff = 0;
-        if (p->transposed) {
+        if (tr) {
           const int th = pa + p->pad_h - r, tw = pb + p->pad_w - s;
           if ((th & 1) || (tw & 1)) continue;
           dy = floordiv2(th);
@@ -869,12 +887,26 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
       }
     if (nt == 0) return ESN_ERR_UNSUPPORTED;  // a phase with no taps would need a bias-only fill
     a.ntaps = nt;
-    a.sy = p->transposed ? 2 : 1;
+    a.sy = tr ? 2 : 1;
     a.sx = a.sy;
-    a.oy = p->transposed ? pa : 0;
-    a.ox = p->transposed ? pb : 0;
+    a.oy = tr ? pa : 0;
+    a.ox = tr ? pb : 0;
 
-    if (a.staged) {  // output / residual maps over this phase's (strided) output positions
+    if (a.staged && fused) {
+      // output seen as (2C, W, H, N) per output-row parity: y[2i+a][2j+b][c] = D[i][j][(a, b, c)]
+      for (int par2 = 0; par2 < 2; ++par2) {
+        const cuuint64_t C2 = 2 * (cuuint64_t)y.c;
+        const cuuint64_t dims[4] = {C2, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)x.n};
+        const cuuint64_t strides[3] = {C2 * 2, 2 * (cuuint64_t)y.w * y.c * 2, (cuuint64_t)y.h * y.w * y.c * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)a.cbo, (cuuint32_t)a.o_boxw, (cuuint32_t)a.bh, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        void* bp = reinterpret_cast<uint8_t*>(y.ptr) + (size_t)par2 * y.w * y.c * 2;
+        if (encode(par2 ? &a.tmY2 : &a.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bp, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return ESN_ERR_CUDA;
+      }
+    } else if (a.staged) {  // output / residual maps over this phase's (strided) output positions
       for (int which = 0; which < (a.has_res ? 2 : 1); ++which) {
         const EsnTensor& t = which ? res : y;
         const cuuint64_t cs = (cuuint64_t)t.c_stride;

@@ -15,6 +15,7 @@ _DT = {torch.float32: L.ESN_F32, torch.bfloat16: L.ESN_BF16, torch.uint8: L.ESN_
 _NULL = L.EsnTensor()
 UMMA_ENABLED = os.environ.get("ESN_DISABLE_UMMA", "0") != "1"
 PAIR_DISABLED = os.environ.get("ESN_DISABLE_PAIR", "0") == "1"
+CONVT_FUSED = os.environ.get("ESN_DISABLE_FUSED_CONVT", "0") != "1"
 
 
 def stream():
@@ -297,6 +298,26 @@ class ConvPrep:
             self._w_umma_s = p.contiguous()
         return self._w_umma_s
 
+    def fused_convt(self):
+        """ConvTranspose2d(3, stride 2, pad 1, output_padding 1) as ONE stride-1 conv with 2x2 taps and 4*Cout outputs
+        ordered (row parity a, column parity b, c): out[2i+a, 2j+b, c] = sum_{dy,dx} x[i+dy, j+dx] . w[a+1-2dy, b+1-2dx]
+        (taps outside 0..2 are zero blocks).  The kernel stores the two row parities through pixel-shuffle tensor maps."""
+        if getattr(self, "_fused", None) is None:
+            w = self._w_src                      # (Cout, Cin, 3, 3) (already transposed from the module's (Cin, Cout, 3, 3))
+            co, ci = w.shape[0], w.shape[1]
+            f = torch.zeros((2, 2, 2, 2, co, ci), dtype=torch.float32, device=w.device)      # [dy][dx][a][b][c][ci]
+            for dy in range(2):
+                for dx in range(2):
+                    for a in range(2):
+                        for b in range(2):
+                            r, q = a + 1 - 2 * dy, b + 1 - 2 * dx
+                            if 0 <= r <= 2 and 0 <= q <= 2:
+                                f[dy, dx, a, b] = w[:, :, r, q]
+            wf = f.reshape(4, 4 * co, ci).to(torch.bfloat16).contiguous()                      # [tap][4*Cout][Cin]
+            rep = lambda v: None if v is None else v.repeat(4).contiguous()
+            self._fused = (wf, rep(self.scale), rep(self.shift), rep(self.alpha))
+        return self._fused
+
     def out_hw(self, h, w):
         if self.transposed:
             return ((h - 1) * self.stride - 2 * self.pad_h + self.dil_h * (self.kh - 1) + self.out_pad + 1,
@@ -342,6 +363,18 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
                                        max(prep.dil_h, prep.dil_w), "T" if prep.transposed else "")
     tc_ok = (UMMA_ENABLED and not force_direct and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
              and prep.groups == 1 and p.x.layout == L.ESN_NHWC)
+    if (tc_ok and prep.transposed and CONVT_FUSED and residual is None and (prep.kh, prep.kw, prep.stride) == (3, 3, 2)
+            and (prep.pad_h, prep.pad_w) == (1, 1) and (ho, wo) == (2 * h, 2 * w) and prep.cout in (8, 16, 32, 64)
+            and (prep.cin in (16, 32, 64) or prep.cin % 64 == 0) and out.stride(3) == prep.cout
+            and 4 * prep.cin * 4 * prep.cout * 2 <= 120 * 1024 and x.stride(3) % 8 == 0 and x.data_ptr() % 16 == 0
+            and out.data_ptr() % 16 == 0):
+        # one launch instead of four output-parity phases: x is read once
+        wf, sc4, sh4, al4 = prep.fused_convt()
+        p.w = wf.data_ptr()
+        p.kh, p.kw, p.stride, p.pad_h, p.pad_w, p.transposed, p.cout_pad = 2, 2, 1, 0, 0, 2, 4 * prep.cout
+        _epilogue(p.ep, sc4, sh4, al4, prep.act, None, getattr(prep, "ep_flags", 0))
+        _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag + "f")
+        return out
     if tc_ok and umma_supported(prep, p):
         p.w = prep.w_umma.data_ptr()
         _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag)

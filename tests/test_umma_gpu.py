@@ -174,3 +174,30 @@ def test_fused_pair_equals_two_convs(case):
             t = torch.where(t >= 0, t, t * alpha.view(1, -1, 1, 1))
     err = (y.float() - t).abs().max() / t.abs().max()
     assert err < 1.5e-2, err
+
+
+@pytest.mark.parametrize("cin,cout,N,H,W", [(64, 16, 2, 12, 256), (64, 16, 1, 9, 130), (32, 32, 2, 10, 128), (128, 16, 1, 7, 64),
+                                             (16, 8, 1, 20, 512)])
+def test_fused_transposed_conv(cin, cout, N, H, W):
+    """ConvTranspose2d(3, s2, p1, op1) as one 2x2-tap conv with 4*Cout outputs and a pixel-shuffle TMA store
+    (ops.conv2d's default route) against torch on the same bf16 operands, BN + ReLU epilogue included."""
+    from esn import ops
+    from esn._lib import ACT_RELU
+    torch.manual_seed(7)
+    m = nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1, bias=True).cuda()
+    with torch.no_grad():
+        m.weight.copy_(m.weight.to(torch.bfloat16).float())
+    scale = torch.rand(cout, device="cuda") + 0.5
+    shift = torch.randn(cout, device="cuda") * 0.1
+    x = ops.new_act(N, cin, H, W, torch.bfloat16, "cuda")
+    x.copy_(torch.randn(N, cin, H, W, device="cuda"))
+    prep = ops.ConvPrep(m, scale, shift, ACT_RELU)
+    ops.launch_count_reset()
+    y = ops.conv2d(x, prep)
+    torch.cuda.synchronize()
+    assert ops.launch_count() == 1, "expected the single-launch phase-fused route"
+    with torch.no_grad():
+        ref = torch.relu(m(x.float()) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert y.shape == ref.shape
+    err = (y.float() - ref).abs().max() / ref.abs().max()
+    assert err < 1.5e-2, err
