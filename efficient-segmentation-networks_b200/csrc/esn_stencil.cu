@@ -154,6 +154,87 @@ __global__ void __launch_bounds__(128) dab_dw_pair_strip_kernel(const DabArgs a)
     if (w0 + p < a.W) st4<TO>(y + (size_t)p * a.y_cs, affine_prelu(r[p], s2, b2, a2));
 }
 
+// Row variant (default): one CTA = one image row x a chunk of CC channels.  Stage 1 of both branches (vertical 3-tap
+// conv + BN + PReLU) is evaluated ONCE per pixel into shared memory (fp32, zero columns either side = the padding of
+// the intermediate tensor), stage 2 reads its three (dilated) columns from there: 5 coalesced global loads and 2
+// stage-1 evaluations per pixel instead of 12 and 4, no bounds tests in the inner loops.  The rows above / below are
+// the centre rows of neighbouring CTAs, so the vertical halo is served by L2 and DRAM traffic stays 1 read + 1 write.
+// BN scales are folded into the taps once per thread (a thread's 4 channels are loop-invariant).
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_prelu(float4 t, float4 al) {
+  return make_float4(prelu1(t.x, al.x), prelu1(t.y, al.y), prelu1(t.z, al.z), prelu1(t.w, al.w));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) dab_dw_pair_row_kernel(const DabArgs a, const int CC, const int nchunk) {
+  extern __shared__ __align__(16) float4 dab_sm[];
+  const int G = CC >> 2, gshift = 31 - __clz(G);          // 4-channel groups per pixel in this chunk (power of two)
+  const int chunk = blockIdx.x % nchunk;
+  const int row = blockIdx.x / nchunk;                     // n * H + h
+  const int h = row % a.H;
+  const int d = a.d, W = a.W;
+  float4* __restrict__ T1 = dab_sm;                        // [(W + 2)][G]   column w lives at (w + 1)
+  float4* __restrict__ T2 = dab_sm + (size_t)(W + 2) * G;  // [(W + 2d)][G]  column w lives at (w + d)
+  const int items = W * G;
+  const int g = threadIdx.x & (G - 1);                     // loop-invariant: blockDim.x % G == 0
+  const int c = chunk * CC + g * 4;
+  auto PR = [&](int r) { return __ldg(reinterpret_cast<const float4*>(a.prm + (size_t)r * a.C + c)); };
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < G; i += blockDim.x) { T1[i] = zero; T1[(W + 1) * G + i] = zero; }
+  for (int i = threadIdx.x; i < d * G; i += blockDim.x) { T2[i] = zero; T2[(W + d) * G + i] = zero; }
+  const TI* __restrict__ xrow = reinterpret_cast<const TI*>(a.x) + (size_t)row * W * a.x_cs + c;   // pixel (h, 0)
+
+  auto stage1 = [&](const int wbase, const int abase, const int dd, float4* __restrict__ T, const int toff) {
+    const float4 sc = PR(abase), sh = PR(abase + 1), al = PR(abase + 2);
+    const float4 w0 = f4_mul(PR(wbase), sc), w1 = f4_mul(PR(wbase + 1), sc), w2 = f4_mul(PR(wbase + 2), sc);
+    const bool up = h - dd >= 0, dn = h + dd < a.H;
+    const ptrdiff_t ro = (ptrdiff_t)dd * W * a.x_cs;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < items; i += 256) {
+      const TI* p = xrow + (size_t)(i >> gshift) * a.x_cs;
+      float4 t = f4_fma(ld4<TI>(p), w1, sh);
+      if (up) t = f4_fma(ld4<TI>(p - ro), w0, t);
+      if (dn) t = f4_fma(ld4<TI>(p + ro), w2, t);
+      T[i + toff] = f4_prelu(t, al);
+    }
+  };
+  stage1(0, 12, 1, T1, G);
+  stage1(6, 18, d, T2, d * G);
+  __syncthreads();
+
+  const float4 sb1 = PR(15), hb1 = PR(16), ab1 = PR(17);
+  const float4 u0 = f4_mul(PR(3), sb1), u1 = f4_mul(PR(4), sb1), u2 = f4_mul(PR(5), sb1);
+  const float4 sb2 = PR(21), hb2 = PR(22), ab2 = PR(23);
+  const float4 v0 = f4_mul(PR(9), sb2), v1 = f4_mul(PR(10), sb2), v2 = f4_mul(PR(11), sb2);
+  const float4 s3 = PR(24), h3 = PR(25), a3 = PR(26);
+  TO* __restrict__ yrow = reinterpret_cast<TO*>(a.y) + (size_t)row * W * a.y_cs + c;
+  const int dG = d * G;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < items; i += 256) {
+    float4 b1 = f4_fma(T1[i], u0, hb1);
+    b1 = f4_fma(T1[i + G], u1, b1);
+    b1 = f4_prelu(f4_fma(T1[i + 2 * G], u2, b1), ab1);
+    float4 b2 = f4_fma(T2[i], v0, hb2);
+    b2 = f4_fma(T2[i + dG], v1, b2);
+    b2 = f4_prelu(f4_fma(T2[i + 2 * dG], v2, b2), ab2);
+    const float4 sum = make_float4(b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w);
+    st4<TO>(yrow + (size_t)(i >> gshift) * a.y_cs, f4_prelu(f4_fma(sum, s3, h3), a3));
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_dab_row(const DabArgs& a, int CC, size_t smem, cudaStream_t st) {
+  auto kfn = dab_dw_pair_row_kernel<TI, TO>;
+  static bool attr_done = false;   // per instantiation; idempotent, so a race only repeats the call
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return ESN_ERR_CUDA;
+    attr_done = true;
+  }
+  const int nchunk = a.C / CC;
+  kfn<<<(unsigned)((long long)a.N * a.H * nchunk), 256, smem, st>>>(a, CC, nchunk);
+  return ESN_OK;
+}
+
 }  // namespace
 
 extern "C" int esn_dab_dw_pair(const EsnDabPair* p, void* stream) {
@@ -179,6 +260,24 @@ extern "C" int esn_dab_dw_pair(const EsnDabPair* p, void* stream) {
   const long long total = (long long)x.n * x.h * x.w * (x.c / 4);
   const int block = 256, grid = esn_cdiv(total, block);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool no_row = getenv("ESN_DAB_NOROW") != nullptr;
+  if (!no_row && (long long)x.n * x.h * (x.c / 4) < (1ll << 31)) {
+    // channel chunk: the largest power of two dividing C whose two stage-1 rows fit 72 KB (3 CTAs per SM)
+    int CC = 4;
+    while (CC * 2 <= 64 && x.c % (CC * 2) == 0) CC *= 2;
+    auto bytes = [&](int cc) { return (size_t)((x.w + 2) + (x.w + 2 * p->dilation)) * (cc / 4) * sizeof(float4); };
+    while (CC > 4 && bytes(CC) > 72 * 1024) CC /= 2;
+    if (bytes(CC) <= 96 * 1024) {
+      int rc;
+      if (x.dtype == ESN_F32 && y.dtype == ESN_F32) rc = launch_dab_row<float, float>(a, CC, bytes(CC), st);
+      else if (x.dtype == ESN_BF16 && y.dtype == ESN_BF16) rc = launch_dab_row<__nv_bfloat16, __nv_bfloat16>(a, CC, bytes(CC), st);
+      else if (x.dtype == ESN_F32) rc = launch_dab_row<float, __nv_bfloat16>(a, CC, bytes(CC), st);
+      else rc = launch_dab_row<__nv_bfloat16, float>(a, CC, bytes(CC), st);
+      if (rc) return rc;
+      ESN_CHECK_LAUNCH();
+      return ESN_OK;
+    }
+  }
   static const bool no_strip = getenv("ESN_DAB_NOSTRIP") != nullptr;
   if (!no_strip && x.w >= 8) {
     constexpr int P = 8;

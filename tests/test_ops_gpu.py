@@ -153,15 +153,19 @@ def test_pools_affine_convert(ops):
         assert torch.allclose(back, x.to(dt).float())
 
 
-def test_dab_pair_matches_torch(ops):
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_dab_pair_matches_torch(ops, dt):
+    """esn_dab_dw_pair (row kernel: stage-1 rows in shared memory) against torch: both DABNet module shapes, dilation 1,
+    dilation wider than the image, odd widths, the narrowest channel chunk (4) and a 3-chunk split (C/2 = 48)."""
     torch.manual_seed(3)
     from model.DABNet import DABModule
     from oracle import fixture
-    for c, d in ((64, 2), (128, 16)):
+    for c, d, hh, ww in ((64, 2, 20, 28), (128, 16, 20, 28), (64, 1, 5, 7), (8, 4, 9, 33), (128, 8, 3, 130), (96, 4, 17, 70),
+                         (64, 40, 6, 12)):
         m = DABModule(c, d=d)
         m.load_state_dict(fixture.randomize_state_dict(m.state_dict(), 5))
         m = m.cuda().eval()
-        x = torch.randn(2, c // 2, 20, 28, device="cuda")
+        x = torch.randn(2, c // 2, hh, ww, device="cuda").to(dt).float()
         with torch.no_grad():
             def cbr(conv, t, pad, dil):
                 y = F.conv2d(t, conv.conv.weight, None, 1, pad, dil, c // 2)
@@ -174,8 +178,10 @@ def test_dab_pair_matches_torch(ops):
             s = F.batch_norm(s, m.bn_relu_2.bn.running_mean, m.bn_relu_2.bn.running_var, m.bn_relu_2.bn.weight,
                              m.bn_relu_2.bn.bias, False, 0.0, 1e-3)
             ref = F.prelu(s, m.bn_relu_2.acti.weight)
-        y = ops.dab_dw_pair(ops.as_act(x, torch.float32), m.prep(x.device), d)
-        assert (y - ref).abs().max() / ref.abs().max() < 1e-5
+        y = ops.dab_dw_pair(ops.as_act(x, dt), m.prep(x.device), d)
+        assert y.dtype == dt
+        tol = 1e-5 if dt == torch.float32 else 1e-2      # bf16: output rounding only (fp32 arithmetic inside)
+        assert (y.float() - ref).abs().max() / ref.abs().max() < tol, (c, d, hh, ww)
 
 
 def test_heads_and_ce(ops):
