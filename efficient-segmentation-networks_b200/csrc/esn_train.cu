@@ -833,6 +833,7 @@ extern "C" int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream) {
 }
 
 bool esn_wgrad_mma_try(const EsnConv* p, void* stream, int* rc);   // esn_wgrad_mma.cu
+bool esn_wgrad_umma_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_umma.cu (tcgen05, stride 1)
 
 extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   // p->x: forward input, p->y: gradient of the conv output, p->w: fp32 dW accumulator
@@ -850,6 +851,7 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   if (eh != dy.h || ew != dy.w || x.n != dy.n) return ESN_ERR_BAD_SHAPE;
   {
     int rc = ESN_OK;   // bf16 dense convs: tensor-core path
+    if (!dw && !nchw && esn_wgrad_umma_try(p, stream, &rc)) return rc;
     if (!dw && !nchw && esn_wgrad_mma_try(p, stream, &rc)) return rc;
   }
   WgradArgs a;

@@ -109,6 +109,7 @@ SYMBOLS = {
     "esn_bn_act_bwd_reduce": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
     "esn_bn_act_bwd_apply": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
     "esn_conv2d_wgrad": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_wgrad_umma_supported": (C.c_int, [C.POINTER(EsnConv)]),
     "esn_maxpool2x2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
     "esn_bilinear_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_float, C.c_void_p]),
     "esn_bilinear_bwd_nhwc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_int32, C.c_void_p]),

@@ -317,6 +317,9 @@ int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream);
  * Replaces the weight branch of aten::convolution_backward.  The input gradient is the transposed /
  * flipped convolution and runs through esn_conv2d_umma / esn_conv2d_direct. */
 int esn_conv2d_wgrad(const EsnConv* p, void* stream);
+/* 1 when esn_conv2d_wgrad runs this problem on the tcgen05 kernel (bf16 NHWC operands, dense, stride 1, k <= 3:
+ * both operands MN-major straight from NHWC through TMA, all taps of a filter row per pass), else 0. */
+int esn_wgrad_umma_supported(const EsnConv* p);
 
 /* MaxPool2d(2,2) backward (first maximum wins, as max_pool2d_with_indices), optionally accumulating
  * into dx; bilinear (align_corners=False) backward from NCHW d logits to NHWC low-res scores,

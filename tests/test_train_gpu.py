@@ -107,6 +107,53 @@ def test_conv_backward_matches_torch(case, dtype):
     assert _rel(pg[conv.bias], gb) < (1e-4 if dtype == torch.float32 else 3e-3)
 
 
+WGU_CASES = [
+    # cin, cout, (kh, kw), (pad_h, pad_w), (dil_h, dil_w), N, H, W
+    (32, 32, (3, 3), (1, 1), (1, 1), 2, 20, 140),     # 4 horizontal taps per MMA (64-byte rows), partial column tile
+    (64, 32, (3, 3), (1, 1), (1, 1), 2, 12, 128),     # 2 taps per MMA + a second MMA for tap 2
+    (128, 64, (3, 3), (1, 1), (1, 1), 2, 16, 64),     # 64-channel boxes; one CTA group per filter row (TMEM columns)
+    (35, 29, (3, 3), (1, 1), (1, 1), 2, 24, 40),      # channel counts padded by TMA zero fill
+    (16, 16, (3, 1), (2, 0), (2, 1), 2, 24, 40),      # ERFNet factorized convs: 32-byte rows, 8 blocks per MMA
+    (16, 16, (1, 3), (0, 1), (1, 1), 2, 24, 40),
+    (128, 128, (1, 3), (0, 4), (1, 4), 1, 12, 96),    # two dY boxes (N = 128), dilated taps
+    (128, 128, (3, 1), (8, 0), (8, 1), 1, 20, 64),    # vertical dilation wider than a row tile
+    (64, 128, (1, 1), (0, 0), (1, 1), 2, 16, 48),     # 1x1
+    (192, 48, (3, 3), (1, 1), (1, 1), 1, 17, 70),     # odd number of 64-channel boxes, odd H, ragged W
+    (384, 64, (1, 1), (0, 0), (1, 1), 2, 16, 32),     # Fast-SCNN linear-bottleneck projection
+    (64, 64, (3, 3), (2, 2), (2, 2), 1, 30, 150),     # dilated dense 3x3 (CGNet / ENet)
+]
+
+
+@pytest.mark.parametrize("case", WGU_CASES)
+def test_wgrad_tcgen05_matches_torch(case):
+    """esn_conv2d_wgrad on the tcgen05 kernel (both operands MN-major from NHWC, taps as shifted descriptors) against
+    torch's conv2d_weight on the same bf16-rounded operands: only the fp32 accumulation order differs."""
+    from esn import ops, _lib as L
+    cin, cout, (kh, kw), (ph, pw), (dh, dw_), N, H, W = case
+    torch.manual_seed(11)
+    x = torch.randn(N, cin, H, W, device="cuda")
+    Ho, Wo = H + 2 * ph - dh * (kh - 1), W + 2 * pw - dw_ * (kw - 1)
+    gy = torch.randn(N, cout, Ho, Wo, device="cuda")
+    xa = _nhwc(x, torch.bfloat16, ops, c_alloc=(cin + 7) // 8 * 8)
+    ga = _nhwc(gy, torch.bfloat16, ops, c_alloc=(cout + 7) // 8 * 8)
+    dwbuf = torch.zeros((kh * kw, cin, cout), dtype=torch.float32, device="cuda")
+    p = L.EsnConv()
+    p.x, p.y, p.w = ops.tdesc(xa), ops.tdesc(ga), dwbuf.data_ptr()
+    p.kh, p.kw, p.stride, p.pad_h, p.pad_w, p.dil_h, p.dil_w = kh, kw, 1, ph, pw, dh, dw_
+    p.groups, p.transposed, p.cout_pad = 1, 0, cout
+    assert L.lib.esn_wgrad_umma_supported(C.byref(p)) == 1
+    for rep in range(2):        # twice: accumulates into the caller's buffer
+        assert L.lib.esn_conv2d_wgrad(C.byref(p), ops.stream()) == 0
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(xa.float(), (cout, cin, kh, kw), ga.float(), stride=1, padding=(ph, pw),
+                                      dilation=(dh, dw_))
+    got = dwbuf.view(kh, kw, cin, cout).permute(3, 2, 0, 1) * 0.5
+    assert _rel(got, ref) < 2e-3, _rel(got, ref)
+    for r in range(kh):          # every tap separately (a wrong tap shift must not hide in the norm)
+        for s_ in range(kw):
+            assert _rel(got[:, :, r, s_], ref[:, :, r, s_]) < 4e-3, (r, s_)
+
+
 def test_pool_bilinear_ce_backward():
     from esn import ops, train as T
     torch.manual_seed(2)
