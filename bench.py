@@ -219,10 +219,10 @@ def main():
         if world > 1:
             parallel.data_parallel(m)
         crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
-        opt = torch.optim.Adam(m.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True)  # train.py:212-215
+        opt = torch.optim.Adam(m.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True,
+                               capturable=not args.no_graph)  # train.py:212-215
         y_host = fixture.make_labels(batch, H, W, 19, seed=1234 + rank).pin_memory()
         y = y_host.cuda(non_blocking=True)
-        args.no_graph = True
     else:
         m.eval()
     torch.cuda.synchronize()
@@ -247,7 +247,17 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = ops.launch_count()
     graph = None
-    if not args.no_graph:
+    gstep = None
+    if train and not args.no_graph:
+        # the whole iteration (forward, loss, backward, gradient all-reduce, Adam) as one CUDA graph (esn/graph.py)
+        from esn.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(m, crit, opt, x, y, warmup=1)
+        graph = gstep.graph
+        mask = gstep.loss
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+    elif not args.no_graph:
         graph = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -323,7 +333,7 @@ def main():
             if i >= 1:
                 pb = (i - 1) & 1
                 main_s.wait_event(ready[pb])
-                mk = step(xin[pb], yin[pb])
+                mk = gstep(xin[pb], yin[pb]) if gstep is not None else step(xin[pb], yin[pb])
                 mask_host[pb].copy_(mk, non_blocking=True)
                 done[pb] = torch.cuda.Event()
                 done[pb].record(main_s)

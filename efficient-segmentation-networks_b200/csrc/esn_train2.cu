@@ -122,7 +122,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
 }
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int C, int H, int W, int x_cs,
-                                                      int y_cs, uint64_t seed, uint32_t thresh, float scale, int per_channel) {
+                                                      int y_cs, uint64_t seed, const unsigned long long* __restrict__ step,
+                                                      uint32_t thresh, float scale, int per_channel) {
+  if (step) seed += 0xd1b54a32d192ed03ULL * (uint64_t)(*step);   // device-side iteration counter (CUDA-graph replays)
   const long long total = (long long)N * H * W * C;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -202,6 +204,11 @@ extern "C" int esn_avgpool3x3s2_bwd(const EsnTensor* dy, const EsnTensor* dx, in
 }
 
 extern "C" int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, int32_t per_channel, void* stream) {
+  return esn_dropout_step(x, y, seed, nullptr, p, per_channel, stream);
+}
+
+extern "C" int esn_dropout_step(const EsnTensor* x, const EsnTensor* y, uint64_t seed, const uint64_t* step, float p,
+                                int32_t per_channel, void* stream) {
   if (!x || !y || !esn_valid_nhwc(*x) || !esn_valid_nhwc(*y)) return ESN_ERR_BAD_ARG;
   if (x->n != y->n || x->c != y->c || x->h != y->h || x->w != y->w || x->dtype != y->dtype) return ESN_ERR_BAD_SHAPE;
   if (!(p >= 0.f) || p >= 1.f) return ESN_ERR_BAD_ARG;
@@ -212,10 +219,10 @@ extern "C" int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x->dtype == ESN_F32)
     dropout_kernel<float><<<grid, 256, 0, st>>>((const float*)x->ptr, (float*)y->ptr, x->n, x->c, x->h, x->w, x->c_stride,
-                                                y->c_stride, seed, thresh, scale, per_channel);
+                                                y->c_stride, seed, reinterpret_cast<const unsigned long long*>(step), thresh, scale, per_channel);
   else
     dropout_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, (__nv_bfloat16*)y->ptr, x->n, x->c, x->h, x->w,
-                                                        x->c_stride, y->c_stride, seed, thresh, scale, per_channel);
+                                                        x->c_stride, y->c_stride, seed, reinterpret_cast<const unsigned long long*>(step), thresh, scale, per_channel);
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }

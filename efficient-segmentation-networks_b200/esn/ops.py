@@ -22,6 +22,27 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_STEP = {}
+
+
+def step_counter(device=None):
+    """Device-resident training-iteration counter (int64 scalar per device) mixed into the dropout seeds; a graphed
+    training step (esn/graph.py) advances it inside the graph so that replays draw fresh masks."""
+    dev = torch.device(device if device is not None else "cuda")
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _STEP.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("esn.ops.step_counter must exist before CUDA-graph capture (run one eager iteration first)")
+        t = torch.zeros((), dtype=torch.int64, device=torch.device("cuda", key))
+        _STEP[key] = t
+    return t
+
+
+def advance_step_counter(device=None):
+    step_counter(device).add_(1)
+
+
 # Optional per-launch profile (bench.py's roofline leg): when PROFILE is a list every C-ABI call is
 # bracketed by CUDA events on the launching stream and (kernel, algorithmic bytes, flops, events)
 # is appended.  None (the default) adds no work to the hot path.

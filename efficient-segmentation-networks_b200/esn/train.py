@@ -577,8 +577,9 @@ def dropout(tape, x, p, per_channel=False, training=True):
     def apply(src):
         dst = ops.new_act(n, c, h, w, src.dtype, src.device)
         a, b = ops.tdesc(src), ops.tdesc(dst)
-        ops._call(L.lib.esn_dropout, "esn_dropout", (C.byref(a), C.byref(b), C.c_uint64(seed), C.c_float(p), int(per_channel)),
-                  ops._nbytes(src) + ops._nbytes(dst))
+        ops._call(L.lib.esn_dropout_step, "esn_dropout", (C.byref(a), C.byref(b), C.c_uint64(seed),
+                                                          C.c_void_p(ops.step_counter(src.device).data_ptr()), C.c_float(p),
+                                                          int(per_channel)), ops._nbytes(src) + ops._nbytes(dst))
         return dst
     y = V(apply(x.t))
 

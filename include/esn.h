@@ -335,6 +335,11 @@ int esn_bilinear_bwd_nhwc(const EsnTensor* dy, const EsnTensor* dx, int32_t alig
 int esn_adaptive_avgpool_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);
 int esn_avgpool3x3s2_bwd(const EsnTensor* dy, const EsnTensor* dx, int32_t accumulate, void* stream);   /* AvgPool2d(3,2,1): /9 always */
 int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, int32_t per_channel, void* stream);
+/* Same, with a device-resident iteration counter mixed into the seed (NULL = none): a training step captured in a
+ * CUDA graph (esn/graph.py) advances the counter inside the graph, so every replay draws fresh masks and the
+ * backward of the same replay regenerates them. */
+int esn_dropout_step(const EsnTensor* x, const EsnTensor* y, uint64_t seed, const uint64_t* step, float p,
+                     int32_t per_channel, void* stream);
 
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);

@@ -381,3 +381,54 @@ def test_grouped_conv_and_avgpool_backward():
         y._g = _nhwc(gy, torch.float32, ops)
         tape.backward()
         assert _rel(xv.g, gx) < 1e-5, (h, w)
+
+
+@pytest.mark.parametrize("net", ["DABNet", "FastSCNN"])
+def test_graphed_train_step_equals_eager(spec, net):
+    """esn.graph.GraphedTrainStep (forward + loss + backward + Adam as ONE CUDA graph) against the same iterations run
+    eagerly: fp32, dropout off, same data -> same losses and weights up to the fp32-atomic accumulation order; with
+    dropout on, replays must draw different masks (device-side step counter) -- the loss changes between replays of
+    identical data only through the weights, so compare against an eager run with dropout too loosely (finite, moving)."""
+    from builders.model_builder import build_model
+    from utils.losses.loss import CrossEntropyLoss2d
+    from esn.graph import GraphedTrainStep
+    x = fixture.make_input(2, 64, 128).cuda()
+    lab = fixture.make_labels(2, 64, 128, 19).cuda()
+    crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
+
+    def make(p_drop):
+        m = build_model(net, 19)
+        m.load_state_dict(spec_state_dict(spec, net))
+        m = m.cuda().train()
+        for mod in m.modules():
+            if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
+                mod.p = p_drop if p_drop is not None else mod.p
+        opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=1e-4, fused=True, capturable=True)
+        return m, opt
+
+    m0, o0 = make(0.0)
+    eager = []
+    for _ in range(4):
+        o0.zero_grad(set_to_none=True)
+        loss = crit(m0(x), lab)
+        loss.backward()
+        o0.step()
+        eager.append(loss.item())
+    m1, o1 = make(0.0)
+    gs = GraphedTrainStep(m1, crit, o1, x, lab, autocast_dtype=None, warmup=1)     # iteration 0 runs eagerly as warm-up
+    graphed = [gs().item() for _ in range(3)]
+    for a, b in zip(eager[1:], graphed):
+        assert abs(a - b) < 2e-3 * abs(a), (eager, graphed)
+    worst = max(_rel(p1.detach(), p0.detach()) for p0, p1 in zip(m0.parameters(), m1.parameters()))
+    assert worst < 5e-2, worst            # Adam normalises tiny gradients: sign-level noise moves a weight by lr
+    # new batch through the static buffers
+    x2 = fixture.make_input(2, 64, 128, seed=7).cuda() if "seed" in fixture.make_input.__code__.co_varnames else x.flip(0)
+    l2 = gs(x2, lab).item()
+    assert l2 == l2 and abs(l2 - graphed[-1]) > 0
+    if net == "FastSCNN":
+        m2, o2 = make(None)               # dropout on: replays of the same batch must not reuse one mask
+        step0 = int(__import__("esn").ops.step_counter().item())
+        gs2 = GraphedTrainStep(m2, crit, o2, x, lab, autocast_dtype=None, warmup=1)
+        ls = [gs2().item() for _ in range(3)]
+        assert all(v == v for v in ls)
+        assert int(__import__("esn").ops.step_counter().item()) == step0 + 4
