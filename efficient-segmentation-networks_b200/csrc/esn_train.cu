@@ -629,6 +629,302 @@ __global__ void __launch_bounds__(kStatThreads) wgrad_dw_kernel(const WgradArgs 
   }
 }
 
+// depthwise, ALL taps in one pass: a thread owns 4 channels and a lane of pixels, loads dY once per pixel and the
+// KH*KW (L1-resident) neighbours of x, keeps KH*KW*4 accumulators.  Rows are walked without per-pixel div/mod.
+// One read of |x| + |dy| from DRAM instead of KH*KW reads (Fast-SCNN / ESPNetv2 / CGNet 3x3, DABNet / EESP 3x1, 1x3).
+template <typename TX, typename TG, int KH, int KW>
+__global__ void __launch_bounds__(kStatThreads) wgrad_dw_all_kernel(const WgradArgs a, const int rows_per_cta) {
+  constexpr int T = KH * KW;
+  __shared__ float red[kStatThreads][4];
+  const int C = a.Cout;
+  const int CG = min((C + 3) / 4, 64);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.z * 64 + cg) * 4;
+  const TX* x = reinterpret_cast<const TX*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy);
+  const bool vx = (a.x_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(x) % (4 * sizeof(TX))) == 0);
+  const bool vg = (a.dy_cs % 4 == 0) && (c + 4 <= C) && ((reinterpret_cast<uintptr_t>(dy) % (4 * sizeof(TG))) == 0);
+  float acc[T][4];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  const int R = a.N * a.Ho;
+  const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  if (KW == 3 && a.stride == 1 && a.dil_w == 1) {
+    // sliding window: a thread walks a contiguous segment of the row and keeps the KH x 3 window of x in registers,
+    // so a step costs KH + 1 loads (the new right-hand column and dY) instead of 3 KH + 1
+    const int L = (a.Wo + lanes - 1) / lanes;
+    const int wb = pl * L, we = min(a.Wo, wb + L);
+    if (pl < lanes && c < C && wb < we) {
+      for (int row = row0; row < row1; ++row) {
+        const int n = row / a.Ho, ho = row - n * a.Ho;
+        const TG* grow = dy + (size_t)row * a.Wo * a.dy_cs + c;
+        const TX* xn = x + (size_t)n * a.Hi * a.Wi * a.x_cs + c;
+        const TX* xr[KH];
+        bool rv[KH];
+#pragma unroll
+        for (int r = 0; r < KH; ++r) {
+          const int hi = ho - a.pad_h + r * a.dil_h;
+          rv[r] = hi >= 0 && hi < a.Hi;
+          xr[r] = xn + (size_t)(rv[r] ? hi : 0) * a.Wi * a.x_cs;
+        }
+        float win[KH][3][4];
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int wi = wb - a.pad_w + q;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) win[r][q][j] = 0.f;
+            if (rv[r] && wi >= 0 && wi < a.Wi) ldv4<TX>(xr[r] + (size_t)wi * a.x_cs, vx, c, C, win[r][q]);
+          }
+        for (int wo = wb; wo < we; ++wo) {
+          float gv[4];
+          ldv4<TG>(grow + (size_t)wo * a.dy_cs, vg, c, C, gv);
+          const int wi = wo - a.pad_w + 2;
+          const bool cv = wi >= 0 && wi < a.Wi;
+#pragma unroll
+          for (int r = 0; r < KH; ++r) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) win[r][2][j] = 0.f;
+            if (rv[r] && cv) ldv4<TX>(xr[r] + (size_t)wi * a.x_cs, vx, c, C, win[r][2]);
+          }
+#pragma unroll
+          for (int r = 0; r < KH; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[r * 3 + q][j] = fmaf(win[r][q][j], gv[j], acc[r * 3 + q][j]);
+#pragma unroll
+          for (int r = 0; r < KH; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              win[r][0][j] = win[r][1][j];
+              win[r][1][j] = win[r][2][j];
+            }
+        }
+      }
+    }
+  } else if (pl < lanes && c < C) {
+    for (int row = row0; row < row1; ++row) {
+      const int n = row / a.Ho, ho = row - n * a.Ho;
+      const TG* grow = dy + (size_t)row * a.Wo * a.dy_cs + c;
+      const TX* xn = x + (size_t)n * a.Hi * a.Wi * a.x_cs + c;
+      const int hi0 = ho * a.stride - a.pad_h;
+      for (int wo = pl; wo < a.Wo; wo += lanes) {
+        float gv[4];
+        ldv4<TG>(grow + (size_t)wo * a.dy_cs, vg, c, C, gv);
+        const int wi0 = wo * a.stride - a.pad_w;
+#pragma unroll
+        for (int r = 0; r < KH; ++r) {
+          const int hi = hi0 + r * a.dil_h;
+          if (hi < 0 || hi >= a.Hi) continue;
+#pragma unroll
+          for (int q = 0; q < KW; ++q) {
+            const int wi = wi0 + q * a.dil_w;
+            if (wi < 0 || wi >= a.Wi) continue;
+            float xv[4];
+            ldv4<TX>(xn + ((size_t)hi * a.Wi + wi) * a.x_cs, vx, c, C, xv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r * KW + q][j] = fmaf(xv[j], gv[j], acc[r * KW + q][j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = acc[t][j];
+    __syncthreads();
+    if (pl == 0 && c < C) {
+      float v[4] = {acc[t][0], acc[t][1], acc[t][2], acc[t][3]};
+      for (int l = 1; l < lanes; ++l)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += red[l * CG + cg][j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < C && v[j] != 0.f) atomicAdd(a.dw + (size_t)t * C + c + j, v[j]);
+    }
+  }
+}
+
+// depthwise, stride 1, dilation 1 -- column-strip variant (default for these): a CTA owns a strip of the image
+// (lanes x LSEG columns, all its channels) and walks DOWN the rows, so the KH input rows of an output row are the rows
+// it loaded one and two steps ago: they stay in registers (each x element is loaded from L2/DRAM once per strip, ncu
+// showed the row-major variant re-reading x KH times from DRAM and waiting on 4 dependent loads per pixel).  A thread
+// = 4 channels x LSEG consecutive pixels: LSEG + 2 + LSEG independent 8/16-byte loads per row step.
+template <typename T> struct Raw4;
+template <> struct Raw4<float> {
+  float4 v;
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ float4 f4() const { return v; }
+};
+template <> struct Raw4<__nv_bfloat16> {
+  uint2 v;
+  __device__ __forceinline__ void zero() { v = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ __forceinline__ float4 f4() const {
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                       __uint_as_float(v.y & 0xffff0000u));
+  }
+};
+
+template <typename TX, typename TG, int KH, int KW, int LSEG>
+__global__ void __launch_bounds__(kStatThreads) wgrad_dw_strip_kernel(const WgradArgs a, const int rows_per_chunk, const int nstrips,
+                                                                      const int nchunks) {
+  constexpr int T = KH * KW, XC = LSEG + KW - 1;
+  __shared__ float red[kStatThreads][4];
+  const int C = a.Cout;
+  const int CG = min(C / 4, 64);
+  const int lanes = kStatThreads / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int c = (blockIdx.z * 64 + cg) * 4;
+  int b = blockIdx.x;
+  const int chunk = b % nchunks; b /= nchunks;
+  const int strip = b % nstrips;
+  const int n = b / nstrips;
+  const int wb = (strip * lanes + pl) * LSEG;                 // first output column of this thread
+  const int h_begin = chunk * rows_per_chunk, h_end = min(a.Ho, h_begin + rows_per_chunk);
+  float acc[T][4];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  if (pl < lanes && c < C && wb < a.Wo && h_begin < h_end) {
+    const TX* xn = reinterpret_cast<const TX*>(a.x) + (size_t)n * a.Hi * a.Wi * a.x_cs + c;
+    const TG* gn = reinterpret_cast<const TG*>(a.dy) + (size_t)n * a.Ho * a.Wo * a.dy_cs + c;
+    Raw4<TX> R[KH][XC];
+    auto load_row = [&](Raw4<TX>* dst, const int hi) {
+      const bool rv = hi >= 0 && hi < a.Hi;
+      const TX* xr = xn + (size_t)(rv ? hi : 0) * a.Wi * a.x_cs;
+#pragma unroll
+      for (int j = 0; j < XC; ++j) {
+        const int wi = wb - a.pad_w + j;
+        dst[j].zero();
+        if (rv && wi >= 0 && wi < a.Wi) dst[j].load(xr + (size_t)wi * a.x_cs);
+      }
+    };
+#pragma unroll
+    for (int r = 0; r + 1 < KH; ++r) load_row(R[r], h_begin - a.pad_h + r);
+    for (int ho = h_begin; ho < h_end; ++ho) {
+      load_row(R[KH - 1], ho - a.pad_h + KH - 1);
+      Raw4<TG> G[LSEG];
+      const TG* gr = gn + (size_t)ho * a.Wo * a.dy_cs;
+#pragma unroll
+      for (int p = 0; p < LSEG; ++p) {
+        G[p].zero();
+        if (wb + p < a.Wo) G[p].load(gr + (size_t)(wb + p) * a.dy_cs);
+      }
+#pragma unroll
+      for (int p = 0; p < LSEG; ++p) {
+        const float4 g = G[p].f4();
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int q = 0; q < KW; ++q) {
+            const float4 xv = R[r][p + q].f4();
+            acc[r * KW + q][0] = fmaf(xv.x, g.x, acc[r * KW + q][0]);
+            acc[r * KW + q][1] = fmaf(xv.y, g.y, acc[r * KW + q][1]);
+            acc[r * KW + q][2] = fmaf(xv.z, g.z, acc[r * KW + q][2]);
+            acc[r * KW + q][3] = fmaf(xv.w, g.w, acc[r * KW + q][3]);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r + 1 < KH; ++r)
+#pragma unroll
+        for (int j = 0; j < XC; ++j) R[r][j] = R[r + 1][j];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = acc[t][j];
+    __syncthreads();
+    if (pl == 0 && c < C) {
+      float v[4] = {acc[t][0], acc[t][1], acc[t][2], acc[t][3]};
+      for (int l = 1; l < lanes; ++l)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += red[l * CG + cg][j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (v[j] != 0.f) atomicAdd(a.dw + (size_t)t * C + c + j, v[j]);
+    }
+  }
+}
+
+// Network stem, second version (3x3, stride 2, Cin = 3 NCHW fp32 image, Cout <= 32): a CTA stages the 3 x 3 input row
+// segments of a strip of 128 output pixels in shared memory with coalesced loads; lane = output channel; a warp takes
+// two neighbouring output pixels at a time, whose 5 input columns per (ci, row) are ONE 16-byte + one 4-byte broadcast
+// shared-memory read (the first version issued 27 dependent global broadcast loads per pixel).
+constexpr int kStemTW = 128;
+template <typename TG>
+__global__ void __launch_bounds__(256) wgrad_stem2_kernel(const WgradArgs a, const int units_per_cta) {
+  __shared__ __align__(16) float xs[9][2 * kStemTW + 8];   // [ci*3 + r][input column - wi0]
+  __shared__ float red[8][27][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* x = reinterpret_cast<const float*>(a.x);
+  const TG* dy = reinterpret_cast<const TG*>(a.dy);
+  const size_t plane = (size_t)a.Hi * a.Wi;
+  const int tiles_w = (a.Wo + kStemTW - 1) / kStemTW;
+  const int nunits = a.N * a.Ho * tiles_w;
+  const int u0 = blockIdx.x * units_per_cta, u1 = min(nunits, u0 + units_per_cta);
+  const bool act = lane < a.Cout;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  for (int u = u0; u < u1; ++u) {
+    const int tw = u % tiles_w, row = u / tiles_w;
+    const int n = row / a.Ho, ho = row - n * a.Ho;
+    const int wo0 = tw * kStemTW, npx = min(kStemTW, a.Wo - wo0);
+    const int wi0 = wo0 * 2 - a.pad_w, hi0 = ho * 2 - a.pad_h;
+    __syncthreads();                                   // the previous unit's readers are done
+    for (int e = threadIdx.x; e < 9 * (2 * kStemTW + 8); e += 256) {
+      const int rr = e / (2 * kStemTW + 8), col = e - rr * (2 * kStemTW + 8);
+      const int ci = rr / 3, r = rr - ci * 3;
+      const int hi = hi0 + r, wi = wi0 + col;
+      float v = 0.f;
+      if (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) v = __ldg(x + ((size_t)n * 3 + ci) * plane + (size_t)hi * a.Wi + wi);
+      xs[rr][col] = v;
+    }
+    __syncthreads();
+    const TG* grow = dy + ((size_t)row * a.Wo + wo0) * a.dy_cs + lane;
+    for (int j = warp * 2; j < npx; j += 16) {         // pixels j, j+1 of the strip
+      const float g0 = act ? ld1<TG>(grow + (size_t)j * a.dy_cs) : 0.f;
+      const float g1 = (act && j + 1 < npx) ? ld1<TG>(grow + (size_t)(j + 1) * a.dy_cs) : 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 9; ++rr) {                 // rr = ci*3 + r
+        const float4 v = *reinterpret_cast<const float4*>(&xs[rr][2 * j]);
+        const float v4 = xs[rr][2 * j + 4];
+        const int ci = rr / 3, r = rr - ci * 3;
+        acc[(r * 3 + 0) * 3 + ci] = fmaf(v.x, g0, acc[(r * 3 + 0) * 3 + ci]);
+        acc[(r * 3 + 1) * 3 + ci] = fmaf(v.y, g0, acc[(r * 3 + 1) * 3 + ci]);
+        acc[(r * 3 + 2) * 3 + ci] = fmaf(v.z, g0, acc[(r * 3 + 2) * 3 + ci]);
+        acc[(r * 3 + 0) * 3 + ci] = fmaf(v.z, g1, acc[(r * 3 + 0) * 3 + ci]);
+        acc[(r * 3 + 1) * 3 + ci] = fmaf(v.w, g1, acc[(r * 3 + 1) * 3 + ci]);
+        acc[(r * 3 + 2) * 3 + ci] = fmaf(v4, g1, acc[(r * 3 + 2) * 3 + ci]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 27; ++t) red[warp][t][lane] = acc[t];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 27 * 32; e += 256) {
+    const int t = e >> 5, co = e & 31;
+    if (co < a.Cout) {
+      float v = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) v += red[wv][t][co];
+      if (v != 0.f) atomicAdd(a.dw + (size_t)t * a.Cout + co, v);     // t = (tap*3 + ci): the [tap][Cin][Cout] layout
+    }
+  }
+}
+
 // ---------------------------------------------------------------- max-pool 2x2 backward (gather form)
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const TX* __restrict__ x, const TG* __restrict__ dy,
@@ -866,7 +1162,55 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   const int taps = p->kh * p->kw;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool xf = x.dtype == ESN_F32, gf = dy.dtype == ESN_F32;
-  if (dw) {
+  static const bool dw_old = getenv("ESN_WGRAD_DW_PER_TAP") != nullptr, stem_old = getenv("ESN_WGRAD_STEM_V1") != nullptr;
+  static const bool dw_nostrip = getenv("ESN_WGRAD_DW_NOSTRIP") != nullptr;
+  const bool dw_k = (p->kh == 3 && p->kw == 3) || (p->kh == 3 && p->kw == 1) || (p->kh == 1 && p->kw == 3);
+  if (dw && !dw_old && !dw_nostrip && dw_k && p->stride == 1 && p->dil_h == 1 && p->dil_w == 1 && dy.c % 4 == 0 &&
+      x.c_stride % 4 == 0 && dy.c_stride % 4 == 0 && ((uintptr_t)x.ptr % (xf ? 16 : 8)) == 0 &&
+      ((uintptr_t)dy.ptr % (gf ? 16 : 8)) == 0) {
+    constexpr int LSEG = 4;
+    const int cblocks = esn_cdiv(dy.c / 4, 64);
+    const int CG = dy.c / 4 < 64 ? dy.c / 4 : 64;
+    const int lanes = kStatThreads / CG;
+    const int nstrips = esn_cdiv(dy.w, lanes * LSEG);
+    const int base_ctas = dy.n * nstrips * cblocks;
+    int nchunks = (148 * 4 + base_ctas - 1) / base_ctas;       // >= 4 CTAs per SM worth of work, chunks of >= 16 rows
+    if (nchunks > dy.h / 16) nchunks = dy.h / 16;
+    if (nchunks < 1) nchunks = 1;
+    const int rpc = esn_cdiv(dy.h, nchunks);
+    nchunks = esn_cdiv(dy.h, rpc);
+    dim3 grid(dy.n * nstrips * nchunks, 1, cblocks);
+#define ESN_DWSTRIP(KH, KW)                                                                                                     \
+    do {                                                                                                                         \
+      if (xf && gf) wgrad_dw_strip_kernel<float, float, KH, KW, LSEG><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks);  \
+      else if (xf) wgrad_dw_strip_kernel<float, __nv_bfloat16, KH, KW, LSEG><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks); \
+      else if (gf) wgrad_dw_strip_kernel<__nv_bfloat16, float, KH, KW, LSEG><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks); \
+      else wgrad_dw_strip_kernel<__nv_bfloat16, __nv_bfloat16, KH, KW, LSEG><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks); \
+    } while (0)
+    if (p->kh == 3 && p->kw == 3) ESN_DWSTRIP(3, 3);
+    else if (p->kh == 3) ESN_DWSTRIP(3, 1);
+    else ESN_DWSTRIP(1, 3);
+#undef ESN_DWSTRIP
+  } else if (dw && !dw_old && dw_k) {
+    const int cblocks = esn_cdiv(esn_cdiv(dy.c, 4), 64);
+    const int R = dy.n * dy.h;
+    int want = (148 * 8) / cblocks;                     // CTAs along the row axis (8 x 256 threads per SM)
+    if (want < 1) want = 1;
+    int rpc = esn_cdiv(R, want);
+    if (rpc < 1) rpc = 1;
+    dim3 grid(esn_cdiv(R, rpc), 1, cblocks);
+#define ESN_DWALL(KH, KW)                                                                                         \
+    do {                                                                                                           \
+      if (xf && gf) wgrad_dw_all_kernel<float, float, KH, KW><<<grid, kStatThreads, 0, st>>>(a, rpc);              \
+      else if (xf) wgrad_dw_all_kernel<float, __nv_bfloat16, KH, KW><<<grid, kStatThreads, 0, st>>>(a, rpc);       \
+      else if (gf) wgrad_dw_all_kernel<__nv_bfloat16, float, KH, KW><<<grid, kStatThreads, 0, st>>>(a, rpc);       \
+      else wgrad_dw_all_kernel<__nv_bfloat16, __nv_bfloat16, KH, KW><<<grid, kStatThreads, 0, st>>>(a, rpc);       \
+    } while (0)
+    if (p->kh == 3 && p->kw == 3) ESN_DWALL(3, 3);
+    else if (p->kh == 3) ESN_DWALL(3, 1);
+    else ESN_DWALL(1, 3);
+#undef ESN_DWALL
+  } else if (dw) {
     const int cblocks = esn_cdiv(esn_cdiv(dy.c, 4), 64);
     a.px_per_cta = pick_chunk(M, taps * cblocks);
     dim3 grid(esn_cdiv(M, a.px_per_cta), taps, cblocks);
@@ -874,6 +1218,14 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
     else if (xf) wgrad_dw_kernel<float, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
     else if (gf) wgrad_dw_kernel<__nv_bfloat16, float><<<grid, kStatThreads, 0, st>>>(a);
     else wgrad_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kStatThreads, 0, st>>>(a);
+  } else if (nchw && x.c == 3 && p->kh == 3 && p->kw == 3 && dy.c <= 32 && p->stride == 2 && p->dil_h == 1 && p->dil_w == 1 &&
+             !stem_old) {
+    const int nunits = dy.n * dy.h * esn_cdiv(dy.w, kStemTW);
+    int upc = esn_cdiv(nunits, 148 * 4);
+    if (upc < 1) upc = 1;
+    const int grid = esn_cdiv(nunits, upc);
+    if (gf) wgrad_stem2_kernel<float><<<grid, 256, 0, st>>>(a, upc);
+    else wgrad_stem2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, upc);
   } else if (nchw && x.c == 3 && p->kh == 3 && p->kw == 3 && dy.c <= 32) {
     a.px_per_cta = (M + 148 * 8 - 1) / (148 * 8);
     if (a.px_per_cta < 256) a.px_per_cta = 256;

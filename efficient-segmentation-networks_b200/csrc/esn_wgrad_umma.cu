@@ -34,14 +34,23 @@ struct alignas(64) WguArgs {
   uint32_t xbox_alloc, xtile_alloc, gbox_bytes, gtile_bytes, stage_bytes, load_bytes;
   uint32_t xrow_bytes, grow_bytes;
   uint32_t adesc_hi, bdesc_hi, a_lbo, b_lbo, idesc;
+  int loop_s, loop_jb;          // MMA issue loops per filter row: taps / tap groups x channel-box pairs
+  uint32_t step_s, step_jb;     // their A start-address steps (bytes)
   int acc_rt[kMaxAcc];          // X row tile (tap row relative to the CTA's first)
   uint32_t acc_off[kMaxAcc];    // byte offset of the A start inside that tile
   int acc_s0[kMaxAcc], acc_ci0[kMaxAcc];
 };
 
-__device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t hi) {
-  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-  return ((uint64_t)hi << 32) | lo;
+__device__ __forceinline__ void umma_mn(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid_constant__ WguArgs a) {
@@ -103,21 +112,36 @@ __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid
     }
   } else if (warp == 1) {
     if (u_begin < u_end) {
+      // MMA issuer: warp-uniform runtime loops whose descriptor words advance with 32-bit adds (no table look-ups, no
+      // predicated-off issue slots: ncu showed the first two versions issue-bound at ~300 cycles per MMA); one elected
+      // lane issues.  Accumulator order = (filter row, tap / tap group, channel-box pair), as in the host's table.
       const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0, accum = 0;
-      const int ksteps = a.BW >> 4;
+      const int ksteps = a.BW >> 4, BH = a.BH, n_rt = a.nrt, n_s = a.loop_s, n_jb = a.loop_jb;
+      const uint32_t a_hi = a.adesc_hi, b_hi = a.bdesc_hi, idesc = a.idesc, N = (uint32_t)a.N;
+      const uint32_t a_lbo_bits = ((a.a_lbo >> 4) & 0x3FFFu) << 16, b_lbo_bits = ((a.b_lbo >> 4) & 0x3FFFu) << 16;
+      const uint32_t kstep_a = a.xrow_bytes, kstep_b = a.grow_bytes;                       // 16 pixel rows, in 16-byte units
+      const uint32_t row_a = ((uint32_t)a.XW * a.xrow_bytes) >> 4, row_b = ((uint32_t)a.BW * a.grow_bytes) >> 4;
+      const uint32_t step_rt = a.xtile_alloc >> 4, step_s = a.step_s >> 4, step_jb = a.step_jb >> 4;
+      const uint32_t stage16 = a.stage_bytes >> 4, gt16 = a.gtile_bytes >> 4;
+      const uint32_t base16 = (base & 0x3FFFFu) >> 4;
       for (int u = u_begin; u < u_end; ++u) {
         mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t g0 = base + (uint32_t)s * a.stage_bytes, x0 = g0 + a.gtile_bytes;
-        for (int hh = 0; hh < a.BH; ++hh) {
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t bd = mn_desc(g0 + (uint32_t)(hh * a.BW + kk * 16) * a.grow_bytes, a.b_lbo, a.bdesc_hi);
-            const uint32_t xo = (uint32_t)(hh * a.XW + kk * 16) * a.xrow_bytes;
-            for (int q = 0; q < a.nacc; ++q) {
-              const uint64_t ad = mn_desc(x0 + (uint32_t)a.acc_rt[q] * a.xtile_alloc + a.acc_off[q] + xo, a.a_lbo, a.adesc_hi);
-              if (leader) umma_bf16(tmem_base + (uint32_t)(q * a.N), ad, bd, a.idesc, accum);
+        const uint32_t g_lo = (base16 + (uint32_t)s * stage16) | b_lbo_bits;
+        const uint32_t x_lo = (base16 + (uint32_t)s * stage16 + gt16) | a_lbo_bits;
+        for (int hh = 0; hh < BH; ++hh) {
+          uint32_t a_k = x_lo + (uint32_t)hh * row_a, b_k = g_lo + (uint32_t)hh * row_b;
+          for (int kk = 0; kk < ksteps; ++kk, a_k += kstep_a, b_k += kstep_b) {
+            uint32_t d = tmem_base, a_rt = a_k;
+            for (int rt = 0; rt < n_rt; ++rt, a_rt += step_rt) {
+              uint32_t a_s = a_rt;
+              for (int ts = 0; ts < n_s; ++ts, a_s += step_s) {
+                uint32_t a_j = a_s;
+                for (int jb = 0; jb < n_jb; ++jb, a_j += step_jb, d += N)
+                  if (leader) umma_mn(d, a_j, a_hi, b_k, b_hi, idesc, accum);
+              }
             }
             accum = 1u;
           }
@@ -135,6 +159,7 @@ __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid
       tc_fence_after();
       const int quad = warp & 3;            // a warp may only touch its own TMEM lane quadrant
       const int m = quad * 32 + lane;
+      const bool vec4 = (a.Cout & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.dw) & 15) == 0);
       for (int q = 0; q < a.nacc; ++q) {
         const int sft = a.small ? m / a.blk : 0;
         const int s = a.acc_s0[q] + sft;
@@ -146,10 +171,19 @@ __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * a.N + c0), v);
           tmem_ld_wait();
           if (valid) {
+            if (vec4 && c0 + 16 <= a.Cout) {
+              // 16-byte reductions: 4 L2 operations per 16 channels instead of 16
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float f = __uint_as_float(v[j]);
-              if (c0 + j < a.Cout && f != 0.f) atomicAdd(dst + c0 + j, f);
+              for (int j = 0; j < 16; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float f = __uint_as_float(v[j]);
+                if (c0 + j < a.Cout && f != 0.f) atomicAdd(dst + c0 + j, f);
+              }
             }
           }
         }
@@ -218,31 +252,34 @@ static bool wgu_plan(const EsnConv* p, WguArgs& a, int& ngroups, bool with_maps)
   const int nblk = 128 / cbx;                                  // taps per MMA in the small case
   const int nmma_s = (p->kw + nblk - 1) / nblk;
   const int acc_per_row = a.small ? nmma_s : p->kw * ((a.nxbox + 1) / 2);
-  a.nrt = p->kh;
-  if (acc_per_row * a.nrt * a.N > 512 || acc_per_row * a.nrt > kMaxAcc) a.nrt = 1;
-  if (acc_per_row * a.nrt * a.N > 512 || acc_per_row * a.nrt > kMaxAcc) return false;
-  ngroups = p->kh / a.nrt;
-  a.nacc = acc_per_row * a.nrt;
-  a.tmem_cols = 32;
-  while (a.tmem_cols < a.nacc * a.N) a.tmem_cols *= 2;
-
   a.BW = dy.w >= 128 ? 128 : (dy.w + 15) / 16 * 16;
   a.XW = a.BW + (p->kw - 1) * p->dil_w;
   if (a.XW > 256) return false;
   const int junk_px = a.small ? (nmma_s * nblk - p->kw) * p->dil_w : 0;
-  a.BH = 256 / a.BW > dy.h ? dy.h : 256 / a.BW;
-  if (a.BH < 1) a.BH = 1;
-  for (;; --a.BH) {
-    a.xbox_alloc = round_up((uint32_t)(a.BH * a.XW + junk_px) * a.xrow_bytes, 1024);
-    a.xtile_alloc = a.xbox_alloc * (a.small ? 1 : (a.nxbox + 1) / 2 * 2);
-    a.gbox_bytes = round_up((uint32_t)(a.BH * a.BW) * a.grow_bytes, 1024);
-    a.gtile_bytes = a.gbox_bytes * a.ngbox;
-    a.stage_bytes = a.gtile_bytes + a.nrt * a.xtile_alloc;
-    a.stages = (int)((lim.max_smem - 1024 - 4096 - 256) / (long long)a.stage_bytes);
-    if (a.stages >= 3 || a.BH == 1) break;
+  bool planned = false;
+  for (int attempt = 0; attempt < 2 && !planned; ++attempt) {
+    a.nrt = attempt == 0 ? p->kh : 1;               // all filter rows in one CTA, else one CTA group per filter row
+    if (attempt == 1 && p->kh == 1) break;
+    if (acc_per_row * a.nrt * a.N > 512 || acc_per_row * a.nrt > kMaxAcc) continue;
+    a.BH = 256 / a.BW > dy.h ? dy.h : 256 / a.BW;
+    if (a.BH < 1) a.BH = 1;
+    for (;; --a.BH) {
+      a.xbox_alloc = round_up((uint32_t)(a.BH * a.XW + junk_px) * a.xrow_bytes, 1024);
+      a.xtile_alloc = a.xbox_alloc * (a.small ? 1 : (a.nxbox + 1) / 2 * 2);
+      a.gbox_bytes = round_up((uint32_t)(a.BH * a.BW) * a.grow_bytes, 1024);
+      a.gtile_bytes = a.gbox_bytes * a.ngbox;
+      a.stage_bytes = a.gtile_bytes + a.nrt * a.xtile_alloc;
+      a.stages = (int)((lim.max_smem - 1024 - 4096 - 256) / (long long)a.stage_bytes);
+      if (a.stages >= 3 || a.BH == 1) break;
+    }
+    planned = a.stages >= 2;
   }
-  if (a.stages < 2) return false;
+  if (!planned) return false;
   if (a.stages > 8) a.stages = 8;
+  ngroups = p->kh / a.nrt;
+  a.nacc = acc_per_row * a.nrt;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.nacc * a.N) a.tmem_cols *= 2;
   a.load_bytes = (uint32_t)(a.ngbox * a.BH * a.BW) * a.grow_bytes + (uint32_t)(a.nrt * a.nxbox * a.BH * a.XW) * a.xrow_bytes;
   a.tiles_w = (dy.w + a.BW - 1) / a.BW;
   a.tiles_h = (dy.h + a.BH - 1) / a.BH;
@@ -254,6 +291,10 @@ static bool wgu_plan(const EsnConv* p, WguArgs& a, int& ngroups, bool with_maps)
   a.b_lbo = a.gbox_bytes;
   if ((a.a_lbo >> 4) > 0x3FFFu) return false;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
+  a.loop_s = a.small ? nmma_s : p->kw;
+  a.loop_jb = a.small ? 1 : (a.nxbox + 1) / 2;
+  a.step_s = (uint32_t)((a.small ? nblk : 1) * p->dil_w) * a.xrow_bytes;
+  a.step_jb = 2 * a.xbox_alloc;
   int q = 0;
   for (int rt = 0; rt < a.nrt; ++rt) {
     if (a.small) {

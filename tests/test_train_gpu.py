@@ -76,6 +76,8 @@ WG_CASES = [
     (384, 64, 1, 1, 0, 1, 1, 8, 16),        # linear-bottleneck projection / expansion
     (96, 576, 1, 1, 0, 1, 1, 4, 8),
     (128, 128, 3, 1, 1, 1, 128, 8, 16),
+    (32, 32, (1, 3), 1, (0, 1), (1, 1), 32, 10, 37),     # depthwise sliding-window wgrad, ragged segments
+    (64, 64, 3, 1, 1, 1, 64, 9, 300),
     (8, 6, 1, 1, 0, 1, 1, 12, 20),          # tiny dense convs: one thread per weight element
     (3, 3, 3, 1, 1, 1, 1, 9, 14),
 ]
