@@ -422,8 +422,7 @@ def main():
                       "note": "block-fused algorithmic bytes (SURVEY 8d) and conv FLOPs of the whole forward / step time"}
 
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
+        _finish(dist)
         return
     line = {"metric": "images/s", "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -440,8 +439,21 @@ def main():
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
     emit(line)
+    _finish(dist)
+
+
+def _finish(dist):
+    """Leave without tearing NCCL down: communicators whose collectives were captured into a CUDA graph (the graphed
+    training step) can block in destroy_process_group / interpreter shutdown, which would hang the launcher after the
+    JSON line has been printed.  All device work is complete here (synchronised above)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if dist:
-        dist.destroy_process_group()
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":
