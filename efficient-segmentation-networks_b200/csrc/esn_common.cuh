@@ -86,6 +86,18 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   return v;
 }
 
+// Blackwell packed fp32 FMA (FFMA2): two lanes per instruction -- for the fp32-issue-bound kernels
+// (DABNet depthwise pair, ERFNet 2x2 transposed-conv head) halving the FMA instruction count is the lever; each lane
+// is an ordinary fma.rn.f32, so results are bit-identical to the scalar form.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;}\n"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 // Device-side copy of the epilogue description.
 struct EpiArgs {
   const float* scale;

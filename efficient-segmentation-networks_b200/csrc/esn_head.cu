@@ -143,26 +143,29 @@ __global__ void __launch_bounds__(128) convt2x2_head_vec_kernel(const ConvtHeadA
     for (int o = 0; o < 8; ++o) { best[o] = -INFINITY; bi[o] = 0; }
 #pragma unroll 1
     for (int q = 0; q < ncls4; ++q) {
-      float acc[4][8];  // [class in quad][output pixel = 2*p + s]
+      float2 acc2[2][8];  // [class pair in quad][output pixel = 2*p + s]: packed FFMA2, two classes per instruction
       const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
 #pragma unroll
-      for (int o = 0; o < 8; ++o) { acc[0][o] = b.x; acc[1][o] = b.y; acc[2][o] = b.z; acc[3][o] = b.w; }
+      for (int o = 0; o < 8; ++o) { acc2[0][o] = make_float2(b.x, b.y); acc2[1][o] = make_float2(b.z, b.w); }
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
         const float4 w0 = *reinterpret_cast<const float4*>(sw + (size_t)((r * 2 + 0) * CIN + c) * 32 + 4 * q);
         const float4 w1 = *reinterpret_cast<const float4*>(sw + (size_t)((r * 2 + 1) * CIN + c) * 32 + 4 * q);
+        const float2 w0a = make_float2(w0.x, w0.y), w0b = make_float2(w0.z, w0.w);
+        const float2 w1a = make_float2(w1.x, w1.y), w1b = make_float2(w1.z, w1.w);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float v = f[p][c];
-          acc[0][2 * p] = fmaf(v, w0.x, acc[0][2 * p]);
-          acc[1][2 * p] = fmaf(v, w0.y, acc[1][2 * p]);
-          acc[2][2 * p] = fmaf(v, w0.z, acc[2][2 * p]);
-          acc[3][2 * p] = fmaf(v, w0.w, acc[3][2 * p]);
-          acc[0][2 * p + 1] = fmaf(v, w1.x, acc[0][2 * p + 1]);
-          acc[1][2 * p + 1] = fmaf(v, w1.y, acc[1][2 * p + 1]);
-          acc[2][2 * p + 1] = fmaf(v, w1.z, acc[2][2 * p + 1]);
-          acc[3][2 * p + 1] = fmaf(v, w1.w, acc[3][2 * p + 1]);
+          const float2 vv = make_float2(f[p][c], f[p][c]);
+          acc2[0][2 * p] = ffma2(vv, w0a, acc2[0][2 * p]);
+          acc2[1][2 * p] = ffma2(vv, w0b, acc2[1][2 * p]);
+          acc2[0][2 * p + 1] = ffma2(vv, w1a, acc2[0][2 * p + 1]);
+          acc2[1][2 * p + 1] = ffma2(vv, w1b, acc2[1][2 * p + 1]);
         }
+      }
+      float acc[4][8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        acc[0][o] = acc2[0][o].x; acc[1][o] = acc2[0][o].y; acc[2][o] = acc2[1][o].x; acc[3][o] = acc2[1][o].y;
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {

@@ -18,17 +18,6 @@ struct DabArgs {
   int N, H, W, C, x_cs, y_cs, d;
 };
 
-// Blackwell packed fp32 FMA (FFMA2): two lanes per instruction -- this kernel is fp32-issue-bound (~40 fp32 ops
-// per channel-pixel against 4 bytes of HBM traffic), so halving the FMA instruction count is the lever.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;}\n"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
 __device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
   const float2 lo = ffma2(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
   const float2 hi = ffma2(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w));
