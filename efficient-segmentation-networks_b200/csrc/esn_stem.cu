@@ -16,12 +16,8 @@ struct StemArgs {
   EpiArgs ep;
 };
 
-// One thread = PX (2) horizontally adjacent output pixels: the 27 weight vectors are read from shared memory once for
-// both (the single-pixel form issued 2 LDS.128 per 4 FFMA2 and was shared-memory-issue-bound), FMAs are packed FFMA2
-// over channel pairs.
 template <typename TO, int CPAD>
 __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
-  constexpr int PX = 2;
   __shared__ float sw[27 * CPAD];
   __shared__ float sp[3 * CPAD];
   for (int i = threadIdx.x; i < 27 * CPAD; i += blockDim.x) {
@@ -35,88 +31,70 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
     sp[2 * CPAD + i] = (in && a.ep.act == ESN_ACT_PRELU) ? a.ep.alpha[i] : 0.f;
   }
   __syncthreads();
-  const int Wq = (a.Wo + PX - 1) / PX;
-  const long long total = (long long)a.N * a.Ho * Wq;
+  const long long total = (long long)a.N * a.Ho * a.Wo;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int wo0 = (int)(idx % Wq) * PX;
-  const int ho = (int)((idx / Wq) % a.Ho);
-  const int n = (int)(idx / ((long long)Wq * a.Ho));
+  const int wo = (int)(idx % a.Wo);
+  const int ho = (int)((idx / a.Wo) % a.Ho);
+  const int n = (int)(idx / ((long long)a.Wo * a.Ho));
   const size_t plane = (size_t)a.H * a.W;
   const float* xb = a.x + (size_t)n * 3 * plane;
 
-  float v[PX][27];
-  unsigned okmask[PX];   // bit (r*3+s): tap inside the image (needed by the 3x3 pool: padding is -inf there)
+  float v[27];
+  unsigned okmask = 0;   // bit (r*3+s): tap inside the image (needed by the 3x3 pool: padding is -inf there)
 #pragma unroll
-  for (int q = 0; q < PX; ++q) {
-    okmask[q] = 0;
+  for (int r = 0; r < 3; ++r) {
+    const int hi = 2 * ho - a.pad + r;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int hi = 2 * ho - a.pad + r;
+    for (int s = 0; s < 3; ++s) {
+      const int wi = 2 * wo - a.pad + s;
+      const bool ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+      okmask |= (ok ? 1u : 0u) << (r * 3 + s);
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int wi = 2 * (wo0 + q) - a.pad + s;
-        const bool ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-        okmask[q] |= (ok ? 1u : 0u) << (r * 3 + s);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[q][(r * 3 + s) * 3 + c] = ok ? __ldg(xb + c * plane + (size_t)hi * a.W + wi) : 0.f;
-      }
+      for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(xb + c * plane + (size_t)hi * a.W + wi) : 0.f;
     }
   }
-  float2 acc2[PX][CPAD / 2];
+  float acc[CPAD];
 #pragma unroll
-  for (int q = 0; q < PX; ++q)
-#pragma unroll
-    for (int c = 0; c < CPAD / 2; ++c) acc2[q][c] = make_float2(0.f, 0.f);
+  for (int c = 0; c < CPAD; ++c) acc[c] = 0.f;
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
 #pragma unroll
     for (int c4 = 0; c4 < CPAD; c4 += 4) {
       const float4 wv = *reinterpret_cast<const float4*>(sw + t * CPAD + c4);
-      const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
+      acc[c4] = fmaf(v[t], wv.x, acc[c4]);
+      acc[c4 + 1] = fmaf(v[t], wv.y, acc[c4 + 1]);
+      acc[c4 + 2] = fmaf(v[t], wv.z, acc[c4 + 2]);
+      acc[c4 + 3] = fmaf(v[t], wv.w, acc[c4 + 3]);
+    }
+  }
+  if (a.with_pool) {  // 1: taps (1,1),(1,2),(2,1),(2,2) = the 2x2 window; 2: all valid taps = MaxPool2d(3,2,1)
 #pragma unroll
-      for (int q = 0; q < PX; ++q) {
-        const float2 vv = make_float2(v[q][t], v[q][t]);
-        acc2[q][c4 / 2] = ffma2(vv, wa, acc2[q][c4 / 2]);
-        acc2[q][c4 / 2 + 1] = ffma2(vv, wb, acc2[q][c4 / 2 + 1]);
+    for (int c = 0; c < 3; ++c) {
+      float m;
+      if (a.with_pool == 2) {
+        m = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          if (okmask & (1u << t)) m = fmaxf(m, v[t * 3 + c]);
+      } else {
+        m = fmaxf(fmaxf(v[(1 * 3 + 1) * 3 + c], v[(1 * 3 + 2) * 3 + c]),
+                  fmaxf(v[(2 * 3 + 1) * 3 + c], v[(2 * 3 + 2) * 3 + c]));
       }
+#pragma unroll
+      for (int k = 0; k < CPAD; ++k)
+        if (k == a.cconv + c) acc[k] = m;
     }
   }
 #pragma unroll
-  for (int q = 0; q < PX; ++q) {
-    if (wo0 + q < a.Wo) {
-    float acc[CPAD];
-#pragma unroll
-    for (int c = 0; c < CPAD / 2; ++c) { acc[2 * c] = acc2[q][c].x; acc[2 * c + 1] = acc2[q][c].y; }
-    float m[3] = {0.f, 0.f, 0.f};
-    if (a.with_pool) {  // 1: taps (1,1),(1,2),(2,1),(2,2) = the 2x2 window; 2: all valid taps = MaxPool2d(3,2,1)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (a.with_pool == 2) {
-          m[c] = -INFINITY;
-#pragma unroll
-          for (int t = 0; t < 9; ++t)
-            if (okmask[q] & (1u << t)) m[c] = fmaxf(m[c], v[q][t * 3 + c]);
-        } else {
-          m[c] = fmaxf(fmaxf(v[q][(1 * 3 + 1) * 3 + c], v[q][(1 * 3 + 2) * 3 + c]),
-                       fmaxf(v[q][(2 * 3 + 1) * 3 + c], v[q][(2 * 3 + 2) * 3 + c]));
-        }
-      }
-    }
-    const int pc = a.with_pool ? a.cconv : CPAD;     // first pooled channel (selects, no dynamic register indexing)
-#pragma unroll
-    for (int c = 0; c < CPAD; ++c) {
-      float t = acc[c];
-      t = (c == pc) ? m[0] : ((c == pc + 1) ? m[1] : ((c == pc + 2) ? m[2] : t));
-      t = fmaf(t, sp[c], sp[CPAD + c]);
-      acc[c] = apply_act(t, a.ep.act, sp[2 * CPAD + c]);
-    }
-    TO* yp = reinterpret_cast<TO*>(a.y) + ((size_t)((size_t)n * a.Ho + ho) * a.Wo + wo0 + q) * a.y_cs;
-#pragma unroll
-    for (int c4 = 0; c4 < CPAD; c4 += 4)
-      if (c4 < a.ctot) st4<TO>(yp + c4, make_float4(acc[c4], acc[c4 + 1], acc[c4 + 2], acc[c4 + 3]));
-    }
+  for (int c = 0; c < CPAD; ++c) {
+    const float t = fmaf(acc[c], sp[c], sp[CPAD + c]);
+    acc[c] = apply_act(t, a.ep.act, sp[2 * CPAD + c]);
   }
+  TO* yp = reinterpret_cast<TO*>(a.y) + (size_t)idx * a.y_cs;
+#pragma unroll
+  for (int c4 = 0; c4 < CPAD; c4 += 4)
+    if (c4 < a.ctot) st4<TO>(yp + c4, make_float4(acc[c4], acc[c4 + 1], acc[c4 + 2], acc[c4 + 3]));
 }
 
 }  // namespace
@@ -153,7 +131,7 @@ extern "C" int esn_stem_conv3x3s2(const EsnStem* p, void* stream) {
   a.with_pool = pool;
   a.pad = pad;
   a.ep = make_epi(p->ep);
-  const long long total = (long long)y.n * y.h * ((y.w + 1) / 2);   // one thread per pair of output pixels
+  const long long total = (long long)y.n * y.h * y.w;
   const int block = 128, grid = esn_cdiv(total, block);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool c16 = ctot <= 16;
