@@ -25,6 +25,15 @@ extern std::atomic<long long> g_esn_launches;
 
 static inline int esn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// One-time initialisation is per DEVICE (cudaFuncSetAttribute applies to the current device only, and under the
+// reference's nn.DataParallel one process drives several GPUs from one thread each, train.py:166-168).
+constexpr int kEsnMaxDevices = 64;
+static inline int esn_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kEsnMaxDevices) dev = 0;
+  return dev;
+}
+
 // ---- element access: T in {float, __nv_bfloat16} ---------------------------------
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return __ldg(p); }

@@ -243,6 +243,65 @@ void launch_pw_vec(const PwArgs& a, cudaStream_t st) {
   pw_vec_kernel<TI, TO, V, OP><<<grid, 256, 0, st>>>(a, ncg, ppb, wpb);
 }
 
+// MaxPool2d(2,2) + affine + activation into a channel slice whose start is NOT 16-byte aligned (DABNet's first
+// DownSamplingBlock writes the 35 pooled channels at channel 29 of its 64-channel output, DABNet.py:104-108).  The
+// scalar path did 4 x 35 two-byte loads per output pixel; here a thread owns one ALIGNED 16-byte vector of the output
+// row (slice channels 8j-OFF .. 8j-OFF+7), reads the two aligned input vectors that straddle it for each of the four
+// window pixels, and stores the vector whole when all 8 channels belong to the slice (per-channel stores at the two ends).
+template <int OFF>
+__global__ void __launch_bounds__(256) maxpool2x2_shift_kernel(const PwArgs a, const int nv) {
+  const long long total = (long long)a.N * a.Ho * a.Wo * nv;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % nv);
+  const long long pix = idx / nv;
+  const int wo = (int)(pix % a.Wo);
+  const int ho = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  const int k0 = 8 * j - OFF;                      // first slice channel of this output vector
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat16* px = x + ((size_t)((size_t)n * a.Hi + 2 * ho + (q >> 1)) * a.Wi + 2 * wo + (q & 1)) * a.x_cs;
+    float fa[8], fb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fa[i] = fb[i] = -INFINITY;
+    if (OFF > 0 && j >= 1) bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(px + 8 * (j - 1))), fa);
+    if (8 * j < a.x_cs) bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(px + 8 * j)), fb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float v = (i < OFF) ? fa[8 - OFF + i] : fb[i - OFF];     // input channel k0 + i
+      m[i] = fmaxf(m[i], v);
+    }
+  }
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)pix * a.y_cs + k0;   // 16-byte aligned
+  float o[8];
+  bool all = true;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + i;
+    const bool ok = k >= 0 && k < a.C;
+    all = all && ok;
+    float t = 0.f;
+    if (ok) {
+      const float sc = a.ep.scale ? __ldg(a.ep.scale + k) : 1.f, sh = a.ep.shift ? __ldg(a.ep.shift + k) : 0.f;
+      const float al = a.ep.act == ESN_ACT_PRELU ? __ldg(a.ep.alpha + k) : 0.f;
+      t = apply_act(fmaf(m[i], sc, sh), a.ep.act, al);
+    }
+    o[i] = t;
+  }
+  if (all) {
+    *reinterpret_cast<uint4*>(yp) = float_to_bf16x8(o);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k0 + i >= 0 && k0 + i < a.C) yp[i] = __float2bfloat16_rn(o[i]);
+  }
+}
+
 template <int OP>
 int run_pw(const EsnPool* p, void* stream) {
   if (!p) return ESN_ERR_BAD_ARG;
@@ -287,6 +346,27 @@ int run_pw(const EsnPool* p, void* stream) {
       ESN_CHECK_LAUNCH();
       return ESN_OK;
     }
+  }
+  static const bool pool_noshift = getenv("ESN_POOL_NOSHIFT") != nullptr;
+  if (OP == OP_MAXPOOL2 && !nchw && x.dtype == ESN_BF16 && y.dtype == ESN_BF16 && !p->ep.residual.ptr && x.c_stride % 8 == 0 &&
+      y.c_stride % 8 == 0 && (uintptr_t)x.ptr % 16 == 0 && (uintptr_t)y.ptr % 2 == 0 && !pool_noshift) {
+    // unaligned output slice: aligned-vector kernel shifted by OFF channels (elements outside the slice are never touched)
+    const int off = (int)(((uintptr_t)y.ptr / 2) % 8);
+    const int nv = (y.c + off + 7) / 8;
+    const long long total = (long long)y.n * y.h * y.w * nv;
+    const int grid = esn_cdiv(total, 256);
+    switch (off) {
+      case 1: maxpool2x2_shift_kernel<1><<<grid, 256, 0, st>>>(a, nv); break;
+      case 2: maxpool2x2_shift_kernel<2><<<grid, 256, 0, st>>>(a, nv); break;
+      case 3: maxpool2x2_shift_kernel<3><<<grid, 256, 0, st>>>(a, nv); break;
+      case 4: maxpool2x2_shift_kernel<4><<<grid, 256, 0, st>>>(a, nv); break;
+      case 5: maxpool2x2_shift_kernel<5><<<grid, 256, 0, st>>>(a, nv); break;
+      case 6: maxpool2x2_shift_kernel<6><<<grid, 256, 0, st>>>(a, nv); break;
+      case 7: maxpool2x2_shift_kernel<7><<<grid, 256, 0, st>>>(a, nv); break;
+      default: maxpool2x2_shift_kernel<0><<<grid, 256, 0, st>>>(a, nv); break;
+    }
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
   }
   const bool v4 = (y.c % 4 == 0) && (y.c_stride % 4 == 0) && ((uintptr_t)y.ptr % (4 * ysz) == 0) &&
                   (nchw || ((x.c_stride % 4 == 0) && ((uintptr_t)x.ptr % (4 * xsz) == 0)));

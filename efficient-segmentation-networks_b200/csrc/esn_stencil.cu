@@ -214,10 +214,11 @@ __global__ void __launch_bounds__(256) dab_dw_pair_row_kernel(const DabArgs a, c
 template <typename TI, typename TO>
 static int launch_dab_row(const DabArgs& a, int CC, size_t smem, cudaStream_t st) {
   auto kfn = dab_dw_pair_row_kernel<TI, TO>;
-  static bool attr_done = false;   // per instantiation; idempotent, so a race only repeats the call
-  if (!attr_done) {
+  static std::atomic<bool> attr_done[kEsnMaxDevices];   // per instantiation and device; idempotent, a race only repeats the call
+  const int dev = esn_current_device();
+  if (!attr_done[dev].load(std::memory_order_acquire)) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return ESN_ERR_CUDA;
-    attr_done = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   const int nchunk = a.C / CC;
   kfn<<<(unsigned)((long long)a.N * a.H * nchunk), 256, smem, st>>>(a, CC, nchunk);

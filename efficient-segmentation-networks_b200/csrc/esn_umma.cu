@@ -624,11 +624,11 @@ struct DeviceLimits {
   int max_smem = 0;
 };
 const DeviceLimits& limits() {
-  static DeviceLimits l;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static DeviceLimits ls[kEsnMaxDevices];
+  static std::once_flag once[kEsnMaxDevices];
+  const int dev = esn_current_device();
+  std::call_once(once[dev], [dev] {
+    DeviceLimits& l = ls[dev];
     cudaDeviceGetAttribute(&l.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&l.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
@@ -639,7 +639,7 @@ const DeviceLimits& limits() {
     ESN_SET_SMEM(64, MODE_GENERIC); ESN_SET_SMEM(64, MODE_HREUSE); ESN_SET_SMEM(64, MODE_VREUSE);
 #undef ESN_SET_SMEM
   });
-  return l;
+  return ls[dev];
 }
 
 }  // namespace

@@ -555,11 +555,11 @@ struct PairLimits {
   int sms = 0, max_smem = 0;
 };
 const PairLimits& pair_limits() {
-  static PairLimits l;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static PairLimits ls[kEsnMaxDevices];
+  static std::once_flag once[kEsnMaxDevices];
+  const int dev = esn_current_device();
+  std::call_once(once[dev], [dev] {
+    PairLimits& l = ls[dev];
     cudaDeviceGetAttribute(&l.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&l.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
@@ -567,7 +567,7 @@ const PairLimits& pair_limits() {
     cudaFuncSetAttribute(conv_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.max_smem);
     cudaFuncSetAttribute(conv_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.max_smem);
   });
-  return l;
+  return ls[dev];
 }
 
 }  // namespace

@@ -201,18 +201,18 @@ struct WguLimits {
   int sms = 0, max_smem = 0;
 };
 const WguLimits& wgu_limits() {
-  static WguLimits l;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static WguLimits ls[kEsnMaxDevices];
+  static std::once_flag once[kEsnMaxDevices];
+  const int dev = esn_current_device();
+  std::call_once(once[dev], [dev] {
+    WguLimits& l = ls[dev];
     cudaDeviceGetAttribute(&l.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&l.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, wgrad_umma_kernel) == cudaSuccess) l.max_smem -= (int)fa.sharedSizeBytes;
     cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.max_smem);
   });
-  return l;
+  return ls[dev];
 }
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

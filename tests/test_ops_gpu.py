@@ -153,6 +153,29 @@ def test_pools_affine_convert(ops):
         assert torch.allclose(back, x.to(dt).float())
 
 
+@pytest.mark.parametrize("c,start,ctot", [(35, 29, 64), (3, 13, 16), (19, 2, 32), (40, 24, 64), (35, 0, 40)])
+def test_maxpool_into_unaligned_channel_slice(ops, c, start, ctot):
+    """MaxPool2d(2,2) + BN + PReLU written into a channel slice that does not start on a 16-byte boundary
+    (DABNet.py:104-108: 35 pooled channels at channel 29 of the 64-channel block output): aligned-vector kernel with a
+    channel shift; the neighbouring channels of the buffer must stay untouched."""
+    from esn._lib import ACT_PRELU
+    torch.manual_seed(5)
+    x = torch.randn(2, c, 12, 20, device="cuda")
+    xb = _nhwc(x, torch.bfloat16, ops, c_alloc=(c + 7) // 8 * 8)
+    out = ops.new_act(2, ctot, 6, 10, torch.bfloat16, x.device)
+    out.fill_(7.0)
+    scale = torch.rand(c, device="cuda") + 0.5
+    shift = torch.randn(c, device="cuda")
+    alpha = torch.rand(c, device="cuda") * 0.4
+    ops.maxpool2x2(xb, out[:, start:start + c], scale, shift, alpha, ACT_PRELU)
+    ref = F.max_pool2d(xb.float(), 2, 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = torch.where(ref >= 0, ref, ref * alpha.view(1, -1, 1, 1))
+    got = out.float()
+    assert (got[:, start:start + c] - ref).abs().max() <= 1e-2 * ref.abs().max()
+    assert torch.equal(got[:, :start], torch.full_like(got[:, :start], 7.0))
+    assert torch.equal(got[:, start + c:], torch.full_like(got[:, start + c:], 7.0))
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_dab_pair_matches_torch(ops, dt):
     """esn_dab_dw_pair (row kernel: stage-1 rows in shared memory) against torch: both DABNet module shapes, dilation 1,
