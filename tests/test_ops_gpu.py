@@ -153,6 +153,47 @@ def test_pools_affine_convert(ops):
         assert torch.allclose(back, x.to(dt).float())
 
 
+@pytest.mark.parametrize("cconv,pool,pad,act,H,W", [
+    (13, 1, 1, "relu", 24, 44),      # ERFNet DownsamplerBlock(3,16): conv || MaxPool2d(2,2)
+    (32, 0, 1, "prelu", 20, 70),     # DABNet Conv(3,32,3,2)+BNPReLU, ragged 16-pixel tiles
+    (13, 2, 1, "prelu", 18, 36),     # ENet InitialBlock: conv || MaxPool2d(3,2,1) (-inf padding)
+    (32, 0, 0, "relu", 33, 67),      # Fast-SCNN stem: padding 0, odd sizes
+    (16, 0, 1, "none", 8, 16),
+])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_stem_conv_matches_torch(ops, cconv, pool, pad, act, H, W, dt):
+    """esn_stem_conv3x3s2 on the NCHW fp32 image (bf16 output: the 3xTF32 tensor-core kernel; fp32 output: the FMA
+    kernel) against torch conv2d (+ pool concat) + affine + activation in fp32, borders included."""
+    from esn._lib import ACT_NONE, ACT_RELU, ACT_PRELU
+    torch.manual_seed(9)
+    x = (torch.randint(0, 256, (2, 3, H, W), device="cuda").float() - 80.0).contiguous()
+    w = torch.randn(cconv, 3, 3, 3, device="cuda") * 0.2
+    ctot = cconv + (3 if pool else 0)
+    scale = torch.rand(ctot, device="cuda") * 0.02 + 0.005
+    shift = torch.randn(ctot, device="cuda") * 0.3
+    alpha = torch.rand(ctot, device="cuda") * 0.4
+    Ho, Wo = (H + 2 * pad - 3) // 2 + 1, (W + 2 * pad - 3) // 2 + 1
+    out = ops.new_act(2, ctot, Ho, Wo, dt, x.device)
+    wd = w.permute(2, 3, 1, 0).reshape(9, 3, cconv).contiguous()
+    code = {"none": ACT_NONE, "relu": ACT_RELU, "prelu": ACT_PRELU}[act]
+    ops.stem_conv3x3s2(x, wd, cconv, pool | (0 if pad else 256), out, scale, shift, alpha if act == "prelu" else None, code)
+    ref = F.conv2d(x, w, None, 2, pad)
+    if pool == 1:
+        ref = torch.cat([ref, F.max_pool2d(x, 2, 2)], 1)
+    elif pool == 2:
+        ref = torch.cat([ref, F.max_pool2d(x, 3, 2, 1)], 1)
+    ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if act == "relu":
+        ref = torch.relu(ref)
+    elif act == "prelu":
+        ref = torch.where(ref >= 0, ref, ref * alpha.view(1, -1, 1, 1))
+    got = out.float()
+    assert got.shape == ref.shape
+    tol = (1e-5, 1e-5) if dt == torch.float32 else (8e-3, 2e-3)
+    err = (got - ref).abs()
+    assert bool((err <= tol[0] * ref.abs() + tol[1] * ref.abs().max()).all()), err.max().item()
+
+
 @pytest.mark.parametrize("c,start,ctot", [(35, 29, 64), (3, 13, 16), (19, 2, 32), (40, 24, 64), (35, 0, 40)])
 def test_maxpool_into_unaligned_channel_slice(ops, c, start, ctot):
     """MaxPool2d(2,2) + BN + PReLU written into a channel slice that does not start on a 16-byte boundary
