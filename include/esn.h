@@ -341,6 +341,13 @@ int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, 
 int esn_dropout_step(const EsnTensor* x, const EsnTensor* y, uint64_t seed, const uint64_t* step, float p,
                      int32_t per_channel, void* stream);
 
+/* Confusion matrix of predicted masks against labels, accumulated on the device: M[gt * nclass + pred] += 1 for every
+ * pixel with 0 <= gt < nclass (ignore label 255 skipped) -- ConfusionMatrix.generateM, utils/metric/metric.py:68-76, as
+ * called by get_iou from test.py:90 / train.py:404.  pred: uint8 [n_pixels] (the fused argmax masks); gt: uint8 or int64
+ * [n_pixels]; M: uint64 [nclass * nclass], zeroed by the caller before the first batch; nclass <= 32. */
+int esn_confusion_matrix(const uint8_t* pred, const void* gt, int32_t gt_is_int64, int64_t n_pixels, int32_t nclass,
+                         uint64_t* M, void* stream);
+
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);
 const char* esn_strerror(int code);
