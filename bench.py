@@ -431,7 +431,10 @@ def main():
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms, 3), "steps": k_e2e,
-                    "note": "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"},
+                    "note": ("pinned fp32 NCHW images + int64 labels -> H2D -> one training iteration (forward, weighted CE, backward, "
+                             "all-reduce, Adam; CUDA graph: %s) -> D2H loss scalar; copies double-buffered on a side stream" % (gstep is not None))
+                    if train else
+                    "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}
