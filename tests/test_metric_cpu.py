@@ -19,3 +19,13 @@ def test_oracle_confusion_matrix_and_miou_match_reference():
     assert abs(mean - float(g["meanIoU"])) < 1e-12
     assert np.allclose(per_class, g["per_class"], rtol=0, atol=1e-12)
     assert int(M.sum()) == int((g["gt"] < nclass).sum())                # ignore label skipped, nothing else
+
+
+def test_host_jaccard_matches_reference():
+    """esn.metric.jaccard_from_matrix (the host half of the device metric) on the reference's golden matrix."""
+    from esn.metric import jaccard_from_matrix
+    g = np.load(GOLD)
+    mean, per_class, M = jaccard_from_matrix(g["M"])
+    assert mean == float(g["meanIoU"])
+    assert np.array_equal(np.asarray(per_class), g["per_class"])
+    assert M is not None and M.shape == (int(g["nclass"]),) * 2
