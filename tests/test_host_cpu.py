@@ -68,3 +68,26 @@ def test_no_cpu_fallback():
         return
     with pytest.raises((RuntimeError, NotImplementedError)):
         m(torch.zeros(1, 3, 32, 64))
+
+
+def test_fused_transposed_conv_packing_equals_conv_transpose():
+    """Host logic of the phase-fused transposed conv (ops.ConvPrep.fused_convt, used for ERFNet's UpsamplerBlock:
+    ERFNet.py:109-112): ConvTranspose2d(3, s2, p1, op1) == ONE stride-1 conv with 2x2 taps and 4*Cout outputs ordered
+    (row parity, column parity, c) + pixel shuffle.  Pure torch on the CPU -- no kernel call."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from esn import ops
+    from esn._lib import ACT_RELU
+    torch.manual_seed(0)
+    for cin, cout in ((8, 4), (16, 16), (64, 16)):
+        m = nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1, bias=True)
+        prep = ops.ConvPrep(m, None, None, ACT_RELU, device="cpu")
+        wf, sc4, sh4, _ = prep.fused_convt()
+        assert tuple(wf.shape) == (4, 4 * cout, cin) and sh4.shape[0] == 4 * cout
+        x = torch.randn(2, cin, 5, 7).to(torch.bfloat16).float()
+        w = wf.float().view(2, 2, 4 * cout, cin).permute(2, 3, 0, 1)                  # [4*Cout][Cin][dy][dx]
+        y4 = F.conv2d(F.pad(x, (0, 1, 0, 1)), w) * sc4.view(1, -1, 1, 1) + sh4.view(1, -1, 1, 1)
+        y = y4.view(2, 2, 2, cout, 5, 7).permute(0, 3, 4, 1, 5, 2).reshape(2, cout, 10, 14)   # out[2i+a, 2j+b]
+        ref = F.conv_transpose2d(x, m.weight.detach().to(torch.bfloat16).float(), m.bias.detach(), 2, 1, 1)
+        assert (y - ref).abs().max() <= 2e-6 * ref.abs().max()
