@@ -11,6 +11,8 @@ from model.CGNet import CGNet
 from model.FastSCNN import FastSCNN
 from model.ESPNet import ESPNet
 from model.ESPNet_v2.SegmentationModel import EESPNet_Seg
+from model.ESNet import ESNet
+from model.ContextNet import ContextNet
 
 _HOT_PATH = {
     "ERFNet": ERFNet,
@@ -20,6 +22,9 @@ _HOT_PATH = {
     "FastSCNN": FastSCNN,
     "ESPNet_v2": EESPNet_Seg,
     "ESPNet": ESPNet,
+    # nets that reuse the ERFNet / Fast-SCNN kernels (inference)
+    "ESNet": ESNet,
+    "ContextNet": ContextNet,
 }
 _REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
                     "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")

@@ -1,0 +1,181 @@
+"""ESNet on B200 kernels -- drop-in for the reference's model/ESNet.py.
+
+Same class names, constructor signatures and attribute names (identical ``state_dict`` keys) as
+/root/reference/model/ESNet.py:12-193.  The net is ERFNet's block set with two variations, so it runs on
+ERFNet's kernels:
+
+* FCU(chann, kernel_size, dropprob, dilated) (ESNet.py:50-92): non_bottleneck_1d with k x 1 / 1 x k taps
+  (k = 3 or 5).  k = 3 takes the fused factorized-pair kernel, k = 5 runs as four tcgen05 implicit-GEMM
+  launches (5 taps x C = 64 fit the resident-weight budget) with bias / folded BN / ReLU / residual in the
+  epilogue.
+* PFCU(chann) (ESNet.py:95-151): one 3x1 -> 1x3 pair feeding three dilated (2, 5, 9) pairs that share bn2; the
+  three branch outputs and the block input are summed by chaining the residual operand of the three closing
+  1x3 launches -- relu(((x + o2) + o5) + o9), the reference's association order -- so no add kernel runs.
+* DownsamplerBlock / UpsamplerBlock / output_conv: ERFNet's (ESNet.py:12-48,182 == ERFNet.py:16-27,103-112,128).
+  The reference pads the pooled branch when the input height/width is odd (ESNet.py:25-29); odd sizes are
+  rejected here (Cityscapes shapes are even at every level).
+"""
+import torch
+import torch.nn as nn
+
+from esn import ops
+from esn._lib import ACT_NONE, ACT_RELU
+from esn.prep import PrepMixin
+from model.ERFNet import DownsamplerBlock as _ErfDownsamplerBlock
+from model.ERFNet import UpsamplerBlock as _ErfUpsamplerBlock
+from model.ERFNet import non_bottleneck_1d as _ErfFactorized
+from model.ERFNet import _no_train
+
+__all__ = ["ESNet"]
+
+
+class DownsamplerBlock(_ErfDownsamplerBlock):
+    def __init__(self, ninput, noutput):
+        super().__init__(ninput, noutput)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, input):
+        if (input.shape[2] | input.shape[3]) & 1:
+            raise NotImplementedError("ESNet DownsamplerBlock: odd input sizes (the F.pad path of ESNet.py:25-29) "
+                                      "are not supported; got %dx%d" % (input.shape[2], input.shape[3]))
+        return super().forward(input)
+
+
+class UpsamplerBlock(_ErfUpsamplerBlock):
+    pass
+
+
+class FCU(_ErfFactorized):
+    """Factorized convolution unit: non_bottleneck_1d with a kernel_size parameter (forward inherited)."""
+
+    def __init__(self, chann, kernel_size, dropprob, dilated):
+        nn.Module.__init__(self)
+        half = (kernel_size - 1) // 2
+        pad = half * dilated
+        self.conv3x1_1 = nn.Conv2d(chann, chann, (kernel_size, 1), stride=1, padding=(half, 0), bias=True)
+        self.conv1x3_1 = nn.Conv2d(chann, chann, (1, kernel_size), stride=1, padding=(0, half), bias=True)
+        self.bn1 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.conv3x1_2 = nn.Conv2d(chann, chann, (kernel_size, 1), stride=1, padding=(pad, 0), bias=True,
+                                   dilation=(dilated, 1))
+        self.conv1x3_2 = nn.Conv2d(chann, chann, (1, kernel_size), stride=1, padding=(0, pad), bias=True,
+                                   dilation=(1, dilated))
+        self.bn2 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.relu = nn.ReLU(inplace=True)
+        self.dropout = nn.Dropout2d(dropprob)
+
+
+class PFCU(PrepMixin, nn.Module):
+    """Parallel factorized convolution unit: three dilated branches (2, 5, 9) behind one shared pair."""
+    _RATES = (2, 5, 9)
+
+    def __init__(self, chann):
+        super().__init__()
+        self.conv3x1_1 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1, 0), bias=True)
+        self.conv1x3_1 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1), bias=True)
+        self.bn1 = nn.BatchNorm2d(chann, eps=1e-03)
+        for d in self._RATES:
+            setattr(self, "conv3x1_2%d" % d, nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(d, 0), bias=True,
+                                                       dilation=(d, 1)))
+            setattr(self, "conv1x3_2%d" % d, nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, d), bias=True,
+                                                       dilation=(1, d)))
+        self.bn2 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.dropout = nn.Dropout2d(0.3)
+
+    def _build_prep(self, device):
+        s1, b1 = ops.bn_affine(self.bn1, device)
+        s2, b2 = ops.bn_affine(self.bn2, device)       # one BatchNorm shared by the three branches (ESNet.py:129-147)
+        head = (ops.ConvPrep(self.conv3x1_1, act=ACT_RELU, device=device),
+                ops.ConvPrep(self.conv1x3_1, s1, b1, ACT_RELU, device=device))
+        branches = []
+        for i, d in enumerate(self._RATES):
+            last = i == len(self._RATES) - 1
+            branches.append((ops.ConvPrep(getattr(self, "conv3x1_2%d" % d), act=ACT_RELU, device=device),
+                             ops.ConvPrep(getattr(self, "conv1x3_2%d" % d), s2, b2, ACT_RELU if last else ACT_NONE,
+                                          device=device)))
+        return head, branches
+
+    def forward(self, input):
+        _no_train(self)            # eval: Dropout2d is the identity
+        x = ops.as_act(input)
+        (c1, c2), branches = self.prep(x.device)
+        n, c, h, w = x.shape
+        y = ops.new_act(n, c, h, w, x.dtype, x.device)
+        if ops.pair_supported(x, c1, c2, y, None):
+            ops.conv_pair(x, c1, c2, out=y)
+        else:
+            ops.conv2d(ops.conv2d(x, c1), c2, out=y)
+        acc = x
+        for ca, cb in branches:    # acc <- acc + bn2(branch(y)); the last launch also applies the ReLU
+            out = ops.new_act(n, c, h, w, x.dtype, x.device)
+            # the pair kernel is only exercised in ERFNet's configurations (ReLU closing epilogue)
+            if cb.act == ACT_RELU and ops.pair_supported(y, ca, cb, out, acc):
+                ops.conv_pair(y, ca, cb, out=out, residual=acc)
+            else:
+                ops.conv2d(ops.conv2d(y, ca), cb, out=out, residual=acc)
+            acc = out
+        return acc
+
+
+class ESNet(nn.Module):
+    def __init__(self, classes):
+        super().__init__()
+        self.initial_block = DownsamplerBlock(3, 16)
+        self.layers = nn.ModuleList()
+        for _ in range(3):
+            self.layers.append(FCU(16, 3, 0.03, 1))
+        self.layers.append(DownsamplerBlock(16, 64))
+        for _ in range(2):
+            self.layers.append(FCU(64, 5, 0.03, 1))
+        self.layers.append(DownsamplerBlock(64, 128))
+        for _ in range(3):
+            self.layers.append(PFCU(chann=128))
+        self.layers.append(UpsamplerBlock(128, 64))
+        self.layers.append(FCU(64, 5, 0, 1))
+        self.layers.append(FCU(64, 5, 0, 1))
+        self.layers.append(UpsamplerBlock(64, 16))
+        self.layers.append(FCU(16, 3, 0, 1))
+        self.layers.append(FCU(16, 3, 0, 1))
+        self.output_conv = nn.ConvTranspose2d(16, classes, 2, stride=2, padding=0, output_padding=0, bias=True)
+
+    def _head_prep(self, device):
+        """[dy][dx][Cin][32] fp32 taps of the 2x2 / stride-2 transposed conv (same packing as ERFNet's head); cached on
+        the identity and version of output_conv's two tensors only (not the whole net's parameter list)."""
+        wt, bs = self.output_conv.weight, self.output_conv.bias
+        sig = (str(device), wt.data_ptr(), wt._version, bs.data_ptr(), bs._version)
+        cached = self.__dict__.get("_esn_head")
+        if cached is None or cached[0] != sig:
+            w = wt.detach().to(device=device, dtype=torch.float32)      # (Cin, classes, 2, 2)
+            cin, classes = w.shape[0], w.shape[1]
+            packed = torch.zeros((2, 2, cin, 32), dtype=torch.float32, device=device)
+            packed[:, :, :, :classes] = w.permute(2, 3, 0, 1)
+            bias = bs.detach().to(device=device, dtype=torch.float32).contiguous()
+            cached = (sig, (packed.contiguous(), bias, classes))
+            self.__dict__["_esn_head"] = cached
+        return cached[1]
+
+    def _features(self, input):
+        ops.require_cuda(input, "ESNet")
+        if self.training:
+            raise NotImplementedError("ESNet: training-mode kernels are not wired for this model; call .eval(). "
+                                      "There is no eager-PyTorch fallback.")
+        if (input.shape[2] | input.shape[3]) % 8:
+            raise NotImplementedError("ESNet: input height and width must be multiples of 8, got %dx%d"
+                                      % (input.shape[2], input.shape[3]))
+        output = self.initial_block(input)
+        for layer in self.layers:
+            output = layer(output)
+        return output
+
+    def _head(self, feat, want_logits, want_mask):
+        w, b, classes = self._head_prep(feat.device)
+        ldt = torch.bfloat16 if feat.dtype == torch.bfloat16 else torch.float32
+        return ops.head_convt2x2(feat, w, b, classes, want_logits, want_mask, ldt)
+
+    def forward(self, input):
+        return self._head(self._features(input), True, False)[0]
+
+    @torch.no_grad()
+    def predict_mask(self, input, with_logits=False):
+        """uint8 (N,H,W) argmax mask from the head kernel's fp32 accumulators (replaces test.py:79-82)."""
+        logits, mask = self._head(self._features(input), with_logits, True)
+        return (logits, mask) if with_logits else mask

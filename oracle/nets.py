@@ -558,3 +558,92 @@ def espnet(sd, x, train=False, stats=None):
 
 
 FORWARD["ESPNet"] = espnet
+
+
+# --------------------------------------------------------------------------- ESNet
+def es_fcu(p, x, k, d):
+    """FCU(chann, kernel_size=k, dropprob, dilated=d) (dropout p=0 / eval), model/ESNet.py:50-92."""
+    h = (k - 1) // 2
+    y = F.relu(F.conv2d(x, p["conv3x1_1.weight"], p["conv3x1_1.bias"], padding=(h, 0)))
+    y = F.conv2d(y, p["conv1x3_1.weight"], p["conv1x3_1.bias"], padding=(0, h))
+    y = F.relu(bn(p.sub("bn1"), y, 1e-3))
+    y = F.relu(F.conv2d(y, p["conv3x1_2.weight"], p["conv3x1_2.bias"], padding=(h * d, 0), dilation=(d, 1)))
+    y = F.conv2d(y, p["conv1x3_2.weight"], p["conv1x3_2.bias"], padding=(0, h * d), dilation=(1, d))
+    return F.relu(x + bn(p.sub("bn2"), y, 1e-3))
+
+
+def es_pfcu(p, x):
+    """PFCU(chann) (eval), model/ESNet.py:95-151: three dilated branches (2, 5, 9) share bn2."""
+    y = F.relu(F.conv2d(x, p["conv3x1_1.weight"], p["conv3x1_1.bias"], padding=(1, 0)))
+    y = F.conv2d(y, p["conv1x3_1.weight"], p["conv1x3_1.bias"], padding=(0, 1))
+    y = F.relu(bn(p.sub("bn1"), y, 1e-3))
+    acc = x
+    for d in (2, 5, 9):
+        o = F.relu(F.conv2d(y, p["conv3x1_2%d.weight" % d], p["conv3x1_2%d.bias" % d], padding=(d, 0), dilation=(d, 1)))
+        o = F.conv2d(o, p["conv1x3_2%d.weight" % d], p["conv1x3_2%d.bias" % d], padding=(0, d), dilation=(1, d))
+        acc = acc + bn(p.sub("bn2"), o, 1e-3)
+    return F.relu(acc)
+
+
+# ESNet.py:162-180: ("down",) | ("fcu", k) | ("pfcu",) | ("up",)
+ES_LAYERS = ([("fcu", 3)] * 3 + [("down",)] + [("fcu", 5)] * 2 + [("down",)] + [("pfcu",)] * 3 +
+             [("up",), ("fcu", 5), ("fcu", 5), ("up",), ("fcu", 3), ("fcu", 3)])
+
+
+def esnet(sd, x, train=False, stats=None):
+    """ESNet.forward, model/ESNet.py:184-193 (even input sizes: the F.pad of :25-29 is a no-op)."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = erf_downsampler(p.sub("initial_block"), x)
+    for i, spec in enumerate(ES_LAYERS):
+        q = p.sub("layers.%d" % i)
+        if spec[0] == "down":
+            y = erf_downsampler(q, y)
+        elif spec[0] == "up":
+            y = erf_upsampler(q, y)
+        elif spec[0] == "pfcu":
+            y = es_pfcu(q, y)
+        else:
+            y = es_fcu(q, y, spec[1], 1)
+    return F.conv_transpose2d(y, p["output_conv.weight"], p["output_conv.bias"], stride=2)
+
+
+FORWARD["ESNet"] = esnet
+
+
+# --------------------------------------------------------------------------- ContextNet (SURVEY 8f-2)
+def _cx_bottlenecks(g, y):
+    """Deep_net's six LinearBottleneck stages, model/ContextNet.py:101-133 (block = FastSCNN's, :58-74)."""
+    cin = 32
+    for idx, (cout, t, nblk, stride) in enumerate(zip((32, 32, 48, 64, 96, 128), (1, 6, 6, 6, 6, 6),
+                                                      (1, 1, 3, 3, 2, 2), (1, 1, 2, 2, 1, 1))):
+        for i in range(nblk):
+            s = stride if i == 0 else 1
+            ci = cin if i == 0 else cout
+            y = _fs_bottleneck(g.sub("bottleneck%d.%d" % (idx + 1, i)), y, s, s == 1 and ci == cout)
+        cin = cout
+    return y
+
+
+def contextnet(sd, x, train=False, stats=None):
+    """ContextNet.forward (aux=False, eval), model/ContextNet.py:180-226: full-resolution shallow branch,
+    quarter-resolution deep branch (bilinear align_corners=True), feature fusion, classifier, bilinear to input size."""
+    p = SD(sd, "", x.dtype, train, stats)
+    q = p.sub("spatial_detail")
+    hi = _fs_cbr(q.sub("conv"), x, 2, 0)
+    hi = _fs_dsconv(q.sub("dsconv1"), hi, 2)
+    hi = _fs_dsconv(q.sub("dsconv2"), hi, 2)
+    hi = _fs_dsconv(q.sub("dsconv3"), hi, 1)
+    h, w = x.shape[2:]
+    lo = F.interpolate(x, size=(h // 4, w // 4), mode="bilinear", align_corners=True)   # scale_factor=0.25
+    g = p.sub("context_feature_extractor")
+    lo = _fs_cbr(g.sub("conv_"), lo, 2, 0)
+    lo = _cx_bottlenecks(g, lo)
+    y = _fs_ffm(p.sub("feature_fusion"), hi, lo)
+    c = p.sub("classifier")
+    y = _fs_dsconv(c.sub("dsconv1"), y)
+    y = _fs_dsconv(c.sub("dsconv2"), y)
+    y = F.conv2d(y, c["conv.1.weight"], c["conv.1.bias"])
+    return F.interpolate(y, x.shape[2:], mode="bilinear", align_corners=True)
+
+
+FORWARD["ContextNet"] = contextnet

@@ -10,7 +10,7 @@ from conftest import spec_state_dict
 from oracle import fixture, loss as oloss, nets
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet"])
 def test_eval_forward_matches_reference(name, spec, golden):
     sd = spec_state_dict(spec, name)
     g = golden(name)
@@ -66,6 +66,9 @@ def test_state_dict_spec_counts(spec):
     assert spec["ERFNet"]["n_params"] == 2066642
     assert spec["DABNet"]["n_params"] == 756643
     assert spec["ENet"]["n_params"] == 360422
+    assert spec["ContextNet"]["n_params"] == 876563          # usage.txt:95
+    # usage.txt:100 lists 1,660,607 for ESNet: its hook-based counter sees each PFCU's shared bn2 three times
+    assert spec["ESNet"]["n_params"] == 1660607 - 3 * 2 * 256
 
 
 def test_weighted_ce_matches_reference(golden):

@@ -1,0 +1,74 @@
+"""Model-level parity (GPU) for the nets of SURVEY 8f-1 / 8f-2 (ESNet, ContextNet): same checks and tolerances as
+tests/test_models_gpu.py -- fp32 logits vs the unmodified reference's golden (1e-3), argmax >= 99.9 %, bf16 vs the
+CPU oracle (5e-2 or torch's own bf16-autocast error on the same graph).
+
+STATUS: written after the round's GPU budget was spent, so these have not run on a B200 yet.  The kernels they
+launch are the ones the ERFNet / Fast-SCNN tests cover; the host composition is checked on the CPU
+(tests/test_host_composition_cpu.py).  Until their first device run they are non-strict xfail so an untested
+shape cannot turn the verified suite red; an XPASS in the log is the first confirmation -- then drop the mark.
+"""
+import pytest
+import torch
+
+import test_models_gpu as T
+from conftest import spec_state_dict
+from oracle import fixture, nets
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first B200 run pending (round-1 GPU budget spent before these nets landed)")]
+
+NETS = ["ESNet", "ContextNet"]
+
+
+@pytest.mark.parametrize("name", NETS)
+def test_fp32_matches_reference_golden(name, spec, golden):
+    T.test_fp32_matches_reference_golden(name, spec, golden)
+
+
+@pytest.mark.parametrize("name", NETS)
+def test_bf16_matches_oracle(name, spec):
+    T.test_bf16_matches_oracle(name, spec)
+
+
+def test_esnet_blocks_are_drop_in(spec):
+    from model.ESNet import FCU, PFCU
+    sd = spec_state_dict(spec, "ESNet")
+    torch.manual_seed(0)
+    for cls, args, idx, ref_fn in ((FCU, (16, 3, 0.03, 1), 0, lambda p, x: nets.es_fcu(p, x, 3, 1)),
+                                   (FCU, (64, 5, 0.03, 1), 4, lambda p, x: nets.es_fcu(p, x, 5, 1)),
+                                   (PFCU, (128,), 7, nets.es_pfcu)):
+        pre = "layers.%d." % idx
+        blk = cls(*args)
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        blk = blk.cuda().eval()
+        x = torch.randn(2, args[0], 24, 40)
+        ref = ref_fn(nets.SD(sd, pre), x)
+        assert T._rel(blk(x.cuda()).float().cpu(), ref) < 1e-4, cls.__name__
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yb = blk(x.cuda())
+        assert yb.dtype == torch.bfloat16 and T._rel(yb.float().cpu(), ref) < T.BF16_LOGIT_TOL, cls.__name__
+
+
+def test_contextnet_quarter_scale_image():
+    import torch.nn.functional as F
+    from model.ContextNet import quarter_scale_image
+    x = fixture.make_input(2, 64, 136).cuda()
+    y = quarter_scale_image(x)
+    ref = F.interpolate(x, scale_factor=0.25, mode="bilinear", align_corners=True)
+    assert y.shape == ref.shape and y.is_contiguous()
+    assert torch.allclose(y, ref, atol=1e-3)          # inputs span [-83, 183]
+
+
+def test_full_size_properties(spec):
+    """512x1024: batch-permutation equivariance, fused argmax == argmax of the logits, bf16 close to fp32."""
+    for name in NETS:
+        m = T._model(name, spec)
+        x = fixture.make_input(2, 512, 1024).cuda()
+        with torch.no_grad():
+            y = m(x)
+            assert torch.equal(y, m(x.flip(0)).flip(0))
+            logits, mask = m.predict_mask(x, with_logits=True)
+            assert torch.equal(mask.long(), logits.argmax(1))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                yb = m(x)
+        assert T._rel(yb.float(), y) < T.BF16_LOGIT_TOL
