@@ -210,9 +210,11 @@ int esn_convert_layout(const EsnTensor* x, const EsnTensor* y, void* stream);
  *   br1 = BNPReLU(dw1x3(BNPReLU(dw3x1(x))))           dilation 1
  *   br2 = BNPReLU(dw1x3_d(BNPReLU(dw3x1_d(x))))       dilation d
  *   y   = PReLU(BN(br1 + br2))                        (bn_relu_2)
- * Per-channel parameter block `prm`, fp32 [15][C]:
- *   rows 0-2  w3x1 taps, 3 scale, 4 shift, 5 alpha      (branch 1, first conv)   -- see esn/plan.py
- *   ... (layout documented in DESIGN.md section 4) */
+ * Per-channel parameter block `prm`, fp32 [27][C]:
+ *   rows  0-11  three taps each of dw3x1, dw1x3 (branch 1) and dw3x1, dw1x3 (branch 2, dilated)
+ *   rows 12-23  (scale, shift, PReLU alpha) of the BNPReLU after each of those four convs, same order
+ *   rows 24-26  (scale, shift, alpha) of bn_relu_2
+ * (packed by DABModule._build_prep in model/DABNet.py; read in csrc/esn_stencil.cu) */
 typedef struct EsnDabPair {
   EsnTensor x, y;
   const float* prm;    /* [27][C] fp32 */

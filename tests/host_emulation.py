@@ -154,7 +154,7 @@ def _finish_head(logits_f32, want_logits, want_mask, logits_dtype):
 
 def head_convt2x2(x, w, bias, classes, want_logits=True, want_mask=False, logits_dtype=torch.float32):
     wt = w[:, :, :, :classes].permute(2, 3, 0, 1)                       # [dy][dx][Cin][32] -> (Cin, classes, 2, 2)
-    return _finish_head(F.conv_transpose2d(x.float(), wt, bias, 2), want_logits, want_mask, logits_dtype)
+    return _finish_head(F.conv_transpose2d(x.float(), wt, None if bias is None else bias[:classes], 2), want_logits, want_mask, logits_dtype)
 
 
 def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, logits_dtype=torch.float32,
@@ -163,7 +163,53 @@ def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, l
     return _finish_head(y, want_logits, want_mask, logits_dtype)
 
 
-_SWAPS = dict(new_act=new_act, require_cuda=require_cuda, as_act=as_act, to_nchw=to_nchw, conv2d=conv2d,
+def fglo_gate(x, w1, b1, w2, b2, out=None, residual=None):
+    """CGNet FGlo (CGNet.py:173-191): y = x * sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2) (+ residual)."""
+    n, c, h, w = x.shape
+    xf = x.float()
+    gate = torch.sigmoid(F.linear(F.relu(F.linear(xf.mean(dim=(2, 3)), w1, b1)), w2, b2)).view(n, c, 1, 1)
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    v = xf * gate
+    return _store(out, v if residual is None else v + residual.float())
+
+
+def maxpool3x3s2_idx(x):
+    """MaxPool2d(3, 2, 1, return_indices=True): (pooled, int32 flat indices h*W+w laid out [N,Ho,Wo,C])."""
+    n, c, h, w = x.shape
+    v, idx = F.max_pool2d(x.float().contiguous(), 3, 2, 1, return_indices=True)
+    y = new_act(n, c, v.shape[2], v.shape[3], x.dtype, x.device)
+    return _store(y, v), idx.permute(0, 2, 3, 1).contiguous().to(torch.int32)
+
+
+def max_unpool2x2(v, idx, ext=None, act=L.ACT_NONE, alpha=None):
+    """y = act(MaxUnpool2d(2)(v, idx) + ext); CPU max_unpool2d is last-writer-wins in raster order, the kernel's rule."""
+    n, c, h, w = v.shape
+    up = F.max_unpool2d(v.float().contiguous(), idx.permute(0, 3, 1, 2).contiguous().long(), 2, output_size=(2 * h, 2 * w))
+    y = new_act(n, c, 2 * h, 2 * w, v.dtype, v.device)
+    return _store(y, _act(up if ext is None else up + ext.float(), act, alpha))
+
+
+def dab_dw_pair(x, prm, dilation, out=None):
+    """include/esn.h EsnDabPair; prm rows: 0-11 taps of (3x1, 1x3, dilated 3x1, dilated 1x3), 12-23 their
+    (scale, shift, alpha) triples, 24-26 the closing BN + PReLU (model/DABNet.py DABModule._build_prep)."""
+    n, c, h, w = x.shape
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    taps, aff, fin = prm[0:12].view(4, 3, c), prm[12:24].view(4, 3, c), prm[24:27]
+
+    def stage(t, i, vertical, d):
+        wt = taps[i].t().reshape(c, 1, 3, 1) if vertical else taps[i].t().reshape(c, 1, 1, 3)
+        t = F.conv2d(t, wt, None, 1, (d, 0) if vertical else (0, d), (d, 1) if vertical else (1, d), c)
+        return _act(t * _vec(aff[i, 0]) + _vec(aff[i, 1]), L.ACT_PRELU, aff[i, 2])
+    xf = x.float()
+    br1 = stage(stage(xf, 0, True, 1), 1, False, 1)
+    br2 = stage(stage(xf, 2, True, dilation), 3, False, dilation)
+    return _store(out, _act((br1 + br2) * _vec(fin[0]) + _vec(fin[1]), L.ACT_PRELU, fin[2]))
+
+
+_SWAPS = dict(fglo_gate=fglo_gate, maxpool3x3s2_idx=maxpool3x3s2_idx, max_unpool2x2=max_unpool2x2,
+              dab_dw_pair=dab_dw_pair, new_act=new_act, require_cuda=require_cuda, as_act=as_act, to_nchw=to_nchw, conv2d=conv2d,
               stem_conv3x3s2=stem_conv3x3s2, maxpool2x2=maxpool2x2, avgpool3x3s2=avgpool3x3s2, affine_act=affine_act,
               adaptive_avgpool=adaptive_avgpool, bilinear=bilinear, head_convt2x2=head_convt2x2,
               head_bilinear=head_bilinear)

@@ -2,8 +2,8 @@
 wrappers replaced by torch-CPU functions of the same contract, each model's forward -- packing, BN folding, channel
 padding, concat slices, residual chaining, layer order -- must reproduce the unmodified reference's golden logits.
 
-ERFNet and FastSCNN are GPU-verified (tests/test_models_gpu.py); they are here to validate the emulation itself.
-ESNet and ContextNet reuse their kernels.
+The seven nets of SURVEY 8a are GPU-verified (tests/test_models_gpu.py); here they validate the emulation itself and
+guard later host-side refactors.  ESNet and ContextNet reuse their kernels.
 """
 import pytest
 import torch
@@ -17,7 +17,7 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm()).item()
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "FastSCNN", "ESNet", "ContextNet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet"])
 def test_model_composition_matches_reference_golden(name, spec, golden):
     from builders.model_builder import build_model
     m = build_model(name, 19)
