@@ -162,6 +162,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="erfnet_infer_bf16_b16_1024x2048", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-input", default="f32", choices=["f32", "u8"],
+                    help="what crosses PCIe in the e2e leg: the reference's pre-processed fp32 NCHW batch (default), or the "
+                         "decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / CHW done on the device "
+                         "(esn_image_u8hwc_to_f32nchw, SURVEY 8f-4)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are
@@ -311,7 +315,13 @@ def main():
     value = world * batch / (ms_per_step / 1e3)
 
     # ---- e2e: pinned host images -> H2D -> forward -> D2H uint8 masks, every step, double-buffered
-    h2d = x_host.numel() * 4 + (y_host.numel() * 8 if train else 0)
+    u8_in = args.e2e_input == "u8"
+    if u8_in:
+        mean_bgr = [72.3924, 82.90902, 73.158325]      # dataset/inform/cityscapes_inform.pkl['mean'] (BGR, fp32)
+        g8 = torch.Generator().manual_seed(1234 + rank)
+        x_host_u8 = torch.randint(0, 256, (batch, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
+        xin_u8 = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    h2d = (x_host_u8.numel() if u8_in else x_host.numel() * 4) + (y_host.numel() * 8 if train else 0)
     d2h = 4 if train else batch * H * W
     mask_host = [(torch.empty((), dtype=torch.float32) if train else torch.empty((batch, H, W), dtype=torch.uint8)).pin_memory()
                  for _ in range(2)]
@@ -329,7 +339,10 @@ def main():
                 with torch.cuda.stream(copy_s):
                     if done[b] is not None:
                         copy_s.wait_event(done[b])      # buffer b free (its compute finished)
-                    xin[b].copy_(x_host, non_blocking=True)
+                    if u8_in:
+                        xin_u8[b].copy_(x_host_u8, non_blocking=True)
+                    else:
+                        xin[b].copy_(x_host, non_blocking=True)
                     if train:
                         yin[b].copy_(y_host, non_blocking=True)
                     ready[b] = torch.cuda.Event()
@@ -337,6 +350,8 @@ def main():
             if i >= 1:
                 pb = (i - 1) & 1
                 main_s.wait_event(ready[pb])
+                if u8_in:      # device half of the dataset class: uint8 HWC BGR -> fp32 NCHW RGB - mean (one launch)
+                    ops.image_u8_to_f32(xin_u8[pb], mean_bgr, True, out=xin[pb])
                 mk = gstep(xin[pb], yin[pb]) if gstep is not None else step(xin[pb], yin[pb])
                 mask_host[pb].copy_(mk, non_blocking=True)
                 done[pb] = torch.cuda.Event()
@@ -438,7 +453,10 @@ def main():
                     "note": ("pinned fp32 NCHW images + int64 labels -> H2D -> one training iteration (forward, weighted CE, backward, "
                              "all-reduce, Adam; CUDA graph: %s) -> D2H loss scalar; copies double-buffered on a side stream" % (gstep is not None))
                     if train else
-                    "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"},
+                    ("pinned uint8 HWC BGR images -> H2D -> esn_image_u8hwc_to_f32nchw -> model.predict_mask -> D2H uint8 masks; "
+                     "copies double-buffered on a side stream" if u8_in else
+                     "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"),
+                    "input": args.e2e_input},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}

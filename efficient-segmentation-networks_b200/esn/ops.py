@@ -665,6 +665,26 @@ def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, 
     return sums, g
 
 
+def image_u8_to_f32(img, mean, reverse_channels=True, out=None):
+    """Device half of the reference's dataset classes (dataset/cityscapes.py:74-78,164-170,208-214): uint8 HWC batch
+    (N,H,W,3) in cv2's BGR order -> fp32 NCHW (N,3,H,W) = (img - mean)[..., ::-1] transposed; `mean` holds three values in
+    the input's channel order (the pickle's fp32 BGR mean).  The result is what the models' stem kernels read."""
+    require_cuda(img, "image_u8_to_f32")
+    if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[3] != 3:
+        raise TypeError("image_u8_to_f32: expected a uint8 (N,H,W,3) tensor, got %s %s" % (img.dtype, tuple(img.shape)))
+    img = img.contiguous()
+    n, h, w, _ = img.shape
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
+    elif out.shape != (n, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != img.device:
+        raise ValueError("image_u8_to_f32: out must be a contiguous fp32 (N,3,H,W) tensor on the input's device")
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    _call(L.lib.esn_image_u8hwc_to_f32nchw, "esn_image_u8hwc_to_f32nchw",
+          (C.c_void_p(img.data_ptr()), C.c_void_p(out.data_ptr()), n, h, w, m, int(bool(reverse_channels))),
+          img.numel() + out.numel() * 4)
+    return out
+
+
 def launch_count():
     return int(L.lib.esn_launch_count())
 

@@ -350,6 +350,15 @@ int esn_dropout_step(const EsnTensor* x, const EsnTensor* y, uint64_t seed, cons
 int esn_confusion_matrix(const uint8_t* pred, const void* gt, int32_t gt_is_int64, int64_t n_pixels, int32_t nclass,
                          uint64_t* M, void* stream);
 
+/* Input pipeline on the device: the arithmetic tail of the reference's dataset classes
+ * (dataset/cityscapes.py:74-78, 164-170, 208-214): uint8 HWC image batch img[n][h][w][3] (BGR as cv2.imread returns it)
+ * -> out[n][3][h][w] fp32, out[co] = (float)img[ci] - mean3[ci] with ci = 2 - co when reverse_channels (BGR -> RGB) else
+ * co.  mean3 is a HOST pointer to three fp32 values in the INPUT channel order (the pickle's dtype,
+ * dataset/inform/cityscapes_inform.pkl); it is read before the call returns.  Bit-identical to the numpy float32 result.
+ * img needs no alignment (16-byte aligned image starts take the vector path); out must be 4-byte aligned. */
+int esn_image_u8hwc_to_f32nchw(const uint8_t* img, float* out, int32_t n, int32_t h, int32_t w, const float* mean3,
+                               int32_t reverse_channels, void* stream);
+
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);
 const char* esn_strerror(int code);

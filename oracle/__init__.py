@@ -15,4 +15,4 @@ container by `tools/make_golden.py` (which imports `/root/reference`
 unmodified behind three import stubs) and committed under `tests/golden/`.
 `tests/test_oracle_golden.py` replays them.
 """
-from . import fixture, nets, loss  # noqa: F401
+from . import fixture, nets, loss, pipeline  # noqa: F401
