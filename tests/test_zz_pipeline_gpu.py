@@ -2,7 +2,8 @@
 oracle (oracle/pipeline.py, pinned on the reference dataset classes) and the golden fixture.
 
 STATUS: written after the round's GPU budget was spent -- not yet run on a B200; non-strict xfail until the first
-device run (an XPASS in the log is that confirmation; then drop the mark)."""
+device run (an XPASS in the log is that confirmation; then drop the mark).  The file name sorts after every verified GPU test
+file so that a fault in unverified device code cannot poison the CUDA context of the verified suite."""
 import numpy as np
 import pytest
 import torch
