@@ -424,7 +424,10 @@ def main():
                                "alg_bytes_per_launch": int(top[1]["bytes"] / top[1]["launches"]), "kernel_launches": n_l,
                                "source": tj["source"]}
         roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "frac": round(achieved / hbm_peak, 4),
+                    # contract: DRAM bytes (read + write) per launch of this kernel from the ncu capture, or null
+                    "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
+                    "peak_source": peak_src,
                     "launches_per_step": top[1]["launches"], "share_of_step": round(top[1]["ms"] / tot_ms, 4),
                     "tensor_TFLOPs": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12, 1),
                     "tensor_frac_of_bf16_peak": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12 / tc_peak, 4),
