@@ -463,7 +463,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:      # contract: rank 0 at N=1 only
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
     emit(line)
