@@ -1,0 +1,314 @@
+"""TEST INFRASTRUCTURE ONLY: a CPU model of the C ABI (include/esn.h) at the level of the structs the host passes.
+
+tests/host_emulation.py replaces the Python wrappers; this file goes one level down and keeps ALL of ``esn.ops``
+running -- routing between the tcgen05 / sliced / direct conv paths, the shape gates, weight packing for each kernel
+family (``w_direct``, ``w_umma``, ``w_umma_scaled``, the phase-fused transposed conv), epilogue parameter blocks,
+descriptors of channel slices -- and intercepts only the foreign call itself (``ops._call``).  Each entry point is
+modelled from the raw arguments: tensors are rebuilt from EsnTensor descriptors over the caller's memory (host memory
+here), weights are decoded from the packed layouts documented in esn.h, arithmetic is fp32 with the result rounded to
+the output dtype, as the kernels do.  A bf16 forward of a model under this emulation therefore checks everything the
+host contributes to a launch, without a GPU.
+
+Nothing in the package imports this file.  Kernel arithmetic itself is checked on the device (``-m gpu`` tests).
+"""
+import contextlib
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from esn import ops
+from esn import _lib as L
+
+_DT = {L.ESN_F32: (torch.float32, 4), L.ESN_BF16: (torch.bfloat16, 2)}
+
+
+def _buf(ptr, count, dtype, esize):
+    if count <= 0:
+        return torch.empty(0, dtype=dtype)
+    assert ptr, "null pointer passed for a non-empty buffer"
+    return torch.frombuffer((C.c_char * (count * esize)).from_address(ptr), dtype=dtype)
+
+
+def tensor(d):
+    """EsnTensor -> logical (N,C,H,W) view over the caller's memory."""
+    dtype, es = _DT[d.dtype]
+    if d.layout == L.ESN_NHWC:
+        assert d.c_stride >= d.c > 0
+        span = (d.n * d.h * d.w - 1) * d.c_stride + d.c
+        return _buf(d.ptr, span, dtype, es).as_strided((d.n, d.c, d.h, d.w), (d.h * d.w * d.c_stride, 1, d.w * d.c_stride, d.c_stride))
+    return _buf(d.ptr, d.n * d.c * d.h * d.w, dtype, es).view(d.n, d.c, d.h, d.w)
+
+
+def vec(ptr, n):
+    return None if not ptr else _buf(ptr, n, torch.float32, 4)
+
+
+def _act(v, act, alpha):
+    if act == L.ACT_RELU:
+        return v.clamp_min(0)
+    if act == L.ACT_PRELU:
+        return v.clamp_min(0) + alpha.view(1, -1, 1, 1) * v.clamp_max(0)
+    return v
+
+
+def epilogue(acc, ep):
+    c = acc.shape[1]
+    sc, sh, al = vec(ep.scale, c), vec(ep.shift, c), vec(ep.alpha, c)
+    res = tensor(ep.residual).float() if ep.residual.ptr else None
+    one = lambda v, dflt: dflt if v is None else v.view(1, -1, 1, 1)
+    if ep.flags & 2:                                                    # ESN_EP_RESIDUAL_FIRST
+        return _act((acc + res) * one(sc, 1.0) + one(sh, 0.0), ep.act, al)
+    v = acc * one(sc, 1.0) + one(sh, 0.0)
+    if res is None:
+        return _act(v, ep.act, al)
+    if ep.flags & 1:                                                    # ESN_EP_ACT_BEFORE_RESIDUAL
+        return _act(_act(v, ep.act, al) + res, ep.act, al)
+    return _act(v + res, ep.act, al)
+
+
+def store(y, v):
+    assert tuple(y.shape) == tuple(v.shape), (tuple(y.shape), tuple(v.shape))
+    y.copy_(v.to(y.dtype))
+
+
+def _finite(x, what):
+    assert torch.isfinite(x).all(), "%s reads non-finite values (uninitialised channel tail?)" % what
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ conv family
+def _conv_core(p, x, wt, cout):
+    """wt: (Cout, Cin/groups, kh, kw) fp32 (transposed: the adjoint conv's (Cout, Cin, kh, kw))."""
+    if p.transposed:
+        n, _, h, w = x.shape
+        yh = tensor(p.y).shape[2]
+        out_pad = yh - ((h - 1) * p.stride - 2 * p.pad_h + p.dil_h * (p.kh - 1) + 1)
+        wtt = wt if (p.groups > 1) else wt.permute(1, 0, 2, 3)
+        return F.conv_transpose2d(x, wtt, None, p.stride, (p.pad_h, p.pad_w), out_pad, p.groups, (p.dil_h, p.dil_w))
+    return F.conv2d(x, wt, None, p.stride, (p.pad_h, p.pad_w), (p.dil_h, p.dil_w), p.groups)
+
+
+def esn_conv2d_direct(ref):
+    p = ref._obj
+    x, y = _finite(tensor(p.x).float(), "esn_conv2d_direct"), tensor(p.y)
+    cin_g, cout, taps = p.x.c // p.groups, p.y.c, p.kh * p.kw
+    wt = _buf(p.w, taps * cin_g * cout, torch.float32, 4).view(p.kh, p.kw, cin_g, cout).permute(3, 2, 0, 1)   # [tap][Cin/g][Cout]
+    store(y, epilogue(_conv_core(p, x, wt, cout), p.ep))
+    return 0
+
+
+def esn_conv2d_umma(ref):
+    p = ref._obj
+    assert p.x.dtype == L.ESN_BF16 and p.y.dtype == L.ESN_BF16 and p.groups == 1
+    assert p.x.c_stride % 8 == 0 and p.y.c_stride % 8 == 0 and p.x.ptr % 16 == 0 and p.y.ptr % 16 == 0, "TMA alignment"
+    x, y = _finite(tensor(p.x).float(), "esn_conv2d_umma"), tensor(p.y)
+    cin, taps = p.x.c, p.kh * p.kw
+    assert cin in (16, 32, 64) or cin % 64 == 0, cin
+    wp = _buf(p.w, taps * p.cout_pad * cin, torch.bfloat16, 2).float().view(p.kh, p.kw, p.cout_pad, cin)       # [tap][Cout_pad][Cin]
+    if p.transposed == 2:
+        # phase-fused ConvTranspose2d(3, s2, p1, op1): 2x2 taps, 4*Cout outputs ordered (row parity, column parity, c)
+        cout = p.y.c
+        assert p.cout_pad == 4 * cout and (p.kh, p.kw, p.stride) == (2, 2, 1) and p.y.h == 2 * p.x.h and p.y.w == 2 * p.x.w
+        acc = F.conv2d(F.pad(x, (0, 1, 0, 1)), wp.permute(2, 3, 0, 1))                                         # (N, 4*Cout, H, W)
+        c4 = 4 * cout
+        sc, sh, al = vec(p.ep.scale, c4), vec(p.ep.shift, c4), vec(p.ep.alpha, c4)
+        v = acc * (1.0 if sc is None else sc.view(1, -1, 1, 1)) + (0.0 if sh is None else sh.view(1, -1, 1, 1))
+        v = _act(v, p.ep.act, al)
+        n, _, h, w = v.shape
+        v = v.view(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)               # pixel shuffle
+        store(y, v)
+        return 0
+    assert p.cout_pad <= 256 and p.y.c <= p.cout_pad
+    wt = wp[:, :, :p.y.c].permute(2, 3, 0, 1)
+    store(y, epilogue(_conv_core(p, x, wt, p.y.c), p.ep))
+    return 0
+
+
+def esn_conv_pair_umma(ref):
+    p = ref._obj
+    x, y = _finite(tensor(p.x).float(), "esn_conv_pair_umma"), tensor(p.y)
+    c, d = p.x.c, p.dilation
+    cp = (c + 15) // 16 * 16
+    assert p.taps == 3 and c in (16, 64)
+    w1 = _buf(p.w1, 3 * cp * c, torch.bfloat16, 2).float().view(3, cp, c)[:, :c]                               # 3x1: [tap][Cout][Cin]
+    w2 = _buf(p.w2, 3 * cp * c, torch.bfloat16, 2).float().view(3, cp, c)[:, :c]                               # 1x3, scale folded in
+    t = F.conv2d(x, w1.permute(1, 2, 0).unsqueeze(3), None, 1, (d, 0), (d, 1))
+    t = epilogue(t, p.ep1).to(torch.bfloat16).float()                   # the intermediate row lives in shared memory as bf16
+    acc = F.conv2d(t, w2.permute(1, 2, 0).unsqueeze(2), None, 1, (0, d), (1, d))
+    assert not p.ep2.scale, "the pair kernel takes the second scale inside w2"
+    store(y, epilogue(acc, p.ep2))
+    return 0
+
+
+def esn_stem_conv3x3s2(ref):
+    p = ref._obj
+    assert p.x.layout == L.ESN_NCHW and p.x.dtype == L.ESN_F32 and p.x.c == 3
+    x, y = tensor(p.x), tensor(p.y)
+    wt = _buf(p.w, 27 * p.cconv, torch.float32, 4).view(3, 3, 3, p.cconv).permute(3, 2, 0, 1)
+    acc = F.conv2d(x, wt, None, 2, 0 if p.with_pool & 256 else 1)
+    if p.with_pool & 3 == 1:
+        acc = torch.cat([acc, F.max_pool2d(x, 2, 2)], 1)
+    elif p.with_pool & 3 == 2:
+        acc = torch.cat([acc, F.max_pool2d(x, 3, 2, 1)], 1)
+    store(y, epilogue(acc, p.ep))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ pointwise / pools / resize
+def _pool(fn):
+    def run(ref):
+        p = ref._obj
+        store(tensor(p.y), epilogue(fn(_finite(tensor(p.x).float(), "pool/affine")), p.ep))
+        return 0
+    return run
+
+
+def esn_convert_layout(xr, yr):
+    store(tensor(yr._obj), tensor(xr._obj).float())
+    return 0
+
+
+def esn_adaptive_avgpool(xr, yr):
+    y = tensor(yr._obj)
+    store(y, F.adaptive_avg_pool2d(tensor(xr._obj).float(), (y.shape[2], y.shape[3])))
+    return 0
+
+
+def esn_bilinear_nhwc(xr, yr, align):
+    y = tensor(yr._obj)
+    store(y, F.interpolate(tensor(xr._obj).float(), (y.shape[2], y.shape[3]), mode="bilinear", align_corners=bool(align)))
+    return 0
+
+
+def _head_out(p, logits_f32):
+    if p.logits.ptr:
+        store(tensor(p.logits), logits_f32)
+    if p.mask:
+        n, _, h, w = logits_f32.shape
+        torch.frombuffer((C.c_char * (n * h * w)).from_address(p.mask), dtype=torch.uint8).view(n, h, w).copy_(
+            logits_f32.argmax(1).to(torch.uint8))
+    return 0
+
+
+def esn_head_convt2x2(ref):
+    p = ref._obj
+    x = tensor(p.x).float()
+    wt = _buf(p.w, 4 * p.x.c * 32, torch.float32, 4).view(2, 2, p.x.c, 32)[:, :, :, :p.classes].permute(2, 3, 0, 1)
+    return _head_out(p, F.conv_transpose2d(x, wt, vec(p.bias, p.classes), 2))
+
+
+def esn_head_bilinear(ref):
+    p = ref._obj
+    x = tensor(p.x).float()[:, :p.classes]
+    return _head_out(p, F.interpolate(x, (p.out_h, p.out_w), mode="bilinear", align_corners=bool(p.align_corners)))
+
+
+def esn_maxpool3x3s2_idx(xr, yr, idx_ptr):
+    x, y = tensor(xr._obj).float().contiguous(), tensor(yr._obj)
+    v, idx = F.max_pool2d(x, 3, 2, 1, return_indices=True)
+    store(y, v)
+    n, c, ho, wo = v.shape
+    _buf(idx_ptr.value, n * ho * wo * c, torch.int32, 4).view(n, ho, wo, c).copy_(idx.permute(0, 2, 3, 1).to(torch.int32))
+    return 0
+
+
+def esn_max_unpool2x2(ref):
+    p = ref._obj
+    v, y = tensor(p.v).float().contiguous(), tensor(p.y)
+    n, c, h, w = v.shape
+    idx = _buf(p.idx, n * h * w * c, torch.int32, 4).view(n, h, w, c).permute(0, 3, 1, 2).contiguous().long()
+    up = F.max_unpool2d(v, idx, 2, output_size=(2 * h, 2 * w))
+    if p.ext.ptr:
+        up = up + tensor(p.ext).float()
+    store(y, _act(up, p.act, vec(p.alpha, c)))
+    return 0
+
+
+def esn_dab_dw_pair(ref):
+    p = ref._obj
+    x, y = tensor(p.x).float(), tensor(p.y)
+    c, d = p.x.c, p.dilation
+    prm = _buf(p.prm, 27 * c, torch.float32, 4).view(27, c)
+    taps, aff, fin = prm[0:12].view(4, 3, c), prm[12:24].view(4, 3, c), prm[24:27]
+
+    def stage(t, i, vertical, dd):
+        wt = taps[i].t().reshape(c, 1, 3, 1) if vertical else taps[i].t().reshape(c, 1, 1, 3)
+        t = F.conv2d(t, wt, None, 1, (dd, 0) if vertical else (0, dd), (dd, 1) if vertical else (1, dd), c)
+        return _act(t * aff[i, 0].view(1, -1, 1, 1) + aff[i, 1].view(1, -1, 1, 1), L.ACT_PRELU, aff[i, 2])
+    br = stage(stage(x, 0, True, 1), 1, False, 1) + stage(stage(x, 2, True, d), 3, False, d)
+    store(y, _act(br * fin[0].view(1, -1, 1, 1) + fin[1].view(1, -1, 1, 1), L.ACT_PRELU, fin[2]))
+    return 0
+
+
+def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
+    src = torch.frombuffer((C.c_char * (n * h * w * 3)).from_address(img.value), dtype=torch.uint8).view(n, h, w, 3)
+    v = src.float() - torch.tensor([mean3[0], mean3[1], mean3[2]], dtype=torch.float32)
+    if reverse:
+        v = v.flip(3)
+    _buf(out.value, n * 3 * h * w, torch.float32, 4).view(n, 3, h, w).copy_(v.permute(0, 3, 1, 2))
+    return 0
+
+
+ENTRY = {
+    "esn_conv2d_direct": esn_conv2d_direct, "esn_conv2d_umma": esn_conv2d_umma, "esn_conv_pair_umma": esn_conv_pair_umma,
+    "esn_stem_conv3x3s2": esn_stem_conv3x3s2,
+    "esn_maxpool2x2_affine_act": _pool(lambda x: F.max_pool2d(x, 2, 2)),
+    "esn_avgpool3x3s2_affine_act": _pool(lambda x: F.avg_pool2d(x, 3, 2, 1)),
+    "esn_affine_act": _pool(lambda x: x),
+    "esn_convert_layout": esn_convert_layout, "esn_adaptive_avgpool": esn_adaptive_avgpool, "esn_bilinear_nhwc": esn_bilinear_nhwc,
+    "esn_head_convt2x2": esn_head_convt2x2, "esn_head_bilinear": esn_head_bilinear,
+    "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
+    "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw,
+}
+CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
+
+
+def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag=""):
+    CALLS.append((name, tag))
+    rc = ENTRY[name](*arg_refs)
+    L.check(rc, name)
+
+
+def _new_act(n, c, h, w, dtype, device, c_alloc=None, zero=False):
+    ca = c if c_alloc is None else c_alloc
+    buf = torch.zeros((n, h, w, ca), dtype=dtype, device=device) if zero else torch.full((n, h, w, ca), float("nan"), dtype=dtype, device=device)
+    t = buf.permute(0, 3, 1, 2)
+    return t if ca == c else t[:, :c]
+
+
+def _to_nchw(x, dtype=None):
+    return x.to(dtype or x.dtype).contiguous()
+
+
+def _fglo_gate(x, w1, b1, w2, b2, out=None, residual=None):
+    # three entry points with device-sized scratch (esn_global_avgpool(+_chunks), esn_fglo_gate, esn_scale_nc): modelled as one
+    n, c, h, w = x.shape
+    xf = x.float()
+    gate = torch.sigmoid(F.linear(F.relu(F.linear(xf.mean(dim=(2, 3)), w1, b1)), w2, b2)).view(n, c, 1, 1)
+    if out is None:
+        out = ops.new_act(n, c, h, w, x.dtype, x.device)
+    v = xf * gate
+    out.copy_((v if residual is None else v + residual.float()).to(out.dtype))
+    return out
+
+
+@contextlib.contextmanager
+def emulate_abi(bf16=False):
+    """Run esn.ops on host tensors with every foreign call answered by the CPU model above.  bf16=True makes
+    ops.compute_dtype choose bf16 (as under torch.autocast('cuda', torch.bfloat16) on the device)."""
+    swaps = dict(_call=_call, require_cuda=lambda t, what: None, new_act=_new_act, to_nchw=_to_nchw, fglo_gate=_fglo_gate)
+    if bf16:
+        swaps["compute_dtype"] = lambda x: torch.bfloat16
+    saved = {k: getattr(ops, k) for k in swaps}
+    saved_profile = ops.PROFILE
+    del CALLS[:]
+    try:
+        for k, v in swaps.items():
+            setattr(ops, k, v)
+        ops.PROFILE = None
+        yield CALLS
+    finally:
+        for k, v in saved.items():
+            setattr(ops, k, v)
+        ops.PROFILE = saved_profile

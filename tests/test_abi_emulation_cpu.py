@@ -1,0 +1,85 @@
+"""Host side of the C ABI, checked without a GPU (tests/abi_emulation.py): all of esn.ops runs -- routing, shape gates,
+weight packing per kernel family, epilogue blocks, channel-slice descriptors -- and only the foreign call is answered by
+a CPU model of the entry point working from the raw structs.
+
+* fp32: every conv goes through esn_conv2d_direct's packed weights; logits must match the reference golden to 1e-5.
+* bf16: the tcgen05 routes (plain, 64-channel input slices, 256-channel output slices, the phase-fused transposed
+  conv, the factorized pair) are taken exactly as on the device; logits must match the fp32 oracle within the bf16
+  tolerance of tests/test_models_gpu.py (5e-2, or 1.5x torch's own bf16-autocast error on the same graph).
+"""
+import pytest
+import torch
+
+from abi_emulation import emulate_abi
+from conftest import spec_state_dict
+from oracle import fixture, nets
+
+NETS = ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet"]
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def _model(name, spec):
+    from builders.model_builder import build_model
+    m = build_model(name, 19)
+    m.load_state_dict(spec_state_dict(spec, name))
+    return m.eval()
+
+
+@pytest.mark.parametrize("name", NETS)
+def test_fp32_through_the_abi_matches_reference_golden(name, spec, golden):
+    m, g = _model(name, spec), golden(name)
+    x = fixture.make_input(1, 64, 128)
+    with emulate_abi() as calls, torch.no_grad():
+        logits, mask = m.predict_mask(x, with_logits=True)
+    assert _rel(logits, torch.from_numpy(g["eval_1x64x128_logits"])) < 1e-5
+    assert (mask.numpy() == g["eval_1x64x128_argmax"]).mean() > 0.9999
+    assert not any(n in ("esn_conv2d_umma", "esn_conv_pair_umma") for n, _ in calls)      # fp32 never takes a bf16 kernel
+
+
+@pytest.mark.parametrize("name", NETS)
+def test_bf16_routes_through_the_abi(name, spec):
+    m = _model(name, spec)
+    sd = spec_state_dict(spec, name)
+    x = fixture.make_input(2, 128, 256)
+    with torch.no_grad():
+        ref = nets.forward(name, sd, x)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            rel_ac = _rel(nets.forward(name, sd, x).float(), ref)
+        with emulate_abi(bf16=True) as calls:
+            y = m(x)
+            names = [n for n, _ in calls]
+    assert y.dtype == torch.bfloat16 and y.shape == ref.shape
+    rel = _rel(y.float(), ref)
+    print("%s bf16 through the ABI model: rel-L2 %.3e (torch bf16 autocast of the oracle graph: %.3e); launches %d, tcgen05 %d"
+          % (name, rel, rel_ac, len(names), sum(n in ("esn_conv2d_umma", "esn_conv_pair_umma") for n in names)))
+    assert rel < max(5e-2, 1.5 * rel_ac), (rel, rel_ac)
+    assert "esn_conv2d_umma" in names                        # the tensor-core route is the one exercised
+
+
+def test_erfnet_routing_is_the_benchmarked_one(spec):
+    """At a pair-kernel shape (W multiple of 128) ERFNet's bf16 step makes the entry-point calls that
+    profiles/r01_bench_erfnet.json lists under "kernels": 18 pair launches (C = 16 / 64 blocks), 36 single tcgen05 convs
+    (8 C=128 blocks x 4, two downsamplers, two transposed convs), the stem, two max-pool branches, the head -- and no
+    direct conv."""
+    m = _model("ERFNet", spec)
+    x = fixture.make_input(1, 128, 1024)
+    with emulate_abi(bf16=True) as calls, torch.no_grad():
+        m.predict_mask(x)
+        names = [n for n, _ in calls]
+    assert names.count("esn_conv_pair_umma") == 18
+    assert names.count("esn_conv2d_umma") == 36
+    assert names.count("esn_conv2d_direct") == 0
+    assert names.count("esn_stem_conv3x3s2") == 1 and names.count("esn_head_convt2x2") == 1
+    assert names.count("esn_maxpool2x2_affine_act") == 2 and len(names) == 58
+
+
+def test_input_pipeline_through_the_abi(golden):
+    from esn import ops
+    g = golden("pipeline")
+    with emulate_abi():
+        for i in range(3):
+            y = ops.image_u8_to_f32(torch.from_numpy(g["image%d" % i][None].copy()), g["mean"])
+            assert (y[0].numpy() == g["input%d" % i]).all()
