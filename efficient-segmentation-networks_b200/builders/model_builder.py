@@ -13,6 +13,7 @@ from model.ESPNet import ESPNet
 from model.ESPNet_v2.SegmentationModel import EESPNet_Seg
 from model.ESNet import ESNet
 from model.ContextNet import ContextNet
+from model.EDANet import EDANet
 
 _HOT_PATH = {
     "ERFNet": ERFNet,
@@ -25,6 +26,7 @@ _HOT_PATH = {
     # nets that reuse the ERFNet / Fast-SCNN kernels (inference)
     "ESNet": ESNet,
     "ContextNet": ContextNet,
+    "EDANet": EDANet,
 }
 _REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
                     "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")

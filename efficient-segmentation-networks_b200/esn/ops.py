@@ -215,6 +215,11 @@ class ConvPrep:
         self.stride = stride
         self.pad_h, self.pad_w = padding
         self.dil_h, self.dil_w = dilation
+        # a dilation along an axis with a single tap has no effect (EDANet.py:53-54 passes dilation=d to 3x1 / 1x3 convs)
+        if self.kh == 1:
+            self.dil_h = 1
+        if self.kw == 1:
+            self.dil_w = 1
         self.out_pad = out_pad
         taps = self.kh * self.kw
         # direct layout: [tap][Cin/groups][Cout]

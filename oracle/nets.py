@@ -647,3 +647,44 @@ def contextnet(sd, x, train=False, stats=None):
 
 
 FORWARD["ContextNet"] = contextnet
+
+
+# --------------------------------------------------------------------------- EDANet
+def eda_down(p, x, n_in, n_out):
+    """DownsamplerBlock, model/EDANet.py:18-38 (BatchNorm2d default eps)."""
+    y = F.conv2d(x, p["conv.weight"], p["conv.bias"], stride=2, padding=1)
+    if n_in < n_out:
+        y = torch.cat([y, F.max_pool2d(x, 2, 2)], 1)
+    return F.relu(bn(p.sub("bn"), y, 1e-5))
+
+
+def eda_module(p, x, d):
+    """EDAModule (eval: Dropout2d is the identity), model/EDANet.py:41-85: no activation between a 3x1 and its 1x3;
+    ``dilation=d`` on a (3,1) / (1,3) kernel only acts along the kernel's long axis."""
+    y = F.relu(bn(p.sub("bn0"), F.conv2d(x, p["conv1x1.weight"], p["conv1x1.bias"]), 1e-5))
+    y = F.conv2d(y, p["conv3x1_1.weight"], p["conv3x1_1.bias"], padding=(1, 0))
+    y = F.relu(bn(p.sub("bn1"), F.conv2d(y, p["conv1x3_1.weight"], p["conv1x3_1.bias"], padding=(0, 1)), 1e-5))
+    y = F.conv2d(y, p["conv3x1_2.weight"], p["conv3x1_2.bias"], padding=(d, 0), dilation=(d, d))
+    y = F.relu(bn(p.sub("bn2"), F.conv2d(y, p["conv1x3_2.weight"], p["conv1x3_2.bias"], padding=(0, d), dilation=(d, d)), 1e-5))
+    return torch.cat([y, x], 1)
+
+
+EDA_BLOCKS = {2: (1, 1, 1, 2, 2), 4: (2, 2, 4, 4, 8, 8, 16, 16)}       # EDANet.py:127-131
+
+
+def edanet(sd, x, train=False, stats=None):
+    """EDANet.forward, model/EDANet.py:148-157."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = eda_down(p.sub("layers.0"), x, 3, 15)
+    y = eda_down(p.sub("layers.1"), y, 15, 60)
+    for i, d in enumerate(EDA_BLOCKS[2]):
+        y = eda_module(p.sub("layers.2.residual_dense_layers.%d" % i), y, d)
+    y = eda_down(p.sub("layers.3"), y, 260, 130)
+    for i, d in enumerate(EDA_BLOCKS[4]):
+        y = eda_module(p.sub("layers.4.residual_dense_layers.%d" % i), y, d)
+    y = F.conv2d(y, p["project_layer.weight"], p["project_layer.bias"])
+    h, w = y.shape[2:]
+    return F.interpolate(y, size=(8 * h, 8 * w), mode="bilinear", align_corners=True)    # scale_factor=8
+
+
+FORWARD["EDANet"] = edanet

@@ -14,7 +14,7 @@ from abi_emulation import emulate_abi
 from conftest import spec_state_dict
 from oracle import fixture, nets
 
-NETS = ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet"]
+NETS = ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet"]
 
 
 def _rel(a, b):

@@ -17,7 +17,7 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm()).item()
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet"])
 def test_model_composition_matches_reference_golden(name, spec, golden):
     from builders.model_builder import build_model
     m = build_model(name, 19)
@@ -74,3 +74,25 @@ def test_contextnet_quarter_scale_image():
     ref = F.interpolate(x, scale_factor=0.25, mode="bilinear", align_corners=True)
     assert y.shape == ref.shape and y.is_contiguous() and y.dtype == torch.float32
     assert torch.allclose(y, ref, atol=1e-4)
+
+
+def test_edanet_blocks_match_oracle(spec):
+    """EDAModule / EDANetBlock on their own return cat([new, input]) like the reference modules."""
+    from model.EDANet import EDAModule, EDANetBlock
+    sd = spec_state_dict(spec, "EDANet")
+    torch.manual_seed(0)
+    with emulate_kernels(), torch.no_grad():
+        pre = "layers.2.residual_dense_layers.3."
+        blk = EDAModule(180, 2).eval()
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, 180, 24, 40)
+        assert _rel(blk(x), nets.eda_module(nets.SD(sd, pre), x, 2)) < 1e-5
+        pre = "layers.2."
+        blk = EDANetBlock(60, 5, [1, 1, 1, 2, 2], 40).eval()
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        x = torch.randn(2, 60, 24, 40)
+        ref = x
+        for i, d in enumerate(nets.EDA_BLOCKS[2]):
+            ref = nets.eda_module(nets.SD(sd, pre + "residual_dense_layers.%d." % i), ref, d)
+        y = blk(x)
+        assert y.shape == ref.shape and _rel(y, ref) < 1e-5

@@ -1,4 +1,4 @@
-"""Model-level parity (GPU) for the nets of SURVEY 8f-1 / 8f-2 (ESNet, ContextNet): same checks and tolerances as
+"""Model-level parity (GPU) for the nets of SURVEY 8f-1 / 8f-2 (ESNet, EDANet, ContextNet): same checks and tolerances as
 tests/test_models_gpu.py -- fp32 logits vs the unmodified reference's golden (1e-3), argmax >= 99.9 %, bf16 vs the
 CPU oracle (5e-2 or torch's own bf16-autocast error on the same graph).
 
@@ -17,7 +17,7 @@ from oracle import fixture, nets
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first B200 run pending (round-1 GPU budget spent before these nets landed)")]
 
-NETS = ["ESNet", "ContextNet"]
+NETS = ["ESNet", "ContextNet", "EDANet"]
 
 
 @pytest.mark.parametrize("name", NETS)
@@ -47,6 +47,33 @@ def test_esnet_blocks_are_drop_in(spec):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             yb = blk(x.cuda())
         assert yb.dtype == torch.bfloat16 and T._rel(yb.float().cpu(), ref) < T.BF16_LOGIT_TOL, cls.__name__
+
+
+def test_edanet_blocks_are_drop_in(spec):
+    """EDAModule / EDANetBlock called on their own (NCHW in, cat([new, input]) out)."""
+    from model.EDANet import EDAModule, EDANetBlock
+    sd = spec_state_dict(spec, "EDANet")
+    torch.manual_seed(0)
+    pre = "layers.2.residual_dense_layers.3."
+    blk = EDAModule(180, 2)
+    blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    x = torch.randn(2, 180, 24, 40)
+    ref = nets.eda_module(nets.SD(sd, pre), x, 2)
+    y = blk.cuda().eval()(x.cuda())
+    assert y.shape == ref.shape and T._rel(y.float().cpu(), ref) < 1e-4
+    pre = "layers.2."
+    blk = EDANetBlock(60, 5, [1, 1, 1, 2, 2], 40)
+    blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    x = torch.randn(2, 60, 24, 40)
+    ref = x
+    for i, d in enumerate(nets.EDA_BLOCKS[2]):
+        ref = nets.eda_module(nets.SD(sd, pre + "residual_dense_layers.%d." % i), ref, d)
+    blk = blk.cuda().eval()
+    y = blk(x.cuda())
+    assert y.shape == ref.shape and T._rel(y.float().cpu(), ref) < 1e-4
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yb = blk(x.cuda())
+    assert yb.dtype == torch.bfloat16 and T._rel(yb.float().cpu(), ref) < T.BF16_LOGIT_TOL
 
 
 def test_contextnet_quarter_scale_image():

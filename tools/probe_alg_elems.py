@@ -19,6 +19,7 @@ from make_golden import import_reference
 UNITS = {
     "ESNet": ("DownsamplerBlock", "FCU", "PFCU", "UpsamplerBlock"),
     "ContextNet": ("Custom_Conv", "DepthSepConv", "LinearBottleneck", "FeatureFusionModule", "Classifer"),
+    "EDANet": ("DownsamplerBlock", "EDAModule"),
     "ERFNet": ("DownsamplerBlock", "non_bottleneck_1d", "UpsamplerBlock"),
     "FastSCNN": ("_ConvBNReLU", "_DSConv", "LinearBottleneck", "PyramidPooling", "FeatureFusionModule", "Classifer"),
 }
