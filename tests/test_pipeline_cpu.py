@@ -23,3 +23,58 @@ def test_batch_layout():
     x = pipeline.batch_to_input(imgs)
     assert x.shape == (2, 3, 6, 10)
     assert x[1, 0, 2, 3] == np.float32(imgs[1, 2, 3, 2]) - pipeline.CITYSCAPES_MEAN_BGR[2]     # R plane = BGR channel 2
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The DEVICE SOURCE of esn_image_u8hwc_to_f32nchw, executed on the CPU: csrc/esn_input_kernel.cuh is free of CUDA headers,
+# tests/cuda_cpu_shim.h maps every CUDA thread of a CTA to a pthread (__syncthreads = pthread barrier, __shared__ = one
+# static instance), tests/input_kernel_host.cpp restates the entry point's launch arithmetic.  Checks the kernel's
+# indexing, ragged tails, both staging branches (16-byte vector / byte copy), both store branches (float4 / guarded
+# scalar), several tiles per CTA and barrier placement -- bit-exact against the oracle.  Not a substitute for the device
+# run (tests/test_zz_pipeline_gpu.py); it is what can be known about the kernel without one.
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def kernel_on_cpu(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path_factory.mktemp("ikh") / "input_kernel_host")
+    subprocess.run([gxx, "-O1", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "tests"),
+                    "-I" + os.path.join(ROOT, "efficient-segmentation-networks_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "input_kernel_host.cpp"), "-o", exe], check=True)
+
+    def run(img, reverse, in_off=0, out_off=0, grid_cap=8):
+        n, h, w, _ = img.shape
+        r = subprocess.run([exe] + [str(v) for v in (n, h, w, int(reverse), in_off, out_off, grid_cap)],
+                           input=img.tobytes(), capture_output=True, timeout=300, check=True)
+        return np.frombuffer(r.stdout, dtype=np.float32).reshape(n, 3, h, w)
+    return run
+
+
+@pytest.mark.parametrize("case", [
+    # (n, h, w, reverse, input byte offset, output float offset, grid cap)
+    (1, 1, 1, 1, 0, 0, 8),          # one pixel: byte staging, scalar stores
+    (2, 17, 23, 1, 0, 0, 8),        # h*w % 4 != 0: ragged tail, image starts off 16-byte alignment
+    (3, 32, 32, 1, 0, 0, 2),        # exactly one full tile per image, CTAs walk two tiles
+    (2, 33, 64, 0, 0, 0, 3),        # full tile + partial tile, channel order kept
+    (2, 40, 64, 1, 1, 0, 2),        # input not 16-byte aligned -> byte staging on full tiles
+    (2, 40, 64, 1, 0, 1, 2),        # output not 16-byte aligned -> guarded scalar stores
+    (5, 31, 33, 1, 3, 3, 4),        # everything ragged
+    (1, 64, 128, 1, 0, 0, 100),     # grid == tiles
+])
+def test_device_source_on_cpu_is_bit_exact(kernel_on_cpu, case):
+    n, h, w, reverse, in_off, out_off, cap = case
+    rng = np.random.RandomState(n * 7919 + h * 31 + w)
+    img = rng.randint(0, 256, (n, h, w, 3)).astype(np.uint8)
+    y = kernel_on_cpu(img, reverse, in_off, out_off, cap)
+    ref = (pipeline.batch_to_input(img) if reverse
+           else (img.astype(np.float32) - pipeline.CITYSCAPES_MEAN_BGR).transpose(0, 3, 1, 2))
+    assert np.array_equal(y, ref)
