@@ -53,15 +53,30 @@ def _nbytes(t):
     return 0 if t is None else t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3] * t.element_size()
 
 
-def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag=""):
+_WARNED_UNSUPPORTED = set()
+
+
+def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag="", allow_unsupported=False):
+    """Launch one C-ABI entry point on the current stream.  Returns True.  With allow_unsupported, an
+    ESN_ERR_UNSUPPORTED answer (the entry point's own shape gate, checked before anything is launched) returns False
+    instead of raising, so the caller can take the next CUDA route; it is reported once per (entry point, shape tag)."""
     if PROFILE is None:
-        L.check(fn(*arg_refs, stream()), name)
-        return
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    L.check(fn(*arg_refs, stream()), name)
-    e1.record()
-    PROFILE.append({"kernel": name, "tag": tag, "bytes": int(alg_bytes), "flops": int(flops), "ev": (e0, e1)})
+        rc = fn(*arg_refs, stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*arg_refs, stream())
+        e1.record()
+    if rc == L.ERR_UNSUPPORTED and allow_unsupported:
+        if (name, tag) not in _WARNED_UNSUPPORTED:
+            _WARNED_UNSUPPORTED.add((name, tag))
+            import warnings
+            warnings.warn("%s declined %s (host-side gate out of date?); taking the direct CUDA kernel" % (name, tag))
+        return False
+    L.check(rc, name)
+    if PROFILE is not None:
+        PROFILE.append({"kernel": name, "tag": tag, "bytes": int(alg_bytes), "flops": int(flops), "ev": (e0, e1)})
+    return True
 
 
 def require_cuda(t, what):
@@ -403,8 +418,9 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
         return out
     if tc_ok and umma_supported(prep, p):
         p.w = prep.w_umma.data_ptr()
-        _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag)
-        return out
+        if _call(L.lib.esn_conv2d_umma, "esn_conv2d_umma", (C.byref(p),), alg, flops, tag, allow_unsupported=True):
+            return out
+        tc_ok = False          # declined by the entry point's own gate: straight to the direct kernel, no slicing
     if tc_ok and prep.cout_pad > 256:
         # more output channels than one UMMA N tile: run 256-channel slices of the weight
         for q in prep.cout_split():

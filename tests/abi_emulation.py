@@ -264,10 +264,16 @@ ENTRY = {
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 
 
-def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag=""):
+DECLINE = set()   # entry-point names the model should answer ESN_ERR_UNSUPPORTED for (to exercise the host's next route)
+
+
+def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag="", allow_unsupported=False):
+    if name in DECLINE and allow_unsupported:      # calls without a fallback route (phase-fused transposed conv) are served
+        return False
     CALLS.append((name, tag))
     rc = ENTRY[name](*arg_refs)
     L.check(rc, name)
+    return True
 
 
 def _new_act(n, c, h, w, dtype, device, c_alloc=None, zero=False):

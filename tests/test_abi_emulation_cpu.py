@@ -83,3 +83,23 @@ def test_input_pipeline_through_the_abi(golden):
         for i in range(3):
             y = ops.image_u8_to_f32(torch.from_numpy(g["image%d" % i][None].copy()), g["mean"])
             assert (y[0].numpy() == g["input%d" % i]).all()
+
+
+def test_declined_tcgen05_call_takes_the_direct_kernel(spec, golden):
+    """If esn_conv2d_umma answers ESN_ERR_UNSUPPORTED for a shape the host-side gate let through, ops.conv2d goes on to
+    the direct CUDA kernel instead of failing the forward (the sliced / phase-fused routes keep raising)."""
+    import abi_emulation as A
+    m = _model("ESNet", spec)
+    sd = spec_state_dict(spec, "ESNet")
+    x = fixture.make_input(1, 64, 128)
+    A.DECLINE.add("esn_conv2d_umma")
+    try:
+        with torch.no_grad(), emulate_abi(bf16=True) as calls:
+            y = m(x)
+            names = [n for n, _ in calls]
+    finally:
+        A.DECLINE.clear()
+    assert names.count("esn_conv2d_umma") == 1 and names.count("esn_conv2d_direct") > 30     # 1 = the phase-fused 64 -> 16 transposed conv
+    with torch.no_grad():
+        ref = nets.forward("ESNet", sd, x)
+    assert _rel(y.float(), ref) < 5e-2
