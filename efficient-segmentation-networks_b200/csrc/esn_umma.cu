@@ -624,6 +624,10 @@ struct DeviceLimits {
   int max_smem = 0;
 };
 const DeviceLimits& limits() {
+  if (esn_dry_run()) {      // nominal B200: 148 SMs, 227 KB opt-in shared memory minus the kernel's static part
+    static const DeviceLimits nominal = {148, 232448 - 1024};
+    return nominal;
+  }
   static DeviceLimits ls[kEsnMaxDevices];
   static std::once_flag once[kEsnMaxDevices];
   const int dev = esn_current_device();
@@ -957,6 +961,7 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     a.g_dw = grid % a.tiles_w;
     a.g_dh = (grid / a.tiles_w) % a.tiles_h;
     a.g_dn = grid / (a.tiles_w * a.tiles_h);
+    if (esn_dry_run()) continue;      // planned and accepted; nothing is launched
 #define ESN_LAUNCH(KBv, Mv) conv_umma_kernel<KBv, Mv><<<grid, kThreads, smem, st>>>(a)
 #define ESN_LAUNCH_KB(KBv)                                                   \
   do {                                                                       \

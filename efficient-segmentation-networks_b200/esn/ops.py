@@ -436,7 +436,9 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
             for i, q in enumerate(parts):
                 last = i == len(parts) - 1
                 xi = x[:, 64 * q.cin_lo:64 * q.cin_lo + q.cin]
-                yi = out if last else new_act(n, prep.cout, ho, wo, out.dtype, x.device)
+                # partial sums live in private buffers whose pixel stride is a multiple of 8 channels (TMA alignment)
+                yi = out if last else new_act(n, prep.cout, ho, wo, out.dtype, x.device,
+                                              c_alloc=(prep.cout + 7) // 8 * 8 if prep.cout % 8 else None)
                 conv2d(xi, q, out=yi, residual=acc)
                 acc = yi
             return out

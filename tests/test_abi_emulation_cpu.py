@@ -103,3 +103,34 @@ def test_declined_tcgen05_call_takes_the_direct_kernel(spec, golden):
     with torch.no_grad():
         ref = nets.forward("ESNet", sd, x)
     assert _rel(y.float(), ref) < 5e-2
+
+
+def test_real_library_planner_accepts_every_call_at_benchmark_shapes():
+    """tests/planner_dry_run.py in a subprocess (ESN_DRY_RUN=1 must not leak into this process): every C-ABI call of a
+    bf16 forward at 1024x2048 goes to the REAL libesn_sm100.so; argument validation of every entry point and the full
+    launch planner of esn_conv2d_umma (tile shapes, reuse mode, shared-memory / TMEM budget, nominal B200 limits) must
+    accept it.  -4 = validation passed and the launch failed for lack of a GPU; 0 = planner dry run accepted."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    args = []
+    for name in NETS:
+        args += [name, "1024", "2048"]
+    for name in ("ESNet", "ContextNet", "EDANet"):
+        args += [name, "64", "128", name, "512", "1024"]
+    env = dict(os.environ, ESN_DRY_RUN="1")
+    r = subprocess.run([sys.executable, os.path.join(here, "planner_dry_run.py")] + args, env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(res) == len(NETS) + 6
+    for key, v in res.items():
+        assert v["refused"] == [], (key, v["refused"][:5])
+        assert all(k.endswith(":0") or k.endswith(":-4") for k in v["calls"]), (key, v["calls"])
+        assert v["calls"].get("esn_conv2d_umma:0", 0) > 10, (key, v["calls"])
+    # the verified default workload launches what the B200 bench recorded (profiles/r01_bench_erfnet.json "kernels")
+    erf = res["ERFNet@1024x2048"]["calls"]
+    assert erf["esn_conv2d_umma:0"] == 36 and erf["esn_conv_pair_umma:-4"] == 18
+    assert "ESN_DRY_RUN" not in os.environ
