@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="erfnet_infer_bf16_b16_1024x2048", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-u8-leg", action="store_true", help="skip the extra e2e_u8 leg (inference, N=1)")
     ap.add_argument("--e2e-input", default="f32", choices=["f32", "u8"],
                     help="what crosses PCIe in the e2e leg: the reference's pre-processed fp32 NCHW batch (default), or the "
                          "decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / CHW done on the device "
@@ -317,11 +318,17 @@ def main():
 
     # ---- e2e: pinned host images -> H2D -> forward -> D2H uint8 masks, every step, double-buffered
     u8_in = args.e2e_input == "u8"
+    mean_bgr = [72.3924, 82.90902, 73.158325]      # dataset/inform/cityscapes_inform.pkl['mean'] (BGR, fp32)
+    u8 = {}
+
+    def u8_buffers():
+        if not u8:
+            g8 = torch.Generator().manual_seed(1234 + rank)
+            u8["host"] = torch.randint(0, 256, (batch, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
+            u8["dev"] = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        return u8["host"], u8["dev"]
     if u8_in:
-        mean_bgr = [72.3924, 82.90902, 73.158325]      # dataset/inform/cityscapes_inform.pkl['mean'] (BGR, fp32)
-        g8 = torch.Generator().manual_seed(1234 + rank)
-        x_host_u8 = torch.randint(0, 256, (batch, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
-        xin_u8 = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        x_host_u8, xin_u8 = u8_buffers()
     h2d = (x_host_u8.numel() if u8_in else x_host.numel() * 4) + (y_host.numel() * 8 if train else 0)
     d2h = 4 if train else batch * H * W
     mask_host = [(torch.empty((), dtype=torch.float32) if train else torch.empty((batch, H, W), dtype=torch.uint8)).pin_memory()
@@ -331,7 +338,9 @@ def main():
     copy_s = torch.cuda.Stream()
     main_s = torch.cuda.current_stream()
 
-    def e2e_loop(k):
+    def e2e_loop(k, from_u8=u8_in):
+        if from_u8:
+            x_host_u8, xin_u8 = u8_buffers()
         ready = [None, None]
         done = [None, None]
         for i in range(k + 1):
@@ -340,7 +349,7 @@ def main():
                 with torch.cuda.stream(copy_s):
                     if done[b] is not None:
                         copy_s.wait_event(done[b])      # buffer b free (its compute finished)
-                    if u8_in:
+                    if from_u8:
                         xin_u8[b].copy_(x_host_u8, non_blocking=True)
                     else:
                         xin[b].copy_(x_host, non_blocking=True)
@@ -351,7 +360,7 @@ def main():
             if i >= 1:
                 pb = (i - 1) & 1
                 main_s.wait_event(ready[pb])
-                if u8_in:      # device half of the dataset class: uint8 HWC BGR -> fp32 NCHW RGB - mean (one launch)
+                if from_u8:    # device half of the dataset class: uint8 HWC BGR -> fp32 NCHW RGB - mean (one launch)
                     ops.image_u8_to_f32(xin_u8[pb], mean_bgr, True, out=xin[pb])
                 mk = gstep(xin[pb], yin[pb]) if gstep is not None else step(xin[pb], yin[pb])
                 mask_host[pb].copy_(mk, non_blocking=True)
@@ -444,6 +453,31 @@ def main():
                       "tensor_frac": round(flops / (ms_per_step / 1e3) / 1e12 / tc_peak, 4),
                       "note": "block-fused algorithmic bytes (SURVEY 8d) and conv FLOPs of the whole forward / step time"}
 
+    # ---- extra leg (inference, N=1): the same e2e loop fed with decoded uint8 HWC BGR images, normalised on the device by
+    # esn_image_u8hwc_to_f32nchw.  Reported next to `e2e`, never instead of it; guarded so that a failure of
+    # this newer kernel cannot cost the line above.  Self-check: bit-equality with the same fp32 arithmetic done by torch.
+    e2e_u8 = None
+    if world == 1 and not train and not u8_in and not args.no_u8_leg:
+        try:
+            x_host_u8, xin_u8 = u8_buffers()
+            xin_u8[0].copy_(x_host_u8)
+            sub = xin_u8[0][:2]
+            got = ops.image_u8_to_f32(sub, mean_bgr, True)
+            want = (sub.float() - torch.tensor(mean_bgr, device="cuda")).flip(3).permute(0, 3, 1, 2)
+            exact = bool(torch.equal(got, want))
+            del got, want
+            e2e_loop(2, True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_loop(k_e2e, True)
+            torch.cuda.synchronize()
+            u8_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
+            e2e_u8 = {"value": round(batch / (u8_ms / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": x_host_u8.numel(),
+                      "d2h_bytes_per_step": d2h, "ms_per_step": round(u8_ms, 3), "steps": k_e2e, "bit_exact_vs_torch": exact,
+                      "note": "pinned uint8 HWC BGR images -> H2D -> esn_image_u8hwc_to_f32nchw -> model.predict_mask -> D2H uint8 masks"}
+        except Exception as exc:      # noqa: BLE001 -- report, do not lose the measured line
+            e2e_u8 = {"error": repr(exc)[:300]}
+
     if rank != 0:
         _finish(dist)
         return
@@ -461,6 +495,7 @@ def main():
                      "copies double-buffered on a side stream" if u8_in else
                      "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"),
                     "input": args.e2e_input},
+            "e2e_u8": e2e_u8,
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}
@@ -468,6 +503,12 @@ def main():
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
     emit(line)
+    if e2e_u8 is not None and "error" in e2e_u8:
+        # the guarded leg failed: if it left a sticky CUDA error, a normal interpreter shutdown could abort after the line
+        # has been printed; leave directly (all results are out)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     _finish(dist)
 
 
