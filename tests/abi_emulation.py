@@ -30,12 +30,25 @@ def _buf(ptr, count, dtype, esize):
     return torch.frombuffer((C.c_char * (count * esize)).from_address(ptr), dtype=dtype)
 
 
+ALLOCS = []       # (begin, end) byte ranges of every activation buffer handed out by ops.new_act under the emulation
+
+
+def _in_bounds(ptr, nbytes):
+    """A descriptor that starts inside a tracked activation buffer must end inside it (a widened channel slice that runs
+    past the last pixel of its buffer would be an out-of-bounds read on the device)."""
+    for lo, hi in ALLOCS:
+        if lo <= ptr < hi:
+            assert ptr + nbytes <= hi, "descriptor overruns its buffer by %d bytes" % (ptr + nbytes - hi)
+            return
+
+
 def tensor(d):
     """EsnTensor -> logical (N,C,H,W) view over the caller's memory."""
     dtype, es = _DT[d.dtype]
     if d.layout == L.ESN_NHWC:
         assert d.c_stride >= d.c > 0
         span = (d.n * d.h * d.w - 1) * d.c_stride + d.c
+        _in_bounds(d.ptr, span * es)
         return _buf(d.ptr, span, dtype, es).as_strided((d.n, d.c, d.h, d.w), (d.h * d.w * d.c_stride, 1, d.w * d.c_stride, d.c_stride))
     return _buf(d.ptr, d.n * d.c * d.h * d.w, dtype, es).view(d.n, d.c, d.h, d.w)
 
@@ -279,8 +292,13 @@ def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag="", allow_unsupported=Fa
 def _new_act(n, c, h, w, dtype, device, c_alloc=None, zero=False):
     ca = c if c_alloc is None else c_alloc
     buf = torch.zeros((n, h, w, ca), dtype=dtype, device=device) if zero else torch.full((n, h, w, ca), float("nan"), dtype=dtype, device=device)
+    ALLOCS.append((buf.data_ptr(), buf.data_ptr() + buf.numel() * buf.element_size()))
+    _KEEP.append(buf)      # keep every buffer alive for the duration of the emulation so that address ranges stay unique
     t = buf.permute(0, 3, 1, 2)
     return t if ca == c else t[:, :c]
+
+
+_KEEP = []
 
 
 def _to_nchw(x, dtype=None):
@@ -309,6 +327,8 @@ def emulate_abi(bf16=False):
     saved = {k: getattr(ops, k) for k in swaps}
     saved_profile = ops.PROFILE
     del CALLS[:]
+    del ALLOCS[:]
+    del _KEEP[:]
     try:
         for k, v in swaps.items():
             setattr(ops, k, v)
@@ -318,3 +338,5 @@ def emulate_abi(bf16=False):
         for k, v in saved.items():
             setattr(ops, k, v)
         ops.PROFILE = saved_profile
+        del ALLOCS[:]
+        del _KEEP[:]

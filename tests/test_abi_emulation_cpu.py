@@ -134,3 +134,16 @@ def test_real_library_planner_accepts_every_call_at_benchmark_shapes():
     erf = res["ERFNet@1024x2048"]["calls"]
     assert erf["esn_conv2d_umma:0"] == 36 and erf["esn_conv_pair_umma:-4"] == 18
     assert "ESN_DRY_RUN" not in os.environ
+
+
+def test_emulator_catches_a_descriptor_that_overruns_its_buffer():
+    """The bounds tracking is live: a channel slice widened past the end of its pixel (legal for ops.widen, which only
+    compares with the pixel stride) overruns the buffer at the last pixel and is refused by the C-ABI model."""
+    from esn import ops
+    from esn._lib import ACT_NONE
+    with emulate_abi():
+        buf = ops.new_act(1, 8, 2, 2, torch.float32, "cpu", zero=True)
+        tail = buf[:, 4:8]
+        ops.affine_act(tail, None, None, None, ACT_NONE)                       # in bounds
+        with pytest.raises(AssertionError, match="overruns"):
+            ops.affine_act(ops.widen(tail, 8), None, None, None, ACT_NONE)     # 4 channels past the last pixel
