@@ -136,14 +136,20 @@ def test_real_library_planner_accepts_every_call_at_benchmark_shapes():
     assert "ESN_DRY_RUN" not in os.environ
 
 
-def test_emulator_catches_a_descriptor_that_overruns_its_buffer():
-    """The bounds tracking is live: a channel slice widened past the end of its pixel (legal for ops.widen, which only
-    compares with the pixel stride) overruns the buffer at the last pixel and is refused by the C-ABI model."""
+def test_a_view_that_overruns_its_buffer_is_refused():
+    """A channel slice widened past the end of its pixel would read out of bounds at the last pixel of the buffer.
+    torch refuses to build such a view when the buffer is the whole storage (ops.widen -> as_strided); the C-ABI model
+    checks descriptors against the tracked activation buffers for the remaining case (a view into a larger storage)."""
+    import abi_emulation as A
     from esn import ops
     from esn._lib import ACT_NONE
     with emulate_abi():
         buf = ops.new_act(1, 8, 2, 2, torch.float32, "cpu", zero=True)
         tail = buf[:, 4:8]
         ops.affine_act(tail, None, None, None, ACT_NONE)                       # in bounds
+        with pytest.raises(RuntimeError, match="out of bounds"):
+            ops.widen(tail, 8)                                                 # 4 channels past the last pixel
+        d = ops.tdesc(tail)
+        d.c = 8                                                                # the same overrun, forged at descriptor level
         with pytest.raises(AssertionError, match="overruns"):
-            ops.affine_act(ops.widen(tail, 8), None, None, None, ACT_NONE)     # 4 channels past the last pixel
+            A.tensor(d)
