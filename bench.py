@@ -42,6 +42,7 @@ WORKLOADS = {
     "esnet_infer_bf16_b16_1024x2048": ("ESNet", 16, 1024, 2048, "infer"),
     "contextnet_infer_bf16_b16_1024x2048": ("ContextNet", 16, 1024, 2048, "infer"),
     "edanet_infer_bf16_b16_1024x2048": ("EDANet", 16, 1024, 2048, "infer"),
+    "lednet_infer_bf16_b16_1024x2048": ("LEDNet", 16, 1024, 2048, "infer"),
     # BASELINE.json configs[2]: DABNet bf16 training, batch 8/GPU, 512x1024, weighted CE, Adam, data parallel
     "dabnet_train_bf16_b8_512x1024": ("DABNet", 8, 512, 1024, "train"),
     "erfnet_train_bf16_b8_512x1024": ("ERFNet", 8, 512, 1024, "train"),
@@ -53,9 +54,9 @@ WORKLOADS = {
 # logits term (19 elements/pixel) is replaced by the 1-byte argmax mask because the head is fused.
 ALG_ELEMS_PER_PX = {"ERFNet": 162.0, "DABNet": 189.5, "ENet": 178.0, "CGNet": 234.3, "FastSCNN": 54.6,
                     "ESPNet": 141.2, "ESPNet_v2": 186.9,
-                    "ESNet": 142.0, "ContextNet": 67.2, "EDANet": 231.7}       # tools/probe_alg_elems.py (reproduces 162.0 / 54.6 for ERFNet / FastSCNN)
+                    "ESNet": 142.0, "ContextNet": 67.2, "EDANet": 231.7, "LEDNet": 146.6}       # tools/probe_alg_elems.py (reproduces 162.0 / 54.6 for ERFNet / FastSCNN)
 GMAC_512x1024 = {"ERFNet": 26.60, "DABNet": 10.22, "ENet": 4.12, "CGNet": 6.76, "FastSCNN": 1.68, "ESPNet": 3.36,
-                 "ESPNet_v2": 5.65, "ESNet": 24.05, "ContextNet": 1.68, "EDANet": 8.83}
+                 "ESPNet_v2": 5.65, "ESNet": 24.05, "ContextNet": 1.68, "EDANet": 8.83, "LEDNet": 11.20}
 
 
 def peaks():

@@ -14,6 +14,7 @@ from model.ESPNet_v2.SegmentationModel import EESPNet_Seg
 from model.ESNet import ESNet
 from model.ContextNet import ContextNet
 from model.EDANet import EDANet
+from model.LEDNet import LEDNet
 
 _HOT_PATH = {
     "ERFNet": ERFNet,
@@ -27,6 +28,7 @@ _HOT_PATH = {
     "ESNet": ESNet,
     "ContextNet": ContextNet,
     "EDANet": EDANet,
+    "LEDNet": LEDNet,
 }
 _REFERENCE_NAMES = ("SQNet", "LinkNet", "SegNet", "UNet", "ENet", "ERFNet", "CGNet", "EDANet", "ESNet", "ESPNet",
                     "LEDNet", "ESPNet_v2", "ContextNet", "FastSCNN", "DABNet", "FSSNet", "FPENet", "DF1Seg", "DF1SegG")

@@ -117,6 +117,7 @@ SYMBOLS = {
     "esn_avgpool3x3s2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
     "esn_dropout": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_uint64, C.c_float, C.c_int32, C.c_void_p]),
     "esn_confusion_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "esn_gate_bcast": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_image_u8hwc_to_f32nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                              C.c_int32, C.c_void_p]),
     "esn_dropout_step": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_uint64, C.c_void_p, C.c_float, C.c_int32,

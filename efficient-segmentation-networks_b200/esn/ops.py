@@ -688,6 +688,18 @@ def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, 
     return sums, g
 
 
+def gate_bcast(g, x, b=None, out=None):
+    """y = g * x + b with g (N,1,H,W), x (N,C,H,W), b (N,C,1,1) or None (LEDNet's APN close, LEDNet.py:279-281)."""
+    n, c, h, w = x.shape
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device, c_alloc=x.stride(3), zero=x.stride(3) != c)
+    dg, dx, dy = tdesc(g), tdesc(x), tdesc(out)
+    db = tdesc(b) if b is not None else _NULL
+    _call(L.lib.esn_gate_bcast, "esn_gate_bcast", (C.byref(dg), C.byref(dx), C.byref(db), C.byref(dy)),
+          _nbytes(g) + _nbytes(x) + _nbytes(out))
+    return out
+
+
 def image_u8_to_f32(img, mean, reverse_channels=True, out=None):
     """Device half of the reference's dataset classes (dataset/cityscapes.py:74-78,164-170,208-214): uint8 HWC batch
     (N,H,W,3) in cv2's BGR order -> fp32 NCHW (N,3,H,W) = (img - mean)[..., ::-1] transposed; `mean` holds three values in

@@ -688,3 +688,72 @@ def edanet(sd, x, train=False, stats=None):
 
 
 FORWARD["EDANet"] = edanet
+
+
+# --------------------------------------------------------------------------- LEDNet (oracle only so far)
+def _led_shuffle(x, groups=2):
+    """Channel_shuffle, model/LEDNet.py:27-39: out[:, j*groups + g] = x[:, g*(C/groups) + j]."""
+    n, c, h, w = x.shape
+    return x.view(n, groups, c // groups, h, w).transpose(1, 2).reshape(n, c, h, w)
+
+
+def led_ssnbt(p, x, d):
+    """SS_nbt_module_paper (eval), model/LEDNet.py:108-186: split in halves; left 3x1 -> 1x3, right 1x3 -> 3x1 (twice,
+    second time dilated), merge, + input, ReLU, channel shuffle."""
+    c1 = x.shape[1] // 2          # round(c * 0.5) for even c
+    x1, x2 = x[:, :c1], x[:, c1:]
+
+    def conv(t, key, vertical, dil):
+        pad = (dil, 0) if vertical else (0, dil)
+        dl = (dil, 1) if vertical else (1, dil)
+        return F.conv2d(t, p[key + ".weight"], p[key + ".bias"], padding=pad, dilation=dl)
+    o1 = F.relu(conv(x1, "conv3x1_1_l", True, 1))
+    o1 = F.relu(bn(p.sub("bn1_l"), conv(o1, "conv1x3_1_l", False, 1), 1e-3))
+    o2 = F.relu(conv(x2, "conv1x3_1_r", False, 1))
+    o2 = F.relu(bn(p.sub("bn1_r"), conv(o2, "conv3x1_1_r", True, 1), 1e-3))
+    o1 = F.relu(conv(o1, "conv3x1_2_l", True, d))
+    o1 = bn(p.sub("bn2_l"), conv(o1, "conv1x3_2_l", False, d), 1e-3)
+    o2 = F.relu(conv(o2, "conv1x3_2_r", False, d))
+    o2 = bn(p.sub("bn2_r"), conv(o2, "conv3x1_2_r", True, d), 1e-3)
+    return _led_shuffle(F.relu(x + torch.cat([o1, o2], 1)))
+
+
+def led_apn(p, x):
+    """APNModule, model/LEDNet.py:189-283: global-pool branch + 1x1 mid branch gated by a 3-level single-channel pyramid
+    (7/5/3-tap asymmetric convs with strides (2,1) then (1,2)); every resize is bilinear, align_corners=True."""
+    h, w = x.shape[2:]
+    up = lambda t, size: F.interpolate(t, size=size, mode="bilinear", align_corners=True)
+
+    def cbr(q, t):      # Conv2dBnRelu :46-56
+        return F.relu(bn(q.sub("conv.1"), F.conv2d(t, q["conv.0.weight"], q["conv.0.bias"]), 1e-3))
+
+    def pair(q, t, i, k, stride):       # (k,1) conv stride (s,1), (1,k) conv stride (1,s), BN, ReLU
+        t = F.conv2d(t, q["%d.weight" % i], q["%d.bias" % i], stride=(stride, 1), padding=(k // 2, 0))
+        t = F.conv2d(t, q["%d.weight" % (i + 1)], q["%d.bias" % (i + 1)], stride=(1, stride), padding=(0, k // 2))
+        return F.relu(bn(q.sub("%d" % (i + 2)), t, 1e-3))
+    b1 = up(cbr(p.sub("branch1.1"), F.adaptive_avg_pool2d(x, 1)), (h, w))
+    mid = cbr(p.sub("mid.0"), x)
+    x1 = pair(p.sub("down1"), x, 0, 7, 2)
+    x2 = pair(p.sub("down2"), x1, 0, 5, 2)
+    x3 = pair(p.sub("down3"), pair(p.sub("down3"), x2, 0, 3, 2), 4, 3, 1)
+    x3 = up(x3, ((h + 3) // 4, (w + 3) // 4))
+    y = up(pair(p.sub("conv2"), x2, 0, 5, 1) + x3, ((h + 1) // 2, (w + 1) // 2))
+    y = up(y + pair(p.sub("conv1"), x1, 0, 7, 1), (h, w))
+    return y * mid + b1
+
+
+LED_LAYERS = [1, 1, 1, None, 1, 1, None, 1, 2, 5, 9, 2, 5, 9, 17]       # LEDNet.py:291-313 (None = DownsamplerBlock)
+
+
+def lednet(sd, x, train=False, stats=None):
+    """LEDNet.forward, model/LEDNet.py:316-327 (even sizes: the F.pad of the downsampler is a no-op)."""
+    p = SD(sd, "", x.dtype, train, stats)
+    y = erf_downsampler(p.sub("initial_block"), x)
+    for i, d in enumerate(LED_LAYERS):
+        q = p.sub("layers.%d" % i)
+        y = erf_downsampler(q, y) if d is None else led_ssnbt(q, y, d)
+    y = led_apn(p.sub("apn"), y)
+    return F.interpolate(y, x.shape[2:], mode="bilinear", align_corners=True)
+
+
+FORWARD["LEDNet"] = lednet

@@ -254,6 +254,17 @@ def esn_dab_dw_pair(ref):
     return 0
 
 
+def esn_gate_bcast(gr, xr, br, yr):
+    g, x, y = tensor(gr._obj).float(), tensor(xr._obj).float(), tensor(yr._obj)
+    assert gr._obj.dtype == xr._obj.dtype == yr._obj.dtype and g.shape[1] == 1
+    v = g * x
+    if br._obj.ptr:
+        assert br._obj.dtype == xr._obj.dtype and (br._obj.h, br._obj.w) == (1, 1)
+        v = v + tensor(br._obj).float()
+    store(y, v)
+    return 0
+
+
 def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
     src = torch.frombuffer((C.c_char * (n * h * w * 3)).from_address(img.value), dtype=torch.uint8).view(n, h, w, 3)
     v = src.float() - torch.tensor([mean3[0], mean3[1], mean3[2]], dtype=torch.float32)
@@ -272,7 +283,7 @@ ENTRY = {
     "esn_convert_layout": esn_convert_layout, "esn_adaptive_avgpool": esn_adaptive_avgpool, "esn_bilinear_nhwc": esn_bilinear_nhwc,
     "esn_head_convt2x2": esn_head_convt2x2, "esn_head_bilinear": esn_head_bilinear,
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
-    "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw,
+    "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 

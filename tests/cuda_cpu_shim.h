@@ -52,3 +52,7 @@ static void shim_launch(unsigned grid, unsigned block, F body) {
     pthread_barrier_destroy(&shim_barrier);
   }
 }
+
+// element access helpers of esn_common.cuh (float only on the CPU; the bf16 specialisations differ in the conversion only)
+template <typename T> static inline float ld1(const T* p) { return static_cast<float>(*p); }
+template <typename T> static inline void st1(T* p, float v) { *p = static_cast<T>(v); }

@@ -190,6 +190,15 @@ def max_unpool2x2(v, idx, ext=None, act=L.ACT_NONE, alpha=None):
     return _store(y, _act(up if ext is None else up + ext.float(), act, alpha))
 
 
+def gate_bcast(g, x, b=None, out=None):
+    """include/esn.h esn_gate_bcast: y = g * x + b, g (N,1,H,W), b (N,C,1,1) or None."""
+    n, c, h, w = x.shape
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device, c_alloc=x.stride(3), zero=x.stride(3) != c)
+    v = g.float() * x.float()
+    return _store(out, v if b is None else v + b.float())
+
+
 def dab_dw_pair(x, prm, dilation, out=None):
     """include/esn.h EsnDabPair; prm rows: 0-11 taps of (3x1, 1x3, dilated 3x1, dilated 1x3), 12-23 their
     (scale, shift, alpha) triples, 24-26 the closing BN + PReLU (model/DABNet.py DABModule._build_prep)."""
@@ -208,7 +217,7 @@ def dab_dw_pair(x, prm, dilation, out=None):
     return _store(out, _act((br1 + br2) * _vec(fin[0]) + _vec(fin[1]), L.ACT_PRELU, fin[2]))
 
 
-_SWAPS = dict(fglo_gate=fglo_gate, maxpool3x3s2_idx=maxpool3x3s2_idx, max_unpool2x2=max_unpool2x2,
+_SWAPS = dict(gate_bcast=gate_bcast, fglo_gate=fglo_gate, maxpool3x3s2_idx=maxpool3x3s2_idx, max_unpool2x2=max_unpool2x2,
               dab_dw_pair=dab_dw_pair, new_act=new_act, require_cuda=require_cuda, as_act=as_act, to_nchw=to_nchw, conv2d=conv2d,
               stem_conv3x3s2=stem_conv3x3s2, maxpool2x2=maxpool2x2, avgpool3x3s2=avgpool3x3s2, affine_act=affine_act,
               adaptive_avgpool=adaptive_avgpool, bilinear=bilinear, head_convt2x2=head_convt2x2,

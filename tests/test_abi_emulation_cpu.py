@@ -14,7 +14,7 @@ from abi_emulation import emulate_abi
 from conftest import spec_state_dict
 from oracle import fixture, nets
 
-NETS = ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet"]
+NETS = ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet", "LEDNet"]
 
 
 def _rel(a, b):
@@ -118,14 +118,14 @@ def test_real_library_planner_accepts_every_call_at_benchmark_shapes():
     args = []
     for name in NETS:
         args += [name, "1024", "2048"]
-    for name in ("ESNet", "ContextNet", "EDANet"):
+    for name in ("ESNet", "ContextNet", "EDANet", "LEDNet"):
         args += [name, "64", "128", name, "512", "1024"]
     env = dict(os.environ, ESN_DRY_RUN="1")
     r = subprocess.run([sys.executable, os.path.join(here, "planner_dry_run.py")] + args, env=env, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
-    assert len(res) == len(NETS) + 6
+    assert len(res) == len(NETS) + 8
     for key, v in res.items():
         assert v["refused"] == [], (key, v["refused"][:5])
         assert all(k.endswith(":0") or k.endswith(":-4") for k in v["calls"]), (key, v["calls"])

@@ -17,7 +17,7 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm()).item()
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet", "LEDNet"])
 def test_model_composition_matches_reference_golden(name, spec, golden):
     from builders.model_builder import build_model
     m = build_model(name, 19)
@@ -96,3 +96,23 @@ def test_edanet_blocks_match_oracle(spec):
             ref = nets.eda_module(nets.SD(sd, pre + "residual_dense_layers.%d." % i), ref, d)
         y = blk(x)
         assert y.shape == ref.shape and _rel(y, ref) < 1e-5
+
+
+def test_lednet_blocks_match_oracle(spec):
+    from model.LEDNet import APNModule, SS_nbt_module_paper
+    sd = spec_state_dict(spec, "LEDNet")
+    torch.manual_seed(0)
+    with emulate_kernels(), torch.no_grad():
+        for idx, chann, d in ((1, 32, 1), (5, 64, 1), (9, 128, 5)):
+            pre = "layers.%d." % idx
+            blk = SS_nbt_module_paper(chann, 0.03, d).eval()
+            blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+            x = torch.randn(2, chann, 24, 40)
+            assert _rel(blk(x), nets.led_ssnbt(nets.SD(sd, pre), x, d)) < 1e-5, (chann, d)
+        apn = APNModule(128, 19).eval()
+        apn.load_state_dict({k[len("apn."):]: v for k, v in sd.items() if k.startswith("apn.")})
+        for hw in ((24, 40), (9, 13)):            # odd sizes: the pyramid levels are ceil(h/2), ceil(h/4), ceil(h/8)
+            x = torch.randn(2, 128, *hw).relu()
+            y = apn(x)
+            ref = nets.led_apn(nets.SD(sd, "apn."), x)
+            assert y.shape == ref.shape and _rel(y, ref) < 1e-5, hw

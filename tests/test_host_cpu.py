@@ -36,7 +36,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(L.EsnConv) == 2 * 40 + 8 + 10 * 4 + 72
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet", "LEDNet"])
 def test_state_dict_keys_match_reference(name, spec):
     from builders.model_builder import build_model
     m = build_model(name, 19)

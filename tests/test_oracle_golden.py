@@ -10,7 +10,7 @@ from conftest import spec_state_dict
 from oracle import fixture, loss as oloss, nets
 
 
-@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet"])
+@pytest.mark.parametrize("name", ["ERFNet", "DABNet", "ENet", "CGNet", "FastSCNN", "ESPNet_v2", "ESPNet", "ESNet", "ContextNet", "EDANet", "LEDNet"])
 def test_eval_forward_matches_reference(name, spec, golden):
     sd = spec_state_dict(spec, name)
     g = golden(name)
@@ -68,6 +68,7 @@ def test_state_dict_spec_counts(spec):
     assert spec["ENet"]["n_params"] == 360422
     assert spec["ContextNet"]["n_params"] == 876563          # usage.txt:95
     assert spec["EDANet"]["n_params"] == 689485              # usage.txt:97
+    assert spec["LEDNet"]["n_params"] == 917387              # usage.txt:105
     # usage.txt:100 lists 1,660,607 for ESNet: its hook-based counter sees each PFCU's shared bn2 three times
     assert spec["ESNet"]["n_params"] == 1660607 - 3 * 2 * 256
 

@@ -1,4 +1,4 @@
-"""Model-level parity (GPU) for the nets of SURVEY 8f-1 / 8f-2 (ESNet, EDANet, ContextNet): same checks and tolerances as
+"""Model-level parity (GPU) for the nets of SURVEY 8f-1 / 8f-2 (ESNet, EDANet, LEDNet, ContextNet): same checks and tolerances as
 tests/test_models_gpu.py -- fp32 logits vs the unmodified reference's golden (1e-3), argmax >= 99.9 %, bf16 vs the
 CPU oracle (5e-2 or torch's own bf16-autocast error on the same graph).
 
@@ -17,7 +17,7 @@ from oracle import fixture, nets
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first B200 run pending (round-1 GPU budget spent before these nets landed)")]
 
-NETS = ["ESNet", "ContextNet", "EDANet"]
+NETS = ["ESNet", "ContextNet", "EDANet", "LEDNet"]
 
 
 @pytest.mark.parametrize("name", NETS)
@@ -74,6 +74,42 @@ def test_edanet_blocks_are_drop_in(spec):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         yb = blk(x.cuda())
     assert yb.dtype == torch.bfloat16 and T._rel(yb.float().cpu(), ref) < T.BF16_LOGIT_TOL
+
+
+def test_lednet_blocks_are_drop_in(spec):
+    """SS_nbt_module_paper (split / two factorized branches / merge + input / shuffle) and APNModule on their own."""
+    from model.LEDNet import APNModule, SS_nbt_module_paper
+    sd = spec_state_dict(spec, "LEDNet")
+    torch.manual_seed(0)
+    for idx, chann, d in ((1, 32, 1), (5, 64, 1), (9, 128, 5)):
+        pre = "layers.%d." % idx
+        blk = SS_nbt_module_paper(chann, 0.03, d)
+        blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        blk = blk.cuda().eval()
+        x = torch.randn(2, chann, 24, 40)
+        ref = nets.led_ssnbt(nets.SD(sd, pre), x, d)
+        assert T._rel(blk(x.cuda()).float().cpu(), ref) < 1e-4, (chann, d)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yb = blk(x.cuda())
+        assert yb.dtype == torch.bfloat16 and T._rel(yb.float().cpu(), ref) < T.BF16_LOGIT_TOL, (chann, d)
+    apn = APNModule(128, 19)
+    apn.load_state_dict({k[len("apn."):]: v for k, v in sd.items() if k.startswith("apn.")})
+    x = torch.randn(2, 128, 24, 40).relu()
+    ref = nets.led_apn(nets.SD(sd, "apn."), x)
+    y = apn.cuda().eval()(x.cuda())
+    assert y.shape == ref.shape and T._rel(y.float().cpu(), ref) < 1e-4
+
+
+def test_gate_bcast_matches_torch():
+    from esn import ops
+    torch.manual_seed(1)
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        g = ops.as_act(torch.randn(2, 1, 9, 13).cuda(), dt)
+        x = ops.as_act(torch.randn(2, 19, 9, 13).cuda(), dt)
+        b = ops.as_act(torch.randn(2, 19, 1, 1).cuda(), dt)
+        want = g.float() * x.float() + b.float()
+        assert T._rel(ops.gate_bcast(g, x, b).float(), want) < tol
+        assert T._rel(ops.gate_bcast(g, x).float(), g.float() * x.float()) < tol
 
 
 def test_contextnet_quarter_scale_image():

@@ -20,6 +20,7 @@ UNITS = {
     "ESNet": ("DownsamplerBlock", "FCU", "PFCU", "UpsamplerBlock"),
     "ContextNet": ("Custom_Conv", "DepthSepConv", "LinearBottleneck", "FeatureFusionModule", "Classifer"),
     "EDANet": ("DownsamplerBlock", "EDAModule"),
+    "LEDNet": ("DownsamplerBlock", "SS_nbt_module_paper", "APNModule"),
     "ERFNet": ("DownsamplerBlock", "non_bottleneck_1d", "UpsamplerBlock"),
     "FastSCNN": ("_ConvBNReLU", "_DSConv", "LinearBottleneck", "PyramidPooling", "FeatureFusionModule", "Classifer"),
 }
