@@ -5,9 +5,10 @@ Under torch.distributed the weighted mean is taken over the GLOBAL batch (SURVEY
 import torch
 import torch.nn as nn
 
+from esn import ops
 from esn import train as T
 
-__all__ = ["CrossEntropyLoss2d"]
+__all__ = ["CrossEntropyLoss2d", "FocalLoss2d"]
 
 
 class CrossEntropyLoss2d(nn.Module):
@@ -23,9 +24,31 @@ class CrossEntropyLoss2d(nn.Module):
             self.weight = None
 
     def forward(self, output, target):
-        if not output.is_cuda:
-            raise RuntimeError("CrossEntropyLoss2d: tensors must live on a CUDA device; this framework has no CPU path")
+        ops.require_cuda(output, "CrossEntropyLoss2d")
         w = self.weight
         if w is not None and w.device != output.device:
             w = w.to(output.device)
         return T.cross_entropy(output, target.long(), w, self.ignore_label, self.distributed)
+
+
+class FocalLoss2d(nn.Module):
+    """Drop-in for the reference's FocalLoss2d (utils/losses/loss.py:96-127; `--use_focal` in train.py).  The reference
+    passes the MEAN-reduced weighted cross-entropy -- a scalar -- through the focal factor (loss.py:122-124), so the loss
+    is alpha * (1 - exp(-L))^gamma * L with L the value of the fused weighted-CE kernel; the three scalar operations run
+    on the device tensor (no host sync) and autograd hands their derivative to the CE kernel's backward as its upstream
+    gradient, which it folds into the d-logits it writes.  size_average: mean / sum of a scalar are the identity."""
+
+    def __init__(self, alpha=0.5, gamma=2, weight=None, ignore_index=255, size_average=True):
+        super().__init__()
+        self.alpha = alpha
+        self.gamma = gamma
+        self.weight = weight
+        self.ignore_index = ignore_index
+        self.size_average = size_average
+        self.ce_fn = CrossEntropyLoss2d(weight=weight, ignore_label=ignore_index)
+
+    def forward(self, output, target):
+        if target.dim() == 4:          # (N,1,H,W) labels, as the reference accepts
+            target = target[:, 0]
+        ce = self.ce_fn(output, target)
+        return self.alpha * (1.0 - torch.exp(-ce)) ** self.gamma * ce

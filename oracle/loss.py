@@ -40,3 +40,14 @@ def weighted_ce_grad(logits, target, weight=None, ignore_label=255):
     wi = wv[ys] * valid.to(x.dtype)
     g = (p - onehot) * (wi / wi.sum()).view(-1, 1)
     return g.view(n, h, w, c).permute(0, 3, 1, 2).contiguous()
+
+
+def focal(logits, target, weight=None, ignore_label=255, alpha=0.5, gamma=2):
+    """FocalLoss2d (utils/losses/loss.py:96-127).  The reference feeds the MEAN-reduced weighted cross-entropy (a scalar,
+    :122) through the focal factor, so the loss is a scalar function of the CE value:  alpha * (1 - e^-L)^gamma * L.
+    Returns (loss, dloss/dlogits)."""
+    ce, _, _ = weighted_ce(logits, target, weight, ignore_label)
+    pt = torch.exp(-ce)
+    loss = alpha * (1 - pt) ** gamma * ce
+    dloss_dce = alpha * ((1 - pt) ** gamma + ce * gamma * (1 - pt) ** (gamma - 1) * pt)
+    return loss, dloss_dce * weighted_ce_grad(logits, target, weight, ignore_label)

@@ -265,6 +265,34 @@ def esn_gate_bcast(gr, xr, br, yr):
     return 0
 
 
+def esn_weighted_ce(ref):
+    """include/esn.h EsnCE: sums[0] += sum w[y]*nll, sums[1] += sum w[y] over pixels with y != ignore; optional
+    dlogits = w[y] * (softmax - onehot) * (*gout) / (*gnorm) (unscaled when the scalars are absent)."""
+    p = ref._obj
+    d = p.logits
+    assert d.layout == L.ESN_NCHW
+    x = tensor(d).float()
+    n, c, h, w = x.shape
+    y = _buf(p.target, n * h * w, torch.int64, 8).view(n, h, w)
+    wv = vec(p.weight, c) if p.weight else torch.ones(c)
+    valid = y != p.ignore_label
+    ys = torch.where(valid, y, torch.zeros_like(y))
+    logp = torch.log_softmax(x, 1)
+    wi = wv[ys] * valid.float()
+    nll = -logp.gather(1, ys.unsqueeze(1)).squeeze(1)
+    sums = _buf(p.sums, 2, torch.float32, 4)
+    sums[0] += (wi * nll).sum()
+    sums[1] += wi.sum()
+    if p.dlogits.ptr:
+        g = (logp.exp() - torch.zeros_like(x).scatter_(1, ys.unsqueeze(1), 1.0)) * wi.unsqueeze(1)
+        if p.gout:
+            g = g * _buf(p.gout, 1, torch.float32, 4)[0]
+        if p.gnorm:
+            g = g / _buf(p.gnorm, 1, torch.float32, 4)[0]
+        store(tensor(p.dlogits), g)
+    return 0
+
+
 def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
     src = torch.frombuffer((C.c_char * (n * h * w * 3)).from_address(img.value), dtype=torch.uint8).view(n, h, w, 3)
     v = src.float() - torch.tensor([mean3[0], mean3[1], mean3[2]], dtype=torch.float32)
@@ -283,7 +311,7 @@ ENTRY = {
     "esn_convert_layout": esn_convert_layout, "esn_adaptive_avgpool": esn_adaptive_avgpool, "esn_bilinear_nhwc": esn_bilinear_nhwc,
     "esn_head_convt2x2": esn_head_convt2x2, "esn_head_bilinear": esn_head_bilinear,
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
-    "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast,
+    "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast, "esn_weighted_ce": esn_weighted_ce,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 

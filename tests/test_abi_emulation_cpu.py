@@ -153,3 +153,23 @@ def test_a_view_that_overruns_its_buffer_is_refused():
         d.c = 8                                                                # the same overrun, forged at descriptor level
         with pytest.raises(AssertionError, match="overruns"):
             A.tensor(d)
+
+
+def test_losses_through_the_abi_match_reference(golden):
+    """utils.losses.loss.CrossEntropyLoss2d / FocalLoss2d (drop-ins for loss.py:15-32 / :96-127): forward value and the
+    gradient autograd returns -- the scalar focal factor reaches the CE kernel's backward as its upstream gradient --
+    against the reference classes' fp64 golden, with esn_weighted_ce answered by the C-ABI model."""
+    from utils.losses.loss import CrossEntropyLoss2d, FocalLoss2d
+    g = golden("loss")
+    lab = torch.from_numpy(g["labels"])
+    w = torch.tensor(fixture.CLASS_WEIGHTS)
+    for crit, lkey, gkey in ((CrossEntropyLoss2d(weight=w, ignore_label=255), "loss", "grad"),
+                             (FocalLoss2d(alpha=0.5, gamma=2, weight=w, ignore_index=255), "focal_loss", "focal_grad")):
+        logits = torch.from_numpy(g["logits"]).float().requires_grad_(True)
+        with emulate_abi():
+            loss = crit(logits, lab)
+            loss.backward()
+        assert abs(loss.item() - g[lkey][0]) < 1e-5 * abs(g[lkey][0]), lkey
+        ref = torch.from_numpy(g[gkey])
+        assert _rel(logits.grad, ref) < 1e-5, gkey
+    assert list(FocalLoss2d(weight=w).state_dict().keys()) == ["ce_fn.weight"]       # the reference's only key

@@ -82,3 +82,13 @@ def test_weighted_ce_matches_reference(golden):
     assert abs(l.item() - g["loss"][0]) < 1e-12
     gr = oloss.weighted_ce_grad(logits, lab, w)
     assert np.abs(gr.numpy() - g["grad"]).max() < 1e-14
+
+
+def test_focal_loss_matches_reference(golden):
+    g = golden("loss")
+    logits = torch.from_numpy(g["logits"])
+    lab = torch.from_numpy(g["labels"])
+    w = torch.tensor(fixture.CLASS_WEIGHTS, dtype=torch.float64)
+    l, gr = oloss.focal(logits, lab, w, 255, alpha=0.5, gamma=2)
+    assert abs(l.item() - g["focal_loss"][0]) < 1e-12
+    assert np.abs(gr.numpy() - g["focal_grad"]).max() < 1e-14

@@ -135,3 +135,17 @@ def test_full_size_properties(spec):
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 yb = m(x)
         assert T._rel(yb.float(), y) < T.BF16_LOGIT_TOL
+
+
+def test_focal_loss_matches_reference_golden(golden):
+    """FocalLoss2d drop-in (loss.py:96-127) on the fused weighted-CE kernel: value and d-logits vs the
+    reference class in fp64."""
+    from utils.losses.loss import FocalLoss2d
+    g = golden("loss")
+    w = torch.tensor(fixture.CLASS_WEIGHTS)
+    crit = FocalLoss2d(alpha=0.5, gamma=2, weight=w, ignore_index=255).cuda()
+    logits = torch.from_numpy(g["logits"]).float().cuda().requires_grad_(True)
+    loss = crit(logits, torch.from_numpy(g["labels"]).cuda())
+    loss.backward()
+    assert abs(loss.item() - g["focal_loss"][0]) < 1e-4 * abs(g["focal_loss"][0])
+    assert T._rel(logits.grad.cpu(), torch.from_numpy(g["focal_grad"])) < 1e-4

@@ -110,9 +110,15 @@ def main():
     logits.requires_grad_(True)
     l = CE(weight=wt, ignore_label=255)(logits, lab)
     l.backward()
+    # ---- focal loss golden (reference FocalLoss2d on the same logits)
+    from utils.losses.loss import FocalLoss2d
+    lf = logits.detach().clone().requires_grad_(True)
+    fl = FocalLoss2d(alpha=0.5, gamma=2, weight=wt, ignore_index=255)(lf, lab)
+    fl.backward()
     np.savez_compressed(os.path.join(GOLD, "loss.npz"), logits=logits.detach().numpy(), labels=lab.numpy(),
-                        loss=np.array([l.item()]), grad=logits.grad.numpy())
-    print("loss golden written", l.item())
+                        loss=np.array([l.item()]), grad=logits.grad.numpy(),
+                        focal_loss=np.array([fl.item()]), focal_grad=lf.grad.numpy())
+    print("loss golden written", l.item(), "focal", fl.item())
 
 
 if __name__ == "__main__":
