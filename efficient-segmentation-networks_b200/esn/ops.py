@@ -146,7 +146,9 @@ def as_act(x, dtype=None):
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     n, c, h, w = x.shape
-    y = new_act(n, c, h, w, dtype, x.device, c_alloc=(c + 7) // 8 * 8 if c % 8 else None)
+    # channel counts that are not a multiple of 8 get a padded pixel stride; a single channel stays dense (for C = 1 the
+    # NHWC and NCHW layouts coincide and tdesc accepts only the dense form)
+    y = new_act(n, c, h, w, dtype, x.device, c_alloc=(c + 7) // 8 * 8 if (c % 8 and c > 1) else None)
     dx, dy = tdesc(x), tdesc(y)
     if dx.layout == L.ESN_NHWC:  # NHWC but other dtype: elementwise copy through the affine kernel
         return affine_act(x, None, None, None, L.ACT_NONE, out=y)

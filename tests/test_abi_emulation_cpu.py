@@ -173,3 +173,17 @@ def test_losses_through_the_abi_match_reference(golden):
         ref = torch.from_numpy(g[gkey])
         assert _rel(logits.grad, ref) < 1e-5, gkey
     assert list(FocalLoss2d(weight=w).state_dict().keys()) == ["ce_fn.weight"]       # the reference's only key
+
+
+def test_pending_gpu_test_code_runs_on_the_abi_model():
+    """tests/preflight_gpu_tests_on_cpu.py: the functions of tests/test_zz_*_gpu.py (not yet run on a B200) executed on
+    the CPU against the C-ABI model, in a subprocess because the script patches torch globally."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "preflight_gpu_tests_on_cpu.py")], capture_output=True, text=True,
+                       timeout=1200)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("PASS", "FAIL"))]
+    assert r.returncode == 0 and lines and not any(ln.startswith("FAIL") for ln in lines), "\n".join(lines[-30:]) + r.stderr[-1500:]
+    assert sum(ln.startswith("PASS") for ln in lines) >= 20
