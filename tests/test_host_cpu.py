@@ -91,3 +91,23 @@ def test_fused_transposed_conv_packing_equals_conv_transpose():
         y = y4.view(2, 2, 2, cout, 5, 7).permute(0, 3, 4, 1, 5, 2).reshape(2, cout, 10, 14)   # out[2i+a, 2j+b]
         ref = F.conv_transpose2d(x, m.weight.detach().to(torch.bfloat16).float(), m.bias.detach(), 2, 1, 1)
         assert (y - ref).abs().max() <= 2e-6 * ref.abs().max()
+
+
+def test_call_wrapper_contract(monkeypatch):
+    """esn.ops._call (the one place every kernel launch goes through): 0 -> True; an error code raises; with
+    allow_unsupported an ESN_ERR_UNSUPPORTED answer returns False (the caller takes its next CUDA route) and warns once."""
+    from esn import ops, _lib
+    monkeypatch.setattr(ops, "stream", lambda: None)
+    monkeypatch.setattr(ops, "PROFILE", None)
+    seen = []
+    assert ops._call(lambda a, st: seen.append((a, st)) or 0, "esn_fake", (7,)) is True and seen == [(7, None)]
+    with pytest.raises(_lib.EsnError, match="configuration not supported"):
+        ops._call(lambda st: -3, "esn_fake", ())
+    with pytest.raises(_lib.EsnError):
+        ops._call(lambda st: -4, "esn_fake", (), allow_unsupported=True)      # only UNSUPPORTED is negotiable
+    with pytest.warns(UserWarning, match="declined"):
+        assert ops._call(lambda st: -3, "esn_fake", (), tag="shape-a", allow_unsupported=True) is False
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert ops._call(lambda st: -3, "esn_fake", (), tag="shape-a", allow_unsupported=True) is False     # warned once already
