@@ -84,12 +84,6 @@ class EsnHead(C.Structure):
                 ("align_corners", C.c_int32)]
 
 
-class EsnSoftCE(C.Structure):
-    _fields_ = [("logits", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sum", C.c_void_p),
-                ("dlogits", EsnTensor), ("gout", C.c_void_p), ("epsilon", C.c_float), ("grad_scale", C.c_float),
-                ("ignore_label", C.c_int32), ("_pad", C.c_int32)]
-
-
 class EsnCE(C.Structure):
     _fields_ = [("logits", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
                 ("dlogits", EsnTensor), ("ignore_label", C.c_int32), ("_pad", C.c_int32),
@@ -123,7 +117,6 @@ SYMBOLS = {
     "esn_avgpool3x3s2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
     "esn_dropout": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_uint64, C.c_float, C.c_int32, C.c_void_p]),
     "esn_confusion_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
-    "esn_soft_ce": (C.c_int, [C.POINTER(EsnSoftCE), C.c_void_p]),
     "esn_gate_bcast": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_image_u8hwc_to_f32nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                              C.c_int32, C.c_void_p]),

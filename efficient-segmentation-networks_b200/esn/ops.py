@@ -702,34 +702,6 @@ def gate_bcast(g, x, b=None, out=None):
     return out
 
 
-def soft_ce(logits, target, weight=None, epsilon=0.1, ignore_label=255, total=None, want_grad=False, grad_scale=1.0,
-            gout=None):
-    """Label-smoothing CE (loss.py:56-86) on NCHW fp32 logits: returns (total[1] += sum of per-pixel losses, dlogits or
-    None); dlogits = d(per-pixel loss) * grad_scale * (*gout)."""
-    require_cuda(logits, "soft_ce")
-    logits = logits.contiguous()
-    target = target.contiguous()
-    if logits.dtype != torch.float32 or target.dtype != torch.int64:
-        raise TypeError("soft_ce: fp32 logits and int64 targets expected")
-    if total is None:
-        total = torch.zeros(1, dtype=torch.float32, device=logits.device)
-    p = L.EsnSoftCE()
-    p.logits = tdesc(logits)
-    p.logits.layout, p.logits.c_stride = L.ESN_NCHW, 0
-    p.target = target.data_ptr()
-    p.weight = weight.data_ptr() if weight is not None else None
-    p.sum = total.data_ptr()
-    p.gout = gout.data_ptr() if gout is not None else None
-    p.epsilon, p.grad_scale, p.ignore_label = float(epsilon), float(grad_scale), int(ignore_label)
-    g = None
-    if want_grad:
-        g = torch.empty_like(logits)
-        p.dlogits = tdesc(g)
-        p.dlogits.layout, p.dlogits.c_stride = L.ESN_NCHW, 0
-    _call(L.lib.esn_soft_ce, "esn_soft_ce", (C.byref(p),), logits.numel() * 4 * (2 if want_grad else 1))
-    return total, g
-
-
 def image_u8_to_f32(img, mean, reverse_channels=True, out=None):
     """Device half of the reference's dataset classes (dataset/cityscapes.py:74-78,164-170,208-214): uint8 HWC batch
     (N,H,W,3) in cv2's BGR order -> fp32 NCHW (N,3,H,W) = (img - mean)[..., ::-1] transposed; `mean` holds three values in

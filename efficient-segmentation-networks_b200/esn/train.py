@@ -645,36 +645,3 @@ class _CEFn(torch.autograd.Function):
 
 def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=True):
     return _CEFn.apply(logits, target, weight, ignore_label, distributed)
-
-
-class _SoftCEFn(torch.autograd.Function):
-    """CrossEntropyLoss2dLabelSmooth (utils/losses/loss.py:56-86): mean over ALL pixels of the GLOBAL batch of the
-    smoothed, class-weighted CE (nn.CrossEntropyLoss with probability targets averages over batch x spatial size)."""
-
-    @staticmethod
-    def forward(ctx, logits, target, weight, epsilon, ignore_label, distributed=True):
-        lg = logits.detach().float().contiguous()
-        total, _ = ops.soft_ce(lg, target, weight, epsilon, ignore_label)
-        world = 1
-        if (distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
-                and torch.distributed.get_world_size() > 1):
-            torch.distributed.all_reduce(total)
-            world = torch.distributed.get_world_size()
-        ctx.save_for_backward(lg, target)
-        ctx.weight, ctx.eps, ctx.ignore = weight, epsilon, ignore_label
-        ctx.inv = 1.0 / (world * lg.shape[0] * lg.shape[2] * lg.shape[3])
-        ctx.in_dtype = logits.dtype
-        return total[0] * ctx.inv
-
-    @staticmethod
-    def backward(ctx, gout):
-        lg, target = ctx.saved_tensors
-        gout = gout.detach().float().reshape(1).contiguous()
-        scratch = torch.zeros(1, dtype=torch.float32, device=lg.device)
-        _, g = ops.soft_ce(lg, target, ctx.weight, ctx.eps, ctx.ignore, total=scratch, want_grad=True, grad_scale=ctx.inv,
-                           gout=gout)
-        return g.to(ctx.in_dtype), None, None, None, None, None
-
-
-def soft_cross_entropy(logits, target, weight=None, epsilon=0.1, ignore_label=255, distributed=True):
-    return _SoftCEFn.apply(logits, target, weight, epsilon, ignore_label, distributed)

@@ -8,7 +8,7 @@ import torch.nn as nn
 from esn import ops
 from esn import train as T
 
-__all__ = ["CrossEntropyLoss2d", "CrossEntropyLoss2dLabelSmooth", "FocalLoss2d"]
+__all__ = ["CrossEntropyLoss2d", "FocalLoss2d"]
 
 
 class CrossEntropyLoss2d(nn.Module):
@@ -52,32 +52,3 @@ class FocalLoss2d(nn.Module):
             target = target[:, 0]
         ce = self.ce_fn(output, target)
         return self.alpha * (1.0 - torch.exp(-ce)) ** self.gamma * ce
-
-
-class CrossEntropyLoss2dLabelSmooth(nn.Module):
-    """Drop-in for the reference's CrossEntropyLoss2dLabelSmooth (utils/losses/loss.py:56-86; `--use_label_smoothing`):
-    targets (1 - epsilon) * onehot + epsilon / C, class weights, mean over all pixels -- one fused kernel each for the
-    forward sum and the gradient (esn_soft_ce).  The reference builds the one-hot with scatter_ and fails on ignore
-    labels; here pixels labelled `ignore_label` contribute nothing (and still count in the mean's denominator, as every
-    pixel does for probability targets)."""
-
-    def __init__(self, weight=None, ignore_label=255, epsilon=0.1, reduction='mean', distributed=True):
-        super().__init__()
-        if reduction != 'mean':
-            raise NotImplementedError("only reduction='mean' (the reference's default) is on the hot path")
-        self.epsilon = epsilon
-        self.ignore_label = ignore_label
-        self.distributed = distributed
-        # the reference keeps its weight inside self.nll_loss (an nn.CrossEntropyLoss): same state_dict key
-        self.nll_loss = nn.Module()
-        if weight is not None:
-            self.nll_loss.register_buffer("weight", torch.as_tensor(weight, dtype=torch.float32))
-        else:
-            self.nll_loss.weight = None
-
-    def forward(self, output, target):
-        ops.require_cuda(output, "CrossEntropyLoss2dLabelSmooth")
-        w = self.nll_loss.weight
-        if w is not None and w.device != output.device:
-            w = w.to(output.device)
-        return T.soft_cross_entropy(output, target.long(), w, self.epsilon, self.ignore_label, self.distributed)

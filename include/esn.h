@@ -365,27 +365,6 @@ int esn_image_u8hwc_to_f32nchw(const uint8_t* img, float* out, int32_t n, int32_
  * b (N,C,1,1) or NULL; all NHWC, one common dtype (f32 or bf16). */
 int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnTensor* b, const EsnTensor* y, void* stream);
 
-/* Label-smoothing cross-entropy: CrossEntropyLoss2dLabelSmooth (utils/losses/loss.py:56-86): soft targets
- * t_c = (1 - epsilon) * [c == y] + epsilon / C, per-pixel loss -sum_c w_c t_c log softmax(x)_c.
- *   *sum += sum over pixels of the per-pixel loss (the caller divides by the pixel count: reduction='mean' with
- *           probability targets averages over ALL pixels);
- *   dlogits (optional, NCHW f32) = d(per-pixel loss)/d logits * grad_scale * (*gout)   (gout: device scalar or NULL = 1).
- * The reference builds its one-hot with scatter_ and therefore cannot take ignore labels; here pixels whose label is
- * ignore_label (or outside [0, C)) contribute nothing and get a zero gradient.  logits: NCHW f32. */
-typedef struct EsnSoftCE {
-  EsnTensor logits;
-  const int64_t* target;   /* (N,H,W) */
-  const float* weight;     /* [C] or NULL */
-  float* sum;              /* [1], accumulated */
-  EsnTensor dlogits;       /* ptr may be NULL */
-  const float* gout;
-  float epsilon;
-  float grad_scale;
-  int32_t ignore_label;
-  int32_t _pad;
-} EsnSoftCE;
-int esn_soft_ce(const EsnSoftCE* p, void* stream);
-
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);
 const char* esn_strerror(int code);

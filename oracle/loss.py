@@ -51,21 +51,3 @@ def focal(logits, target, weight=None, ignore_label=255, alpha=0.5, gamma=2):
     loss = alpha * (1 - pt) ** gamma * ce
     dloss_dce = alpha * ((1 - pt) ** gamma + ce * gamma * (1 - pt) ** (gamma - 1) * pt)
     return loss, dloss_dce * weighted_ce_grad(logits, target, weight, ignore_label)
-
-
-def label_smooth_ce(logits, target, weight=None, epsilon=0.1):
-    """CrossEntropyLoss2dLabelSmooth (utils/losses/loss.py:56-86): soft targets (1 - eps) * onehot + eps / C into
-    nn.CrossEntropyLoss(weight, reduction='mean'), which for probability targets is the mean over ALL N*H*W pixels of
-    -sum_c w_c t_c log softmax(x)_c.  No ignore labels (the reference's scatter_ cannot take them).
-    Returns (loss, dloss/dlogits)."""
-    n, c, h, w = logits.shape
-    x = logits.permute(0, 2, 3, 1).reshape(-1, c)
-    y = target.reshape(-1)
-    t = torch.full_like(x, epsilon / c)
-    t[torch.arange(x.shape[0]), y] += 1.0 - epsilon
-    wv = torch.ones(c, dtype=x.dtype) if weight is None else weight.to(x.dtype)
-    a = t * wv.view(1, -1)
-    logp = torch.log_softmax(x, dim=1)
-    loss = -(a * logp).sum() / x.shape[0]
-    g = (a.sum(dim=1, keepdim=True) * logp.exp() - a) / x.shape[0]
-    return loss, g.view(n, h, w, c).permute(0, 3, 1, 2).contiguous()
