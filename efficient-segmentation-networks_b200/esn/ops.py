@@ -715,6 +715,8 @@ def image_u8_to_f32(img, mean, reverse_channels=True, out=None):
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
     elif out.shape != (n, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != img.device:
         raise ValueError("image_u8_to_f32: out must be a contiguous fp32 (N,3,H,W) tensor on the input's device")
+    if img.numel() == 0:          # empty batch: nothing to launch (an empty tensor has no device pointer to pass)
+        return out
     m = (C.c_float * 3)(*[float(v) for v in mean])
     _call(L.lib.esn_image_u8hwc_to_f32nchw, "esn_image_u8hwc_to_f32nchw",
           (C.c_void_p(img.data_ptr()), C.c_void_p(out.data_ptr()), n, h, w, m, int(bool(reverse_channels))),
