@@ -14,7 +14,9 @@ extern "C" int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnT
   if (g->c != 1 || g->n != x->n || g->h != x->h || g->w != x->w) return ESN_ERR_BAD_SHAPE;
   if (y->n != x->n || y->h != x->h || y->w != x->w || y->c != x->c) return ESN_ERR_BAD_SHAPE;
   if (has_b && (b->n != x->n || b->c != x->c || b->h != 1 || b->w != 1)) return ESN_ERR_BAD_SHAPE;
-  if (g->dtype != x->dtype || y->dtype != x->dtype || (has_b && b->dtype != x->dtype)) return ESN_ERR_UNSUPPORTED;
+  // the gate may be fp32 next to bf16 scores (fp32 pyramid, bf16 class scores); everything else shares x's type
+  if (y->dtype != x->dtype || (has_b && b->dtype != x->dtype)) return ESN_ERR_UNSUPPORTED;
+  if (g->dtype != x->dtype && !(g->dtype == ESN_F32 && x->dtype == ESN_BF16)) return ESN_ERR_UNSUPPORTED;
   const long long npix = (long long)x->n * x->h * x->w;
   const long long total = npix * x->c;
   long long grid = (total + 255) / 256;
@@ -25,6 +27,10 @@ extern "C" int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnT
     gate_bcast_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)g->ptr, g->c_stride, (const float*)x->ptr, x->c_stride,
                                                             has_b ? (const float*)b->ptr : nullptr, has_b ? b->c_stride : 0,
                                                             (float*)y->ptr, y->c_stride, npix, hw, x->c);
+  else if (g->dtype == ESN_F32)
+    gate_bcast_kernel<__nv_bfloat16, float><<<(unsigned)grid, 256, 0, st>>>(
+        (const float*)g->ptr, g->c_stride, (const __nv_bfloat16*)x->ptr, x->c_stride,
+        has_b ? (const __nv_bfloat16*)b->ptr : nullptr, has_b ? b->c_stride : 0, (__nv_bfloat16*)y->ptr, y->c_stride, npix, hw, x->c);
   else
     gate_bcast_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(
         (const __nv_bfloat16*)g->ptr, g->c_stride, (const __nv_bfloat16*)x->ptr, x->c_stride,

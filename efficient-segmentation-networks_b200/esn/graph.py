@@ -17,6 +17,7 @@ masks (esn.train.dropout).
 import torch
 
 from . import ops
+from .prep import bump_weights_generation
 
 
 class GraphedTrainStep:
@@ -61,4 +62,7 @@ class GraphedTrainStep:
         if labels is not None and labels is not self.labels:
             self.labels.copy_(labels, non_blocking=True)
         self.graph.replay()
+        # the replay changed weights and BN buffers behind autograd's back (no `_version` bump): invalidate every packed-
+        # weight / folded-BN cache so that a following model.eval() or eager iteration rebuilds from the new values
+        bump_weights_generation()
         return self.loss

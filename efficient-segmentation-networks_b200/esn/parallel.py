@@ -108,6 +108,15 @@ class GradBuckets:
         self.reset()
 
 
+_ACTIVE = False
+
+
+def is_active():
+    """True once data_parallel() attached SUM-reduced gradient buckets over more than one rank in this process;
+    CrossEntropyLoss2d(distributed=None) then normalises by the global sum of class weights."""
+    return _ACTIVE
+
+
 def data_parallel(model, bucket_bytes=1 << 20, process_group=None):
     """Attach gradient buckets to a model built by build_model(); its train-mode forward/backward then
     all-reduces gradients across the process group.  Parameters are broadcast once from rank 0."""
@@ -115,4 +124,6 @@ def data_parallel(model, bucket_bytes=1 << 20, process_group=None):
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=0, group=process_group)
     model.__dict__["_esn_buckets"] = GradBuckets(model, bucket_bytes, process_group)
+    global _ACTIVE
+    _ACTIVE = _ACTIVE or model.__dict__["_esn_buckets"].world > 1
     return model

@@ -8,9 +8,24 @@ utils/utils.py:16-19 of the reference).
 """
 import torch
 
+# Parameters can also change WITHOUT any ATen op being dispatched: a replay of a captured training iteration
+# (esn/graph.py) updates weights, BN running statistics and num_batches_tracked on the device while every tensor's
+# `_version` stays where it was at capture time.  Every cache keyed on `_version` therefore also carries this
+# process-wide generation number, which GraphedTrainStep bumps on each replay.
+_GENERATION = 0
+
+
+def weights_generation():
+    return _GENERATION
+
+
+def bump_weights_generation():
+    global _GENERATION
+    _GENERATION += 1
+
 
 def _signature(module):
-    sig = []
+    sig = [_GENERATION]
     for t in list(module.parameters()) + list(module.buffers()):
         sig.append((t.data_ptr(), t._version, t.dtype))
     for m in module.modules():

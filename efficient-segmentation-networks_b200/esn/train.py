@@ -16,6 +16,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from .prep import weights_generation
 
 
 class V:
@@ -103,7 +104,7 @@ class ConvT:
     def preps(self):
         c = self.conv
         w = c.weight
-        key = (w.data_ptr(), w._version, None if c.bias is None else c.bias._version)
+        key = (weights_generation(), w.data_ptr(), w._version, None if c.bias is None else c.bias._version)
         if self._key != key:
             wd = w.detach().float()
             bias = None if c.bias is None else c.bias.detach().float()
@@ -219,7 +220,7 @@ class ConvTransposeT:
     def preps(self):
         c = self.conv
         w = c.weight
-        key = (w.data_ptr(), w._version, None if c.bias is None else c.bias._version)
+        key = (weights_generation(), w.data_ptr(), w._version, None if c.bias is None else c.bias._version)
         if self._key != key:
             self.fwd_prep = ops.ConvPrep(c)
             # (Cin, Cout, kh, kw) read as a conv weight (out = Cin, in = Cout): conv2d(dy, W, stride, padding) = dx
@@ -620,28 +621,27 @@ class _CEFn(torch.autograd.Function):
     loss and its gradient equal the reference's gathered-batch value."""
 
     @staticmethod
-    def forward(ctx, logits, target, weight, ignore_label, distributed=True):
+    def forward(ctx, logits, target, weight, ignore_label, distributed=False, reduction="mean"):
         lg = logits.detach().contiguous()
         sums, _ = ops.weighted_ce(lg, target, weight, ignore_label, want_grad=False)
         if (distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
                 and torch.distributed.get_world_size() > 1):
             torch.distributed.all_reduce(sums)
-            ctx.world = torch.distributed.get_world_size()
-        else:
-            ctx.world = 1
         ctx.save_for_backward(lg, target, sums)
-        ctx.weight, ctx.ignore = weight, ignore_label
-        return sums[0] / sums[1]
+        ctx.weight, ctx.ignore, ctx.reduction = weight, ignore_label, reduction
+        return sums[0] / sums[1] if reduction == "mean" else sums[0].clone()
 
     @staticmethod
     def backward(ctx, gout):
         lg, target, sums = ctx.saved_tensors
         gout = gout.detach().float().reshape(1).contiguous()
         scratch = torch.zeros(2, dtype=torch.float32, device=lg.device)
-        _, g = ops.weighted_ce(lg, target, ctx.weight, ctx.ignore, want_grad=True, sums=scratch, gnorm=sums[1:2],
-                               gout=gout)
-        return g, None, None, None, None
+        gnorm = sums[1:2] if ctx.reduction == "mean" else torch.ones(1, dtype=torch.float32, device=lg.device)
+        _, g = ops.weighted_ce(lg, target, ctx.weight, ctx.ignore, want_grad=True, sums=scratch, gnorm=gnorm, gout=gout)
+        return g, None, None, None, None, None
 
 
-def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=True):
-    return _CEFn.apply(logits, target, weight, ignore_label, distributed)
+def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=False, reduction="mean"):
+    """distributed=True all-reduces (sum w*nll, sum w) over the default process group: only correct together with
+    SUM-reduced gradients (esn.parallel); see utils/losses/loss.py."""
+    return _CEFn.apply(logits, target, weight, ignore_label, distributed, reduction)

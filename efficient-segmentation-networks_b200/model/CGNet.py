@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from esn import ops
 from esn._lib import ACT_NONE, ACT_PRELU
-from esn.prep import PrepMixin
+from esn.prep import PrepMixin, weights_generation
 
 __all__ = ["CGNet"]
 
@@ -175,7 +175,7 @@ class FGlo(PrepMixin, nn.Module):
 def _joint(block, y, bn, act, device):
     """[F_loc(y), F_sur(y)] -> BN -> PReLU, each depthwise conv writing its half with its BN/PReLU slice."""
     n, c, h, w = y.shape
-    key = (str(device), tuple((t.data_ptr(), t._version) for t in list(bn.parameters()) + list(bn.buffers()) + [act.weight]),
+    key = (str(device), weights_generation(), tuple((t.data_ptr(), t._version) for t in list(bn.parameters()) + list(bn.buffers()) + [act.weight]),
            block.F_loc.conv.weight._version, block.F_sur.conv.weight._version, bn.eps)
     cached = block.__dict__.get("_esn_joint")
     if cached is None or cached[0] != key:

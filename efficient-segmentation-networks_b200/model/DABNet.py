@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from esn import ops
 from esn._lib import ACT_NONE, ACT_PRELU
-from esn.prep import PrepMixin
+from esn.prep import PrepMixin, weights_generation
 
 __all__ = ["DABNet"]
 
@@ -286,7 +286,7 @@ class DABNet(nn.Module):
 
     def _cls_prep(self, device):
         m = self.classifier[0]
-        key = (str(device), m.conv.weight.data_ptr(), m.conv.weight._version)
+        key = (str(device), weights_generation(), m.conv.weight.data_ptr(), m.conv.weight._version)
         cached = self.__dict__.get("_esn_cls")
         if cached is None or cached[0] != key:
             cached = (key, ops.ConvPrep(m.conv, device=device, cin_pad=320, cout_pad=32))

@@ -25,7 +25,7 @@ import torch.nn as nn
 
 from esn import ops
 from esn._lib import ACT_NONE, ACT_RELU
-from esn.prep import PrepMixin
+from esn.prep import PrepMixin, weights_generation
 
 __all__ = ["EDANet"]
 
@@ -262,7 +262,7 @@ class EDANet(nn.Module):
 
     def _project_prep(self, device):
         conv = self.project_layer
-        sig = (str(device), conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)
+        sig = (str(device), weights_generation(), conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)
         cached = self.__dict__.get("_esn_project")
         if cached is None or cached[0] != sig:
             with torch.no_grad():

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from esn import ops
 from esn._lib import ACT_NONE, ACT_RELU
-from esn.prep import PrepMixin
+from esn.prep import PrepMixin, weights_generation
 from model.ERFNet import DownsamplerBlock as _ErfDownsamplerBlock
 from model.ERFNet import UpsamplerBlock as _ErfUpsamplerBlock
 from model.ERFNet import non_bottleneck_1d as _ErfFactorized
@@ -141,7 +141,7 @@ class ESNet(nn.Module):
         """[dy][dx][Cin][32] fp32 taps of the 2x2 / stride-2 transposed conv (same packing as ERFNet's head); cached on
         the identity and version of output_conv's two tensors only (not the whole net's parameter list)."""
         wt, bs = self.output_conv.weight, self.output_conv.bias
-        sig = (str(device), wt.data_ptr(), wt._version, bs.data_ptr(), bs._version)
+        sig = (str(device), weights_generation(), wt.data_ptr(), wt._version, bs.data_ptr(), bs._version)
         cached = self.__dict__.get("_esn_head")
         if cached is None or cached[0] != sig:
             w = wt.detach().to(device=device, dtype=torch.float32)      # (Cin, classes, 2, 2)

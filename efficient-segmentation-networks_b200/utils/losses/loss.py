@@ -2,6 +2,8 @@
 (nn.CrossEntropyLoss(weight, ignore_index, reduction='mean') on (N,C,H,W) logits / (N,H,W) int64
 targets), computed by the fused esn_weighted_ce kernel (forward sums and backward gradient).
 Under torch.distributed the weighted mean is taken over the GLOBAL batch."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -11,24 +13,53 @@ from esn import train as T
 __all__ = ["CrossEntropyLoss2d", "FocalLoss2d"]
 
 
+def _fused_ce(output, target, w, ignore_label, distributed, reduction):
+    ops.require_cuda(output, "CrossEntropyLoss2d")
+    if w is not None and w.device != output.device:
+        w = w.to(output.device)
+    target = target.long()
+    if os.environ.get("ESN_CHECK_LABELS") == "1":
+        bad = (target != ignore_label) & ((target < 0) | (target >= output.shape[1]))
+        if bool(bad.any()):
+            raise IndexError("Target %d is out of bounds." % int(target[bad][0]))
+    if distributed is None:
+        from esn import parallel
+        distributed = parallel.is_active()
+    return T.cross_entropy(output, target, w, ignore_label, distributed, reduction)
+
+
 class CrossEntropyLoss2d(nn.Module):
-    def __init__(self, weight=None, ignore_label=255, reduction='mean', distributed=True):
+    """Same constructor as the reference (weight, ignore_label, reduction) and the same `state_dict` key
+    (`nll_loss.weight`: the reference keeps an nn.CrossEntropyLoss child named nll_loss, loss.py:23; here that child only
+    holds the class weights, the arithmetic is the fused kernel).
+
+    distributed: None (default) = all-reduce the two loss sums over the default process group ONLY when the model was wrapped
+    by esn.parallel.data_parallel in this process, whose gradient buckets are SUM-reduced -- each rank's loss is then already
+    divided by the GLOBAL sum of class weights, so summed gradients equal the reference's gathered-batch gradient.
+    Under stock DistributedDataParallel (mean-reduced gradients) or any other process-group use the loss stays local, as
+    nn.CrossEntropyLoss is.  True / False force it.
+
+    reduction: 'mean' (reference default) or 'sum'; 'none' (a per-pixel loss map) is not on the hot path and raises.
+    Labels outside [0, classes) other than ignore_label are an error in torch; the kernel treats them as ignored -- set
+    ESN_CHECK_LABELS=1 to validate them (one host sync per call) while debugging a dataset."""
+
+    def __init__(self, weight=None, ignore_label=255, reduction='mean', distributed=None):
         super().__init__()
-        self.distributed = distributed   # all-reduce the two loss sums over the default process group
-        if reduction != 'mean':
-            raise NotImplementedError("only reduction='mean' (the reference's default) is on the hot path")
+        self.distributed = distributed
+        if reduction not in ('mean', 'sum'):
+            raise NotImplementedError("reduction=%r is not on the hot path (only 'mean', the reference's default, and 'sum')"
+                                      % (reduction,))
+        self.reduction = reduction
         self.ignore_label = ignore_label
-        if weight is not None:
-            self.register_buffer("weight", torch.as_tensor(weight, dtype=torch.float32))
-        else:
-            self.weight = None
+        self.nll_loss = nn.CrossEntropyLoss(weight=None if weight is None else torch.as_tensor(weight, dtype=torch.float32),
+                                            ignore_index=ignore_label, reduction=reduction)
+
+    @property
+    def weight(self):
+        return self.nll_loss.weight
 
     def forward(self, output, target):
-        ops.require_cuda(output, "CrossEntropyLoss2d")
-        w = self.weight
-        if w is not None and w.device != output.device:
-            w = w.to(output.device)
-        return T.cross_entropy(output, target.long(), w, self.ignore_label, self.distributed)
+        return _fused_ce(output, target, self.weight, self.ignore_label, self.distributed, self.reduction)
 
 
 class FocalLoss2d(nn.Module):
@@ -45,10 +76,12 @@ class FocalLoss2d(nn.Module):
         self.weight = weight
         self.ignore_index = ignore_index
         self.size_average = size_average
-        self.ce_fn = CrossEntropyLoss2d(weight=weight, ignore_label=ignore_index)
+        # the reference's child and state_dict key (`ce_fn.weight`, loss.py:104); here it only holds the class weights
+        self.ce_fn = nn.CrossEntropyLoss(weight=None if weight is None else torch.as_tensor(weight, dtype=torch.float32),
+                                         ignore_index=ignore_index)
 
     def forward(self, output, target):
         if target.dim() == 4:          # (N,1,H,W) labels, as the reference accepts
             target = target[:, 0]
-        ce = self.ce_fn(output, target)
+        ce = _fused_ce(output, target, self.ce_fn.weight, self.ignore_index, None, "mean")
         return self.alpha * (1.0 - torch.exp(-ce)) ** self.gamma * ce

@@ -362,7 +362,8 @@ int esn_image_u8hwc_to_f32nchw(const uint8_t* img, float* out, int32_t n, int32_
 /* Per-pixel gate with a per-image bias: y[n,h,w,c] = g[n,h,w] * x[n,h,w,c] + b[n,c] -- the close of LEDNet's attention
  * pyramid (APNModule.forward, model/LEDNet.py:279-281: torch.mul(x, mid) + the global-pooling branch, whose bilinear
  * upsampling from 1x1 with align_corners=True is a constant per image and class).  g (N,1,H,W), x and y (N,C,H,W),
- * b (N,C,1,1) or NULL; all NHWC, one common dtype (f32 or bf16). */
+ * b (N,C,1,1) or NULL; all NHWC; x, b and y share one dtype (f32 or bf16), g has the same dtype or is f32 next to bf16
+ * scores (LEDNet keeps its single-channel pyramid in fp32). */
 int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnTensor* b, const EsnTensor* y, void* stream);
 
 /* Library / device queries (host-side, no stream). */

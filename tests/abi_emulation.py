@@ -256,7 +256,8 @@ def esn_dab_dw_pair(ref):
 
 def esn_gate_bcast(gr, xr, br, yr):
     g, x, y = tensor(gr._obj).float(), tensor(xr._obj).float(), tensor(yr._obj)
-    assert gr._obj.dtype == xr._obj.dtype == yr._obj.dtype and g.shape[1] == 1
+    assert xr._obj.dtype == yr._obj.dtype and g.shape[1] == 1
+    assert gr._obj.dtype == xr._obj.dtype or (gr._obj.dtype, xr._obj.dtype) == (L.ESN_F32, L.ESN_BF16)     # fp32 gate on bf16 scores
     v = g * x
     if br._obj.ptr:
         assert br._obj.dtype == xr._obj.dtype and (br._obj.h, br._obj.w) == (1, 1)

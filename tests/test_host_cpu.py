@@ -111,3 +111,22 @@ def test_call_wrapper_contract(monkeypatch):
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         assert ops._call(lambda st: -3, "esn_fake", (), tag="shape-a", allow_unsupported=True) is False     # warned once already
+
+
+def test_cross_entropy_module_is_a_drop_in():
+    """Same state_dict key as the reference's CrossEntropyLoss2d (its nn.CrossEntropyLoss child is named nll_loss,
+    utils/losses/loss.py:23); the global-batch normalisation is opt-in / tied to esn.parallel, never implied by an
+    initialised process group alone."""
+    from utils.losses.loss import CrossEntropyLoss2d, FocalLoss2d
+    from esn import parallel
+    w = torch.arange(1, 20, dtype=torch.float32)
+    crit = CrossEntropyLoss2d(weight=w, ignore_label=255)
+    assert list(crit.state_dict().keys()) == ["nll_loss.weight"]
+    assert torch.equal(crit.weight, w) and crit.distributed is None and not parallel.is_active()
+    assert list(CrossEntropyLoss2d().state_dict().keys()) == []
+    assert CrossEntropyLoss2d(reduction="sum").reduction == "sum"
+    with pytest.raises(NotImplementedError):
+        CrossEntropyLoss2d(reduction="none")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        crit(torch.zeros(1, 19, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
+    assert list(FocalLoss2d(weight=w).state_dict().keys()) == ["ce_fn.weight"]       # loss.py:104

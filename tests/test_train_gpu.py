@@ -434,3 +434,47 @@ def test_graphed_train_step_equals_eager(spec, net):
         ls = [gs2().item() for _ in range(3)]
         assert all(v == v for v in ls)
         assert int(__import__("esn").ops.step_counter().item()) == step0 + 4
+
+
+@pytest.mark.parametrize("net", ["DABNet", "ERFNet"])
+def test_eval_after_graph_replays_sees_the_new_weights(spec, net):
+    """Replays update weights and BN buffers without touching any tensor `_version`; the packed-weight / folded-BN caches
+    must not survive them (esn.prep.weights_generation).  Sequence of the reference trainer (train.py validates every
+    epoch): graph-train, eval, graph-train, eval -- each eval must equal a FRESH model loaded from the state_dict."""
+    from builders.model_builder import build_model
+    from utils.losses.loss import CrossEntropyLoss2d
+    from esn.graph import GraphedTrainStep
+    x = fixture.make_input(2, 64, 128).cuda()
+    lab = fixture.make_labels(2, 64, 128, 19).cuda()
+    crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
+    m = build_model(net, 19)
+    m.load_state_dict(spec_state_dict(spec, net))
+    m = m.cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-3, fused=True, capturable=True)
+    gs = GraphedTrainStep(m, crit, opt, x, lab, autocast_dtype=None, warmup=1)
+
+    def eval_pair():
+        m.eval()
+        with torch.no_grad():
+            y = m(x)
+        fresh = build_model(net, 19)
+        fresh.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+        fresh = fresh.cuda().eval()
+        with torch.no_grad():
+            y_fresh = fresh(x)
+        m.train()
+        return y, y_fresh
+
+    gs()
+    y1, f1 = eval_pair()
+    assert torch.equal(y1, f1)
+    for _ in range(3):
+        gs()
+    y2, f2 = eval_pair()
+    assert torch.equal(y2, f2), _rel(y2, f2)
+    assert _rel(y2, y1) > 1e-4          # the weights did move
+    # an eager iteration after replays must also start from the replayed weights (train-mode packed-weight caches)
+    opt.zero_grad(set_to_none=True)
+    l_eager = crit(m(x), lab)
+    l_graph = gs()
+    assert l_eager.item() > l_graph.item() - 0.5 and l_eager.item() == l_eager.item()
