@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- images/s of the segmentation hot path on B200 (driver contract in the task brief).
 
-Default workload = BASELINE.json configs[1]: ERFNet (19 classes), bf16, inference, batch 16 per GPU,
-3x1024x2048 synthetic Cityscapes-shaped input, fused argmax head (uint8 mask out).
-A "step" is one forward of one batch.  N>1 shards images across ranks with no data-path
-collective (inference; "weak" scaling: 16 images per GPU).
+Default workload = BASELINE.json configs[2]: DABNet (19 classes), bf16 training, batch 8 per GPU, 512x1024 (the metric's
+resolution and the only config that names 1/2/4/8 GPUs), weighted cross-entropy, Adam, data parallel: a "step" is one
+training iteration (forward, loss, backward, bucketed NCCL gradient all-reduce, fused Adam) of one batch per GPU, so the
+driver's --gpus N runs exercise the path that communicates ("weak" scaling: 8 images per GPU).  The same JSON line carries,
+under `legs`, BASELINE.json configs[1] -- ERFNet bf16 inference, batch 16 per GPU, 3x1024x2048, fused argmax head (images
+sharded over ranks, no collective) -- measured the same way; any workload can be made the primary with --workload.
 
     python bench.py                                   # N=1
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
@@ -123,7 +125,11 @@ def cpu_reference_leg(model, h, w, steps, warmup, budget_s=25.0, train=False):
     sample of the workload: one image of the workload's resolution per step (inference: forward +
     numpy argmax; training: train-mode forward + weighted CE + backward through torch autograd)."""
     from oracle import fixture, nets, loss as oloss
-    threads = os.cpu_count() or 1
+    try:        # the GPU arm pins the process next to its GPU (numa_local_affinity); the CPU reference gets every core back
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        threads = len(os.sched_getaffinity(0))
+    except Exception:      # noqa: BLE001
+        threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = fixture_state_dict(model)
     x = fixture.make_input(1, h, w)
@@ -239,81 +245,197 @@ def gpu_eager_reference_leg(model, batch, h, w, train, warmup=10, steps=20, vari
                     ("train-mode forward + weighted CE + backward + fused Adam" if train else "forward + device argmax")}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
-    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the gpu_eager_baseline leg (N=1)")
-    ap.add_argument("--workload", default="erfnet_infer_bf16_b16_1024x2048", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-u8-leg", action="store_true", help="skip the extra e2e_u8 leg (inference, N=1)")
-    ap.add_argument("--e2e-input", default="f32", choices=["f32", "u8"],
-                    help="what crosses PCIe in the e2e leg: the reference's pre-processed fp32 NCHW batch (default), or the "
-                         "decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / CHW done on the device "
-                         "(esn_image_u8hwc_to_f32nchw, SURVEY 8f-4)")
-    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
-    args = ap.parse_args()
-    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are
-    # redirected to stderr for the duration of the run; the JSON goes to the saved descriptor.
-    sys.stdout.flush()
-    _real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
+# SURVEY 8(a) block units: class names whose OUTERMOST instances are the units of SURVEY 8(d)'s algorithmic-byte count
+# (tensors entering + leaving the unit, each once).  Launches outside any unit (heads, input-injection pyramid, stand-alone
+# BN/PReLU passes on concat tensors) are their own units.
+UNIT_CLASSES = {
+    "ERFNet": ("DownsamplerBlock", "non_bottleneck_1d", "UpsamplerBlock"),
+    "DABNet": ("DABModule", "DownSamplingBlock"),
+    "ENet": ("InitialBlock", "RegularBottleneck", "DownsamplingBottleneck", "UpsamplingBottleneck"),
+    "CGNet": ("ContextGuidedBlock", "ContextGuidedBlock_Down"),
+    "FastSCNN": ("_ConvBNReLU", "_DSConv", "LinearBottleneck", "PyramidPooling", "FeatureFusionModule", "Classifer"),
+    "ESPNet": ("DownSamplerB", "DilatedParllelResidualBlockB"),
+    "ESPNet_v2": ("EESP", "DownSampler", "PSPModule"),
+    "ESNet": ("DownsamplerBlock", "FCU", "PFCU", "UpsamplerBlock"),
+    "ContextNet": ("Custom_Conv", "DepthSepConv", "LinearBottleneck", "FeatureFusionModule", "Classifer"),
+    "EDANet": ("DownsamplerBlock", "EDAModule"),
+    "LEDNet": ("DownsamplerBlock", "SS_nbt_module_paper", "APNModule"),
+}
 
-    def emit(obj):
-        _real_stdout.write(json.dumps(obj) + "\n")
-        _real_stdout.flush()
-    model_name, batch, H, W, mode = WORKLOADS[args.workload]
+
+def numa_local_affinity(local_rank):
+    """Pin this process to the CPUs next to its GPU BEFORE any pinned host buffer is allocated, so that the pages the H2D
+    copies read are first-touched on the GPU's NUMA node (round 1: every rank allocated on node 0 and the 8-GPU e2e figure
+    was bound by one socket's memory).  Best effort: returns a short description for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = open(base + "/numa_node").read().strip()
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+        return {"numa_node": node, "cpus": 0, "pci": bdf, "note": "no usable CPU in local_cpulist; affinity unchanged"}
+    except Exception as exc:      # noqa: BLE001
+        return {"error": repr(exc)[:120]}
+
+
+def unit_roofline(model, model_name, prof_step, hbm_peak, tc_peak):
+    """per block unit, algorithmic bytes = the tensors entering + leaving the unit (each once), FLOPs = 2 x the
+    MACs of its convs; t_HBM = bytes / measured HBM peak, t_TC = FLOPs / measured bf16 peak; the binding roof is the larger,
+    frac = t_binding / measured time.  Unit boundaries come from forward hooks on the outermost block modules; times are CUDA
+    events around every C-ABI launch inside them (one instrumented eager step)."""
+    from esn import ops
+    names = UNIT_CLASSES.get(model_name, ())
+    state = {"depth": 0, "cur": None}
+    handles = []
+
+    def numel_bytes(t):
+        if torch.is_tensor(t):
+            return t.numel() * t.element_size() if t.is_floating_point() else 0
+        if isinstance(t, (tuple, list)):
+            return sum(numel_bytes(v) for v in t)
+        return 0
+
+    def shape_of(t):
+        while isinstance(t, (tuple, list)):
+            t = t[0]
+        return tuple(t.shape) if torch.is_tensor(t) else ()
+
+    units = []
+
+    def pre(mod, inp):
+        if state["depth"] == 0:
+            state["cur"] = {"kind": type(mod).__name__, "first": len(ops.PROFILE), "in": numel_bytes(inp), "shape": shape_of(inp)}
+        state["depth"] += 1
+
+    def post(mod, inp, out):
+        state["depth"] -= 1
+        if state["depth"] == 0 and state["cur"] is not None:
+            u = state["cur"]
+            u["last"] = len(ops.PROFILE)
+            u["out"] = numel_bytes(out)
+            u["oshape"] = shape_of(out)
+            units.append(u)
+            state["cur"] = None
+    for mod in model.modules():
+        if type(mod).__name__ in names:
+            handles.append(mod.register_forward_pre_hook(pre))
+            handles.append(mod.register_forward_hook(post))
+    try:
+        for _ in range(2):
+            del units[:]
+            ops.PROFILE = []
+            prof_step()
+            torch.cuda.synchronize()
+            prof, ops.PROFILE = ops.PROFILE, None
+    finally:
+        ops.PROFILE = None
+        for hd in handles:
+            hd.remove()
+    owner = [None] * len(prof)
+    for ui, u in enumerate(units):
+        for i in range(u["first"], u["last"]):
+            owner[i] = ui
+    agg = {}
+
+    def add(key, ms, nbytes, flops, launches, count):
+        a = agg.setdefault(key, {"units": 0, "launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+        a["units"] += count
+        a["launches"] += launches
+        a["ms"] += ms
+        a["bytes"] += nbytes
+        a["flops"] += flops
+    for ui, u in enumerate(units):
+        rs = prof[u["first"]:u["last"]]
+        ms = sum(r["ev"][0].elapsed_time(r["ev"][1]) for r in rs)
+        s = u["shape"]
+        key = "%s c%d->%d @%dx%d" % (u["kind"], s[1], u["oshape"][1], s[2], s[3]) if len(s) == 4 else u["kind"]
+        add(key, ms, u["in"] + u["out"], sum(r["flops"] for r in rs), len(rs), 1)
+    for i, r in enumerate(prof):
+        if owner[i] is None:
+            add("(top level) " + r["kernel"], r["ev"][0].elapsed_time(r["ev"][1]), r["bytes"], r["flops"], 1, 1)
+    tot = sum(a["ms"] for a in agg.values())
+    table = {}
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        t_hbm = a["bytes"] / (hbm_peak * 1e9) * 1e3
+        t_tc = a["flops"] / (tc_peak * 1e12) * 1e3
+        bound = "tensor" if t_tc > t_hbm else "hbm"
+        table[k] = {"units": a["units"], "launches": a["launches"], "ms": round(a["ms"], 4), "share": round(a["ms"] / tot, 4),
+                    "alg_bytes": a["bytes"], "flops": a["flops"], "bound": bound,
+                    "GBps": round(a["bytes"] / a["ms"] / 1e6, 1), "TFLOPs": round(a["flops"] / a["ms"] / 1e9, 1),
+                    "hbm_frac": round(t_hbm / a["ms"], 4), "tensor_frac": round(t_tc / a["ms"], 4),
+                    "frac": round(max(t_hbm, t_tc) / a["ms"], 4)}
+    return prof, table, tot
+
+
+def kernel_tables(prof):
+    agg = {}
+    for r in prof:
+        ms = r["ev"][0].elapsed_time(r["ev"][1])
+        a = agg.setdefault(r["kernel"], {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+        a["launches"] += 1
+        a["ms"] += ms
+        a["bytes"] += r["bytes"]
+        a["flops"] += r["flops"]
+    tot_ms = sum(a["ms"] for a in agg.values())
+    kernels = {k: {"launches": a["launches"], "ms": round(a["ms"], 4), "share": round(a["ms"] / tot_ms, 4),
+                   "alg_GBps": round(a["bytes"] / a["ms"] / 1e6, 1), "TFLOPs": round(a["flops"] / a["ms"] / 1e9, 2)}
+               for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    by_tag = {}
+    for r in prof:
+        ms = r["ev"][0].elapsed_time(r["ev"][1])
+        a = by_tag.setdefault(r["kernel"].replace("esn_", "") + " " + r["tag"], [0, 0.0, 0, 0])
+        a[0] += 1
+        a[1] += ms
+        a[2] += r["bytes"]
+        a[3] += r["flops"]
+    layers = {k: {"n": v[0], "ms": round(v[1], 3), "alg_GBps": round(v[2] / v[1] / 1e6, 1), "TFLOPs": round(v[3] / v[1] / 1e9, 1)}
+              for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][1])[:24]}
+    return agg, kernels, layers, tot_ms
+
+
+def ncu_traffic(workload, kernel):
+    """Per-launch DRAM bytes (read + write) of `kernel` from the committed ncu launch list of the same command, or None."""
+    fam_names = {"esn_conv2d_umma": "conv_umma_kernel", "esn_conv_pair_umma": "conv_pair_kernel", "esn_conv2d_direct": "conv_direct_kernel",
+                 "esn_dab_dw_pair": "dab_dw_pair", "esn_affine_act": "pw_", "esn_conv2d_wgrad": "wgrad", "esn_nb1d_umma": "nb1d_kernel",
+                 "esn_dw_conv": "dw_", "esn_dwconv": "dw"}
+    for rnd in ("r02", "r01"):
+        for stem in (workload, workload.split("_")[0] + ("_train" if "_train_" in workload else "")):
+            tpath = os.path.join(ROOT, "profiles", "%s_traffic_%s.json" % (rnd, stem))
+            if not os.path.exists(tpath) or kernel not in fam_names:
+                continue
+            tj = json.load(open(tpath))
+            if tj.get("workload") != workload:
+                continue
+            fams = [v for k, v in tj["families"].items() if fam_names[kernel] in k]
+            n_l = sum(v["launches"] for v in fams)
+            if n_l:
+                return {"dram_bytes_per_launch": int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in fams) / n_l),
+                        "kernel_launches": n_l, "source": tj["source"]}
+    return None
+
+
+def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
+    """One workload -> the JSON line's fields (rank 0) or None (other ranks)."""
+    from builders.model_builder import build_model
+    from esn import ops
+    from oracle import fixture
+    model_name, batch, H, W, mode = WORKLOADS[wl_name]
     train = mode == "train"
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": args.workload, "net": model_name, "classes": 19, "batch_per_gpu": batch,
+    u8_in = (args.e2e_input == "u8") and not train
+    config = {"workload": wl_name, "net": model_name, "classes": 19, "batch_per_gpu": batch,
               "input": "3x%dx%d fp32 NCHW" % (H, W),
               "mode": "training step: forward + weighted CE + backward + Adam" if train else "inference",
               "head": "bilinear -> fp32 logits -> fused weighted-CE kernel" if train else "argmax fused (uint8 mask)",
               "sharding": ("data parallel: flat fp32 gradient buckets all-reduced (NCCL) from inside the backward tape, "
                            "2-scalar loss all-reduce, per-GPU BatchNorm") if train else "images across ranks, no collective",
               "l2": "no flush: per-step working set (input %.0f MB + activations) >> 126 MB L2" % (batch * 3 * H * W * 4 / 1e6)}
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, max(args.warmup, 3), budget_s=90.0, train=train)
-        line = {"impl": "reference", "metric": "images/s", "value": base["value"], "unit": "images/s",
-                "n_gpus": args.gpus, "steps": n, "warmup": max(args.warmup, 3), "ms_per_step": mean * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, mode="inference (CPU, reference arithmetic)", batch_per_gpu=1),
-                "cpu_baseline": base,
-                "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        emit(line)
-        return
-
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    if args.impl == "reference-gpu":
-        # the reference graph eager on this GPU (every variant incl. true fp32); one process, rank 0 only
-        if rank != 0:
-            return
-        g = gpu_eager_reference_leg(model_name, batch, H, W, train, warmup=max(args.warmup, 5), steps=args.steps,
-                                    variants=["fp32", "fp32_tf32", "bf16_autocast", "bf16_autocast_channels_last",
-                                              "bf16_weights_channels_last"])
-        emit({"impl": "reference-gpu", "metric": "images/s", "value": g["value"], "unit": "images/s", "n_gpus": 1,
-              "steps": args.steps, "warmup": max(args.warmup, 5),
-              "ms_per_step": g["variants"][g["fastest"]]["ms_per_step"] if g["fastest"] else None,
-              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": g["fastest"], "data": "synthetic",
-              "config": config, "gpu_eager_baseline": g, "gpu_launches": 0})
-        return
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from builders.model_builder import build_model
-    from esn import ops
-    from oracle import fixture
-
     m = build_model(model_name, 19)
     m.load_state_dict(fixture_state_dict(model_name))
     m = m.cuda()
@@ -346,7 +468,7 @@ def main():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             return m.predict_mask(inp)
 
-    # ---- warm-up (also builds the packed-weight caches), then optional CUDA-graph capture
+    # ---- warm-up (also builds the packed-weight caches), then CUDA-graph capture
     for _ in range(max(args.warmup, 3)):
         mask = step(x)
     torch.cuda.synchronize()
@@ -354,17 +476,13 @@ def main():
     step(x)
     torch.cuda.synchronize()
     launches_per_step = ops.launch_count()
-    graph = None
-    gstep = None
+    graph = gstep = None
     if train and not args.no_graph:
         # the whole iteration (forward, loss, backward, gradient all-reduce, Adam) as one CUDA graph (esn/graph.py)
         from esn.graph import GraphedTrainStep
         gstep = GraphedTrainStep(m, crit, opt, x, y, warmup=1)
         graph = gstep.graph
         mask = gstep.loss
-        for _ in range(2):
-            graph.replay()
-        torch.cuda.synchronize()
     elif not args.no_graph:
         graph = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
@@ -374,6 +492,7 @@ def main():
             with torch.cuda.graph(graph, stream=s):
                 mask = step(x)
         torch.cuda.current_stream().wait_stream(s)
+    if graph is not None:
         torch.cuda.synchronize()
         for _ in range(2):
             graph.replay()
@@ -414,67 +533,75 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = world * batch / (ms_per_step / 1e3)
 
-    # ---- e2e: pinned host images -> H2D -> forward -> D2H uint8 masks, every step, double-buffered
-    u8_in = args.e2e_input == "u8"
+    # ---- e2e through the public API with HOST buffers: every step copies that step's input from pinned host memory and
+    # reads the result back.  Inference (default --e2e-input u8): decoded uint8 HWC BGR images, as cv2.imread hands them to
+    # the reference's dataset class, -> H2D (copy stream) -> esn_image_u8hwc_to_f32nchw (the dataset class's arithmetic
+    # tail, dataset/cityscapes.py:74-78, on the device) -> model.predict_mask (the captured graph) -> uint8 masks -> D2H
+    # (third stream).  --e2e-input f32 ships the reference's pre-processed fp32 NCHW batch instead (4x the bytes).
     mean_bgr = [72.3924, 82.90902, 73.158325]      # dataset/inform/cityscapes_inform.pkl['mean'] (BGR, fp32)
-    u8 = {}
-
-    def u8_buffers():
-        if not u8:
-            g8 = torch.Generator().manual_seed(1234 + rank)
-            u8["host"] = torch.randint(0, 256, (batch, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
-            u8["dev"] = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
-        return u8["host"], u8["dev"]
+    copy_s, d2h_s, main_s = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
     if u8_in:
-        x_host_u8, xin_u8 = u8_buffers()
-    h2d = (x_host_u8.numel() if u8_in else x_host.numel() * 4) + (y_host.numel() * 8 if train else 0)
+        g8 = torch.Generator().manual_seed(1234 + rank)
+        in_host = torch.randint(0, 256, (batch, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
+        in_dev = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    else:
+        in_host = x_host
+        in_dev = [torch.empty_like(x) for _ in range(2)]
+    lab_dev = [torch.empty_like(y), torch.empty_like(y)] if train else [None, None]
+    h2d = in_host.numel() * in_host.element_size() + (y_host.numel() * 8 if train else 0)
     d2h = 4 if train else batch * H * W
-    mask_host = [(torch.empty((), dtype=torch.float32) if train else torch.empty((batch, H, W), dtype=torch.uint8)).pin_memory()
-                 for _ in range(2)]
-    xin = [torch.empty_like(x), torch.empty_like(x)]
-    yin = [torch.empty_like(y), torch.empty_like(y)] if train else [None, None]
-    copy_s = torch.cuda.Stream()
-    d2h_s = torch.cuda.Stream()
-    main_s = torch.cuda.current_stream()
+    out_host = [(torch.empty((), dtype=torch.float32) if train else torch.empty((batch, H, W), dtype=torch.uint8)).pin_memory()
+                for _ in range(2)]
+    out_stage = [torch.empty_like(mask) for _ in range(2)]
+    exact = None
+    if u8_in:       # self-check of the device pre-processing: bit-equal to the same fp32 arithmetic done by torch
+        in_dev[0].copy_(in_host)
+        sub = in_dev[0][:2]
+        got = ops.image_u8_to_f32(sub, mean_bgr, True)
+        want = (sub.float() - torch.tensor(mean_bgr, device="cuda")).flip(3).permute(0, 3, 1, 2)
+        exact = bool(torch.equal(got, want))
+        del got, want
 
-    def e2e_loop(k, from_u8=u8_in):
-        if from_u8:
-            x_host_u8, xin_u8 = u8_buffers()
-        ready = [None, None]
-        done = [None, None]
+    def e2e_loop(k):
+        ready, freed, read = [None, None], [None, None], [None, None]
         for i in range(k + 1):
             b = i & 1
             if i < k:
                 with torch.cuda.stream(copy_s):
-                    if done[b] is not None:
-                        copy_s.wait_event(done[b])      # buffer b free (its compute finished)
-                    if from_u8:
-                        xin_u8[b].copy_(x_host_u8, non_blocking=True)
-                    else:
-                        xin[b].copy_(x_host, non_blocking=True)
+                    if freed[b] is not None:
+                        copy_s.wait_event(freed[b])      # input buffer b was consumed by its step
+                    in_dev[b].copy_(in_host, non_blocking=True)
                     if train:
-                        yin[b].copy_(y_host, non_blocking=True)
+                        lab_dev[b].copy_(y_host, non_blocking=True)
                     ready[b] = torch.cuda.Event()
                     ready[b].record(copy_s)
             if i >= 1:
                 pb = (i - 1) & 1
                 main_s.wait_event(ready[pb])
-                if from_u8:    # device half of the dataset class: uint8 HWC BGR -> fp32 NCHW RGB - mean (one launch)
-                    ops.image_u8_to_f32(xin_u8[pb], mean_bgr, True, out=xin[pb])
-                mk = gstep(xin[pb], yin[pb]) if gstep is not None else step(xin[pb], yin[pb])
-                if from_u8 and gstep is None:
-                    # with 3 bytes per pixel going up, the 1 byte per pixel coming down is no longer hidden behind the H2D
-                    # copy: read the masks back on a third stream so the next step's kernels do not queue behind it
-                    done[pb] = torch.cuda.Event()
-                    done[pb].record(main_s)                 # compute finished: input buffer pb is free, the mask is ready
-                    with torch.cuda.stream(d2h_s):
-                        d2h_s.wait_event(done[pb])
-                        mask_host[pb].copy_(mk, non_blocking=True)
-                    mk.record_stream(d2h_s)                 # the allocator must not hand the mask's memory out before the copy ran
-                    continue
-                mask_host[pb].copy_(mk, non_blocking=True)
-                done[pb] = torch.cuda.Event()
-                done[pb].record(main_s)
+                if gstep is not None:
+                    res = gstep(in_dev[pb], lab_dev[pb])
+                elif graph is not None:
+                    if u8_in:
+                        ops.image_u8_to_f32(in_dev[pb], mean_bgr, True, out=x)      # into the graph's static input
+                    else:
+                        x.copy_(in_dev[pb], non_blocking=True)
+                    graph.replay()
+                    res = mask
+                else:
+                    xi = ops.image_u8_to_f32(in_dev[pb], mean_bgr, True, out=x) if u8_in else in_dev[pb]
+                    res = step(xi, lab_dev[pb])
+                freed[pb] = torch.cuda.Event()
+                freed[pb].record(main_s)
+                if read[pb] is not None:
+                    main_s.wait_event(read[pb])          # the previous D2H out of this staging buffer has finished
+                out_stage[pb].copy_(res, non_blocking=True)     # D2D: the graph's static output is free for the next replay
+                done = torch.cuda.Event()
+                done.record(main_s)
+                with torch.cuda.stream(d2h_s):
+                    d2h_s.wait_event(done)
+                    out_host[pb].copy_(out_stage[pb], non_blocking=True)
+                    read[pb] = torch.cuda.Event()
+                    read[pb].record(d2h_s)
         main_s.wait_stream(copy_s)
         main_s.wait_stream(d2h_s)
 
@@ -486,72 +613,55 @@ def main():
     t0 = time.perf_counter()
     e2e_loop(k_e2e)
     torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    e2e_ms = (t1 - t0) * 1e3 / k_e2e
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
     if dist:
         t = torch.tensor([e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
     e2e_value = world * batch / (e2e_ms / 1e3)
 
-    # ---- per-kernel roofline: one instrumented eager step, CUDA events around every launch
+    # ---- roofline: one instrumented eager step, CUDA events around every launch
     hbm_peak, tc_peak, peak_src = peaks()
-    roofline, kernels = None, None
-    # (every rank runs the step -- a training step contains collectives -- only rank 0 keeps the profile)
-    for _ in range(2):
-        ops.PROFILE = []
-        step(x)
-        torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
+    roofline = model_roof = kernels = layers = units = None
+    if train:
+        # (every rank runs the step -- it contains collectives -- only rank 0 keeps the profile)
+        for _ in range(2):
+            ops.PROFILE = []
+            step(x)
+            torch.cuda.synchronize()
+            prof, ops.PROFILE = ops.PROFILE, None
+    else:
+        prof, units, _ = unit_roofline(m, model_name, lambda: step(x), hbm_peak, tc_peak)
     if rank == 0:
-        agg = {}
-        for r in prof:
-            ms = r["ev"][0].elapsed_time(r["ev"][1])
-            a = agg.setdefault(r["kernel"], {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
-            a["launches"] += 1
-            a["ms"] += ms
-            a["bytes"] += r["bytes"]
-            a["flops"] += r["flops"]
-        tot_ms = sum(a["ms"] for a in agg.values())
-        kernels = {k: {"launches": a["launches"], "ms": round(a["ms"], 4), "share": round(a["ms"] / tot_ms, 4),
-                       "alg_GBps": round(a["bytes"] / a["ms"] / 1e6, 1), "TFLOPs": round(a["flops"] / a["ms"] / 1e9, 2)}
-                   for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-        by_tag = {}
-        for r in prof:
-            ms = r["ev"][0].elapsed_time(r["ev"][1])
-            a = by_tag.setdefault(r["kernel"].replace("esn_", "") + " " + r["tag"], [0, 0.0, 0, 0])
-            a[0] += 1
-            a[1] += ms
-            a[2] += r["bytes"]
-            a[3] += r["flops"]
-        layers = {k: {"n": v[0], "ms": round(v[1], 3), "alg_GBps": round(v[2] / v[1] / 1e6, 1),
-                      "TFLOPs": round(v[3] / v[1] / 1e9, 1)}
-                  for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][1])[:24]}
+        agg, kernels, layers, tot_ms = kernel_tables(prof)
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        achieved = top[1]["bytes"] / (top[1]["ms"] / 1e3) / 1e9
-        # DRAM traffic of the same kernel family from the committed ncu launch list (separate run)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % model_name.lower())
-        fam_names = {"esn_conv2d_umma": "conv_umma_kernel", "esn_conv_pair_umma": "conv_pair_kernel", "esn_conv2d_direct": "conv_direct_kernel",
-                     "esn_dab_dw_pair": "dab_dw_pair_kernel", "esn_affine_act": "pw_kernel"}
-        if os.path.exists(tpath) and top[0] in fam_names:
-            tj = json.load(open(tpath))
-            if tj.get("workload") == args.workload:
-                fams = [v for k, v in tj["families"].items() if k.startswith(fam_names[top[0]])]
-                n_l = sum(v["launches"] for v in fams)
-                if n_l:
-                    traffic = {"dram_bytes_per_launch": int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in fams) / n_l),
-                               "alg_bytes_per_launch": int(top[1]["bytes"] / top[1]["launches"]), "kernel_launches": n_l,
-                               "source": tj["source"]}
-        roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4),
-                    # contract: DRAM bytes (read + write) per launch of this kernel from the ncu capture, or null
-                    "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
-                    "peak_source": peak_src,
-                    "launches_per_step": top[1]["launches"], "share_of_step": round(top[1]["ms"] / tot_ms, 4),
-                    "tensor_TFLOPs": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12, 1),
-                    "tensor_frac_of_bf16_peak": round(top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12 / tc_peak, 4),
-                    "definition": "sum over the step's launches of (|x|+|y|+|residual| bytes) / sum of their CUDA-event durations"}
+        per_launch = {"kernel": top[0], "achieved_GBps": round(top[1]["bytes"] / top[1]["ms"] / 1e6, 1),
+                      "frac_of_hbm_peak": round(top[1]["bytes"] / top[1]["ms"] / 1e6 / hbm_peak, 4),
+                      "TFLOPs": round(top[1]["flops"] / top[1]["ms"] / 1e9, 1),
+                      "frac_of_bf16_peak": round(top[1]["flops"] / top[1]["ms"] / 1e9 / tc_peak, 4),
+                      "launches_per_step": top[1]["launches"], "share_of_step": round(top[1]["ms"] / tot_ms, 4),
+                      "definition": "sum over the kernel's launches of (|x|+|y|+|residual| bytes, conv FLOPs) / sum of their "
+                                    "CUDA-event durations (what each launch itself must move; round-1 definition)"}
+        traffic = ncu_traffic(wl_name, top[0])
+        if units:
+            uk, u = next(iter(units.items()))
+            tensor = u["bound"] == "tensor"
+            roofline = {"unit": "TFLOP/s" if tensor else "GB/s", "bound": u["bound"], "dominant_unit": uk,
+                        "achieved": u["TFLOPs"] if tensor else u["GBps"], "peak": tc_peak if tensor else hbm_peak,
+                        "frac": u["frac"], "hbm_frac": u["hbm_frac"], "tensor_frac": u["tensor_frac"],
+                        "share_of_step": u["share"], "units_per_step": u["units"], "launches_per_unit": round(u["launches"] / u["units"], 2),
+                        "definition": "SURVEY 8(d): algorithmic bytes of a block unit = tensors entering + leaving it, each "
+                                      "once (2*C*h*w elements for a non_bottleneck_1d / DABModule), FLOPs = 2 x its conv MACs; "
+                                      "the binding roof is the larger of bytes/HBM-peak and FLOPs/bf16-peak; frac = that time "
+                                      "/ the CUDA-event time of the unit's launches"}
+        else:
+            achieved = top[1]["bytes"] / (top[1]["ms"] / 1e3) / 1e9
+            roofline = {"unit": "GB/s", "bound": "hbm", "dominant_unit": top[0], "achieved": round(achieved, 1), "peak": hbm_peak,
+                        "frac": round(achieved / hbm_peak, 4), "share_of_step": round(top[1]["ms"] / tot_ms, 4),
+                        "definition": "training step: per-kernel algorithmic bytes (|x|+|dy| for a weight gradient, in+out for "
+                                      "the others) / CUDA-event time, for the kernel with the largest share"}
+        roofline.update({"traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
+                         "peak_source": peak_src, "per_launch": per_launch})
         # whole-network figure against SURVEY 8(d)'s block-fused algorithmic bytes
         px = batch * H * W
         alg_bytes = px * ((ALG_ELEMS_PER_PX[model_name] - 19.0) * 2 + 1 + 3 * 4 - 3 * 2)
@@ -559,89 +669,168 @@ def main():
         if train:   # ~3.5x the forward block-fused traffic (saved activations + gradients), 3x the FLOPs
             alg_bytes = px * 3.5 * ALG_ELEMS_PER_PX[model_name] * 2
             flops *= 3
-        model_roof = {"alg_bytes_per_step": int(alg_bytes), "hbm_frac": round(alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak, 4),
-                      "tensor_frac": round(flops / (ms_per_step / 1e3) / 1e12 / tc_peak, 4),
-                      "note": "block-fused algorithmic bytes (SURVEY 8d) and conv FLOPs of the whole forward / step time"}
-
-    # ---- extra leg (inference, N=1): the same e2e loop fed with decoded uint8 HWC BGR images, normalised on the device by
-    # esn_image_u8hwc_to_f32nchw.  Reported next to `e2e`, never instead of it; guarded so that a failure of
-    # this newer kernel cannot cost the line above.  Self-check: bit-equality with the same fp32 arithmetic done by torch.
-    e2e_u8 = None
-    if world == 1 and not train and not u8_in and not args.no_u8_leg:
-        try:
-            x_host_u8, xin_u8 = u8_buffers()
-            xin_u8[0].copy_(x_host_u8)
-            sub = xin_u8[0][:2]
-            got = ops.image_u8_to_f32(sub, mean_bgr, True)
-            want = (sub.float() - torch.tensor(mean_bgr, device="cuda")).flip(3).permute(0, 3, 1, 2)
-            exact = bool(torch.equal(got, want))
-            del got, want
-            e2e_loop(2, True)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            e2e_loop(k_e2e, True)
-            torch.cuda.synchronize()
-            u8_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
-            e2e_u8 = {"value": round(batch / (u8_ms / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": x_host_u8.numel(),
-                      "d2h_bytes_per_step": d2h, "ms_per_step": round(u8_ms, 3), "steps": k_e2e, "bit_exact_vs_torch": exact,
-                      "note": "pinned uint8 HWC BGR images -> H2D (side stream) -> esn_image_u8hwc_to_f32nchw -> model.predict_mask -> D2H uint8 masks (third stream)"}
-        except Exception as exc:      # noqa: BLE001 -- report, do not lose the measured line
-            e2e_u8 = {"error": repr(exc)[:300]}
-
+        t_hbm, t_tc = alg_bytes / (hbm_peak * 1e9) * 1e3, flops / (tc_peak * 1e12) * 1e3
+        model_roof = {"alg_bytes_per_step": int(alg_bytes), "hbm_frac": round(t_hbm / ms_per_step, 4),
+                      "tensor_frac": round(t_tc / ms_per_step, 4), "bound": "tensor" if t_tc > t_hbm else "hbm",
+                      "frac": round(max(t_hbm, t_tc) / ms_per_step, 4),
+                      "note": "block-fused algorithmic bytes (SURVEY 8d) and conv FLOPs of the whole step / step time"}
     if rank != 0:
-        _finish(dist)
-        return
+        del graph, gstep
+        return None
     line = {"metric": "images/s", "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(config, cuda_graph=graph is not None),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms, 3), "steps": k_e2e,
+                    "ms_per_step": round(e2e_ms, 3), "steps": k_e2e, "input": "u8" if u8_in else "f32",
+                    "preprocessing_bit_exact_vs_torch": exact,
                     "note": ("pinned fp32 NCHW images + int64 labels -> H2D -> one training iteration (forward, weighted CE, backward, "
-                             "all-reduce, Adam; CUDA graph: %s) -> D2H loss scalar; copies double-buffered on a side stream" % (gstep is not None))
+                             "all-reduce, Adam; CUDA graph: %s) -> D2H loss scalar; copies double-buffered on side streams" % (gstep is not None))
                     if train else
-                    ("pinned uint8 HWC BGR images -> H2D -> esn_image_u8hwc_to_f32nchw -> model.predict_mask -> D2H uint8 masks; "
-                     "copies double-buffered on a side stream" if u8_in else
-                     "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on a side stream"),
-                    "input": args.e2e_input},
-            "e2e_u8": e2e_u8,
+                    ("pinned uint8 HWC BGR images (what cv2.imread gives the reference's dataset class) -> H2D -> "
+                     "esn_image_u8hwc_to_f32nchw -> model.predict_mask -> D2H uint8 masks; copies double-buffered on side streams"
+                     if u8_in else
+                     "pinned fp32 NCHW images -> H2D -> model.predict_mask -> D2H uint8 masks; copies double-buffered on side streams")},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "model_roofline": model_roof, "kernels": kernels, "layers": layers}
-    if not args.no_cpu_baseline and world == 1:      # contract: rank 0 at N=1 only
+            "roofline": roofline, "model_roofline": model_roof, "units": dict(list(units.items())[:12]) if units else None,
+            "kernels": kernels, "layers": layers}
+    if primary and not args.no_cpu_baseline and world == 1:      # contract: rank 0 at N=1 only
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base
+    del graph, gstep, m
+    torch.cuda.empty_cache()
     if not args.no_gpu_eager and world == 1:
-        torch.cuda.empty_cache()
         try:
             g = gpu_eager_reference_leg(model_name, batch, H, W, train)
             g["speedup_vs_fastest"] = round(value / g["value"], 3) if g["value"] else None
             line["gpu_eager_baseline"] = g
         except Exception as exc:      # noqa: BLE001 -- report, do not lose the measured line
             line["gpu_eager_baseline"] = {"error": repr(exc)[:300]}
-    emit(line)
-    if e2e_u8 is not None and "error" in e2e_u8:
-        # the guarded leg failed: if it left a sticky CUDA error, a normal interpreter shutdown could abort after the line
-        # has been printed; leave directly (all results are out)
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    return line
+
+
+DEFAULT_WORKLOAD = "dabnet_train_bf16_b8_512x1024"
+SECONDARY = {"dabnet_train_bf16_b8_512x1024": ["erfnet_infer_bf16_b16_1024x2048"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the gpu_eager_baseline leg (N=1)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the secondary workloads reported under `legs`")
+    ap.add_argument("--e2e-input", default="u8", choices=["f32", "u8"],
+                    help="inference e2e leg: what crosses PCIe -- decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / "
+                         "CHW done on the device (esn_image_u8hwc_to_f32nchw, SURVEY 8f-4; default), or the reference's "
+                         "pre-processed fp32 NCHW batch")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    args = ap.parse_args()
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are
+    # redirected to stderr for the duration of the run; the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        _real_stdout.write(json.dumps(obj) + "\n")
+        _real_stdout.flush()
+    model_name, batch, H, W, mode = WORKLOADS[args.workload]
+    train = mode == "train"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wu = max(args.warmup, 3)
+        base, mean, n = cpu_reference_leg(model_name, H, W, args.steps, wu, budget_s=90.0, train=train)
+        emit({"impl": "reference", "metric": "images/s", "value": base["value"], "unit": "images/s",
+              "n_gpus": args.gpus, "steps": n, "warmup": wu, "ms_per_step": mean * 1e3,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": args.workload, "net": model_name, "classes": 19, "batch_per_gpu": 1,
+                         "input": "3x%dx%d fp32 NCHW" % (H, W),
+                         "mode": ("training step (CPU, reference arithmetic): train-mode forward + weighted CE + backward"
+                                  if train else "inference (CPU, reference arithmetic)"),
+                         "sample": "each step = ONE image of the workload's resolution (bounded sample of the %d-image batch)" % batch},
+              "cpu_baseline": base,
+              "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "gpu_launches": 0})
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if args.impl == "reference-gpu":
+        # the reference graph eager on this GPU (every variant incl. true fp32); one process, rank 0 only
+        if rank != 0:
+            return
+        g = gpu_eager_reference_leg(model_name, batch, H, W, train, warmup=max(args.warmup, 5), steps=args.steps,
+                                    variants=["fp32", "fp32_tf32", "bf16_autocast", "bf16_autocast_channels_last",
+                                              "bf16_weights_channels_last"])
+        emit({"impl": "reference-gpu", "metric": "images/s", "value": g["value"], "unit": "images/s", "n_gpus": 1,
+              "steps": args.steps, "warmup": max(args.warmup, 5),
+              "ms_per_step": g["variants"][g["fastest"]]["ms_per_step"] if g["fastest"] else None,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": g["fastest"], "data": "synthetic",
+              "config": {"workload": args.workload, "net": model_name, "batch_per_gpu": batch, "input": "3x%dx%d" % (H, W)},
+              "gpu_eager_baseline": g, "gpu_launches": 0})
+        return
+    affinity = numa_local_affinity(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = measure(args, args.workload, rank, world, local_rank, dist, primary=True)
+    legs = {}
+    if not args.no_legs:
+        for name in SECONDARY.get(args.workload, []):
+            try:
+                leg = measure(args, name, rank, world, local_rank, dist, primary=False)
+            except Exception as exc:      # noqa: BLE001 -- a failing secondary leg must not cost the primary line
+                leg = {"error": repr(exc)[:300]}
+            if rank == 0:
+                legs[name] = leg
+    if rank == 0:
+        line["host_affinity"] = affinity
+        if legs:
+            line["legs"] = legs
+        emit(line)
     _finish(dist)
 
 
 def _finish(dist):
-    """Leave without tearing NCCL down: communicators whose collectives were captured into a CUDA graph (the graphed
-    training step) can block in destroy_process_group / interpreter shutdown, which would hang the launcher after the
-    JSON line has been printed.  All device work is complete here (synchronised above)."""
+    """Orderly exit.  Round 1 left through os._exit(0) because destroy_process_group could block after NCCL collectives had
+    been captured into a CUDA graph: the captured graphs keep the communicator's streams and buffers referenced.  Now the
+    graphs are destroyed first (measure() drops them), the device is synchronised, every rank meets at a barrier and the
+    process group is destroyed.  A watchdog still guarantees that the launcher is released if teardown stalls (it says so
+    on stderr)."""
     sys.stdout.flush()
     sys.stderr.flush()
-    if dist:
-        try:
-            torch.cuda.synchronize()
-        except Exception:
-            pass
+    if not dist:
+        return
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+
+    def bail():
+        sys.stderr.write("bench.py: process-group teardown did not finish in 30 s; leaving through os._exit\n")
+        sys.stderr.flush()
         os._exit(0)
+    timer = threading.Timer(30.0, bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        sys.stderr.write("bench.py: process group destroyed cleanly\n")
+    finally:
+        timer.cancel()
 
 
 if __name__ == "__main__":
