@@ -230,7 +230,8 @@ int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y, bool allow_resi
   return ESN_OK;
 }
 
-bool esn_dwconv_try(const EsnConv* p, void* stream, int* rc);   // esn_stencil.cu: vectorised depthwise path
+bool esn_dwconv_try(const EsnConv* p, void* stream, int* rc);   // esn_stencil.cu: vectorised depthwise path (gather)
+bool esn_dw_strip_try(const EsnConv* p, void* stream, int* rc); // esn_dw_strip.cu: register-strip depthwise path (stride 1, 'same')
 
 extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
   if (!p || !p->w) return ESN_ERR_BAD_ARG;
@@ -259,6 +260,7 @@ extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
   }
   int rc = esn_check_epilogue(p->ep, y);
   if (rc) return rc;
+  if (dw && !getenv("ESN_DISABLE_DW_STRIP") && esn_dw_strip_try(p, stream, &rc)) return rc;
   if (dw && esn_dwconv_try(p, stream, &rc)) return rc;
 
   DirectArgs a;

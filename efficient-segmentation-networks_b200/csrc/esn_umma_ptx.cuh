@@ -152,14 +152,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// Planner dry run (tests only): with ESN_DRY_RUN=1 in the environment the host side of esn_conv2d_umma runs every gate
-// and the whole launch plan against nominal B200 limits (148 SMs, 227 KB shared memory) and returns right before the
-// launch without touching CUDA -- so the CPU test suite can check that the shapes a model sends are accepted by the
-// library's own planner (tests/test_abi_emulation_cpu.py).  Read once; has no effect when unset.
+// Planner dry run (TEST BUILD ONLY, -DESN_TESTING -> libesn_sm100_testing.so): with ESN_DRY_RUN=1 in the environment the
+// host side of esn_conv2d_umma runs every gate and the whole launch plan against nominal B200 limits (148 SMs, 227 KB
+// shared memory) and returns right before the launch without touching CUDA -- so the CPU test suite can check that the
+// shapes a model sends are accepted by the library's own planner (tests/test_abi_emulation_cpu.py).  The shipped
+// libesn_sm100.so does not contain the switch: no environment variable can turn its launches into no-ops.
+#ifdef ESN_TESTING
 inline bool esn_dry_run() {
   static const bool v = [] { const char* e = getenv("ESN_DRY_RUN"); return e && e[0] == '1'; }();
   return v;
 }
+#else
+constexpr bool esn_dry_run() { return false; }
+#endif
 inline CUresult esn_dry_encode(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {

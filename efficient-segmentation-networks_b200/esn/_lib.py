@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesn_sm100.so")
+# ESN_LIB_PATH: load another build of the same C ABI (the test suite points it at libesn_sm100_testing.so)
+LIB_PATH = os.environ.get("ESN_LIB_PATH") or os.path.join(_HERE, "libesn_sm100.so")
 
 ESN_F32, ESN_BF16, ESN_U8, ESN_I64, ESN_I32 = 0, 1, 2, 3, 4
 ESN_NHWC, ESN_NCHW = 0, 1

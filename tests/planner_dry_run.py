@@ -1,13 +1,14 @@
 """TEST INFRASTRUCTURE ONLY (run as a subprocess by tests/test_abi_emulation_cpu.py, never imported by the package).
 
-Sends every C-ABI call of a bf16 forward to the REAL libesn_sm100.so with ESN_DRY_RUN=1: argument validation of every
+Sends every C-ABI call of a bf16 forward to the REAL library (its test build libesn_sm100_testing.so, selected through
+ESN_LIB_PATH: the shipped libesn_sm100.so has no dry-run switch) with ESN_DRY_RUN=1: argument validation of every
 entry point runs as on the device, and esn_conv2d_umma additionally runs its whole launch planner (tile shapes, reuse
 mode, shared-memory / TMEM budget) against nominal B200 limits and returns before launching.  Return codes:
   0  = accepted (planner dry run), -4 = accepted by validation, then the launch failed because this box has no GPU;
   anything else = the library would refuse the call on the device.
 Shapes only: the CPU model of the arithmetic is skipped, so full benchmark resolutions are cheap.
 
-    ESN_DRY_RUN=1 python tests/planner_dry_run.py NET H W [NET H W ...]   ->  one JSON object on stdout
+    ESN_DRY_RUN=1 ESN_LIB_PATH=.../esn/libesn_sm100_testing.so python tests/planner_dry_run.py NET H W [NET H W ...]   ->  one JSON object on stdout
 """
 import collections
 import json

@@ -120,7 +120,10 @@ def test_real_library_planner_accepts_every_call_at_benchmark_shapes():
         args += [name, "1024", "2048"]
     for name in ("ESNet", "ContextNet", "EDANet", "LEDNet"):
         args += [name, "64", "128", name, "512", "1024"]
-    env = dict(os.environ, ESN_DRY_RUN="1")
+    # the dry-run switch exists only in the test build of the library (csrc/Makefile: -DESN_TESTING)
+    tlib = os.path.join(os.path.dirname(here), "efficient-segmentation-networks_b200", "esn", "libesn_sm100_testing.so")
+    assert os.path.exists(tlib), "run `make -C efficient-segmentation-networks_b200/csrc` (builds the testing library too)"
+    env = dict(os.environ, ESN_DRY_RUN="1", ESN_LIB_PATH=tlib)
     r = subprocess.run([sys.executable, os.path.join(here, "planner_dry_run.py")] + args, env=env, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]

@@ -305,3 +305,57 @@ def test_enet_pool_unpool_matches_cpu_reference(ops):
     refb = F.relu(F.max_unpool2d(vb.contiguous(), ref_i, 2) + eb)
     outb = ops.max_unpool2x2(_nhwc(vb.cuda(), torch.bfloat16, ops), idx, ext=_nhwc(eb.cuda(), torch.bfloat16, ops), act=ACT_RELU)
     assert outb.dtype == torch.bfloat16 and torch.equal(outb.float().cpu(), refb)
+
+
+DW_STRIP_CASES = [
+    # C, k, dil, H, W, act, residual mode (None / "post" / "pre_act")
+    (64, (3, 3), (1, 1), 33, 50, "prelu", None),        # CGNet F_loc
+    (64, (3, 3), (4, 4), 33, 50, "prelu", None),        # CGNet F_sur
+    (128, (3, 3), (2, 2), 40, 36, "relu", "post"),
+    (384, (3, 3), (1, 1), 16, 24, "relu", None),        # Fast-SCNN bottleneck expansion
+    (32, (3, 1), (16, 1), 40, 24, "prelu", None),       # DABNet branch, dilation 16
+    (32, (1, 3), (1, 16), 24, 40, "prelu", "pre_act"),
+    (64, (3, 1), (1, 1), 70, 9, "none", "post"),        # chains longer than one segment
+    (8, (3, 3), (3, 3), 5, 7, "none", None),            # dilation ~ image size
+    (16, (3, 3), (1, 1), 130, 140, "relu", None),
+]
+
+
+@pytest.mark.parametrize("case", DW_STRIP_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_depthwise_strip_matches_torch(ops, case, dtype):
+    """The register-strip depthwise kernel (csrc/esn_dw_strip.cu) behind esn_conv2d_direct: every tap shape, dilated column
+    chains, segment halos, ragged widths, both residual orders -- against torch's depthwise conv2d in fp32, and against the
+    gather kernel it replaces (same C-ABI call with ESN_DISABLE_DW_STRIP=1)."""
+    import os
+    from esn._lib import ACT_NONE, ACT_PRELU, ACT_RELU, EP_ACT_BEFORE_RESIDUAL
+    C, k, dil, H, W, act, rmode = case
+    pad = ((k[0] // 2) * dil[0], (k[1] // 2) * dil[1])
+    m = _rand_conv(C, C, k, 1, pad, dil, C, False)
+    torch.manual_seed(2)
+    x = torch.randn(3, C, H, W, device="cuda")
+    scale = torch.rand(C, device="cuda") + 0.5
+    shift = torch.randn(C, device="cuda") * 0.1
+    alpha = torch.rand(C, device="cuda") * 0.4
+    xa = _nhwc(x, dtype, ops)
+    f = {"none": lambda t: t, "relu": torch.relu, "prelu": lambda t: torch.where(t >= 0, t, t * alpha.view(1, -1, 1, 1))}[act]
+    with torch.no_grad():
+        ref = m(xa.float()) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        resa = None
+        if rmode:
+            resa = _nhwc(torch.randn_like(ref), dtype, ops)
+            ref = (f(ref) if rmode == "pre_act" else ref) + resa.float()
+        ref = f(ref)
+    prep = ops.ConvPrep(m, scale, shift, {"none": ACT_NONE, "relu": ACT_RELU, "prelu": ACT_PRELU}[act], alpha if act == "prelu" else None)
+    if rmode == "pre_act":
+        prep.ep_flags = EP_ACT_BEFORE_RESIDUAL
+    y = ops.conv2d(xa, prep, residual=resa, force_direct=True)
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    err = (y.float() - ref).abs().max() / ref.abs().max()
+    assert err < tol, err
+    os.environ["ESN_DISABLE_DW_STRIP"] = "1"
+    try:
+        y_old = ops.conv2d(xa, prep, residual=resa, force_direct=True)
+    finally:
+        del os.environ["ESN_DISABLE_DW_STRIP"]
+    assert (y.float() - y_old.float()).abs().max() / ref.abs().max() < tol
