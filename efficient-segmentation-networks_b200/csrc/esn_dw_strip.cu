@@ -35,9 +35,9 @@ __device__ __forceinline__ void stv(__nv_bfloat16* p, float2 (&v)[4]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[i].x, v[i].y);
   *reinterpret_cast<uint4*>(p) = r;
 }
-__device__ __forceinline__ float2 dws_act2(float2 v, int act, float2 al) {
-  if (act == ESN_ACT_RELU) return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
-  if (act == ESN_ACT_PRELU) return make_float2(v.x >= 0.f ? v.x : v.x * al.x, v.y >= 0.f ? v.y : v.y * al.y);
+template <int ACT> __device__ __forceinline__ float2 dws_act2(float2 v, float2 al) {
+  if (ACT == ESN_ACT_RELU) return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+  if (ACT == ESN_ACT_PRELU) return make_float2(v.x >= 0.f ? v.x : v.x * al.x, v.y >= 0.f ? v.y : v.y * al.y);
   return v;
 }
 }  // namespace
@@ -45,14 +45,31 @@ __device__ __forceinline__ float2 dws_act2(float2 v, int act, float2 al) {
 #include "esn_dw_strip_kernel.cuh"
 
 namespace {
-template <typename T, int V, int KH, int KW, int TW>
-int launch_strip(DwsArgs a, cudaStream_t st) {
-  dws_plan(a, V, KH, KW, TW, 148LL * 2048 * 4);
+template <typename T, int V, int KH, int KW, int TW, int ACT, int RES>
+int launch_strip2(const DwsArgs& a, cudaStream_t st) {
   const long long grid = (a.total + 127) / 128;
   if (grid > 0x7fffffffLL) return ESN_ERR_UNSUPPORTED;
-  dw_strip_kernel<T, V, KH, KW, TW><<<(unsigned)grid, 128, 0, st>>>(a);
+  // the 3x3 kernel on 8-channel vectors holds 72 taps + 48 accumulators + 3 row buffers: ~210 registers, 2 CTAs per SM
+  // (measured: capping it at 168 registers for a third CTA spills and is 5-10 % slower)
+  constexpr int MINB = (KH == 3 && KW == 3 && V == 8) ? 2 : 3;
+  dw_strip_kernel<T, V, KH, KW, TW, ACT, RES, MINB><<<(unsigned)grid, 128, 0, st>>>(a);
   ESN_CHECK_LAUNCH();
   return ESN_OK;
+}
+template <typename T, int V, int KH, int KW, int TW>
+int launch_strip(DwsArgs a, cudaStream_t st) {
+  // 3 CTAs x 128 threads resident per SM; keep >= ~4 waves of them before chains are allowed to be long (each chain pays two
+  // halo rows, so longer is cheaper per output row, but a tail of idle SMs costs more)
+  dws_plan(a, V, KH, KW, TW, 148LL * 256 * 4);
+  const bool res = a.res != nullptr;
+  switch (a.act) {
+    case ESN_ACT_RELU:
+      return res ? launch_strip2<T, V, KH, KW, TW, ESN_ACT_RELU, 1>(a, st) : launch_strip2<T, V, KH, KW, TW, ESN_ACT_RELU, 0>(a, st);
+    case ESN_ACT_PRELU:
+      return res ? launch_strip2<T, V, KH, KW, TW, ESN_ACT_PRELU, 1>(a, st) : launch_strip2<T, V, KH, KW, TW, ESN_ACT_PRELU, 0>(a, st);
+    default:
+      return res ? launch_strip2<T, V, KH, KW, TW, ESN_ACT_NONE, 1>(a, st) : launch_strip2<T, V, KH, KW, TW, ESN_ACT_NONE, 0>(a, st);
+  }
 }
 }  // namespace
 

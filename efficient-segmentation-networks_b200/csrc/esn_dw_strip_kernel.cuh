@@ -15,7 +15,8 @@
 // multiply-adds are issued as packed FFMA2 (two channels per instruction).  The vectors of the next input row are
 // requested before the current row's arithmetic, so two rows of loads are in flight per thread.
 //
-// DwsRaw<T>, ldraw / unpack / stv (one 16-byte channel vector <-> float2[V/2]), ffma2, dws_act2 come from the including file.
+// DwsRaw<T>, ldraw / unpack / stv (one 16-byte channel vector <-> float2[V/2]), ldw4, ffma2, dws_act2<ACT> come from the
+// including file.
 #pragma once
 #include <stdint.h>
 
@@ -54,8 +55,9 @@ static inline void dws_plan(DwsArgs& a, int V, int KH, int KW, int TW, long long
   a.total = per_row * a.VS;
 }
 
-// One thread.  V = channels per 16-byte vector of T.
-template <typename T, int V, int KH, int KW, int TW>
+// One thread.  V = channels per 16-byte vector of T.  ACT / RES: compile-time epilogue (ACT: ESN_ACT_* value; RES: 0 no residual,
+// 1 residual, with a.pre_act deciding whether the activation also runs before the add).
+template <typename T, int V, int KH, int KW, int TW, int ACT, int RES>
 __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
   constexpr int NCOL = TW + KW - 1;
   constexpr int H2 = V / 2;
@@ -75,9 +77,9 @@ __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
   int nrows = (a.H - h_first + dh - 1) / dh;      // rows left in this chain
   if (nrows > a.seg) nrows = a.seg;
 
-  // taps (x epilogue scale), shift and slopes in registers
+  // taps (x epilogue scale) in registers; the shift is the accumulators' initial value
   float2 wr[KH * KW][H2];
-  float2 sh[H2], al[H2];
+  float2 sh[H2];
 #pragma unroll
   for (int i = 0; i < H2; i += 2) {       // 16-byte parameter loads: channels c + 2i .. c + 2i + 3
     const float4 sc = a.scale ? ldw4(a.scale + c + 2 * i) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -88,13 +90,10 @@ __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
       wr[tap][i + 1] = make_float2(wv.z * sc.z, wv.w * sc.w);
     }
     const float4 sv = a.shift ? ldw4(a.shift + c + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 av = (a.act == 2) ? ldw4(a.alpha + c + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     sh[i] = make_float2(sv.x, sv.y);
     sh[i + 1] = make_float2(sv.z, sv.w);
-    al[i] = make_float2(av.x, av.y);
-    al[i + 1] = make_float2(av.z, av.w);
   }
-  // column validity (zero padding left / right, ragged right edge)
+  // column validity (zero padding left / right, ragged right edge); interior threads take the unchecked path
   unsigned cmask = 0, omask = 0;
 #pragma unroll
   for (int j = 0; j < NCOL; ++j) {
@@ -104,47 +103,69 @@ __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
 #pragma unroll
   for (int j = 0; j < TW; ++j)
     if (w0 + j * dw < a.W) omask |= 1u << j;
-  const T* xb = reinterpret_cast<const T*>(a.x) + ((long long)n * a.H * a.W + (w0 - ((KW - 1) / 2) * dw)) * a.x_cs + c;
-  T* yb = reinterpret_cast<T*>(a.y) + ((size_t)n * a.H * a.W + w0) * a.y_cs + c;
-  const T* rb = a.res ? reinterpret_cast<const T*>(a.res) + ((size_t)n * a.H * a.W + w0) * a.res_cs + c : nullptr;
-  const size_t xcol = (size_t)dw * a.x_cs, ycol = (size_t)dw * a.y_cs, rcol = (size_t)dw * a.res_cs;
+  const bool interior = cmask == (1u << NCOL) - 1u && omask == (1u << TW) - 1u;
+  const long long xrow = (long long)a.W * a.x_cs, yrow = (long long)a.W * a.y_cs, rrow = (long long)a.W * a.res_cs;
+  const long long xcol = (long long)dw * a.x_cs, ycol = (long long)dw * a.y_cs, rcol = (long long)dw * a.res_cs;
+  // running row pointers: input row about to be loaded, output row about to be stored
+  const int first_in = (KH == 1) ? h_first : h_first - dh;
+  const T* xp = reinterpret_cast<const T*>(a.x) + ((long long)n * a.H + first_in) * xrow + (long long)(w0 - ((KW - 1) / 2) * dw) * a.x_cs + c;
+  T* yp = reinterpret_cast<T*>(a.y) + ((long long)n * a.H + h_first) * yrow + (long long)w0 * a.y_cs + c;
+  const T* rp = RES ? reinterpret_cast<const T*>(a.res) + ((long long)n * a.H + h_first) * rrow + (long long)w0 * a.res_cs + c : nullptr;
+  int in_row = first_in;
 
   typedef typename DwsRaw<T>::type raw_t;
-  auto load_row = [&](int row, raw_t (&r)[NCOL]) {
-    const bool ok = row >= 0 && row < a.H;
-    const T* p = xb + (long long)row * a.W * a.x_cs;
+  auto load_row = [&](raw_t (&r)[NCOL]) {          // loads input row `in_row`, then advances to the next row of the chain
+    const bool ok = in_row >= 0 && in_row < a.H;
+    if (ok && interior) {
 #pragma unroll
-    for (int j = 0; j < NCOL; ++j) r[j] = (ok && (cmask >> j & 1)) ? ldraw(p + j * xcol) : DwsRaw<T>::zero();
+      for (int j = 0; j < NCOL; ++j) r[j] = ldraw(xp + j * xcol);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) r[j] = (ok && (cmask >> j & 1)) ? ldraw(xp + j * xcol) : DwsRaw<T>::zero();
+    }
+    xp += dh * xrow;
+    in_row += dh;
   };
-  auto store_row = [&](int row, float2 (&acc)[TW][H2]) {
+  auto store_row = [&](float2 (&acc)[TW][H2]) {    // epilogue of one finished output row, then advances the output row
+    float2 al[H2];
+#pragma unroll
+    for (int i = 0; i < H2; ++i) al[i] = make_float2(0.f, 0.f);
+    if (ACT == 2) {       // PReLU slopes: L1-resident 16-byte loads, not worth 8 registers across the whole walk
+#pragma unroll
+      for (int i = 0; i < H2; i += 2) {
+        const float4 av = ldw4(a.alpha + c + 2 * i);
+        al[i] = make_float2(av.x, av.y);
+        al[i + 1] = make_float2(av.z, av.w);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < TW; ++j) {
-      if (!(omask >> j & 1)) continue;
+      if (!interior && !(omask >> j & 1)) continue;
       float2 v[H2];
 #pragma unroll
-      for (int i = 0; i < H2; ++i) v[i] = make_float2(acc[j][i].x + sh[i].x, acc[j][i].y + sh[i].y);
-      if (rb) {
+      for (int i = 0; i < H2; ++i) v[i] = acc[j][i];
+      if (RES) {
         float2 r[H2];
-        unpack(ldraw(rb + (size_t)row * a.W * a.res_cs + j * rcol), r);
+        unpack(ldraw(rp + j * rcol), r);
 #pragma unroll
         for (int i = 0; i < H2; ++i) {
-          if (a.pre_act) v[i] = dws_act2(v[i], a.act, al[i]);
+          if (a.pre_act) v[i] = dws_act2<ACT>(v[i], al[i]);
           v[i].x += r[i].x;
           v[i].y += r[i].y;
         }
       }
 #pragma unroll
-      for (int i = 0; i < H2; ++i) v[i] = dws_act2(v[i], a.act, al[i]);
-      stv(yb + (size_t)row * a.W * a.y_cs + j * ycol, v);
+      for (int i = 0; i < H2; ++i) v[i] = dws_act2<ACT>(v[i], al[i]);
+      stv(yp + j * ycol, v);
     }
+    yp += dh * yrow;
+    if (RES) rp += dh * rrow;
   };
 
-  raw_t cur[NCOL], nxt[NCOL];
-  if (KH == 1) {
-    load_row(h_first, cur);
-    for (int k = 0; k < nrows; ++k) {
-      const int row = h_first + k;
-      if (k + 1 < nrows) load_row(row + 1, nxt);
+  raw_t R0[NCOL], R1[NCOL];       // row buffers swap roles every step (no register copies)
+  if constexpr (KH == 1) {
+    auto row1 = [&](int k, raw_t (&cur)[NCOL], raw_t (&nxt)[NCOL]) {
+      if (k + 1 < nrows) load_row(nxt);
       float2 xf[NCOL][H2];
 #pragma unroll
       for (int j = 0; j < NCOL; ++j) unpack(cur[j], xf[j]);
@@ -153,26 +174,32 @@ __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
       for (int j = 0; j < TW; ++j)
 #pragma unroll
         for (int i = 0; i < H2; ++i) {
-          float2 s = make_float2(xf[j][i].x * wr[0][i].x, xf[j][i].y * wr[0][i].y);
+          float2 s = sh[i];
 #pragma unroll
-          for (int tp = 1; tp < KW; ++tp) s = ffma2(xf[j + tp][i], wr[tp][i], s);
+          for (int tp = 0; tp < KW; ++tp) s = ffma2(xf[j + tp][i], wr[tp][i], s);
           acc[j][i] = s;
         }
-      store_row(row, acc);
-#pragma unroll
-      for (int j = 0; j < NCOL; ++j) cur[j] = nxt[j];
+      store_row(acc);
+    };
+    load_row(R0);
+    for (int k = 0; k < nrows; k += 2) {
+      row1(k, R0, R1);
+      if (k + 1 >= nrows) break;
+      row1(k + 1, R1, R0);
     }
-    return;
-  }
+  } else {
   // KH == 3: input row I_k = h_first + k*dh feeds output rows k-1 (bottom tap), k (centre), k+1 (top tap)
   float2 A[TW][H2], B[TW][H2], Cc[TW][H2];
 #pragma unroll
   for (int j = 0; j < TW; ++j)
 #pragma unroll
     for (int i = 0; i < H2; ++i) A[j][i] = B[j][i] = Cc[j][i] = make_float2(0.f, 0.f);
-  auto step = [&](int k, float2 (&prev)[TW][H2], float2 (&mid)[TW][H2], float2 (&next)[TW][H2]) {
-    const int row = h_first + k * dh;
-    if (k < nrows) load_row(row + dh, nxt);
+  // Three row buffers: while row k is consumed, rows k+1 and k+2 are in flight -- with two resident CTAs per SM (the 3x3
+  // kernel needs ~200 registers) one step of arithmetic is shorter than a DRAM round trip, two steps are not.
+  raw_t R2[NCOL];
+  auto step = [&](int k, raw_t (&cur)[NCOL], raw_t (&fill)[NCOL], float2 (&prev)[TW][H2], float2 (&mid)[TW][H2],
+                  float2 (&next)[TW][H2]) {
+    if (k + 2 <= nrows) load_row(fill);
     float2 xf[NCOL][H2];
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) unpack(cur[j], xf[j]);
@@ -180,9 +207,9 @@ __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
     for (int j = 0; j < TW; ++j)
 #pragma unroll
       for (int i = 0; i < H2; ++i) {
-        float2 nx = make_float2(xf[j][i].x * wr[0][i].x, xf[j][i].y * wr[0][i].y);
+        float2 nx = sh[i];
 #pragma unroll
-        for (int tp = 1; tp < KW; ++tp) nx = ffma2(xf[j + tp][i], wr[tp][i], nx);
+        for (int tp = 0; tp < KW; ++tp) nx = ffma2(xf[j + tp][i], wr[tp][i], nx);
         next[j][i] = nx;
 #pragma unroll
         for (int tp = 0; tp < KW; ++tp) {
@@ -190,24 +217,24 @@ __device__ __forceinline__ void dw_strip_thread(const DwsArgs& a, long long t) {
           prev[j][i] = ffma2(xf[j + tp][i], wr[2 * KW + tp][i], prev[j][i]);
         }
       }
-    if (k >= 1) store_row(row - dh, prev);
-#pragma unroll
-    for (int j = 0; j < NCOL; ++j) cur[j] = nxt[j];
+    if (k >= 1) store_row(prev);
   };
-  load_row(h_first - dh, cur);
-  for (int k = -1; k <= nrows; k += 3) {
-    step(k, A, B, Cc);
+  load_row(R0);       // input rows I_-1 and I_0
+  load_row(R1);
+  for (int k = -1; k <= nrows; k += 3) {      // accumulator roles and row-buffer roles both rotate with period 3
+    step(k, R0, R2, A, B, Cc);
     if (k + 1 > nrows) break;
-    step(k + 1, B, Cc, A);
+    step(k + 1, R1, R0, B, Cc, A);
     if (k + 2 > nrows) break;
-    step(k + 2, Cc, A, B);
+    step(k + 2, R2, R1, Cc, A, B);
+  }
   }
 }
 
-template <typename T, int V, int KH, int KW, int TW>
-__global__ void __launch_bounds__(128) dw_strip_kernel(const DwsArgs a) {
+template <typename T, int V, int KH, int KW, int TW, int ACT, int RES, int MINB>
+__global__ void __launch_bounds__(128, MINB) dw_strip_kernel(const DwsArgs a) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < a.total) dw_strip_thread<T, V, KH, KW, TW>(a, t);
+  if (t < a.total) dw_strip_thread<T, V, KH, KW, TW, ACT, RES>(a, t);
 }
 
 }  // namespace

@@ -368,6 +368,8 @@ struct CEArgs {
   int N, C, H, W, ignore;
   const float* gnorm;
   const float* gout;
+  float* prob_out;           // optional: softmax probability of the target class per pixel (1 where ignored)
+  const float* keep_thresh;  // optional device scalar: pixels whose target probability exceeds it count as ignored (OHEM)
 };
 
 template <typename T>
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(256) weighted_ce_kernel(const CEArgs a) {
     const long long px = idx % hw;
     const T* lp = reinterpret_cast<const T*>(a.logits) + (size_t)n * a.C * hw + px;
     const long long y = a.target[idx];
-    const bool valid = (y != a.ignore) && y >= 0 && y < a.C;
+    bool valid = (y != a.ignore) && y >= 0 && y < a.C;
     float v[kMaxClasses];
     float m = -INFINITY, xy = 0.f;
 #pragma unroll
@@ -398,6 +400,13 @@ __global__ void __launch_bounds__(256) weighted_ce_kernel(const CEArgs a) {
         v[k] = __expf(v[k] - m);
         s += v[k];
       }
+    if (a.prob_out || a.keep_thresh) {
+      // OHEM (utils/losses/loss.py:189-206): probability of the labelled class, 1 for ignored pixels; the same expression in
+      // the recording pass and in the thresholded pass, so both see identical bits
+      const float py = valid ? __expf(xy - m) / s : 1.f;
+      if (a.prob_out) a.prob_out[idx] = py;
+      if (a.keep_thresh && !(py <= __ldg(a.keep_thresh))) valid = false;
+    }
     const float wy = valid ? (a.weight ? __ldg(a.weight + y) : 1.f) : 0.f;
     if (valid) {
       wl = wy * (m + logf(s) - xy);  // w * (lse - x_y)
@@ -596,6 +605,8 @@ extern "C" int esn_weighted_ce(const EsnCE* p, void* stream) {
   a.ignore = p->ignore_label;
   a.gnorm = p->gnorm;
   a.gout = p->gout;
+  a.prob_out = p->prob_out;
+  a.keep_thresh = p->keep_thresh;
   const long long total = (long long)l.n * l.h * l.w;
   const int block = 256, grid = esn_cdiv(total, block);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -14,6 +14,7 @@ ESN_F32, ESN_BF16, ESN_U8, ESN_I64, ESN_I32 = 0, 1, 2, 3, 4
 ESN_NHWC, ESN_NCHW = 0, 1
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 ERR_UNSUPPORTED = -3
+EP_ACT_BEFORE_RESIDUAL, EP_RESIDUAL_FIRST = 1, 2      # EsnEpilogue.flags (include/esn.h)
 
 
 class EsnTensor(C.Structure):
@@ -88,7 +89,7 @@ class EsnHead(C.Structure):
 class EsnCE(C.Structure):
     _fields_ = [("logits", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
                 ("dlogits", EsnTensor), ("ignore_label", C.c_int32), ("_pad", C.c_int32),
-                ("gnorm", C.c_void_p), ("gout", C.c_void_p)]
+                ("gnorm", C.c_void_p), ("gout", C.c_void_p), ("prob_out", C.c_void_p), ("keep_thresh", C.c_void_p)]
 
 
 # every symbol include/esn.h declares: name -> (restype, argtypes)
@@ -105,6 +106,8 @@ SYMBOLS = {
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
+    "esn_ohem_workspace_bytes": (C.c_int64, []),
+    "esn_ohem_threshold": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esn_channel_stats": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_int32, C.c_void_p]),
     "esn_bn_finalize": (C.c_int, [C.POINTER(EsnBnFinalize), C.c_void_p]),
     "esn_bn_act_bwd_reduce": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),

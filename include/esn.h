@@ -257,8 +257,25 @@ typedef struct EsnCE {
   int32_t _pad;
   const float* gnorm;     /* optional device scalar: dlogits are divided by *gnorm (the global sum of weights) */
   const float* gout;      /* optional device scalar: upstream gradient of the loss */
+  /* Online hard example mining, ProbOhemCrossEntropy2d (utils/losses/loss.py:163-216): */
+  float* prob_out;          /* optional (N,H,W) f32: softmax probability of the labelled class per pixel, 1 where ignored
+                               (mask_prob, loss.py:195-198) */
+  const float* keep_thresh; /* optional device scalar: pixels whose labelled-class probability exceeds *keep_thresh are
+                               treated as ignored (kept_mask, loss.py:203-206) */
 } EsnCE;
 int esn_weighted_ce(const EsnCE* p, void* stream);
+
+/* OHEM threshold on the device (loss.py:199-203), no host synchronisation:
+ *   if min_kept > *num_valid            -> *out = +inf                (nothing is filtered)
+ *   else kth = the min(n, min_kept)-th smallest of prob[0..n)  (what mask_prob.argsort()[min_kept - 1] selects)
+ *                                       -> *out = max(thresh, kth)
+ * prob holds non-negative floats (esn_weighted_ce's prob_out), so the order of their bit patterns is their numeric order:
+ * the k-th value is found exactly by a three-pass radix select (12 + 12 + 8 bits) over shared-memory histograms.
+ * num_valid: device scalar (f32 count of non-ignored pixels = sums[1] of an unweighted esn_weighted_ce pass).
+ * workspace: esn_ohem_workspace_bytes() bytes, zeroed by the caller before the call. */
+int64_t esn_ohem_workspace_bytes(void);
+int esn_ohem_threshold(const float* prob, int64_t n, int64_t min_kept, float thresh, const float* num_valid, float* out,
+                       void* workspace, void* stream);
 
 /* ------------------------------------------------------------------ training path
  * Train-mode BatchNorm2d (torch semantics: biased batch variance normalises, running_var is updated

@@ -22,20 +22,27 @@ inline float4 ldw4(const float* p) { return float4{p[0], p[1], p[2], p[3]}; }
 inline float4 ldraw(const float* p) { return float4{p[0], p[1], p[2], p[3]}; }
 inline void unpack(const float4& r, float2 (&f)[2]) { f[0] = make_float2(r.x, r.y); f[1] = make_float2(r.z, r.w); }
 inline void stv(float* p, float2 (&v)[2]) { p[0] = v[0].x; p[1] = v[0].y; p[2] = v[1].x; p[3] = v[1].y; }
-inline float2 dws_act2(float2 v, int act, float2 al) {
-  if (act == 1) return make_float2(fmaxf_(v.x, 0.f), fmaxf_(v.y, 0.f));
-  if (act == 2) return make_float2(v.x >= 0.f ? v.x : v.x * al.x, v.y >= 0.f ? v.y : v.y * al.y);
+template <int ACT> inline float2 dws_act2(float2 v, float2 al) {
+  if (ACT == 1) return make_float2(fmaxf_(v.x, 0.f), fmaxf_(v.y, 0.f));
+  if (ACT == 2) return make_float2(v.x >= 0.f ? v.x : v.x * al.x, v.y >= 0.f ? v.y : v.y * al.y);
   return v;
 }
 }  // namespace
 #include "esn_dw_strip_kernel.cuh"
 
+template <int KH, int KW, int TW, int ACT, int RES>
+static void run2(const DwsArgs& a) {
+  const long long slack = 37;      // threads beyond `total` must do nothing
+  for (long long t = 0; t < a.total + slack; ++t)
+    if (t < a.total) dw_strip_thread<float, 4, KH, KW, TW, ACT, RES>(a, t);
+}
 template <int KH, int KW, int TW>
 static void run(DwsArgs a, int seg_max, long long min_threads) {
   dws_plan(a, 4, KH, KW, TW, min_threads, seg_max);
-  const long long slack = 37;      // threads beyond `total` must do nothing
-  for (long long t = 0; t < a.total + slack; ++t)
-    if (t < a.total) dw_strip_thread<float, 4, KH, KW, TW>(a, t);
+  const bool res = a.res != nullptr;
+  if (a.act == 1) res ? run2<KH, KW, TW, 1, 1>(a) : run2<KH, KW, TW, 1, 0>(a);
+  else if (a.act == 2) res ? run2<KH, KW, TW, 2, 1>(a) : run2<KH, KW, TW, 2, 0>(a);
+  else res ? run2<KH, KW, TW, 0, 1>(a) : run2<KH, KW, TW, 0, 0>(a);
 }
 
 int main(int argc, char** argv) {

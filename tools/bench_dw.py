@@ -44,6 +44,9 @@ def main():
         row = {"shape": name, "alg_MB": round(nbytes / 1e6, 1)}
         for label, env in (("strip", None), ("gather", "1")):
             if env:
+                if os.environ.get("BENCH_DW_SKIP_GATHER"):
+                    row["gather_ms"], row["gather_GBps"] = float("nan"), float("nan")
+                    continue
                 os.environ["ESN_DISABLE_DW_STRIP"] = env
             for _ in range(5):
                 ops.conv2d(x, prep, out=y, force_direct=True)
