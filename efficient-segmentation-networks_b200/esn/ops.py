@@ -664,9 +664,11 @@ def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, l
                  want_logits, want_mask, logits_dtype, align_corners)
 
 
-def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, sums=None, gnorm=None, gout=None):
+def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, sums=None, gnorm=None, gout=None,
+                prob_out=None, keep_thresh=None):
     """Returns (sums[2] = [sum w*nll, sum w], dlogits or None); dlogits are scaled by gout/gnorm
-    (device scalars) when given, unnormalised otherwise."""
+    (device scalars) when given, unnormalised otherwise.  OHEM (loss.py:163-216): prob_out (N,H,W) fp32 receives the softmax
+    probability of the labelled class (1 where ignored); keep_thresh (device scalar) makes pixels above it count as ignored."""
     require_cuda(logits, "weighted_ce")
     logits = logits.contiguous()
     target = target.contiguous()
@@ -686,8 +688,23 @@ def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, 
         p.dlogits = tdesc(g)
         p.dlogits.layout, p.dlogits.c_stride = L.ESN_NCHW, 0
     p.ignore_label = ignore_label
+    p.prob_out = prob_out.data_ptr() if prob_out is not None else None
+    p.keep_thresh = keep_thresh.data_ptr() if keep_thresh is not None else None
     _call(L.lib.esn_weighted_ce, "esn_weighted_ce", (C.byref(p),), logits.numel() * logits.element_size() * (2 if want_grad else 1))
     return sums, g
+
+
+def ohem_threshold(prob, min_kept, thresh, num_valid):
+    """Device scalar max(thresh, min_kept-th smallest of prob), or +inf when min_kept exceeds *num_valid (loss.py:199-203);
+    radix select on the device, no host synchronisation."""
+    require_cuda(prob, "ohem_threshold")
+    prob = prob.contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=prob.device)
+    ws = torch.zeros((int(L.lib.esn_ohem_workspace_bytes()) + 7) // 8, dtype=torch.int64, device=prob.device)
+    _call(L.lib.esn_ohem_threshold, "esn_ohem_threshold",
+          (C.c_void_p(prob.data_ptr()), prob.numel(), int(min_kept), float(thresh), C.c_void_p(num_valid.data_ptr()),
+           C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr())), 3 * prob.numel() * 4)
+    return out
 
 
 def gate_bcast(g, x, b=None, out=None):

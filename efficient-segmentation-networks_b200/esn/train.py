@@ -621,9 +621,10 @@ class _CEFn(torch.autograd.Function):
     loss and its gradient equal the reference's gathered-batch value."""
 
     @staticmethod
-    def forward(ctx, logits, target, weight, ignore_label, distributed=False, reduction="mean"):
+    def forward(ctx, logits, target, weight, ignore_label, distributed=False, reduction="mean", keep_thresh=None):
         lg = logits.detach().contiguous()
-        sums, _ = ops.weighted_ce(lg, target, weight, ignore_label, want_grad=False)
+        sums, _ = ops.weighted_ce(lg, target, weight, ignore_label, want_grad=False, keep_thresh=keep_thresh)
+        ctx.keep_thresh = keep_thresh
         if (distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
                 and torch.distributed.get_world_size() > 1):
             torch.distributed.all_reduce(sums)
@@ -637,11 +638,13 @@ class _CEFn(torch.autograd.Function):
         gout = gout.detach().float().reshape(1).contiguous()
         scratch = torch.zeros(2, dtype=torch.float32, device=lg.device)
         gnorm = sums[1:2] if ctx.reduction == "mean" else torch.ones(1, dtype=torch.float32, device=lg.device)
-        _, g = ops.weighted_ce(lg, target, ctx.weight, ctx.ignore, want_grad=True, sums=scratch, gnorm=gnorm, gout=gout)
-        return g, None, None, None, None, None
+        _, g = ops.weighted_ce(lg, target, ctx.weight, ctx.ignore, want_grad=True, sums=scratch, gnorm=gnorm, gout=gout,
+                               keep_thresh=ctx.keep_thresh)
+        return g, None, None, None, None, None, None
 
 
-def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=False, reduction="mean"):
+def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=False, reduction="mean", keep_thresh=None):
     """distributed=True all-reduces (sum w*nll, sum w) over the default process group: only correct together with
-    SUM-reduced gradients (esn.parallel); see utils/losses/loss.py."""
-    return _CEFn.apply(logits, target, weight, ignore_label, distributed, reduction)
+    SUM-reduced gradients (esn.parallel); see utils/losses/loss.py.  keep_thresh: device scalar, pixels whose labelled-class
+    probability exceeds it are ignored (OHEM)."""
+    return _CEFn.apply(logits, target, weight, ignore_label, distributed, reduction, keep_thresh)

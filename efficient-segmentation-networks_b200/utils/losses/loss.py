@@ -10,10 +10,10 @@ import torch.nn as nn
 from esn import ops
 from esn import train as T
 
-__all__ = ["CrossEntropyLoss2d", "FocalLoss2d"]
+__all__ = ["CrossEntropyLoss2d", "FocalLoss2d", "ProbOhemCrossEntropy2d"]
 
 
-def _fused_ce(output, target, w, ignore_label, distributed, reduction):
+def _fused_ce(output, target, w, ignore_label, distributed, reduction, keep_thresh=None):
     ops.require_cuda(output, "CrossEntropyLoss2d")
     if w is not None and w.device != output.device:
         w = w.to(output.device)
@@ -25,7 +25,7 @@ def _fused_ce(output, target, w, ignore_label, distributed, reduction):
     if distributed is None:
         from esn import parallel
         distributed = parallel.is_active()
-    return T.cross_entropy(output, target, w, ignore_label, distributed, reduction)
+    return T.cross_entropy(output, target, w, ignore_label, distributed, reduction, keep_thresh)
 
 
 class CrossEntropyLoss2d(nn.Module):
@@ -85,3 +85,41 @@ class FocalLoss2d(nn.Module):
             target = target[:, 0]
         ce = _fused_ce(output, target, self.ce_fn.weight, self.ignore_index, None, "mean")
         return self.alpha * (1.0 - torch.exp(-ce)) ** self.gamma * ce
+
+
+class ProbOhemCrossEntropy2d(nn.Module):
+    """Drop-in for the reference's ProbOhemCrossEntropy2d (utils/losses/loss.py:163-216; what train.py:147-149 selects for
+    Cityscapes with --use_ohem): online hard example mining.  Same constructor, same `criterion` child (state_dict key
+    `criterion.weight` with use_weight=True, the class-balance weights of loss.py:173-177).
+
+    Three device steps, no host synchronisation (the reference argsorts all pixels and compares on the host twice per step):
+    1. esn_weighted_ce writes the softmax probability of the labelled class per pixel (mask_prob) and counts the valid pixels;
+    2. esn_ohem_threshold finds max(thresh, min_kept-th smallest mask_prob) by an exact radix select (+inf when
+       min_kept > number of valid pixels, where the reference filters nothing);
+    3. the fused weighted-CE kernel (forward sums, and the gradient in backward) skips pixels above that threshold.
+    The threshold carries no gradient, as in the reference (masks are index / comparison results).  down_ratio is stored and
+    unused, as in the reference.  Under esn.parallel the threshold is per rank (each rank mines its own shard)."""
+
+    def __init__(self, ignore_label=255, reduction='mean', thresh=0.6, min_kept=256, down_ratio=1, use_weight=False):
+        super().__init__()
+        if reduction not in ('mean', 'sum'):
+            raise NotImplementedError("reduction=%r is not on the hot path" % (reduction,))
+        self.ignore_label = ignore_label
+        self.thresh = float(thresh)
+        self.min_kept = int(min_kept)
+        self.down_ratio = down_ratio
+        self.reduction = reduction
+        weight = None
+        if use_weight:
+            weight = torch.FloatTensor([0.8373, 0.918, 0.866, 1.0345, 1.0166, 0.9969, 0.9754, 1.0489, 0.8786, 1.0023, 0.9539,
+                                        0.9843, 1.1116, 0.9037, 1.0865, 1.0955, 1.0865, 1.1529, 1.0507])      # loss.py:173-177
+        self.criterion = nn.CrossEntropyLoss(reduction=reduction, weight=weight, ignore_index=ignore_label)
+
+    def forward(self, pred, target):
+        ops.require_cuda(pred, "ProbOhemCrossEntropy2d")
+        target = target.long().contiguous()
+        lg = pred.detach().contiguous()
+        prob = torch.empty(target.shape, dtype=torch.float32, device=pred.device)
+        sums, _ = ops.weighted_ce(lg, target, None, self.ignore_label, prob_out=prob)      # sums[1] = number of valid pixels
+        thr = ops.ohem_threshold(prob, self.min_kept, self.thresh, sums[1:2])
+        return _fused_ce(pred, target, self.criterion.weight, self.ignore_label, None, self.reduction, keep_thresh=thr)

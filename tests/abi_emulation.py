@@ -279,6 +279,12 @@ def esn_weighted_ce(ref):
     valid = y != p.ignore_label
     ys = torch.where(valid, y, torch.zeros_like(y))
     logp = torch.log_softmax(x, 1)
+    if p.prob_out or p.keep_thresh:      # OHEM: probability of the labelled class (1 where ignored), optional threshold mask
+        py = logp.gather(1, ys.unsqueeze(1)).squeeze(1).exp().masked_fill(~valid, 1.0)
+        if p.prob_out:
+            _buf(p.prob_out, n * h * w, torch.float32, 4).view(n, h, w).copy_(py)
+        if p.keep_thresh:
+            valid = valid & (py <= _buf(p.keep_thresh, 1, torch.float32, 4)[0])
     wi = wv[ys] * valid.float()
     nll = -logp.gather(1, ys.unsqueeze(1)).squeeze(1)
     sums = _buf(p.sums, 2, torch.float32, 4)
@@ -291,6 +297,18 @@ def esn_weighted_ce(ref):
         if p.gnorm:
             g = g / _buf(p.gnorm, 1, torch.float32, 4)[0]
         store(tensor(p.dlogits), g)
+    return 0
+
+
+def esn_ohem_threshold(prob, n, min_kept, thresh, num_valid, out, workspace):
+    """include/esn.h: +inf if min_kept > *num_valid (or min_kept <= 0), else max(thresh, min(n, min_kept)-th smallest prob)."""
+    pv = _buf(prob.value, n, torch.float32, 4)
+    nv = float(_buf(num_valid.value, 1, torch.float32, 4)[0])
+    o = _buf(out.value, 1, torch.float32, 4)
+    if min_kept > nv or nv <= 0 or min_kept <= 0:
+        o[0] = float("inf")
+    else:
+        o[0] = max(float(thresh.value if hasattr(thresh, "value") else thresh), float(torch.sort(pv).values[min(n, min_kept) - 1]))
     return 0
 
 
@@ -313,6 +331,7 @@ ENTRY = {
     "esn_head_convt2x2": esn_head_convt2x2, "esn_head_bilinear": esn_head_bilinear,
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
     "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast, "esn_weighted_ce": esn_weighted_ce,
+    "esn_ohem_threshold": esn_ohem_threshold,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 

@@ -178,6 +178,23 @@ def test_losses_through_the_abi_match_reference(golden):
     assert list(FocalLoss2d(weight=w).state_dict().keys()) == ["ce_fn.weight"]       # the reference's only key
 
 
+@pytest.mark.parametrize("case", ["kth_above_thresh", "thresh_wins", "nothing_filtered", "unweighted"])
+def test_ohem_loss_through_the_abi_matches_reference(golden, case):
+    """utils.losses.loss.ProbOhemCrossEntropy2d (drop-in for loss.py:163-216): value and gradient against the reference
+    class's fp64 golden (tools/make_golden_ohem.py), the three entry points answered by the C-ABI model."""
+    from utils.losses.loss import ProbOhemCrossEntropy2d
+    g, o = golden("loss"), golden("ohem")
+    thresh, min_kept, use_weight = o[case + "_cfg"]
+    crit = ProbOhemCrossEntropy2d(ignore_label=255, thresh=float(thresh), min_kept=int(min_kept), use_weight=bool(use_weight))
+    assert list(crit.state_dict().keys()) == (["criterion.weight"] if use_weight else [])
+    logits = torch.from_numpy(g["logits"]).float().requires_grad_(True)
+    with emulate_abi():
+        loss = crit(logits, torch.from_numpy(g["labels"]))
+        loss.backward()
+    assert abs(loss.item() - o[case + "_loss"][0]) < 1e-5 * abs(o[case + "_loss"][0])
+    assert _rel(logits.grad, torch.from_numpy(o[case + "_grad"])) < 1e-5
+
+
 def test_pending_gpu_test_code_runs_on_the_abi_model():
     """tests/preflight_gpu_tests_on_cpu.py: the functions of tests/test_zz_*_gpu.py (not yet run on a B200) executed on
     the CPU against the C-ABI model, in a subprocess because the script patches torch globally."""

@@ -92,3 +92,19 @@ def test_focal_loss_matches_reference(golden):
     l, gr = oloss.focal(logits, lab, w, 255, alpha=0.5, gamma=2)
     assert abs(l.item() - g["focal_loss"][0]) < 1e-12
     assert np.abs(gr.numpy() - g["focal_grad"]).max() < 1e-14
+
+
+@pytest.mark.parametrize("case", ["kth_above_thresh", "thresh_wins", "nothing_filtered", "unweighted"])
+def test_ohem_matches_reference(golden, case):
+    """oracle/loss.py:ohem against the unmodified reference ProbOhemCrossEntropy2d (tools/make_golden_ohem.py), fp64."""
+    g, o = golden("loss"), golden("ohem")
+    thresh, min_kept, use_weight = o[case + "_cfg"]
+    w = torch.tensor(oloss.OHEM_CLASS_WEIGHTS, dtype=torch.float32).double() if use_weight else None
+    l, gr, thr = oloss.ohem(torch.from_numpy(g["logits"]), torch.from_numpy(g["labels"]), w, 255, float(thresh), int(min_kept))
+    assert abs(l.item() - o[case + "_loss"][0]) < 1e-12
+    assert np.abs(gr.numpy() - o[case + "_grad"]).max() < 1e-14
+    assert (thr is None) == (case == "nothing_filtered")
+    if case == "kth_above_thresh":
+        assert thr > thresh
+    if case == "thresh_wins":
+        assert thr == thresh
