@@ -406,9 +406,11 @@ def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32, alig
         dl = holder["dlogits"]
 
         def run(ex, dst):
-            assert ex is None
+            # the logits are the only consumer of the scores: their gradient is written, not accumulated (when the scores
+            # are a channel slice of a wider buffer, `dst` is that slice of the zero-filled gradient buffer)
+            assert ex is None or ex is dst
             n, c, h, w = scores.t.shape
-            dlow = ops.new_act(n, c, h, w, scores.t.dtype, dl.device, c_alloc=scores.t.stride(3))
+            dlow = dst if dst is not None else ops.new_act(n, c, h, w, scores.t.dtype, dl.device, c_alloc=scores.t.stride(3))
             a, b = ops.tdesc(dl), ops.tdesc(dlow)
             a.layout, a.c_stride = L.ESN_NCHW, 0
             if align_corners:

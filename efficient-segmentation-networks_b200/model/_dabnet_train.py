@@ -106,11 +106,18 @@ def dabnet_train_forward(model, input):
     for i, blk in enumerate(blocks):
         y = _dab_module(tape, blk, y, out=cat2.slice(0, 128) if i == len(blocks) - 1 else None)
     ops.affine_act(d3, None, None, None, ACT_NONE, out=cat2.t[:, 256:259])
-    c2 = _bnprelu(tape, model.bn_prelu_3, cat2)
-
     classes = model.classifier[0].conv.out_channels
     hh, ww = d3.shape[2:]
-    scores = T.V(ops.new_act(n, classes, hh, ww, dt, dev, c_alloc=32))
-    _conv(tape, model.classifier[0], c2, out=scores)
+    if dt == torch.bfloat16:
+        # 1x1 classifier 259 -> 19 on the tensor cores in all three directions (forward, input gradient, weight gradient):
+        # the BNPReLU output lives in a 320-channel buffer with a zero tail, the scores in a 32-channel one (zero weight rows)
+        c2 = _bnprelu(tape, model.bn_prelu_3, cat2, out=T.V(ops.new_act(n, 259, hh, ww, dt, dev, c_alloc=320, zero=True)))
+        wide = T.V(ops.new_act(n, 32, hh, ww, dt, dev))
+        _convT(model.classifier[0].conv, 320, 32).forward(tape, c2, out=wide)
+        scores = wide.slice(0, classes)
+    else:
+        c2 = _bnprelu(tape, model.bn_prelu_3, cat2)
+        scores = T.V(ops.new_act(n, classes, hh, ww, dt, dev, c_alloc=32))
+        _conv(tape, model.classifier[0], c2, out=scores)
     logits, holder = T.bilinear_logits(tape, scores, H, W, torch.float32)
     return logits, tape, holder

@@ -26,7 +26,7 @@ def test_ohem_threshold_is_the_exact_kth_value(n, k):
     kth = torch.sort(p).values[min(n, k) - 1].item()
     for thresh in (0.0, 0.5):
         out = ops.ohem_threshold(p, k, thresh, nv)
-        assert out.item() == max(thresh, kth), (out.item(), kth)
+        assert out.item() == max(float(np.float32(thresh)), kth), (out.item(), kth)
     # min_kept larger than the number of valid pixels, or not positive: nothing is filtered
     assert ops.ohem_threshold(p, n + 1, 0.5, nv).item() == float("inf")
     assert ops.ohem_threshold(p, 0, 0.5, nv).item() == float("inf")
@@ -68,7 +68,7 @@ def test_ohem_full_size_properties(dtype):
         assert sums[1].item() == valid.sum().item()
         kth = torch.kthvalue(prob.flatten(), min_kept).values.item()
         thr = ops.ohem_threshold(prob, min_kept, thresh, sums[1:2]).item()
-        assert thr == max(thresh, kth)
+        assert thr == max(float(np.float32(thresh)), kth)          # the threshold is an fp32 device scalar
         keep = valid & (prob <= thr)
         assert keep.sum().item() >= min_kept
         tgt = torch.where(keep, lab, torch.full_like(lab, 255))
