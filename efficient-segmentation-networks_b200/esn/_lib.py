@@ -106,6 +106,10 @@ SYMBOLS = {
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
+    "esn_dot_nc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
+    "esn_scale_add_nc": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_void_p, C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
+    "esn_maxpool3x3s2_idx_bwd": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
+    "esn_max_unpool2x2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.c_void_p]),
     "esn_ohem_workspace_bytes": (C.c_int64, []),
     "esn_ohem_threshold": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esn_channel_stats": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_int32, C.c_void_p]),

@@ -126,8 +126,9 @@ class ConvT:
             self._key = key
         return self.fwd_prep, self.dgrad_prep
 
-    def forward(self, tape, x, out=None, residual=None, need_dx=True, dtype=None):
-        """x: V (or a raw NCHW input tensor wrapped in V with need_dx=False)."""
+    def forward(self, tape, x, out=None, residual=None, need_dx=True, dtype=None, precomputed=False):
+        """x: V (or a raw NCHW input tensor wrapped in V with need_dx=False).  precomputed: `out` already holds the conv
+        result (written by a fused kernel, e.g. ENet's conv || max-pool stem); only the backward is recorded."""
         fwd_prep, dgrad_prep = self.preps()
         xt = x.t if not self.cin_pad else ops.widen(x.t, self.cin_pad)
         cin_real, cout_real = self.conv.in_channels, self.conv.out_channels
@@ -136,7 +137,9 @@ class ConvT:
             ho, wo = fwd_prep.out_hw(h, w)
             out = ops.new_act(n, fwd_prep.cout, ho, wo, dtype or (xt.dtype if ops.is_nhwc(xt) else torch.float32), xt.device)
         y = out if isinstance(out, V) else V(out)      # `out` may be a channel slice (V) of a concat buffer
-        if (not ops.is_nhwc(xt) and xt.dtype == torch.float32 and xt.is_contiguous() and fwd_prep.cin == 3 and residual is None
+        if precomputed:
+            pass
+        elif (not ops.is_nhwc(xt) and xt.dtype == torch.float32 and xt.is_contiguous() and fwd_prep.cin == 3 and residual is None
                 and (fwd_prep.kh, fwd_prep.kw, fwd_prep.stride) == (3, 3, 2) and (fwd_prep.pad_h, fwd_prep.pad_w) in ((0, 0), (1, 1))
                 and fwd_prep.cout % 4 == 0 and fwd_prep.cout <= 32 and y.t.shape[1] == fwd_prep.cout and y.t.stride(3) % 4 == 0
                 and (fwd_prep.pad_h == 0 or not ((xt.shape[2] | xt.shape[3]) & 1))):
@@ -286,8 +289,11 @@ class BNActT:
     """Train-mode nn.BatchNorm2d followed by PReLU / ReLU / nothing; or, with bn=None, the
     activation alone (its backward then also yields sum(dz) = the bias gradient of a preceding conv)."""
 
-    def __init__(self, bn, act, prelu=None):
-        self.bn, self.act, self.prelu = bn, act, prelu
+    def __init__(self, bn, act, prelu=None, alpha_sink=None):
+        """prelu: nn.PReLU with one slope per channel, or ONE slope for all channels (nn.PReLU(), ENet: its gradient is the
+        sum over channels).  alpha_sink(param, grad): where the slope gradient goes instead of the tape -- a SharedParamGrad
+        when one PReLU module serves several call sites of a block (ENet.py:53-89)."""
+        self.bn, self.act, self.prelu, self.alpha_sink = bn, act, prelu, alpha_sink
 
     def forward(self, tape, x, out=None):
         xt = x.t
@@ -295,6 +301,9 @@ class BNActT:
         dev = xt.device
         bn = self.bn
         alpha = None if self.prelu is None else self.prelu.weight.detach()
+        one_slope = alpha is not None and alpha.numel() == 1 and c > 1
+        if one_slope:
+            alpha = alpha.expand(c).contiguous()
         scale = shift = mean = invstd = None
         if bn is not None:
             sums = _f64zeros(2 * c, dev)
@@ -351,10 +360,73 @@ class BNActT:
                 tape.add_param_grad(bn.weight, dgamma)
                 tape.add_param_grad(bn.bias, dbeta)
             if prelu is not None:
-                tape.add_param_grad(prelu.weight, dalpha)
+                ga = dalpha.sum().reshape(1) if one_slope else dalpha
+                (self.alpha_sink or tape.add_param_grad)(prelu.weight, ga)
 
         tape.push(bwd)
         return y
+
+
+class SharedParamGrad:
+    """One parameter used at several places of a block (ENet's shared activation module): the contributions are summed here
+    and handed to the tape ONCE, after the last of them in backward order -- create it BEFORE the block's first use in the
+    forward (its flush step is pushed first, so it runs last), so that data-parallel gradient buckets see each parameter
+    exactly once per step."""
+
+    def __init__(self, tape, param):
+        self.tape, self.param, self.total = tape, param, None
+        tape.push(self.flush)
+
+    def __call__(self, param, g):
+        assert param is self.param
+        self.total = g if self.total is None else self.total + g
+
+    def flush(self):
+        if self.total is not None:
+            self.tape.add_param_grad(self.param, self.total)
+            self.total = None
+
+
+def maxpool3x3s2_idx(tape, x):
+    """MaxPool2d(3, 2, 1, return_indices=True) (ENet.py:126-130): returns (V pooled, int32 indices); the backward is a
+    deterministic gather over the input pixels."""
+    yt, idx = ops.maxpool3x3s2_idx(x.t)
+    y = V(yt)
+
+    def bwd():
+        dy = y.g
+
+        def run(ex, dst):
+            n, c, h, w = x.t.shape
+            dx = dst if dst is not None else (ex if ex is not None else ops.new_act(n, c, h, w, dy.dtype, dy.device))
+            a, b = ops.tdesc(dy), ops.tdesc(dx)
+            ops._call(L.lib.esn_maxpool3x3s2_idx_bwd, "esn_maxpool3x3s2_idx_bwd",
+                      (C.byref(a), C.c_void_p(idx.data_ptr()), C.byref(b), int(ex is not None)), 2 * ops._nbytes(dx))
+            return dx
+        x.add_grad(run)
+    tape.push(bwd)
+    return y, idx
+
+
+def max_unpool2x2(tape, v, idx):
+    """MaxUnpool2d(2)(v, idx) (ENet.py:225, 262); backward: every pooled cell reads the gradient at its scatter position."""
+    y = V(ops.max_unpool2x2(v.t, idx))
+
+    def bwd():
+        dy = y.g
+
+        def run(ex, dst):
+            n, c, h, w = v.t.shape
+            dv = ops.new_act(n, c, h, w, dy.dtype, dy.device)
+            a, b = ops.tdesc(dy), ops.tdesc(dv)
+            ops._call(L.lib.esn_max_unpool2x2_bwd, "esn_max_unpool2x2_bwd", (C.byref(a), C.c_void_p(idx.data_ptr()), C.byref(b)),
+                      2 * ops._nbytes(dv))
+            if ex is None and dst is None:
+                return dv
+            return ops.affine_act(dv, None, None, None, L.ACT_NONE, out=dst, residual=ex)
+        v.add_grad(run)
+    tape.push(bwd)
+    return y
 
 
 def add(tape, a, b, out=None):
@@ -650,3 +722,54 @@ def cross_entropy(logits, target, weight=None, ignore_label=255, distributed=Fal
     SUM-reduced gradients (esn.parallel); see utils/losses/loss.py.  keep_thresh: device scalar, pixels whose labelled-class
     probability exceeds it are ignored (OHEM)."""
     return _CEFn.apply(logits, target, weight, ignore_label, distributed, reduction, keep_thresh)
+
+
+def fglo(tape, fc, x, out=None, residual=None):
+    """CGNet's global-context gate FGlo (CGNet.py:173-191): y = x * sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2) (+ residual).
+    The activation-sized work is three kernels forward (partial sums, gate multiply) and two backward (sum_hw dy*x, dy*g + the
+    pooled-mean gradient); the two nn.Linear layers act on (N, C) vectors -- a few kFLOP -- and go through torch autograd on a
+    local graph, which also yields their weight / bias gradients.  fc = the module's nn.Sequential(Linear, ReLU, Linear, Sigmoid)."""
+    xt = x.t
+    n, c, h, w = xt.shape
+    dev = xt.device
+    dx_ = ops.tdesc(xt)
+    chunks = L.lib.esn_global_avgpool_chunks(C.byref(dx_))
+    sums = torch.empty((chunks, n, c), dtype=torch.float32, device=dev)
+    ops._call(L.lib.esn_global_avgpool, "esn_global_avgpool", (C.byref(dx_), C.c_void_p(sums.data_ptr())), ops._nbytes(xt))
+    lin1, lin2 = fc[0], fc[2]
+    params = [lin1.weight, lin1.bias, lin2.weight, lin2.bias]
+    with torch.enable_grad(), torch.autocast("cuda", enabled=False):      # the gate is fp32 in every precision mode, as in inference
+        pooled = (sums.sum(0) / float(h * w)).requires_grad_(True)
+        gate = torch.sigmoid(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(pooled, lin1.weight.float(), lin1.bias.float())),
+                                                        lin2.weight.float(), lin2.bias.float()))
+    g = gate.detach().contiguous()
+    y = out if isinstance(out, V) else V(out if out is not None else ops.new_act(n, c, h, w, xt.dtype, dev))
+    dy_ = ops.tdesc(y.t)
+    dr_ = ops.tdesc(residual.t) if residual is not None else ops._NULL
+    ops._call(L.lib.esn_scale_add_nc, "esn_scale_add_nc", (C.byref(dx_), C.c_void_p(g.data_ptr()), None, C.byref(dr_), C.byref(dy_)),
+              ops._nbytes(xt) + ops._nbytes(y.t) + (ops._nbytes(residual.t) if residual is not None else 0))
+
+    def bwd():
+        dy = y.g
+        dg = torch.zeros((n, c), dtype=torch.float32, device=dev)
+        a, b = ops.tdesc(dy), ops.tdesc(xt)
+        ops._call(L.lib.esn_dot_nc, "esn_dot_nc", (C.byref(a), C.byref(b), C.c_void_p(dg.data_ptr())), ops._nbytes(dy) + ops._nbytes(xt))
+        grads = torch.autograd.grad(gate, [pooled] + params, dg)
+        dpool = (grads[0] / float(h * w)).contiguous()
+        for p_, g_ in zip(params, grads[1:]):
+            tape.add_param_grad(p_, g_)
+        if residual is not None:
+            residual.add_grad(lambda ex, dst: dy if (ex is None and dst is None) else
+                              ops.affine_act(dy, None, None, None, L.ACT_NONE, out=dst, residual=ex))
+
+        def run(ex, dst):
+            dx = dst if dst is not None else ops.new_act(n, c, h, w, dy.dtype, dev)
+            e = ops.tdesc(ex) if ex is not None else ops._NULL
+            o = ops.tdesc(dx)
+            ops._call(L.lib.esn_scale_add_nc, "esn_scale_add_nc",
+                      (C.byref(a), C.c_void_p(g.data_ptr()), C.c_void_p(dpool.data_ptr()), C.byref(e), C.byref(o)),
+                      2 * ops._nbytes(dy) + (ops._nbytes(ex) if ex is not None else 0))
+            return dx
+        x.add_grad(run)
+    tape.push(bwd)
+    return y

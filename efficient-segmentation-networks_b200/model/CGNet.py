@@ -323,6 +323,11 @@ class CGNet(PrepMixin, nn.Module):
         return scores, (h, w), dt
 
     def forward(self, input):
+        if self.training:
+            # batch-statistics BatchNorm and the recorded backward (esn/train.py); one autograd node for the net
+            from esn import train as T
+            from model._cgnet_train import cgnet_train_forward
+            return T.run_network(self, lambda inp: cgnet_train_forward(self, inp), input)
         scores, (h, w), dt = self._scores(input)
         ldt = torch.bfloat16 if dt == torch.bfloat16 else torch.float32
         return ops.head_bilinear(scores, scores.shape[1], h, w, True, False, ldt)[0]

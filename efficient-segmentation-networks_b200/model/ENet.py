@@ -272,6 +272,11 @@ class ENet(PrepMixin, nn.Module):
         return s[:, :classes], classes
 
     def forward(self, x):
+        if self.training:
+            # batch-statistics BatchNorm, Dropout2d and the recorded backward (esn/train.py); one autograd node for the net
+            from esn import train as T
+            from model._enet_train import enet_train_forward
+            return T.run_network(self, lambda inp: enet_train_forward(self, inp), x)
         s, classes = self._scores(x)
         n, _, h, w = s.shape
         ldt = torch.bfloat16 if s.dtype == torch.bfloat16 else torch.float32

@@ -549,6 +549,11 @@ class ESPNet(PrepMixin, nn.Module):
         return ops.widen(y, 20), P
 
     def forward(self, input):
+        if self.training:
+            # batch-statistics BatchNorm and the recorded backward (esn/train.py); one autograd node for the net
+            from esn import train as T
+            from model._espnet_train import espnet_train_forward
+            return T.run_network(self, lambda inp: espnet_train_forward(self, inp), input)
         y, P = self.features(input)
         ldt = torch.bfloat16 if y.dtype == torch.bfloat16 else torch.float32
         return ops.head_convt2x2(y, P["head_w"], P["head_b"], P["classes"], True, False, ldt)[0]

@@ -174,11 +174,22 @@ typedef struct EsnUnpool {
   int32_t _pad;
 } EsnUnpool;
 int esn_max_unpool2x2(const EsnUnpool* p, void* stream);
+/* Their backward passes (training; autograd of the same modules reached from loss.backward(), train.py:353):
+ * esn_maxpool3x3s2_idx_bwd: dx[n,h,w,c] (+)= sum of dy over the windows whose recorded arg-max is (h,w) -- a gather over the
+ * input pixels (deterministic, no atomics although the windows overlap); accumulate != 0 adds to dx.
+ * esn_max_unpool2x2_bwd: dv[n,i,j,c] = dy at the position idx[n,i,j,c] of the (2Hp x 2Wp) output plane -- every pooled cell,
+ * including cells that lost a collision in the forward scatter, as torch's max_unpool2d backward does. */
+int esn_maxpool3x3s2_idx_bwd(const EsnTensor* dy, const int32_t* idx, const EsnTensor* dx, int32_t accumulate, void* stream);
+int esn_max_unpool2x2_bwd(const EsnTensor* dy, const int32_t* idx, const EsnTensor* dv, void* stream);
 
 /* CGNet global-context gate FGlo (CGNet.py:173-191): x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2), and the
  * block's residual (CGNet.py:258-260).  esn_global_avgpool: per-chunk partial sums over H*W;
  * esn_fglo_gate: gate[n][c] from the sums and the two nn.Linear layers (row-major weights);
  * esn_scale_nc: y = x * gate[n][c] (+ residual). */
+/* Backward of the gate (training): esn_dot_nc: out[n][c] += sum_hw a*b (fp32 atomics, out zeroed by the caller) = d gate;
+ * esn_scale_add_nc: y = a * s[n][c] + t[n][c] (+ extra) = d x (t may be NULL: plain per-(n,c) scaling, the forward gate). */
+int esn_dot_nc(const EsnTensor* a, const EsnTensor* b, float* out, void* stream);
+int esn_scale_add_nc(const EsnTensor* a, const float* s, const float* t, const EsnTensor* extra, const EsnTensor* y, void* stream);
 int esn_global_avgpool_chunks(const EsnTensor* x);   /* host query: number of partial-sum chunks K for this view */
 int esn_global_avgpool(const EsnTensor* x, float* sums /* [K][N][C] partial sums, no atomics */, void* stream);
 typedef struct EsnFGlo {

@@ -223,7 +223,7 @@ def _train_step(name, spec, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("net", ["DABNet", "FastSCNN", "ESPNet_v2", "ERFNet"])
+@pytest.mark.parametrize("net", ["DABNet", "FastSCNN", "ESPNet_v2", "ERFNet", "ENet", "ESPNet", "CGNet"])
 def test_training_matches_reference_fp64(spec, golden, dtype, net):
     """loss / logits / every parameter gradient against the reference's fp64 run (tests/golden; dropout off)."""
     g = golden(net)
@@ -299,7 +299,12 @@ def test_training_matches_reference_fp64(spec, golden, dtype, net):
         y = nets.forward(net, sd, x, train=True)
         l = F.cross_entropy(y.float(), lab, torch.tensor(fixture.CLASS_WEIGHTS, device="cuda"), ignore_index=255)
     l.backward()
-    ref_errs = sorted(abs(sd[k].grad.double().norm().item() - gn) / gn
+    def oracle_grad(k):
+        g_ = sd[k].grad
+        if g_ is None:      # ENet: one activation module per block; the oracle reads its last alias (out_prelu.weight)
+            g_ = sd[k.split(".")[0] + ".out_prelu.weight"].grad
+        return g_
+    ref_errs = sorted(abs(oracle_grad(k).double().norm().item() - gn) / gn
                       for k, (gn, _, wn) in stats.items() if gn >= 1e-10 * max(wn, 1e-30))
     r_p90, r_med = ref_errs[int(0.9 * len(ref_errs))], ref_errs[len(ref_errs) // 2]
     print("   torch bf16-autocast on the same graph: median %.3e p90 %.3e worst %.3e" % (r_med, r_p90, ref_errs[-1]))
@@ -478,3 +483,38 @@ def test_eval_after_graph_replays_sees_the_new_weights(spec, net):
     l_eager = crit(m(x), lab)
     l_graph = gs()
     assert l_eager.item() > l_graph.item() - 0.5 and l_eager.item() == l_eager.item()
+
+
+def test_enet_pool_unpool_backward_matches_torch():
+    """esn_maxpool3x3s2_idx_bwd / esn_max_unpool2x2_bwd (ENet's MaxPool2d(3,2,1,return_indices) / MaxUnpool2d(2)) against
+    torch autograd on the CPU, incl. tied maxima, overlapping windows, odd sizes and both channel-vector widths."""
+    from esn import ops, train as T
+    torch.manual_seed(11)
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        for c, h, w in ((16, 12, 20), (4, 9, 7), (3, 6, 10)):
+            x = torch.randn(2, c, h, w).round_()            # small integers: many ties, exact in bf16
+            xr = x.clone().requires_grad_(True)
+            pooled, idx = F.max_pool2d(xr, 3, 2, 1, return_indices=True)
+            gy = torch.randn_like(pooled).to(dt).float()
+            gx, = torch.autograd.grad(pooled, xr, gy)
+            tape = T.Tape()
+            xv = T.V(_nhwc(x.cuda(), dt, ops))
+            y, i32 = T.maxpool3x3s2_idx(tape, xv)
+            assert torch.equal(y.t.float().cpu(), pooled.detach())
+            assert torch.equal(i32.permute(0, 3, 1, 2).cpu().long(), idx)
+            y._g = _nhwc(gy.cuda(), dt, ops)
+            tape.backward()
+            assert _rel(xv.g.float().cpu(), gx) < tol, (dt, c, h, w)
+            if h % 2 == 0 and w % 2 == 0:
+                # un-pool with those indices: forward = last writer wins (the CPU reference), backward = gather
+                v = torch.randn(2, c, h // 2, w // 2).to(dt).float().requires_grad_(True)
+                up = F.max_unpool2d(v, idx, 2)
+                gu = torch.randn_like(up).to(dt).float()
+                gv, = torch.autograd.grad(up, v, gu)
+                tape = T.Tape()
+                vv = T.V(_nhwc(v.detach().cuda(), dt, ops))
+                u = T.max_unpool2x2(tape, vv, i32)
+                assert torch.equal(u.t.float().cpu(), up.detach())
+                u._g = _nhwc(gu.cuda(), dt, ops)
+                tape.backward()
+                assert _rel(vv.g.float().cpu(), gv) < tol, (dt, c, h, w)

@@ -68,7 +68,7 @@ def main():
                     out[tag + "_logits_s4"] = y[:, :, ::4, ::4].contiguous().numpy()
                     out[tag + "_sum"] = np.array([y.double().sum().item(), y.double().abs().sum().item()])
                 out[tag + "_argmax"] = np.argmax(y.numpy(), axis=1).astype(np.uint8)
-        if name not in ("ERFNet", "DABNet", "FastSCNN", "ESPNet_v2"):          # inference-only nets so far: no training golden
+        if name not in ("ERFNet", "DABNet", "FastSCNN", "ESPNet_v2", "ENet", "CGNet", "ESPNet"):      # inference-only nets: no training golden
             np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
             print(name, "golden written:", {k: v.shape for k, v in out.items()})
             continue
