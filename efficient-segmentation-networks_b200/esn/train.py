@@ -22,10 +22,11 @@ from .prep import weights_generation
 class V:
     """An activation and its gradient slot.  A V may be a channel slice of a wider (concat) V, in
     which case its gradient is the same slice of the parent's gradient buffer."""
-    __slots__ = ("t", "_g", "parent", "lo", "hi")
+    __slots__ = ("t", "_g", "parent", "lo", "hi", "_own")
 
     def __init__(self, t, parent=None, lo=0, hi=0):
         self.t, self._g, self.parent, self.lo, self.hi = t, None, parent, lo, hi
+        self._own = False      # _g is a buffer of this V alone (safe to accumulate into in place)
 
     @property
     def g(self):
@@ -47,6 +48,17 @@ class V:
             if root._g is None:     # gradient buffer of the whole concat tensor, zero-filled once
                 n, c, h, w = root.t.shape
                 root._g = ops.new_act(n, c, h, w, root.t.dtype, root.t.device, c_alloc=root.t.stride(3), zero=True)
+                root._own = True
+            elif not root._own:
+                # the root's gradient was handed over by a whole-tensor consumer and may be shared with another V (a
+                # residual add passes the SAME tensor to both operands): slices accumulate in place, so take a private copy
+                # first (ESPNet's block: BN(input + cat[...]) -- the in-place sums into cat's slices would otherwise leak
+                # into the gradient of `input`)
+                n, c, h, w = root.t.shape
+                priv = ops.new_act(n, c, h, w, root._g.dtype, root._g.device, c_alloc=root.t.stride(3),
+                                   zero=root.t.stride(3) != c)
+                root._g = ops.affine_act(root._g, None, None, None, L.ACT_NONE, out=priv)
+                root._own = True
             view = self.g
             out = fn(view, view)
             assert out.data_ptr() == view.data_ptr()
