@@ -508,9 +508,12 @@ class ESPNet(PrepMixin, nn.Module):
                         alpha=self.conv.act.weight.detach().float().to(device)),
         )
         w = self.classifier.weight.detach().to(device=device, dtype=torch.float32)      # (Cin, classes, 2, 2)
-        packed = torch.zeros((2, 2, 20, 32), dtype=torch.float32, device=device)
-        packed[:, :, :w.shape[0], :classes] = w.permute(2, 3, 0, 1)
-        P["head_w"], P["head_b"] = packed.contiguous(), torch.zeros(32, dtype=torch.float32, device=device)
+        if classes == 19:
+            packed = torch.zeros((2, 2, 20, 32), dtype=torch.float32, device=device)
+            packed[:, :, :w.shape[0], :classes] = w.permute(2, 3, 0, 1)
+            P["head_w"], P["head_b"] = packed.contiguous(), torch.zeros(32, dtype=torch.float32, device=device)
+        else:
+            P["cls_t"] = ops.ConvPrep(self.classifier, device=device)
         return P
 
     def features(self, input):
@@ -521,8 +524,8 @@ class ESPNet(PrepMixin, nn.Module):
         dt, dev = ops.compute_dtype(input), input.device
         P = self.prep(dev)
         classes = P["classes"]
-        if classes != 19 or self.conv.conv.in_channels != 2 * 19:
-            raise NotImplementedError("ESPNet: the decoder is laid out for 19 classes (ESPNet.py:345 hard-codes 19 + classes)")
+        if classes > 32:
+            raise NotImplementedError("ESPNet: the decoder buffers are laid out for at most 32 classes, got %d" % classes)
         tc = dt == torch.bfloat16
         m_e = P["m_e"]
         cat_e = ops.new_act(n, m_e.width, h // 2, w // 2, dt, dev, zero=True)
@@ -546,7 +549,20 @@ class ESPNet(PrepMixin, nn.Module):
             ops.conv2d(cat_e, P["convp"], out=ops.widen(y, 32))
         else:
             ops.conv2d(cat_e, P["conv"], out=y)
-        return ops.widen(y, 20), P
+        return (ops.widen(y, 20) if classes == 19 else y), P
+
+    def _head(self, y, P, want_logits, want_mask):
+        """The closing ConvTranspose2d(classes, classes, 2, stride 2) (ESPNet.py:353) -> NCHW logits and / or the argmax mask:
+        the fused 2x2 transposed-conv head for the 19-class layout, otherwise (any other class count, ESPNet.py:350 takes it
+        as a constructor argument) the transposed conv through esn_conv2d_direct followed by the same-size head kernel."""
+        ldt = torch.bfloat16 if y.dtype == torch.bfloat16 else torch.float32
+        classes = P["classes"]
+        if classes == 19:
+            return ops.head_convt2x2(y, P["head_w"], P["head_b"], classes, want_logits, want_mask, ldt)
+        n, _, h, w = y.shape
+        s = ops.new_act(n, classes, 2 * h, 2 * w, y.dtype, y.device, c_alloc=(classes + 7) // 8 * 8)
+        ops.conv2d(y, P["cls_t"], out=s)
+        return ops.head_bilinear(s, classes, 2 * h, 2 * w, want_logits, want_mask, ldt)
 
     def forward(self, input):
         if self.training:
@@ -555,12 +571,10 @@ class ESPNet(PrepMixin, nn.Module):
             from model._espnet_train import espnet_train_forward
             return T.run_network(self, lambda inp: espnet_train_forward(self, inp), input)
         y, P = self.features(input)
-        ldt = torch.bfloat16 if y.dtype == torch.bfloat16 else torch.float32
-        return ops.head_convt2x2(y, P["head_w"], P["head_b"], P["classes"], True, False, ldt)[0]
+        return self._head(y, P, True, False)[0]
 
     @torch.no_grad()
     def predict_mask(self, input, with_logits=False):
         y, P = self.features(input)
-        ldt = torch.bfloat16 if y.dtype == torch.bfloat16 else torch.float32
-        logits, mask = ops.head_convt2x2(y, P["head_w"], P["head_b"], P["classes"], with_logits, True, ldt)
+        logits, mask = self._head(y, P, with_logits, True)
         return (logits, mask) if with_logits else mask

@@ -207,3 +207,28 @@ def test_pending_gpu_test_code_runs_on_the_abi_model():
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("PASS", "FAIL"))]
     assert r.returncode == 0 and lines and not any(ln.startswith("FAIL") for ln in lines), "\n".join(lines[-30:]) + r.stderr[-1500:]
     assert sum(ln.startswith("PASS") for ln in lines) >= 20
+
+
+@pytest.mark.parametrize("classes", [11, 32])
+def test_espnet_with_another_class_count(classes):
+    """build_model('ESPNet', C) for C != 19 (ESPNet.py:350 takes the class count as an argument; only the 19-class layout has
+    the fused 2x2 transposed-conv head, the others close with esn_conv2d_direct + the same-size head kernel): fp32 and bf16
+    against the oracle on the model's own seeded weights, through the C-ABI model."""
+    from builders.model_builder import build_model
+    m = build_model("ESPNet", classes)
+    sd = fixture.randomize_state_dict(m.state_dict(), 77)
+    m.load_state_dict(sd)
+    m = m.eval()
+    x = fixture.make_input(1, 64, 128)
+    with torch.no_grad():
+        ref = nets.forward("ESPNet", sd, x)
+        with emulate_abi() as calls:
+            logits, mask = m.predict_mask(x, with_logits=True)
+        assert logits.shape == (1, classes, 64, 128) and _rel(logits, ref) < 1e-5
+        assert (mask.numpy() == nets.argmax_mask(ref)).mean() > 0.9999
+        assert "esn_head_convt2x2" not in [n for n, _ in calls]
+        with emulate_abi(bf16=True):
+            yb = m(x)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            rel_ac = _rel(nets.forward("ESPNet", sd, x).float(), ref)
+    assert yb.dtype == torch.bfloat16 and _rel(yb.float(), ref) < max(5e-2, 1.5 * rel_ac)

@@ -173,3 +173,24 @@ def test_full_size_properties_erfnet(spec):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             yb = m(x)
     assert _rel(yb.float(), y) < BF16_LOGIT_TOL
+
+
+@pytest.mark.parametrize("classes", [11, 32])
+def test_espnet_with_another_class_count(classes):
+    """ESPNet takes the class count as a constructor argument (ESPNet.py:350); only the 19-class layout has the fused 2x2
+    transposed-conv head.  Same checks as the golden tests, against the oracle on the model's own seeded weights."""
+    from builders.model_builder import build_model
+    m = build_model("ESPNet", classes)
+    sd = fixture.randomize_state_dict(m.state_dict(), 77)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = fixture.make_input(2, 64, 128)
+    with torch.no_grad():
+        ref = nets.forward("ESPNet", sd, x)
+        logits, mask = m.predict_mask(x.cuda(), with_logits=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yb = m(x.cuda())
+    assert logits.shape == ref.shape and _rel(logits.cpu(), ref) < FP32_LOGIT_TOL
+    assert (mask.cpu().numpy() == nets.argmax_mask(ref)).mean() >= ARGMAX_MIN
+    assert torch.equal(mask.long(), logits.argmax(1))
+    assert _rel(yb.float().cpu(), ref) < BF16_LOGIT_TOL
