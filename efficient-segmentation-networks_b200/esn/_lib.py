@@ -86,6 +86,11 @@ class EsnHead(C.Structure):
                 ("align_corners", C.c_int32)]
 
 
+class EsnAugItem(C.Structure):
+    _fields_ = [("img", C.c_void_p), ("label", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("rh", C.c_int32), ("rw", C.c_int32),
+                ("scale", C.c_double), ("h_off", C.c_int32), ("w_off", C.c_int32), ("flip", C.c_int32), ("do_scale", C.c_int32)]
+
+
 class EsnCE(C.Structure):
     _fields_ = [("logits", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
                 ("dlogits", EsnTensor), ("ignore_label", C.c_int32), ("_pad", C.c_int32),
@@ -106,6 +111,9 @@ SYMBOLS = {
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
+    "esn_augment_max_batch": (C.c_int32, []),
+    "esn_augment_u8": (C.c_int, [C.POINTER(EsnAugItem), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "esn_dot_nc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
     "esn_scale_add_nc": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.c_void_p, C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_maxpool3x3s2_idx_bwd": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),

@@ -387,6 +387,26 @@ int esn_confusion_matrix(const uint8_t* pred, const void* gt, int32_t gt_is_int6
 int esn_image_u8hwc_to_f32nchw(const uint8_t* img, float* out, int32_t n, int32_t h, int32_t w, const float* mean3,
                                int32_t reverse_channels, void* stream);
 
+/* Training-time augmentation of the reference's CityscapesDataSet.__getitem__ (dataset/cityscapes.py:67-104) on the device,
+ * one launch per batch: random scale (cv2.resize: INTER_LINEAR on the uint8 image in OpenCV's 11-bit fixed-point arithmetic,
+ * bit-identical to cv2; INTER_NEAREST on the labels), fp32 mean subtraction, BGR -> RGB, zero / ignore padding up to the crop
+ * size, crop, CHW, mirror.  The random draws (scale factor, offsets, mirror) are made by the caller -- the reference makes
+ * them with Python's random / numpy.random -- and passed per image; the resized image is never materialised.
+ * items: HOST array of n <= esn_augment_max_batch() entries, read before the call returns.  mean3: HOST, input channel order. */
+typedef struct EsnAugItem {
+  const uint8_t* img;    /* device, (h, w, 3) uint8 BGR */
+  const uint8_t* label;  /* device, (h, w) uint8 */
+  int32_t h, w;          /* decoded size */
+  int32_t rh, rw;        /* size after the resize: cvRound(h * f), cvRound(w * f) (= h, w when do_scale == 0) */
+  double scale;          /* 1 / f */
+  int32_t h_off, w_off;  /* crop offset inside the padded resized image */
+  int32_t flip;          /* 1 = mirror the columns of the crop */
+  int32_t do_scale;      /* 0 = no resize step (scale=False) */
+} EsnAugItem;
+int32_t esn_augment_max_batch(void);
+int esn_augment_u8(const EsnAugItem* items, int32_t n, int32_t crop_h, int32_t crop_w, const float* mean3, int32_t ignore_label,
+                   float* out_img /* (n,3,crop_h,crop_w) */, int64_t* out_label /* (n,crop_h,crop_w) */, void* stream);
+
 /* Per-pixel gate with a per-image bias: y[n,h,w,c] = g[n,h,w] * x[n,h,w,c] + b[n,c] -- the close of LEDNet's attention
  * pyramid (APNModule.forward, model/LEDNet.py:279-281: torch.mul(x, mid) + the global-pooling branch, whose bilinear
  * upsampling from 1x1 with align_corners=True is a constant per image and class).  g (N,1,H,W), x and y (N,C,H,W),

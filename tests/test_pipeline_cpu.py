@@ -78,3 +78,69 @@ def test_device_source_on_cpu_is_bit_exact(kernel_on_cpu, case):
     ref = (pipeline.batch_to_input(img) if reverse
            else (img.astype(np.float32) - pipeline.CITYSCAPES_MEAN_BGR).transpose(0, 3, 1, 2))
     assert np.array_equal(y, ref)
+
+
+# --------------------------------------------------------------------------- training-time augmentation
+def test_resize_restatement_is_bit_exact_against_cv2():
+    """oracle/pipeline.py restates cv2.resize (cv2 is a third-party dependency of the reference, absent from /root/reference):
+    INTER_LINEAR on uint8 (11-bit fixed point) and INTER_NEAREST, every scale factor of the reference, odd sizes, 1 and 3
+    channels -- bit-exact against the cv2 installed here."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(3)
+    for h, w in ((64, 128), (37, 53), (33, 70), (100, 31), (5, 7)):
+        for ch in (3, 1):
+            img = rng.randint(0, 256, (h, w, ch)).astype(np.uint8)
+            img = img[:, :, 0] if ch == 1 else img
+            for f in pipeline.SCALES:
+                assert np.array_equal(pipeline.resize_linear_u8(img, f), cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_LINEAR))
+                assert np.array_equal(pipeline.resize_nearest_u8(img, f), cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_NEAREST))
+
+
+def _golden_cases():
+    import random
+    g = np.load(os.path.join(ROOT, "tests", "golden", "augment.npz"))
+    for k in range(int(g["n_cases"][0])):
+        i, ch, cw, seed = [int(v) for v in g["case%d" % k]]
+        random.seed(seed)
+        np.random.seed(seed)
+        params = pipeline.draw_train_params(g["image%d" % i].shape[:2], (ch, cw))
+        yield g, k, g["image%d" % i], g["label%d" % i], (ch, cw), params
+
+
+def test_train_augmentation_oracle_matches_reference_class():
+    """oracle.pipeline.train_item + draw_train_params against the UNMODIFIED CityscapesDataSet (tools/make_golden_augment.py):
+    18 seeded samples, every scale factor, padding in no / one / both directions, both mirror states -- bit-exact."""
+    scales = set()
+    for g, k, img, lab, crop, params in _golden_cases():
+        x, y = pipeline.train_item(img, lab, *params, crop, g["mean"])
+        assert np.array_equal(x, g["x%d" % k]) and np.array_equal(y, g["y%d" % k]), k
+        scales.add(params[0])
+    assert scales == set(pipeline.SCALES)
+
+
+@pytest.fixture(scope="module")
+def augment_on_cpu(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path_factory.mktemp("aug") / "augment_kernel_host")
+    subprocess.run([gxx, "-O1", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "tests"),
+                    "-I" + os.path.join(ROOT, "efficient-segmentation-networks_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "augment_kernel_host.cpp"), "-o", exe], check=True)
+    return exe
+
+
+def test_augment_device_source_on_cpu_matches_reference_class(augment_on_cpu):
+    """The kernel's DEVICE SOURCE (csrc/esn_augment_kernel.cuh) compiled with g++ reproduces the reference class's crops and
+    label crops bit for bit on all 18 golden samples."""
+    for g, k, img, lab, (ch, cw), (f, h_off, w_off, flip) in _golden_cases():
+        h, w = img.shape[:2]
+        rh, rw = pipeline.resized_size(h, w, f)
+        args = [h, w, ch, cw, rh, rw, repr(1.0 / f), h_off, w_off, int(flip < 0), 1, 255] + [repr(float(v)) for v in g["mean"]]
+        r = subprocess.run([augment_on_cpu] + [str(v) for v in args], input=img.tobytes() + lab.tobytes(), capture_output=True,
+                           timeout=300, check=True)
+        n = 3 * ch * cw
+        x = np.frombuffer(r.stdout[:4 * n], dtype=np.float32).reshape(3, ch, cw)
+        y = np.frombuffer(r.stdout[4 * n:], dtype=np.int64).reshape(ch, cw)
+        assert np.array_equal(x, g["x%d" % k]), k
+        assert np.array_equal(y.astype(np.float32), g["y%d" % k]), k

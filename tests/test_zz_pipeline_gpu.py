@@ -55,3 +55,46 @@ def test_full_size_properties():
     ref = (img.float() - mean).flip(3).permute(0, 3, 1, 2)
     assert torch.equal(y, ref)
     assert y.is_contiguous() and y.shape == (16, 3, 1024, 2048)
+
+
+# --------------------------------------------------------------------------- training-time augmentation (esn_augment_u8)
+def test_train_augmentation_matches_reference_class(golden):
+    """esn.augment.CityscapesTrainAugment against the UNMODIFIED CityscapesDataSet (tests/golden/augment.npz, 18 seeded
+    samples: every scale factor, padding in no / one / both directions, both mirror states): with `random` / `np.random`
+    seeded as the generator seeded them, the device crops and label crops are bit-identical."""
+    import random
+    from esn.augment import CityscapesTrainAugment
+    g = golden("augment")
+    for k in range(int(g["n_cases"][0])):
+        i, ch, cw, seed = [int(v) for v in g["case%d" % k]]
+        aug = CityscapesTrainAugment(crop_size=(ch, cw), mean=g["mean"], scale=True, mirror=True, ignore_label=255)
+        random.seed(seed)
+        np.random.seed(seed)
+        x, y = aug([torch.from_numpy(g["image%d" % i]).cuda()], [torch.from_numpy(g["label%d" % i]).cuda()])
+        assert np.array_equal(x[0].cpu().numpy(), g["x%d" % k]), k
+        assert np.array_equal(y[0].cpu().numpy().astype(np.float32), g["y%d" % k]), k
+    aug = CityscapesTrainAugment(crop_size=(32, 32), mean=g["mean"], scale=False, mirror=False)
+    random.seed(5)
+    np.random.seed(5)
+    x, y = aug([torch.from_numpy(g["image0"]).cuda()], [torch.from_numpy(g["label0"]).cuda()])
+    assert np.array_equal(x[0].cpu().numpy(), g["noscale_x"]) and np.array_equal(y[0].cpu().numpy().astype(np.float32), g["noscale_y"])
+
+
+def test_train_augmentation_full_size_batch():
+    """Cityscapes-sized inputs (1024 x 2048), crop 512 x 1024 (train.py's default input_size), a batch of 8 with mixed scale
+    factors in ONE launch: every sample equals the oracle (oracle/pipeline.py, pinned on the reference class and on cv2)."""
+    from esn.augment import CityscapesTrainAugment
+    rng = np.random.RandomState(9)
+    imgs = [rng.randint(0, 256, (1024, 2048, 3)).astype(np.uint8) for _ in range(2)]
+    labs = [rng.randint(0, 19, (1024, 2048)).astype(np.uint8) for _ in range(2)]
+    params = [(0.75, 0, 17, -1), (1.0, 300, 511, 1), (1.25, 768, 1536, -1), (1.5, 5, 2000, 1), (1.75, 1280, 0, -1), (2.0, 1536, 3072, 1),
+              (0.75, 256, 512, 1), (None, 512, 1024, -1)]
+    aug = CityscapesTrainAugment(crop_size=(512, 1024), mean=pipeline.CITYSCAPES_MEAN_BGR)
+    gi = [torch.from_numpy(imgs[k % 2]).cuda() for k in range(8)]
+    gl = [torch.from_numpy(labs[k % 2]).cuda() for k in range(8)]
+    x, y = aug(gi, gl, params=params)
+    assert x.shape == (8, 3, 512, 1024) and y.shape == (8, 512, 1024) and y.dtype == torch.int64
+    for k, (f, ho, wo, fl) in enumerate(params):
+        rx, ry = pipeline.train_item(imgs[k % 2], labs[k % 2], f, ho, wo, fl, (512, 1024))
+        assert np.array_equal(x[k].cpu().numpy(), rx), k
+        assert np.array_equal(y[k].cpu().numpy(), ry.astype(np.int64)), k
