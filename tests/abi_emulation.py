@@ -312,6 +312,34 @@ def esn_ohem_threshold(prob, n, min_kept, thresh, num_valid, out, workspace):
     return 0
 
 
+def esn_augment_u8(items, n, crop_h, crop_w, mean3, ignore_label, out_img, out_label):
+    """include/esn.h EsnAugItem / esn_augment_u8, from the raw structs: oracle.pipeline's cv2 restatement driven by the
+    struct's own (rh, rw, scale) -- the resized image is materialised here, the kernel gathers instead."""
+    import numpy as np
+    from oracle import pipeline as P
+    mean = np.array([mean3[0], mean3[1], mean3[2]], dtype=np.float32)
+    xo = _buf(out_img.value, n * 3 * crop_h * crop_w, torch.float32, 4).view(n, 3, crop_h, crop_w)
+    yo = _buf(out_label.value, n * crop_h * crop_w, torch.int64, 8).view(n, crop_h, crop_w)
+    for k in range(n):
+        it = items[k]
+        img = torch.frombuffer((C.c_char * (it.h * it.w * 3)).from_address(it.img), dtype=torch.uint8).view(it.h, it.w, 3).numpy()
+        lab = torch.frombuffer((C.c_char * (it.h * it.w)).from_address(it.label), dtype=torch.uint8).view(it.h, it.w).numpy()
+        if it.do_scale:
+            xof, xa = P._linear_coeffs(it.rw, it.w, it.scale, True)
+            yof, ya = P._linear_coeffs(it.rh, it.h, it.scale, False)
+            s = img.astype(np.int32)
+            hb = s[:, xof] * xa[:, 0][None, :, None] + s[:, np.minimum(xof + 1, it.w - 1)] * xa[:, 1][None, :, None]
+            s0, s1 = hb[np.clip(yof, 0, it.h - 1)], hb[np.clip(yof + 1, 0, it.h - 1)]
+            img = ((((ya[:, 0][:, None, None] * (s0 >> 4)) >> 16) + ((ya[:, 1][:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2).astype(np.uint8)
+            sy = np.minimum(np.floor(np.arange(it.rh) * it.scale).astype(np.int64), it.h - 1)
+            sx = np.minimum(np.floor(np.arange(it.rw) * it.scale).astype(np.int64), it.w - 1)
+            lab = lab[sy][:, sx]
+        x, y = P.train_item(img, lab, None, it.h_off, it.w_off, -1 if it.flip else 1, (crop_h, crop_w), mean, ignore_label)
+        xo[k].copy_(torch.from_numpy(x))
+        yo[k].copy_(torch.from_numpy(y.astype(np.int64)))
+    return 0
+
+
 def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
     src = torch.frombuffer((C.c_char * (n * h * w * 3)).from_address(img.value), dtype=torch.uint8).view(n, h, w, 3)
     v = src.float() - torch.tensor([mean3[0], mean3[1], mean3[2]], dtype=torch.float32)
@@ -331,7 +359,7 @@ ENTRY = {
     "esn_head_convt2x2": esn_head_convt2x2, "esn_head_bilinear": esn_head_bilinear,
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
     "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast, "esn_weighted_ce": esn_weighted_ce,
-    "esn_ohem_threshold": esn_ohem_threshold,
+    "esn_ohem_threshold": esn_ohem_threshold, "esn_augment_u8": esn_augment_u8,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 
