@@ -66,8 +66,45 @@ class V:
             self._g = fn(self._g, None)
 
 
+class _ZeroArena:
+    """ONE memset per training step for all the small zero-initialised scratch buffers of the tape (BatchNorm statistic sums,
+    weight-gradient accumulators: ~200 per DABNet iteration, each a separate torch.zeros fill kernel in round 1 = 5 % of the
+    step).  Sized from what the previous step used; a request that does not fit falls back to its own torch.zeros.  A new
+    buffer is allocated per step, so views handed out as parameter gradients stay valid until the optimizer drops them."""
+
+    def __init__(self):
+        self.need, self.buf, self.off, self.used, self.dev = {}, None, 0, 0, None
+
+    def begin(self, device):
+        if self.dev is not None:
+            self.need[self.dev] = self.used
+        self.dev, self.off, self.used = device, 0, 0
+        size = self.need.get(device, 0)
+        self.buf = torch.zeros(size, dtype=torch.uint8, device=device) if size else None
+
+    def take(self, shape, dtype, device):
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        n = 1
+        for v in shape:
+            n *= v
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        aligned = (nbytes + 255) // 256 * 256
+        if device == self.dev:
+            self.used += aligned
+            if self.buf is not None and self.off + aligned <= self.buf.numel():
+                view = self.buf[self.off:self.off + nbytes].view(dtype).view(shape)
+                self.off += aligned
+                return view
+        return torch.zeros(shape, dtype=dtype, device=device)
+
+
+_ARENA = _ZeroArena()
+
+
 class Tape:
-    def __init__(self, buckets=None):
+    def __init__(self, buckets=None, device=None):
+        if device is not None:
+            _ARENA.begin(torch.device(device))
         self.steps = []
         self.param_grads = {}     # parameter -> fp32 gradient tensor
         self.buckets = buckets    # esn.parallel.GradBuckets or None
@@ -96,7 +133,11 @@ class Tape:
 
 
 def _f64zeros(n, device):
-    return torch.zeros(n, dtype=torch.float64, device=device)
+    return _ARENA.take(n, torch.float64, torch.device(device))
+
+
+def _f32zeros(shape, device):
+    return _ARENA.take(shape, torch.float32, torch.device(device))
 
 
 # --------------------------------------------------------------------------- convolution
@@ -167,7 +208,7 @@ class ConvT:
             # weight gradient [tap][Cin/g][Cout] -> (Cout, Cin/g, kh, kw)
             kh, kw = fwd_prep.kh, fwd_prep.kw
             cin_g = fwd_prep.cin // fwd_prep.groups
-            dwbuf = torch.zeros((kh * kw, cin_g, fwd_prep.cout), dtype=torch.float32, device=dy.device)
+            dwbuf = _f32zeros((kh * kw, cin_g, fwd_prep.cout), dy.device)
             p = L.EsnConv()
             xw = xt
             stem = (not ops.is_nhwc(xt) and fwd_prep.cin == 3 and (kh, kw) == (3, 3) and fwd_prep.cout <= 32
@@ -182,7 +223,7 @@ class ConvT:
                           ops._nbytes(xt) + ops._nbytes(x8))
                 xw = ops.widen(x8, 8)
                 cin_g = 8
-                dwbuf = torch.zeros((kh * kw, cin_g, fwd_prep.cout), dtype=torch.float32, device=dy.device)
+                dwbuf = _f32zeros((kh * kw, cin_g, fwd_prep.cout), dy.device)
                 p.w = dwbuf.data_ptr()
             p.x, p.y = ops.tdesc(xw), ops.tdesc(dy)
             p.w = dwbuf.data_ptr()
@@ -250,7 +291,7 @@ class ConvTransposeT:
         kh, kw = conv.kernel_size
         cin, cout = conv.in_channels, conv.out_channels
         xt = x.t
-        dwbuf = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=dy.device)   # [tap][Cout][Cin]
+        dwbuf = _f32zeros((kh * kw, cout, cin), dy.device)   # [tap][Cout][Cin]
         p = L.EsnConv()
         p.x, p.y, p.w = ops.tdesc(dy), ops.tdesc(xt), dwbuf.data_ptr()
         p.kh, p.kw, p.stride = kh, kw, conv.stride[0]
@@ -763,7 +804,7 @@ def fglo(tape, fc, x, out=None, residual=None):
 
     def bwd():
         dy = y.g
-        dg = torch.zeros((n, c), dtype=torch.float32, device=dev)
+        dg = _f32zeros((n, c), dev)
         a, b = ops.tdesc(dy), ops.tdesc(xt)
         ops._call(L.lib.esn_dot_nc, "esn_dot_nc", (C.byref(a), C.byref(b), C.c_void_p(dg.data_ptr())), ops._nbytes(dy) + ops._nbytes(xt))
         grads = torch.autograd.grad(gate, [pooled] + params, dg)

@@ -93,7 +93,7 @@ def espnetv2_train_forward(model, input):
     if (H | W) & 15:
         raise ValueError("EESPNet_Seg: input height and width must be multiples of 16, got %dx%d" % (H, W))
     dt, dev = ops.compute_dtype(input), input.device
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)
     net = model.net
 
     # image pyramid for the input reinforcement (no parameters, no gradient)

@@ -57,7 +57,7 @@ def cgnet_train_forward(model, input):
     n, _, H, W = input.shape
     dt = ops.compute_dtype(input)
     dev = input.device
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)
     m = model
     inp1 = m.sample1(input)            # input-injection pyramid: no parameters, no gradient
     inp2 = m.sample1(inp1)

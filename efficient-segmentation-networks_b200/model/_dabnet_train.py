@@ -72,7 +72,7 @@ def dabnet_train_forward(model, input):
     dt = ops.compute_dtype(input)
     dev = input.device
     n, _, H, W = input.shape
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))     # data-parallel gradient buckets, if attached
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)     # data-parallel gradient buckets, if attached
 
     d1 = model.down_1(input)          # input-injection pyramid: no parameters, no gradient needed
     d2 = model.down_1(d1)

@@ -116,7 +116,7 @@ def enet_train_forward(model, input):
     if (H | W) & 7:
         raise ValueError("ENet: input height and width must be multiples of 8, got %dx%d" % (H, W))
     dt = ops.compute_dtype(input)
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)
     m = model
     x = _initial(tape, m.initial_block, input, dt)
     x, i1 = _down(tape, m.downsample1_0, x)

@@ -54,7 +54,7 @@ def erfnet_train_forward(model, input):
     if (H | W) & 7:
         raise ValueError("ERFNet: input height and width must be multiples of 8, got %dx%d" % (H, W))
     dt = ops.compute_dtype(input)
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)
     enc, dec = model.encoder, model.decoder
     y = _down(tape, enc.initial_block, T.V(input), dt, image=True)
     for layer in enc.layers:

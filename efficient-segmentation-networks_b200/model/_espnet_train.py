@@ -72,7 +72,7 @@ def espnet_train_forward(model, input):
     if (H | W) & 7:
         raise ValueError("ESPNet: input height and width must be multiples of 8, got %dx%d" % (H, W))
     dt = ops.compute_dtype(input)
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)
     enc = model.encoder
     classes = model.classifier.out_channels
     img = T.V(input)

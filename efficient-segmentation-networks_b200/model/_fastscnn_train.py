@@ -42,7 +42,7 @@ def fastscnn_train_forward(model, input):
     dt = ops.compute_dtype(input)
     dev = input.device
     n, _, H, W = input.shape
-    tape = T.Tape(model.__dict__.get("_esn_buckets"))     # data-parallel gradient buckets, if attached
+    tape = T.Tape(model.__dict__.get("_esn_buckets"), device=input.device)     # data-parallel gradient buckets, if attached
 
     ltd = model.learning_to_downsample
     y = _cbr(tape, ltd.conv.conv, T.V(input), need_dx=False, dtype=dt)
