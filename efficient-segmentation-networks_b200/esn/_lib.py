@@ -64,6 +64,11 @@ class EsnBnBwd(C.Structure):
                 ("dalpha", C.c_void_p), ("act", C.c_int32), ("train_stats", C.c_int32)]
 
 
+class EsnBnTrainFwd(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("fin", EsnBnFinalize), ("alpha", C.c_void_p), ("barrier", C.c_void_p),
+                ("act", C.c_int32), ("_pad", C.c_int32)]
+
+
 class EsnUnpool(C.Structure):
     _fields_ = [("v", EsnTensor), ("idx", C.c_void_p), ("ext", EsnTensor), ("y", EsnTensor), ("alpha", C.c_void_p),
                 ("act", C.c_int32), ("_pad", C.c_int32)]
@@ -124,6 +129,8 @@ SYMBOLS = {
     "esn_bn_finalize": (C.c_int, [C.POINTER(EsnBnFinalize), C.c_void_p]),
     "esn_bn_act_bwd_reduce": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
     "esn_bn_act_bwd_apply": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
+    "esn_bn_act_train_fwd": (C.c_int, [C.POINTER(EsnBnTrainFwd), C.c_void_p]),
+    "esn_bn_act_bwd_fused": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p, C.c_void_p]),
     "esn_conv2d_wgrad": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
     "esn_wgrad_umma_supported": (C.c_int, [C.POINTER(EsnConv)]),
     "esn_maxpool2x2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),

@@ -64,6 +64,11 @@ class V:
             assert out.data_ptr() == view.data_ptr()
         else:
             self._g = fn(self._g, None)
+            # ownership is taken ONCE, by the V that receives the buffer from the op that allocated it: when this V's producer
+            # later hands the same tensor on (a residual add gives it to both operands), nobody else may accumulate into it
+            self._own = bool(getattr(self._g, "_esn_fresh", False))
+            if self._own:
+                self._g._esn_fresh = False
 
 
 class _ZeroArena:
@@ -108,6 +113,16 @@ class Tape:
         self.steps = []
         self.param_grads = {}     # parameter -> fp32 gradient tensor
         self.buckets = buckets    # esn.parallel.GradBuckets or None
+        self.bn_counters = []     # num_batches_tracked of the BatchNorm layers of this forward: bumped by ONE foreach kernel
+
+    def count_batch(self, bn):
+        if bn.num_batches_tracked is not None:
+            self.bn_counters.append(bn.num_batches_tracked)
+
+    def flush_counters(self):
+        if self.bn_counters:
+            torch._foreach_add_(self.bn_counters, 1)
+            self.bn_counters = []
 
     def push(self, fn):
         self.steps.append(fn)
@@ -138,6 +153,24 @@ def _f64zeros(n, device):
 
 def _f32zeros(shape, device):
     return _ARENA.take(shape, torch.float32, torch.device(device))
+
+
+import os as _os
+FUSED_BN = _os.environ.get("ESN_FUSED_BN", "1") != "0"      # one cooperative launch per BatchNorm layer and direction
+_FUSED_DIR = _os.environ.get("ESN_FUSED_BN_DIR", "fwd,bwd")  # diagnosis: restrict the fused kernels to one direction
+BN_REPLICAS = 8                                              # ESN_BN_FUSED_REPLICAS (include/esn.h)
+
+
+def _fresh(t):
+    """Mark a gradient buffer as allocated by the op that returns it and referenced by nobody else: V.add_grad then lets
+    channel slices accumulate into it in place instead of taking a private copy first."""
+    t._esn_fresh = True
+    return t
+
+
+def _v8(t):
+    """bf16 NHWC view whose channel vectors are 16-byte aligned (what the 16-byte kernels of esn_bn_fused.cu take)."""
+    return (t.dtype == torch.bfloat16 and ops.is_nhwc(t) and t.stride(3) % 8 == 0 and t.data_ptr() % 16 == 0)
 
 
 # --------------------------------------------------------------------------- convolution
@@ -225,12 +258,12 @@ class ConvT:
                 cin_g = 8
                 dwbuf = _f32zeros((kh * kw, cin_g, fwd_prep.cout), dy.device)
                 p.w = dwbuf.data_ptr()
+            flops = 2 * dy.shape[0] * dy.shape[2] * dy.shape[3] * fwd_prep.cout * cin_g * kh * kw
             p.x, p.y = ops.tdesc(xw), ops.tdesc(dy)
             p.w = dwbuf.data_ptr()
             p.kh, p.kw, p.stride = kh, kw, fwd_prep.stride
             p.pad_h, p.pad_w, p.dil_h, p.dil_w = fwd_prep.pad_h, fwd_prep.pad_w, fwd_prep.dil_h, fwd_prep.dil_w
             p.groups, p.transposed, p.cout_pad = fwd_prep.groups, 0, fwd_prep.cout_pad
-            flops = 2 * dy.shape[0] * dy.shape[2] * dy.shape[3] * fwd_prep.cout * cin_g * kh * kw
             ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy), flops,
                       "%dx%d c%d-%d s%d g%d" % (kh, kw, fwd_prep.cin, fwd_prep.cout, fwd_prep.stride, fwd_prep.groups))
             dw4 = dwbuf.view(kh, kw, cin_g, fwd_prep.cout).permute(3, 2, 0, 1)
@@ -358,12 +391,10 @@ class BNActT:
         if one_slope:
             alpha = alpha.expand(c).contiguous()
         scale = shift = mean = invstd = None
+        fused_out = None
         if bn is not None:
-            sums = _f64zeros(2 * c, dev)
-            d = ops.tdesc(xt)
-            ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 1),
-                      ops._nbytes(xt))
-            scale, shift, mean, invstd = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
+            sums = _f64zeros(BN_REPLICAS * 2 * c + 1, dev)    # replicated sums + the fused kernel's grid barrier word
+            scale, shift, mean, invstd = torch.empty(4, c, dtype=torch.float32, device=dev).unbind(0)
             f = L.EsnBnFinalize()
             f.sums, f.count = sums.data_ptr(), n * h * w
             f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
@@ -371,9 +402,26 @@ class BNActT:
             f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             f.scale, f.shift, f.mean, f.invstd = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr()
             f.channels = c
-            ops._call(L.lib.esn_bn_finalize, "esn_bn_finalize", (C.byref(f),))
-            bn.num_batches_tracked += 1
-        if isinstance(out, V):
+            dst = out.t if isinstance(out, V) else out
+            if FUSED_BN and "fwd" in _FUSED_DIR and _v8(xt) and (_v8(dst) if dst is not None else c % 8 == 0):
+                # one launch: statistics -> grid barrier -> finalize + normalise + activate out of L2 (esn_bn_fused.cu)
+                if dst is None:
+                    dst = ops.new_act(n, c, h, w, xt.dtype, dev)
+                q = L.EsnBnTrainFwd()
+                q.x, q.y, q.fin = ops.tdesc(xt), ops.tdesc(dst), f
+                q.alpha = alpha.data_ptr() if alpha is not None else None
+                q.barrier, q.act = sums.data_ptr() + 8 * BN_REPLICAS * 2 * c, self.act
+                ops._call(L.lib.esn_bn_act_train_fwd, "esn_bn_act_train_fwd", (C.byref(q),), ops._nbytes(xt) + ops._nbytes(dst))
+                fused_out = dst
+            else:
+                d = ops.tdesc(xt)
+                ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 1),
+                          ops._nbytes(xt))
+                ops._call(L.lib.esn_bn_finalize, "esn_bn_finalize", (C.byref(f),))
+            tape.count_batch(bn)
+        if fused_out is not None:
+            y = out if isinstance(out, V) else V(fused_out)
+        elif isinstance(out, V):
             y = out
             ops.affine_act(xt, scale, shift, alpha, self.act, out=y.t)
         else:
@@ -382,13 +430,17 @@ class BNActT:
 
         def bwd():
             dy = y.g
-            sums3 = _f64zeros(3 * c, dev)
+            sums3 = _f64zeros(BN_REPLICAS * 3 * c + 1, dev)   # replicated sums + the fused kernel's grid barrier word
             dgamma = torch.empty(c, dtype=torch.float32, device=dev) if bn is not None else None
             dbeta = torch.empty(c, dtype=torch.float32, device=dev)
             dalpha = torch.empty(c, dtype=torch.float32, device=dev) if prelu is not None else None
 
             def run(ex, dst):
-                dx = dst if dst is not None else ops.new_act(n, c, h, w, dy.dtype, dev)
+                fresh = dst is None
+                if fresh:       # 16-byte channel vectors also for 35 / 131 / 259 channels (zero tail inside the pixel stride)
+                    dx = ops.new_act(n, c, h, w, dy.dtype, dev, c_alloc=(c + 7) // 8 * 8, zero=c % 8 != 0)
+                else:
+                    dx = dst
                 p = L.EsnBnBwd()
                 p.x, p.dy, p.dx = ops.tdesc(xt), ops.tdesc(dy), ops.tdesc(dx)
                 if ex is not None:
@@ -404,9 +456,14 @@ class BNActT:
                 p.dalpha = dalpha.data_ptr() if dalpha is not None else None
                 p.act, p.train_stats = act, int(bn is not None)
                 nb = ops._nbytes(xt) + ops._nbytes(dy)
+                if (FUSED_BN and "bwd" in _FUSED_DIR and bn is not None and _v8(xt) and _v8(dy) and _v8(dx) and (ex is None or _v8(ex))
+                        and dx.data_ptr() not in (dy.data_ptr(), xt.data_ptr())):
+                    ops._call(L.lib.esn_bn_act_bwd_fused, "esn_bn_act_bwd_fused",
+                              (C.byref(p), C.c_void_p(sums3.data_ptr() + 8 * BN_REPLICAS * 3 * c)), nb + ops._nbytes(dx))
+                    return _fresh(dx) if fresh else dx
                 ops._call(L.lib.esn_bn_act_bwd_reduce, "esn_bn_act_bwd_reduce", (C.byref(p),), nb)
                 ops._call(L.lib.esn_bn_act_bwd_apply, "esn_bn_act_bwd_apply", (C.byref(p),), nb + ops._nbytes(dx))
-                return dx
+                return _fresh(dx) if fresh else dx
 
             x.add_grad(run)
             if bn is not None:
@@ -511,7 +568,8 @@ def maxpool2x2(tape, x, out, need_dx=True):
 
         def run(ex, dst):
             n, c, h, w = x.t.shape
-            dx = dst if dst is not None else (ex if ex is not None else ops.new_act(n, c, h, w, dy.dtype, dy.device))
+            dx = dst if dst is not None else (ex if ex is not None else
+                                              ops.new_act(n, c, h, w, dy.dtype, dy.device, c_alloc=(c + 7) // 8 * 8, zero=c % 8 != 0))
             dxd, dyd, xd = ops.tdesc(dx), ops.tdesc(dy), ops.tdesc(x.t)
             ops._call(L.lib.esn_maxpool2x2_bwd, "esn_maxpool2x2_bwd", (C.byref(xd), C.byref(dyd), C.byref(dxd),
                                                                       int(ex is not None)), 2 * ops._nbytes(dx))
@@ -727,6 +785,7 @@ class _NetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, run_forward, x, *params):
         logits, tape, holder = run_forward(x)
+        tape.flush_counters()
         ctx.tape, ctx.holder, ctx.params = tape, holder, params
         return logits
 
@@ -734,7 +793,12 @@ class _NetFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         ctx.holder["dlogits"] = dlogits.contiguous()
         grads = ctx.tape.backward()
-        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+        out = tuple(grads.get(p) for p in ctx.params)
+        # the tape must not keep the gradients alive: AccumulateGrad adopts a returned tensor only when nobody else holds it
+        # (otherwise it clones: one device copy per parameter, 213 of them in a DABNet step)
+        ctx.tape.param_grads = {}
+        del grads
+        return (None, None) + out
 
 
 def run_network(model, run_forward, x):

@@ -342,6 +342,32 @@ typedef struct EsnBnBwd {
 int esn_bn_act_bwd_reduce(const EsnBnBwd* p, void* stream);
 int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream);
 
+/* The same two layers as ONE launch each (bf16 NHWC operands with 16-byte-aligned channel vectors; anything else returns
+ * ESN_ERR_UNSUPPORTED with nothing launched and the caller uses the calls above): a co-resident grid (cooperative launch)
+ * reduces over its pixel chunks, meets at one grid-wide barrier and then normalises / back-propagates the SAME chunks out of
+ * L2, so a BatchNorm layer reads its operands from DRAM once and costs one launch instead of three (forward: statistics,
+ * finalize, affine + activation) or two (backward).  The reduction scratch holds ESN_BN_FUSED_REPLICAS copies of the sums (a
+ * CTA adds into one of them, so fewer atomics meet at one address); it and `barrier` must be zero on entry.
+ *   esn_bn_act_train_fwd: y = act(BN_train(x)); fin.scale / shift / mean / invstd and the running statistics are written as
+ *                         by esn_bn_finalize; fin.sums: [ESN_BN_FUSED_REPLICAS][2][C] doubles of scratch.
+ *   esn_bn_act_bwd_fused: esn_bn_act_bwd_reduce + esn_bn_act_bwd_apply with train_stats = 1; p->sums:
+ *                         [ESN_BN_FUSED_REPLICAS][3][C] doubles of scratch.
+ * Replaces aten::native_batch_norm(training=True) + _prelu_kernel / threshold and native_batch_norm_backward +
+ * _prelu_kernel_backward / threshold_backward of every BatchNorm2d on the path (DABNet.py:41, ERFNet.py:21,38,45,107;
+ * train.py:351-356). */
+#define ESN_BN_FUSED_REPLICAS 8
+typedef struct EsnBnTrainFwd {
+  EsnTensor x;          /* BN input (= conv output) */
+  EsnTensor y;          /* out: act(x*scale + shift), may be a channel slice of a wider buffer; must not alias x */
+  EsnBnFinalize fin;    /* as for esn_bn_finalize; fin.sums is written (scratch), fin.channels == x.c */
+  const float* alpha;   /* [C] PReLU slopes (act == ESN_ACT_PRELU) */
+  uint32_t* barrier;    /* one zeroed 32-bit word of device memory, private to this call */
+  int32_t act;
+  int32_t _pad;
+} EsnBnTrainFwd;
+int esn_bn_act_train_fwd(const EsnBnTrainFwd* p, void* stream);
+int esn_bn_act_bwd_fused(const EsnBnBwd* p, uint32_t* barrier, void* stream);
+
 /* Weight gradient of a dense or depthwise Conv2d: p->x = forward input, p->y = gradient of the conv
  * output, p->w = fp32 accumulator [kh*kw][Cin/groups][Cout] (zeroed by the caller; atomics).
  * Replaces the weight branch of aten::convolution_backward.  The input gradient is the transposed /

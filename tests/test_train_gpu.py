@@ -62,6 +62,85 @@ def test_bn_act_forward_backward_matches_torch(c, act):
         assert _rel(pg[prelu.weight], grads[3]) < 1e-4
 
 
+@pytest.mark.parametrize("c,c_alloc,act,shape", [(64, 64, "prelu", (4, 40, 72)), (35, 40, "prelu", (2, 24, 40)),
+                                                 (32, 32, "relu", (8, 64, 128)), (320, 320, "prelu", (2, 16, 24)),
+                                                 (16, 16, "none", (1, 3, 5)),
+                                                 # Fast-SCNN: ReLU / no activation, 48 ... 768 channels (2-3 channel blocks), the
+                                                 # pyramid-pooling levels (1x1 ... 6x6 at batch 2)
+                                                 (48, 48, "relu", (2, 7, 9)), (384, 384, "none", (2, 4, 8)),
+                                                 (576, 576, "relu", (2, 2, 4)), (32, 32, "relu", (2, 1, 1)),
+                                                 (96, 96, "none", (2, 8, 16)), (768, 768, "relu", (2, 2, 4)),
+                                                 (128, 128, "relu", (2, 6, 6)), (64, 64, "relu", (2, 16, 32))])
+def test_bn_act_fused_launch_matches_multi_launch_bf16(c, c_alloc, act, shape):
+    """The one-launch BatchNorm layer (cooperative grid + barrier, esn_bn_fused.cu) against the three- / two-launch path on the
+    same bf16 operands (forward output, saved statistics, running statistics, dx with a second consumer's gradient, parameter
+    gradients), and both against torch on the bf16-rounded input; the output also lands in a channel slice of a wider buffer."""
+    from esn import ops, train as T
+    from esn._lib import ACT_NONE, ACT_PRELU, ACT_RELU
+    torch.manual_seed(3)
+    n, h, w = shape
+    code = {"prelu": ACT_PRELU, "relu": ACT_RELU, "none": ACT_NONE}[act]
+    x = torch.randn(n, c, h, w, device="cuda") * 2 + 0.5
+    gy, extra = torch.randn_like(x), torch.randn_like(x)
+    res = {}
+    for fused in (True, False):
+        T.FUSED_BN = fused
+        try:
+            bn = nn.BatchNorm2d(c, eps=1e-3).cuda()
+            with torch.no_grad():
+                bn.weight.copy_(torch.linspace(0.5, 1.5, c)); bn.bias.copy_(torch.linspace(-0.2, 0.2, c))
+            prelu = nn.PReLU(c).cuda() if act == "prelu" else None
+            if prelu is not None:
+                with torch.no_grad():
+                    prelu.weight.copy_(torch.linspace(0.05, 0.45, c))
+            tape = T.Tape(device="cuda")
+            xv = T.V(_nhwc(x, torch.bfloat16, ops, c_alloc=c_alloc))
+            xv._g = _nhwc(extra, torch.bfloat16, ops, c_alloc=c_alloc)
+            wide = T.V(ops.new_act(n, c_alloc + 16, h, w, torch.bfloat16, "cuda", zero=True))
+            launches0 = ops.L.lib.esn_launch_count()
+            y = T.BNActT(bn, code, prelu).forward(tape, xv, out=wide.slice(8, 8 + c) if c_alloc % 8 == 0 and c % 8 == 0 else None)
+            fwd_launches = ops.L.lib.esn_launch_count() - launches0
+            if y.parent is not None:
+                wide._g = ops.new_act(n, c_alloc + 16, h, w, torch.bfloat16, "cuda", zero=True)
+                wide._own = True
+                wide._g[:, 8:8 + c].copy_(gy)
+            else:
+                y._g = _nhwc(gy, torch.bfloat16, ops, c_alloc=c_alloc)
+            launches0 = ops.L.lib.esn_launch_count()
+            pg = tape.backward()
+            bwd_launches = ops.L.lib.esn_launch_count() - launches0
+            torch.cuda.synchronize()
+            res[fused] = dict(y=y.t.float().clone(), dx=xv.g.float().clone(), rm=bn.running_mean.clone(), rv=bn.running_var.clone(),
+                              dg=pg[bn.weight].clone(), db=pg[bn.bias].clone(),
+                              da=pg[prelu.weight].clone() if prelu is not None else None, launches=(fwd_launches, bwd_launches))
+        finally:
+            T.FUSED_BN = True
+    # 35 channels: the forward output (dense, 70-byte pixels) keeps the three-launch path, the gradient buffer is padded to 40
+    assert res[True]["launches"] == ((1, 1) if c % 8 == 0 else (3, 1)) and res[False]["launches"] == (3, 2)
+    f, u = res[True], res[False]
+    assert _rel(f["y"], u["y"]) < 2e-3 and _rel(f["dx"], u["dx"]) < 2e-3         # one bf16 ulp on a few elements at most
+    for k in ("rm", "rv", "dg", "db", "da"):
+        if f[k] is not None:
+            assert _rel(f[k], u[k]) < 1e-4, k
+    # torch on the same (bf16-rounded) operands
+    xr = x.bfloat16().float().requires_grad_(True)
+    bn_ref = nn.BatchNorm2d(c, eps=1e-3).cuda()
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.linspace(0.5, 1.5, c)); bn_ref.bias.copy_(torch.linspace(-0.2, 0.2, c))
+    ref = bn_ref(xr)
+    if act == "prelu":
+        aw = torch.linspace(0.05, 0.45, c, device="cuda").requires_grad_(True)
+        ref = F.prelu(ref, aw)
+    elif act == "relu":
+        ref = F.relu(ref)
+    gx, gg, gb = torch.autograd.grad(ref, [xr, bn_ref.weight, bn_ref.bias], gy.bfloat16().float(), retain_graph=True)
+    assert _rel(f["y"], ref.detach()) < 4e-3
+    assert _rel(f["dx"], gx + extra.bfloat16().float()) < 6e-3
+    assert _rel(f["dg"], gg) < 2e-3 and _rel(f["db"], gb) < 2e-3
+    assert torch.allclose(f["rm"], bn_ref.running_mean, atol=1e-5, rtol=1e-4)
+    assert torch.allclose(f["rv"], bn_ref.running_var, atol=1e-5, rtol=1e-4)
+
+
 WG_CASES = [
     # cin, cout, k, stride, pad, dil, groups, H, W
     (64, 32, 3, 1, 1, 1, 1, 12, 20),
