@@ -408,12 +408,15 @@ int resident_ctas(K kernel, int* cache) {
   return cache[dev];
 }
 
-// pixel chunk so that (chunks x channel blocks) <= the co-resident capacity; >= 32 pixels per CTA
+// pixel chunk so that (chunks x channel blocks) <= the co-resident capacity; >= 256 pixels per CTA, the same floor as the
+// multi-launch kernels (esn_train.cu: pick_chunk), so that small layers sum their statistics in exactly the same order on both
+// paths: train-mode BatchNorm over a handful of values (Fast-SCNN's 1x1 pyramid level at batch 2 is a sign function of the
+// difference of two numbers) turns a last-bit difference of the mean into a different network output
 inline long long plan_chunk(long long M, int cblocks, int capacity, int* gx) {
   long long want = capacity / cblocks;
   if (want < 1) want = 1;
   long long chunk = (M + want - 1) / want;
-  if (chunk < 32) chunk = 32;
+  if (chunk < 256) chunk = 256;
   *gx = esn_cdiv(M, chunk);
   return chunk;
 }
