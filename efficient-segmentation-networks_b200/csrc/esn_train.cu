@@ -953,6 +953,64 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const TX* __restric
   st1<TG>(o, accumulate ? ld1<TG>(o) + g : g);
 }
 
+// 16-byte version (bf16, even H and W): a thread owns one pooled pixel x 8 channels -- the four input vectors of its window,
+// the (possibly unaligned: the pooled channels sit at channel 29 of DABNet's down-sampler output) gradient values, and the
+// four gradient vectors it writes.  The per-element kernel above spent 0.34 ms on DABNet's 8 x 256 x 512 x 35 tensor.
+template <bool DYVEC>
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_v8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ dx, long long total, int Ho, int Wo, int C,
+                                                                int x_cs, int dy_cs, int dx_cs, int accumulate) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ng = (C + 7) / 8;
+  const int c = (int)(idx % ng) * 8;
+  const long long pp = idx / ng;
+  const int wo = (int)(pp % Wo), ho = (int)((pp / Wo) % Ho);
+  const long long n = pp / ((long long)Wo * Ho);
+  const int Wi = 2 * Wo;
+  const size_t p00 = ((size_t)(n * 2 * Ho + 2 * ho) * Wi + 2 * wo);
+  float xv[4][8], gv[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + (p00 + (size_t)(k >> 1) * Wi + (k & 1)) * x_cs + c)), xv[k]);
+  const __nv_bfloat16* g = dy + (size_t)pp * dy_cs + c;
+  if (DYVEC) {
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(g)), gv);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = (c + j < C) ? __bfloat162float(g[j]) : 0.f;
+  }
+  float out[4][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float best = xv[0][j];            // first maximum in raster order wins (torch max_pool2d_with_indices)
+    int bi = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (xv[k][j] > best) { best = xv[k][j]; bi = k; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k][j] = (bi == k) ? gv[j] : 0.f;
+  }
+  const bool full = c + 8 <= C;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat16* o = dx + (p00 + (size_t)(k >> 1) * Wi + (k & 1)) * dx_cs + c;
+    if (accumulate) {
+      float prev[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(o), prev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[k][j] += prev[j];
+    }
+    if (full) {
+      *reinterpret_cast<uint4*>(o) = float_to_bf16x8(out[k]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j < C) o[j] = __float2bfloat16_rn(out[k][j]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- bilinear backward (align_corners=False)
 // d low[n,h,w,c] = sum over output pixels of d logits * weight; gather over the <= (2*ceil(1/s)+1)^2 window
 template <typename TL, typename TO>
@@ -966,35 +1024,82 @@ __global__ void __launch_bounds__(128) bilinear_bwd_kernel(const TL* __restrict_
   const int h = (int)((idx / Wi) % Hi);
   const int c = (int)((idx / ((long long)Wi * Hi)) % C);
   const int n = (int)(idx / ((long long)Wi * Hi * C));
-  // output rows whose source index floor is h-1 or h (or clamps onto h)
+  // The weight of output pixel (ho, wo) on source pixel (h, w) is a product of two hat functions of the clamped source
+  // coordinates, max(0, 1 - |fh - h|) * max(0, 1 - |fw - w|) -- the same numbers as (1 - frac, frac) on (floor, floor + 1),
+  // including the clamps at both borders -- so only the ~2/s output rows / columns inside the hat are visited (round 1 walked
+  // a (2/s + 5)^2 window and rebuilt both index pairs per element: 0.36 ms of DABNet's training step).
   const float rh = 1.f / sh, rw = 1.f / sw;
-  int ho0 = (int)floorf(((float)h - 1.f + 0.5f) * rh - 0.5f) - 1, ho1 = (int)ceilf(((float)h + 1.f + 0.5f) * rh - 0.5f) + 1;
-  int wo0 = (int)floorf(((float)w - 1.f + 0.5f) * rw - 0.5f) - 1, wo1 = (int)ceilf(((float)w + 1.f + 0.5f) * rw - 0.5f) + 1;
-  ho0 = max(ho0, 0); ho1 = min(ho1, Ho - 1);
-  wo0 = max(wo0, 0); wo1 = min(wo1, Wo - 1);
+  const int ho0 = max((int)ceilf(((float)h - 0.5f) * rh - 0.5f) - 1, 0), ho1 = min((int)floorf(((float)h + 1.5f) * rh - 0.5f) + 1, Ho - 1);
+  const int wo0 = max((int)ceilf(((float)w - 0.5f) * rw - 0.5f) - 1, 0), wo1 = min((int)floorf(((float)w + 1.5f) * rw - 0.5f) + 1, Wo - 1);
   const TL* plane = dl + ((size_t)n * C + c) * Ho * Wo;
+  const float hmax = (float)(Hi - 1), wmax = (float)(Wi - 1);
   float acc = 0.f;
   for (int ho = ho0; ho <= ho1; ++ho) {
-    float fh = sh * (ho + 0.5f) - 0.5f;
-    fh = fh < 0.f ? 0.f : fh;
-    const int h0 = (int)fh;
-    const int h1 = h0 + ((h0 < Hi - 1) ? 1 : 0);
-    const float l1 = fh - h0, l0 = 1.f - l1;
-    const float wh = (h0 == h ? l0 : 0.f) + (h1 == h ? l1 : 0.f);
-    if (wh == 0.f) continue;
+    const float fh = fminf(fmaxf(sh * ((float)ho + 0.5f) - 0.5f, 0.f), hmax);
+    const float wh = 1.f - fabsf(fh - (float)h);
+    if (wh <= 0.f) continue;
+    const TL* row = plane + (size_t)ho * Wo;
     float rowacc = 0.f;
     for (int wo = wo0; wo <= wo1; ++wo) {
-      float fw = sw * (wo + 0.5f) - 0.5f;
-      fw = fw < 0.f ? 0.f : fw;
-      const int w0 = (int)fw;
-      const int w1 = w0 + ((w0 < Wi - 1) ? 1 : 0);
-      const float m1 = fw - w0, m0 = 1.f - m1;
-      const float ww = (w0 == w ? m0 : 0.f) + (w1 == w ? m1 : 0.f);
-      if (ww != 0.f) rowacc += ww * ld1<TL>(plane + (size_t)ho * Wo + wo);
+      const float fw = fminf(fmaxf(sw * ((float)wo + 0.5f) - 0.5f, 0.f), wmax);
+      const float ww = fmaxf(1.f - fabsf(fw - (float)w), 0.f);
+      rowacc = fmaf(ww, ld1<TL>(row + wo), rowacc);
     }
-    acc += wh * rowacc;
+    acc = fmaf(wh, rowacc, acc);
   }
   st1<TO>(dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c, acc * gscale);
+}
+
+// The same sum, separable and coalesced: a CTA owns (n, c, source row h, kTWL source columns).  Pass 1: every thread takes
+// output columns wo of the CTA's window and sums its column over the ~2/s output rows inside the vertical hat -- consecutive
+// threads read consecutive addresses of d logits (the per-element kernel above has neighbouring lanes 1/s floats apart: every
+// warp load touches 32 sectors, L1-transaction-bound at 1 TB/s).  Pass 2: kTWL threads finish the horizontal hat from shared
+// memory.
+constexpr int kTWL = 32;
+template <typename TL, typename TO>
+__global__ void __launch_bounds__(288) bilinear_bwd_rows_kernel(const TL* __restrict__ dl, TO* __restrict__ dlow, int C, int Hi, int Wi,
+                                                                int Ho, int Wo, int low_cs, float sh, float sw, float gscale,
+                                                                int wtiles) {
+  extern __shared__ float colsum[];
+  const int wt = blockIdx.x % wtiles;
+  const int h = (blockIdx.x / wtiles) % Hi;
+  const int c = (blockIdx.x / (wtiles * Hi)) % C;
+  const int n = blockIdx.x / (wtiles * Hi * C);
+  const int w0 = wt * kTWL, w1 = min(w0 + kTWL, Wi) - 1;
+  const float rh = 1.f / sh, rw = 1.f / sw;
+  const int ho0 = max((int)ceilf(((float)h - 0.5f) * rh - 0.5f) - 1, 0), ho1 = min((int)floorf(((float)h + 1.5f) * rh - 0.5f) + 1, Ho - 1);
+  const int wlo = max((int)ceilf(((float)w0 - 0.5f) * rw - 0.5f) - 1, 0), whi = min((int)floorf(((float)w1 + 1.5f) * rw - 0.5f) + 1, Wo - 1);
+  const TL* plane = dl + ((size_t)n * C + c) * Ho * Wo;
+  const float hmax = (float)(Hi - 1), wmax = (float)(Wi - 1);
+  for (int wo = wlo + threadIdx.x; wo <= whi; wo += blockDim.x) {
+    float acc = 0.f;
+    // kRB rows per batch, all loads issued before the first use: with 33 waves of CTAs the kernel's time is (dependent round
+    // trips per CTA) x (waves), so a x8 up-sampling (20 rows) is one round trip and the CTA (288 threads) covers its
+    // 272-column window in one pass
+    constexpr int kRB = 24;
+    for (int hb = ho0; hb <= ho1; hb += kRB) {
+      float v[kRB];
+#pragma unroll
+      for (int k = 0; k < kRB; ++k) v[k] = (hb + k <= ho1) ? ld1<TL>(plane + (size_t)(hb + k) * Wo + wo) : 0.f;
+#pragma unroll
+      for (int k = 0; k < kRB; ++k) {
+        const float fh = fminf(fmaxf(sh * ((float)(hb + k) + 0.5f) - 0.5f, 0.f), hmax);
+        acc = fmaf(fmaxf(1.f - fabsf(fh - (float)h), 0.f), v[k], acc);
+      }
+    }
+    colsum[wo - wlo] = acc;
+  }
+  __syncthreads();
+  const int w = w0 + threadIdx.x;
+  if ((int)threadIdx.x < kTWL && w <= w1) {
+    const int a0 = max((int)ceilf(((float)w - 0.5f) * rw - 0.5f) - 1, wlo), a1 = min((int)floorf(((float)w + 1.5f) * rw - 0.5f) + 1, whi);
+    float acc = 0.f;
+    for (int wo = a0; wo <= a1; ++wo) {
+      const float fw = fminf(fmaxf(sw * ((float)wo + 0.5f) - 0.5f, 0.f), wmax);
+      acc = fmaf(fmaxf(1.f - fabsf(fw - (float)w), 0.f), colsum[wo - wlo], acc);
+    }
+    st1<TO>(dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c, acc * gscale);
+  }
 }
 
 inline long long pick_chunk(long long M, int other_ctas) {
@@ -1130,6 +1235,7 @@ extern "C" int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream) {
 
 bool esn_wgrad_mma_try(const EsnConv* p, void* stream, int* rc);   // esn_wgrad_mma.cu
 bool esn_wgrad_umma_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_umma.cu (tcgen05, stride 1)
+bool esn_wgrad_rows_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_rows.cu (mma.sync, dense 3x3, all taps per pass)
 
 extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   // p->x: forward input, p->y: gradient of the conv output, p->w: fp32 dW accumulator
@@ -1147,6 +1253,7 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   if (eh != dy.h || ew != dy.w || x.n != dy.n) return ESN_ERR_BAD_SHAPE;
   {
     int rc = ESN_OK;   // bf16 dense convs: tensor-core path
+    if (!dw && !nchw && esn_wgrad_rows_try(p, stream, &rc)) return rc;
     if (!dw && !nchw && esn_wgrad_umma_try(p, stream, &rc)) return rc;
     if (!dw && !nchw && esn_wgrad_mma_try(p, stream, &rc)) return rc;
   }
@@ -1264,6 +1371,18 @@ extern "C" int esn_maxpool2x2_bwd(const EsnTensor* x, const EsnTensor* dy, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = esn_cdiv(total, 256);
   const bool xf = x->dtype == ESN_F32, gf = dy->dtype == ESN_F32;
+  if (!xf && !gf && v8_ok(x->ptr, x->c_stride) && v8_ok(dx->ptr, dx->c_stride) && !((x->h | x->w) & 1)) {
+    const long long groups = (long long)dy->n * dy->h * dy->w * ((x->c + 7) / 8);
+    const int g8 = esn_cdiv(groups, 256);
+    if (v8_ok(dy->ptr, dy->c_stride))
+      maxpool2x2_bwd_v8_kernel<true><<<g8, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, (const __nv_bfloat16*)dy->ptr, (__nv_bfloat16*)dx->ptr,
+                                                         groups, dy->h, dy->w, x->c, x->c_stride, dy->c_stride, dx->c_stride, accumulate);
+    else
+      maxpool2x2_bwd_v8_kernel<false><<<g8, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, (const __nv_bfloat16*)dy->ptr, (__nv_bfloat16*)dx->ptr,
+                                                          groups, dy->h, dy->w, x->c, x->c_stride, dy->c_stride, dx->c_stride, accumulate);
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
+  }
 #define ESN_MPB(TX, TG)                                                                                              \
   maxpool2x2_bwd_kernel<TX, TG><<<grid, 256, 0, st>>>((const TX*)x->ptr, (const TG*)dy->ptr, (TG*)dx->ptr, x->n, x->h, \
                                                       x->w, x->c, x->c_stride, dy->c_stride, dx->c_stride, accumulate)
@@ -1284,6 +1403,25 @@ extern "C" int esn_bilinear_bwd(const EsnTensor* dlogits, const EsnTensor* dlow,
   const float sh = (float)dlow->h / (float)dlogits->h, sw = (float)dlow->w / (float)dlogits->w;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool lf = dlogits->dtype == ESN_F32, of = dlow->dtype == ESN_F32;
+  {
+    const int wtiles = esn_cdiv(dlow->w, kTWL);
+    const long long ctas = (long long)dlow->n * dlow->c * dlow->h * wtiles;
+    const int window = (int)((kTWL + 2) / sw) + 8;          // output columns under the hats of kTWL source columns
+    if (window <= 8192 && ctas < (1LL << 31) && dlogits->w >= 2 * dlow->w) {
+      const int smem = window * (int)sizeof(float);
+#define ESN_BLR(TL, TO)                                                                                                       \
+      bilinear_bwd_rows_kernel<TL, TO><<<(unsigned)ctas, 288, smem, st>>>((const TL*)dlogits->ptr, (TO*)dlow->ptr, dlow->c, dlow->h, \
+                                                                          dlow->w, dlogits->h, dlogits->w, dlow->c_stride, sh, sw, \
+                                                                          gscale, wtiles)
+      if (lf && of) ESN_BLR(float, float);
+      else if (lf) ESN_BLR(float, __nv_bfloat16);
+      else if (of) ESN_BLR(__nv_bfloat16, float);
+      else ESN_BLR(__nv_bfloat16, __nv_bfloat16);
+#undef ESN_BLR
+      ESN_CHECK_LAUNCH();
+      return ESN_OK;
+    }
+  }
 #define ESN_BLB(TL, TO)                                                                                            \
   bilinear_bwd_kernel<TL, TO><<<grid, 128, 0, st>>>((const TL*)dlogits->ptr, (TO*)dlow->ptr, dlow->n, dlow->c,      \
                                                     dlow->h, dlow->w, dlogits->h, dlogits->w, dlow->c_stride, sh, sw, \

@@ -40,6 +40,7 @@ class GradBuckets:
                 off += p.numel()
             self.views.append(vs)
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.wgrad_stream = None     # set by esn.train.Tape when it runs weight gradients off the critical path
         self.reset()
 
     def reset(self):
@@ -67,6 +68,8 @@ class GradBuckets:
         return view
 
     def _pack(self, i):
+        if self.wgrad_stream is not None:       # the tape computes weight gradients on a side stream: join it before reading them
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
         dense_v, dense_g = [], []
         for p, g in self.staged[i].items():
             v = self.views[i][p]

@@ -10,6 +10,7 @@ Semantics follow torch: train-mode BatchNorm normalises with the 
 variance and updates running_var with the unbiased one; PReLU per channel; MaxPool2d(2,2) routes
 the gradient to the first maximum; bilinear align_corners=False.
 """
+import contextlib
 import ctypes as C
 
 import torch
@@ -114,6 +115,26 @@ class Tape:
         self.param_grads = {}     # parameter -> fp32 gradient tensor
         self.buckets = buckets    # esn.parallel.GradBuckets or None
         self.bn_counters = []     # num_batches_tracked of the BatchNorm layers of this forward: bumped by ONE foreach kernel
+        self.side = None          # stream for work off the critical path of the backward (weight gradients)
+        self.keep = []            # tensors read on the side stream: kept alive until it has been joined
+
+    def off_critical_path(self, *tensors):
+        """Context manager: kernels launched inside run on a side stream that has waited for everything issued so far on the
+        current stream.  Weight gradients are leaves of the backward -- nothing downstream in the tape reads them -- while the
+        chain BatchNorm backward -> input gradient -> BatchNorm backward ... is a sequence of small latency-bound kernels; run
+        concurrently, the weight gradients fill the SMs the chain leaves idle.  The side stream is joined before the gradients
+        are handed to anyone (end of backward / a data-parallel bucket being packed)."""
+        if not SIDE_WGRAD or not torch.cuda.is_available():
+            return contextlib.nullcontext()
+        cur = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = _SIDE_STREAMS.setdefault(cur.device_index, None) or torch.cuda.Stream()
+            _SIDE_STREAMS[cur.device_index] = self.side
+            if self.buckets is not None:
+                self.buckets.wgrad_stream = self.side
+        self.side.wait_stream(cur)
+        self.keep.extend(tensors)
+        return torch.cuda.stream(self.side)
 
     def count_batch(self, bn):
         if bn.num_batches_tracked is not None:
@@ -130,6 +151,8 @@ class Tape:
     def add_param_grad(self, p, g):
         g = g.to(p.dtype) if g.dtype != p.dtype else g
         if p in self.param_grads:
+            if self.side is not None:       # the earlier contribution may still be in flight on the side stream
+                torch.cuda.current_stream().wait_stream(self.side)
             prev = self.param_grads[p]
             if self.buckets is not None:       # the bucket view is only filled when its bucket is packed
                 prev = self.buckets.staged[self.buckets.bucket_of[p]].get(p, prev)
@@ -142,6 +165,9 @@ class Tape:
         for fn in reversed(self.steps):
             fn()
         self.steps = []
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.keep = []
         if self.buckets is not None:
             self.buckets.finish()
         return self.param_grads
@@ -158,6 +184,8 @@ def _f32zeros(shape, device):
 import os as _os
 FUSED_BN = _os.environ.get("ESN_FUSED_BN", "1") != "0"      # one cooperative launch per BatchNorm layer and direction
 _FUSED_DIR = _os.environ.get("ESN_FUSED_BN_DIR", "fwd,bwd")  # diagnosis: restrict the fused kernels to one direction
+SIDE_WGRAD = _os.environ.get("ESN_SIDE_WGRAD", "1") != "0"   # weight gradients on a side stream, concurrent with the dgrad chain
+_SIDE_STREAMS = {}
 BN_REPLICAS = 8                                              # ESN_BN_FUSED_REPLICAS (include/esn.h)
 
 
@@ -241,41 +269,46 @@ class ConvT:
             # weight gradient [tap][Cin/g][Cout] -> (Cout, Cin/g, kh, kw)
             kh, kw = fwd_prep.kh, fwd_prep.kw
             cin_g = fwd_prep.cin // fwd_prep.groups
-            dwbuf = _f32zeros((kh * kw, cin_g, fwd_prep.cout), dy.device)
-            p = L.EsnConv()
-            xw = xt
             stem = (not ops.is_nhwc(xt) and fwd_prep.cin == 3 and (kh, kw) == (3, 3) and fwd_prep.cout <= 32
                     and xt.dtype == torch.float32)          # esn_conv2d_wgrad has a kernel for the NCHW fp32 image
-            if not stem and not ops.is_nhwc(xt) and dy.dtype == torch.bfloat16 and fwd_prep.groups == 1 and fwd_prep.cin < 8:
-                # network stem (NCHW fp32 image, Cin=3): give the tensor-core wgrad an NHWC bf16 copy
-                # padded to 8 channels; the padded rows of dW are dropped below
-                n_, c_, h_, w_ = xt.shape
-                x8 = ops.new_act(n_, c_, h_, w_, torch.bfloat16, xt.device, c_alloc=8, zero=True)
-                dxs, dx8 = ops.tdesc(xt), ops.tdesc(x8)
-                ops._call(L.lib.esn_convert_layout, "esn_convert_layout", (C.byref(dxs), C.byref(dx8)),
-                          ops._nbytes(xt) + ops._nbytes(x8))
-                xw = ops.widen(x8, 8)
+            pad8 = not stem and not ops.is_nhwc(xt) and dy.dtype == torch.bfloat16 and fwd_prep.groups == 1 and fwd_prep.cin < 8
+            if pad8:
                 cin_g = 8
-                dwbuf = _f32zeros((kh * kw, cin_g, fwd_prep.cout), dy.device)
+            dwbuf = _f32zeros((kh * kw, cin_g, fwd_prep.cout), dy.device)
+            bsums = _f64zeros(fwd_prep.cout, dy.device) if conv.bias is not None else None
+            with tape.off_critical_path(dy, xt):
+                p = L.EsnConv()
+                xw = xt
+                if pad8:
+                    # network stem (NCHW fp32 image, Cin=3): give the tensor-core wgrad an NHWC bf16 copy
+                    # padded to 8 channels; the padded rows of dW are dropped below
+                    n_, c_, h_, w_ = xt.shape
+                    x8 = ops.new_act(n_, c_, h_, w_, torch.bfloat16, xt.device, c_alloc=8, zero=True)
+                    dxs, dx8 = ops.tdesc(xt), ops.tdesc(x8)
+                    ops._call(L.lib.esn_convert_layout, "esn_convert_layout", (C.byref(dxs), C.byref(dx8)),
+                              ops._nbytes(xt) + ops._nbytes(x8))
+                    xw = ops.widen(x8, 8)
+                    tape.keep.append(x8)
+                flops = 2 * dy.shape[0] * dy.shape[2] * dy.shape[3] * fwd_prep.cout * cin_g * kh * kw
+                p.x, p.y = ops.tdesc(xw), ops.tdesc(dy)
                 p.w = dwbuf.data_ptr()
-            flops = 2 * dy.shape[0] * dy.shape[2] * dy.shape[3] * fwd_prep.cout * cin_g * kh * kw
-            p.x, p.y = ops.tdesc(xw), ops.tdesc(dy)
-            p.w = dwbuf.data_ptr()
-            p.kh, p.kw, p.stride = kh, kw, fwd_prep.stride
-            p.pad_h, p.pad_w, p.dil_h, p.dil_w = fwd_prep.pad_h, fwd_prep.pad_w, fwd_prep.dil_h, fwd_prep.dil_w
-            p.groups, p.transposed, p.cout_pad = fwd_prep.groups, 0, fwd_prep.cout_pad
-            ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy), flops,
-                      "%dx%d c%d-%d s%d g%d" % (kh, kw, fwd_prep.cin, fwd_prep.cout, fwd_prep.stride, fwd_prep.groups))
+                p.kh, p.kw, p.stride = kh, kw, fwd_prep.stride
+                p.pad_h, p.pad_w, p.dil_h, p.dil_w = fwd_prep.pad_h, fwd_prep.pad_w, fwd_prep.dil_h, fwd_prep.dil_w
+                p.groups, p.transposed, p.cout_pad = fwd_prep.groups, 0, fwd_prep.cout_pad
+                ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy), flops,
+                          "%dx%d c%d-%d s%d g%d" % (kh, kw, fwd_prep.cin, fwd_prep.cout, fwd_prep.stride, fwd_prep.groups))
+                if bsums is not None:
+                    d = ops.tdesc(dy)
+                    ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(bsums.data_ptr()), 0),
+                              ops._nbytes(dy))
+                    bgrad = bsums.float()
+                    tape.keep.append(bsums)
             dw4 = dwbuf.view(kh, kw, cin_g, fwd_prep.cout).permute(3, 2, 0, 1)
             if fwd_prep.groups == 1:
                 dw4 = dw4[:cout_real, :cin_real]        # drop the zero-padded channels
             tape.add_param_grad(conv.weight, dw4)
             if conv.bias is not None:
-                sums = _f64zeros(fwd_prep.cout, dy.device)
-                d = ops.tdesc(dy)
-                ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 0),
-                          ops._nbytes(dy))
-                tape.add_param_grad(conv.bias, sums.float())
+                tape.add_param_grad(conv.bias, bgrad)
             if residual is not None:
                 residual.add_grad(lambda ex, dst: dy if ex is None else ops.affine_act(dy, None, None, None, L.ACT_NONE,
                                                                                         out=dst, residual=ex))
@@ -325,19 +358,23 @@ class ConvTransposeT:
         cin, cout = conv.in_channels, conv.out_channels
         xt = x.t
         dwbuf = _f32zeros((kh * kw, cout, cin), dy.device)   # [tap][Cout][Cin]
-        p = L.EsnConv()
-        p.x, p.y, p.w = ops.tdesc(dy), ops.tdesc(xt), dwbuf.data_ptr()
-        p.kh, p.kw, p.stride = kh, kw, conv.stride[0]
-        p.pad_h, p.pad_w, p.dil_h, p.dil_w = conv.padding[0], conv.padding[1], 1, 1
-        p.groups, p.transposed, p.cout_pad = 1, 0, (cin + 15) // 16 * 16
-        ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy),
-                  2 * xt.shape[0] * xt.shape[2] * xt.shape[3] * cin * cout * kh * kw, "%dx%dT c%d-%d" % (kh, kw, cin, cout))
+        sums = _f64zeros(cout, dy.device) if conv.bias is not None else None
+        with tape.off_critical_path(dy, xt):
+            p = L.EsnConv()
+            p.x, p.y, p.w = ops.tdesc(dy), ops.tdesc(xt), dwbuf.data_ptr()
+            p.kh, p.kw, p.stride = kh, kw, conv.stride[0]
+            p.pad_h, p.pad_w, p.dil_h, p.dil_w = conv.padding[0], conv.padding[1], 1, 1
+            p.groups, p.transposed, p.cout_pad = 1, 0, (cin + 15) // 16 * 16
+            ops._call(L.lib.esn_conv2d_wgrad, "esn_conv2d_wgrad", (C.byref(p),), ops._nbytes(xt) + ops._nbytes(dy),
+                      2 * xt.shape[0] * xt.shape[2] * xt.shape[3] * cin * cout * kh * kw, "%dx%dT c%d-%d" % (kh, kw, cin, cout))
+            if sums is not None:
+                d = ops.tdesc(dy)
+                ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 0), ops._nbytes(dy))
+                bgrad = sums.float()
+                tape.keep.append(sums)
         tape.add_param_grad(conv.weight, dwbuf.view(kh, kw, cout, cin).permute(3, 2, 0, 1))
         if conv.bias is not None:
-            sums = _f64zeros(cout, dy.device)
-            d = ops.tdesc(dy)
-            ops._call(L.lib.esn_channel_stats, "esn_channel_stats", (C.byref(d), C.c_void_p(sums.data_ptr()), 0), ops._nbytes(dy))
-            tape.add_param_grad(conv.bias, sums.float())
+            tape.add_param_grad(conv.bias, bgrad)
         x.add_grad(lambda ex, dst: ops.conv2d(dy, dgrad_prep, out=dst, residual=ex))
 
     def forward(self, tape, x, out=None):
@@ -705,6 +742,13 @@ class _GradCollector:
     def add_param_grad(self, p, g):
         self.grads[id(p)] = g
 
+    def off_critical_path(self, *tensors):
+        return self.tape.off_critical_path(*tensors)
+
+    @property
+    def keep(self):
+        return self.tape.keep
+
 
 class GroupedConvT:
     """nn.Conv2d with 1 < groups < channels (ESPNetv2's g=4 1x1 convs, cnn_utils.py:27-110): one dense ConvT per
@@ -729,7 +773,9 @@ class GroupedConvT:
         og, cg = conv.out_channels // conv.groups, conv.in_channels // conv.groups
 
         def assemble():      # pushed first => runs after every group's backward
-            tape.add_param_grad(conv.weight, torch.cat([coll.grads[id(sc.weight)] for sc in self.subs], 0))
+            with tape.off_critical_path():      # same stream as the groups' weight-gradient kernels, after them
+                full = torch.cat([coll.grads[id(sc.weight)] for sc in self.subs], 0)
+            tape.add_param_grad(conv.weight, full)
         tape.push(assemble)
         for g, ct in enumerate(self.convts):
             ct.forward(coll, x.slice(g * cg, (g + 1) * cg), out=out.slice(g * og, (g + 1) * og))

@@ -158,6 +158,12 @@ WG_CASES = [
     (32, 32, (1, 3), 1, (0, 1), (1, 1), 32, 10, 37),     # depthwise sliding-window wgrad, ragged segments
     (64, 64, 3, 1, 1, 1, 64, 9, 300),
     (8, 6, 1, 1, 0, 1, 1, 12, 20),          # tiny dense convs: one thread per weight element
+    (64, 32, 3, 2, 1, 1, 1, 24, 80),        # dense 3x3 on the all-taps mma.sync kernel (esn_wgrad_rows.cu): stride 2 (even / odd
+    (192, 128, 3, 2, 1, 1, 1, 16, 48),      # pixel planes), 6 x 4 channel tiles, ragged row segments, odd input sizes, dilation
+    (32, 32, 3, 1, 1, 1, 1, 20, 150),
+    (40, 24, 3, 2, 1, 1, 1, 15, 33),
+    (64, 64, 3, 1, 4, 4, 1, 18, 140),
+    (128, 64, 3, 1, 1, 1, 1, 16, 64),
     (3, 3, 3, 1, 1, 1, 1, 9, 14),
 ]
 
@@ -253,18 +259,42 @@ def test_pool_bilinear_ce_backward():
     buf._g[:, 29:64].copy_(gy)
     tape.backward()
     assert torch.allclose(xv.g, gx)
-    # bilinear x8 backward
-    s = torch.randn(2, 19, 8, 16, device="cuda").requires_grad_(True)
-    ref = F.interpolate(s, (64, 128), mode="bilinear", align_corners=False)
-    gl = torch.randn_like(ref)
-    gs, = torch.autograd.grad(ref, s, gl)
-    tape = T.Tape()
-    sv = T.V(_nhwc(s.detach(), torch.float32, ops, c_alloc=32))
-    logits, holder = T.bilinear_logits(tape, sv, 64, 128)
-    assert torch.allclose(logits, ref.detach(), atol=1e-5, rtol=1e-5)
-    holder["dlogits"] = gl
-    tape.backward()
-    assert _rel(sv.g, gs) < 1e-5
+    # the same in bf16 (16-byte kernel: unaligned gradient slice at channel 29, 35 of 40 channels, first-maximum ties), once
+    # writing a fresh gradient and once accumulating on top of an existing one
+    xb = (torch.randn(2, 35, 8, 12, device="cuda") * 2).round().bfloat16()       # small integers: plenty of ties
+    xr = xb.float().requires_grad_(True)
+    refb = F.max_pool2d(xr, 2, 2)
+    gyb = torch.randn_like(refb).bfloat16()
+    gxb, = torch.autograd.grad(refb, xr, gyb.float())
+    for existing in (False, True):
+        tape = T.Tape()
+        xv = T.V(_nhwc(xb, torch.bfloat16, ops, c_alloc=40))
+        buf = T.V(ops.new_act(2, 64, 4, 6, torch.bfloat16, x.device, zero=True))
+        out = buf.slice(29, 64)
+        T.maxpool2x2(tape, xv, out)
+        assert torch.equal(out.t.float(), refb.detach())
+        buf._g = ops.new_act(2, 64, 4, 6, torch.bfloat16, x.device, zero=True)
+        buf._g[:, 29:64].copy_(gyb)
+        prev = torch.randn(2, 35, 8, 12, device="cuda").bfloat16()
+        if existing:
+            xv._g = _nhwc(prev, torch.bfloat16, ops, c_alloc=40)
+        tape.backward()
+        want = gxb + (prev.float() if existing else 0)
+        assert torch.allclose(xv.g.float(), want.bfloat16().float(), atol=1e-2, rtol=1e-2)
+        assert torch.equal(xv.g.float() != 0, want.bfloat16().float() != 0) or existing
+    # bilinear x8 backward, and a non-integer ratio (hat-function window bounds)
+    for (hi, wi, ho, wo) in ((8, 16, 64, 128), (5, 7, 13, 20), (6, 9, 64, 30)):
+        s = torch.randn(2, 19, hi, wi, device="cuda").requires_grad_(True)
+        ref = F.interpolate(s, (ho, wo), mode="bilinear", align_corners=False)
+        gl = torch.randn_like(ref)
+        gs, = torch.autograd.grad(ref, s, gl)
+        tape = T.Tape()
+        sv = T.V(_nhwc(s.detach(), torch.float32, ops, c_alloc=32))
+        logits, holder = T.bilinear_logits(tape, sv, ho, wo)
+        assert torch.allclose(logits, ref.detach(), atol=1e-5, rtol=1e-5)
+        holder["dlogits"] = gl
+        tape.backward()
+        assert _rel(sv.g, gs) < 1e-5, (hi, wi, ho, wo, _rel(sv.g, gs))
     # weighted CE through the autograd Function (normalised gradient)
     lg = (torch.randn(2, 19, 16, 32, device="cuda") * 3).requires_grad_(True)
     lab = fixture.make_labels(2, 16, 32, 19, seed=5).cuda()
