@@ -1050,58 +1050,6 @@ __global__ void __launch_bounds__(128) bilinear_bwd_kernel(const TL* __restrict_
   st1<TO>(dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c, acc * gscale);
 }
 
-// The same sum, separable and coalesced: a CTA owns (n, c, source row h, kTWL source columns).  Pass 1: every thread takes
-// output columns wo of the CTA's window and sums its column over the ~2/s output rows inside the vertical hat -- consecutive
-// threads read consecutive addresses of d logits (the per-element kernel above has neighbouring lanes 1/s floats apart: every
-// warp load touches 32 sectors, L1-transaction-bound at 1 TB/s).  Pass 2: kTWL threads finish the horizontal hat from shared
-// memory.
-constexpr int kTWL = 32;
-template <typename TL, typename TO>
-__global__ void __launch_bounds__(288) bilinear_bwd_rows_kernel(const TL* __restrict__ dl, TO* __restrict__ dlow, int C, int Hi, int Wi,
-                                                                int Ho, int Wo, int low_cs, float sh, float sw, float gscale,
-                                                                int wtiles) {
-  extern __shared__ float colsum[];
-  const int wt = blockIdx.x % wtiles;
-  const int h = (blockIdx.x / wtiles) % Hi;
-  const int c = (blockIdx.x / (wtiles * Hi)) % C;
-  const int n = blockIdx.x / (wtiles * Hi * C);
-  const int w0 = wt * kTWL, w1 = min(w0 + kTWL, Wi) - 1;
-  const float rh = 1.f / sh, rw = 1.f / sw;
-  const int ho0 = max((int)ceilf(((float)h - 0.5f) * rh - 0.5f) - 1, 0), ho1 = min((int)floorf(((float)h + 1.5f) * rh - 0.5f) + 1, Ho - 1);
-  const int wlo = max((int)ceilf(((float)w0 - 0.5f) * rw - 0.5f) - 1, 0), whi = min((int)floorf(((float)w1 + 1.5f) * rw - 0.5f) + 1, Wo - 1);
-  const TL* plane = dl + ((size_t)n * C + c) * Ho * Wo;
-  const float hmax = (float)(Hi - 1), wmax = (float)(Wi - 1);
-  for (int wo = wlo + threadIdx.x; wo <= whi; wo += blockDim.x) {
-    float acc = 0.f;
-    // kRB rows per batch, all loads issued before the first use: with 33 waves of CTAs the kernel's time is (dependent round
-    // trips per CTA) x (waves), so a x8 up-sampling (20 rows) is one round trip and the CTA (288 threads) covers its
-    // 272-column window in one pass
-    constexpr int kRB = 24;
-    for (int hb = ho0; hb <= ho1; hb += kRB) {
-      float v[kRB];
-#pragma unroll
-      for (int k = 0; k < kRB; ++k) v[k] = (hb + k <= ho1) ? ld1<TL>(plane + (size_t)(hb + k) * Wo + wo) : 0.f;
-#pragma unroll
-      for (int k = 0; k < kRB; ++k) {
-        const float fh = fminf(fmaxf(sh * ((float)(hb + k) + 0.5f) - 0.5f, 0.f), hmax);
-        acc = fmaf(fmaxf(1.f - fabsf(fh - (float)h), 0.f), v[k], acc);
-      }
-    }
-    colsum[wo - wlo] = acc;
-  }
-  __syncthreads();
-  const int w = w0 + threadIdx.x;
-  if ((int)threadIdx.x < kTWL && w <= w1) {
-    const int a0 = max((int)ceilf(((float)w - 0.5f) * rw - 0.5f) - 1, wlo), a1 = min((int)floorf(((float)w + 1.5f) * rw - 0.5f) + 1, whi);
-    float acc = 0.f;
-    for (int wo = a0; wo <= a1; ++wo) {
-      const float fw = fminf(fmaxf(sw * ((float)wo + 0.5f) - 0.5f, 0.f), wmax);
-      acc = fmaf(fmaxf(1.f - fabsf(fw - (float)w), 0.f), colsum[wo - wlo], acc);
-    }
-    st1<TO>(dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c, acc * gscale);
-  }
-}
-
 inline long long pick_chunk(long long M, int other_ctas) {
   // ~4 CTAs per SM in total
   long long want = (4LL * 148 + other_ctas - 1) / other_ctas;
@@ -1234,6 +1182,8 @@ extern "C" int esn_bn_act_bwd_apply(const EsnBnBwd* p, void* stream) {
 }
 
 bool esn_wgrad_mma_try(const EsnConv* p, void* stream, int* rc);   // esn_wgrad_mma.cu
+bool esn_bilinear_bwd_rows_try(const EsnTensor* dy, const EsnTensor* dx, int align_corners, int accumulate, float gscale,
+                               void* stream);                      // esn_train3.cu
 bool esn_wgrad_umma_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_umma.cu (tcgen05, stride 1)
 bool esn_wgrad_rows_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_rows.cu (mma.sync, dense 3x3, all taps per pass)
 
@@ -1403,24 +1353,9 @@ extern "C" int esn_bilinear_bwd(const EsnTensor* dlogits, const EsnTensor* dlow,
   const float sh = (float)dlow->h / (float)dlogits->h, sw = (float)dlow->w / (float)dlogits->w;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool lf = dlogits->dtype == ESN_F32, of = dlow->dtype == ESN_F32;
-  {
-    const int wtiles = esn_cdiv(dlow->w, kTWL);
-    const long long ctas = (long long)dlow->n * dlow->c * dlow->h * wtiles;
-    const int window = (int)((kTWL + 2) / sw) + 8;          // output columns under the hats of kTWL source columns
-    if (window <= 8192 && ctas < (1LL << 31) && dlogits->w >= 2 * dlow->w) {
-      const int smem = window * (int)sizeof(float);
-#define ESN_BLR(TL, TO)                                                                                                       \
-      bilinear_bwd_rows_kernel<TL, TO><<<(unsigned)ctas, 288, smem, st>>>((const TL*)dlogits->ptr, (TO*)dlow->ptr, dlow->c, dlow->h, \
-                                                                          dlow->w, dlogits->h, dlogits->w, dlow->c_stride, sh, sw, \
-                                                                          gscale, wtiles)
-      if (lf && of) ESN_BLR(float, float);
-      else if (lf) ESN_BLR(float, __nv_bfloat16);
-      else if (of) ESN_BLR(__nv_bfloat16, float);
-      else ESN_BLR(__nv_bfloat16, __nv_bfloat16);
-#undef ESN_BLR
-      ESN_CHECK_LAUNCH();
-      return ESN_OK;
-    }
+  if (esn_bilinear_bwd_rows_try(dlogits, dlow, 0, 0, gscale, stream)) {
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
   }
 #define ESN_BLB(TL, TO)                                                                                            \
   bilinear_bwd_kernel<TL, TO><<<grid, 128, 0, st>>>((const TL*)dlogits->ptr, (TO*)dlow->ptr, dlow->n, dlow->c,      \

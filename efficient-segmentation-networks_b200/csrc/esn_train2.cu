@@ -136,7 +136,28 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
   st1<T>(y + (size_t)pix * y_cs + c, keep ? ld1<T>(x + (size_t)pix * x_cs + c) * scale : 0.f);
 }
 
+// Dropout2d: the N x C scale factors (0 or 1 / (1 - p)), same keys and hash as the per-element kernel's per_channel mode
+__global__ void dropout_mask_nc_kernel(float* __restrict__ mask, long long count, uint64_t seed,
+                                       const unsigned long long* __restrict__ step, uint32_t thresh, float scale) {
+  if (step) seed += 0xd1b54a32d192ed03ULL * (uint64_t)(*step);
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  mask[i] = mix32(seed + 0x9e3779b97f4a7c15ULL * ((uint64_t)i + 1)) >= thresh ? scale : 0.f;
+}
+
 }  // namespace
+
+bool esn_bilinear_bwd_rows_try(const EsnTensor* dy, const EsnTensor* dx, int align_corners, int accumulate, float gscale,
+                               void* stream);      // esn_train3.cu
+
+extern "C" int esn_dropout_mask_nc(float* mask, int64_t count, uint64_t seed, const uint64_t* step, float p, void* stream) {
+  if (!mask || count < 1 || !(p >= 0.f) || p >= 1.f) return ESN_ERR_BAD_ARG;
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  dropout_mask_nc_kernel<<<esn_cdiv(count, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      mask, count, seed, reinterpret_cast<const unsigned long long*>(step), thresh, 1.f / (1.f - p));
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
 
 extern "C" int esn_bilinear_bwd_nhwc(const EsnTensor* dy, const EsnTensor* dx, int32_t align_corners, int32_t accumulate,
                                      void* stream) {
@@ -151,6 +172,10 @@ extern "C" int esn_bilinear_bwd_nhwc(const EsnTensor* dy, const EsnTensor* dx, i
   } else {
     sh = (float)dx->h / (float)dy->h;
     sw = (float)dx->w / (float)dy->w;
+  }
+  if (nchw && esn_bilinear_bwd_rows_try(dy, dx, align_corners ? 1 : 0, accumulate ? 1 : 0, 1.f, stream)) {
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
   }
   const long long total = (long long)dx->n * dx->h * dx->w * dx->c;
   const int grid = esn_cdiv(total, 128);

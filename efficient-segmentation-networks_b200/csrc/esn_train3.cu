@@ -62,7 +62,106 @@ __global__ void __launch_bounds__(256) max_unpool2x2_bwd_kernel(const T* __restr
   }
 }
 
+// ---------------------------------------------------------------- bilinear backward, separable and coalesced
+// d low[n,h,w,c] = sum over output pixels (ho, wo) of d high[n,c,ho,wo] * weight.  The weight of (ho, wo) on source pixel
+// (h, w) is a product of two hat functions of the clamped source coordinates, max(0, 1 - |fh - h|) * max(0, 1 - |fw - w|), with
+// f(o) = clamp(s * o + t, 0, size - 1): s = in / out, t = s / 2 - 1/2 for align_corners = False; s = (in - 1) / (out - 1), t = 0
+// for align_corners = True -- the same numbers as (1 - frac, frac) on (floor, floor + 1), both border clamps included.
+// A CTA owns (n, c, source row h, kTWL source columns).  Pass 1: every thread takes one output column of the CTA's window
+// and sums it over the ~2/s output rows under the vertical hat -- consecutive threads read consecutive addresses of the NCHW
+// gradient, all loads of a thread issued before the first use (the per-element kernels have neighbouring lanes 1/s floats
+// apart and one load in flight: 1 TB/s on DABNet's 318 MB of d logits, 4.4 ms of Fast-SCNN's step).  Pass 2: kTWL threads
+// finish the horizontal hat from shared memory.  Replaces upsample_bilinear2d_backward of DABNet.py:181 / FastSCNN.py:233.
+constexpr int kTWL = 32;
+constexpr int kRB = 24;
+constexpr int kMaxRows = 96;      // output rows under one vertical hat (2 / s + 3): up-sampling factors up to ~46
+template <typename TL, typename TO>
+__global__ void __launch_bounds__(288) bilinear_bwd_rows_kernel(const TL* __restrict__ dl, TO* __restrict__ dlow, int C, int Hi, int Wi,
+                                                                int Ho, int Wo, int low_cs, float sh, float th, float sw, float tw,
+                                                                float gscale, int wtiles, int accumulate) {
+  extern __shared__ float colsum[];
+  const int wt = blockIdx.x % wtiles;
+  const int h = (blockIdx.x / wtiles) % Hi;
+  const int c = (blockIdx.x / (wtiles * Hi)) % C;
+  const int n = blockIdx.x / (wtiles * Hi * C);
+  const int w0 = wt * kTWL, w1 = min(w0 + kTWL, Wi) - 1;
+  const float rh = 1.f / sh, rw = 1.f / sw;
+  // outputs o with |s*o + t - h| < 1, one extra on each side for rounding; the border clamps only add outputs that the
+  // image bounds cut off anyway
+  const int ho0 = max((int)ceilf(((float)h - 1.f - th) * rh) - 1, 0), ho1 = min((int)floorf(((float)h + 1.f - th) * rh) + 1, Ho - 1);
+  const int wlo = max((int)ceilf(((float)w0 - 1.f - tw) * rw) - 1, 0), whi = min((int)floorf(((float)w1 + 1.f - tw) * rw) + 1, Wo - 1);
+  const TL* plane = dl + ((size_t)n * C + c) * Ho * Wo;
+  const float hmax = (float)(Hi - 1), wmax = (float)(Wi - 1);
+  // the vertical weights are the same for every thread of the CTA: computed once (ncu: the first version of this kernel
+  // rebuilt them per element and was instruction-bound -- 295 M warp instructions, SM pipes 85 % busy at 1 TB/s)
+  __shared__ float wh_s[kMaxRows];
+  const int nrows = ho1 - ho0 + 1;
+  if ((int)threadIdx.x < nrows) {
+    const float fh = fminf(fmaxf(fmaf(sh, (float)(ho0 + (int)threadIdx.x), th), 0.f), hmax);
+    wh_s[threadIdx.x] = fmaxf(1.f - fabsf(fh - (float)h), 0.f);
+  }
+  __syncthreads();
+  for (int wo = wlo + threadIdx.x; wo <= whi; wo += blockDim.x) {
+    float acc = 0.f;
+    const TL* col = plane + (size_t)ho0 * Wo + wo;
+    for (int r0 = 0; r0 < nrows; r0 += kRB) {
+      float v[kRB];
+#pragma unroll
+      for (int k = 0; k < kRB; ++k) v[k] = (r0 + k < nrows) ? ld1<TL>(col + (size_t)(r0 + k) * Wo) : 0.f;
+#pragma unroll
+      for (int k = 0; k < kRB; ++k) acc = fmaf((r0 + k < nrows) ? wh_s[r0 + k] : 0.f, v[k], acc);
+    }
+    colsum[wo - wlo] = acc;
+  }
+  __syncthreads();
+  const int w = w0 + threadIdx.x;
+  if ((int)threadIdx.x < kTWL && w <= w1) {
+    const int a0 = max((int)ceilf(((float)w - 1.f - tw) * rw) - 1, wlo), a1 = min((int)floorf(((float)w + 1.f - tw) * rw) + 1, whi);
+    float acc = 0.f;
+    for (int wo = a0; wo <= a1; ++wo) {
+      const float fw = fminf(fmaxf(fmaf(sw, (float)wo, tw), 0.f), wmax);
+      acc = fmaf(fmaxf(1.f - fabsf(fw - (float)w), 0.f), colsum[wo - wlo], acc);
+    }
+    TO* o = dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c;
+    acc *= gscale;
+    st1<TO>(o, accumulate ? ld1<TO>(o) + acc : acc);
+  }
+}
+
 }  // namespace
+
+// dy: NCHW gradient of the up-sampled tensor, dx: NHWC gradient of the source; false when the problem is not this kernel's
+bool esn_bilinear_bwd_rows_try(const EsnTensor* dy, const EsnTensor* dx, int align_corners, int accumulate, float gscale,
+                               void* stream) {
+  if (dy->layout != ESN_NCHW || dy->w < 2 * dx->w || dy->h < 2 || dy->w < 2 || dx->h < 1) return false;
+  float sh, th, sw, tw;
+  if (align_corners) {
+    if (dx->h < 2 || dx->w < 2) return false;
+    sh = (float)(dx->h - 1) / (float)(dy->h - 1), th = 0.f;
+    sw = (float)(dx->w - 1) / (float)(dy->w - 1), tw = 0.f;
+  } else {
+    sh = (float)dx->h / (float)dy->h, th = 0.5f * sh - 0.5f;
+    sw = (float)dx->w / (float)dy->w, tw = 0.5f * sw - 0.5f;
+  }
+  const int wtiles = esn_cdiv(dx->w, kTWL);
+  const long long ctas = (long long)dx->n * dx->c * dx->h * wtiles;
+  const int window = (int)((kTWL + 2) / sw) + 8;          // output columns under the hats of kTWL source columns
+  if (window > 8192 || ctas >= (1LL << 31) || (int)(2.f / sh) + 4 > kMaxRows) return false;
+  const int smem = window * (int)sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool lf = dy->dtype == ESN_F32, of = dx->dtype == ESN_F32;
+#define ESN_BLR(TL, TO)                                                                                                      \
+  bilinear_bwd_rows_kernel<TL, TO><<<(unsigned)ctas, 288, smem, st>>>((const TL*)dy->ptr, (TO*)dx->ptr, dx->c, dx->h, dx->w,   \
+                                                                      dy->h, dy->w, dx->c_stride, sh, th, sw, tw, gscale,    \
+                                                                      wtiles, accumulate)
+  if (lf && of) ESN_BLR(float, float);
+  else if (lf) ESN_BLR(float, __nv_bfloat16);
+  else if (of) ESN_BLR(__nv_bfloat16, float);
+  else ESN_BLR(__nv_bfloat16, __nv_bfloat16);
+#undef ESN_BLR
+  return true;
+}
+
 
 extern "C" int esn_maxpool3x3s2_idx_bwd(const EsnTensor* dy, const int32_t* idx, const EsnTensor* dx, int32_t accumulate,
                                         void* stream) {

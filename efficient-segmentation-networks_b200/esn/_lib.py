@@ -131,6 +131,7 @@ SYMBOLS = {
     "esn_bn_act_bwd_apply": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
     "esn_bn_act_train_fwd": (C.c_int, [C.POINTER(EsnBnTrainFwd), C.c_void_p]),
     "esn_bn_act_bwd_fused": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p, C.c_void_p]),
+    "esn_act_bwd": (C.c_int, [C.POINTER(EsnBnBwd), C.c_void_p]),
     "esn_conv2d_wgrad": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
     "esn_wgrad_umma_supported": (C.c_int, [C.POINTER(EsnConv)]),
     "esn_maxpool2x2_bwd": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
@@ -145,6 +146,7 @@ SYMBOLS = {
                                              C.c_int32, C.c_void_p]),
     "esn_dropout_step": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_uint64, C.c_void_p, C.c_float, C.c_int32,
                                    C.c_void_p]),
+    "esn_dropout_mask_nc": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_float, C.c_void_p]),
     "esn_maxpool3x3s2_idx": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p, C.c_void_p]),
     "esn_max_unpool2x2": (C.c_int, [C.POINTER(EsnUnpool), C.c_void_p]),
     "esn_global_avgpool_chunks": (C.c_int, [C.POINTER(EsnTensor)]),

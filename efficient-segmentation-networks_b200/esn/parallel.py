@@ -8,8 +8,15 @@ two scalars sum(w*nll), sum(w) are all-reduced inside CrossEntropyLoss2d), Batch
 per-GPU as in the reference.  Gradients are SUMMED: every rank's loss is already divided by the
 global sum of class weights.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# ESN_DP_DEFER=1: all-reduce every bucket after the last backward kernel instead of from inside the backward.  The backward's
+# BatchNorm layers are co-resident (cooperative) grids that need every SM; an NCCL kernel spinning on a few SMs makes them wait
+# for it, so overlapping 3 MB of all-reduce with the backward can cost more than it hides (measured, DESIGN section 7).
+DEFER_ALLREDUCE = os.environ.get("ESN_DP_DEFER", "0") == "1"
 
 
 class GradBuckets:
@@ -48,6 +55,7 @@ class GradBuckets:
         self.seen = set()
         self.works = []
         self.staged = [dict() for _ in self.buckets]     # parameter -> gradient waiting to be packed
+        self.deferred = []
 
     def grad_ready(self, p, g):
         """Called by the tape when parameter p's gradient is final.  The copy into the flat bucket is deferred until
@@ -61,8 +69,11 @@ class GradBuckets:
             self.seen.add(p)
             self.pending[i] -= 1
             if self.pending[i] == 0:
-                self._pack(i)
-                self._launch(i)
+                if DEFER_ALLREDUCE:
+                    self.deferred.append(i)
+                else:
+                    self._pack(i)
+                    self._launch(i)
         elif self.pending[i] == 0:        # bucket already reduced: late extra contribution (not on the hot-path nets)
             raise RuntimeError("gradient for %r arrived after its bucket was all-reduced" % (tuple(p.shape),))
         return view
@@ -96,6 +107,10 @@ class GradBuckets:
 
     def finish(self):
         """Parameters that produced no gradient this step count as zeros; wait for all reductions."""
+        for i in self.deferred:
+            self._pack(i)
+            self._launch(i)
+        self.deferred = []
         for i, b in enumerate(self.buckets):
             if self.pending[i] > 0:
                 for p in b:

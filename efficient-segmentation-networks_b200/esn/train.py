@@ -498,7 +498,13 @@ class BNActT:
                     ops._call(L.lib.esn_bn_act_bwd_fused, "esn_bn_act_bwd_fused",
                               (C.byref(p), C.c_void_p(sums3.data_ptr() + 8 * BN_REPLICAS * 3 * c)), nb + ops._nbytes(dx))
                     return _fresh(dx) if fresh else dx
-                ops._call(L.lib.esn_bn_act_bwd_reduce, "esn_bn_act_bwd_reduce", (C.byref(p),), nb)
+                if (bn is None and prelu is None and c % 8 == 0 and _v8(xt) and _v8(dy) and _v8(dx)
+                        and (ex is None or _v8(ex))):
+                    # a bare ReLU has no sums anyone reads: dx = dy * [x > 0] is one streaming pass
+                    ops._call(L.lib.esn_act_bwd, "esn_act_bwd", (C.byref(p),), nb + ops._nbytes(dx))
+                    return _fresh(dx) if fresh else dx
+                if bn is not None or prelu is not None:
+                    ops._call(L.lib.esn_bn_act_bwd_reduce, "esn_bn_act_bwd_reduce", (C.byref(p),), nb)
                 ops._call(L.lib.esn_bn_act_bwd_apply, "esn_bn_act_bwd_apply", (C.byref(p),), nb + ops._nbytes(dx))
                 return _fresh(dx) if fresh else dx
 
@@ -797,14 +803,45 @@ def copy_into(tape, x, out):
 _DROPOUT_CALLS = [0]
 
 
-def dropout(tape, x, p, per_channel=False, training=True):
-    """nn.Dropout (element-wise) / nn.Dropout2d (per (n, c) plane): keep mask regenerated from the seed in backward.
-    The seed is drawn from torch's CPU generator, so torch.manual_seed makes runs repeatable."""
+def _scale_nc(src, mask, residual=None, out=None):
+    """out = src * mask[n][c] (+ residual): the per-plane scaling kernel of CGNet's FGlo gate (esn_fglo.cu)."""
+    n, c, h, w = src.shape
+    if out is None:
+        out = ops.new_act(n, c, h, w, src.dtype, src.device)
+    a, b = ops.tdesc(src), ops.tdesc(out)
+    r = ops.tdesc(residual) if residual is not None else ops._NULL
+    ops._call(L.lib.esn_scale_nc, "esn_scale_nc", (C.byref(a), C.c_void_p(mask.data_ptr()), C.byref(r), C.byref(b)),
+              ops._nbytes(src) + ops._nbytes(out) + (ops._nbytes(residual) if residual is not None else 0))
+    return out
+
+
+def dropout(tape, x, p, per_channel=False, training=True, residual=None):
+    """nn.Dropout (element-wise) / nn.Dropout2d (per (n, c) plane); with `residual` (a V) the result is dropout(x) + residual in
+    the same pass (ERFNet's `output + input`, ERFNet.py:62-65).  Element-wise: the keep mask is regenerated from the seed in
+    backward.  Per plane: the N x C scale factors (0 or 1 / (1 - p)) are drawn once into a small table and forward / backward
+    are one per-plane scaling each -- the per-element kernel hashed every element (62 us per ERFNet block on a 17 MB tensor).
+    The seed is drawn from torch's CPU generator, so torch.manual_seed makes runs repeatable; the iteration counter lives on
+    the device, so CUDA-graph replays draw new masks."""
     if not training or p <= 0.0:
-        return x
+        return x if residual is None else add(tape, x, residual)
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) + _DROPOUT_CALLS[0]
     _DROPOUT_CALLS[0] += 1
     n, c, h, w = x.t.shape
+    if per_channel:
+        mask = torch.empty(n * c, dtype=torch.float32, device=x.t.device)
+        ops._call(L.lib.esn_dropout_mask_nc, "esn_dropout_mask_nc",
+                  (C.c_void_p(mask.data_ptr()), C.c_int64(n * c), C.c_uint64(seed),
+                   C.c_void_p(ops.step_counter(x.t.device).data_ptr()), C.c_float(p)))
+        y = V(_scale_nc(x.t, mask, residual=None if residual is None else residual.t))
+
+        def bwd_nc():
+            dy = y.g
+            if residual is not None:
+                residual.add_grad(lambda ex, dst: dy if (ex is None and dst is None) else
+                                  ops.affine_act(dy, None, None, None, L.ACT_NONE, out=dst, residual=ex))
+            x.add_grad(lambda ex, dst: _scale_nc(dy, mask, residual=ex, out=dst))
+        tape.push(bwd_nc)
+        return y
 
     def apply(src):
         dst = ops.new_act(n, c, h, w, src.dtype, src.device)
@@ -820,7 +857,7 @@ def dropout(tape, x, p, per_channel=False, training=True):
         x.add_grad(lambda ex, dst: g if (ex is None and dst is None) else
                    ops.affine_act(g, None, None, None, L.ACT_NONE, out=dst, residual=ex))
     tape.push(bwd)
-    return y
+    return y if residual is None else add(tape, y, residual)
 
 
 # --------------------------------------------------------------------------- autograd glue

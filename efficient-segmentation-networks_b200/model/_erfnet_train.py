@@ -25,6 +25,17 @@ def _down(tape, m, x, dt, image=False):
     n, c, h, w = x.t.shape
     nc = m.conv.out_channels
     cat = T.V(ops.new_act(n, nc + c, h // 2, w // 2, dt, x.t.device))
+    if image and not ops.is_nhwc(x.t) and not ((h | w) & 1):
+        # initial block on the NCHW fp32 image: conv and pool in ONE pass of the stem kernel (raw concat, the conv bias as the
+        # shift); only the conv's weight gradient is recorded -- no gradient flows to the image
+        ct = _convT(m.conv)
+        fwd_prep, _ = ct.preps()
+        ones = torch.ones(nc + c, device=x.t.device)
+        shift = torch.zeros(nc + c, device=x.t.device)
+        shift[:nc] = fwd_prep.shift
+        ops.stem_conv3x3s2(x.t, fwd_prep.w_direct, nc, 1, cat.t, ones, shift, None, ACT_NONE)
+        ct.forward(tape, x, out=cat.slice(0, nc), need_dx=False, dtype=dt, precomputed=True)
+        return T.BNActT(m.bn, ACT_RELU).forward(tape, cat)
     _convT(m.conv).forward(tape, x, out=cat.slice(0, nc), need_dx=not image, dtype=dt)
     T.maxpool2x2(tape, x, cat.slice(nc, nc + c), need_dx=not image)
     return T.BNActT(m.bn, ACT_RELU).forward(tape, cat)
@@ -37,7 +48,7 @@ def _nb1d(tape, m, x):
     y = _relu(tape, _convT(m.conv3x1_2).forward(tape, y))
     y = T.BNActT(m.bn2, ACT_NONE).forward(tape, _convT(m.conv1x3_2).forward(tape, y))
     if m.dropout.p != 0:
-        y = T.dropout(tape, y, m.dropout.p, per_channel=True)
+        return _relu(tape, T.dropout(tape, y, m.dropout.p, per_channel=True, residual=x))     # dropout(y) + x in one pass
     return _relu(tape, T.add(tape, y, x))
 
 

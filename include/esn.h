@@ -367,6 +367,10 @@ typedef struct EsnBnTrainFwd {
 } EsnBnTrainFwd;
 int esn_bn_act_train_fwd(const EsnBnTrainFwd* p, void* stream);
 int esn_bn_act_bwd_fused(const EsnBnBwd* p, uint32_t* barrier, void* stream);
+/* Backward of a bare activation (train_stats = 0, ReLU or none: conv bias + ReLU, ERFNet.py:49,55): dx = dy * act'(x*scale +
+ * shift) * scale (+ extra) in one streaming pass -- nothing is reduced, p->sums / dgamma / dbeta / dalpha are not touched.
+ * bf16 NHWC, channel counts multiples of 8; otherwise ESN_ERR_UNSUPPORTED and the caller uses esn_bn_act_bwd_apply. */
+int esn_act_bwd(const EsnBnBwd* p, void* stream);
 
 /* Weight gradient of a dense or depthwise Conv2d: p->x = forward input, p->y = gradient of the conv
  * output, p->w = fp32 accumulator [kh*kw][Cin/groups][Cout] (zeroed by the caller; atomics).
@@ -396,6 +400,10 @@ int esn_dropout(const EsnTensor* x, const EsnTensor* y, uint64_t seed, float p, 
  * backward of the same replay regenerates them. */
 int esn_dropout_step(const EsnTensor* x, const EsnTensor* y, uint64_t seed, const uint64_t* step, float p,
                      int32_t per_channel, void* stream);
+/* nn.Dropout2d as a table: mask[n*C + c] = 0 or 1 / (1 - p), the same keys, hash and device-side iteration counter as
+ * esn_dropout_step(per_channel = 1); forward and backward are then one esn_scale_nc each (y = x * mask[n][c] (+ residual)).
+ * Replaces aten::feature_dropout of ERFNet.py:62 / ENet.py:86 / ESPNet_v2 in train mode. */
+int esn_dropout_mask_nc(float* mask, int64_t count, uint64_t seed, const uint64_t* step, float p, void* stream);
 
 /* Confusion matrix of predicted masks against labels, accumulated on the device: M[gt * nclass + pred] += 1 for every
  * pixel with 0 <= gt < nclass (ignore label 255 skipped) -- ConfusionMatrix.generateM, utils/metric/metric.py:68-76, as

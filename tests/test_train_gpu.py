@@ -141,6 +141,28 @@ def test_bn_act_fused_launch_matches_multi_launch_bf16(c, c_alloc, act, shape):
     assert torch.allclose(f["rv"], bn_ref.running_var, atol=1e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bare_relu_backward_is_one_pass(dtype):
+    """Conv bias + ReLU without BatchNorm (ERFNet.py:49,55): the backward is dx = dy * [x > 0] (+ the other consumer's
+    gradient) -- one launch in bf16 (esn_act_bwd), the general apply kernel alone in fp32, never a reduction pass."""
+    from esn import ops, train as T
+    from esn._lib import ACT_RELU
+    torch.manual_seed(4)
+    x = torch.randn(2, 64, 9, 33, device="cuda")
+    gy, extra = torch.randn_like(x), torch.randn_like(x)
+    tape = T.Tape()
+    xv = T.V(_nhwc(x, dtype, ops))
+    xv._g = _nhwc(extra, dtype, ops)
+    y = T.BNActT(None, ACT_RELU).forward(tape, xv)
+    assert torch.equal(y.t.float(), F.relu(xv.t.float()))
+    y._g = _nhwc(gy, dtype, ops)
+    n0 = ops.L.lib.esn_launch_count()
+    tape.backward()
+    assert ops.L.lib.esn_launch_count() - n0 == 1
+    want = gy.to(dtype).float() * (xv.t.float() > 0) + extra.to(dtype).float()
+    assert torch.allclose(xv.g.float(), want.to(dtype).float(), atol=1e-6 if dtype == torch.float32 else 2e-2, rtol=1e-2)
+
+
 WG_CASES = [
     # cin, cout, k, stride, pad, dil, groups, H, W
     (64, 32, 3, 1, 1, 1, 1, 12, 20),
@@ -283,18 +305,19 @@ def test_pool_bilinear_ce_backward():
         assert torch.allclose(xv.g.float(), want.bfloat16().float(), atol=1e-2, rtol=1e-2)
         assert torch.equal(xv.g.float() != 0, want.bfloat16().float() != 0) or existing
     # bilinear x8 backward, and a non-integer ratio (hat-function window bounds)
-    for (hi, wi, ho, wo) in ((8, 16, 64, 128), (5, 7, 13, 20), (6, 9, 64, 30)):
-        s = torch.randn(2, 19, hi, wi, device="cuda").requires_grad_(True)
-        ref = F.interpolate(s, (ho, wo), mode="bilinear", align_corners=False)
-        gl = torch.randn_like(ref)
-        gs, = torch.autograd.grad(ref, s, gl)
-        tape = T.Tape()
-        sv = T.V(_nhwc(s.detach(), torch.float32, ops, c_alloc=32))
-        logits, holder = T.bilinear_logits(tape, sv, ho, wo)
-        assert torch.allclose(logits, ref.detach(), atol=1e-5, rtol=1e-5)
-        holder["dlogits"] = gl
-        tape.backward()
-        assert _rel(sv.g, gs) < 1e-5, (hi, wi, ho, wo, _rel(sv.g, gs))
+    for align in (False, True):
+        for (hi, wi, ho, wo) in ((8, 16, 64, 128), (5, 7, 13, 20), (6, 9, 64, 30), (3, 40, 17, 161)):
+            s = torch.randn(2, 19, hi, wi, device="cuda").requires_grad_(True)
+            ref = F.interpolate(s, (ho, wo), mode="bilinear", align_corners=align)
+            gl = torch.randn_like(ref)
+            gs, = torch.autograd.grad(ref, s, gl)
+            tape = T.Tape()
+            sv = T.V(_nhwc(s.detach(), torch.float32, ops, c_alloc=32))
+            logits, holder = T.bilinear_logits(tape, sv, ho, wo, align_corners=align)
+            assert torch.allclose(logits, ref.detach(), atol=1e-5, rtol=1e-5)
+            holder["dlogits"] = gl
+            tape.backward()
+            assert _rel(sv.g, gs) < 1e-5, (align, hi, wi, ho, wo, _rel(sv.g, gs))
     # weighted CE through the autograd Function (normalised gradient)
     lg = (torch.randn(2, 19, 16, 32, device="cuda") * 3).requires_grad_(True)
     lab = fixture.make_labels(2, 16, 32, 19, seed=5).cuda()
