@@ -400,11 +400,58 @@ def kernel_tables(prof):
     return agg, kernels, layers, tot_ms
 
 
+# C-ABI entry point -> substrings of the CUDA kernels it launches (for the in-graph kernel table of training workloads)
+ENTRY_KERNELS = {
+    "esn_bn_act_bwd_fused": ("bn_act_bwd_fused_kernel",), "esn_bn_act_train_fwd": ("bn_act_train_fwd_kernel",),
+    "esn_conv2d_wgrad": ("wgrad_",), "esn_conv2d_umma": ("conv_umma_kernel",), "esn_conv_pair_umma": ("conv_pair_kernel",),
+    "esn_conv2d_direct": ("conv_direct_kernel", "dw_strip_kernel", "dwconv_kernel"), "esn_weighted_ce": ("weighted_ce_kernel",),
+    "esn_bilinear_bwd": ("bilinear_bwd_rows_kernel", "bilinear_bwd_kernel"), "esn_bilinear_bwd_nhwc": ("bilinear_bwd2_kernel",),
+    "esn_bn_act_bwd_apply": ("bn_act_bwd_apply",), "esn_bn_act_bwd_reduce": ("bn_act_bwd_reduce",),
+    "esn_channel_stats": ("channel_stats",), "esn_act_bwd": ("act_bwd_kernel",), "esn_scale_nc": ("scale_nc_kernel",),
+    "esn_dropout": ("dropout_kernel",), "esn_head_bilinear": ("bilinear_head",), "esn_maxpool2x2_bwd": ("maxpool2x2_bwd",),
+    "esn_affine_act": ("pw_vec_kernel", "pw_kernel"), "esn_stem_conv3x3s2": ("stem_",),
+}
+
+
+def graph_kernel_table(graph, agg, step_ms, reps=3):
+    """Device durations of the kernels INSIDE the replayed CUDA graph (CUPTI activity records through torch.profiler, taken
+    after the timed region; no kernel replay, caches warm).  CUDA events cannot bracket kernels inside a graph, and the
+    events-around-eager-launches table over-states short kernels by the launch latency, so this is the table the training
+    roofline is read from.  Returns (per-entry table, per-kernel table, summary)."""
+    from collections import defaultdict
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            graph.replay()
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    per = defaultdict(lambda: [0, 0.0])
+    for e in ev:
+        name = e.name.replace("void ", "").replace("(anonymous namespace)::", "").replace("at::native::", "").split("(")[0][:96]
+        per[name][0] += 1
+        per[name][1] += e.time_range.elapsed_us()
+    kernels = {k: {"launches": round(v[0] / reps, 1), "ms": round(v[1] / reps / 1e3, 4)}
+               for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:40]}
+    entries = {}
+    for entry, subs in ENTRY_KERNELS.items():
+        if entry not in agg:
+            continue
+        ms = sum(v[1] for k, v in per.items() if any(s_ in k for s_ in subs)) / reps / 1e3
+        if ms <= 0:
+            continue
+        entries[entry] = {"launches": agg[entry]["launches"], "ms": round(ms, 4), "share_of_step": round(ms / step_ms, 4),
+                          "alg_GBps": round(agg[entry]["bytes"] / ms / 1e6, 1), "TFLOPs": round(agg[entry]["flops"] / ms / 1e9, 2)}
+    entries = dict(sorted(entries.items(), key=lambda kv: -kv[1]["ms"]))
+    total = sum(v[1] for v in per.values()) / reps / 1e3
+    return entries, kernels, {"sum_of_kernel_ms": round(total, 3), "kernels_per_step": round(len(ev) / reps, 1),
+                              "note": "kernels on the side streams (weight gradients, NCCL) overlap the main chain, so the sum can exceed the step"}
+
+
 def ncu_traffic(workload, kernel):
     """Per-launch DRAM bytes (read + write) of `kernel` from the committed ncu launch list of the same command, or None."""
     fam_names = {"esn_conv2d_umma": "conv_umma_kernel", "esn_conv_pair_umma": "conv_pair_kernel", "esn_conv2d_direct": "conv_direct_kernel",
                  "esn_dab_dw_pair": "dab_dw_pair", "esn_affine_act": "pw_", "esn_conv2d_wgrad": "wgrad", "esn_nb1d_umma": "nb1d_kernel",
-                 "esn_dw_conv": "dw_", "esn_dwconv": "dw"}
+                 "esn_dw_conv": "dw_", "esn_dwconv": "dw", "esn_bn_act_bwd_fused": "bn_act_bwd_fused_kernel",
+                 "esn_bn_act_train_fwd": "bn_act_train_fwd_kernel"}
     for rnd in ("r02", "r01"):
         for stem in (workload, workload.split("_")[0] + ("_train" if "_train_" in workload else "")):
             tpath = os.path.join(ROOT, "profiles", "%s_traffic_%s.json" % (rnd, stem))
@@ -660,6 +707,24 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
                         "frac": round(achieved / hbm_peak, 4), "share_of_step": round(top[1]["ms"] / tot_ms, 4),
                         "definition": "training step: per-kernel algorithmic bytes (|x|+|dy| for a weight gradient, in+out for "
                                       "the others) / CUDA-event time, for the kernel with the largest share"}
+        graph_tables = None
+        if train and graph is not None and world == 1:      # (the graph holds collectives when world > 1: every rank would have to replay)
+            try:
+                g_entries, g_kernels, g_sum = graph_kernel_table(graph, agg, ms_per_step)
+                graph_tables = {"entries": g_entries, "kernels": g_kernels, "summary": g_sum}
+                gk, gv = next(iter(g_entries.items()))
+                achieved = agg[gk]["bytes"] / (gv["ms"] / 1e3) / 1e9
+                roofline = {"unit": "GB/s", "bound": "hbm", "dominant_unit": gk, "achieved": round(achieved, 1), "peak": hbm_peak,
+                            "frac": round(achieved / hbm_peak, 4), "share_of_step": gv["share_of_step"],
+                            "launches_per_step": gv["launches"],
+                            "definition": "training step = one replayed CUDA graph: algorithmic bytes of the entry point's launches "
+                                          "(in + out per launch; |x|+|dy| for a weight gradient; x + dy + dx for a BatchNorm "
+                                          "backward) / their device time inside the replayed graph (CUPTI activity records, "
+                                          "graph_kernels), for the entry point with the largest in-graph time; the "
+                                          "events-around-eager-launches figure of the eager step's top kernel is under per_launch"}
+                traffic = ncu_traffic(wl_name, gk)
+            except Exception as exc:      # noqa: BLE001 -- a diagnostic table must not lose the measured line
+                graph_tables = {"error": repr(exc)[:300]}
         roofline.update({"traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
                          "peak_source": peak_src, "per_launch": per_launch})
         # whole-network figure against SURVEY 8(d)'s block-fused algorithmic bytes
@@ -696,6 +761,8 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "model_roofline": model_roof, "units": dict(list(units.items())[:12]) if units else None,
             "kernels": kernels, "layers": layers}
+    if train and graph is not None and world == 1:
+        line["graph_kernels"] = graph_tables
     if primary and not args.no_cpu_baseline and world == 1:      # contract: rank 0 at N=1 only
         base, _, _ = cpu_reference_leg(model_name, H, W, 4, 1, budget_s=20.0, train=train)
         line["cpu_baseline"] = base

@@ -233,6 +233,73 @@ int esn_check_epilogue(const EsnEpilogue& e, const EsnTensor& y, bool allow_resi
 bool esn_dwconv_try(const EsnConv* p, void* stream, int* rc);   // esn_stencil.cu: vectorised depthwise path (gather)
 bool esn_dw_strip_try(const EsnConv* p, void* stream, int* rc); // esn_dw_strip.cu: register-strip depthwise path (stride 1, 'same')
 
+namespace {
+
+// Transposed depthwise 3x3 / stride 2 (the input gradient of Fast-SCNN's / ESPNetv2's strided depthwise convs,
+// FastSCNN.py:28-45,62-82, ESPNet_v2/Model.py:15-99): y[ho, wo, c] = sum over the taps (r, s) with ho + pad - r and wo + pad - s even
+// of x[(ho + pad - r) / 2, (wo + pad - s) / 2, c] * w[r][s][c] (+ residual).  An output pixel has 1, 2 or 4 such taps, decided by
+// its parities: a thread owns one output pixel x 8 channels and visits exactly those (the generic kernel above walks all nine
+// with a modulo per tap, 4 channels per thread: 1.1 ms per launch on Fast-SCNN's 535 MB gradients, 5.6 ms of its 30.6 ms step).
+__global__ void __launch_bounds__(256) dwT3x3s2_v8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          const float* __restrict__ w, const __nv_bfloat16* __restrict__ res,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          long long total, int Hi, int Wi, int Ho, int Wo, int C, int x_cs, int y_cs,
+                                                          int res_cs, int pad_h, int pad_w) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ng = C / 8;
+  const int c = (int)(idx % ng) * 8;
+  const long long pix = idx / ng;
+  const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho);
+  const long long n = pix / ((long long)Wo * Ho);
+  const int th = ho + pad_h, tw = wo + pad_w;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  // rows: th odd -> r = 1; th even -> r = 0 and r = 2
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int r = (th & 1) ? 1 : 2 * a;
+    if ((th & 1) && a == 1) break;
+    const int t = th - r;
+    if (t < 0) continue;
+    const int hi = t >> 1;
+    if (hi >= Hi) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int s = (tw & 1) ? 1 : 2 * b;
+      if ((tw & 1) && b == 1) break;
+      const int u = tw - s;
+      if (u < 0) continue;
+      const int wi = u >> 1;
+      if (wi >= Wi) continue;
+      float xv[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + ((size_t)(n * Hi + hi) * Wi + wi) * x_cs + c)), xv);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(r * 3 + s) * C + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(r * 3 + s) * C + c + 4));
+      acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
+      acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
+      acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
+      acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
+    }
+  }
+  if (scale || shift) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(acc[j], scale ? __ldg(scale + c + j) : 1.f, shift ? __ldg(shift + c + j) : 0.f);
+  }
+  if (res) {
+    float rv[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(res + (size_t)pix * res_cs + c), rv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += rv[j];
+  }
+  *reinterpret_cast<uint4*>(y + (size_t)pix * y_cs + c) = float_to_bf16x8(acc);
+}
+
+inline bool al16(const void* p, int cs) { return p && cs % 8 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
 extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
   if (!p || !p->w) return ESN_ERR_BAD_ARG;
   const EsnTensor& x = p->x;
@@ -260,6 +327,18 @@ extern "C" int esn_conv2d_direct(const EsnConv* p, void* stream) {
   }
   int rc = esn_check_epilogue(p->ep, y);
   if (rc) return rc;
+  if (dw && p->transposed && p->kh == 3 && p->kw == 3 && p->stride == 2 && p->dil_h == 1 && p->dil_w == 1 && x.dtype == ESN_BF16 &&
+      y.dtype == ESN_BF16 && x.c % 8 == 0 && al16(x.ptr, x.c_stride) && al16(y.ptr, y.c_stride) && ((uintptr_t)p->w % 16) == 0 &&
+      p->ep.act == ESN_ACT_NONE && p->ep.flags == 0 &&
+      (!p->ep.residual.ptr || (p->ep.residual.dtype == ESN_BF16 && al16(p->ep.residual.ptr, p->ep.residual.c_stride)))) {
+    const long long total = (long long)y.n * y.h * y.w * (y.c / 8);
+    dwT3x3s2_v8_kernel<<<esn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)x.ptr, (__nv_bfloat16*)y.ptr, reinterpret_cast<const float*>(p->w),
+        (const __nv_bfloat16*)p->ep.residual.ptr, p->ep.scale, p->ep.shift, total, x.h, x.w, y.h, y.w, y.c, x.c_stride, y.c_stride, p->ep.residual.c_stride,
+        p->pad_h, p->pad_w);
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
+  }
   if (dw && !getenv("ESN_DISABLE_DW_STRIP") && esn_dw_strip_try(p, stream, &rc)) return rc;
   if (dw && esn_dwconv_try(p, stream, &rc)) return rc;
 

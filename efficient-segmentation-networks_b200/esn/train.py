@@ -827,7 +827,19 @@ def dropout(tape, x, p, per_channel=False, training=True, residual=None):
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) + _DROPOUT_CALLS[0]
     _DROPOUT_CALLS[0] += 1
     n, c, h, w = x.t.shape
-    if per_channel:
+    def apply(src):
+        dst = ops.new_act(n, c, h, w, src.dtype, src.device)
+        a, b = ops.tdesc(src), ops.tdesc(dst)
+        ops._call(L.lib.esn_dropout_step, "esn_dropout", (C.byref(a), C.byref(b), C.c_uint64(seed),
+                                                          C.c_void_p(ops.step_counter(src.device).data_ptr()), C.c_float(p),
+                                                          int(per_channel)), ops._nbytes(src) + ops._nbytes(dst))
+        return dst
+
+    def nc_ok(t):       # what esn_scale_nc takes: 4-channel vectors
+        return t is None or (ops.is_nhwc(t) and t.shape[1] % 4 == 0 and t.stride(3) % 4 == 0
+                             and t.data_ptr() % (4 * t.element_size()) == 0)
+
+    if per_channel and nc_ok(x.t) and (residual is None or nc_ok(residual.t)):
         mask = torch.empty(n * c, dtype=torch.float32, device=x.t.device)
         ops._call(L.lib.esn_dropout_mask_nc, "esn_dropout_mask_nc",
                   (C.c_void_p(mask.data_ptr()), C.c_int64(n * c), C.c_uint64(seed),
@@ -839,17 +851,16 @@ def dropout(tape, x, p, per_channel=False, training=True, residual=None):
             if residual is not None:
                 residual.add_grad(lambda ex, dst: dy if (ex is None and dst is None) else
                                   ops.affine_act(dy, None, None, None, L.ACT_NONE, out=dst, residual=ex))
-            x.add_grad(lambda ex, dst: _scale_nc(dy, mask, residual=ex, out=dst))
+
+            def run(ex, dst):
+                if nc_ok(dy) and nc_ok(ex) and nc_ok(dst):
+                    return _scale_nc(dy, mask, residual=ex, out=dst)
+                g = apply(dy)          # odd layouts: the per-element kernel draws the same mask (same keys, hash and counter)
+                return g if (ex is None and dst is None) else ops.affine_act(g, None, None, None, L.ACT_NONE, out=dst, residual=ex)
+            x.add_grad(run)
         tape.push(bwd_nc)
         return y
 
-    def apply(src):
-        dst = ops.new_act(n, c, h, w, src.dtype, src.device)
-        a, b = ops.tdesc(src), ops.tdesc(dst)
-        ops._call(L.lib.esn_dropout_step, "esn_dropout", (C.byref(a), C.byref(b), C.c_uint64(seed),
-                                                          C.c_void_p(ops.step_counter(src.device).data_ptr()), C.c_float(p),
-                                                          int(per_channel)), ops._nbytes(src) + ops._nbytes(dst))
-        return dst
     y = V(apply(x.t))
 
     def bwd():

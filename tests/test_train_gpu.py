@@ -489,8 +489,8 @@ def test_resize_pool_dropout_backward():
         tape.backward()
         assert _rel(xv.g, gx) < 1e-5, (size, h, w)
     # dropout: ~p of the elements dropped, survivors scaled by 1/(1-p), backward uses the same mask
-    x = torch.randn(4, 32, 16, 16, device="cuda")
-    for per_channel in (False, True):
+    for ch, per_channel in ((32, False), (32, True), (35, True)):      # 35 channels: the per-element kernel (odd layout)
+        x = torch.randn(4, ch, 16, 16, device="cuda")
         tape = T.Tape()
         xv = T.V(_nhwc(x, torch.float32, ops))
         y = T.dropout(tape, xv, 0.25, per_channel=per_channel)
