@@ -5,8 +5,9 @@
 // tcgen05 kernel (esn_wgrad_umma.cu) feeds them to the tensor core as MN-major descriptors, which B200 fetches at ~16 B/clk
 // (measured): 222 us for DABNet's 32 -> 32 convs at 8 x 256 x 512, 10x the HBM time of the two tensors; the wmma
 // kernel (esn_wgrad_mma.cu) that served stride 2 runs one tap per CTA and reads both tensors nine times.  Here
-//   * a work unit is one output row segment of TW pixels: its dY segment and the three input row segments it touches are
-//     staged in shared memory with 16-byte cp.async (zero fill = the conv's padding), double buffered;
+//   * a work unit is one output row segment of TW pixels; a CTA walks DOWN a column strip, so with vertical dilation 1 an
+//     input row segment is staged ONCE (16-byte cp.async, zero fill = the conv's padding) into a ring of 3 + stride slots and
+//     serves up to three output rows; the dY segment is double buffered;
 //   * `ldmatrix.trans` delivers both operands in mma.sync's fragment layout straight from the [pixel][channel] tiles, so
 //     nothing is transposed by threads; the 80-byte pixel pitch keeps the eight row addresses of a ldmatrix in different
 //     banks, and for stride 2 even / odd input pixels are stored in two planes so a tap's 16 pixels are contiguous again;
@@ -36,10 +37,12 @@ struct RowsArgs {
   int ntw;            // units per output row
   int npx;            // staged input pixels per row segment
   int plane;          // stride 2: pixels per parity plane (npx = 2 * plane); stride 1: unused
-  int units;          // N * Ho * ntw
-  int units_per_cta;
+  int rows_per_cta;   // output rows of one column strip (n, wt) per CTA
+  int chunks;         // CTAs per strip
   int nci;            // ci tiles
-  int stage_bytes;    // 3 x-row segments + 1 dy segment
+  int ring;           // x-row slots in shared memory: 3 + stride (vertical dilation 1: a row is staged ONCE and serves up to
+                      // three output rows) or 6 (two independent sets of three)
+  int reuse;          // 1: ring mode
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -70,36 +73,39 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_rows_kernel(const RowsArgs 
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci0 = (blockIdx.y % a.nci) * kCT, co0 = (blockIdx.y / a.nci) * kCT;
-  const int u0 = blockIdx.x * a.units_per_cta, u1 = min(a.units, u0 + a.units_per_cta);
+  // CTA -> (column strip (n, wt), chunk of output rows [h0, h1)): consecutive units of a CTA are consecutive output rows
+  const int strip = blockIdx.x / a.chunks, chunk = blockIdx.x % a.chunks;
+  const int n = strip / a.ntw, wt = strip % a.ntw;
+  const int h0 = chunk * a.rows_per_cta, h1 = min(a.Ho, h0 + a.rows_per_cta);
+  const int wo0 = wt * a.tw;
+  const int wi0 = wo0 * a.stride - a.pad_w;                   // input column of staged pixel 0
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const int xrow_bytes = a.npx * kPitch;
+  const uint32_t dybase = sbase + a.ring * xrow_bytes;
+  const int dy_bytes = a.tw * kPitch;
+  // slot of tap row r of output row ho: ring mode -- input row hi = ho*stride - pad + r lives in slot (ho*stride + r) % ring, so
+  // the rows shared with the previous output row are already there; otherwise two sets of three slots
+  auto slot = [&](int ho, int r) { return a.reuse ? (ho * a.stride + r) % a.ring : ((ho - h0) & 1) * 3 + r; };
 
-  // ---- loader: every thread issues 16-byte copies; unit u -> (n, ho, wt)
-  auto load_unit = [&](int u, int stage) {
-    const int wt = u % a.ntw;
-    const int ho = (u / a.ntw) % a.Ho;
-    const int n = u / (a.ntw * a.Ho);
-    const int wo0 = wt * a.tw;
-    const int wi0 = wo0 * a.stride - a.pad_w;                 // input column of staged pixel 0
-    const uint32_t st = sbase + stage * a.stage_bytes;
-    // thread -> (16-byte chunk of 8 channels, pixel lane): no divisions in the copy loops
+  // ---- loader: every thread issues 16-byte copies; thread -> (16-byte chunk of 8 channels, pixel lane): no divisions
+  auto load_unit = [&](int ho, bool first) {
     const int ch = threadIdx.x & 3, pl = threadIdx.x >> 2;
     constexpr int kLanes = kThreads / 4;
     const int cx = ci0 + ch * 8;
     const bool cx_ok = cx < a.Cin;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
+    const int r_lo = (a.reuse && !first) ? 3 - a.stride : 0;  // rows not staged by the previous unit
+    for (int r = r_lo; r < 3; ++r) {
       const int hi = ho * a.stride - a.pad_h + r * a.dil_h;
       const bool row_ok = cx_ok && hi >= 0 && hi < a.Hi;
       const __nv_bfloat16* rowp = a.x + (size_t)((size_t)n * a.Hi + (row_ok ? hi : 0)) * a.Wi * a.x_cs + cx;
-      const uint32_t dst = st + r * xrow_bytes + ch * 16;
+      const uint32_t dst = sbase + slot(ho, r) * xrow_bytes + ch * 16;
       for (int q = pl; q < a.npx; q += kLanes) {
         const int wi = wi0 + q;
         const bool ok = row_ok && wi >= 0 && wi < a.Wi;
         cp_async16(dst + xpos<STRIDE>(q, a.plane) * kPitch, ok ? rowp + (size_t)wi * a.x_cs : a.x, ok);
       }
     }
-    const uint32_t sd = st + 3 * xrow_bytes + ch * 16;
+    const uint32_t sd = dybase + ((ho - h0) & 1) * dy_bytes + ch * 16;
     const int cd = co0 + ch * 8;
     const bool cd_ok = cd < a.Cout;
     const __nv_bfloat16* dyp = a.dy + (size_t)((size_t)n * a.Ho + ho) * a.Wo * a.dy_cs + cd;
@@ -126,17 +132,15 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_rows_kernel(const RowsArgs 
   // B (dy): matrix mi -> k half (mi & 1), n tile of the pair (mi >> 1)
   const int b_k = (mi & 1) * 8 + rr, b_c = (mi >> 1) * 8;
 
-  if (u0 < u1) load_unit(u0, 0);
+  if (h0 < h1) load_unit(h0, true);
   cp_async_commit();
-  for (int u = u0; u < u1; ++u) {
-    const int stage = (u - u0) & 1;
-    if (u + 1 < u1) load_unit(u + 1, stage ^ 1);
+  for (int ho = h0; ho < h1; ++ho) {
+    if (ho + 1 < h1) load_unit(ho + 1, false);      // into slots the current output row does not read
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    const uint32_t st = sbase + stage * a.stage_bytes;
-    const uint32_t sx = st + tr * xrow_bytes;
-    const uint32_t sd = st + 3 * xrow_bytes;
+    const uint32_t sx = sbase + slot(ho, tr) * xrow_bytes;
+    const uint32_t sd = dybase + ((ho - h0) & 1) * dy_bytes;
     const int ksteps = a.tw >> 4;
     // fragments of k-step ks + 1 are loaded before the MMAs of k-step ks are issued (two register sets, loop unrolled by two)
     auto ldfr = [&](int ks, uint32_t (&af)[2][4], uint32_t (&bf)[4][2]) {
@@ -239,12 +243,13 @@ bool esn_wgrad_rows_try(const EsnConv* p, void* stream, int* rc) {
     a.plane = 0;
   }
   a.npx = npx;
-  a.stage_bytes = (3 * npx + a.tw) * kPitch;
-  const int smem = 2 * a.stage_bytes;
+  a.reuse = p->dil_h == 1 ? 1 : 0;
+  a.ring = a.reuse ? 3 + p->stride : 6;
+  const int smem = (a.ring * npx + 2 * a.tw) * kPitch;
   if (smem > 200 * 1024) return false;
   a.nci = esn_cdiv(x.c, kCT);
   const int tiles = a.nci * esn_cdiv(dy.c, kCT);
-  a.units = dy.n * dy.h * a.ntw;
+  const int strips = dy.n * a.ntw;
   const int dev = esn_current_device();
   const int si = p->stride - 1;
   if (g_smem_set[si][dev] < smem) {
@@ -256,15 +261,18 @@ bool esn_wgrad_rows_try(const EsnConv* p, void* stream, int* rc) {
     }
     g_smem_set[si][dev] = 200 * 1024;
   }
-  // CTAs: ~ (CTAs that fit per SM by shared memory, at most 3) x 148 in total, at least 4 units each
+  // CTAs: ~ (CTAs that fit per SM, at most 2 by registers) x 148 in total; a CTA owns >= 8 output rows of one column strip
+  // (the first row of a CTA stages three input rows, every further one `stride`)
   int per_sm = (220 * 1024) / (smem + 1024);
-  if (per_sm > 3) per_sm = 3;                                          // 72 registers x 288 threads: three CTAs per SM
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
-  int gx = (148 * per_sm + tiles - 1) / tiles;
-  if (gx > a.units / 4) gx = a.units / 4;
-  if (gx < 1) gx = 1;
-  a.units_per_cta = esn_cdiv(a.units, gx);
-  gx = esn_cdiv(a.units, a.units_per_cta);
+  int want = (148 * per_sm + tiles - 1) / tiles;              // CTAs along x
+  int chunks = want / strips;                                 // rounded down: one full wave rather than one and a bit
+  if (chunks > dy.h / 8) chunks = dy.h / 8;
+  if (chunks < 1) chunks = 1;
+  a.rows_per_cta = esn_cdiv(dy.h, chunks);
+  a.chunks = esn_cdiv(dy.h, a.rows_per_cta);
+  const int gx = strips * a.chunks;
   dim3 grid(gx, tiles);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (si == 0) wgrad_rows_kernel<1><<<grid, kThreads, smem, st>>>(a);

@@ -475,7 +475,8 @@ class BNActT:
             def run(ex, dst):
                 fresh = dst is None
                 if fresh:       # 16-byte channel vectors also for 35 / 131 / 259 channels (zero tail inside the pixel stride)
-                    dx = ops.new_act(n, c, h, w, dy.dtype, dev, c_alloc=(c + 7) // 8 * 8, zero=c % 8 != 0)
+                    # (the <= 7 pad lanes are never read: consumers are channel slices of the c real channels)
+                    dx = ops.new_act(n, c, h, w, dy.dtype, dev, c_alloc=(c + 7) // 8 * 8)
                 else:
                     dx = dst
                 p = L.EsnBnBwd()
@@ -612,7 +613,7 @@ def maxpool2x2(tape, x, out, need_dx=True):
         def run(ex, dst):
             n, c, h, w = x.t.shape
             dx = dst if dst is not None else (ex if ex is not None else
-                                              ops.new_act(n, c, h, w, dy.dtype, dy.device, c_alloc=(c + 7) // 8 * 8, zero=c % 8 != 0))
+                                              ops.new_act(n, c, h, w, dy.dtype, dy.device, c_alloc=(c + 7) // 8 * 8))
             dxd, dyd, xd = ops.tdesc(dx), ops.tdesc(dy), ops.tdesc(x.t)
             ops._call(L.lib.esn_maxpool2x2_bwd, "esn_maxpool2x2_bwd", (C.byref(xd), C.byref(dyd), C.byref(dxd),
                                                                       int(ex is not None)), 2 * ops._nbytes(dx))

@@ -79,8 +79,23 @@ def dabnet_train_forward(model, input):
     d3 = model.down_1(d2)
 
     def cat_buffer(c, like):
+        # every one of the c channels is written by a producer; the <= 7 pad lanes of the 16-byte-aligned pixel stride are read
+        # (full vectors) but never used by the BatchNorm kernels, so the buffer needs no fill
         hh, ww = like.shape[2:]
-        return T.V(ops.new_act(n, c, hh, ww, dt, dev, c_alloc=(c + 7) // 8 * 8, zero=True))
+        return T.V(ops.new_act(n, c, hh, ww, dt, dev, c_alloc=(c + 7) // 8 * 8))
+
+    def padded_out(key, c, like, c_alloc):
+        # BNPReLU output read by a tensor-core conv over its zero-padded width (35 -> 64, 131 -> 192, 259 -> 320): the BatchNorm
+        # kernel only ever writes the c real channels, so the zero tail is written ONCE and the buffer kept on the model
+        # (a 134 / 100 / 42 MB fill per step otherwise)
+        hh, ww = like.shape[2:]
+        cache = model.__dict__.setdefault("_esn_train_bufs", {})
+        shape = (n, hh, ww, dt, str(dev))
+        held = cache.get(key)
+        if held is None or held[0] != shape:          # one buffer per role: a new batch shape replaces the old buffer
+            held = (shape, ops.new_act(n, c, hh, ww, dt, dev, c_alloc=c_alloc, zero=True))
+            cache[key] = held
+        return T.V(held[1])
 
     x = T.V(input)
     y = _conv(tape, model.init_conv[0], x, need_dx=False, dtype=dt)
@@ -88,8 +103,7 @@ def dabnet_train_forward(model, input):
     cat0 = cat_buffer(35, d1)
     _conv(tape, model.init_conv[2], y, out=cat0.slice(0, 32))
     ops.affine_act(d1, None, None, None, ACT_NONE, out=cat0.t[:, 32:35])
-    c0 = _bnprelu(tape, model.bn_prelu_1, cat0, out=T.V(ops.new_act(n, 35, d1.shape[2], d1.shape[3], dt, dev,
-                                                                       c_alloc=64, zero=True)))
+    c0 = _bnprelu(tape, model.bn_prelu_1, cat0, out=padded_out("c0", 35, d1, 64))
 
     cat1 = cat_buffer(131, d2)
     y = _down(tape, model.downsample_1, c0, cat1.slice(64, 128), dt)
@@ -97,8 +111,7 @@ def dabnet_train_forward(model, input):
     for i, blk in enumerate(blocks):
         y = _dab_module(tape, blk, y, out=cat1.slice(0, 64) if i == len(blocks) - 1 else None)
     ops.affine_act(d2, None, None, None, ACT_NONE, out=cat1.t[:, 128:131])
-    c1 = _bnprelu(tape, model.bn_prelu_2, cat1, out=T.V(ops.new_act(n, 131, d2.shape[2], d2.shape[3], dt, dev,
-                                                                       c_alloc=192, zero=True)))
+    c1 = _bnprelu(tape, model.bn_prelu_2, cat1, out=padded_out("c1", 131, d2, 192))
 
     cat2 = cat_buffer(259, d3)
     y = _down(tape, model.downsample_2, c1, cat2.slice(128, 256), dt)
@@ -111,7 +124,7 @@ def dabnet_train_forward(model, input):
     if dt == torch.bfloat16:
         # 1x1 classifier 259 -> 19 on the tensor cores in all three directions (forward, input gradient, weight gradient):
         # the BNPReLU output lives in a 320-channel buffer with a zero tail, the scores in a 32-channel one (zero weight rows)
-        c2 = _bnprelu(tape, model.bn_prelu_3, cat2, out=T.V(ops.new_act(n, 259, hh, ww, dt, dev, c_alloc=320, zero=True)))
+        c2 = _bnprelu(tape, model.bn_prelu_3, cat2, out=padded_out("c2", 259, d3, 320))
         wide = T.V(ops.new_act(n, 32, hh, ww, dt, dev))
         _convT(model.classifier[0].conv, 320, 32).forward(tape, c2, out=wide)
         scores = wide.slice(0, classes)
