@@ -75,54 +75,67 @@ __global__ void __launch_bounds__(256) max_unpool2x2_bwd_kernel(const T* __restr
 constexpr int kTWL = 32;
 constexpr int kRB = 24;
 constexpr int kMaxRows = 96;      // output rows under one vertical hat (2 / s + 3): up-sampling factors up to ~46
-template <typename TL, typename TO>
+template <typename TL, typename TO, int HG>
 __global__ void __launch_bounds__(288) bilinear_bwd_rows_kernel(const TL* __restrict__ dl, TO* __restrict__ dlow, int C, int Hi, int Wi,
                                                                 int Ho, int Wo, int low_cs, float sh, float th, float sw, float tw,
-                                                                float gscale, int wtiles, int accumulate) {
-  extern __shared__ float colsum[];
+                                                                float gscale, int wtiles, int hgroups, int window, int accumulate) {
+  // HG consecutive source rows per CTA: their vertical hats overlap by half, so the union of output rows is (HG + 1) / s
+  // instead of 2 HG / s -- each output row is loaded once and feeds (at most two of) the HG column sums
+  extern __shared__ float colsum[];           // [HG][window]
   const int wt = blockIdx.x % wtiles;
-  const int h = (blockIdx.x / wtiles) % Hi;
-  const int c = (blockIdx.x / (wtiles * Hi)) % C;
-  const int n = blockIdx.x / (wtiles * Hi * C);
+  const int hg = (blockIdx.x / wtiles) % hgroups;
+  const int c = (blockIdx.x / (wtiles * hgroups)) % C;
+  const int n = blockIdx.x / (wtiles * hgroups * C);
+  const int h0 = hg * HG, h1 = min(h0 + HG, Hi) - 1;
   const int w0 = wt * kTWL, w1 = min(w0 + kTWL, Wi) - 1;
   const float rh = 1.f / sh, rw = 1.f / sw;
-  // outputs o with |s*o + t - h| < 1, one extra on each side for rounding; the border clamps only add outputs that the
-  // image bounds cut off anyway
-  const int ho0 = max((int)ceilf(((float)h - 1.f - th) * rh) - 1, 0), ho1 = min((int)floorf(((float)h + 1.f - th) * rh) + 1, Ho - 1);
+  // outputs o with |s*o + t - h| < 1 for some h of the group, one extra on each side for rounding; the border clamps only
+  // add outputs that the image bounds cut off anyway
+  const int ho0 = max((int)ceilf(((float)h0 - 1.f - th) * rh) - 1, 0), ho1 = min((int)floorf(((float)h1 + 1.f - th) * rh) + 1, Ho - 1);
   const int wlo = max((int)ceilf(((float)w0 - 1.f - tw) * rw) - 1, 0), whi = min((int)floorf(((float)w1 + 1.f - tw) * rw) + 1, Wo - 1);
   const TL* plane = dl + ((size_t)n * C + c) * Ho * Wo;
   const float hmax = (float)(Hi - 1), wmax = (float)(Wi - 1);
   // the vertical weights are the same for every thread of the CTA: computed once (ncu: the first version of this kernel
   // rebuilt them per element and was instruction-bound -- 295 M warp instructions, SM pipes 85 % busy at 1 TB/s)
-  __shared__ float wh_s[kMaxRows];
+  __shared__ float wh_s[HG][kMaxRows];
   const int nrows = ho1 - ho0 + 1;
-  if ((int)threadIdx.x < nrows) {
-    const float fh = fminf(fmaxf(fmaf(sh, (float)(ho0 + (int)threadIdx.x), th), 0.f), hmax);
-    wh_s[threadIdx.x] = fmaxf(1.f - fabsf(fh - (float)h), 0.f);
+  for (int i = threadIdx.x; i < HG * nrows; i += blockDim.x) {
+    const int j = i / nrows, r = i - j * nrows;
+    const float fh = fminf(fmaxf(fmaf(sh, (float)(ho0 + r), th), 0.f), hmax);
+    wh_s[j][r] = (h0 + j <= h1) ? fmaxf(1.f - fabsf(fh - (float)(h0 + j)), 0.f) : 0.f;
   }
   __syncthreads();
   for (int wo = wlo + threadIdx.x; wo <= whi; wo += blockDim.x) {
-    float acc = 0.f;
+    float acc[HG];
+#pragma unroll
+    for (int j = 0; j < HG; ++j) acc[j] = 0.f;
     const TL* col = plane + (size_t)ho0 * Wo + wo;
     for (int r0 = 0; r0 < nrows; r0 += kRB) {
       float v[kRB];
 #pragma unroll
       for (int k = 0; k < kRB; ++k) v[k] = (r0 + k < nrows) ? ld1<TL>(col + (size_t)(r0 + k) * Wo) : 0.f;
 #pragma unroll
-      for (int k = 0; k < kRB; ++k) acc = fmaf((r0 + k < nrows) ? wh_s[r0 + k] : 0.f, v[k], acc);
+      for (int k = 0; k < kRB; ++k)
+        if (r0 + k < nrows) {
+#pragma unroll
+          for (int j = 0; j < HG; ++j) acc[j] = fmaf(wh_s[j][r0 + k], v[k], acc[j]);
+        }
     }
-    colsum[wo - wlo] = acc;
+#pragma unroll
+    for (int j = 0; j < HG; ++j) colsum[j * window + wo - wlo] = acc[j];
   }
   __syncthreads();
-  const int w = w0 + threadIdx.x;
-  if ((int)threadIdx.x < kTWL && w <= w1) {
+  // HG x kTWL results: thread -> (row of the group, source column)
+  const int j = threadIdx.x / kTWL, w = w0 + (int)threadIdx.x % kTWL;
+  if (j < HG && h0 + j <= h1 && w <= w1) {
     const int a0 = max((int)ceilf(((float)w - 1.f - tw) * rw) - 1, wlo), a1 = min((int)floorf(((float)w + 1.f - tw) * rw) + 1, whi);
     float acc = 0.f;
+    const float* cs = colsum + j * window - wlo;
     for (int wo = a0; wo <= a1; ++wo) {
       const float fw = fminf(fmaxf(fmaf(sw, (float)wo, tw), 0.f), wmax);
-      acc = fmaf(fmaxf(1.f - fabsf(fw - (float)w), 0.f), colsum[wo - wlo], acc);
+      acc = fmaf(fmaxf(1.f - fabsf(fw - (float)w), 0.f), cs[wo], acc);
     }
-    TO* o = dlow + ((size_t)((size_t)n * Hi + h) * Wi + w) * low_cs + c;
+    TO* o = dlow + ((size_t)((size_t)n * Hi + h0 + j) * Wi + w) * low_cs + c;
     acc *= gscale;
     st1<TO>(o, accumulate ? ld1<TO>(o) + acc : acc);
   }
@@ -146,21 +159,31 @@ bool esn_bilinear_bwd_rows_try(const EsnTensor* dy, const EsnTensor* dx, int ali
     sw = (float)dx->w / (float)dy->w, tw = 0.5f * sw - 0.5f;
   }
   const int wtiles = esn_cdiv(dx->w, kTWL);
-  const long long ctas = (long long)dx->n * dx->c * dx->h * wtiles;
   const int window = (int)((kTWL + 2) / sw) + 8;          // output columns under the hats of kTWL source columns
-  if (window > 8192 || ctas >= (1LL << 31) || (int)(2.f / sh) + 4 > kMaxRows) return false;
-  const int smem = window * (int)sizeof(float);
+  // four source rows per CTA when the union of their output rows fits the weight table, else one
+  const int hgsize = ((int)(5.f / sh) + 4 <= kMaxRows && dx->h >= 4) ? 4 : 1;
+  if ((int)((hgsize + 1) / sh) + 4 > kMaxRows) return false;
+  const int hgroups = esn_cdiv(dx->h, hgsize);
+  const long long ctas = (long long)dx->n * dx->c * hgroups * wtiles;
+  if (window > 8192 || ctas >= (1LL << 31)) return false;
+  const int smem = hgsize * window * (int)sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool lf = dy->dtype == ESN_F32, of = dx->dtype == ESN_F32;
-#define ESN_BLR(TL, TO)                                                                                                      \
-  bilinear_bwd_rows_kernel<TL, TO><<<(unsigned)ctas, 288, smem, st>>>((const TL*)dy->ptr, (TO*)dx->ptr, dx->c, dx->h, dx->w,   \
-                                                                      dy->h, dy->w, dx->c_stride, sh, th, sw, tw, gscale,    \
-                                                                      wtiles, accumulate)
+#define ESN_BLR2(TL, TO, HG)                                                                                                  \
+  bilinear_bwd_rows_kernel<TL, TO, HG><<<(unsigned)ctas, 288, smem, st>>>((const TL*)dy->ptr, (TO*)dx->ptr, dx->c, dx->h, dx->w, \
+                                                                          dy->h, dy->w, dx->c_stride, sh, th, sw, tw, gscale,  \
+                                                                          wtiles, hgroups, window, accumulate)
+#define ESN_BLR(TL, TO)                    \
+  do {                                     \
+    if (hgsize == 4) ESN_BLR2(TL, TO, 4);  \
+    else ESN_BLR2(TL, TO, 1);              \
+  } while (0)
   if (lf && of) ESN_BLR(float, float);
   else if (lf) ESN_BLR(float, __nv_bfloat16);
   else if (of) ESN_BLR(__nv_bfloat16, float);
   else ESN_BLR(__nv_bfloat16, __nv_bfloat16);
 #undef ESN_BLR
+#undef ESN_BLR2
   return true;
 }
 

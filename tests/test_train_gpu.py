@@ -306,7 +306,7 @@ def test_pool_bilinear_ce_backward():
         assert torch.equal(xv.g.float() != 0, want.bfloat16().float() != 0) or existing
     # bilinear x8 backward, and a non-integer ratio (hat-function window bounds)
     for align in (False, True):
-        for (hi, wi, ho, wo) in ((8, 16, 64, 128), (5, 7, 13, 20), (6, 9, 64, 30), (3, 40, 17, 161)):
+        for (hi, wi, ho, wo) in ((8, 16, 64, 128), (5, 7, 13, 20), (6, 9, 64, 30), (3, 40, 17, 161), (9, 20, 70, 161), (13, 33, 52, 140)):
             s = torch.randn(2, 19, hi, wi, device="cuda").requires_grad_(True)
             ref = F.interpolate(s, (ho, wo), mode="bilinear", align_corners=align)
             gl = torch.randn_like(ref)
