@@ -774,10 +774,12 @@ template <> struct Raw4<__nv_bfloat16> {
   }
 };
 
-template <typename TX, typename TG, int KH, int KW, int LSEG>
+template <typename TX, typename TG, int KH, int KW, int LSEG, int S = 1>
 __global__ void __launch_bounds__(kStatThreads) wgrad_dw_strip_kernel(const WgradArgs a, const int rows_per_chunk, const int nstrips,
                                                                       const int nchunks) {
-  constexpr int T = KH * KW, XC = LSEG + KW - 1;
+  // S = conv stride (1, or 2 for the strided depthwise convs of Fast-SCNN / ESPNetv2): an output row then advances the input
+  // window by S rows (KH - S rows stay in registers) and output column p reads input columns p*S .. p*S + KW - 1
+  constexpr int T = KH * KW, XC = (LSEG - 1) * S + KW;
   __shared__ float red[kStatThreads][4];
   const int C = a.Cout;
   const int CG = min(C / 4, 64);
@@ -804,15 +806,16 @@ __global__ void __launch_bounds__(kStatThreads) wgrad_dw_strip_kernel(const Wgra
       const TX* xr = xn + (size_t)(rv ? hi : 0) * a.Wi * a.x_cs;
 #pragma unroll
       for (int j = 0; j < XC; ++j) {
-        const int wi = wb - a.pad_w + j;
+        const int wi = wb * S - a.pad_w + j;
         dst[j].zero();
         if (rv && wi >= 0 && wi < a.Wi) dst[j].load(xr + (size_t)wi * a.x_cs);
       }
     };
 #pragma unroll
-    for (int r = 0; r + 1 < KH; ++r) load_row(R[r], h_begin - a.pad_h + r);
+    for (int r = 0; r + S < KH; ++r) load_row(R[r], h_begin * S - a.pad_h + r);
     for (int ho = h_begin; ho < h_end; ++ho) {
-      load_row(R[KH - 1], ho - a.pad_h + KH - 1);
+#pragma unroll
+      for (int r = (KH - S > 0 ? KH - S : 0); r < KH; ++r) load_row(R[r], ho * S - a.pad_h + r);
       Raw4<TG> G[LSEG];
       const TG* gr = gn + (size_t)ho * a.Wo * a.dy_cs;
 #pragma unroll
@@ -827,7 +830,7 @@ __global__ void __launch_bounds__(kStatThreads) wgrad_dw_strip_kernel(const Wgra
         for (int r = 0; r < KH; ++r)
 #pragma unroll
           for (int q = 0; q < KW; ++q) {
-            const float4 xv = R[r][p + q].f4();
+            const float4 xv = R[r][p * S + q].f4();
             acc[r * KW + q][0] = fmaf(xv.x, g.x, acc[r * KW + q][0]);
             acc[r * KW + q][1] = fmaf(xv.y, g.y, acc[r * KW + q][1]);
             acc[r * KW + q][2] = fmaf(xv.z, g.z, acc[r * KW + q][2]);
@@ -835,9 +838,9 @@ __global__ void __launch_bounds__(kStatThreads) wgrad_dw_strip_kernel(const Wgra
           }
       }
 #pragma unroll
-      for (int r = 0; r + 1 < KH; ++r)
+      for (int r = 0; r + S < KH; ++r)
 #pragma unroll
-        for (int j = 0; j < XC; ++j) R[r][j] = R[r + 1][j];
+        for (int j = 0; j < XC; ++j) R[r][j] = R[r + S][j];
     }
   }
 #pragma unroll
@@ -1222,7 +1225,8 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   static const bool dw_old = getenv("ESN_WGRAD_DW_PER_TAP") != nullptr, stem_old = getenv("ESN_WGRAD_STEM_V1") != nullptr;
   static const bool dw_nostrip = getenv("ESN_WGRAD_DW_NOSTRIP") != nullptr;
   const bool dw_k = (p->kh == 3 && p->kw == 3) || (p->kh == 3 && p->kw == 1) || (p->kh == 1 && p->kw == 3);
-  if (dw && !dw_old && !dw_nostrip && dw_k && p->stride == 1 && p->dil_h == 1 && p->dil_w == 1 && dy.c % 4 == 0 &&
+  const bool s2_33 = p->stride == 2 && p->kh == 3 && p->kw == 3;
+  if (dw && !dw_old && !dw_nostrip && dw_k && (p->stride == 1 || s2_33) && p->dil_h == 1 && p->dil_w == 1 && dy.c % 4 == 0 &&
       x.c_stride % 4 == 0 && dy.c_stride % 4 == 0 && ((uintptr_t)x.ptr % (xf ? 16 : 8)) == 0 &&
       ((uintptr_t)dy.ptr % (gf ? 16 : 8)) == 0) {
     constexpr int LSEG = 4;
@@ -1244,7 +1248,12 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
       else if (gf) wgrad_dw_strip_kernel<__nv_bfloat16, float, KH, KW, LSEG><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks); \
       else wgrad_dw_strip_kernel<__nv_bfloat16, __nv_bfloat16, KH, KW, LSEG><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks); \
     } while (0)
-    if (p->kh == 3 && p->kw == 3) ESN_DWSTRIP(3, 3);
+    if (s2_33) {
+      if (xf && gf) wgrad_dw_strip_kernel<float, float, 3, 3, LSEG, 2><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks);
+      else if (xf) wgrad_dw_strip_kernel<float, __nv_bfloat16, 3, 3, LSEG, 2><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks);
+      else if (gf) wgrad_dw_strip_kernel<__nv_bfloat16, float, 3, 3, LSEG, 2><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks);
+      else wgrad_dw_strip_kernel<__nv_bfloat16, __nv_bfloat16, 3, 3, LSEG, 2><<<grid, kStatThreads, 0, st>>>(a, rpc, nstrips, nchunks);
+    } else if (p->kh == 3 && p->kw == 3) ESN_DWSTRIP(3, 3);
     else if (p->kh == 3) ESN_DWSTRIP(3, 1);
     else ESN_DWSTRIP(1, 3);
 #undef ESN_DWSTRIP
