@@ -1189,6 +1189,7 @@ bool esn_bilinear_bwd_rows_try(const EsnTensor* dy, const EsnTensor* dx, int ali
                                void* stream);                      // esn_train3.cu
 bool esn_wgrad_umma_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_umma.cu (tcgen05, stride 1)
 bool esn_wgrad_rows_try(const EsnConv* p, void* stream, int* rc);  // esn_wgrad_rows.cu (mma.sync, dense 3x3, all taps per pass)
+bool esn_wgrad_taps3_try(const EsnConv* p, void* stream, int* rc); // esn_wgrad_taps3.cu (mma.sync, dense 3x1 / 1x3)
 
 extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   // p->x: forward input, p->y: gradient of the conv output, p->w: fp32 dW accumulator
@@ -1207,6 +1208,7 @@ extern "C" int esn_conv2d_wgrad(const EsnConv* p, void* stream) {
   {
     int rc = ESN_OK;   // bf16 dense convs: tensor-core path
     if (!dw && !nchw && esn_wgrad_rows_try(p, stream, &rc)) return rc;
+    if (!dw && !nchw && esn_wgrad_taps3_try(p, stream, &rc)) return rc;
     if (!dw && !nchw && esn_wgrad_umma_try(p, stream, &rc)) return rc;
     if (!dw && !nchw && esn_wgrad_mma_try(p, stream, &rc)) return rc;
   }

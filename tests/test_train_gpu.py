@@ -186,6 +186,11 @@ WG_CASES = [
     (40, 24, 3, 2, 1, 1, 1, 15, 33),
     (64, 64, 3, 1, 4, 4, 1, 18, 140),
     (128, 64, 3, 1, 1, 1, 1, 16, 64),
+    (64, 64, (3, 1), 1, (1, 0), (1, 1), 1, 20, 150),      # dense three-tap convs on esn_wgrad_taps3.cu: row ring (dilation 1),
+    (64, 64, (3, 1), 1, (4, 0), (4, 1), 1, 24, 70),       # dilated rows (two sets of three slots), 1x3 taps as pixel offsets,
+    (64, 64, (1, 3), 1, (0, 8), (1, 8), 1, 12, 140),      # ragged row segments, 2 x 2 / single channel tiles
+    (16, 16, (1, 3), 1, (0, 1), (1, 1), 1, 18, 260),
+    (32, 16, (3, 1), 1, (2, 0), (2, 1), 1, 17, 48),
     (3, 3, 3, 1, 1, 1, 1, 9, 14),
 ]
 
