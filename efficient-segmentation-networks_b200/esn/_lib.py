@@ -91,6 +91,11 @@ class EsnHead(C.Structure):
                 ("align_corners", C.c_int32)]
 
 
+class EsnHeadT3(C.Structure):
+    _fields_ = [("x", EsnTensor), ("wfrag", C.c_void_p), ("bias", C.c_void_p), ("mask", C.c_void_p),
+                ("classes", C.c_int32), ("_pad", C.c_int32)]
+
+
 class EsnAugItem(C.Structure):
     _fields_ = [("img", C.c_void_p), ("label", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("rh", C.c_int32), ("rw", C.c_int32),
                 ("scale", C.c_double), ("h_off", C.c_int32), ("w_off", C.c_int32), ("flip", C.c_int32), ("do_scale", C.c_int32)]
@@ -115,6 +120,7 @@ SYMBOLS = {
     "esn_dab_dw_pair": (C.c_int, [C.POINTER(EsnDabPair), C.c_void_p]),
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
+    "esn_head_convt3x3s2_mask": (C.c_int, [C.POINTER(EsnHeadT3), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
     "esn_augment_max_batch": (C.c_int32, []),
     "esn_augment_u8": (C.c_int, [C.POINTER(EsnAugItem), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_void_p,

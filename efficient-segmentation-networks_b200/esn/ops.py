@@ -664,6 +664,41 @@ def head_bilinear(x, classes, out_h, out_w, want_logits=True, want_mask=False, l
                  want_logits, want_mask, logits_dtype, align_corners)
 
 
+def pack_convt3x3s2_frags(weight, classes):
+    """ConvTranspose2d(16, classes, 3, 2, 1, 1).weight (16, classes, 3, 3) -> the bf16 B fragments of esn_head_convt3x3s2_mask
+    (include/esn.h): int32 [9 pairs][3 class tiles][32 lanes][2]."""
+    w = weight.detach().float()
+    assert w.shape[0] == 16 and w.shape[2:] == (3, 3) and classes <= 24
+    pairs = ((0, 0, 0, 0), (0, 1, 0, 0), (0, 1, 0, 1), (1, 0, 0, 0), (1, 0, 1, 0), (1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 1, 0), (1, 1, 1, 1))
+    B = torch.zeros(9, 16, 24, dtype=torch.float32, device=w.device)
+    for p, (a, b, dy, dx) in enumerate(pairs):
+        B[p, :, :classes] = w[:, :classes, a + 1 - 2 * dy, b + 1 - 2 * dx]
+    lane = torch.arange(32, device=w.device)
+    g, t = lane // 4, lane % 4
+    frag = torch.empty(9, 3, 32, 2, 2, dtype=torch.bfloat16, device=w.device)       # [..., register, (low, high)]
+    for nt in range(3):
+        for r in range(2):
+            k0 = 2 * t + 8 * r
+            frag[:, nt, :, r, 0] = B[:, k0, nt * 8 + g].to(torch.bfloat16)
+            frag[:, nt, :, r, 1] = B[:, k0 + 1, nt * 8 + g].to(torch.bfloat16)
+    return frag.contiguous().view(torch.int32).reshape(9, 3, 32, 2).contiguous()
+
+
+def head_convt3x3s2_mask(x, wfrag, bias, classes):
+    """uint8 argmax mask (N, 2h, 2w) of ConvTranspose2d(16, classes, 3, 2, 1, 1)(x) in one launch (tensor cores, the scores
+    stay in registers); None when the entry point does not take the shape (the caller then runs conv + head)."""
+    n, c, h, w = x.shape
+    if not (x.dtype == torch.bfloat16 and is_nhwc(x) and c == 16 and w % 16 == 0 and classes <= 24):
+        return None
+    mask = torch.empty((n, 2 * h, 2 * w), dtype=torch.uint8, device=x.device)
+    p = L.EsnHeadT3()
+    p.x, p.wfrag, p.mask, p.classes = tdesc(x), wfrag.data_ptr(), mask.data_ptr(), classes
+    p.bias = bias.data_ptr() if bias is not None else None
+    _call(L.lib.esn_head_convt3x3s2_mask, "esn_head_convt3x3s2_mask", (C.byref(p),), _nbytes(x) + mask.numel(),
+          2 * n * h * w * 9 * 16 * classes)
+    return mask
+
+
 def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, sums=None, gnorm=None, gout=None,
                 prob_out=None, keep_thresh=None):
     """Returns (sums[2] = [sum w*nll, sum w], dlogits or None); dlogits are scaled by gout/gnorm

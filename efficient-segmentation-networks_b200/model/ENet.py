@@ -14,6 +14,8 @@ block (ENet.py:53-89), so ``state_dict`` carries the same aliased keys.  Inferen
 * head: ConvTranspose2d(16, classes, 3, s2) on the tensor cores (Cout padded to 32) + identity head
   kernel writing NCHW logits and/or the argmax mask.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -49,6 +51,8 @@ def _cba(conv, bn, activation, device, pre_residual=False, cout_pad=None):
     prep.ep_flags = _PRE if pre_residual else 0
     return prep
 
+
+FUSED_HEAD = os.environ.get("ESN_ENET_FUSED_HEAD", "1") != "0"      # transposed conv + argmax as one tensor-core launch
 
 class InitialBlock(PrepMixin, nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, padding=0, bias=False, relu=True):
@@ -248,9 +252,16 @@ class ENet(PrepMixin, nn.Module):
 
     def _build_prep(self, device):
         classes = self.transposed_conv.out_channels
-        return ops.ConvPrep(self.transposed_conv, device=device, cout_pad=(classes + 7) // 8 * 8), classes
+        tc = self.transposed_conv
+        # bf16 mask-only path: transposed conv + argmax in one launch on the tensor cores (esn_head_convt3x3s2_mask)
+        frags = None
+        if (tc.in_channels == 16 and classes <= 24 and tc.kernel_size == (3, 3) and tc.stride == (2, 2) and tc.padding == (1, 1)
+                and tc.output_padding == (1, 1) and tc.dilation == (1, 1) and tc.groups == 1):
+            frags = (ops.pack_convt3x3s2_frags(tc.weight.to(device), classes),
+                     None if tc.bias is None else tc.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+        return ops.ConvPrep(tc, device=device, cout_pad=(classes + 7) // 8 * 8), classes, frags
 
-    def _scores(self, x):
+    def _features(self, x):
         ops.require_cuda(x, "ENet")
         if self.training:
             _no_train(self)
@@ -266,8 +277,11 @@ class ENet(PrepMixin, nn.Module):
         x = self.upsample4_0(x, i2)
         x = self.regular4_2(self.regular4_1(x))
         x = self.upsample5_0(x, i1)
-        x = self.regular5_1(x)
-        head, classes = self.prep(x.device)
+        return self.regular5_1(x)
+
+    def _scores(self, x):
+        x = self._features(x)
+        head, classes, _ = self.prep(x.device)
         s = ops.conv2d(x, head)                       # (N, classes padded to 24, H, W) NHWC
         return s[:, :classes], classes
 
@@ -284,7 +298,16 @@ class ENet(PrepMixin, nn.Module):
 
     @torch.no_grad()
     def predict_mask(self, x, with_logits=False):
-        s, classes = self._scores(x)
+        if not with_logits and FUSED_HEAD:
+            f = self._features(x)
+            _, classes, frags = self.prep(f.device)
+            mask = ops.head_convt3x3s2_mask(f, frags[0], frags[1], classes) if frags is not None else None
+            if mask is not None:          # bf16 features: the full-resolution scores never leave the registers
+                return mask
+            head, classes, _ = self.prep(f.device)
+            s = ops.conv2d(f, head)[:, :classes]
+        else:
+            s, classes = self._scores(x)
         n, _, h, w = s.shape
         ldt = torch.bfloat16 if s.dtype == torch.bfloat16 else torch.float32
         logits, mask = ops.head_bilinear(s, classes, h, w, with_logits, True, ldt)

@@ -253,6 +253,24 @@ typedef struct EsnHead {
 int esn_head_convt2x2(const EsnHead* p, void* stream);
 int esn_head_bilinear(const EsnHead* p, void* stream);
 
+/* ENet's head as ONE launch: ConvTranspose2d(16, classes <= 24, 3, stride 2, padding 1, output_padding 1, bias optional)
+ * (ENet.py:229-236) fused with the argmax over classes (test.py:79-82: first maximum wins) on the warp-level tensor cores;
+ * the full-resolution scores are never written.  x: bf16 NHWC with 16 channels, width a multiple of 16; mask: (N, 2h, 2w)
+ * uint8.  wfrag: the bf16 weights in mma.m16n8k16 B-fragment order, [9 pairs][3 class tiles][32 lanes][2] 32-bit words:
+ * pair p = (output position (a, b), neighbour (dy, dx)) in the order (0,0|0,0) (0,1|0,0) (0,1|0,1) (1,0|0,0) (1,0|1,0)
+ * (1,1|0,0) (1,1|0,1) (1,1|1,0) (1,1|1,1) uses W[:, :, a+1-2dy, b+1-2dx]; lane (g = lane / 4, t = lane % 4) holds
+ * {W[2t, n], W[2t+1, n]} and {W[2t+8, n], W[2t+9, n]} for class n = 8*tile + g (zero for n >= classes), low half first.
+ * Anything else answers ESN_ERR_UNSUPPORTED and the host runs esn_conv2d_umma + esn_head_bilinear. */
+typedef struct EsnHeadT3 {
+  EsnTensor x;
+  const uint32_t* wfrag;
+  const float* bias;      /* [classes] or NULL */
+  uint8_t* mask;
+  int32_t classes;
+  int32_t _pad;
+} EsnHeadT3;
+int esn_head_convt3x3s2_mask(const EsnHeadT3* p, void* stream);
+
 /* Weighted cross-entropy over NCHW logits (utils/losses/loss.py:15-32):
  *   sums[0] += sum_i w[y_i]*nll_i,  sums[1] += sum_i w[y_i]   (fp32 atomics per CTA)
  * and, if dlogits != NULL, the gradient w[y_i]*(softmax - onehot) * (*gout) / (*gnorm); gnorm is the

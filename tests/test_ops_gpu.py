@@ -373,3 +373,26 @@ def test_depthwise_strip_matches_torch(ops, case, dtype):
     finally:
         del os.environ["ESN_DISABLE_DW_STRIP"]
     assert (y.float() - y_old.float()).abs().max() / ref.abs().max() < tol
+
+
+@pytest.mark.parametrize("classes,bias,shape", [(19, False, (2, 24, 48)), (5, True, (1, 7, 16)), (24, True, (3, 9, 32))])
+def test_convt3x3s2_argmax_head_on_tensor_cores(classes, bias, shape):
+    """ENet's head in one launch (esn_head_convt3x3s2_mask: transposed conv 3x3 / s2 + argmax, scores in registers) against
+    torch's conv_transpose2d on the same bf16 operands: identical masks wherever the top-2 margin exceeds fp32 rounding."""
+    import torch.nn.functional as F
+    from esn import ops
+    torch.manual_seed(11)
+    n, h, w = shape
+    x = ops.new_act(n, 16, h, w, torch.bfloat16, "cuda").normal_()
+    wt = (torch.randn(16, classes, 3, 3, device="cuda") * 0.3)
+    b = torch.randn(classes, device="cuda") if bias else None
+    frags = ops.pack_convt3x3s2_frags(wt, classes)
+    mask = ops.head_convt3x3s2_mask(x, frags, b, classes)
+    assert mask is not None and mask.shape == (n, 2 * h, 2 * w) and mask.dtype == torch.uint8
+    ref = F.conv_transpose2d(x.float(), wt.bfloat16().float(), b, stride=2, padding=1, output_padding=1)
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref.abs().amax(dim=1).clamp_min(1.0)
+    want = ref.argmax(1)
+    assert clear.float().mean().item() > 0.99
+    assert torch.equal(mask.long()[clear], want[clear])
+    assert (mask.long() == want).float().mean().item() > 0.999
