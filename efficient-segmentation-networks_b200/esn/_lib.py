@@ -91,6 +91,14 @@ class EsnHead(C.Structure):
                 ("align_corners", C.c_int32)]
 
 
+class EsnBneck4(C.Structure):
+    _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p),
+                ("scale1", C.c_void_p), ("shift1", C.c_void_p), ("alpha1", C.c_void_p),
+                ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("alpha2", C.c_void_p),
+                ("scale3", C.c_void_p), ("shift3", C.c_void_p), ("alpha3", C.c_void_p),
+                ("dilation", C.c_int32), ("act", C.c_int32)]
+
+
 class EsnHeadT3(C.Structure):
     _fields_ = [("x", EsnTensor), ("wfrag", C.c_void_p), ("bias", C.c_void_p), ("mask", C.c_void_p),
                 ("classes", C.c_int32), ("_pad", C.c_int32)]
@@ -121,6 +129,7 @@ SYMBOLS = {
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_convt3x3s2_mask": (C.c_int, [C.POINTER(EsnHeadT3), C.c_void_p]),
+    "esn_bottleneck4": (C.c_int, [C.POINTER(EsnBneck4), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
     "esn_augment_max_batch": (C.c_int32, []),
     "esn_augment_u8": (C.c_int, [C.POINTER(EsnAugItem), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_void_p,

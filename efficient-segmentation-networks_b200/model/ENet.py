@@ -53,6 +53,7 @@ def _cba(conv, bn, activation, device, pre_residual=False, cout_pad=None):
 
 
 FUSED_HEAD = os.environ.get("ESN_ENET_FUSED_HEAD", "1") != "0"      # transposed conv + argmax as one tensor-core launch
+FUSED_BNECK4 = os.environ.get("ESN_ENET_FUSED_BNECK4", "1") != "0"  # the 16-channel bottleneck (4 internal channels) in one launch
 
 class InitialBlock(PrepMixin, nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, padding=0, bias=False, relu=True):
@@ -126,6 +127,24 @@ class RegularBottleneck(PrepMixin, nn.Module):
         _no_train(self)   # eval: Dropout2d is the identity
         x = ops.as_act(input)
         preps = self.prep(x.device)
+        if (FUSED_BNECK4 and len(preps) == 3 and x.dtype == torch.bfloat16 and x.shape[1] == 16 and preps[0].cout == 4
+                and (preps[1].kh, preps[1].kw, preps[1].stride) == (3, 3, 1) and preps[1].dil_h == preps[1].dil_w <= 4
+                and (preps[1].pad_h, preps[1].pad_w) == (preps[1].dil_h, preps[1].dil_w)
+                and x.stride(3) % 8 == 0 and x.data_ptr() % 16 == 0):
+            # four internal channels (regular5_1): the whole block in one launch, the intermediates in shared memory
+            n, c, h, w = x.shape
+            y = ops.new_act(n, c, h, w, x.dtype, x.device)
+            q = ops.L.EsnBneck4()
+            q.x, q.y = ops.tdesc(x), ops.tdesc(y)
+            q.w1, q.w2, q.w3 = (p.w_direct.data_ptr() for p in preps)
+            for i, p in enumerate(preps, 1):
+                setattr(q, "scale%d" % i, p.scale.data_ptr())
+                setattr(q, "shift%d" % i, p.shift.data_ptr())
+                setattr(q, "alpha%d" % i, p.alpha.data_ptr() if p.alpha is not None else None)
+            q.dilation, q.act = preps[1].dil_h, preps[0].act
+            ops._call(ops.L.lib.esn_bottleneck4, "esn_bottleneck4", (ops.C.byref(q),), 2 * ops._nbytes(x),
+                      2 * n * h * w * (64 + 144 + 64))
+            return y
         y = x
         for p in preps[:-1]:
             y = ops.conv2d(y, p)

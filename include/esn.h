@@ -261,6 +261,22 @@ int esn_head_bilinear(const EsnHead* p, void* stream);
  * (1,1|0,0) (1,1|0,1) (1,1|1,0) (1,1|1,1) uses W[:, :, a+1-2dy, b+1-2dx]; lane (g = lane / 4, t = lane % 4) holds
  * {W[2t, n], W[2t+1, n]} and {W[2t+8, n], W[2t+9, n]} for class n = 8*tile + g (zero for n >= classes), low half first.
  * Anything else answers ESN_ERR_UNSUPPORTED and the host runs esn_conv2d_umma + esn_head_bilinear. */
+/* ENet's RegularBottleneck with four internal channels (channels = 16, regular 3x3: ENet.py:46-100, `regular5_1`) as ONE launch:
+ *   y = act(x + act(BN3(W3 . act(BN2(W2 * act(BN1(W1 . x)))))))      (eval-mode BN as scale / shift, Dropout2d = identity)
+ * W1 [16][4], W2 [9][4][4], W3 [4][16] fp32 in the direct kernels' (tap, cin, cout) order; act = ReLU or PReLU (alpha1/2: [4],
+ * alpha3: [16], also the slope of the outer activation).  bf16 NHWC, 16 channels, dilation 1..4; anything else answers
+ * ESN_ERR_UNSUPPORTED and the host runs the three convs. */
+typedef struct EsnBneck4 {
+  EsnTensor x, y;
+  const float *w1, *w2, *w3;
+  const float *scale1, *shift1, *alpha1;
+  const float *scale2, *shift2, *alpha2;
+  const float *scale3, *shift3, *alpha3;
+  int32_t dilation;
+  int32_t act;
+} EsnBneck4;
+int esn_bottleneck4(const EsnBneck4* p, void* stream);
+
 typedef struct EsnHeadT3 {
   EsnTensor x;
   const uint32_t* wfrag;

@@ -396,3 +396,44 @@ def test_convt3x3s2_argmax_head_on_tensor_cores(classes, bias, shape):
     assert clear.float().mean().item() > 0.99
     assert torch.equal(mask.long()[clear], want[clear])
     assert (mask.long() == want).float().mean().item() > 0.999
+
+
+@pytest.mark.parametrize("relu,dilation,shape", [(True, 1, (2, 19, 70)), (False, 1, (1, 8, 32)), (False, 2, (2, 13, 45))])
+def test_enet_bottleneck4_in_one_launch(relu, dilation, shape):
+    """ENet's RegularBottleneck(16) (four internal channels) as one launch against the reference arithmetic in fp32 on the same
+    bf16 input, and against the three-launch path of the same module."""
+    import model.ENet as E
+    torch.manual_seed(12)
+    n, h, w = shape
+    blk = E.RegularBottleneck(16, padding=dilation, dilation=dilation, dropout_prob=0.1, relu=relu).cuda().eval()
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+            if isinstance(m, nn.PReLU):
+                m.weight.fill_(0.2)
+    x = torch.randn(n, 16, h, w, device="cuda")
+    xb = x.bfloat16().float()
+    with torch.no_grad():
+        act = blk.out_prelu
+        e = act(blk.ext_conv1[1](F.conv2d(xb, blk.ext_conv1[0].weight)))
+        e = act(blk.ext_conv2[1](F.conv2d(e, blk.ext_conv2[0].weight, padding=dilation, dilation=dilation)))
+        e = act(blk.ext_conv3[1](F.conv2d(e, blk.ext_conv3[0].weight)))
+        ref = act(xb + e)
+        outs = {}
+        for fused in (True, False):
+            E.FUSED_BNECK4 = fused
+            try:
+                from esn import ops
+                xa = ops.as_act(x, torch.bfloat16)
+                n0 = ops.L.lib.esn_launch_count()
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    y = blk(xa)
+                outs[fused] = (y.float(), ops.L.lib.esn_launch_count() - n0)
+            finally:
+                E.FUSED_BNECK4 = True
+    assert outs[True][1] == 1 and outs[False][1] == 3
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert rel(outs[True][0], ref) < 6e-3, rel(outs[True][0], ref)          # bf16 output rounding only
+    assert rel(outs[False][0], ref) < 2e-2
+    assert rel(outs[True][0], outs[False][0]) < 2e-2
