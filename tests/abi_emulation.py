@@ -211,6 +211,47 @@ def esn_head_convt2x2(ref):
     return _head_out(p, F.conv_transpose2d(x, wt, vec(p.bias, p.classes), 2))
 
 
+def esn_head_convt3x3s2_mask(ref):
+    """ConvTranspose2d(16, classes, 3, 2, 1, 1) + argmax from the packed mma B fragments (include/esn.h): the weights are decoded
+    back from fragment order, so a wrong packing on the host shows up here."""
+    p = ref._obj
+    assert p.x.dtype == L.ESN_BF16 and p.x.c == 16 and p.x.w % 16 == 0 and p.classes <= 24
+    x = tensor(p.x).float()
+    frag = _buf(p.wfrag, 9 * 3 * 32 * 2 * 2, torch.bfloat16, 2).view(9, 3, 32, 2, 2).float()
+    pairs = ((0, 0, 0, 0), (0, 1, 0, 0), (0, 1, 0, 1), (1, 0, 0, 0), (1, 0, 1, 0), (1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 1, 0), (1, 1, 1, 1))
+    w = torch.zeros(16, 24, 3, 3)
+    for q, (a, b, dy, dx) in enumerate(pairs):
+        for nt in range(3):
+            for lane in range(32):
+                g, t = lane // 4, lane % 4
+                for r in range(2):
+                    for e in range(2):
+                        w[2 * t + 8 * r + e, nt * 8 + g, a + 1 - 2 * dy, b + 1 - 2 * dx] = frag[q, nt, lane, r, e]
+    assert (w[:, p.classes:] == 0).all(), "padded classes must carry zero weights"
+    logits = F.conv_transpose2d(x, w[:, :p.classes], vec(p.bias, p.classes), 2, 1, 1)
+    n, _, h, ww = logits.shape
+    torch.frombuffer((C.c_char * (n * h * ww)).from_address(p.mask), dtype=torch.uint8).view(n, h, ww).copy_(
+        logits.argmax(1).to(torch.uint8))
+    return 0
+
+
+def esn_bottleneck4(ref):
+    """ENet's 16-channel RegularBottleneck: y = act(x + act(BN3(W3 . act(BN2(W2 * act(BN1(W1 . x)))))))."""
+    p = ref._obj
+    assert p.x.dtype == L.ESN_BF16 and p.x.c == 16 and 1 <= p.dilation <= 4
+    x, y = _finite(tensor(p.x).float(), "esn_bottleneck4"), tensor(p.y)
+    d = p.dilation
+    w1 = _buf(p.w1, 64, torch.float32, 4).view(1, 1, 16, 4).permute(3, 2, 0, 1)
+    w2 = _buf(p.w2, 144, torch.float32, 4).view(3, 3, 4, 4).permute(3, 2, 0, 1)
+    w3 = _buf(p.w3, 64, torch.float32, 4).view(1, 1, 4, 16).permute(3, 2, 0, 1)
+    aff = lambda v, s_, b_, c: v * vec(s_, c).view(1, -1, 1, 1) + vec(b_, c).view(1, -1, 1, 1)
+    e = _act(aff(F.conv2d(x, w1), p.scale1, p.shift1, 4), p.act, vec(p.alpha1, 4))
+    e = _act(aff(F.conv2d(e, w2, padding=d, dilation=d), p.scale2, p.shift2, 4), p.act, vec(p.alpha2, 4))
+    e = _act(aff(F.conv2d(e, w3), p.scale3, p.shift3, 16), p.act, vec(p.alpha3, 16))
+    store(y, _act(x + e, p.act, vec(p.alpha3, 16)))
+    return 0
+
+
 def esn_head_bilinear(ref):
     p = ref._obj
     x = tensor(p.x).float()[:, :p.classes]
@@ -360,6 +401,7 @@ ENTRY = {
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
     "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast, "esn_weighted_ce": esn_weighted_ce,
     "esn_ohem_threshold": esn_ohem_threshold, "esn_augment_u8": esn_augment_u8,
+    "esn_head_convt3x3s2_mask": esn_head_convt3x3s2_mask, "esn_bottleneck4": esn_bottleneck4,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 
