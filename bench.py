@@ -302,10 +302,20 @@ def unit_roofline(model, model_name, prof_step, hbm_peak, tc_peak):
             return sum(numel_bytes(v) for v in t)
         return 0
 
+    def first_tensor(t):
+        # a block that also emits the next block's BNPReLU returns (output, BNPReLU(output)) or (None, BNPReLU(output)):
+        # the unit's logical output is one tensor of the block's shape (SURVEY 8d counts it once)
+        if isinstance(t, (tuple, list)):
+            for v in t:
+                r = first_tensor(v)
+                if r is not None:
+                    return r
+            return None
+        return t if torch.is_tensor(t) else None
+
     def shape_of(t):
-        while isinstance(t, (tuple, list)):
-            t = t[0]
-        return tuple(t.shape) if torch.is_tensor(t) else ()
+        t = first_tensor(t)
+        return tuple(t.shape) if t is not None else ()
 
     units = []
 
@@ -319,7 +329,7 @@ def unit_roofline(model, model_name, prof_step, hbm_peak, tc_peak):
         if state["depth"] == 0 and state["cur"] is not None:
             u = state["cur"]
             u["last"] = len(ops.PROFILE)
-            u["out"] = numel_bytes(out)
+            u["out"] = numel_bytes(first_tensor(out))
             u["oshape"] = shape_of(out)
             units.append(u)
             state["cur"] = None

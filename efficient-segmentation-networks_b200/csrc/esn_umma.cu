@@ -29,12 +29,21 @@ struct alignas(64) UmmaArgs {
   CUtensorMap tmY2;  // phase-fused transposed conv: output rows 2i+1 (tmY: rows 2i)
 
   CUtensorMap tmR;   // residual, 4-D (staged epilogue with residual only)
+  CUtensorMap tmZ;   // second output, 4-D (dual == 2)
+  // second epilogue stage: v2 = act2(bf16(v) * scale2 + shift2).  dual == 1: only v2 is stored (through tmY, built over
+  // y2); dual == 2: v leaves through tmY and v2 through tmZ out of a second set of staging buffers
+  int dual, act2;
+  int warp_issue;    // MMA issuer: 1 = warp-uniform loop with an elected lane, 0 = one thread runs the whole loop
+  const float* scale2;
+  const float* shift2;
+  const float* alpha2;
   int mode, nunits;
   int g_dw, g_dh, g_dn;              // MODE_GENERIC: (tw, th, n) increment of one grid stride (interleaved tiles)
   int ntaps, nkb, kb_elems, N, cout, MT;
   int bw, bh, tiles_w, tiles_h, gh, gw;
   int a_boxw, a_nbox, o_boxw, o_nbox;
   int hs_d, hs_pad;                  // MODE_HREUSE: tap spacing / left padding in pixels
+  int hr_kh, hr_dh, hr_ph;           // MODE_HREUSE: tap rows (1 for 1 x k convs), their spacing and the top padding in rows
   int vr_d, vr_pad, vr_L, vr_nseg;   // MODE_VREUSE: row stride, top padding, outputs per unit, segments
   int vr_cnt, vr_rem;                // rows of the longest residue class; residues >= vr_rem have one less
   int vr_kh, vr_kw;                  // MODE_VREUSE: tap rows (ring slots per output) x taps per row (shifted windows of one slot)
@@ -148,6 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const uint32_t tfull0 = bar_base + 8u * (2 * S + 1), tempty0 = bar_base + 8u * (2 * S + 5);
   const uint32_t sfull0 = bar_base + 8u * (2 * S + 9), sfree0 = bar_base + 8u * (2 * S + 13);
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 17);
+  const uint32_t prm2_base = (bar_base + 512u + 1023u) & ~1023u;   // dual only: scale2|shift2|alpha2, then the y2 staging set
+  const uint32_t o2_delta = prm2_base + 3072u - o_base;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* prm = reinterpret_cast<float*>(smem_raw + (prm_base - raw));
 
@@ -160,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (a.staged) tma_prefetch_desc(&a.tmY);
     if (a.staged && a.shuf_bpa) tma_prefetch_desc(&a.tmY2);
     if (a.has_res && a.staged) tma_prefetch_desc(&a.tmR);
+    if (a.dual == 2) tma_prefetch_desc(&a.tmZ);
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8u * s, 1);
       mbar_init(empty0 + 8u * s, 1);
@@ -186,6 +198,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     prm[i] = (in && a.ep.scale) ? a.ep.scale[i] : 1.f;
     prm[256 + i] = (in && a.ep.shift) ? a.ep.shift[i] : 0.f;
     prm[512 + i] = (in && a.ep.act == ESN_ACT_PRELU) ? a.ep.alpha[i] : 0.f;
+  }
+  if (a.dual) {
+    float* prm2 = reinterpret_cast<float*>(smem_raw + (prm2_base - raw));
+    for (int i = threadIdx.x; i < a.N; i += kThreads) {
+      const bool in = i < a.cout;
+      prm2[i] = (in && a.scale2) ? a.scale2[i] : 1.f;
+      prm2[256 + i] = (in && a.shift2) ? a.shift2[i] : 0.f;
+      prm2[512 + i] = (in && a.act2 == ESN_ACT_PRELU) ? a.alpha2[i] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -235,17 +256,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           }
         } else if (MODE == MODE_HREUSE) {
           const int wl = un.w0 - a.hs_pad;   // window [w0 - pad, w0 + bw + (k-1)d - pad)
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(empty0 + 8u * s, ph ^ 1u);
-            if (leader) {
-              mbar_expect_tx(full0 + 8u * s, a.load_bytes);
-              const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
-              for (int q = 0; q < a.a_nbox; ++q)
-                tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, kb * KB, wl + q * a.a_boxw, 0,
-                            un.h0, un.n);
-              tma_load_5d(dst + (uint32_t)a.bw * RB, &a.tmAh, full0 + 8u * s, kb * KB, wl + a.bw, 0, un.h0, un.n);
+          // one window per (tap row, K block); rows outside the image are zero-filled by TMA (the conv's padding)
+          int row = un.h0 - a.hr_ph;
+          for (int r = 0; r < a.hr_kh; ++r, row += a.hr_dh) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(empty0 + 8u * s, ph ^ 1u);
+              if (leader) {
+                mbar_expect_tx(full0 + 8u * s, a.load_bytes);
+                const uint32_t dst = a_base + (uint32_t)s * a.stage_bytes;
+                for (int q = 0; q < a.a_nbox; ++q)
+                  tma_load_5d(dst + (uint32_t)(q * a.a_boxw) * RB, &a.tmA, full0 + 8u * s, kb * KB, wl + q * a.a_boxw, 0,
+                              row, un.n);
+                tma_load_5d(dst + (uint32_t)a.bw * RB, &a.tmAh, full0 + 8u * s, kb * KB, wl + a.bw, 0, row, un.n);
+              }
+              if (++s == S) { s = 0; ph ^= 1u; }
             }
-            if (++s == S) { s = 0; ph ^= 1u; }
           }
         } else {
           for (int t = 0; t < ntaps; ++t) {
@@ -264,9 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && a.warp_issue) {
     if (u_begin < u_end) {
-      // ---------------- MMA issuer: warp-uniform loops (operands stay in uniform registers), one
+      // ---------------- MMA issuer, warp-uniform form (ESN_UMMA_ISSUE=warp; kept for A/B measurements): warp-uniform loops (operands stay in uniform registers), one
       // elected lane issues tcgen05.mma / tcgen05.commit; descriptors advance with 32-bit adds
       const bool leader = elect_one();
       mbar_wait(wfull_bar, 0);
@@ -318,21 +343,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             }
           } else if (MODE == MODE_HREUSE) {
             const uint32_t shift16 = ((uint32_t)a.hs_d * RB) >> 4;   // tap spacing in descriptor units
-            for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(full0 + 8u * s, ph);
-              uint32_t al = a_lo0 + (uint32_t)s * stage16;
-              uint32_t bl = w_lo + (uint32_t)kb * wblk16;
-              for (int t = 0; t < ntaps; ++t, al += shift16, bl += (uint32_t)nkb * wblk16) {
-                for (int m = 0; m < MT; ++m) {
+            const int kwt = ntaps / a.hr_kh;                          // taps per tap row
+            for (int r = 0; r < a.hr_kh; ++r) {
+              for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full0 + 8u * s, ph);
+                uint32_t al = a_lo0 + (uint32_t)s * stage16;
+                uint32_t bl = w_lo + (uint32_t)(r * kwt * nkb + kb) * wblk16;
+                for (int t = 0; t < kwt; ++t, al += shift16, bl += (uint32_t)nkb * wblk16) {
+                  for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    if (leader)
-                      umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi,
-                                   idesc, (kb | t | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < KSTEPS; ++k)
+                      if (leader)
+                        umma_bf16_lo(d_tmem + (uint32_t)m * N, al + (uint32_t)m * SUB16 + 2u * k, bl + 2u * k, dhi,
+                                     idesc, (r | kb | t | k) != 0 ? 1u : 0u);
+                  }
                 }
+                if (leader) umma_commit(empty0 + 8u * s);
+                if (++s == S) { s = 0; ph ^= 1u; }
               }
-              if (leader) umma_commit(empty0 + 8u * s);
-              if (++s == S) { s = 0; ph ^= 1u; }
             }
           } else {
             const int kiters = ntaps * nkb;
@@ -353,6 +381,85 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           }
           if (leader) umma_commit(tfull0 + 8u * acc);  // accumulators ready for the epilogue
           __syncwarp();
+          if (++acc == NA) { acc = 0; aph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (u_begin < u_end && elect_one()) {
+      // ---------------- MMA issuer: ONE thread runs the whole issue loop.  (A warp-uniform loop with the elected lane
+      // branching around every tcgen05.mma cost ~130 cycles per instruction -- reconvergence points, re-read kernel
+      // parameters -- and that issue rate, not the tensor pipe or HBM, bounded every conv: r02_prof_conv3x3_*.txt.)
+      // Loop bounds and strides live in registers, descriptors advance by 32-bit adds, the K steps are unrolled.
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      const uint32_t dhi = a.desc_hi, idesc = a.idesc;
+      const uint32_t w_lo = desc_lo(w_base), wblk16 = a.wblock_bytes >> 4;
+      const uint32_t a_lo0 = desc_lo(a_base), stage16 = a.stage_bytes >> 4;
+      const uint32_t N = (uint32_t)a.N;
+      const uint32_t shift16 = ((uint32_t)a.hs_d * RB) >> 4;   // horizontal tap spacing in descriptor units
+      const int kh = a.vr_kh, kw = a.vr_kw;
+      const uint32_t tapstep16 = (uint32_t)nkb * wblk16;
+      // all MT sub-tiles x KSTEPS of one (A window, weight block) pair; first == 0 starts a new accumulation
+      auto issue = [&](uint32_t d, uint32_t al, uint32_t bl, uint32_t first) {
+        for (int m = 0; m < MT; ++m, d += N, al += SUB16) {
+          umma_bf16_lo(d, al, bl, dhi, idesc, first);
+#pragma unroll
+          for (int k = 1; k < KSTEPS; ++k) umma_bf16_lo(d, al + 2u * k, bl + 2u * k, dhi, idesc, 1u);
+        }
+      };
+      int s = 0;
+      uint32_t ph = 0, acc = 0, aph = 0;
+      UnitIter<MODE> un;
+      un.init(a, u_begin);
+      for (int u = u_begin; u < u_end; u += u_step, un.next(a)) {
+        if (un.len <= 0) continue;
+        for (int i = 0; i < un.len; ++i) {
+          mbar_wait(tempty0 + 8u * acc, aph ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * acc_cols;
+          if (MODE == MODE_VREUSE) {
+            // tap row t of this output lives in ring slot s+t (s = slot of the oldest live row)
+            int st = s;
+            uint32_t pt = ph;
+            uint32_t bl = w_lo;
+            for (int t = 0; t < kh; ++t) {
+              if (i == 0 || t == kh - 1) mbar_wait(full0 + 8u * st, pt);
+              uint32_t al = a_lo0 + (uint32_t)st * stage16;
+              for (int q = 0; q < kw; ++q, al += shift16, bl += wblk16) issue(d_tmem, al, bl, (t | q) != 0 ? 1u : 0u);
+              if (++st == S) { st = 0; pt ^= 1u; }
+            }
+            umma_commit(empty0 + 8u * s);   // the oldest row is dead once these MMAs retire
+            if (++s == S) { s = 0; ph ^= 1u; }
+            if (i == un.len - 1) {          // unit done: release the kh-1 rows still held
+              for (int t = 1; t < kh; ++t) {
+                umma_commit(empty0 + 8u * s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+              }
+            }
+          } else if (MODE == MODE_HREUSE) {
+            const int hkh = a.hr_kh, kwt = ntaps / hkh;
+            for (int r = 0; r < hkh; ++r) {
+              for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full0 + 8u * s, ph);
+                uint32_t al = a_lo0 + (uint32_t)s * stage16;
+                uint32_t bl = w_lo + (uint32_t)(r * kwt * nkb + kb) * wblk16;
+                for (int t = 0; t < kwt; ++t, al += shift16, bl += tapstep16) issue(d_tmem, al, bl, (r | kb | t) != 0 ? 1u : 0u);
+                umma_commit(empty0 + 8u * s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+              }
+            }
+          } else {
+            const int kiters = ntaps * nkb;
+            uint32_t bl = w_lo;
+            for (int ki = 0; ki < kiters; ++ki, bl += wblk16) {
+              mbar_wait(full0 + 8u * s, ph);
+              issue(d_tmem, a_lo0 + (uint32_t)s * stage16, bl, ki != 0 ? 1u : 0u);
+              umma_commit(empty0 + 8u * s);  // frees the smem stage when these MMAs retire
+              if (++s == S) { s = 0; ph ^= 1u; }
+            }
+          }
+          umma_commit(tfull0 + 8u * acc);  // accumulators ready for the epilogue
           if (++acc == NA) { acc = 0; aph ^= 1u; }
         }
       }
@@ -386,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int nchunk = a.N >> 4;
     const uint32_t row_bytes = (uint32_t)a.cbo * 2u;
     const uint32_t nsmask = (uint32_t)NS - 1u, nsshift = NS == 4 ? 2u : (NS == 2 ? 1u : 0u);
-    const int staged = a.staged, has_res = a.has_res, act = a.ep.act, cout = a.cout;
+    const int staged = a.staged, has_res = a.has_res, act = a.ep.act, cout = a.cout, dual = a.dual;
     const uint32_t swz = a.out_swz_mask;
     const bool wide = a.ncb > 1;                 // several column blocks of cbo (16 / 32 / 64) channels
     const int cbo_shift = a.cbo == 64 ? 6 : (a.cbo == 32 ? 5 : 4);
@@ -484,7 +591,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * al[j];
                   }
-                  sts128(saddr, float_to_bf16x8(f));
+                  if (dual) {
+                    // second stage on the value as stored (bf16): the same numbers a separate affine pass over y would read
+                    const uint4 pk = float_to_bf16x8(f);
+                    if (dual == 2) sts128(saddr, pk);
+                    float g[8];
+                    bf16x8_to_float(pk, g);
+                    const uint32_t pb = prm2_base + 4u * (uint32_t)cb8;
+                    const float4 s0 = lds_f4(pb), s1 = lds_f4(pb + 16u);
+                    const float4 h0 = lds_f4(pb + 1024u), h1 = lds_f4(pb + 1040u);
+                    g[0] = fmaf(g[0], s0.x, h0.x); g[1] = fmaf(g[1], s0.y, h0.y);
+                    g[2] = fmaf(g[2], s0.z, h0.z); g[3] = fmaf(g[3], s0.w, h0.w);
+                    g[4] = fmaf(g[4], s1.x, h1.x); g[5] = fmaf(g[5], s1.y, h1.y);
+                    g[6] = fmaf(g[6], s1.z, h1.z); g[7] = fmaf(g[7], s1.w, h1.w);
+                    if (a.act2 == ESN_ACT_RELU) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(g[j], 0.f);
+                    } else if (a.act2 == ESN_ACT_PRELU) {
+                      const float4 a0 = lds_f4(pb + 2048u), a1 = lds_f4(pb + 2064u);
+                      const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) g[j] = g[j] >= 0.f ? g[j] : g[j] * al[j];
+                    }
+                    sts128(dual == 2 ? saddr + o2_delta : saddr, float_to_bf16x8(g));
+                  } else {
+                    sts128(saddr, float_to_bf16x8(f));
+                  }
                 }
               }
             }
@@ -597,6 +729,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               for (int qb = 0; qb < a.o_nbox; ++qb)
                 tma_store_4d(odd ? &a.tmY2 : &a.tmY, obuf + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
                              cc, un.w0 + qb * a.o_boxw, th0, un.n);
+              if (dual == 2)
+                for (int qb = 0; qb < a.o_nbox; ++qb)
+                  tma_store_4d(&a.tmZ, obuf + o2_delta + (uint32_t)cb * a.out_block_bytes + (uint32_t)(qb * a.o_boxw) * row_bytes,
+                               cc, un.w0 + qb * a.o_boxw, th0, un.n);
             }
             tma_store_commit();
             // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
@@ -612,6 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();   // the issuer role ran on one lane: reconverge before the .sync.aligned instruction
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }
@@ -648,11 +785,23 @@ const DeviceLimits& limits() {
 
 }  // namespace
 
-extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
+namespace {
+// dual: nullptr, or the second epilogue stage (esn_conv2d_umma_dual)
+int conv_umma_impl(const EsnConv* p, const EsnConvDual* dual, void* stream) {
   if (!p || !p->w) return ESN_ERR_BAD_ARG;
   const EsnTensor& x = p->x;
-  const EsnTensor& y = p->y;
+  // store_y == 0: only the second-stage value is stored, so every output map is built over y2
+  const EsnTensor& y = (dual && !dual->store_y) ? dual->y2 : p->y;
   if (!esn_valid_nhwc(x) || !esn_valid_nhwc(y)) return ESN_ERR_BAD_ARG;
+  if (dual) {
+    const EsnTensor& z = dual->y2;
+    if (!esn_valid_nhwc(z) || z.dtype != ESN_BF16 || z.n != p->y.n || z.h != p->y.h || z.w != p->y.w || z.c != p->y.c)
+      return ESN_ERR_BAD_SHAPE;
+    if (z.c_stride % 8 || ((uintptr_t)z.ptr % 16)) return ESN_ERR_ALIGN;
+    if (dual->act2 != ESN_ACT_NONE && dual->act2 != ESN_ACT_RELU && dual->act2 != ESN_ACT_PRELU) return ESN_ERR_BAD_ARG;
+    if (dual->act2 == ESN_ACT_PRELU && !dual->alpha2) return ESN_ERR_BAD_ARG;
+    if (p->transposed) return ESN_ERR_UNSUPPORTED;
+  }
   if (x.dtype != ESN_BF16 || y.dtype != ESN_BF16 || p->groups != 1) return ESN_ERR_UNSUPPORTED;
   const EsnTensor& res = p->ep.residual;
   if (res.ptr && res.dtype != ESN_BF16) return ESN_ERR_UNSUPPORTED;
@@ -737,8 +886,22 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     const uint32_t need = wreg + (uint32_t)(p->kh + 1) * stage + (stg ? (uint32_t)mt * kTileM * Cout * 2 : 0u) + 3072u + 512u + 1024u;
     if (need <= (uint32_t)lim.max_smem) a.mode = MODE_VREUSE;
   }
+  if (a.mode == MODE_GENERIC && rowable && p->kh >= 2 && p->kw >= 2 && (p->kw - 1) * p->dil_w <= 256 &&
+      !getenv("ESN_UMMA_NOHROWS")) {
+    // k_h x k_w convs whose row ring does not fit (two K blocks, or weights that fill the shared memory): row tiles with one
+    // window per (tap row, K block); the k_w taps of a row are shifted reads of it -- k_w times less L2 -> shared-memory
+    // traffic than one box per tap.  Needs two windows, one staging tile and the weights.
+    int mt = MT;
+    while (mt > 1 && mt * kTileM > gw) mt >>= 1;
+    const uint32_t stage = ((uint32_t)(mt * kTileM + (p->kw - 1) * p->dil_w) * (uint32_t)(KB * 2) + 1023u) & ~1023u;
+    const uint32_t wreg = ((uint32_t)ntaps_all * nkb * N * KB * 2 + 1023u) & ~1023u;
+    const bool stg = (Cout % 8 == 0) && (Cout <= 64 || Cout % 64 == 0);
+    const uint32_t need = wreg + 3u * stage + (stg ? (uint32_t)mt * kTileM * Cout * 2 : 0u) + 3072u + 512u + 1024u +
+                          (dual ? 4096u + (dual->store_y ? (uint32_t)mt * kTileM * Cout * 2 : 0u) : 0u);
+    if (need <= (uint32_t)lim.max_smem) a.mode = MODE_HREUSE;
+  }
   if (a.mode != MODE_GENERIC) {
-    if (a.mode == MODE_HREUSE && KB == 64 && nkb == 1 && N <= 64) MT = 2;   // 256-pixel row tiles for C=64
+    if (a.mode == MODE_HREUSE && p->kh == 1 && KB == 64 && nkb == 1 && N <= 64) MT = 2;   // 256-pixel row tiles for C=64
     while (MT > 1 && MT * kTileM > gw) MT >>= 1;
     a.bw = MT * kTileM;
     a.bh = 1;
@@ -770,6 +933,9 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   if (a.mode == MODE_HREUSE) {
     a.hs_d = p->dil_w;
     a.hs_pad = p->pad_w;
+    a.hr_kh = p->kh;
+    a.hr_dh = p->dil_h;
+    a.hr_ph = p->pad_h;
     const int extra = (p->kw - 1) * p->dil_w;
     a.load_bytes = (uint32_t)(a.bw + extra) * row_bytes;
     a.stage_bytes = (a.load_bytes + 1023u) & ~1023u;
@@ -805,6 +971,14 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
   // staged epilogue (swizzled smem tile + TMA store, residual prefetched by TMA into the same tile)
   a.staged = (Cout % 8 == 0) && (Cout <= 64 || Cout % 64 == 0);
   a.has_res = res.ptr != nullptr;
+  if (dual) {
+    if (!a.staged) return ESN_ERR_UNSUPPORTED;     // the second stage lives in the staged epilogue only
+    a.dual = dual->store_y ? 2 : 1;
+    a.act2 = dual->act2;
+    a.scale2 = dual->scale2;
+    a.shift2 = dual->shift2;
+    a.alpha2 = dual->alpha2;
+  }
   CUtensorMapSwizzle oswz = CU_TENSOR_MAP_SWIZZLE_NONE;
   if (a.staged) {
     a.cbo = Cout <= 64 ? Cout : 64;
@@ -910,16 +1084,17 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
           return ESN_ERR_CUDA;
       }
-    } else if (a.staged) {  // output / residual maps over this phase's (strided) output positions
-      for (int which = 0; which < (a.has_res ? 2 : 1); ++which) {
-        const EsnTensor& t = which ? res : y;
+    } else if (a.staged) {  // output / residual (/ second output) maps over this phase's (strided) output positions
+      for (int which = 0; which < 3; ++which) {
+        if ((which == 1 && !a.has_res) || (which == 2 && a.dual != 2)) continue;
+        const EsnTensor& t = which == 2 ? dual->y2 : (which ? res : y);
         const cuuint64_t cs = (cuuint64_t)t.c_stride;
         const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)x.n};
         const cuuint64_t strides[3] = {cs * 2 * a.sx, (cuuint64_t)y.w * cs * 2 * a.sy, (cuuint64_t)y.h * y.w * cs * 2};
         const cuuint32_t box[4] = {(cuuint32_t)a.cbo, (cuuint32_t)a.o_boxw, (cuuint32_t)a.bh, 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         void* bp = reinterpret_cast<uint8_t*>(t.ptr) + ((size_t)a.oy * y.w + a.ox) * cs * 2;
-        if (encode(which ? &a.tmR : &a.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bp, dims, strides, box, es,
+        if (encode(which == 2 ? &a.tmZ : (which ? &a.tmR : &a.tmY), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bp, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
           return ESN_ERR_CUDA;
@@ -931,12 +1106,20 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     // shared memory plan: resident weights + A ring + staging + params + barriers (+1 KB alignment slack)
     // trade staging buffers for A stages until the load pipeline is deep enough to cover ~2 tiles
     const int min_stages = a.mode == MODE_VREUSE ? p->kh + 1 : 2;
-    const int per_tile = a.mode == MODE_VREUSE ? 1 : (a.mode == MODE_HREUSE ? nkb : nt * nkb);
+    const int per_tile = a.mode == MODE_VREUSE ? 1 : (a.mode == MODE_HREUSE ? p->kh * nkb : nt * nkb);
     int want = a.mode == MODE_VREUSE ? p->kh + 3 : (a.mode == MODE_HREUSE ? per_tile + 1 : 2 * per_tile + 1);
     if (want > 8) want = 8;
-    int ns = a.staged ? (a.out_buf_bytes <= 16384 ? 4 : 2) : 0;
+    // the residual tile is prefetched into the staging buffer its output leaves from, so with a residual the number of
+    // buffers is the number of residual loads in flight: 2 left a 256-pixel tile waiting a full HBM round trip per tile
+    const char* ns_env = getenv("ESN_UMMA_NS");            // A/B: "2" restores the old plan
+    const bool ns4 = a.has_res && !(ns_env && ns_env[0] == '2');
+    int ns = a.staged ? ((a.out_buf_bytes <= 16384 || ns4) ? 4 : 2) : 0;
+    // second epilogue stage: its parameter block (+ alignment) and, with both outputs stored, a second staging set
+    const auto dual_extra = [&](int nsb) -> uint32_t {
+      return a.dual ? 1024u + 3072u + (a.dual == 2 ? (uint32_t)nsb * a.out_buf_bytes : 0u) : 0u;
+    };
     for (;;) {
-      const uint32_t fixed = a.w_region_bytes + (uint32_t)ns * a.out_buf_bytes + 3072u + 512u + 1024u;
+      const uint32_t fixed = a.w_region_bytes + (uint32_t)ns * a.out_buf_bytes + 3072u + 512u + 1024u + dual_extra(ns);
       int stages = fixed < (uint32_t)lim.max_smem ? (int)(((uint32_t)lim.max_smem - fixed) / a.stage_bytes) : 0;
       if (stages > 8) stages = 8;
       if (stages >= want || ns <= 1) {
@@ -955,9 +1138,15 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     while (cols < (uint32_t)(na * MT * N)) cols <<= 1;
     a.tmem_cols = cols;
     const size_t smem = a.w_region_bytes + (size_t)a.NS * a.out_buf_bytes + 3072u + 512u + 1024u +
-                        (size_t)a.stages * a.stage_bytes;
+                        (size_t)a.stages * a.stage_bytes + dual_extra(a.NS);
     int grid = lim.sms;
     if (grid > a.nunits) grid = a.nunits;
+    {
+      // measured on one box (profiles/r02_issue_ab.txt): the one-thread loop is 1.1-1.45x faster for N <= 64 and equal for
+      // N = 128; ESN_UMMA_ISSUE=warp selects the old form for A/B runs (read per call)
+      const char* force = getenv("ESN_UMMA_ISSUE");
+      a.warp_issue = force ? (force[0] == 'w') : 0;
+    }
     a.g_dw = grid % a.tiles_w;
     a.g_dh = (grid / a.tiles_w) % a.tiles_h;
     a.g_dn = grid / (a.tiles_w * a.tiles_h);
@@ -977,4 +1166,12 @@ extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) {
     ESN_CHECK_LAUNCH();
   }
   return ESN_OK;
+}
+}  // namespace
+
+extern "C" int esn_conv2d_umma(const EsnConv* p, void* stream) { return conv_umma_impl(p, nullptr, stream); }
+
+extern "C" int esn_conv2d_umma_dual(const EsnConvDual* p, void* stream) {
+  if (!p) return ESN_ERR_BAD_ARG;
+  return conv_umma_impl(&p->conv, p, stream);
 }

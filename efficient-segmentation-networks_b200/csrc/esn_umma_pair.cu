@@ -233,11 +233,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     // warps (below): ~20 % faster per launch because the issue stream itself -- waits, tcgen05.mma, ~100-cycle
     // tcgen05.commits -- was the critical path.  The split that works keeps ONE consumer on the TMA ring (warp 1 also
     // issues the residual MMA); letting warp 2 consume ring slots as well produced a rare "unspecified launch failure".
-    if (G > 0 && a.issuers == 2) {
+    if (G > 0 && a.issuers == 2 && elect_one()) {
       // ---- two-issuer mode, warp 1: conv1 of tile g from the ring, then (residual pairs) the residual tile of
       // g-3 as the FIRST MMA of conv2's accumulator (accumulate = 0); warp 2 adds the 1 x k taps on top once
       // rres[slot] says that MMA has been issued.  The ring has a single consumer.
-      const bool leader = elect_one();
+      constexpr bool leader = true;   // the whole loop runs on the one elected thread (see esn_umma.cu)
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
       const uint32_t dhi = a.desc_hi, idesc = a.idesc;
@@ -284,10 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
           }
           if (++s == S) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
       }
-    } else if (G > 0) {
-      const bool leader = elect_one();
+    } else if (G > 0 && a.issuers != 2 && elect_one()) {
+      constexpr bool leader = true;
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
       const uint32_t dhi = a.desc_hi, idesc = a.idesc;
@@ -363,13 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
             umma_commit(ifree0 + 8u * (ib * kMaxTR + j));   // epilogue 1 waits on tile j+1's commit before rewriting tile j
           }
         }
-        __syncwarp();
       }
     }
   } else if (warp == 2) {
-    if (G > 0 && a.issuers == 2) {
+    if (G > 0 && a.issuers == 2 && elect_one()) {
       // ---- two-issuer mode, warp 2: conv2 (1 x k) of tile g-3 from the intermediate row
-      const bool leader = elect_one();
+      constexpr bool leader = true;   // the whole loop runs on the one elected thread (see esn_umma.cu)
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
       const uint32_t dhi = a.desc_hi, idesc = a.idesc;
@@ -406,7 +404,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
           umma_commit(t2full0 + 8u * slot2);
           umma_commit(ifree0 + 8u * (ib * kMaxTR + j));
         }
-        __syncwarp();
       }
     }
   } else {
@@ -547,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();   // the issuer role ran on one lane: reconverge before the .sync.aligned instruction
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }

@@ -111,11 +111,13 @@ __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (u_begin < u_end) {
-      // MMA issuer: warp-uniform runtime loops whose descriptor words advance with 32-bit adds (no table look-ups, no
-      // predicated-off issue slots: ncu showed the first two versions issue-bound at ~300 cycles per MMA); one elected
-      // lane issues.  Accumulator order = (filter row, tap / tap group, channel-box pair), as in the host's table.
-      const bool leader = elect_one();
+    if (u_begin < u_end && elect_one()) {
+      // MMA issuer: runtime loops whose descriptor words advance with 32-bit adds (no table look-ups, no predicated-off
+      // issue slots: ncu showed the first two versions issue-bound at ~300 cycles per MMA), run by ONE elected thread
+      // (a warp-uniform loop with the elected lane branching around each tcgen05.mma still cost ~130 cycles per
+      // instruction: see esn_umma.cu).  Accumulator order = (filter row, tap / tap group, channel-box pair), as in the
+      // host's table.
+      constexpr bool leader = true;
       int s = 0;
       uint32_t ph = 0, accum = 0;
       const int ksteps = a.BW >> 4, BH = a.BH, n_rt = a.nrt, n_s = a.loop_s, n_jb = a.loop_jb;
@@ -147,11 +149,9 @@ __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid
           }
         }
         if (leader) umma_commit(empty0 + 8u * s);   // the stage is free once these MMAs have read it
-        __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
       if (leader) umma_commit(tfull);
-      __syncwarp();
     }
   } else {
     if (u_begin < u_end) {
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kWguThreads, 1) wgrad_umma_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();   // the issuer role ran on one lane: reconverge before the .sync.aligned instruction
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }

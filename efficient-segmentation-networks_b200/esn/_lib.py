@@ -36,6 +36,11 @@ class EsnConv(C.Structure):
                 ("ep", EsnEpilogue)]
 
 
+class EsnConvDual(C.Structure):
+    _fields_ = [("conv", EsnConv), ("y2", EsnTensor), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+                ("alpha2", C.c_void_p), ("act2", C.c_int32), ("store_y", C.c_int32)]
+
+
 class EsnConvPair(C.Structure):
     _fields_ = [("x", EsnTensor), ("y", EsnTensor), ("w1", C.c_void_p), ("w2", C.c_void_p),
                 ("taps", C.c_int32), ("dilation", C.c_int32), ("ep1", EsnEpilogue), ("ep2", EsnEpilogue)]
@@ -119,6 +124,7 @@ class EsnCE(C.Structure):
 SYMBOLS = {
     "esn_conv2d_direct": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
     "esn_conv2d_umma": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
+    "esn_conv2d_umma_dual": (C.c_int, [C.POINTER(EsnConvDual), C.c_void_p]),
     "esn_conv_pair_umma": (C.c_int, [C.POINTER(EsnConvPair), C.c_void_p]),
     "esn_stem_conv3x3s2": (C.c_int, [C.POINTER(EsnStem), C.c_void_p]),
     "esn_maxpool2x2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),

@@ -449,6 +449,55 @@ def conv2d(x, prep, out=None, residual=None, force_direct=False):
     return out
 
 
+DUAL_ENABLED = os.environ.get("ESN_DUAL", "1") != "0"
+
+
+def conv2d_then_affine(x, prep, scale2, shift2, alpha2, act2, out2, out=None, residual=None, store_y=True):
+    """y = conv2d(x, prep, residual) and y2 = act2(y * scale2 + shift2) in one tcgen05 launch (esn_conv2d_umma_dual): the
+    second stage reads the value as it is stored, so the result is bit-identical to conv2d followed by affine_act.  With
+    store_y=False only y2 is written.  Shapes the dual entry point does not take run as those two launches.
+    Returns (y or None, y2)."""
+    n, c, h, w = x.shape
+    assert c == prep.cin, (c, prep.cin)
+    ho, wo = prep.out_hw(h, w)
+    if out is None and store_y:
+        out = new_act(n, prep.cout, ho, wo, x.dtype if x.dtype == torch.bfloat16 else torch.float32, x.device)
+    yref = out if store_y else out2
+    ok = (DUAL_ENABLED and UMMA_ENABLED and x.dtype == torch.bfloat16 and yref.dtype == torch.bfloat16
+          and out2.dtype == torch.bfloat16 and not prep.grouped and prep.groups == 1 and not prep.transposed
+          and prep.cout % 8 == 0 and (prep.cout <= 64 or prep.cout % 64 == 0) and prep.cout_pad <= 256 and is_nhwc(x)
+          and is_nhwc(out2) and out2.stride(3) % 8 == 0 and out2.data_ptr() % 16 == 0)
+    if ok:
+        d = L.EsnConvDual()
+        p = d.conv
+        p.x, p.y = tdesc(x), tdesc(yref)
+        p.kh, p.kw, p.stride = prep.kh, prep.kw, prep.stride
+        p.pad_h, p.pad_w, p.dil_h, p.dil_w = prep.pad_h, prep.pad_w, prep.dil_h, prep.dil_w
+        p.groups, p.transposed, p.cout_pad = prep.groups, prep.transposed, prep.cout_pad
+        _epilogue(p.ep, prep.scale, prep.shift, prep.alpha, prep.act, residual, getattr(prep, "ep_flags", 0))
+        ok = umma_supported(prep, p)
+    if ok:
+        p.w = prep.w_umma.data_ptr()
+        d.y2 = tdesc(out2)
+        d.scale2 = scale2.data_ptr() if scale2 is not None else None
+        d.shift2 = shift2.data_ptr() if shift2 is not None else None
+        d.alpha2 = alpha2.data_ptr() if alpha2 is not None else None
+        d.act2, d.store_y = act2, 1 if store_y else 0
+        alg = _nbytes(x) + _nbytes(out2) + _nbytes(residual) + (_nbytes(out) if store_y else 0)
+        flops = 2 * n * ho * wo * prep.cout * prep.cin * prep.kh * prep.kw
+        tag = "%dx%d c%d-%d s%d d%d %s" % (prep.kh, prep.kw, prep.cin, prep.cout, prep.stride, max(prep.dil_h, prep.dil_w),
+                                           "dual" if store_y else "chain")
+        if _call(L.lib.esn_conv2d_umma_dual, "esn_conv2d_umma_dual", (C.byref(d),), alg, flops, tag, allow_unsupported=True):
+            return (out if store_y else None), out2
+    if store_y:
+        conv2d(x, prep, out=out, residual=residual)
+        affine_act(out, scale2, shift2, alpha2, act2, out=out2)
+        return out, out2
+    conv2d(x, prep, out=out2, residual=residual)
+    affine_act(out2, scale2, shift2, alpha2, act2, out=out2)
+    return None, out2
+
+
 def pair_supported(x, p1, p2, out, residual):
     """Mirror of esn_conv_pair_umma's gate (csrc/esn_umma_pair.cu)."""
     if not UMMA_ENABLED or PAIR_DISABLED or x.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:

@@ -53,9 +53,15 @@ class Conv(PrepMixin, nn.Module):
             return ops.ConvPrep(self.conv, s, b, ACT_PRELU, a, device=device)
         return ops.ConvPrep(self.conv, device=device)
 
-    def forward(self, input, out=None, residual=None):
+    def forward(self, input, out=None, residual=None, then=None, out2=None, keep=True):
+        """then = (scale, shift, alpha) of a BNPReLU that consumes this conv's output: computed in the same launch
+        (esn_conv2d_umma_dual) into out2; keep=False writes only out2.  Returns out, or (out, out2) with `then`."""
         _no_train(self)
         n_in = input.shape[1]
+        if then is not None:
+            x = ops.as_act(input)
+            return ops.conv2d_then_affine(x, self.prep(x.device), then[0], then[1], then[2], ACT_PRELU, out2, out=out,
+                                          residual=residual, store_y=keep)
         x = input if (n_in < 8 and input.is_contiguous() and input.dtype == torch.float32
                       and not ops.is_nhwc(input)) else ops.as_act(input)
         prep = self.prep(x.device)
@@ -130,14 +136,23 @@ class DABModule(PrepMixin, nn.Module):
         rows.append(torch.stack(_bnprelu_affine(self.bn_relu_2, device)))
         return torch.cat(rows, 0).contiguous()
 
-    def forward(self, input, out=None):
+    def forward(self, input, out=None, pre=None, then=None, keep=True):
+        """pre: bn_relu_1(input) when the producer of `input` already computed it.  then = (scale, shift, alpha) of the
+        BNPReLU that reads this module's output (the next module's bn_relu_1, or a concat's bn_prelu slice): computed in
+        the conv1x1 + residual launch.  With `then` the result is (output, BNPReLU(output)); keep=False stores only the
+        second one, into `out`."""
         _no_train(self)
         x = ops.as_act(input)
         prm = self.prep(x.device)
-        y = self.bn_relu_1(x)
+        y = self.bn_relu_1(x) if pre is None else pre
         y = self.conv3x3(y)
         y = ops.dab_dw_pair(y, prm, self._d)
-        return self.conv1x1(y, out=out, residual=x)     # output + input
+        if then is None:
+            return self.conv1x1(y, out=out, residual=x)     # output + input
+        if not keep:
+            return self.conv1x1(y, residual=x, then=then, out2=out, keep=False)
+        n, c, h, w = x.shape
+        return self.conv1x1(y, out=out, residual=x, then=then, out2=ops.new_act(n, c, h, w, x.dtype, x.device))
 
 
 class DownSamplingBlock(PrepMixin, nn.Module):
@@ -249,29 +264,29 @@ class DABNet(nn.Module):
 
         h1, w1 = d1.shape[2:]
         cat0 = ops.new_act(n, 35, h1, w1, dt, dev, c_alloc=64, zero=True)
+        # The BNPReLU over each concat (DABNet.py:166,171,176) never runs as a pass over the whole buffer: every producer
+        # applies its channel slice of it -- in its own epilogue where the raw value has no other reader
         y = self.init_conv[0](input)
         y = self.init_conv[1](y)
-        self.init_conv[2](y, out=cat0[:, :32])
-        ops.affine_act(d1, None, None, None, ACT_NONE, out=cat0[:, 32:35])
-        self.bn_prelu_1(cat0, out=cat0)
+        s, b, a = self.bn_prelu_1.prep(dev)[:3]
+        self.init_conv[2](y, then=(s[:32], b[:32], a[:32]), out2=cat0[:, :32], keep=False)
+        ops.affine_act(d1, s[32:], b[32:], a[32:], ACT_PRELU, out=cat0[:, 32:35])
 
         h2, w2 = d2.shape[2:]
         cat1 = ops.new_act(n, 131, h2, w2, dt, dev, c_alloc=192, zero=True)
+        s, b, a = self.bn_prelu_2.prep(dev)[:3]
         y = self.downsample_1(cat0, out=cat1[:, 64:128])
-        blocks = list(self.DAB_Block_1)
-        for i, blk in enumerate(blocks):
-            y = blk(y, out=cat1[:, 0:64] if i == len(blocks) - 1 else None)
-        ops.affine_act(d2, None, None, None, ACT_NONE, out=cat1[:, 128:131])
-        self.bn_prelu_2(cat1, out=cat1)
+        self._dab_block(list(self.DAB_Block_1), y, cat1[:, 0:64], (s[:64], b[:64], a[:64]))
+        ops.affine_act(y, s[64:128], b[64:128], a[64:128], ACT_PRELU, out=y)     # the down-sampler's slice, after its last reader
+        ops.affine_act(d2, s[128:], b[128:], a[128:], ACT_PRELU, out=cat1[:, 128:131])
 
         h3, w3 = d3.shape[2:]
         cat2 = ops.new_act(n, 259, h3, w3, dt, dev, c_alloc=320, zero=True)
+        s, b, a = self.bn_prelu_3.prep(dev)[:3]
         y = self.downsample_2(cat1, out=cat2[:, 128:256])
-        blocks = list(self.DAB_Block_2)
-        for i, blk in enumerate(blocks):
-            y = blk(y, out=cat2[:, 0:128] if i == len(blocks) - 1 else None)
-        ops.affine_act(d3, None, None, None, ACT_NONE, out=cat2[:, 256:259])
-        self.bn_prelu_3(cat2, out=cat2)
+        self._dab_block(list(self.DAB_Block_2), y, cat2[:, 0:128], (s[:128], b[:128], a[:128]))
+        ops.affine_act(y, s[128:256], b[128:256], a[128:256], ACT_PRELU, out=y)
+        ops.affine_act(d3, s[256:], b[256:], a[256:], ACT_PRELU, out=cat2[:, 256:259])
 
         classes = self.classifier[0].conv.out_channels
         if dt == torch.bfloat16:
@@ -283,6 +298,17 @@ class DABNet(nn.Module):
             scores = ops.new_act(n, classes, h3, w3, torch.float32, dev, c_alloc=32)
             self.classifier[0](cat2, out=scores)
         return scores, (h, w), dt
+
+    @staticmethod
+    def _dab_block(blocks, y, out, out_affine):
+        """A chain of DABModules: each conv1x1 + residual launch also emits the next module's bn_relu_1; the last one
+        writes only BNPReLU_concat(output) into its slice `out` of the concat buffer."""
+        pre = None
+        for i, blk in enumerate(blocks):
+            if i == len(blocks) - 1:
+                blk(y, out=out, pre=pre, then=out_affine, keep=False)
+            else:
+                y, pre = blk(y, pre=pre, then=blocks[i + 1].bn_relu_1.prep(y.device)[:3])
 
     def _cls_prep(self, device):
         m = self.classifier[0]

@@ -113,6 +113,26 @@ int esn_conv2d_direct(const EsnConv* p, void* stream);
  * ESN_ERR_UNSUPPORTED for anything else (the host then calls esn_conv2d_direct). */
 int esn_conv2d_umma(const EsnConv* p, void* stream);
 
+/* esn_conv2d_umma with a second epilogue stage computed on the value as it is stored (bf16):
+ *   v  = act(acc*scale + shift (+ residual))            -> conv.y   (store_y != 0)
+ *   v2 = act2(bf16(v) * scale2[c] + shift2[c])          -> y2
+ * One launch for "conv1x1 + input" followed by the next DABModule's bn_relu_1 (DABNet.py:69-83 then :70 of the next
+ * module: the sum is needed as that module's residual, its BNPReLU as the module's conv input), and, with store_y == 0,
+ * for a conv whose only consumer is a BNPReLU over a concat (init_conv[2] -> bn_prelu_1, DABNet.py:158-166; the last
+ * DABModule of a block -> bn_prelu_2 / bn_prelu_3, DABNet.py:171,176).  y2 has conv.y's shape (its own channel stride);
+ * results are bit-identical to esn_conv2d_umma followed by esn_affine_act.  Stride-1/2 forward convs whose Cout the
+ * staged epilogue takes (a multiple of 8, <= 64 or a multiple of 64); ESN_ERR_UNSUPPORTED otherwise. */
+typedef struct EsnConvDual {
+  EsnConv conv;
+  EsnTensor y2;
+  const float* scale2; /* [Cout] or NULL (=1) */
+  const float* shift2; /* [Cout] or NULL (=0) */
+  const float* alpha2; /* [Cout] PReLU slopes when act2 == ESN_ACT_PRELU */
+  int32_t act2;
+  int32_t store_y;     /* 0: conv.y is not written (it still carries the output shape) */
+} EsnConvDual;
+int esn_conv2d_umma_dual(const EsnConvDual* p, void* stream);
+
 /* Fused factorized pair: y = act2( conv_1xk( act1( conv_kx1(x)*s1 + b1 ) )*s2 + b2 (+ residual) ), both convs
  * dense C -> C with `taps` taps, padding (taps-1)/2 * dilation, the same dilation.  One half of the reference's
  * non_bottleneck_1d (ERFNet.py:44-65: conv3x1 -> ReLU -> conv1x3 -> BN -> ReLU, and the dilated second pair

@@ -138,6 +138,28 @@ def esn_conv2d_umma(ref):
     return 0
 
 
+def esn_conv2d_umma_dual(ref):
+    """include/esn.h EsnConvDual: y = epilogue(conv) (stored when store_y), y2 = act2(bf16(y) * scale2 + shift2)."""
+    d = ref._obj
+    p = d.conv
+    assert p.x.dtype == L.ESN_BF16 and p.y.dtype == L.ESN_BF16 and d.y2.dtype == L.ESN_BF16 and p.groups == 1 and not p.transposed
+    assert p.x.c_stride % 8 == 0 and p.y.c_stride % 8 == 0 and d.y2.c_stride % 8 == 0 and d.y2.ptr % 16 == 0, "TMA alignment"
+    cout = p.y.c
+    assert cout % 8 == 0 and (cout <= 64 or cout % 64 == 0) and p.cout_pad <= 256, "staged epilogue only"
+    assert (d.y2.n, d.y2.h, d.y2.w, d.y2.c) == (p.y.n, p.y.h, p.y.w, p.y.c)
+    x = _finite(tensor(p.x).float(), "esn_conv2d_umma_dual")
+    cin, taps = p.x.c, p.kh * p.kw
+    assert cin in (16, 32, 64) or cin % 64 == 0, cin
+    wp = _buf(p.w, taps * p.cout_pad * cin, torch.bfloat16, 2).float().view(p.kh, p.kw, p.cout_pad, cin)
+    v = epilogue(_conv_core(p, x, wp[:, :, :cout].permute(2, 3, 0, 1), cout), p.ep).to(torch.bfloat16)
+    if d.store_y:
+        store(tensor(p.y), v)
+    sc, sh, al = vec(d.scale2, cout), vec(d.shift2, cout), vec(d.alpha2, cout)
+    one = lambda t, dflt: dflt if t is None else t.view(1, -1, 1, 1)
+    store(tensor(d.y2), _act(v.float() * one(sc, 1.0) + one(sh, 0.0), d.act2, al))
+    return 0
+
+
 def esn_conv_pair_umma(ref):
     p = ref._obj
     x, y = _finite(tensor(p.x).float(), "esn_conv_pair_umma"), tensor(p.y)
@@ -391,7 +413,7 @@ def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
 
 
 ENTRY = {
-    "esn_conv2d_direct": esn_conv2d_direct, "esn_conv2d_umma": esn_conv2d_umma, "esn_conv_pair_umma": esn_conv_pair_umma,
+    "esn_conv2d_direct": esn_conv2d_direct, "esn_conv2d_umma": esn_conv2d_umma, "esn_conv2d_umma_dual": esn_conv2d_umma_dual, "esn_conv_pair_umma": esn_conv_pair_umma,
     "esn_stem_conv3x3s2": esn_stem_conv3x3s2,
     "esn_maxpool2x2_affine_act": _pool(lambda x: F.max_pool2d(x, 2, 2)),
     "esn_avgpool3x3s2_affine_act": _pool(lambda x: F.avg_pool2d(x, 3, 2, 1)),

@@ -232,3 +232,24 @@ def test_espnet_with_another_class_count(classes):
         with torch.autocast("cpu", dtype=torch.bfloat16):
             rel_ac = _rel(nets.forward("ESPNet", sd, x).float(), ref)
     assert yb.dtype == torch.bfloat16 and _rel(yb.float(), ref) < max(5e-2, 1.5 * rel_ac)
+
+
+def test_dabnet_dual_epilogue_routing_equals_two_launches(spec, monkeypatch):
+    """DABNet's bf16 step: 7 of the 9 conv1x1 + residual launches also emit the next module's bn_relu_1 (dual), the last
+    module of each block and init_conv[2] write only the concat's BNPReLU slice (chain), no BNPReLU pass runs over a whole
+    concat buffer -- and the logits are bit-identical to the route with one launch per op (ESN_DUAL=0)."""
+    from esn import ops
+    m = _model("DABNet", spec)
+    x = fixture.make_input(2, 128, 256)
+    with emulate_abi(bf16=True) as calls, torch.no_grad():
+        y1 = m(x)
+        names = [n for n, _ in calls]
+    assert names.count("esn_conv2d_umma_dual") == 10          # 7 dual + 2 chained block outputs + init_conv[2]
+    n_affine = names.count("esn_affine_act")
+    monkeypatch.setattr(ops, "DUAL_ENABLED", False)
+    with emulate_abi(bf16=True) as calls, torch.no_grad():
+        y0 = m(x)
+        names0 = [n for n, _ in calls]
+    assert "esn_conv2d_umma_dual" not in names0
+    assert names0.count("esn_affine_act") == n_affine + 10
+    assert torch.equal(y0, y1)

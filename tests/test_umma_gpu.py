@@ -49,6 +49,10 @@ CASES = [
     ("hv_3x3_64_64_d2_w200", 64, 64, 3, 1, 2, 2, False, 0, 2, 21, 200),
     ("hv_3x3_32_d16_w256", 32, 32, 3, 1, 16, 16, False, 0, 1, 40, 256),
     ("hv_fallback_3x3_64_128_w256", 64, 128, 3, 1, 1, 1, False, 0, 1, 10, 256),   # ring + 147 KB of weights do not fit: generic mode
+    # k_h x k_w convs with two K blocks: row tiles, one window per (tap row, K block), horizontal taps as shifted reads
+    ("hrows_3x3_128_64_w256", 128, 64, 3, 1, 1, 1, False, 0, 2, 12, 256),
+    ("hrows_3x3_128_64_d2_w200", 128, 64, 3, 1, 2, 2, False, 0, 2, 9, 200),
+    ("hrows_3x3_128_32_d4_w128", 128, 32, 3, 1, 4, 4, False, 0, 1, 11, 128),
 ]
 
 
@@ -201,3 +205,52 @@ def test_fused_transposed_conv(cin, cout, N, H, W):
     assert y.shape == ref.shape
     err = (y.float() - ref).abs().max() / ref.abs().max()
     assert err < 1.5e-2, err
+
+
+# second epilogue stage (esn_conv2d_umma_dual): bit-identical to conv followed by the affine pass, in every tile mode
+DUAL_CASES = [
+    # cin, cout, k, pad, dil, N, H, W, residual
+    (32, 64, 1, 0, 1, 2, 20, 256, True),      # DABModule conv1x1 + input, C = 64 (generic tiles, 128-byte rows)
+    (64, 128, 1, 0, 1, 2, 24, 128, True),     # C = 128 (two 64-channel column blocks)
+    (32, 32, 3, 1, 1, 2, 20, 256, False),     # init_conv[2] on the row ring
+    (32, 32, 3, 1, 1, 1, 9, 40, False),       # generic mode, partial tiles
+    (64, 64, (1, 3), (0, 2), (1, 2), 2, 8, 256, True),    # horizontal reuse
+    (16, 16, (3, 1), (1, 0), (1, 1), 2, 19, 512, False),  # vertical reuse, MT = 4
+]
+
+
+@pytest.mark.parametrize("keep", [True, False], ids=["dual", "chain"])
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[str(c) for c in DUAL_CASES])
+def test_dual_epilogue_equals_conv_then_affine(case, keep):
+    from esn import ops
+    from esn._lib import ACT_PRELU
+    cin, cout, k, pad, dil, N, H, W, use_res = case
+    torch.manual_seed(1)
+    conv = nn.Conv2d(cin, cout, k, padding=pad, dilation=dil).cuda()
+    s1, b1, a1 = (torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda") * 0.1, torch.rand(cout, device="cuda") * 0.3)
+    s2, b2, a2 = (torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda") * 0.1, torch.rand(cout, device="cuda") * 0.3)
+    prep = ops.ConvPrep(conv, s1, b1, ACT_PRELU, a1)
+    x = ops.new_act(N, cin, H, W, torch.bfloat16, "cuda")
+    x.copy_(torch.randn(N, cin, H, W, device="cuda"))
+    res = None
+    if use_res:
+        res = ops.new_act(N, cout, H, W, torch.bfloat16, "cuda")
+        res.copy_(torch.randn(N, cout, H, W, device="cuda"))
+    # reference: two launches
+    y_ref = ops.conv2d(x, prep, residual=res)
+    y2_ref = ops.affine_act(y_ref, s2, b2, a2, ACT_PRELU)
+    # one launch, second output into a channel slice of a wider buffer (as DABNet's concat slices are)
+    wide = ops.new_act(N, cout + 64, H, W, torch.bfloat16, "cuda", zero=True)
+    y2 = wide[:, 64:64 + cout]
+    ops.PROFILE = []
+    try:
+        y, _ = ops.conv2d_then_affine(x, prep, s2, b2, a2, ACT_PRELU, y2, residual=res, store_y=keep)
+        torch.cuda.synchronize()
+        names = [r["kernel"] for r in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert names == ["esn_conv2d_umma_dual"], names
+    assert torch.equal(y2, y2_ref)
+    if keep:
+        assert torch.equal(y, y_ref)
+    assert float(wide[:, :64].abs().max()) == 0.0          # nothing written outside the slice
