@@ -735,9 +735,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                                cc, un.w0 + qb * a.o_boxw, th0, un.n);
             }
             tma_store_commit();
-            // all but the newest NS-1 stores have finished reading smem -> the buffer tile tc+1 wants is free
-            if (NS == 4) tma_store_wait_read<3>(); else if (NS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-            if (tc + 1 >= (uint32_t)NS) mbar_arrive(sfree0 + 8u * ((tc + 1) & nsmask));
+            // A buffer is handed back as soon as its store has read it -- the store of the PREVIOUS tile, so this thread
+            // never waits on the one it just issued -- and not just in time for the tile that reuses it: the residual
+            // producer then runs NS-2 tiles ahead of the epilogue instead of issuing each residual load (an HBM round
+            // trip) when the epilogue is already waiting for it.
+            if (NS == 1) {
+              tma_store_wait_read<0>();
+              mbar_arrive(sfree0);
+            } else {
+              tma_store_wait_read<1>();
+              if (tc >= 1u) mbar_arrive(sfree0 + 8u * ((tc - 1u) & nsmask));
+            }
           }
         }
       }

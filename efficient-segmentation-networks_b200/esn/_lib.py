@@ -130,6 +130,7 @@ SYMBOLS = {
     "esn_maxpool2x2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
     "esn_avgpool3x3s2_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
     "esn_affine_act": (C.c_int, [C.POINTER(EsnPool), C.c_void_p]),
+    "esn_concat_tail": (C.c_int, [C.POINTER(EsnPool), C.c_int32, C.c_void_p]),
     "esn_convert_layout": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_dab_dw_pair": (C.c_int, [C.POINTER(EsnDabPair), C.c_void_p]),
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),

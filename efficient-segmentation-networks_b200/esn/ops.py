@@ -604,6 +604,21 @@ def affine_act(x, scale, shift, alpha, act, out=None, residual=None, flags=0):
     return _pool_call(L.lib.esn_affine_act, "esn_affine_act", x, out, scale, shift, alpha, act, residual, flags)
 
 
+def concat_tail(x, buf, c0, scale=None, shift=None, alpha=None, act=L.ACT_NONE):
+    """buf[:, c0:c0+c) = act(x*scale + shift) and zeros from there to the end of buf's padded pixel (esn_concat_tail):
+    x = the c <= 4 injected channels (fp32 NHWC, pixel stride 4), buf = a concat buffer whose pixel stride covers its
+    channel padding.  Whole-vector writes: the buffer needs no zero fill."""
+    n, c, h, w = x.shape
+    stride = buf.stride(3)
+    y = buf.as_strided((n, c, h, w), buf.stride(), buf.storage_offset() + c0)
+    p = L.EsnPool()
+    p.x, p.y = tdesc(x), tdesc(y)
+    _epilogue(p.ep, scale, shift, alpha, act, None, 0)
+    tail = stride - c0
+    _call(L.lib.esn_concat_tail, "esn_concat_tail", (C.byref(p), tail), _nbytes(x) + n * h * w * tail * buf.element_size())
+    return y
+
+
 def fglo_gate(x, w1, b1, w2, b2, out=None, residual=None):
     """CGNet FGlo: y = x * sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2) (+ residual)."""
     n, c, h, w = x.shape

@@ -263,30 +263,32 @@ class DABNet(nn.Module):
         d3 = self.down_1(d2)
 
         h1, w1 = d1.shape[2:]
-        cat0 = ops.new_act(n, 35, h1, w1, dt, dev, c_alloc=64, zero=True)
+        # concat buffers are written whole (producers' slices + esn_concat_tail, which also zeroes the channel padding):
+        # no zero fill
+        cat0 = ops.new_act(n, 35, h1, w1, dt, dev, c_alloc=64)
         # The BNPReLU over each concat (DABNet.py:166,171,176) never runs as a pass over the whole buffer: every producer
         # applies its channel slice of it -- in its own epilogue where the raw value has no other reader
         y = self.init_conv[0](input)
         y = self.init_conv[1](y)
         s, b, a = self.bn_prelu_1.prep(dev)[:3]
         self.init_conv[2](y, then=(s[:32], b[:32], a[:32]), out2=cat0[:, :32], keep=False)
-        ops.affine_act(d1, s[32:], b[32:], a[32:], ACT_PRELU, out=cat0[:, 32:35])
+        ops.concat_tail(d1, cat0, 32, s[32:], b[32:], a[32:], ACT_PRELU)
 
         h2, w2 = d2.shape[2:]
-        cat1 = ops.new_act(n, 131, h2, w2, dt, dev, c_alloc=192, zero=True)
+        cat1 = ops.new_act(n, 131, h2, w2, dt, dev, c_alloc=192)
         s, b, a = self.bn_prelu_2.prep(dev)[:3]
         y = self.downsample_1(cat0, out=cat1[:, 64:128])
         self._dab_block(list(self.DAB_Block_1), y, cat1[:, 0:64], (s[:64], b[:64], a[:64]))
         ops.affine_act(y, s[64:128], b[64:128], a[64:128], ACT_PRELU, out=y)     # the down-sampler's slice, after its last reader
-        ops.affine_act(d2, s[128:], b[128:], a[128:], ACT_PRELU, out=cat1[:, 128:131])
+        ops.concat_tail(d2, cat1, 128, s[128:], b[128:], a[128:], ACT_PRELU)
 
         h3, w3 = d3.shape[2:]
-        cat2 = ops.new_act(n, 259, h3, w3, dt, dev, c_alloc=320, zero=True)
+        cat2 = ops.new_act(n, 259, h3, w3, dt, dev, c_alloc=320)
         s, b, a = self.bn_prelu_3.prep(dev)[:3]
         y = self.downsample_2(cat1, out=cat2[:, 128:256])
         self._dab_block(list(self.DAB_Block_2), y, cat2[:, 0:128], (s[:128], b[:128], a[:128]))
         ops.affine_act(y, s[128:256], b[128:256], a[128:256], ACT_PRELU, out=y)
-        ops.affine_act(d3, s[256:], b[256:], a[256:], ACT_PRELU, out=cat2[:, 256:259])
+        ops.concat_tail(d3, cat2, 256, s[256:], b[256:], a[256:], ACT_PRELU)
 
         classes = self.classifier[0].conv.out_channels
         if dt == torch.bfloat16:

@@ -234,6 +234,13 @@ int esn_bilinear_nhwc(const EsnTensor* x, const EsnTensor* y, int32_t align_corn
  * standalone BNPReLU on concat tensors (DABNet.py:38-48,166,171,176). */
 int esn_affine_act(const EsnPool* p, void* stream);
 
+/* Tail of a channel concat: y[..., 0:c) = act(x*scale + shift) for the c <= 4 injected channels of x (fp32 NHWC, pixel
+ * stride 4: what the InputInjection average pools write, DABNet.py:113-124) and y[..., c:tail_c) = 0, where y is the view of
+ * the concat buffer that starts at the first injected channel and tail_c (a multiple of 4, <= y.c_stride) reaches the end of
+ * the padded pixel.  With the concat's BNPReLU slice in (scale, shift, alpha) this is "torch.cat([..., down_k], 1)" +
+ * bn_prelu_k for those channels (DABNet.py:166,171,176) in whole-sector writes; the concat buffer needs no zero fill. */
+int esn_concat_tail(const EsnPool* p, int32_t tail_c, void* stream);
+
 /* Layout / dtype conversion between NCHW f32 and NHWC f32|bf16 views. */
 int esn_convert_layout(const EsnTensor* x, const EsnTensor* y, void* stream);
 

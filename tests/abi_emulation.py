@@ -160,6 +160,24 @@ def esn_conv2d_umma_dual(ref):
     return 0
 
 
+def esn_concat_tail(ref, tail_c):
+    """include/esn.h: y[..., :c) = act(x*scale + shift), y[..., c:tail_c) = 0 (y = view of a concat buffer at the first
+    injected channel; the zero channels lie in the buffer's pixel padding, behind the view's logical channels)."""
+    p = ref._obj
+    tail_c = int(getattr(tail_c, "value", tail_c))
+    assert p.x.dtype == L.ESN_F32 and p.x.c <= 4 and p.x.c_stride == 4 and tail_c % 4 == 0 and 4 <= tail_c <= p.y.c_stride
+    c = p.x.c
+    sc, sh, al = vec(p.ep.scale, c), vec(p.ep.shift, c), vec(p.ep.alpha, c)
+    one = lambda t, dflt: dflt if t is None else t.view(1, -1, 1, 1)
+    v = _act(tensor(p.x).float() * one(sc, 1.0) + one(sh, 0.0), p.ep.act, al)
+    wide = L.EsnTensor.from_buffer_copy(p.y)
+    wide.c = tail_c
+    yw = tensor(wide)
+    yw.zero_()
+    store(yw[:, :c], v)
+    return 0
+
+
 def esn_conv_pair_umma(ref):
     p = ref._obj
     x, y = _finite(tensor(p.x).float(), "esn_conv_pair_umma"), tensor(p.y)
@@ -413,7 +431,7 @@ def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
 
 
 ENTRY = {
-    "esn_conv2d_direct": esn_conv2d_direct, "esn_conv2d_umma": esn_conv2d_umma, "esn_conv2d_umma_dual": esn_conv2d_umma_dual, "esn_conv_pair_umma": esn_conv_pair_umma,
+    "esn_conv2d_direct": esn_conv2d_direct, "esn_conv2d_umma": esn_conv2d_umma, "esn_conv2d_umma_dual": esn_conv2d_umma_dual, "esn_concat_tail": esn_concat_tail, "esn_conv_pair_umma": esn_conv_pair_umma,
     "esn_stem_conv3x3s2": esn_stem_conv3x3s2,
     "esn_maxpool2x2_affine_act": _pool(lambda x: F.max_pool2d(x, 2, 2)),
     "esn_avgpool3x3s2_affine_act": _pool(lambda x: F.avg_pool2d(x, 3, 2, 1)),
