@@ -432,33 +432,51 @@ __global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, TO* __restrict__ y
 
 }  // namespace
 
-// ---- concat tail: y[:, 0:c) = act(x * scale + shift), y[:, c:tail_c) = 0, four channels per thread.  Every pixel's tail
-// is written as whole 16 / 8-byte vectors (whole 32-byte sectors when tail_c covers them), so the concat buffer needs no
-// zero fill and the three injected channels cost no partial-sector read-modify-write.
+// ---- concat tail: y[:, 0:c) = act(x * scale + shift), y[:, c:tail_c) = 0, eight channels (16 bytes of bf16) per thread.
+// Every pixel's tail is written as whole vectors (whole 32-byte sectors), so the concat buffer needs no zero fill and the
+// three injected channels cost no partial-sector read-modify-write.
 namespace {
 template <typename TO>
-__global__ void __launch_bounds__(256) concat_tail_kernel(const float* __restrict__ x, TO* __restrict__ y, long long npix,
-                                                          int c, int y_cs, int nvec, EpiArgs ep) {
+__global__ void __launch_bounds__(256) concat_tail_kernel(const float* __restrict__ x, TO* __restrict__ y, long long total,
+                                                          int c, int y_cs, int vshift, EpiArgs ep) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= npix * nvec) return;
-  const long long pix = idx / nvec;
-  const int v = (int)(idx - pix * nvec);
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx >= total) return;
+  const long long pix = idx >> vshift;
+  const int v = (int)(idx & ((1 << vshift) - 1));
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (v == 0) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(x) + pix);
-    float f[4] = {t.x, t.y, t.z, t.w};
+    const float in[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j)
       if (j < c) {
-        const float r = f[j] * (ep.scale ? __ldg(ep.scale + j) : 1.f) + (ep.shift ? __ldg(ep.shift + j) : 0.f);
+        const float r = in[j] * (ep.scale ? __ldg(ep.scale + j) : 1.f) + (ep.shift ? __ldg(ep.shift + j) : 0.f);
         f[j] = apply_act(r, ep.act, ep.act == ESN_ACT_PRELU ? __ldg(ep.alpha + j) : 0.f);
-      } else {
-        f[j] = 0.f;
       }
-    }
-    o = make_float4(f[0], f[1], f[2], f[3]);
   }
-  st4<TO>(y + pix * y_cs + 4 * v, o);
+  TO* yp = y + pix * y_cs + 8 * v;
+  st4<TO>(yp, make_float4(f[0], f[1], f[2], f[3]));
+  st4<TO>(yp + 4, make_float4(f[4], f[5], f[6], f[7]));
+}
+template <>
+__global__ void __launch_bounds__(256) concat_tail_kernel<__nv_bfloat16>(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                                         long long total, int c, int y_cs, int vshift, EpiArgs ep) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long pix = idx >> vshift;
+  const int v = (int)(idx & ((1 << vshift) - 1));
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (v == 0) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(x) + pix);
+    const float in[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < c) {
+        const float r = in[j] * (ep.scale ? __ldg(ep.scale + j) : 1.f) + (ep.shift ? __ldg(ep.shift + j) : 0.f);
+        f[j] = apply_act(r, ep.act, ep.act == ESN_ACT_PRELU ? __ldg(ep.alpha + j) : 0.f);
+      }
+  }
+  *reinterpret_cast<uint4*>(y + pix * y_cs + 8 * v) = float_to_bf16x8(f);
 }
 }  // namespace
 
@@ -467,22 +485,24 @@ extern "C" int esn_concat_tail(const EsnPool* p, int32_t tail_c, void* stream) {
   const EsnTensor& x = p->x;
   const EsnTensor& y = p->y;
   if (x.n != y.n || x.h != y.h || x.w != y.w || x.c != y.c) return ESN_ERR_BAD_SHAPE;
-  if (x.dtype != ESN_F32 || x.c > 4 || x.c_stride != 4 || tail_c % 4 || tail_c < 4 || tail_c > y.c_stride) return ESN_ERR_UNSUPPORTED;
+  // whole pixels of 8-channel vectors, a power of two of them (DABNet: 32 or 64 channels)
+  if (x.dtype != ESN_F32 || x.c > 4 || x.c_stride != 4 || tail_c < 8 || tail_c > y.c_stride || (tail_c & (tail_c - 1)))
+    return ESN_ERR_UNSUPPORTED;
   if (p->ep.residual.ptr) return ESN_ERR_UNSUPPORTED;
   int rc = esn_check_epilogue(p->ep, y);
   if (rc) return rc;
   const size_t ysz = y.dtype == ESN_F32 ? 4 : 2;
-  if (((uintptr_t)x.ptr % 16) || ((uintptr_t)y.ptr % (4 * ysz)) || y.c_stride % 4) return ESN_ERR_ALIGN;
-  const long long npix = (long long)x.n * x.h * x.w;
-  const int nvec = tail_c / 4;
-  const long long total = npix * nvec;
+  if (((uintptr_t)x.ptr % 16) || ((uintptr_t)y.ptr % (8 * ysz)) || y.c_stride % 8) return ESN_ERR_ALIGN;
+  int vshift = 0;
+  while ((8 << vshift) < tail_c) ++vshift;
+  const long long total = ((long long)x.n * x.h * x.w) << vshift;
   const unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const EpiArgs ep = make_epi(p->ep);
   if (y.dtype == ESN_F32)
-    concat_tail_kernel<float><<<grid, 256, 0, st>>>((const float*)x.ptr, (float*)y.ptr, npix, x.c, y.c_stride, nvec, ep);
+    concat_tail_kernel<float><<<grid, 256, 0, st>>>((const float*)x.ptr, (float*)y.ptr, total, x.c, y.c_stride, vshift, ep);
   else
-    concat_tail_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x.ptr, (__nv_bfloat16*)y.ptr, npix, x.c, y.c_stride, nvec, ep);
+    concat_tail_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x.ptr, (__nv_bfloat16*)y.ptr, total, x.c, y.c_stride, vshift, ep);
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }

@@ -154,65 +154,41 @@ __device__ __forceinline__ float4 f4_prelu(float4 t, float4 al) {
   return make_float4(prelu1(t.x, al.x), prelu1(t.y, al.y), prelu1(t.z, al.z), prelu1(t.w, al.w));
 }
 
-// Stage-1 values in shared memory: fp32 for fp32 activations; for bf16 activations they are rounded to bf16 (what the tensor
-// between two separate bf16 kernels would hold), which halves the shared-memory wavefronts of the L1-bound kernel.
-template <typename TI> struct DabInter { using T = float4; };
-template <> struct DabInter<__nv_bfloat16> { using T = uint2; };
-__device__ __forceinline__ float4 inter_ld(const float4& v) { return v; }
-__device__ __forceinline__ float4 inter_ld(const uint2& v) {
-  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
-  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ void inter_st(float4& d, const float4 v) { d = v; }
-__device__ __forceinline__ void inter_st(uint2& d, const float4 v) {
-  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-  d = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-}
-
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) dab_dw_pair_row_kernel(const DabArgs a, const int CC, const int nchunk) {
-  using TS = typename DabInter<TI>::T;
-  extern __shared__ __align__(16) unsigned char dab_sm_raw[];
-  TS* dab_sm = reinterpret_cast<TS*>(dab_sm_raw);
+  extern __shared__ __align__(16) float4 dab_sm[];
   const int G = CC >> 2, gshift = 31 - __clz(G);          // 4-channel groups per pixel in this chunk (power of two)
   const int chunk = blockIdx.x % nchunk;
   const int row = blockIdx.x / nchunk;                     // n * H + h
   const int h = row % a.H;
   const int d = a.d, W = a.W;
-  TS* __restrict__ T1 = dab_sm;                            // [(W + 2)][G]   column w lives at (w + 1)
-  TS* __restrict__ T2 = dab_sm + (size_t)(W + 2) * G;      // [(W + 2d)][G]  column w lives at (w + d)
+  float4* __restrict__ T1 = dab_sm;                        // [(W + 2)][G]   column w lives at (w + 1)
+  float4* __restrict__ T2 = dab_sm + (size_t)(W + 2) * G;  // [(W + 2d)][G]  column w lives at (w + d)
   const int items = W * G;
   const int g = threadIdx.x & (G - 1);                     // loop-invariant: blockDim.x % G == 0
   const int c = chunk * CC + g * 4;
   auto PR = [&](int r) { return __ldg(reinterpret_cast<const float4*>(a.prm + (size_t)r * a.C + c)); };
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = threadIdx.x; i < G; i += blockDim.x) { inter_st(T1[i], zero); inter_st(T1[(W + 1) * G + i], zero); }
-  for (int i = threadIdx.x; i < d * G; i += blockDim.x) { inter_st(T2[i], zero); inter_st(T2[(W + d) * G + i], zero); }
+  for (int i = threadIdx.x; i < G; i += blockDim.x) { T1[i] = zero; T1[(W + 1) * G + i] = zero; }
+  for (int i = threadIdx.x; i < d * G; i += blockDim.x) { T2[i] = zero; T2[(W + d) * G + i] = zero; }
   const TI* __restrict__ xrow = reinterpret_cast<const TI*>(a.x) + (size_t)row * W * a.x_cs + c;   // pixel (h, 0)
 
-  {
-    // stage 1 of both branches in one pass: the centre row is loaded once (5 global loads per item)
-    const float4 sc1 = PR(12), sh1 = PR(13), al1 = PR(14);
-    const float4 p0 = f4_mul(PR(0), sc1), p1 = f4_mul(PR(1), sc1), p2 = f4_mul(PR(2), sc1);
-    const float4 sc2 = PR(18), sh2 = PR(19), al2 = PR(20);
-    const float4 q0 = f4_mul(PR(6), sc2), q1 = f4_mul(PR(7), sc2), q2 = f4_mul(PR(8), sc2);
-    const bool up1 = h - 1 >= 0, dn1 = h + 1 < a.H, upd = h - d >= 0, dnd = h + d < a.H;
-    const ptrdiff_t r1 = (ptrdiff_t)W * a.x_cs, rd = (ptrdiff_t)d * W * a.x_cs;
-    const int dG = d * G;
-#pragma unroll 2
+  auto stage1 = [&](const int wbase, const int abase, const int dd, float4* __restrict__ T, const int toff) {
+    const float4 sc = PR(abase), sh = PR(abase + 1), al = PR(abase + 2);
+    const float4 w0 = f4_mul(PR(wbase), sc), w1 = f4_mul(PR(wbase + 1), sc), w2 = f4_mul(PR(wbase + 2), sc);
+    const bool up = h - dd >= 0, dn = h + dd < a.H;
+    const ptrdiff_t ro = (ptrdiff_t)dd * W * a.x_cs;
+#pragma unroll 4
     for (int i = threadIdx.x; i < items; i += 256) {
       const TI* p = xrow + (size_t)(i >> gshift) * a.x_cs;
-      const float4 xc = ld4<TI>(p);
-      float4 t = f4_fma(xc, p1, sh1), u = f4_fma(xc, q1, sh2);
-      if (up1) t = f4_fma(ld4<TI>(p - r1), p0, t);
-      if (dn1) t = f4_fma(ld4<TI>(p + r1), p2, t);
-      if (upd) u = f4_fma(ld4<TI>(p - rd), q0, u);
-      if (dnd) u = f4_fma(ld4<TI>(p + rd), q2, u);
-      inter_st(T1[i + G], f4_prelu(t, al1));
-      inter_st(T2[i + dG], f4_prelu(u, al2));
+      float4 t = f4_fma(ld4<TI>(p), w1, sh);
+      if (up) t = f4_fma(ld4<TI>(p - ro), w0, t);
+      if (dn) t = f4_fma(ld4<TI>(p + ro), w2, t);
+      T[i + toff] = f4_prelu(t, al);
     }
-  }
+  };
+  stage1(0, 12, 1, T1, G);
+  stage1(6, 18, d, T2, d * G);
   __syncthreads();
 
   const float4 sb1 = PR(15), hb1 = PR(16), ab1 = PR(17);
@@ -224,12 +200,12 @@ __global__ void __launch_bounds__(256) dab_dw_pair_row_kernel(const DabArgs a, c
   const int dG = d * G;
 #pragma unroll 4
   for (int i = threadIdx.x; i < items; i += 256) {
-    float4 b1 = f4_fma(inter_ld(T1[i]), u0, hb1);
-    b1 = f4_fma(inter_ld(T1[i + G]), u1, b1);
-    b1 = f4_prelu(f4_fma(inter_ld(T1[i + 2 * G]), u2, b1), ab1);
-    float4 b2 = f4_fma(inter_ld(T2[i]), v0, hb2);
-    b2 = f4_fma(inter_ld(T2[i + dG]), v1, b2);
-    b2 = f4_prelu(f4_fma(inter_ld(T2[i + 2 * dG]), v2, b2), ab2);
+    float4 b1 = f4_fma(T1[i], u0, hb1);
+    b1 = f4_fma(T1[i + G], u1, b1);
+    b1 = f4_prelu(f4_fma(T1[i + 2 * G], u2, b1), ab1);
+    float4 b2 = f4_fma(T2[i], v0, hb2);
+    b2 = f4_fma(T2[i + dG], v1, b2);
+    b2 = f4_prelu(f4_fma(T2[i + 2 * dG], v2, b2), ab2);
     const float4 sum = make_float4(b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w);
     st4<TO>(yrow + (size_t)(i >> gshift) * a.y_cs, f4_prelu(f4_fma(sum, s3, h3), a3));
   }
@@ -279,8 +255,7 @@ extern "C" int esn_dab_dw_pair(const EsnDabPair* p, void* stream) {
     // channel chunk: the largest power of two dividing C whose two stage-1 rows fit 72 KB (3 CTAs per SM)
     int CC = 4;
     while (CC * 2 <= 64 && x.c % (CC * 2) == 0) CC *= 2;
-    const size_t inter_sz = x.dtype == ESN_BF16 ? sizeof(uint2) : sizeof(float4);     // DabInter<TI>::T
-    auto bytes = [&](int cc) { return (size_t)((x.w + 2) + (x.w + 2 * p->dilation)) * (cc / 4) * inter_sz; };
+    auto bytes = [&](int cc) { return (size_t)((x.w + 2) + (x.w + 2 * p->dilation)) * (cc / 4) * sizeof(float4); };
     while (CC > 4 && bytes(CC) > 72 * 1024) CC /= 2;
     if (bytes(CC) <= 96 * 1024) {
       int rc;

@@ -236,7 +236,7 @@ int esn_affine_act(const EsnPool* p, void* stream);
 
 /* Tail of a channel concat: y[..., 0:c) = act(x*scale + shift) for the c <= 4 injected channels of x (fp32 NHWC, pixel
  * stride 4: what the InputInjection average pools write, DABNet.py:113-124) and y[..., c:tail_c) = 0, where y is the view of
- * the concat buffer that starts at the first injected channel and tail_c (a multiple of 4, <= y.c_stride) reaches the end of
+ * the concat buffer that starts at the first injected channel and tail_c (a power of two >= 8, <= y.c_stride) reaches the end of
  * the padded pixel.  With the concat's BNPReLU slice in (scale, shift, alpha) this is "torch.cat([..., down_k], 1)" +
  * bn_prelu_k for those channels (DABNet.py:166,171,176) in whole-sector writes; the concat buffer needs no zero fill. */
 int esn_concat_tail(const EsnPool* p, int32_t tail_c, void* stream);

@@ -165,7 +165,7 @@ def esn_concat_tail(ref, tail_c):
     injected channel; the zero channels lie in the buffer's pixel padding, behind the view's logical channels)."""
     p = ref._obj
     tail_c = int(getattr(tail_c, "value", tail_c))
-    assert p.x.dtype == L.ESN_F32 and p.x.c <= 4 and p.x.c_stride == 4 and tail_c % 4 == 0 and 4 <= tail_c <= p.y.c_stride
+    assert p.x.dtype == L.ESN_F32 and p.x.c <= 4 and p.x.c_stride == 4 and (tail_c & (tail_c - 1)) == 0 and 8 <= tail_c <= p.y.c_stride
     c = p.x.c
     sc, sh, al = vec(p.ep.scale, c), vec(p.ep.shift, c), vec(p.ep.alpha, c)
     one = lambda t, dflt: dflt if t is None else t.view(1, -1, 1, 1)

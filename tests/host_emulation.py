@@ -133,6 +133,17 @@ def affine_act(x, scale, shift, alpha, act, out=None, residual=None, flags=0):
     return _store(out, _epilogue(x.float(), scale, shift, alpha, act, residual, flags))
 
 
+def concat_tail(x, buf, c0, scale=None, shift=None, alpha=None, act=L.ACT_NONE):
+    """include/esn.h esn_concat_tail: the injected channels through their BNPReLU slice, zeros to the end of the padded pixel."""
+    n, c, h, w = x.shape
+    tail = buf.stride(3) - c0
+    assert tail >= 8 and tail & (tail - 1) == 0, tail
+    full = buf.as_strided((n, tail, h, w), buf.stride(), buf.storage_offset() + c0)
+    full.zero_()
+    full[:, :c].copy_(_epilogue(x.float(), scale, shift, alpha, act, None).to(buf.dtype))
+    return full[:, :c]
+
+
 def adaptive_avgpool(x, size, dtype=None):
     n, c, h, w = x.shape
     y = new_act(n, c, size, size, dtype or x.dtype, x.device)
@@ -219,7 +230,7 @@ def dab_dw_pair(x, prm, dilation, out=None):
 
 _SWAPS = dict(gate_bcast=gate_bcast, fglo_gate=fglo_gate, maxpool3x3s2_idx=maxpool3x3s2_idx, max_unpool2x2=max_unpool2x2,
               dab_dw_pair=dab_dw_pair, new_act=new_act, require_cuda=require_cuda, as_act=as_act, to_nchw=to_nchw, conv2d=conv2d,
-              stem_conv3x3s2=stem_conv3x3s2, maxpool2x2=maxpool2x2, avgpool3x3s2=avgpool3x3s2, affine_act=affine_act,
+              stem_conv3x3s2=stem_conv3x3s2, maxpool2x2=maxpool2x2, avgpool3x3s2=avgpool3x3s2, affine_act=affine_act, concat_tail=concat_tail,
               adaptive_avgpool=adaptive_avgpool, bilinear=bilinear, head_convt2x2=head_convt2x2,
               head_bilinear=head_bilinear)
 

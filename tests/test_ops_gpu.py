@@ -258,8 +258,7 @@ def test_dab_pair_matches_torch(ops, dt):
             ref = F.prelu(s, m.bn_relu_2.acti.weight)
         y = ops.dab_dw_pair(ops.as_act(x, dt), m.prep(x.device), d)
         assert y.dtype == dt
-        # bf16: fp32 arithmetic, the stage-1 values (the tensor between dconv3x1 and dconv1x3) and the output rounded to bf16
-        tol = 1e-5 if dt == torch.float32 else 2e-2
+        tol = 1e-5 if dt == torch.float32 else 1e-2      # bf16: output rounding only (fp32 arithmetic inside)
         assert (y.float() - ref).abs().max() / ref.abs().max() < tol, (c, d, hh, ww)
 
 
