@@ -506,8 +506,12 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
         if world > 1:
             parallel.data_parallel(m)
         crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
-        opt = torch.optim.Adam(m.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True,
-                               capturable=not args.no_graph)  # train.py:212-215
+        if args.torch_adam:
+            opt = torch.optim.Adam(m.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True,
+                                   capturable=not args.no_graph)
+        else:
+            from esn.optim import Adam      # train.py:212-215's torch.optim.Adam as one esn_adam_step launch
+            opt = Adam(m.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
         y_host = fixture.make_labels(batch, H, W, 19, seed=1234 + rank).pin_memory()
         y = y_host.cuda(non_blocking=True)
     else:
@@ -815,6 +819,8 @@ def main():
                     help="inference e2e leg: what crosses PCIe -- decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / "
                          "CHW done on the device (esn_image_u8hwc_to_f32nchw, SURVEY 8f-4; default), or the reference's "
                          "pre-processed fp32 NCHW batch")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="training workloads: step torch.optim.Adam(fused=True) instead of esn.optim.Adam (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are

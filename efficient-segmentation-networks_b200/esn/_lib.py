@@ -177,6 +177,9 @@ SYMBOLS = {
     "esn_scale_nc": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_adaptive_avgpool": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_bilinear_nhwc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
+    "esn_adam_chunk": (C.c_int32, []),
+    "esn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_void_p]),
     "esn_version": (C.c_int, []),
     "esn_strerror": (C.c_char_p, [C.c_int]),
     "esn_launch_count": (C.c_int64, []),

@@ -10,7 +10,8 @@ the graph, so a data-parallel step has no host work besides copying the batch in
     for images, labels in loader:
         loss = step(images, labels)        # device scalar; .item() only when you log
 
-The optimizer must keep its state on the device (`torch.optim.Adam(..., capturable=True)`).  Dropout masks are a function
+The optimizer must keep its state on the device: `esn.optim.Adam` (one launch per step; float learning rates written by a
+host-side schedule are uploaded before each replay) or `torch.optim.Adam(..., capturable=True)`.  Dropout masks are a function
 of (seed, element, step): the step counter lives on the device and is advanced inside the graph, so replays draw new
 masks (esn.train.dropout).
 """
@@ -61,6 +62,8 @@ class GraphedTrainStep:
             self.images.copy_(images, non_blocking=True)
         if labels is not None and labels is not self.labels:
             self.labels.copy_(labels, non_blocking=True)
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()        # esn.optim.Adam: float learning rates written by a host-side schedule
         self.graph.replay()
         # the replay changed weights and BN buffers behind autograd's back (no `_version` bump): invalidate every packed-
         # weight / folded-BN cache so that a following model.eval() or eager iteration rebuilds from the new values

@@ -509,6 +509,26 @@ int esn_augment_u8(const EsnAugItem* items, int32_t n, int32_t crop_h, int32_t c
  * scores (LEDNet keeps its single-channel pyramid in fp32). */
 int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnTensor* b, const EsnTensor* y, void* stream);
 
+/* Optimizer step of the training iteration (train.py:355 `optimizer.step()` on the torch.optim.Adam of train.py:212-215):
+ * Adam with L2 weight decay (torch.optim.Adam semantics, amsgrad = False, maximize = False) over every parameter tensor of a
+ * param group in ONE launch.  table: DEVICE array of fp32 tensors (parameter, gradient, exp_avg, exp_avg_sq: n elements each,
+ * 4-byte aligned; 16-byte aligned chunks take the vector path).  blocks: DEVICE array of n_blocks (tensor index, chunk index)
+ * int32 pairs, one per CTA, chunk = esn_adam_chunk() elements -- together they cover every element once.  lr, step: DEVICE
+ * scalars (fp32); *step is the number of updates done so far: the launch uses step + 1 for the bias corrections and stores it
+ * back (the last CTA to finish does, through the zero-initialised DEVICE counter done, which it re-arms).  For every element:
+ *   g += weight_decay * p;  m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps). */
+typedef struct EsnAdamTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} EsnAdamTensor;
+int32_t esn_adam_chunk(void);
+int esn_adam_step(const EsnAdamTensor* table, const int32_t* blocks, int32_t n_blocks, const float* lr, float* step,
+                  uint32_t* done, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);
 const char* esn_strerror(int code);

@@ -556,17 +556,21 @@ def test_graphed_train_step_equals_eager(spec, net):
     lab = fixture.make_labels(2, 64, 128, 19).cuda()
     crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
 
-    def make(p_drop):
+    def make(p_drop, ours=True):
         m = build_model(net, 19)
         m.load_state_dict(spec_state_dict(spec, net))
         m = m.cuda().train()
         for mod in m.modules():
             if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
                 mod.p = p_drop if p_drop is not None else mod.p
-        opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=1e-4, fused=True, capturable=True)
+        if ours:        # the graphed steps run esn.optim.Adam (one launch), the eager reference torch's fused Adam
+            from esn.optim import Adam
+            opt = Adam(m.parameters(), lr=5e-4, weight_decay=1e-4)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=1e-4, fused=True, capturable=True)
         return m, opt
 
-    m0, o0 = make(0.0)
+    m0, o0 = make(0.0, ours=False)
     eager = []
     for _ in range(4):
         o0.zero_grad(set_to_none=True)
