@@ -119,6 +119,116 @@ __global__ void __launch_bounds__(128, 3) head_convt3x3s2_mask_kernel(const Head
   }
 }
 
+// ---- ConvTranspose2d(16, classes, 2, stride 2) + argmax: the close of ERFNet / ESNet (ERFNet.py:112,128; ESNet.py:182) --------
+//
+//   y[2i+a, 2j+b, co] = x[i, j, :] . W[:, co, a, b] + bias[co]
+//
+// Every input pixel owns its four output pixels, so a warp takes 16 consecutive input pixels and runs, per output position
+// (a, b), one mma.m16n8k16 per 8 classes (M = 16 pixels, K = 16 channels, N = 24 = classes padded).  The CUDA-core kernel
+// (esn_head_convt2x2) spends 1216 FMAs per input pixel and is FP32-issue-bound at 0.09 of the HBM roofline; here the
+// arithmetic is 24 MMAs per 16 pixels and the kernel streams.  The weights stay fp32-accurate: W = hi + lo in bf16, two
+// MMAs per tile (the activations are bf16 either way).  The K slots of the MMA are a permutation of the channels chosen so
+// that lane (g, t) needs channels 4t .. 4t+3 of pixel g (one 8-byte load: four lanes read a whole 32-byte pixel); the host
+// packs the B fragments with the same permutation.  Two tiles are prefetched ahead of the one being multiplied.
+struct HeadT2Args {
+  const __nv_bfloat16* x;
+  const uint32_t* wfrag;    // [2 hi/lo][4 positions][3 n-tiles][32 lanes][2]
+  const float* bias;
+  uint8_t* mask;            // (N, 2h, 2w)
+  int W, x_cs, classes;
+  long long tiles;
+};
+
+__global__ void __launch_bounds__(128, 4) head_convt2x2_mask_kernel(const HeadT2Args a) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  uint32_t bf[2][4][3][2];
+#pragma unroll
+  for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.wfrag) + ((hl * 4 + p) * 3 + nt) * 32 + lane);
+        bf[hl][p][nt][0] = v.x;
+        bf[hl][p][nt][1] = v.y;
+      }
+  float binit[3][2];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int cls = nt * 8 + 2 * t + e;
+      binit[nt][e] = cls < a.classes ? (a.bias ? __ldg(a.bias + cls) : 0.f) : -INFINITY;
+    }
+  // rows g and g + 8 of a tile: channels 4t .. 4t+3 of pixels tile * 16 + g (+ 8)
+  auto load = [&](long long tile, uint2& r0, uint2& r1) {
+    const __nv_bfloat16* px = a.x + (size_t)(tile * 16 + g) * a.x_cs + 4 * t;
+    r0 = __ldg(reinterpret_cast<const uint2*>(px));
+    r1 = __ldg(reinterpret_cast<const uint2*>(px + (size_t)8 * a.x_cs));
+  };
+  const uint2 z2 = make_uint2(0u, 0u);
+  long long tile = warp, nxt = warp + nwarps, nn = warp + 2 * nwarps;
+  uint2 c0 = z2, c1 = z2, n0 = z2, n1 = z2;
+  if (tile < a.tiles) load(tile, c0, c1);
+  if (nxt < a.tiles) load(nxt, n0, n1);
+  for (; tile < a.tiles; tile = nxt, nxt = nn, nn += nwarps) {
+    uint2 f0 = z2, f1 = z2;
+    if (nn < a.tiles) load(nn, f0, f1);
+    const uint32_t af[4] = {c0.x, c1.x, c0.y, c1.y};     // (row g, slots 2t..), (row g+8, slots 2t..), (row g, 2t+8..), (row g+8, 2t+8..)
+    float acc[4][3][4];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        acc[pos][nt][0] = acc[pos][nt][2] = binit[nt][0];
+        acc[pos][nt][1] = acc[pos][nt][3] = binit[nt][1];
+      }
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        mma_bf16_16816(acc[pos][nt], af, bf[1][pos][nt][0], bf[1][pos][nt][1]);      // low parts first
+        mma_bf16_16816(acc[pos][nt], af, bf[0][pos][nt][0], bf[0][pos][nt][1]);
+      }
+    int res[4][2];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs) {
+        float bv = acc[pos][0][hs * 2];
+        int bi = 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (nt == 0 && e == 0) continue;
+            const float v = acc[pos][nt][hs * 2 + e];
+            if (v > bv) { bv = v; bi = nt * 8 + 2 * t + e; }
+          }
+#pragma unroll
+        for (int off = 1; off < 4; off <<= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        res[pos][hs] = bi;
+      }
+    // lane t of a quad stores the two mask bytes of output row a = t >> 1 for pixel g + 8 * (t & 1)
+    const int hs = t & 1, ra = t >> 1;
+    const int s0 = hs ? res[0][1] : res[0][0], s1 = hs ? res[1][1] : res[1][0];
+    const int s2 = hs ? res[2][1] : res[2][0], s3 = hs ? res[3][1] : res[3][0];
+    const uchar2 out = make_uchar2((uint8_t)(ra ? s2 : s0), (uint8_t)(ra ? s3 : s1));
+    const long long pix = tile * 16 + g + 8 * hs;
+    const long long row = pix / a.W;                     // n * H + i
+    const int j = (int)(pix - row * a.W);
+    uint8_t* o = a.mask + ((size_t)(2 * row + ra) * (2 * a.W) + 2 * j);
+    *reinterpret_cast<uchar2*>(o) = out;
+    c0 = n0; c1 = n1; n0 = f0; n1 = f1;
+  }
+}
+
 }  // namespace
 
 extern "C" int esn_head_convt3x3s2_mask(const EsnHeadT3* p, void* stream) {
@@ -137,6 +247,26 @@ extern "C" int esn_head_convt3x3s2_mask(const EsnHeadT3* p, void* stream) {
   long long ctas = (a.tiles + 3) / 4;                   // four warps per CTA
   if (ctas > 148 * 3 * 4) ctas = 148 * 3 * 4;           // grid-stride beyond ~4 waves of resident CTAs
   head_convt3x3s2_mask_kernel<<<(unsigned)ctas, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}
+
+extern "C" int esn_head_convt2x2_mask(const EsnHeadT3* p, void* stream) {
+  if (!p || !p->wfrag || !p->mask || !esn_valid_nhwc(p->x)) return ESN_ERR_BAD_ARG;
+  if (p->classes < 1 || p->classes > 24) return ESN_ERR_UNSUPPORTED;
+  const EsnTensor& x = p->x;
+  if (x.dtype != ESN_BF16 || x.c != 16 || x.w % 16 || x.c_stride % 4) return ESN_ERR_UNSUPPORTED;
+  if (((uintptr_t)x.ptr % 8) || ((uintptr_t)p->wfrag % 8) || ((uintptr_t)p->mask % 2)) return ESN_ERR_ALIGN;
+  HeadT2Args a;
+  a.x = (const __nv_bfloat16*)x.ptr;
+  a.wfrag = p->wfrag;
+  a.bias = p->bias;
+  a.mask = p->mask;
+  a.W = x.w; a.x_cs = x.c_stride; a.classes = p->classes;
+  a.tiles = (long long)x.n * x.h * (x.w / 16);
+  long long ctas = (a.tiles + 3) / 4;                   // four warps per CTA
+  if (ctas > 148 * 4 * 2) ctas = 148 * 4 * 2;           // grid-stride beyond two waves of resident CTAs
+  head_convt2x2_mask_kernel<<<(unsigned)ctas, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }

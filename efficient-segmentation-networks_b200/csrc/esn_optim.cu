@@ -15,30 +15,29 @@ namespace {
 constexpr int kAdamThreads = 256;
 constexpr int kAdamChunk = 2048;      // elements per CTA (ESN_ADAM_CHUNK in esn.h)
 
-__device__ __forceinline__ float adam1(float& p, float g, float& m, float& v, float b1, float b2, float wd, float step_size,
-                                       float bc2_sqrt, float eps) {
+// b = (beta1, 1 - beta1, beta2, 1 - beta2): the complements are rounded from the double values, not formed as 1 - float(beta)
+// (1 - 0.999f is off by 1.3e-5 relative, which the second moment would carry)
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const float4 b, float wd, float step_size,
+                                      float bc2_sqrt, float eps) {
   if (wd != 0.f) g = fmaf(p, wd, g);                               // L2 penalty folded into the gradient (torch.optim.Adam)
-  m = fmaf(b1, m, fmaf(-b1, g, g));                                // m = b1 m + (1 - b1) g
-  const float g2 = g * g;
-  v = fmaf(b2, v, fmaf(-b2, g2, g2));                              // v = b2 v + (1 - b2) g^2
+  m = fmaf(b.x, m, b.y * g);
+  v = fmaf(b.z, v, b.w * g * g);
   const float denom = sqrtf(v) / bc2_sqrt + eps;
   p -= step_size * m / denom;
-  return p;
 }
 
 __global__ void __launch_bounds__(kAdamThreads) adam_table_kernel(const EsnAdamTensor* __restrict__ tab,
                                                                   const int2* __restrict__ blocks,
                                                                   const float* __restrict__ lr, float* step,
-                                                                  unsigned int* done, const float beta1, const float beta2,
+                                                                  unsigned int* done, const double beta1, const double beta2,
                                                                   const float eps, const float wd) {
   __shared__ float s_c[2];
   if (threadIdx.x == 0) {
-    const float t = *reinterpret_cast<volatile float*>(step) + 1.f;          // this update's step number
-    const float bc1 = 1.f - powf(beta1, t);
-    const float bc2 = 1.f - powf(beta2, t);
-    s_c[0] = __ldg(lr) / bc1;
-    s_c[1] = sqrtf(bc2);
+    const double t = (double)*reinterpret_cast<volatile float*>(step) + 1.0;  // this update's step number
+    s_c[0] = (float)((double)__ldg(lr) / (1.0 - pow(beta1, t)));             // lr / bias_correction1
+    s_c[1] = (float)sqrt(1.0 - pow(beta2, t));                               // sqrt(bias_correction2)
   }
+  const float4 bt = make_float4((float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2));
   const int2 b = __ldg(blocks + blockIdx.x);
   const EsnAdamTensor T = tab[b.x];
   __syncthreads();
@@ -65,10 +64,10 @@ __global__ void __launch_bounds__(kAdamThreads) adam_table_kernel(const EsnAdamT
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int i = threadIdx.x + k * kAdamThreads;
-      adam1(P[k].x, G[k].x, M[k].x, V[k].x, beta1, beta2, wd, step_size, bc2_sqrt, eps);
-      adam1(P[k].y, G[k].y, M[k].y, V[k].y, beta1, beta2, wd, step_size, bc2_sqrt, eps);
-      adam1(P[k].z, G[k].z, M[k].z, V[k].z, beta1, beta2, wd, step_size, bc2_sqrt, eps);
-      adam1(P[k].w, G[k].w, M[k].w, V[k].w, beta1, beta2, wd, step_size, bc2_sqrt, eps);
+      adam1(P[k].x, G[k].x, M[k].x, V[k].x, bt, wd, step_size, bc2_sqrt, eps);
+      adam1(P[k].y, G[k].y, M[k].y, V[k].y, bt, wd, step_size, bc2_sqrt, eps);
+      adam1(P[k].z, G[k].z, M[k].z, V[k].z, bt, wd, step_size, bc2_sqrt, eps);
+      adam1(P[k].w, G[k].w, M[k].w, V[k].w, bt, wd, step_size, bc2_sqrt, eps);
       reinterpret_cast<float4*>(p)[i] = P[k];
       reinterpret_cast<float4*>(m)[i] = M[k];
       reinterpret_cast<float4*>(v)[i] = V[k];
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_table_kernel(const EsnAdamT
     for (int k = 0; k < 8; ++k) {
       const int i = threadIdx.x + k * kAdamThreads;
       if (i < cnt) {
-        adam1(P[k], G[k], M[k], V[k], beta1, beta2, wd, step_size, bc2_sqrt, eps);
+        adam1(P[k], G[k], M[k], V[k], bt, wd, step_size, bc2_sqrt, eps);
         p[i] = P[k]; m[i] = M[k]; v[i] = V[k];
       }
     }
@@ -107,14 +106,14 @@ __global__ void __launch_bounds__(kAdamThreads) adam_table_kernel(const EsnAdamT
 extern "C" int32_t esn_adam_chunk(void) { return kAdamChunk; }
 
 extern "C" int esn_adam_step(const EsnAdamTensor* table, const int32_t* blocks, int32_t n_blocks, const float* lr, float* step,
-                             uint32_t* done, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+                             uint32_t* done, double beta1, double beta2, double eps, double weight_decay, void* stream) {
   if (!table || !blocks || !lr || !step || !done) return ESN_ERR_BAD_ARG;
   if (n_blocks < 0) return ESN_ERR_BAD_SHAPE;
   if (n_blocks == 0) return ESN_OK;
-  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && weight_decay >= 0.f)) return ESN_ERR_BAD_ARG;
+  if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0 && weight_decay >= 0.0)) return ESN_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(table) % 8) || (reinterpret_cast<uintptr_t>(blocks) % 8)) return ESN_ERR_ALIGN;
   adam_table_kernel<<<(unsigned)n_blocks, kAdamThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      table, reinterpret_cast<const int2*>(blocks), lr, step, done, beta1, beta2, eps, weight_decay);
+      table, reinterpret_cast<const int2*>(blocks), lr, step, done, beta1, beta2, (float)eps, (float)weight_decay);
   ESN_CHECK_LAUNCH();
   return ESN_OK;
 }

@@ -136,6 +136,7 @@ SYMBOLS = {
     "esn_head_convt2x2": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_bilinear": (C.c_int, [C.POINTER(EsnHead), C.c_void_p]),
     "esn_head_convt3x3s2_mask": (C.c_int, [C.POINTER(EsnHeadT3), C.c_void_p]),
+    "esn_head_convt2x2_mask": (C.c_int, [C.POINTER(EsnHeadT3), C.c_void_p]),
     "esn_bottleneck4": (C.c_int, [C.POINTER(EsnBneck4), C.c_void_p]),
     "esn_weighted_ce": (C.c_int, [C.POINTER(EsnCE), C.c_void_p]),
     "esn_augment_max_batch": (C.c_int32, []),
@@ -178,8 +179,8 @@ SYMBOLS = {
     "esn_adaptive_avgpool": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_bilinear_nhwc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
     "esn_adam_chunk": (C.c_int32, []),
-    "esn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                C.c_float, C.c_float, C.c_void_p]),
+    "esn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                C.c_double, C.c_double, C.c_void_p]),
     "esn_version": (C.c_int, []),
     "esn_strerror": (C.c_char_p, [C.c_int]),
     "esn_launch_count": (C.c_int64, []),

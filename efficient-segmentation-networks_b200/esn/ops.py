@@ -763,6 +763,43 @@ def head_convt3x3s2_mask(x, wfrag, bias, classes):
     return mask
 
 
+def pack_convt2x2_frags(weight, classes):
+    """ConvTranspose2d(16, classes, 2, 2).weight (16, classes, 2, 2) -> the bf16 B fragments of esn_head_convt2x2_mask
+    (include/esn.h): int32 [2 hi/lo][4 positions][3 class tiles][32 lanes][2]; w = hi + lo keeps the fp32 weights to ~2^-17."""
+    w = weight.detach().float()
+    assert w.shape[0] == 16 and w.shape[2:] == (2, 2) and classes <= 24
+    B = torch.zeros(4, 16, 24, dtype=torch.float32, device=w.device)
+    for a in range(2):
+        for b in range(2):
+            B[a * 2 + b, :, :classes] = w[:, :classes, a, b]
+    hi = B.to(torch.bfloat16)
+    lo = (B - hi.float()).to(torch.bfloat16)
+    lane = torch.arange(32, device=w.device)
+    g, t = lane // 4, lane % 4
+    frag = torch.empty(2, 4, 3, 32, 2, 2, dtype=torch.bfloat16, device=w.device)    # [..., register, (low, high)]
+    for hl, part in enumerate((hi, lo)):
+        for nt in range(3):
+            for r in range(2):
+                frag[hl, :, nt, :, r, 0] = part[:, 4 * t + 2 * r, nt * 8 + g]
+                frag[hl, :, nt, :, r, 1] = part[:, 4 * t + 2 * r + 1, nt * 8 + g]
+    return frag.contiguous().view(torch.int32).reshape(2, 4, 3, 32, 2).contiguous()
+
+
+def head_convt2x2_mask(x, wfrag, bias, classes):
+    """uint8 argmax mask (N, 2h, 2w) of ConvTranspose2d(16, classes, 2, 2)(x) in one tensor-core launch; None when the entry
+    point does not take the shape (the caller then runs esn_head_convt2x2)."""
+    n, c, h, w = x.shape
+    if not (x.dtype == torch.bfloat16 and is_nhwc(x) and c == 16 and w % 16 == 0 and classes <= 24 and x.stride(3) % 4 == 0):
+        return None
+    mask = torch.empty((n, 2 * h, 2 * w), dtype=torch.uint8, device=x.device)
+    p = L.EsnHeadT3()
+    p.x, p.wfrag, p.mask, p.classes = tdesc(x), wfrag.data_ptr(), mask.data_ptr(), classes
+    p.bias = bias.data_ptr() if bias is not None else None
+    _call(L.lib.esn_head_convt2x2_mask, "esn_head_convt2x2_mask", (C.byref(p),), _nbytes(x) + mask.numel(),
+          2 * n * h * w * 4 * 16 * classes)
+    return mask
+
+
 def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, sums=None, gnorm=None, gout=None,
                 prob_out=None, keep_thresh=None):
     """Returns (sums[2] = [sum w*nll, sum w], dlogits or None); dlogits are scaled by gout/gnorm

@@ -167,7 +167,10 @@ class Decoder(PrepMixin, nn.Module):
         cin, classes = w.shape[0], w.shape[1]
         packed = torch.zeros((2, 2, cin, 32), dtype=torch.float32, device=device)
         packed[:, :, :, :classes] = w.permute(2, 3, 0, 1)
-        return packed.contiguous(), self.output_conv.bias.detach().to(device=device, dtype=torch.float32).contiguous(), classes
+        # mask-only bf16 path: transposed conv + argmax on the tensor cores (esn_head_convt2x2_mask)
+        frags = ops.pack_convt2x2_frags(w, classes) if (cin == 16 and classes <= 24) else None
+        return (packed.contiguous(), self.output_conv.bias.detach().to(device=device, dtype=torch.float32).contiguous(), classes,
+                frags)
 
     def features(self, input):
         output = input
@@ -176,7 +179,11 @@ class Decoder(PrepMixin, nn.Module):
         return output
 
     def head(self, feat, want_logits=True, want_mask=False):
-        w, b, classes = self.prep(feat.device)
+        w, b, classes, frags = self.prep(feat.device)
+        if want_mask and not want_logits and frags is not None:
+            mask = ops.head_convt2x2_mask(feat, frags, b, classes)
+            if mask is not None:          # bf16 features: the full-resolution scores never leave the registers
+                return None, mask
         ldt = torch.bfloat16 if feat.dtype == torch.bfloat16 else torch.float32
         return ops.head_convt2x2(feat, w, b, classes, want_logits, want_mask, ldt)
 

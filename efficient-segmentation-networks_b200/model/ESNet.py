@@ -149,7 +149,8 @@ class ESNet(nn.Module):
             packed = torch.zeros((2, 2, cin, 32), dtype=torch.float32, device=device)
             packed[:, :, :, :classes] = w.permute(2, 3, 0, 1)
             bias = bs.detach().to(device=device, dtype=torch.float32).contiguous()
-            cached = (sig, (packed.contiguous(), bias, classes))
+            frags = ops.pack_convt2x2_frags(w, classes) if (cin == 16 and classes <= 24) else None
+            cached = (sig, (packed.contiguous(), bias, classes, frags))
             self.__dict__["_esn_head"] = cached
         return cached[1]
 
@@ -167,7 +168,11 @@ class ESNet(nn.Module):
         return output
 
     def _head(self, feat, want_logits, want_mask):
-        w, b, classes = self._head_prep(feat.device)
+        w, b, classes, frags = self._head_prep(feat.device)
+        if want_mask and not want_logits and frags is not None:
+            mask = ops.head_convt2x2_mask(feat, frags, b, classes)      # tensor cores, scores stay in registers
+            if mask is not None:
+                return None, mask
         ldt = torch.bfloat16 if feat.dtype == torch.bfloat16 else torch.float32
         return ops.head_convt2x2(feat, w, b, classes, want_logits, want_mask, ldt)
 

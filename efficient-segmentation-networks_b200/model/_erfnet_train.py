@@ -72,6 +72,6 @@ def erfnet_train_forward(model, input):
         y = _nb1d(tape, layer, y) if hasattr(layer, "conv3x1_1") else _down(tape, layer, y, dt)
     for layer in dec.layers:
         y = _nb1d(tape, layer, y) if hasattr(layer, "conv3x1_1") else _up(tape, layer, y)
-    w, b, classes = dec.prep(y.t.device)
+    w, b, classes, _ = dec.prep(y.t.device)
     logits, holder = T.convt2x2_logits(tape, _convT(dec.output_conv), y, w, b, classes)
     return logits, tape, holder

@@ -314,6 +314,16 @@ typedef struct EsnHeadT3 {
 } EsnHeadT3;
 int esn_head_convt3x3s2_mask(const EsnHeadT3* p, void* stream);
 
+/* ConvTranspose2d(16, classes <= 24, 2, stride 2) + argmax over classes in one tensor-core launch: ERFNet's / ESNet's
+ * output_conv (ERFNet.py:112,128; ESNet.py:182) fused with the CPU argmax of test.py:79-82, mask only -- the mask-only form of
+ * esn_head_convt2x2.  x: bf16 NHWC, 16 channels, w % 16 == 0, 8-byte aligned pixels; mask: uint8 (N, 2h, 2w).
+ * wfrag: uint32 [2][4][3][32][2] = the weights as bf16 B fragments of mma.m16n8k16, hi part ([0]) and lo part ([1]) of the fp32
+ * value (w = hi + lo), per output position a * 2 + b, per 8-class tile nt, per lane (g = lane / 4, t = lane % 4):
+ * register r holds (low half, high half) = W[4t + 2r, nt * 8 + g, a, b], W[4t + 2r + 1, nt * 8 + g, a, b] (zero for padded
+ * classes) -- the K slots of the MMA carry the channels in the order that lets a lane load its four channels in one piece.
+ * Ties resolve to the lower class, as numpy's argmax does. */
+int esn_head_convt2x2_mask(const EsnHeadT3* p, void* stream);
+
 /* Weighted cross-entropy over NCHW logits (utils/losses/loss.py:15-32):
  *   sums[0] += sum_i w[y_i]*nll_i,  sums[1] += sum_i w[y_i]   (fp32 atomics per CTA)
  * and, if dlogits != NULL, the gradient w[y_i]*(softmax - onehot) * (*gout) / (*gnorm); gnorm is the
@@ -517,7 +527,8 @@ int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnTensor* b, c
  * scalars (fp32); *step is the number of updates done so far: the launch uses step + 1 for the bias corrections and stores it
  * back (the last CTA to finish does, through the zero-initialised DEVICE counter done, which it re-arms).  For every element:
  *   g += weight_decay * p;  m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2;
- *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps). */
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * in fp32, with 1 - beta and the bias corrections formed in double (as torch's Python scalars are). */
 typedef struct EsnAdamTensor {
   float* p;
   const float* g;
@@ -527,7 +538,7 @@ typedef struct EsnAdamTensor {
 } EsnAdamTensor;
 int32_t esn_adam_chunk(void);
 int esn_adam_step(const EsnAdamTensor* table, const int32_t* blocks, int32_t n_blocks, const float* lr, float* step,
-                  uint32_t* done, float beta1, float beta2, float eps, float weight_decay, void* stream);
+                  uint32_t* done, double beta1, double beta2, double eps, double weight_decay, void* stream);
 
 /* Library / device queries (host-side, no stream). */
 int esn_version(void);

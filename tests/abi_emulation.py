@@ -275,6 +275,30 @@ def esn_head_convt3x3s2_mask(ref):
     return 0
 
 
+def esn_head_convt2x2_mask(ref):
+    """ConvTranspose2d(16, classes, 2, 2) + argmax from the packed hi / lo mma B fragments (include/esn.h): the weights are
+    decoded back from fragment order (channel 4t + 2r + e in register r of lane (g, t)) and summed hi + lo."""
+    p = ref._obj
+    assert p.x.dtype == L.ESN_BF16 and p.x.c == 16 and p.x.w % 16 == 0 and p.classes <= 24 and p.x.c_stride % 4 == 0
+    x = tensor(p.x).float()
+    frag = _buf(p.wfrag, 2 * 4 * 3 * 32 * 2 * 2, torch.bfloat16, 2).view(2, 4, 3, 32, 2, 2).float()
+    w = torch.zeros(16, 24, 2, 2)
+    for hl in range(2):
+        for pos in range(4):
+            for nt in range(3):
+                for lane in range(32):
+                    g, t = lane // 4, lane % 4
+                    for r in range(2):
+                        for e in range(2):
+                            w[4 * t + 2 * r + e, nt * 8 + g, pos // 2, pos % 2] += frag[hl, pos, nt, lane, r, e]
+    assert (w[:, p.classes:] == 0).all(), "padded classes must carry zero weights"
+    logits = F.conv_transpose2d(x, w[:, :p.classes], vec(p.bias, p.classes), 2)
+    n, _, h, ww = logits.shape
+    torch.frombuffer((C.c_char * (n * h * ww)).from_address(p.mask), dtype=torch.uint8).view(n, h, ww).copy_(
+        logits.argmax(1).to(torch.uint8))
+    return 0
+
+
 def esn_bottleneck4(ref):
     """ENet's 16-channel RegularBottleneck: y = act(x + act(BN3(W3 . act(BN2(W2 * act(BN1(W1 . x)))))))."""
     p = ref._obj
@@ -441,7 +465,7 @@ ENTRY = {
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
     "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast, "esn_weighted_ce": esn_weighted_ce,
     "esn_ohem_threshold": esn_ohem_threshold, "esn_augment_u8": esn_augment_u8,
-    "esn_head_convt3x3s2_mask": esn_head_convt3x3s2_mask, "esn_bottleneck4": esn_bottleneck4,
+    "esn_head_convt3x3s2_mask": esn_head_convt3x3s2_mask, "esn_head_convt2x2_mask": esn_head_convt2x2_mask, "esn_bottleneck4": esn_bottleneck4,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 

@@ -72,8 +72,26 @@ def test_erfnet_routing_is_the_benchmarked_one(spec):
     assert names.count("esn_conv_pair_umma") == 18
     assert names.count("esn_conv2d_umma") == 36
     assert names.count("esn_conv2d_direct") == 0
-    assert names.count("esn_stem_conv3x3s2") == 1 and names.count("esn_head_convt2x2") == 1
+    assert names.count("esn_stem_conv3x3s2") == 1 and names.count("esn_head_convt2x2_mask") == 1
     assert names.count("esn_maxpool2x2_affine_act") == 2 and len(names) == 58
+
+
+@pytest.mark.parametrize("name", ["ERFNet", "ESNet"])
+def test_tensor_core_mask_head_equals_the_logits_head(name, spec):
+    """predict_mask (esn_head_convt2x2_mask: hi / lo bf16 weight fragments in mma order) against the argmax of the logits of
+    esn_head_convt2x2 on the same features: the host packing of the fragments, decoded by the ABI model, must reproduce the
+    weights (masks equal wherever the top-2 margin exceeds the 2^-17 of the hi + lo split)."""
+    m = _model(name, spec)
+    x = fixture.make_input(1, 64, 128)
+    with emulate_abi(bf16=True) as calls, torch.no_grad():
+        mask = m.predict_mask(x)
+        assert [n for n, _ in calls].count("esn_head_convt2x2_mask") == 1
+        logits, mask2 = m.predict_mask(x, with_logits=True)
+    assert mask.dtype == torch.uint8 and mask.shape == mask2.shape
+    top2 = logits.float().topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-2 * logits.float().abs().amax(dim=1).clamp_min(1.0)      # logits are bf16-rounded
+    assert clear.float().mean().item() > 0.9
+    assert torch.equal(mask[clear], mask2[clear])
 
 
 def test_input_pipeline_through_the_abi(golden):

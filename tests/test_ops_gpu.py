@@ -375,6 +375,36 @@ def test_depthwise_strip_matches_torch(ops, case, dtype):
     assert (y.float() - y_old.float()).abs().max() / ref.abs().max() < tol
 
 
+@pytest.mark.parametrize("classes,bias,shape", [(19, True, (2, 24, 48)), (5, False, (1, 7, 16)), (24, True, (3, 9, 32)),
+                                                (19, True, (2, 64, 4096))])
+def test_convt2x2_argmax_head_on_tensor_cores(classes, bias, shape):
+    """ERFNet's / ESNet's head in one launch (esn_head_convt2x2_mask: transposed conv 2x2 / s2 + argmax on mma.sync, fp32
+    weights as hi + lo bf16 fragments) against torch's conv_transpose2d with the FP32 weights on the same bf16 activations,
+    and against the CUDA-core head kernel it replaces."""
+    import torch.nn.functional as F
+    from esn import ops
+    torch.manual_seed(12)
+    n, h, w = shape
+    x = ops.new_act(n, 16, h, w, torch.bfloat16, "cuda").normal_()
+    wt = (torch.randn(16, classes, 2, 2, device="cuda") * 0.3)
+    b = torch.randn(classes, device="cuda") if bias else None
+    frags = ops.pack_convt2x2_frags(wt, classes)
+    mask = ops.head_convt2x2_mask(x, frags, b, classes)
+    assert mask is not None and mask.shape == (n, 2 * h, 2 * w) and mask.dtype == torch.uint8
+    ref = F.conv_transpose2d(x.double(), wt.double(), None if b is None else b.double(), stride=2)
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref.abs().amax(dim=1).clamp_min(1.0)
+    want = ref.argmax(1)
+    assert clear.float().mean().item() > 0.99
+    assert torch.equal(mask.long()[clear], want[clear])
+    assert (mask.long() == want).float().mean().item() > 0.9995
+    packed = torch.zeros((2, 2, 16, 32), dtype=torch.float32, device="cuda")
+    packed[:, :, :, :classes] = wt.permute(2, 3, 0, 1)
+    bb = b if b is not None else torch.zeros(classes, device="cuda")
+    _, old = ops.head_convt2x2(x, packed.contiguous(), bb, classes, False, True, torch.bfloat16)
+    assert torch.equal(mask[clear], old[clear])
+
+
 @pytest.mark.parametrize("classes,bias,shape", [(19, False, (2, 24, 48)), (5, True, (1, 7, 16)), (24, True, (3, 9, 32))])
 def test_convt3x3s2_argmax_head_on_tensor_cores(classes, bias, shape):
     """ENet's head in one launch (esn_head_convt3x3s2_mask: transposed conv 3x3 / s2 + argmax, scores in registers) against
