@@ -164,6 +164,14 @@ class Adam(torch.optim.Optimizer):
             gs["keep"] = grads               # gradients made contiguous for this launch stay alive until the next one
         return loss
 
+    def state_dict(self):
+        """torch.optim.Adam's layout.  The group's device step counter is ONE tensor here; every parameter entry gets its own
+        copy (torch's foreach implementation increments each entry of the list it is handed)."""
+        sd = super().state_dict()
+        sd["state"] = {k: {**st, "step": st["step"].clone()} if isinstance(st.get("step"), torch.Tensor) else dict(st)
+                       for k, st in sd["state"].items()}
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._g.clear()                     # loaded moments are copied into fresh flat buffers at the next step
