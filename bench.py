@@ -489,7 +489,12 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
     config = {"workload": wl_name, "net": model_name, "classes": 19, "batch_per_gpu": batch,
               "input": "3x%dx%d fp32 NCHW" % (H, W),
               "mode": "training step: forward + weighted CE + backward + Adam" if train else "inference",
-              "head": "bilinear -> fp32 logits -> fused weighted-CE kernel" if train else "argmax fused (uint8 mask)",
+              "head": ("head + loss: the model's fused close where it has one (DABNet: esn_bilinear_ce = bilinear up-sampling + "
+                       "weighted CE + both gradients in one launch), else head kernel -> fp32 logits -> weighted-CE kernel"
+                       if not args.no_fused_loss else "bilinear -> fp32 logits -> fused weighted-CE kernel")
+              if train else "argmax fused (uint8 mask)",
+              "optimizer": ("torch.optim.Adam(fused=True)" if args.torch_adam else "esn.optim.Adam (one esn_adam_step launch)")
+              if train else None,
               "sharding": ("data parallel: flat fp32 gradient buckets all-reduced (NCCL) from inside the backward tape, "
                            "2-scalar loss all-reduce, per-GPU BatchNorm") if train else "images across ranks, no collective",
               "l2": "no flush: per-step working set (input %.0f MB + activations) >> 126 MB L2" % (batch * 3 * H * W * 4 / 1e6)}
@@ -541,7 +546,7 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
     if train and not args.no_graph:
         # the whole iteration (forward, loss, backward, gradient all-reduce, Adam) as one CUDA graph (esn/graph.py)
         from esn.graph import GraphedTrainStep
-        gstep = GraphedTrainStep(m, crit, opt, x, y, warmup=1)
+        gstep = GraphedTrainStep(m, crit, opt, x, y, warmup=1, fuse_loss=not args.no_fused_loss)
         graph = gstep.graph
         mask = gstep.loss
     elif not args.no_graph:
@@ -819,6 +824,8 @@ def main():
                     help="inference e2e leg: what crosses PCIe -- decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / "
                          "CHW done on the device (esn_image_u8hwc_to_f32nchw, SURVEY 8f-4; default), or the reference's "
                          "pre-processed fp32 NCHW batch")
+    ap.add_argument("--no-fused-loss", action="store_true",
+                    help="training workloads: criterion(model(x), y) as two modules instead of the model's fused head + loss (A/B)")
     ap.add_argument("--torch-adam", action="store_true",
                     help="training workloads: step torch.optim.Adam(fused=True) instead of esn.optim.Adam (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")

@@ -1,0 +1,237 @@
+// Close of a training iteration for the nets whose head is a bilinear up-sampling of low-resolution class scores
+// (DABNet.py:181, FastSCNN.py:233, ContextNet, CGNet, EDANet: F.interpolate(scores, input.size()[2:], mode='bilinear',
+// align_corners=False)) followed by CrossEntropyLoss2d (utils/losses/loss.py:15-32, called at train.py:351-353):
+//
+//     logits = interpolate(scores);  loss = sum_p w[t_p] (lse(logits_p) - logits_p[t_p]) / sum_p w[t_p]
+//     d scores = interpolate^T ( w[t_p] (softmax(logits_p) - onehot(t_p)) )                    (times 1 / sum w, applied later)
+//
+// in ONE pass that never writes a full-resolution tensor.  The separate kernels write the fp32 logits (319 MB at
+// 8 x 19 x 512 x 1024), read them twice for the loss and its gradient, write the gradient and read it back for the transposed
+// interpolation: 1.6 GB of traffic and 0.55 ms of a 7.4 ms DABNet step for 2.5 MB of scores and 33 MB of labels.
+//
+// Geometry (integer scale s = H / h = W / w, s even): output rows s k + s/2 ... s k + 3 s/2 - 1 form "cell" k (k = -1 ... h-1,
+// clipped to the image); every pixel of a cell blends source rows k and k + 1 (clamped), likewise for columns.  A CTA OWNS a
+// kCR x kCC block of source pixels, walks the (kCR + 1) x (kCC + 1) cells that touch them (the border cells are recomputed by
+// the neighbouring CTA: arithmetic is cheap here) and keeps only the gradient contributions to its own source pixels, in
+// shared memory -- so the score gradient is written with plain stores: no global atomics, no zero fill.  A
+// pixel's loss is counted by the CTA that owns the cell's upper-left source pixel.
+//
+// Inside a warp: lane = (cell q of four adjacent cells, row r of the cell); a thread blends its row's two source vectors
+// once (A, B), walks the s pixels of its cell row (logit_c = A_c + lx (B_c - A_c), soft-max, w (p - onehot)), sums the
+// gradient against (1 - lx) and lx in registers, and the eight rows of a cell are combined with three shuffle rounds per
+// value before lane r = 0 adds them into the CTA's tile.
+#include "esn_common.cuh"
+
+namespace {
+
+constexpr int kCR = 4, kCC = 16;          // source pixels owned by a CTA
+constexpr int kThreads = 256;
+
+struct BceArgs {
+  const void* scores;
+  const long long* target;
+  const float* weight;
+  float* sums;
+  float* dscores;
+  int N, h, w, C, cs, dcs, H, W, s, ignore;
+};
+
+template <typename TS, int CP>
+__global__ void __launch_bounds__(kThreads, 1) bilinear_ce_kernel(const BceArgs a) {
+  __shared__ float S[(kCR + 2) * (kCC + 2) * CP];      // source scores: tile row tr = source row clamp(k0 - 1 + tr)
+  __shared__ float dS[kCR * kCC * CP];                 // gradient of the owned source pixels
+  __shared__ float red[2][kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = lane & 7, q = lane >> 3;
+  const int bw = (a.w + kCC - 1) / kCC, bh = (a.h + kCR - 1) / kCR;
+  int b = blockIdx.x;
+  const int bl = b % bw;
+  b /= bw;
+  const int bk = b % bh, n = b / bh;
+  const int k0 = bk * kCR, l0 = bl * kCC;
+  const int kr = min(kCR, a.h - k0), lc = min(kCC, a.w - l0);       // owned extent
+  const TS* sc = reinterpret_cast<const TS*>(a.scores);
+  for (int i = tid; i < (kCR + 2) * (kCC + 2) * CP; i += kThreads) {
+    const int c = i % CP, p = i / CP;
+    const int tc = p % (kCC + 2), tr = p / (kCC + 2);
+    const int sr = min(max(k0 - 1 + tr, 0), a.h - 1), scol = min(max(l0 - 1 + tc, 0), a.w - 1);
+    S[i] = c < a.C ? ld1<TS>(sc + ((size_t)(n * a.h + sr) * a.w + scol) * a.cs + c) : -1e30f;   // padded classes: exp() == 0
+  }
+  for (int i = tid; i < kCR * kCC * CP; i += kThreads) dS[i] = 0.f;
+  __syncthreads();
+
+  const float inv_s = 1.f / (float)a.s;
+  const int half = a.s >> 1;
+  const int groups = (lc + 1 + 3) >> 2;                 // cell columns lci = 0 .. lc in groups of four
+  float loss_acc = 0.f, w_acc = 0.f;
+  for (int it = warp; it < (kr + 1) * groups; it += kThreads / 32) {
+    const int kc = it / groups, lci = (it - kc * groups) * 4 + q;   // cell (k0 - 1 + kc, l0 - 1 + lci)
+    const bool cell_ok = lci <= lc;
+    const int k = k0 - 1 + kc, l = l0 - 1 + lci;
+    const bool own_cell = cell_ok && (kc >= 1 || k0 == 0) && (lci >= 1 || l0 == 0);
+    // tile rows kc, kc + 1 / columns lci, lci + 1 hold the (clamped) source pixels of this cell; which of them are ours
+    const int rsA = min(max(k, 0), a.h - 1), rsB = min(max(k + 1, 0), a.h - 1);
+    const int csA = min(max(l, 0), a.w - 1), csB = min(max(l + 1, 0), a.w - 1);
+    const bool orA = rsA >= k0 && rsA < k0 + kr, orB = rsB >= k0 && rsB < k0 + kr;
+    const bool ocA = csA >= l0 && csA < l0 + lc, ocB = csB >= l0 && csB < l0 + lc;
+    float* dAA = dS + ((rsA - k0) * kCC + (csA - l0)) * CP;
+    float* dAB = dS + ((rsA - k0) * kCC + (csB - l0)) * CP;
+    float* dBA = dS + ((rsB - k0) * kCC + (csA - l0)) * CP;
+    float* dBB = dS + ((rsB - k0) * kCC + (csB - l0)) * CP;
+    const float* sAA = S + (kc * (kCC + 2) + min(lci, kCC)) * CP;
+    const float* sAB = sAA + CP;
+    const float* sBA = sAA + (kCC + 2) * CP;
+    const float* sBB = sBA + CP;
+    for (int yy0 = 0; yy0 < a.s; yy0 += 8) {
+      const int yy = yy0 + r;
+      const int y = a.s * k + half + yy;
+      const bool row_ok = cell_ok && yy < a.s && y >= 0 && y < a.H;
+      float GA[CP], GB[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) GA[c] = GB[c] = 0.f;
+      float ly = 0.f;
+      if (row_ok) {
+        const float srcy = fmaxf(((float)y + 0.5f) * inv_s - 0.5f, 0.f);
+        ly = srcy - floorf(srcy);
+        float A[CP], D[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+          const float va = sAA[c] + ly * (sBA[c] - sAA[c]);
+          const float vb = sAB[c] + ly * (sBB[c] - sAB[c]);
+          A[c] = va;
+          D[c] = vb - va;
+        }
+        const long long* trow = a.target + ((size_t)n * a.H + y) * a.W;
+        const int x0 = a.s * l + half;
+        for (int j = 0; j < a.s; ++j) {
+          const int x = x0 + j;
+          if (x < 0 || x >= a.W) continue;
+          const long long t = __ldg(trow + x);
+          if (t == a.ignore || t < 0 || t >= a.C) continue;
+          const float wy = a.weight ? __ldg(a.weight + t) : 1.f;
+          const float srcx = fmaxf(((float)x + 0.5f) * inv_s - 0.5f, 0.f);
+          const float lx = srcx - floorf(srcx);
+          float v[CP];
+          float m = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            v[c] = fmaf(lx, D[c], A[c]);
+            m = fmaxf(m, v[c]);
+          }
+          float z = 0.f;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            v[c] = __expf(v[c] - m);
+            z += v[c];
+          }
+          // the labelled class's logit, from the tile (a dynamic index into v[] would spill it)
+          const int ti = (int)t;
+          const float ta = sAA[ti] + ly * (sBA[ti] - sAA[ti]), tb = sAB[ti] + ly * (sBB[ti] - sAB[ti]);
+          const float xt = fmaf(lx, tb - ta, ta);
+          if (own_cell) {
+            loss_acc += wy * (m + logf(z) - xt);
+            w_acc += wy;
+          }
+          const float inv = wy / z;
+          const float wa = 1.f - lx;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            const float g = fmaf(v[c], inv, c == ti ? -wy : 0.f);
+            GA[c] = fmaf(wa, g, GA[c]);
+            GB[c] = fmaf(lx, g, GB[c]);
+          }
+        }
+      }
+      // combine the eight rows of every cell (all lanes take part; idle lanes carry zeros) and add into the owned tile
+      const float wyA = 1.f - ly;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        float v0 = wyA * GA[c], v1 = wyA * GB[c], v2 = ly * GA[c], v3 = ly * GB[c];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+          v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+        }
+        if (r == 0 && cell_ok) {
+          if (orA && ocA) atomicAdd(dAA + c, v0);
+          if (orA && ocB) atomicAdd(dAB + c, v1);
+          if (orB && ocA) atomicAdd(dBA + c, v2);
+          if (orB && ocB) atomicAdd(dBB + c, v3);
+        }
+      }
+    }
+  }
+  // loss sums: warp shuffle -> shared -> one atomic pair per CTA
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+    w_acc += __shfl_xor_sync(0xffffffffu, w_acc, o);
+  }
+  if (lane == 0) {
+    red[0][warp] = loss_acc;
+    red[1][warp] = w_acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    loss_acc = lane < kThreads / 32 ? red[0][lane] : 0.f;
+    w_acc = lane < kThreads / 32 ? red[1][lane] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+      w_acc += __shfl_xor_sync(0xffffffffu, w_acc, o);
+    }
+    if (lane == 0) {
+      atomicAdd(a.sums, loss_acc);
+      atomicAdd(a.sums + 1, w_acc);
+    }
+  }
+  // the owned gradients, every lane of the padded pixel (zeros behind the classes)
+  for (int i = tid; i < kr * lc * a.dcs; i += kThreads) {
+    const int c = i % a.dcs, p = i / a.dcs;
+    const int tc = p % lc, tr = p / lc;
+    a.dscores[((size_t)(n * a.h + k0 + tr) * a.w + l0 + tc) * a.dcs + c] = c < CP ? dS[(tr * kCC + tc) * CP + c] : 0.f;
+  }
+}
+
+template <typename TS>
+void launch_bce(const BceArgs& a, int grid, cudaStream_t st) {
+  if (a.C <= 12)
+    bilinear_ce_kernel<TS, 12><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C <= 20)
+    bilinear_ce_kernel<TS, 20><<<grid, kThreads, 0, st>>>(a);
+  else
+    bilinear_ce_kernel<TS, 32><<<grid, kThreads, 0, st>>>(a);
+}
+
+}  // namespace
+
+extern "C" int esn_bilinear_ce(const EsnBilinearCE* p, void* stream) {
+  if (!p || !p->target || !p->sums || !esn_valid_nhwc(p->scores) || !esn_valid_nhwc(p->dscores)) return ESN_ERR_BAD_ARG;
+  const EsnTensor& x = p->scores;
+  const EsnTensor& g = p->dscores;
+  if (x.dtype != ESN_F32 && x.dtype != ESN_BF16) return ESN_ERR_BAD_ARG;
+  if (g.dtype != ESN_F32) return ESN_ERR_BAD_ARG;
+  if (g.n != x.n || g.h != x.h || g.w != x.w || g.c != x.c) return ESN_ERR_BAD_SHAPE;
+  if (x.c < 1 || x.c > 32) return ESN_ERR_UNSUPPORTED;
+  if (p->out_h < 1 || p->out_w < 1 || p->out_h % x.h || p->out_w % x.w) return ESN_ERR_UNSUPPORTED;
+  const int s = p->out_h / x.h;
+  if (s != p->out_w / x.w || s < 2 || (s & 1) || s > 64) return ESN_ERR_UNSUPPORTED;      // integer, even, isotropic scale
+  BceArgs a;
+  a.scores = x.ptr;
+  a.target = reinterpret_cast<const long long*>(p->target);
+  a.weight = p->weight;
+  a.sums = p->sums;
+  a.dscores = reinterpret_cast<float*>(g.ptr);
+  a.N = x.n; a.h = x.h; a.w = x.w; a.C = x.c; a.cs = x.c_stride; a.dcs = g.c_stride;
+  a.H = p->out_h; a.W = p->out_w; a.s = s; a.ignore = p->ignore_label;
+  const long long grid = (long long)x.n * ((x.h + kCR - 1) / kCR) * ((x.w + kCC - 1) / kCC);
+  if (grid > 0x7fffffffLL) return ESN_ERR_UNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x.dtype == ESN_F32)
+    launch_bce<float>(a, (int)grid, st);
+  else
+    launch_bce<__nv_bfloat16>(a, (int)grid, st);
+  ESN_CHECK_LAUNCH();
+  return ESN_OK;
+}

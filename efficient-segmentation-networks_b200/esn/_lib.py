@@ -120,6 +120,12 @@ class EsnCE(C.Structure):
                 ("gnorm", C.c_void_p), ("gout", C.c_void_p), ("prob_out", C.c_void_p), ("keep_thresh", C.c_void_p)]
 
 
+class EsnBilinearCE(C.Structure):
+    _fields_ = [("scores", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
+                ("dscores", EsnTensor), ("out_h", C.c_int32), ("out_w", C.c_int32), ("ignore_label", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
 # every symbol include/esn.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "esn_conv2d_direct": (C.c_int, [C.POINTER(EsnConv), C.c_void_p]),
@@ -178,6 +184,7 @@ SYMBOLS = {
     "esn_scale_nc": (C.c_int, [C.POINTER(EsnTensor), C.c_void_p, C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_adaptive_avgpool": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_void_p]),
     "esn_bilinear_nhwc": (C.c_int, [C.POINTER(EsnTensor), C.POINTER(EsnTensor), C.c_int32, C.c_void_p]),
+    "esn_bilinear_ce": (C.c_int, [C.POINTER(EsnBilinearCE), C.c_void_p]),
     "esn_adam_chunk": (C.c_int32, []),
     "esn_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_void_p]),

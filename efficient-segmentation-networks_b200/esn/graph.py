@@ -22,11 +22,12 @@ from .prep import bump_weights_generation
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, images, labels, autocast_dtype=torch.bfloat16, warmup=3):
+    def __init__(self, model, criterion, optimizer, images, labels, autocast_dtype=torch.bfloat16, warmup=3, fuse_loss=True):
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (there is no CPU path)")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.autocast_dtype = autocast_dtype
+        self.fuse_loss = fuse_loss
         self.images = images.clone()
         self.labels = labels.clone()
         self.graph = None
@@ -45,13 +46,21 @@ class GraphedTrainStep:
         self.loss = loss
         self.launches = None
 
+    def _loss(self):
+        # a model may offer its head and the criterion as one fused launch (DABNet.fused_loss -> esn_bilinear_ce); it falls
+        # back to criterion(model(images), labels) itself for criteria / shapes it has no fused form for
+        fused = getattr(self.model, "fused_loss", None) if self.fuse_loss else None
+        if fused is not None:
+            return fused(self.images, self.labels, self.criterion)
+        return self.criterion(self.model(self.images), self.labels)
+
     def _iteration(self):
         self.optimizer.zero_grad(set_to_none=True)
         if self.autocast_dtype is not None:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
-                loss = self.criterion(self.model(self.images), self.labels)
+                loss = self._loss()
         else:
-            loss = self.criterion(self.model(self.images), self.labels)
+            loss = self._loss()
         loss.backward()
         self.optimizer.step()
         ops.advance_step_counter()

@@ -652,6 +652,30 @@ def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32, alig
     return logits, holder
 
 
+def bilinear_ce(tape, scores, out_h, out_w, target, weight, ignore_label):
+    """bilinear_logits + CrossEntropyLoss2d + both backward passes as one launch (ops.bilinear_ce): returns (sums, holder) with
+    sums = [sum w*nll, sum w] of this rank, or None when the geometry is not taken.  The tape step scales the stored gradient
+    by holder["gscale"] (a device scalar: upstream gradient / normaliser, set by _NetLossFn.backward) while converting it to
+    the scores' dtype."""
+    res = ops.bilinear_ce(scores.t, target, weight, ignore_label, out_h, out_w, sums=_f32zeros(2, scores.t.device))
+    if res is None:
+        return None
+    sums, ds = res
+    holder = {}
+
+    def bwd():
+        n, c, h, w = scores.t.shape
+        scale = holder["gscale"].reshape(1).expand(c).contiguous()
+
+        def run(ex, dst):
+            assert ex is None or ex is dst          # the loss is the only consumer of the scores
+            dlow = dst if dst is not None else ops.new_act(n, c, h, w, scores.t.dtype, ds.device, c_alloc=scores.t.stride(3))
+            return ops.affine_act(ds, scale, None, None, L.ACT_NONE, out=dlow)
+        scores.add_grad(run)
+    tape.push(bwd)
+    return sums, holder
+
+
 def _accumulating(fn_into):
     """add_grad adapter for kernels with an `accumulate` flag: fn_into(dx, accumulate) fills / adds into dx."""
     def run(ex, dst, alloc):
@@ -894,6 +918,40 @@ class _NetFn(torch.autograd.Function):
         ctx.tape.param_grads = {}
         del grads
         return (None, None) + out
+
+
+class _NetLossFn(torch.autograd.Function):
+    """The whole network AND its loss as one autograd node (the fused close of ops.bilinear_ce): forward returns the
+    weighted-mean (or summed) cross-entropy, backward hands d loss / d scores to the tape.  Same global-batch normalisation
+    as _CEFn when `distributed`."""
+
+    @staticmethod
+    def forward(ctx, run_forward, x, reduction, distributed, *params):
+        sums, tape, holder = run_forward(x)
+        tape.flush_counters()
+        if (distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(sums)
+        ctx.tape, ctx.holder, ctx.params, ctx.reduction = tape, holder, params, reduction
+        ctx.save_for_backward(sums)
+        return sums[0] / sums[1] if reduction == "mean" else sums[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        (sums,) = ctx.saved_tensors
+        g = gout.detach().float().reshape(())
+        ctx.holder["gscale"] = g / sums[1] if ctx.reduction == "mean" else g
+        grads = ctx.tape.backward()
+        out = tuple(grads.get(p) for p in ctx.params)
+        ctx.tape.param_grads = {}
+        del grads
+        return (None, None, None, None) + out
+
+
+def run_network_loss(model, run_forward, x, reduction="mean", distributed=False):
+    """run_forward(x) -> (sums, tape, holder) with the loss sums of T.bilinear_ce; returns the loss (a scalar with grad_fn)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    return _NetLossFn.apply(run_forward, x, reduction, distributed, *params)
 
 
 def run_network(model, run_forward, x):

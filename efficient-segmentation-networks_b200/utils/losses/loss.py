@@ -28,6 +28,27 @@ def _fused_ce(output, target, w, ignore_label, distributed, reduction, keep_thre
     return T.cross_entropy(output, target, w, ignore_label, distributed, reduction, keep_thresh)
 
 
+def fused_head_spec(criterion, output_device, target, classes):
+    """What a model's fused head + loss (e.g. DABNet.fused_loss -> esn_bilinear_ce) needs from a CrossEntropyLoss2d:
+    (int64 target, class weights on the device or None, ignore label, reduction, distributed) -- the same label check and the
+    same resolution of `distributed=None` as the module's own forward.  None for any other criterion (no fused form)."""
+    if type(criterion) is not CrossEntropyLoss2d:
+        return None
+    w = criterion.weight
+    if w is not None and w.device != output_device:
+        w = w.to(output_device)
+    target = target.long()
+    if os.environ.get("ESN_CHECK_LABELS") == "1":
+        bad = (target != criterion.ignore_label) & ((target < 0) | (target >= classes))
+        if bool(bad.any()):
+            raise IndexError("Target %d is out of bounds." % int(target[bad][0]))
+    distributed = criterion.distributed
+    if distributed is None:
+        from esn import parallel
+        distributed = parallel.is_active()
+    return target, w, criterion.ignore_label, criterion.reduction, distributed
+
+
 class CrossEntropyLoss2d(nn.Module):
     """Same constructor as the reference (weight, ignore_label, reduction) and the same `state_dict` key
     (`nll_loss.weight`: the reference keeps an nn.CrossEntropyLoss child named nll_loss, loss.py:23; here that child only

@@ -519,6 +519,29 @@ int esn_augment_u8(const EsnAugItem* items, int32_t n, int32_t crop_h, int32_t c
  * scores (LEDNet keeps its single-channel pyramid in fp32). */
 int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnTensor* b, const EsnTensor* y, void* stream);
 
+/* Bilinear up-sampling of low-resolution class scores + weighted cross-entropy + the gradient of the scores, in one pass that
+ * never writes a full-resolution tensor: the close of a training iteration of the nets whose head is
+ * F.interpolate(scores, input.size()[2:], mode='bilinear', align_corners=False) (DABNet.py:181, FastSCNN.py:233, CGNet,
+ * ContextNet, EDANet) under CrossEntropyLoss2d (utils/losses/loss.py:15-32; train.py:351-353).  Replaces esn_head_bilinear ->
+ * esn_weighted_ce (forward, backward) -> esn_bilinear_bwd.
+ *   scores: NHWC (n, h, w, c <= 32), f32 or bf16;  target: int64 (n, out_h, out_w);  weight: [c] f32 or NULL;
+ *   out_h = s h, out_w = s w with one even integer s (2 .. 64): anything else answers ESN_ERR_UNSUPPORTED.
+ *   sums[0] += sum_p w[t_p] (lse(logits_p) - logits_p[t_p]),  sums[1] += sum_p w[t_p]   over pixels with t_p in [0, c) and
+ *   t_p != ignore_label (fp32 atomics; zeroed by the caller);
+ *   dscores: f32 NHWC (n, h, w, c), every lane of its pixel stride written (zeros behind the classes):
+ *   d sums[0] / d scores -- the caller scales it by (upstream gradient) / sums[1] for the mean reduction. */
+typedef struct EsnBilinearCE {
+  EsnTensor scores;
+  const int64_t* target;
+  const float* weight;
+  float* sums;
+  EsnTensor dscores;
+  int32_t out_h, out_w;
+  int32_t ignore_label;
+  int32_t _pad;
+} EsnBilinearCE;
+int esn_bilinear_ce(const EsnBilinearCE* p, void* stream);
+
 /* Optimizer step of the training iteration (train.py:355 `optimizer.step()` on the torch.optim.Adam of train.py:212-215):
  * Adam with L2 weight decay (torch.optim.Adam semantics, amsgrad = False, maximize = False) over every parameter tensor of a
  * param group in ONE launch.  table: DEVICE array of fp32 tensors (parameter, gradient, exp_avg, exp_avg_sq: n elements each,

@@ -299,6 +299,29 @@ def esn_head_convt2x2_mask(ref):
     return 0
 
 
+def esn_bilinear_ce(ref):
+    """Bilinear up-sampling + weighted CE sums + d sums[0] / d scores (include/esn.h), by torch autograd in fp32."""
+    p = ref._obj
+    x = tensor(p.scores).float().contiguous().requires_grad_(True)
+    n, c, h, w = x.shape
+    H, W = p.out_h, p.out_w
+    assert H % h == 0 and W % w == 0 and H // h == W // w and (H // h) % 2 == 0
+    tgt = _buf(p.target, n * H * W, torch.int64, 8).view(n, H, W).clone()
+    tgt[(tgt < 0) | (tgt >= c)] = p.ignore_label
+    wt = vec(p.weight, c)
+    with torch.enable_grad():
+        logits = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=False)
+        loss = F.cross_entropy(logits, tgt, wt, ignore_index=p.ignore_label, reduction="sum")
+        (g,) = torch.autograd.grad(loss, x)
+    valid = tgt != p.ignore_label
+    sums = _buf(p.sums, 2, torch.float32, 4)
+    sums[0] += loss.detach()
+    sums[1] += (wt[tgt[valid]].sum() if wt is not None else valid.float().sum())
+    _buf(p.dscores.ptr, n * h * w * p.dscores.c_stride, torch.float32, 4).zero_()      # every lane of the pixel stride is written
+    tensor(p.dscores).copy_(g)
+    return 0
+
+
 def esn_bottleneck4(ref):
     """ENet's 16-channel RegularBottleneck: y = act(x + act(BN3(W3 . act(BN2(W2 * act(BN1(W1 . x)))))))."""
     p = ref._obj
@@ -465,7 +488,7 @@ ENTRY = {
     "esn_maxpool3x3s2_idx": esn_maxpool3x3s2_idx, "esn_max_unpool2x2": esn_max_unpool2x2, "esn_dab_dw_pair": esn_dab_dw_pair,
     "esn_image_u8hwc_to_f32nchw": esn_image_u8hwc_to_f32nchw, "esn_gate_bcast": esn_gate_bcast, "esn_weighted_ce": esn_weighted_ce,
     "esn_ohem_threshold": esn_ohem_threshold, "esn_augment_u8": esn_augment_u8,
-    "esn_head_convt3x3s2_mask": esn_head_convt3x3s2_mask, "esn_head_convt2x2_mask": esn_head_convt2x2_mask, "esn_bottleneck4": esn_bottleneck4,
+    "esn_head_convt3x3s2_mask": esn_head_convt3x3s2_mask, "esn_head_convt2x2_mask": esn_head_convt2x2_mask, "esn_bilinear_ce": esn_bilinear_ce, "esn_bottleneck4": esn_bottleneck4,
 }
 CALLS = []        # (entry point, tag) of every emulated launch, for assertions about routing
 

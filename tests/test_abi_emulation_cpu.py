@@ -271,3 +271,28 @@ def test_dabnet_dual_epilogue_routing_equals_two_launches(spec, monkeypatch):
     assert "esn_conv2d_umma_dual" not in names0
     assert names0.count("esn_affine_act") == n_affine + 10
     assert torch.equal(y0, y1)
+
+
+def test_bilinear_ce_wrapper_through_the_abi():
+    """ops.bilinear_ce (the fused close of a training iteration, esn_bilinear_ce): descriptors, target / weight pointers and the
+    padded fp32 gradient buffer as the host passes them, answered by the ABI model (torch autograd)."""
+    import torch.nn.functional as F
+    from esn import ops
+    torch.manual_seed(3)
+    n, c, h, w, s = 2, 19, 4, 6, 8
+    tgt = torch.randint(0, c, (n, s * h, s * w))
+    tgt[:, :5] = 255
+    wt = torch.rand(c) + 0.5
+    with emulate_abi(bf16=False) as calls:
+        x = ops.new_act(n, c, h, w, torch.float32, "cpu", c_alloc=32)
+        x.copy_(torch.randn(n, c, h, w))
+        sums, ds = ops.bilinear_ce(x, tgt, wt, 255, s * h, s * w)
+        assert ops.bilinear_ce(x, tgt[:, :, :40], wt, 255, s * h, 40) is None        # anisotropic scale: declined on the host
+        assert [nm for nm, _ in calls] == ["esn_bilinear_ce"]
+    xr = x.detach().clone().contiguous().requires_grad_(True)
+    loss = F.cross_entropy(F.interpolate(xr, scale_factor=s, mode="bilinear", align_corners=False), tgt, wt, ignore_index=255,
+                           reduction="sum")
+    loss.backward()
+    assert abs(sums[0].item() - loss.item()) < 1e-4 * abs(loss.item())
+    assert abs(sums[1].item() - wt[tgt[tgt != 255]].sum().item()) < 1e-3
+    assert ds.shape == (n, c, h, w) and ds.stride(3) == 20 and _rel(ds, xr.grad) < 1e-5
