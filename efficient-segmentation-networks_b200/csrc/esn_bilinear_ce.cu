@@ -36,8 +36,14 @@ struct BceArgs {
   int N, h, w, C, cs, dcs, H, W, s, ignore;
 };
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <typename TS, int CP>
-__global__ void __launch_bounds__(kThreads, 1) bilinear_ce_kernel(const BceArgs a) {
+__global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel(const BceArgs a) {
   __shared__ float S[(kCR + 2) * (kCC + 2) * CP];      // source scores: tile row tr = source row clamp(k0 - 1 + tr)
   __shared__ float dS[kCR * kCC * CP];                 // gradient of the owned source pixels
   __shared__ float red[2][kThreads / 32];
@@ -61,11 +67,12 @@ __global__ void __launch_bounds__(kThreads, 1) bilinear_ce_kernel(const BceArgs 
 
   const float inv_s = 1.f / (float)a.s;
   const int half = a.s >> 1;
-  const int groups = (lc + 1 + 3) >> 2;                 // cell columns lci = 0 .. lc in groups of four
+  const int ncell = (kr + 1) * (lc + 1);                // cells (k0 - 1 + kc, l0 - 1 + lci), kc = 0 .. kr, lci = 0 .. lc
   float loss_acc = 0.f, w_acc = 0.f;
-  for (int it = warp; it < (kr + 1) * groups; it += kThreads / 32) {
-    const int kc = it / groups, lci = (it - kc * groups) * 4 + q;   // cell (k0 - 1 + kc, l0 - 1 + lci)
-    const bool cell_ok = lci <= lc;
+  for (int it = warp; it * 4 < ncell; it += kThreads / 32) {
+    const int ci = it * 4 + q;                          // four consecutive cells of the flattened walk per warp
+    const bool cell_ok = ci < ncell;
+    const int kc = min(ci, ncell - 1) / (lc + 1), lci = min(ci, ncell - 1) - kc * (lc + 1);
     const int k = k0 - 1 + kc, l = l0 - 1 + lci;
     const bool own_cell = cell_ok && (kc >= 1 || k0 == 0) && (lci >= 1 || l0 == 0);
     // tile rows kc, kc + 1 / columns lci, lci + 1 hold the (clamped) source pixels of this cell; which of them are ours
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) bilinear_ce_kernel(const BceArgs 
     float* dAB = dS + ((rsA - k0) * kCC + (csB - l0)) * CP;
     float* dBA = dS + ((rsB - k0) * kCC + (csA - l0)) * CP;
     float* dBB = dS + ((rsB - k0) * kCC + (csB - l0)) * CP;
-    const float* sAA = S + (kc * (kCC + 2) + min(lci, kCC)) * CP;
+    const float* sAA = S + (kc * (kCC + 2) + lci) * CP;
     const float* sAB = sAA + CP;
     const float* sBA = sAA + (kCC + 2) * CP;
     const float* sBB = sBA + CP;
@@ -92,22 +99,29 @@ __global__ void __launch_bounds__(kThreads, 1) bilinear_ce_kernel(const BceArgs 
       if (row_ok) {
         const float srcy = fmaxf(((float)y + 0.5f) * inv_s - 0.5f, 0.f);
         ly = srcy - floorf(srcy);
+        // the row's two blended source vectors, in units of log2 (one FFMA + one EX2 per class and pixel below)
+        constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
         float A[CP], D[CP];
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
           const float va = sAA[c] + ly * (sBA[c] - sAA[c]);
           const float vb = sAB[c] + ly * (sBB[c] - sAB[c]);
-          A[c] = va;
-          D[c] = vb - va;
+          A[c] = va * kLog2e;
+          D[c] = (vb - va) * kLog2e;
         }
         const long long* trow = a.target + ((size_t)n * a.H + y) * a.W;
         const int x0 = a.s * l + half;
+        // onehot part of the gradient: labels come in runs, so it is summed per run and folded into GA / GB when the label
+        // changes (a select chain over the classes per run instead of per pixel)
+        int cur = -1;
+        float oa = 0.f, ob = 0.f;
         for (int j = 0; j < a.s; ++j) {
           const int x = x0 + j;
           if (x < 0 || x >= a.W) continue;
           const long long t = __ldg(trow + x);
           if (t == a.ignore || t < 0 || t >= a.C) continue;
-          const float wy = a.weight ? __ldg(a.weight + t) : 1.f;
+          const int ti = (int)t;
+          const float wy = a.weight ? __ldg(a.weight + ti) : 1.f;
           const float srcx = fmaxf(((float)x + 0.5f) * inv_s - 0.5f, 0.f);
           const float lx = srcx - floorf(srcx);
           float v[CP];
@@ -120,25 +134,39 @@ __global__ void __launch_bounds__(kThreads, 1) bilinear_ce_kernel(const BceArgs 
           float z = 0.f;
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            v[c] = __expf(v[c] - m);
+            v[c] = ex2_ftz(v[c] - m);
             z += v[c];
           }
-          // the labelled class's logit, from the tile (a dynamic index into v[] would spill it)
-          const int ti = (int)t;
-          const float ta = sAA[ti] + ly * (sBA[ti] - sAA[ti]), tb = sAB[ti] + ly * (sBB[ti] - sAB[ti]);
-          const float xt = fmaf(lx, tb - ta, ta);
           if (own_cell) {
-            loss_acc += wy * (m + logf(z) - xt);
+            // the labelled class's logit from the tile (a dynamic index into v[] would spill it)
+            const float ta = sAA[ti] + ly * (sBA[ti] - sAA[ti]), tb = sAB[ti] + ly * (sBB[ti] - sAB[ti]);
+            loss_acc += wy * ((m + __log2f(z)) * kLn2 - fmaf(lx, tb - ta, ta));
             w_acc += wy;
           }
-          const float inv = wy / z;
+          const float inv = __fdividef(wy, z);
           const float wa = 1.f - lx;
+          const float ia = wa * inv, ib = lx * inv;
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            const float g = fmaf(v[c], inv, c == ti ? -wy : 0.f);
-            GA[c] = fmaf(wa, g, GA[c]);
-            GB[c] = fmaf(lx, g, GB[c]);
+            GA[c] = fmaf(ia, v[c], GA[c]);
+            GB[c] = fmaf(ib, v[c], GB[c]);
           }
+          if (ti != cur) {
+            if (cur >= 0) {
+#pragma unroll
+              for (int c = 0; c < CP; ++c)
+                if (c == cur) { GA[c] -= oa; GB[c] -= ob; }
+            }
+            cur = ti;
+            oa = ob = 0.f;
+          }
+          oa = fmaf(wa, wy, oa);
+          ob = fmaf(lx, wy, ob);
+        }
+        if (cur >= 0) {
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+            if (c == cur) { GA[c] -= oa; GB[c] -= ob; }
         }
       }
       // combine the eight rows of every cell (all lanes take part; idle lanes carry zeros) and add into the owned tile

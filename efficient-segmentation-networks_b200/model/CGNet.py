@@ -322,6 +322,14 @@ class CGNet(PrepMixin, nn.Module):
             self.classifier[-1](cat2, out=scores)
         return scores, (h, w), dt
 
+    def fused_loss(self, input, target, criterion):
+        """criterion(self(input), target) (train.py:351-352) with the bilinear head (CGNet.py:332), CrossEntropyLoss2d and both
+        their backward passes as ONE launch (esn_bilinear_ce); esn.graph.GraphedTrainStep calls this.  Falls back to the
+        two-module form for other criteria, eval mode, or inputs that are not multiples of 8."""
+        from esn import train as T
+        from model._cgnet_train import cgnet_train_forward
+        return T.fused_bilinear_loss(self, cgnet_train_forward, input, target, criterion, self.classifier[-1].conv.out_channels, 8)
+
     def forward(self, input):
         if self.training:
             # batch-statistics BatchNorm and the recorded backward (esn/train.py); one autograd node for the net

@@ -336,15 +336,9 @@ class DABNet(nn.Module):
         backward passes as ONE launch (esn_bilinear_ce: the full-resolution logits and their gradient are never written).
         esn.graph.GraphedTrainStep calls this when the model offers it.  Any other criterion, eval mode, or an input size
         whose 1/8-resolution scores are not an exact 8x down-sampling takes the two-module form."""
-        from utils.losses.loss import fused_head_spec
-        spec = fused_head_spec(criterion, input.device, target, self.classifier[0].conv.out_channels) if (self.training and torch.is_grad_enabled()) else None
-        if spec is None or (input.shape[2] | input.shape[3]) % 8 or target.dim() != 3:
-            return criterion(self(input), target)
         from esn import train as T
         from model._dabnet_train import dabnet_train_forward
-        tgt, w, ignore, reduction, distributed = spec
-        return T.run_network_loss(self, lambda x: dabnet_train_forward(self, x, loss=(tgt, w, ignore)), input,
-                                  reduction, distributed)
+        return T.fused_bilinear_loss(self, dabnet_train_forward, input, target, criterion, self.classifier[0].conv.out_channels, 8)
 
     @torch.no_grad()
     def predict_mask(self, input, with_logits=False):

@@ -50,7 +50,7 @@ def _block(tape, blk, x, out=None):
     return T.fglo(tape, blk.F_glo.fc, j, out=out, residual=x if blk.add else None)
 
 
-def cgnet_train_forward(model, input):
+def cgnet_train_forward(model, input, loss=None):
     ops.require_cuda(input, "CGNet")
     if input.dtype != torch.float32 or not input.is_contiguous():
         input = input.float().contiguous()
@@ -95,5 +95,5 @@ def cgnet_train_forward(model, input):
     classes = conv.out_channels
     scores = T.V(ops.new_act(n, classes, h3, w3, dt, dev, c_alloc=32))
     _convT(conv).forward(tape, c2, out=scores)
-    logits, holder = T.bilinear_logits(tape, scores, H, W, torch.float32)
-    return logits, tape, holder
+    # fp32 logits, or the loss sums of the fused close when called from CGNet.fused_loss (esn_bilinear_ce)
+    return T.bilinear_close(tape, scores, H, W, loss)

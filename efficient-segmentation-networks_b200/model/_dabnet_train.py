@@ -132,12 +132,5 @@ def dabnet_train_forward(model, input, loss=None):
         c2 = _bnprelu(tape, model.bn_prelu_3, cat2)
         scores = T.V(ops.new_act(n, classes, hh, ww, dt, dev, c_alloc=32))
         _conv(tape, model.classifier[0], c2, out=scores)
-    if loss is not None:
-        # fused close (DABNet.fused_loss): interpolation + weighted CE + both gradients in one launch; `loss` = (target, class
-        # weights, ignore label); DABNet.fused_loss has checked the geometry
-        res = T.bilinear_ce(tape, scores, H, W, *loss)
-        if res is None:
-            raise RuntimeError("DABNet.fused_loss: esn_bilinear_ce does not take %dx%d scores for a %dx%d target" % (hh, ww, H, W))
-        return res[0], tape, res[1]
-    logits, holder = T.bilinear_logits(tape, scores, H, W, torch.float32)
-    return logits, tape, holder
+    # fp32 logits, or the loss sums of the fused close when called from DABNet.fused_loss (esn_bilinear_ce)
+    return T.bilinear_close(tape, scores, H, W, loss)

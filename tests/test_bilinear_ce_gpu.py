@@ -53,9 +53,10 @@ def test_bilinear_ce_declines_other_geometries():
         assert ops.bilinear_ce(x, torch.zeros(1, H, W, dtype=torch.int64, device="cuda"), None, 255, H, W) is None
 
 
+@pytest.mark.parametrize("net", ["DABNet", "CGNet"])
 @pytest.mark.parametrize("dt", [None, torch.bfloat16])
-def test_dabnet_fused_loss_equals_the_two_module_form(spec, dt):
-    """loss and parameter gradients of DABNet.fused_loss (one esn_bilinear_ce launch) against criterion(model(x), y)."""
+def test_fused_loss_equals_the_two_module_form(spec, dt, net):
+    """loss and parameter gradients of model.fused_loss (one esn_bilinear_ce launch) against criterion(model(x), y)."""
     import contextlib
     from builders.model_builder import build_model
     from utils.losses.loss import CrossEntropyLoss2d
@@ -66,8 +67,8 @@ def test_dabnet_fused_loss_equals_the_two_module_form(spec, dt):
     ctx = (lambda: torch.autocast("cuda", dtype=dt)) if dt is not None else contextlib.nullcontext
 
     def run(fused):
-        m = build_model("DABNet", 19)
-        m.load_state_dict(spec_state_dict(spec, "DABNet"))
+        m = build_model(net, 19)
+        m.load_state_dict(spec_state_dict(spec, net))
         m = m.cuda().train()
         ops.PROFILE = []
         try:
