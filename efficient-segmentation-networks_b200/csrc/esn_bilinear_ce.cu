@@ -17,9 +17,10 @@
 // pixel's loss is counted by the CTA that owns the cell's upper-left source pixel.
 //
 // Inside a warp: lane = (cell q of four adjacent cells, row r of the cell); a thread blends its row's two source vectors
-// once (A, B), walks the s pixels of its cell row (logit_c = A_c + lx (B_c - A_c), soft-max, w (p - onehot)), sums the
-// gradient against (1 - lx) and lx in registers, and the eight rows of a cell are combined with three shuffle rounds per
-// value before lane r = 0 adds them into the CTA's tile.
+// once (A, B), walks the s pixels of its cell row (logit_c = A_c + lx (B_c - A_c), soft-max in the log2 domain: one FFMA and
+// one ex2.approx per class), sums the soft-max part of the gradient against (1 - lx) and lx in registers -- the onehot part
+// goes straight into the CTA's tile, once per run of equal labels -- and the eight rows of a cell are combined by a
+// reduce-scatter over the four source pixels (four shuffles per class), after which four lanes per cell add into the tile.
 #include "esn_common.cuh"
 
 namespace {
@@ -88,13 +89,16 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
     const float* sAB = sAA + CP;
     const float* sBA = sAA + (kCC + 2) * CP;
     const float* sBB = sBA + CP;
+    const bool row_b = (r & 4) != 0, col_b = (r & 2) != 0;        // the source pixel this lane collects after the reduction
+    float* dmine = row_b ? (col_b ? dBB : dBA) : (col_b ? dAB : dAA);
+    const bool own_mine = cell_ok && (r & 1) == 0 && (row_b ? orB : orA) && (col_b ? ocB : ocA);
     for (int yy0 = 0; yy0 < a.s; yy0 += 8) {
       const int yy = yy0 + r;
       const int y = a.s * k + half + yy;
       const bool row_ok = cell_ok && yy < a.s && y >= 0 && y < a.H;
-      float GA[CP], GB[CP];
+      float G0[CP], G1[CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) GA[c] = GB[c] = 0.f;
+      for (int c = 0; c < CP; ++c) G0[c] = G1[c] = 0.f;
       float ly = 0.f;
       if (row_ok) {
         const float srcy = fmaxf(((float)y + 0.5f) * inv_s - 0.5f, 0.f);
@@ -111,8 +115,15 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
         }
         const long long* trow = a.target + ((size_t)n * a.H + y) * a.W;
         const int x0 = a.s * l + half;
-        // onehot part of the gradient: labels come in runs, so it is summed per run and folded into GA / GB when the label
-        // changes (a select chain over the classes per run instead of per pixel)
+        // onehot part of the gradient: summed per run of equal labels and added straight into the owned tile when the label
+        // changes (four shared-memory atomics per run; per pixel when every pixel has another label)
+        const float wyA = 1.f - ly;
+        auto flush = [&](int cls, float oa, float ob) {
+          if (orA && ocA) atomicAdd(dAA + cls, -(wyA * oa));
+          if (orA && ocB) atomicAdd(dAB + cls, -(wyA * ob));
+          if (orB && ocA) atomicAdd(dBA + cls, -(ly * oa));
+          if (orB && ocB) atomicAdd(dBB + cls, -(ly * ob));
+        };
         int cur = -1;
         float oa = 0.f, ob = 0.f;
         for (int j = 0; j < a.s; ++j) {
@@ -145,47 +156,37 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
           }
           const float inv = __fdividef(wy, z);
           const float wa = 1.f - lx;
-          const float ia = wa * inv, ib = lx * inv;
+          const float i0 = (col_b ? lx : wa) * inv, i1 = (col_b ? wa : lx) * inv;      // G0 = this lane's column, G1 = the other
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            GA[c] = fmaf(ia, v[c], GA[c]);
-            GB[c] = fmaf(ib, v[c], GB[c]);
+            G0[c] = fmaf(i0, v[c], G0[c]);
+            G1[c] = fmaf(i1, v[c], G1[c]);
           }
           if (ti != cur) {
-            if (cur >= 0) {
-#pragma unroll
-              for (int c = 0; c < CP; ++c)
-                if (c == cur) { GA[c] -= oa; GB[c] -= ob; }
-            }
+            if (cur >= 0) flush(cur, oa, ob);
             cur = ti;
             oa = ob = 0.f;
           }
           oa = fmaf(wa, wy, oa);
           ob = fmaf(lx, wy, ob);
         }
-        if (cur >= 0) {
-#pragma unroll
-          for (int c = 0; c < CP; ++c)
-            if (c == cur) { GA[c] -= oa; GB[c] -= ob; }
-        }
+        if (cur >= 0) flush(cur, oa, ob);
       }
-      // combine the eight rows of every cell (all lanes take part; idle lanes carry zeros) and add into the owned tile
-      const float wyA = 1.f - ly;
+      // combine the eight rows of a cell by reduce-scatter: a lane ends up with ONE of the four source pixels -- row B when
+      // r & 4, column B when r & 2 -- so it multiplies by the row weight it keeps (wm) and the one it hands over (wt), swaps
+      // the row halves with lane ^ 4, the column halves with lane ^ 2 and sums the last pair with lane ^ 1: four shuffles
+      // per class instead of twelve.  Idle lanes carry zeros.
+      {
+        const float wyA = 1.f - ly;
+        const float wm = row_b ? ly : wyA, wt = row_b ? wyA : ly;
 #pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        float v0 = wyA * GA[c], v1 = wyA * GB[c], v2 = ly * GA[c], v3 = ly * GB[c];
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-          v3 += __shfl_xor_sync(0xffffffffu, v3, o);
-        }
-        if (r == 0 && cell_ok) {
-          if (orA && ocA) atomicAdd(dAA + c, v0);
-          if (orA && ocB) atomicAdd(dAB + c, v1);
-          if (orB && ocA) atomicAdd(dBA + c, v2);
-          if (orB && ocB) atomicAdd(dBB + c, v3);
+        for (int c = 0; c < CP; ++c) {
+          float p0 = wm * G0[c], p1 = wm * G1[c];
+          p0 += __shfl_xor_sync(0xffffffffu, wt * G0[c], 4);
+          p1 += __shfl_xor_sync(0xffffffffu, wt * G1[c], 4);
+          p0 += __shfl_xor_sync(0xffffffffu, p1, 2);
+          p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+          if (own_mine) atomicAdd(dmine + c, p0);
         }
       }
     }

@@ -82,15 +82,18 @@ def test_fused_loss_equals_the_two_module_form(spec, dt, net):
         return loss.item(), [p.grad.detach().clone() for p in m.parameters()], names
 
     l0, g0, n0 = run(False)
+    _, g0b, _ = run(False)
     l1, g1, n1 = run(True)
     assert "esn_bilinear_ce" in n1 and "esn_weighted_ce" not in n1 and "esn_head_bilinear" not in n1 and "esn_bilinear_bwd" not in n1
     assert "esn_weighted_ce" in n0 and "esn_bilinear_ce" not in n0
     assert len(n1) == len(n0) - 2                     # head, CE forward, CE backward, bilinear backward -> fused + scale
     assert abs(l1 - l0) <= (1e-5 if dt is None else 2e-3) * abs(l0), (l0, l1)
     worst = max(_rel(a, b) for a, b in zip(g1, g0) if float(b.abs().max()) > 0)
-    # fp32: only summation order differs; bf16: the two-module form rounds d logits -> d scores identically (fp32 inside both),
-    # what differs is atomics order in the weight gradients of either run
-    assert worst < (2e-3 if dt is None else 5e-2), worst
+    # the noise floor is the two-module form against itself: fp32 atomics order in the weight gradients and -- in bf16, for
+    # train-mode BatchNorm layers over few values (CGNet's FGlo / 1/8-resolution stages) -- last-bit differences of the batch
+    # statistics; the fused close may differ from the two-module form by what two runs of the latter differ by
+    noise = max(_rel(a, b) for a, b in zip(g0b, g0) if float(b.abs().max()) > 0)
+    assert worst < max(2e-3 if dt is None else 5e-2, 3.0 * noise), (worst, noise)
 
 
 def test_dabnet_fused_loss_falls_back(spec):
