@@ -22,7 +22,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 wt = torch.tensor(fixture.CLASS_WEIGHTS)
 
 
-def run(dp, seed, distributed_loss, dtype):
+def run(dp, seed, distributed_loss, dtype, fused=False):
     m = build_model("DABNet", 19)
     m.load_state_dict(bench.fixture_state_dict("DABNet"))
     m = m.cuda().train()
@@ -31,11 +31,12 @@ def run(dp, seed, distributed_loss, dtype):
     crit = CrossEntropyLoss2d(weight=wt, ignore_label=255, distributed=distributed_loss).cuda()
     x = fixture.make_input(2, 128, 256, seed=seed).cuda()
     y = fixture.make_labels(2, 128, 256, 19, seed=seed).cuda()
+    call = (lambda: m.fused_loss(x, y, crit)) if fused else (lambda: crit(m(x), y))     # fused: esn_bilinear_ce close
     if dtype == torch.bfloat16:
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = crit(m(x), y)
+            loss = call()
     else:
-        loss = crit(m(x), y)
+        loss = call()
     loss.backward()
     return loss.detach(), torch.cat([p.grad.flatten().float() for p in m.parameters()])
 
@@ -50,6 +51,12 @@ for dtype in (torch.float32, torch.bfloat16):
     if rank == 0:
         print("%s identical-data: loss rel diff %.2e, all-reduced grad vs single-process rel-L2 %.2e (tol %.0e)" % (dtype, same, rel, tol))
     ok &= rel < tol and same < 1e-5
+    l_f, g_f = run(True, 7, True, dtype, fused=True)     # the fused head + loss (DABNet.fused_loss), same data on every rank
+    rel_f = ((g_f - g_ref).norm() / g_ref.norm()).item()
+    same_f = abs(l_f.item() - l_ref.item()) / abs(l_ref.item())
+    if rank == 0:
+        print("%s identical-data, fused close: loss rel diff %.2e, all-reduced grad vs single-process rel-L2 %.2e" % (dtype, same_f, rel_f))
+    ok &= rel_f < max(tol, 2e-4) and same_f < 1e-5
     l2, g2 = run(True, 100 + rank, True, dtype)          # different data per rank
     gs = [torch.zeros_like(g2) for _ in range(world)]
     dist.all_gather(gs, g2)
