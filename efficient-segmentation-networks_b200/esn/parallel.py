@@ -1,6 +1,6 @@
-"""Batch-sharded data parallelism: one process per GPU, NCCL all-reduce of flat gradient buckets
-launched from inside the backward tape (as soon as the last gradient of a bucket exists) on a side
-stream, so communication overlaps the remaining backward kernels.
+"""Batch-sharded data parallelism: one process per GPU, NCCL all-reduce of flat gradient buckets on a side stream --
+launched behind the last backward kernel (default, see ESN_DP_DEFER below) or from inside the backward tape as soon as the
+last gradient of a bucket exists, so that communication overlaps the remaining backward kernels.
 
 Replaces the reference's single-process nn.DataParallel (train.py:166-168): no per-step parameter
 broadcast (replicas stay identical by construction), no logits gather (the loss is local; only the
@@ -13,10 +13,15 @@ import os
 import torch
 import torch.distributed as dist
 
-# ESN_DP_DEFER=1: all-reduce every bucket after the last backward kernel instead of from inside the backward.  The backward's
-# BatchNorm layers are co-resident (cooperative) grids that need every SM; an NCCL kernel spinning on a few SMs makes them wait
-# for it, so overlapping 3 MB of all-reduce with the backward can cost more than it hides (measured).
-DEFER_ALLREDUCE = os.environ.get("ESN_DP_DEFER", "0") == "1"
+# ESN_DP_DEFER (default 1): all-reduce every bucket after the last backward kernel instead of from inside the backward
+# (ESN_DP_DEFER=0).  The backward's BatchNorm layers are co-resident (cooperative) grids that need every SM; an NCCL kernel
+# spinning on a few SMs makes them wait for it, so overlapping 3 MB of all-reduce with the backward costs more than it hides
+# once the optimizer step behind it is a single launch: DABNet training on 8 B200 7.72 ms per step overlapped, 7.60 deferred
+# (2 GPUs: 7.67 / 7.58; profiles/r02_allreduce_schedule.json).  With torch's 8-launch fused Adam behind the
+# reductions the overlap was the faster one (8.55 against 8.73 ms on 2 GPUs), which is why it used to be the default.
+DEFER_ALLREDUCE = os.environ.get("ESN_DP_DEFER", "1") == "1"
+# ESN_DP_BUCKET_BYTES: size of a flat gradient bucket when data_parallel() is not given one (default 1 MB)
+DEFAULT_BUCKET_BYTES = int(os.environ.get("ESN_DP_BUCKET_BYTES", str(1 << 20)))
 
 
 class GradBuckets:
@@ -135,13 +140,13 @@ def is_active():
     return _ACTIVE
 
 
-def data_parallel(model, bucket_bytes=1 << 20, process_group=None):
+def data_parallel(model, bucket_bytes=None, process_group=None):
     """Attach gradient buckets to a model built by build_model(); its train-mode forward/backward then
     all-reduces gradients across the process group.  Parameters are broadcast once from rank 0."""
     if dist.is_initialized() and dist.get_world_size(process_group) > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=0, group=process_group)
-    model.__dict__["_esn_buckets"] = GradBuckets(model, bucket_bytes, process_group)
+    model.__dict__["_esn_buckets"] = GradBuckets(model, bucket_bytes or DEFAULT_BUCKET_BYTES, process_group)
     global _ACTIVE
     _ACTIVE = _ACTIVE or model.__dict__["_esn_buckets"].world > 1
     return model
