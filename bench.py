@@ -485,7 +485,7 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
     from oracle import fixture
     model_name, batch, H, W, mode = WORKLOADS[wl_name]
     train = mode == "train"
-    u8_in = (args.e2e_input == "u8") and not train
+    u8_in = args.e2e_input == "u8"
     config = {"workload": wl_name, "net": model_name, "classes": 19, "batch_per_gpu": batch,
               "input": "3x%dx%d fp32 NCHW" % (H, W),
               "mode": "training step: forward + weighted CE + backward + Adam" if train else "inference",
@@ -613,8 +613,11 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
     else:
         in_host = x_host
         in_dev = [torch.empty_like(x) for _ in range(2)]
-    lab_dev = [torch.empty_like(y), torch.empty_like(y)] if train else [None, None]
-    h2d = in_host.numel() * in_host.element_size() + (y_host.numel() * 8 if train else 0)
+    # training labels: the uint8 label map the dataset class decodes (dataset/cityscapes.py:70) when the images travel as uint8,
+    # cast to int64 on the device (train.py:349 does `labels.long()` on the host and ships 8 bytes per pixel); int64 otherwise
+    lab_host = (y_host.to(torch.uint8).pin_memory() if u8_in else y_host) if train else None
+    lab_dev = [torch.empty_like(y, dtype=lab_host.dtype) for _ in range(2)] if train else [None, None]
+    h2d = in_host.numel() * in_host.element_size() + (lab_host.numel() * lab_host.element_size() if train else 0)
     d2h = 4 if train else batch * H * W
     out_host = [(torch.empty((), dtype=torch.float32) if train else torch.empty((batch, H, W), dtype=torch.uint8)).pin_memory()
                 for _ in range(2)]
@@ -638,14 +641,18 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
                         copy_s.wait_event(freed[b])      # input buffer b was consumed by its step
                     in_dev[b].copy_(in_host, non_blocking=True)
                     if train:
-                        lab_dev[b].copy_(y_host, non_blocking=True)
+                        lab_dev[b].copy_(lab_host, non_blocking=True)
                     ready[b] = torch.cuda.Event()
                     ready[b].record(copy_s)
             if i >= 1:
                 pb = (i - 1) & 1
                 main_s.wait_event(ready[pb])
                 if gstep is not None:
-                    res = gstep(in_dev[pb], lab_dev[pb])
+                    if u8_in:       # pre-processing straight into the graph's static image buffer
+                        ops.image_u8_to_f32(in_dev[pb], mean_bgr, True, out=gstep.images)
+                        res = gstep(None, lab_dev[pb])
+                    else:
+                        res = gstep(in_dev[pb], lab_dev[pb])
                 elif graph is not None:
                     if u8_in:
                         ops.image_u8_to_f32(in_dev[pb], mean_bgr, True, out=x)      # into the graph's static input
@@ -778,8 +785,11 @@ def measure(args, wl_name, rank, world, local_rank, dist, primary=True):
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms, 3), "steps": k_e2e, "input": "u8" if u8_in else "f32",
                     "preprocessing_bit_exact_vs_torch": exact,
-                    "note": ("pinned fp32 NCHW images + int64 labels -> H2D -> one training iteration (forward, weighted CE, backward, "
-                             "all-reduce, Adam; CUDA graph: %s) -> D2H loss scalar; copies double-buffered on side streams" % (gstep is not None))
+                    "note": (("pinned uint8 HWC BGR images + uint8 label maps (what cv2.imread gives the reference's dataset class) -> H2D "
+                              "-> esn_image_u8hwc_to_f32nchw + label cast on the device" if u8_in else
+                              "pinned fp32 NCHW images + int64 labels -> H2D") +
+                             " -> one training iteration (forward, weighted CE, backward, all-reduce, Adam; CUDA graph: %s) -> D2H "
+                             "loss scalar; copies double-buffered on side streams" % (gstep is not None))
                     if train else
                     ("pinned uint8 HWC BGR images (what cv2.imread gives the reference's dataset class) -> H2D -> "
                      "esn_image_u8hwc_to_f32nchw -> model.predict_mask -> D2H uint8 masks; copies double-buffered on side streams"
@@ -821,7 +831,7 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the gpu_eager_baseline leg (N=1)")
     ap.add_argument("--no-legs", action="store_true", help="skip the secondary workloads reported under `legs`")
     ap.add_argument("--e2e-input", default="u8", choices=["f32", "u8"],
-                    help="inference e2e leg: what crosses PCIe -- decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / "
+                    help="e2e leg: what crosses PCIe -- decoded uint8 HWC BGR images with mean subtraction / BGR->RGB / "
                          "CHW done on the device (esn_image_u8hwc_to_f32nchw, SURVEY 8f-4; default), or the reference's "
                          "pre-processed fp32 NCHW batch")
     ap.add_argument("--no-fused-loss", action="store_true",
