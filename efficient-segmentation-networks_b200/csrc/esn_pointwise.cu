@@ -49,7 +49,12 @@ __global__ void __launch_bounds__(256) pw_kernel(const PwArgs a) {
   const int c = cg * V;
   const TI* __restrict__ x = reinterpret_cast<const TI*>(a.x);
   float v[V];
-  if (OP == OP_MAXPOOL2) {
+  if (OP == OP_MAXPOOL2 && (2 * ho + 1 >= a.Hi || 2 * wo + 1 >= a.Wi)) {
+    // odd input: MaxPool2d(2, 2) has floor(H / 2) rows; the row / column behind them is the zero padding that
+    // ESNet's DownsamplerBlock adds before the concat (ESNet.py:25-29), still followed by the BatchNorm slice + ReLU
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = 0.f;
+  } else if (OP == OP_MAXPOOL2) {
     float t[V];
     load_px<TI, V>(a, x, n, 2 * ho, 2 * wo, c, v);
     load_px<TI, V>(a, x, n, 2 * ho, 2 * wo + 1, c, t);
@@ -311,7 +316,9 @@ int run_pw(const EsnPool* p, void* stream) {
   const bool nchw = x.layout == ESN_NCHW;
   if (nchw ? (!x.ptr || x.dtype != ESN_F32) : !esn_valid_nhwc(x)) return ESN_ERR_BAD_ARG;
   if (x.n != y.n || x.c != y.c) return ESN_ERR_BAD_SHAPE;
-  if (OP == OP_MAXPOOL2 && (y.h != x.h / 2 || y.w != x.w / 2)) return ESN_ERR_BAD_SHAPE;
+  // max-pool: floor(H / 2) x floor(W / 2), or -- odd sizes -- ceil x ceil with a zero last row / column (scalar kernel only)
+  const bool padded = OP == OP_MAXPOOL2 && (y.h != x.h / 2 || y.w != x.w / 2);
+  if (padded && (y.h != (x.h + 1) / 2 || y.w != (x.w + 1) / 2)) return ESN_ERR_BAD_SHAPE;
   if (OP == OP_AVGPOOL3S2 && (y.h != (x.h - 1) / 2 + 1 || y.w != (x.w - 1) / 2 + 1)) return ESN_ERR_BAD_SHAPE;
   if (OP == OP_AFFINE && (y.h != x.h || y.w != x.w)) return ESN_ERR_BAD_SHAPE;
   int rc = esn_check_epilogue(p->ep, y, OP == OP_AFFINE);
@@ -331,7 +338,7 @@ int run_pw(const EsnPool* p, void* stream) {
   a.ep = make_epi(p->ep);
   const size_t ysz = y.dtype == ESN_F32 ? 4 : 2, xsz = x.dtype == ESN_F32 ? 4 : 2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!nchw) {
+  if (!nchw && !padded) {
     const bool all16 = x.dtype == ESN_BF16 && y.dtype == ESN_BF16 && (!p->ep.residual.ptr || p->ep.residual.dtype == ESN_BF16);
     const int V = all16 ? 8 : 4;
     const EsnTensor& r = p->ep.residual;
@@ -348,7 +355,7 @@ int run_pw(const EsnPool* p, void* stream) {
     }
   }
   static const bool pool_noshift = getenv("ESN_POOL_NOSHIFT") != nullptr;
-  if (OP == OP_MAXPOOL2 && !nchw && x.dtype == ESN_BF16 && y.dtype == ESN_BF16 && !p->ep.residual.ptr && x.c_stride % 8 == 0 &&
+  if (OP == OP_MAXPOOL2 && !padded && !nchw && x.dtype == ESN_BF16 && y.dtype == ESN_BF16 && !p->ep.residual.ptr && x.c_stride % 8 == 0 &&
       y.c_stride % 8 == 0 && (uintptr_t)x.ptr % 16 == 0 && (uintptr_t)y.ptr % 2 == 0 && !pool_noshift) {
     // unaligned output slice: aligned-vector kernel shifted by OFF channels (elements outside the slice are never touched)
     const int off = (int)(((uintptr_t)y.ptr / 2) % 8);

@@ -96,12 +96,12 @@ class Adam(torch.optim.Optimizer):
         self._g[id(group)] = gs
         return gs
 
-    def _tables(self, gs, grads):
-        key = tuple(g.data_ptr() for g in grads) + tuple(p.data_ptr() for p in gs["plist"])
+    def _tables(self, gs, plist, offs, grads):
+        key = tuple(g.data_ptr() for g in grads) + tuple(p.data_ptr() for p in plist)
         if key == gs["key"]:
             return
-        tab, blk = build_tables([p.data_ptr() for p in gs["plist"]], [g.data_ptr() for g in grads],
-                                [p.numel() for p in gs["plist"]], gs["offs"], gs["m"].data_ptr(), gs["v"].data_ptr(), self._chunk)
+        tab, blk = build_tables([p.data_ptr() for p in plist], [g.data_ptr() for g in grads], [p.numel() for p in plist], offs,
+                                gs["m"].data_ptr(), gs["v"].data_ptr(), self._chunk)
         host = torch.empty(tab.size * 8 + blk.size * 4, dtype=torch.uint8).pin_memory()
         host[:tab.size * 8].copy_(torch.from_numpy(tab.reshape(-1).view(np.uint8)))
         host[tab.size * 8:].copy_(torch.from_numpy(blk.reshape(-1).view(np.uint8)))
@@ -138,16 +138,22 @@ class Adam(torch.optim.Optimizer):
             gs = self._g.get(id(group))
             if gs is None:
                 continue
-            grads = []
-            for p in gs["plist"]:
+            # parameters without a gradient take no part in this step, as in torch.optim.Adam (ERFNet's encoder.output_conv,
+            # ERFNet.py:88-89); the step counter is the group's, so a parameter that only sometimes receives a gradient sees
+            # the group's bias corrections rather than its own count (no such parameter on the hot-path nets)
+            plist, offs, grads = [], [], []
+            for p, o in zip(gs["plist"], gs["offs"]):
                 g = p.grad
                 if g is None:
-                    raise RuntimeError("esn.optim.Adam: a parameter of the group has no gradient (the one-launch update covers "
-                                       "the whole group; freeze unused parameters with requires_grad_(False))")
+                    continue
                 if g.is_sparse or g.dtype != torch.float32:
                     raise NotImplementedError("esn.optim.Adam: dense fp32 gradients only")
+                plist.append(p)
+                offs.append(o)
                 grads.append(g if g.is_contiguous() else g.contiguous())
-            self._tables(gs, grads)
+            if not plist:
+                continue
+            self._tables(gs, plist, offs, grads)
             lr = group["lr"]
             if isinstance(lr, torch.Tensor):
                 if not (lr.is_cuda and lr.dtype == torch.float32 and lr.numel() == 1):

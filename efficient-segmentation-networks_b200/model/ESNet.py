@@ -12,8 +12,9 @@ ERFNet's kernels:
   three branch outputs and the block input are summed by chaining the residual operand of the three closing
   1x3 launches -- relu(((x + o2) + o5) + o9), the reference's association order -- so no add kernel runs.
 * DownsamplerBlock / UpsamplerBlock / output_conv: ERFNet's (ESNet.py:12-48,182 == ERFNet.py:16-27,103-112,128).
-  The reference pads the pooled branch when the input height/width is odd (ESNet.py:25-29); odd sizes are
-  rejected here (Cityscapes shapes are even at every level).
+  The reference pads the pooled branch when the input height/width is odd (ESNet.py:25-29); so does the block here
+  (direct-kernel conv + the pool kernel's padded mode), so any input size runs and the logits have
+  8 * ceil(ceil(ceil(H / 2) / 2) / 2) rows as in the reference.
 """
 import torch
 import torch.nn as nn
@@ -35,10 +36,23 @@ class DownsamplerBlock(_ErfDownsamplerBlock):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, input):
-        if (input.shape[2] | input.shape[3]) & 1:
-            raise NotImplementedError("ESNet DownsamplerBlock: odd input sizes (the F.pad path of ESNet.py:25-29) "
-                                      "are not supported; got %dx%d" % (input.shape[2], input.shape[3]))
-        return super().forward(input)
+        if not (input.shape[2] | input.shape[3]) & 1:
+            return super().forward(input)
+        # odd height / width (ESNet.py:22-29): the stride-2 conv has ceil(H/2) rows, the pool floor(H/2); the reference pads
+        # the pooled map with a zero row / column at the bottom / right before the concat.  The conv takes the direct kernel
+        # (the tcgen05 stride-2 route wants even sizes), the pool kernel writes the padded map itself (include/esn.h).
+        _no_train(self)
+        dtype = ops.compute_dtype(input)
+        x = input if (input.shape[1] < 8 and input.is_contiguous() and input.dtype == torch.float32
+                      and not ops.is_nhwc(input)) else ops.as_act(input, dtype)
+        ops.require_cuda(x, "DownsamplerBlock")
+        conv, pscale, pshift, _, _ = self.prep(x.device)
+        n, c, h, w = x.shape
+        nc = conv.cout
+        y = ops.new_act(n, nc + c, (h + 1) // 2, (w + 1) // 2, dtype, x.device)
+        ops.conv2d(x, conv, out=y[:, :nc])
+        ops.maxpool2x2(x, y[:, nc:], pscale, pshift, None, ACT_RELU)
+        return y
 
 
 class UpsamplerBlock(_ErfUpsamplerBlock):
@@ -159,9 +173,7 @@ class ESNet(nn.Module):
         if self.training:
             raise NotImplementedError("ESNet: training-mode kernels are not wired for this model; call .eval(). "
                                       "There is no eager-PyTorch fallback.")
-        if (input.shape[2] | input.shape[3]) % 8:
-            raise NotImplementedError("ESNet: input height and width must be multiples of 8, got %dx%d"
-                                      % (input.shape[2], input.shape[3]))
+        # any input size (ESNet.py:22-29): the logits have 8 * ceil(ceil(ceil(H / 2) / 2) / 2) rows, as in the reference
         output = self.initial_block(input)
         for layer in self.layers:
             output = layer(output)

@@ -167,7 +167,10 @@ int esn_stem_conv3x3s2(const EsnStem* p, void* stream);
 /* MaxPool2d(2, stride 2) followed by the per-channel affine + activation of
  * the BatchNorm slice it is concatenated into.
  * Replaces the pool branch of ERFNet.py:24-27 (DownsamplerBlock) and
- * DABNet.py:104-108 (DownSamplingBlock): y[..., c] = act(max2x2(x)[c]*scale[c]+shift[c]). */
+ * DABNet.py:104-108 (DownSamplingBlock): y[..., c] = act(max2x2(x)[c]*scale[c]+shift[c]).
+ * y is floor(h/2) x floor(w/2); for an odd h or w it may instead be ceil(h/2) x ceil(w/2): the pooled map then sits in the
+ * upper-left corner and the last row / column is the zero padding ESNet's DownsamplerBlock inserts before the concat
+ * (ESNet.py:25-29: F.pad(x1, [0, diffX, 0, diffY])), i.e. y = act(shift) there. */
 typedef struct EsnPool {
   EsnTensor x, y;
   EsnEpilogue ep;

@@ -57,9 +57,14 @@ def prelu(x, alpha):
 
 # --------------------------------------------------------------------------- ERFNet
 def erf_downsampler(p, x):
-    """DownsamplerBlock, model/ERFNet.py:16-27."""
-    y = torch.cat([F.conv2d(x, p["conv.weight"], p["conv.bias"], stride=2, padding=1),
-                   F.max_pool2d(x, 2, 2)], 1)
+    """DownsamplerBlock, model/ERFNet.py:16-27; for odd sizes the pooled map is zero-padded at the bottom / right up to the
+    conv's ceil(H/2) rows, as ESNet's and LEDNet's copies of the block do (model/ESNet.py:22-29; ERFNet's own copy raises)."""
+    y2 = F.conv2d(x, p["conv.weight"], p["conv.bias"], stride=2, padding=1)
+    y1 = F.max_pool2d(x, 2, 2)
+    dy, dx = y2.shape[2] - y1.shape[2], y2.shape[3] - y1.shape[3]
+    if dy or dx:
+        y1 = F.pad(y1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    y = torch.cat([y2, y1], 1)
     return F.relu(bn(p.sub("bn"), y, 1e-3))
 
 
@@ -603,7 +608,7 @@ ES_LAYERS = ([("fcu", 3)] * 3 + [("down",)] + [("fcu", 5)] * 2 + [("down",)] + [
 
 
 def esnet(sd, x, train=False, stats=None):
-    """ESNet.forward, model/ESNet.py:184-193 (even input sizes: the F.pad of :25-29 is a no-op)."""
+    """ESNet.forward, model/ESNet.py:184-193 (any input size: erf_downsampler pads like ESNet.py:25-29)."""
     p = SD(sd, "", x.dtype, train, stats)
     y = erf_downsampler(p.sub("initial_block"), x)
     for i, spec in enumerate(ES_LAYERS):

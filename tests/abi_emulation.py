@@ -217,6 +217,17 @@ def _pool(fn):
     return run
 
 
+def _maxpool2(ref):
+    """MaxPool2d(2, 2); when y has ceil(h/2) x ceil(w/2) pixels (odd input), zero padding behind the pooled map (include/esn.h)."""
+    p = ref._obj
+    v = F.max_pool2d(_finite(tensor(p.x).float(), "pool"), 2, 2)
+    if (p.y.h, p.y.w) != tuple(v.shape[2:]):
+        assert (p.y.h, p.y.w) == ((p.x.h + 1) // 2, (p.x.w + 1) // 2)
+        v = F.pad(v, [0, p.y.w - v.shape[3], 0, p.y.h - v.shape[2]])
+    store(tensor(p.y), epilogue(v, p.ep))
+    return 0
+
+
 def esn_convert_layout(xr, yr):
     store(tensor(yr._obj), tensor(xr._obj).float())
     return 0
@@ -480,7 +491,7 @@ def esn_image_u8hwc_to_f32nchw(img, out, n, h, w, mean3, reverse):
 ENTRY = {
     "esn_conv2d_direct": esn_conv2d_direct, "esn_conv2d_umma": esn_conv2d_umma, "esn_conv2d_umma_dual": esn_conv2d_umma_dual, "esn_concat_tail": esn_concat_tail, "esn_conv_pair_umma": esn_conv_pair_umma,
     "esn_stem_conv3x3s2": esn_stem_conv3x3s2,
-    "esn_maxpool2x2_affine_act": _pool(lambda x: F.max_pool2d(x, 2, 2)),
+    "esn_maxpool2x2_affine_act": _maxpool2,
     "esn_avgpool3x3s2_affine_act": _pool(lambda x: F.avg_pool2d(x, 3, 2, 1)),
     "esn_affine_act": _pool(lambda x: x),
     "esn_convert_layout": esn_convert_layout, "esn_adaptive_avgpool": esn_adaptive_avgpool, "esn_bilinear_nhwc": esn_bilinear_nhwc,

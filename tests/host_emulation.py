@@ -119,7 +119,10 @@ def stem_conv3x3s2(x, w_direct, cconv, with_pool, out, scale, shift, alpha, act)
 
 
 def maxpool2x2(x, out, scale=None, shift=None, alpha=None, act=L.ACT_NONE):
-    return _store(out, _epilogue(F.max_pool2d(x.float(), 2, 2), scale, shift, alpha, act, None))
+    v = F.max_pool2d(x.float(), 2, 2)
+    if tuple(out.shape[2:]) != tuple(v.shape[2:]):       # odd input: zero padding behind the pooled map (include/esn.h)
+        v = F.pad(v, [0, out.shape[3] - v.shape[3], 0, out.shape[2] - v.shape[2]])
+    return _store(out, _epilogue(v, scale, shift, alpha, act, None))
 
 
 def avgpool3x3s2(x, out, scale=None, shift=None, alpha=None, act=L.ACT_NONE):

@@ -296,3 +296,19 @@ def test_bilinear_ce_wrapper_through_the_abi():
     assert abs(sums[0].item() - loss.item()) < 1e-4 * abs(loss.item())
     assert abs(sums[1].item() - wt[tgt[tgt != 255]].sum().item()) < 1e-3
     assert ds.shape == (n, c, h, w) and ds.stride(3) == 20 and _rel(ds, xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_esnet_odd_input_sizes_through_the_abi(size, bf16, spec, golden):
+    """ESNet.py:22-29: odd heights / widths.  The stride-2 conv of the block takes the direct kernel, the pool kernel writes
+    the zero-padded map (esn_maxpool2x2_affine_act with a ceil-sized output); fp32 must reproduce the reference's golden."""
+    n, h, w = size
+    m = _model("ESNet", spec)
+    ref = torch.from_numpy(golden("oddsize")["ESNet_%dx%dx%d_logits" % size])
+    with emulate_abi(bf16=bf16) as calls, torch.no_grad():
+        y = m(fixture.make_input(n, h, w))
+        mask = m.predict_mask(fixture.make_input(n, h, w))
+    assert y.shape == ref.shape and mask.shape == (n,) + tuple(ref.shape[2:])
+    assert _rel(y.float(), ref) < (1e-5 if not bf16 else 5e-2)
+    assert any(nm == "esn_maxpool2x2_affine_act" for nm, _ in calls)

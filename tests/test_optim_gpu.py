@@ -141,3 +141,25 @@ def test_state_dict_moves_both_ways():
     _close(ours, theirs)
     _close(ours2, theirs)
     _close(theirs2, theirs)
+
+
+def test_parameters_without_a_gradient_are_left_alone():
+    """ERFNet's encoder.output_conv takes no part in the forward (ERFNet.py:88-89) and never gets a gradient: torch.optim.Adam
+    skips such parameters, so does the one-launch step."""
+    from esn.optim import Adam
+    ours, theirs = _params(), _params()
+    a = Adam(ours, lr=1e-3, weight_decay=1e-4)
+    b = torch.optim.Adam(theirs, lr=1e-3, weight_decay=1e-4)
+    frozen = (2, 7)
+    before = [ours[i].detach().clone() for i in frozen]
+    for it in range(3):
+        _set_grads(ours, it)
+        _set_grads(theirs, it)
+        for i in frozen:
+            ours[i].grad = None
+            theirs[i].grad = None
+        a.step()
+        b.step()
+    _close(ours, theirs)
+    for i, p0 in zip(frozen, before):
+        assert torch.equal(ours[i].detach(), p0)

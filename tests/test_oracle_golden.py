@@ -31,6 +31,18 @@ def test_eval_forward_matches_reference(name, spec, golden):
     assert (nets.argmax_mask(y) == g["eval_2x128x256_argmax"]).mean() > 0.9999
 
 
+@pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
+def test_esnet_odd_sizes_match_reference(size, spec, golden):
+    """The F.pad path of ESNet's DownsamplerBlock (model/ESNet.py:22-29): inputs that are odd at one or more levels; the logits
+    have 8 * ceil(ceil(ceil(H / 2) / 2) / 2) rows (tools/make_golden_oddsize.py, unmodified reference)."""
+    n, h, w = size
+    ref = torch.from_numpy(golden("oddsize")["ESNet_%dx%dx%d_logits" % size])
+    with torch.no_grad():
+        y = nets.forward("ESNet", spec_state_dict(spec, "ESNet"), fixture.make_input(n, h, w))
+    assert y.shape == ref.shape == (n, 19, 8 * -(-(-(-(-(-h // 2)) // 2)) // 2), 8 * -(-(-(-(-(-w // 2)) // 2)) // 2))
+    assert (y - ref).norm() / ref.norm() < 1e-5
+
+
 @pytest.mark.parametrize("name", ["ERFNet", "DABNet"])
 def test_train_forward_backward_matches_reference_fp64(name, spec, golden):
     sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v)
