@@ -219,3 +219,23 @@ def test_focal_loss_matches_reference_golden(golden):
     loss.backward()
     assert abs(loss.item() - g["focal_loss"][0]) < 1e-4 * abs(g["focal_loss"][0])
     assert T._rel(logits.grad.cpu(), torch.from_numpy(g["focal_grad"])) < 1e-4
+
+
+@pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
+def test_esnet_odd_input_sizes(size, spec, golden):
+    """ESNet.py:22-29 on the device: inputs that are odd at one or more levels.  fp32 logits against the unmodified
+    reference (tests/golden/oddsize.npz), bf16 logits and the fused mask against the CPU oracle."""
+    n, h, w = size
+    m = T._model("ESNet", spec)
+    ref = torch.from_numpy(golden("oddsize")["ESNet_%dx%dx%d_logits" % size])
+    x = fixture.make_input(n, h, w).cuda()
+    with torch.no_grad():
+        y = m(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16, mask = m.predict_mask(x, with_logits=True)
+    assert y.shape == ref.shape and mask.shape == (n,) + tuple(ref.shape[2:])
+    assert T._rel(y.cpu(), ref) < 1e-3
+    assert (y.cpu().argmax(1) == ref.argmax(1)).float().mean().item() >= 0.999
+    assert T._rel(y16.float().cpu(), ref) < 5e-2
+    assert torch.equal(mask.cpu().long(), y16.float().cpu().argmax(1)) or \
+        (mask.cpu().long() == y16.float().cpu().argmax(1)).float().mean().item() > 0.995     # fp32 accumulators vs bf16-rounded logits
