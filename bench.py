@@ -420,6 +420,7 @@ ENTRY_KERNELS = {
     "esn_channel_stats": ("channel_stats",), "esn_act_bwd": ("act_bwd_kernel",), "esn_scale_nc": ("scale_nc_kernel",),
     "esn_dropout": ("dropout_kernel",), "esn_head_bilinear": ("bilinear_head",), "esn_maxpool2x2_bwd": ("maxpool2x2_bwd",),
     "esn_affine_act": ("pw_vec_kernel", "pw_kernel"), "esn_stem_conv3x3s2": ("stem_",),
+    "esn_bilinear_ce": ("bilinear_ce_kernel",), "esn_adam_step": ("adam_table_kernel",),
 }
 
 

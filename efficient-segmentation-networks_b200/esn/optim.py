@@ -163,10 +163,11 @@ class Adam(torch.optim.Optimizer):
                 lr_ptr = gs["lr_dev"].data_ptr()
             b1, b2 = group["betas"]
             with torch.cuda.device(gs["m"].device):
-                rc = L.lib.esn_adam_step(C.c_void_p(gs["table"].data_ptr()), C.c_void_p(gs["blocks"].data_ptr()), gs["n_blocks"],
-                                         C.c_void_p(lr_ptr), C.c_void_p(gs["step"].data_ptr()), C.c_void_p(gs["done"].data_ptr()),
-                                         float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), ops.stream())
-            L.check(rc, "esn_adam_step")
+                ops._call(L.lib.esn_adam_step, "esn_adam_step",
+                          (C.c_void_p(gs["table"].data_ptr()), C.c_void_p(gs["blocks"].data_ptr()), gs["n_blocks"],
+                           C.c_void_p(lr_ptr), C.c_void_p(gs["step"].data_ptr()), C.c_void_p(gs["done"].data_ptr()),
+                           float(b1), float(b2), float(group["eps"]), float(group["weight_decay"])),
+                          28 * sum(p.numel() for p in plist))        # p, g, m, v read; p, m, v written
             gs["keep"] = grads               # gradients made contiguous for this launch stay alive until the next one
         return loss
 

@@ -82,18 +82,30 @@ def test_fused_loss_equals_the_two_module_form(spec, dt, net):
         return loss.item(), [p.grad.detach().clone() for p in m.parameters()], names
 
     l0, g0, n0 = run(False)
-    _, g0b, _ = run(False)
     l1, g1, n1 = run(True)
     assert "esn_bilinear_ce" in n1 and "esn_weighted_ce" not in n1 and "esn_head_bilinear" not in n1 and "esn_bilinear_bwd" not in n1
     assert "esn_weighted_ce" in n0 and "esn_bilinear_ce" not in n0
     assert len(n1) == len(n0) - 2                     # head, CE forward, CE backward, bilinear backward -> fused + scale
     assert abs(l1 - l0) <= (1e-5 if dt is None else 2e-3) * abs(l0), (l0, l1)
-    worst = max(_rel(a, b) for a, b in zip(g1, g0) if float(b.abs().max()) > 0)
-    # the noise floor is the two-module form against itself: fp32 atomics order in the weight gradients and -- in bf16, for
-    # train-mode BatchNorm layers over few values (CGNet's FGlo / 1/8-resolution stages) -- last-bit differences of the batch
-    # statistics; the fused close may differ from the two-module form by what two runs of the latter differ by
-    noise = max(_rel(a, b) for a, b in zip(g0b, g0) if float(b.abs().max()) > 0)
-    assert worst < max(2e-3 if dt is None else 5e-2, 3.0 * noise), (worst, noise)
+    live = [i for i, b in enumerate(g0) if float(b.abs().max()) > 0]
+    if dt is None:
+        worst = max(_rel(g1[i], g0[i]) for i in live)
+        assert worst < 2e-3, worst                    # fp32: only the summation order differs
+        return
+    # bf16: both forms round the same d scores to bf16 from values that differ in the last fp32 bits (atomics order of the
+    # weight sum), so single roundings flip.  Some parameter gradients are sums of cancelling terms (train-mode BatchNorm) and
+    # move by 10-20 % under such flips -- in the two-module form as much as in the fused one.  So: all gradients together
+    # agree closely, and parameter by parameter the fused form is as close to the FP32 gradients as the two-module form is.
+    cat = lambda gs: torch.cat([gs[i].flatten().double() for i in live])
+    assert _rel(cat(g1), cat(g0)) < 2e-2, _rel(cat(g1), cat(g0))
+    m32 = build_model(net, 19)
+    m32.load_state_dict(spec_state_dict(spec, net))
+    m32 = m32.cuda().train()
+    crit(m32(x), lab).backward()                      # the two-module form in fp32
+    g32 = [p.grad.detach().clone() for p in m32.parameters()]
+    for i in live:
+        e1, e0 = _rel(g1[i], g32[i]), _rel(g0[i], g32[i])
+        assert e1 < max(5e-2, 2.0 * e0), (i, e1, e0)
 
 
 def test_dabnet_fused_loss_falls_back(spec):
