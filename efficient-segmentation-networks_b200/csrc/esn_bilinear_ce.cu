@@ -9,15 +9,15 @@
 // 8 x 19 x 512 x 1024), read them twice for the loss and its gradient, write the gradient and read it back for the transposed
 // interpolation: 1.6 GB of traffic and 0.55 ms of a 7.4 ms DABNet step for 2.5 MB of scores and 33 MB of labels.
 //
-// Geometry (integer scale s = H / h = W / w, s even): output rows s k + s/2 ... s k + 3 s/2 - 1 form "cell" k (k = -1 ... h-1,
-// clipped to the image); every pixel of a cell blends source rows k and k + 1 (clamped), likewise for columns.  A CTA OWNS a
-// kCR x kCC block of source pixels, walks the (kCR + 1) x (kCC + 1) cells that touch them (the border cells are recomputed by
-// the neighbouring CTA: arithmetic is cheap here) and keeps only the gradient contributions to its own source pixels, in
-// shared memory -- so the score gradient is written with plain stores: no global atomics, no zero fill.  A
-// pixel's loss is counted by the CTA that owns the cell's upper-left source pixel.
+// Geometry: an output row y reads source rows k = floor(src(y)) and min(k + 1, h - 1), with src(y) as ATen computes it in fp32
+// (align_corners = False: max(0, (y + 0.5) h / H - 0.5); True: y (h - 1) / (H - 1)); the rows with the same k form "cell" k,
+// likewise for columns -- any scale, both modes.  A CTA OWNS a kCR x kCC block of source pixels, walks the (kCR + 1) x
+// (kCC + 1) cells that touch them (the border cells are recomputed by the neighbouring CTA: arithmetic is cheap here) and keeps
+// only the gradient contributions to its own source pixels, in shared memory -- so the score gradient is written with plain
+// stores: no global atomics, no zero fill.  A pixel's loss is counted by the CTA that owns the cell's upper-left source pixel.
 //
 // Inside a warp: lane = (cell q of four adjacent cells, row r of the cell); a thread blends its row's two source vectors
-// once (A, B), walks the s pixels of its cell row (logit_c = A_c + lx (B_c - A_c), soft-max in the log2 domain: one FFMA and
+// once (A, B), walks the pixels of its cell row (logit_c = A_c + lx (B_c - A_c), soft-max in the log2 domain: one FFMA and
 // one ex2.approx per class), sums the soft-max part of the gradient against (1 - lx) and lx in registers -- the onehot part
 // goes straight into the CTA's tile, once per run of equal labels -- and the eight rows of a cell are combined by a
 // reduce-scatter over the four source pixels (four shuffles per class), after which four lanes per cell add into the tile.
@@ -34,8 +34,25 @@ struct BceArgs {
   const float* weight;
   float* sums;
   float* dscores;
-  int N, h, w, C, cs, dcs, H, W, s, ignore;
+  int N, h, w, C, cs, dcs, H, W, align, ignore;
+  float sy, sx;       // source step per output row / column, as ATen's area_pixel_compute_scale gives it
 };
+
+// source coordinate of output index o (ATen's area_pixel_compute_source_index, fp32)
+__device__ __forceinline__ float src_coord(int o, float scale, int align) {
+  return align ? scale * (float)o : fmaxf(scale * ((float)o + 0.5f) - 0.5f, 0.f);
+}
+// first output index whose source cell floor(src) is >= k (n_out when there is none): an estimate from the inverse map,
+// corrected against src_coord itself so that cells and per-pixel weights can never disagree
+__device__ __forceinline__ int first_out(int k, float scale, int align, int n_out) {
+  if (k <= 0) return 0;
+  if (!(scale > 0.f)) return n_out;
+  int o = (int)ceilf(align ? (float)k / scale : ((float)k + 0.5f) / scale - 0.5f);
+  o = min(max(o, 0), n_out);
+  while (o > 0 && (int)src_coord(o - 1, scale, align) >= k) --o;
+  while (o < n_out && (int)src_coord(o, scale, align) < k) ++o;
+  return o;
+}
 
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
@@ -66,8 +83,6 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
   for (int i = tid; i < kCR * kCC * CP; i += kThreads) dS[i] = 0.f;
   __syncthreads();
 
-  const float inv_s = 1.f / (float)a.s;
-  const int half = a.s >> 1;
   const int ncell = (kr + 1) * (lc + 1);                // cells (k0 - 1 + kc, l0 - 1 + lci), kc = 0 .. kr, lci = 0 .. lc
   float loss_acc = 0.f, w_acc = 0.f;
   for (int it = warp; it * 4 < ncell; it += kThreads / 32) {
@@ -75,7 +90,12 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
     const bool cell_ok = ci < ncell;
     const int kc = min(ci, ncell - 1) / (lc + 1), lci = min(ci, ncell - 1) - kc * (lc + 1);
     const int k = k0 - 1 + kc, l = l0 - 1 + lci;
-    const bool own_cell = cell_ok && (kc >= 1 || k0 == 0) && (lci >= 1 || l0 == 0);
+    const bool live = cell_ok && k >= 0 && l >= 0;                 // cells start at source row / column 0
+    const bool own_cell = live && kc >= 1 && lci >= 1;
+    // output rows / columns of this cell
+    const int ya = live ? first_out(k, a.sy, a.align, a.H) : 0, yb = live ? (k + 1 < a.h ? first_out(k + 1, a.sy, a.align, a.H) : a.H) : 0;
+    const int xa = live ? first_out(l, a.sx, a.align, a.W) : 0, xb = live ? (l + 1 < a.w ? first_out(l + 1, a.sx, a.align, a.W) : a.W) : 0;
+    const int max_rows = __reduce_max_sync(0xffffffffu, yb - ya);
     // tile rows kc, kc + 1 / columns lci, lci + 1 hold the (clamped) source pixels of this cell; which of them are ours
     const int rsA = min(max(k, 0), a.h - 1), rsB = min(max(k + 1, 0), a.h - 1);
     const int csA = min(max(l, 0), a.w - 1), csB = min(max(l + 1, 0), a.w - 1);
@@ -91,18 +111,16 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
     const float* sBB = sBA + CP;
     const bool row_b = (r & 4) != 0, col_b = (r & 2) != 0;        // the source pixel this lane collects after the reduction
     float* dmine = row_b ? (col_b ? dBB : dBA) : (col_b ? dAB : dAA);
-    const bool own_mine = cell_ok && (r & 1) == 0 && (row_b ? orB : orA) && (col_b ? ocB : ocA);
-    for (int yy0 = 0; yy0 < a.s; yy0 += 8) {
-      const int yy = yy0 + r;
-      const int y = a.s * k + half + yy;
-      const bool row_ok = cell_ok && yy < a.s && y >= 0 && y < a.H;
+    const bool own_mine = live && (r & 1) == 0 && (row_b ? orB : orA) && (col_b ? ocB : ocA);
+    for (int yy0 = 0; yy0 < max_rows; yy0 += 8) {          // eight rows of every cell per pass (warp-uniform trip count)
+      const int y = ya + yy0 + r;
+      const bool row_ok = y < yb;
       float G0[CP], G1[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) G0[c] = G1[c] = 0.f;
       float ly = 0.f;
       if (row_ok) {
-        const float srcy = fmaxf(((float)y + 0.5f) * inv_s - 0.5f, 0.f);
-        ly = srcy - floorf(srcy);
+        ly = src_coord(y, a.sy, a.align) - (float)k;
         // the row's two blended source vectors, in units of log2 (one FFMA + one EX2 per class and pixel below)
         constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
         float A[CP], D[CP];
@@ -114,7 +132,6 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
           D[c] = (vb - va) * kLog2e;
         }
         const long long* trow = a.target + ((size_t)n * a.H + y) * a.W;
-        const int x0 = a.s * l + half;
         // onehot part of the gradient: summed per run of equal labels and added straight into the owned tile when the label
         // changes (four shared-memory atomics per run; per pixel when every pixel has another label)
         const float wyA = 1.f - ly;
@@ -126,15 +143,12 @@ __global__ void __launch_bounds__(kThreads, CP <= 20 ? 2 : 1) bilinear_ce_kernel
         };
         int cur = -1;
         float oa = 0.f, ob = 0.f;
-        for (int j = 0; j < a.s; ++j) {
-          const int x = x0 + j;
-          if (x < 0 || x >= a.W) continue;
+        for (int x = xa; x < xb; ++x) {
           const long long t = __ldg(trow + x);
           if (t == a.ignore || t < 0 || t >= a.C) continue;
           const int ti = (int)t;
           const float wy = a.weight ? __ldg(a.weight + ti) : 1.f;
-          const float srcx = fmaxf(((float)x + 0.5f) * inv_s - 0.5f, 0.f);
-          const float lx = srcx - floorf(srcx);
+          const float lx = src_coord(x, a.sx, a.align) - (float)l;
           float v[CP];
           float m = -INFINITY;
 #pragma unroll
@@ -243,9 +257,7 @@ extern "C" int esn_bilinear_ce(const EsnBilinearCE* p, void* stream) {
   if (g.dtype != ESN_F32) return ESN_ERR_BAD_ARG;
   if (g.n != x.n || g.h != x.h || g.w != x.w || g.c != x.c) return ESN_ERR_BAD_SHAPE;
   if (x.c < 1 || x.c > 32) return ESN_ERR_UNSUPPORTED;
-  if (p->out_h < 1 || p->out_w < 1 || p->out_h % x.h || p->out_w % x.w) return ESN_ERR_UNSUPPORTED;
-  const int s = p->out_h / x.h;
-  if (s != p->out_w / x.w || s < 2 || (s & 1) || s > 64) return ESN_ERR_UNSUPPORTED;      // integer, even, isotropic scale
+  if (p->out_h < 1 || p->out_w < 1) return ESN_ERR_BAD_SHAPE;
   BceArgs a;
   a.scores = x.ptr;
   a.target = reinterpret_cast<const long long*>(p->target);
@@ -253,7 +265,11 @@ extern "C" int esn_bilinear_ce(const EsnBilinearCE* p, void* stream) {
   a.sums = p->sums;
   a.dscores = reinterpret_cast<float*>(g.ptr);
   a.N = x.n; a.h = x.h; a.w = x.w; a.C = x.c; a.cs = x.c_stride; a.dcs = g.c_stride;
-  a.H = p->out_h; a.W = p->out_w; a.s = s; a.ignore = p->ignore_label;
+  a.H = p->out_h; a.W = p->out_w; a.ignore = p->ignore_label;
+  a.align = p->align_corners ? 1 : 0;
+  // ATen's area_pixel_compute_scale<float>: align_corners ? (in - 1) / (out - 1) (0 for out == 1) : in / out
+  a.sy = a.align ? (a.H > 1 ? (float)(x.h - 1) / (float)(a.H - 1) : 0.f) : (float)x.h / (float)a.H;
+  a.sx = a.align ? (a.W > 1 ? (float)(x.w - 1) / (float)(a.W - 1) : 0.f) : (float)x.w / (float)a.W;
   const long long grid = (long long)x.n * ((x.h + kCR - 1) / kCR) * ((x.w + kCC - 1) / kCC);
   if (grid > 0x7fffffffLL) return ESN_ERR_UNSUPPORTED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -123,7 +123,7 @@ class EsnCE(C.Structure):
 class EsnBilinearCE(C.Structure):
     _fields_ = [("scores", EsnTensor), ("target", C.c_void_p), ("weight", C.c_void_p), ("sums", C.c_void_p),
                 ("dscores", EsnTensor), ("out_h", C.c_int32), ("out_w", C.c_int32), ("ignore_label", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("align_corners", C.c_int32)]
 
 
 # every symbol include/esn.h declares: name -> (restype, argtypes)

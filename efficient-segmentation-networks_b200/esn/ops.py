@@ -830,15 +830,14 @@ def weighted_ce(logits, target, weight=None, ignore_label=255, want_grad=False, 
     return sums, g
 
 
-def bilinear_ce(scores, target, weight, ignore_label, out_h, out_w, sums=None):
-    """F.interpolate(scores, (out_h, out_w), bilinear, align_corners=False) -> weighted cross-entropy sums + the gradient of the
+def bilinear_ce(scores, target, weight, ignore_label, out_h, out_w, sums=None, align_corners=False):
+    """F.interpolate(scores, (out_h, out_w), bilinear, align_corners) -> weighted cross-entropy sums + the gradient of the
     scores, in one launch (esn_bilinear_ce; no full-resolution tensor is written).  Returns (sums[2] = [sum w*nll, sum w],
-    dscores fp32 NHWC = d sums[0] / d scores), or None when the entry point does not take the geometry (an integer, even,
-    isotropic scale is required)."""
+    dscores fp32 NHWC = d sums[0] / d scores), or None for what the entry point does not take (more than 32 classes, a
+    target that is not int64 (N, out_h, out_w))."""
     require_cuda(scores, "bilinear_ce")
     n, c, h, w = scores.shape
-    if not (is_nhwc(scores) and c <= 32 and out_h % h == 0 and out_w % w == 0 and out_h // h == out_w // w
-            and (out_h // h) % 2 == 0 and 2 <= out_h // h <= 64 and tuple(target.shape) == (n, out_h, out_w)
+    if not (is_nhwc(scores) and c <= 32 and out_h >= 1 and out_w >= 1 and tuple(target.shape) == (n, out_h, out_w)
             and target.dtype == torch.int64):
         return None
     target = target.contiguous()
@@ -850,7 +849,7 @@ def bilinear_ce(scores, target, weight, ignore_label, out_h, out_w, sums=None):
     p.target = target.data_ptr()
     p.weight = weight.data_ptr() if weight is not None else None
     p.sums = sums.data_ptr()
-    p.out_h, p.out_w, p.ignore_label = out_h, out_w, ignore_label
+    p.out_h, p.out_w, p.ignore_label, p.align_corners = out_h, out_w, ignore_label, int(bool(align_corners))
     _call(L.lib.esn_bilinear_ce, "esn_bilinear_ce", (C.byref(p),), _nbytes(scores) + target.numel() * 8 + _nbytes(ds))
     return sums, ds
 

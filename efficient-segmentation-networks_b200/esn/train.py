@@ -652,12 +652,13 @@ def bilinear_logits(tape, scores, out_h, out_w, logits_dtype=torch.float32, alig
     return logits, holder
 
 
-def bilinear_ce(tape, scores, out_h, out_w, target, weight, ignore_label):
+def bilinear_ce(tape, scores, out_h, out_w, target, weight, ignore_label, align_corners=False):
     """bilinear_logits + CrossEntropyLoss2d + both backward passes as one launch (ops.bilinear_ce): returns (sums, holder) with
     sums = [sum w*nll, sum w] of this rank, or None when the geometry is not taken.  The tape step scales the stored gradient
     by holder["gscale"] (a device scalar: upstream gradient / normaliser, set by _NetLossFn.backward) while converting it to
     the scores' dtype."""
-    res = ops.bilinear_ce(scores.t, target, weight, ignore_label, out_h, out_w, sums=_f32zeros(2, scores.t.device))
+    res = ops.bilinear_ce(scores.t, target, weight, ignore_label, out_h, out_w, sums=_f32zeros(2, scores.t.device),
+                          align_corners=align_corners)
     if res is None:
         return None
     sums, ds = res
@@ -676,28 +677,28 @@ def bilinear_ce(tape, scores, out_h, out_w, target, weight, ignore_label):
     return sums, holder
 
 
-def bilinear_close(tape, scores, out_h, out_w, loss=None):
-    """The close of a training forward whose head is F.interpolate(scores, (H, W), bilinear, align_corners=False): the fp32
+def bilinear_close(tape, scores, out_h, out_w, loss=None, align_corners=False):
+    """The close of a training forward whose head is F.interpolate(scores, (H, W), bilinear, align_corners): the fp32
     NCHW logits -- or, with loss = (target, class weights, ignore label) from a model's fused_loss, the loss sums of
     bilinear_ce.  Returns what _NetFn / _NetLossFn expect from run_forward: (output, tape, holder)."""
     if loss is not None:
-        res = bilinear_ce(tape, scores, out_h, out_w, *loss)
+        res = bilinear_ce(tape, scores, out_h, out_w, *loss, align_corners=align_corners)
         if res is None:
             raise RuntimeError("fused_loss: esn_bilinear_ce does not take %dx%d scores for a %dx%d target"
                                % (scores.t.shape[2], scores.t.shape[3], out_h, out_w))
         return res[0], tape, res[1]
-    logits, holder = bilinear_logits(tape, scores, out_h, out_w, torch.float32)
+    logits, holder = bilinear_logits(tape, scores, out_h, out_w, torch.float32, align_corners=align_corners)
     return logits, tape, holder
 
 
-def fused_bilinear_loss(model, train_forward, input, target, criterion, classes, stride):
+def fused_bilinear_loss(model, train_forward, input, target, criterion, classes):
     """Body of a model's fused_loss(input, target, criterion): criterion(model(input), target) (train.py:351-352) with the
     bilinear head, CrossEntropyLoss2d and both their backward passes as ONE launch (esn_bilinear_ce).  train_forward(model,
-    input, loss=...) is the model's tape forward ending in bilinear_close; stride = the down-sampling factor of its scores.
-    Eval mode, no-grad, any other criterion, or an input that is not a multiple of `stride` take the two-module form."""
+    input, loss=...) is the model's tape forward ending in bilinear_close.  Eval mode, no-grad, any other criterion, more than
+    32 classes or a target that is not (N, H, W) take the two-module form."""
     from utils.losses.loss import fused_head_spec
     spec = fused_head_spec(criterion, input.device, target, classes) if (model.training and torch.is_grad_enabled()) else None
-    if spec is None or input.shape[2] % stride or input.shape[3] % stride or stride % 2 or target.dim() != 3:
+    if spec is None or classes > 32 or target.dim() != 3 or tuple(target.shape[1:]) != tuple(input.shape[2:]):
         return criterion(model(input), target)
     tgt, w, ignore, reduction, distributed = spec
     return run_network_loss(model, lambda x: train_forward(model, x, loss=(tgt, w, ignore)), input, reduction, distributed)

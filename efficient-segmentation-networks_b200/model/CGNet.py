@@ -325,10 +325,10 @@ class CGNet(PrepMixin, nn.Module):
     def fused_loss(self, input, target, criterion):
         """criterion(self(input), target) (train.py:351-352) with the bilinear head (CGNet.py:332), CrossEntropyLoss2d and both
         their backward passes as ONE launch (esn_bilinear_ce); esn.graph.GraphedTrainStep calls this.  Falls back to the
-        two-module form for other criteria, eval mode, or inputs that are not multiples of 8."""
+        two-module form for other criteria and in eval mode."""
         from esn import train as T
         from model._cgnet_train import cgnet_train_forward
-        return T.fused_bilinear_loss(self, cgnet_train_forward, input, target, criterion, self.classifier[-1].conv.out_channels, 8)
+        return T.fused_bilinear_loss(self, cgnet_train_forward, input, target, criterion, self.classifier[-1].conv.out_channels)
 
     def forward(self, input):
         if self.training:

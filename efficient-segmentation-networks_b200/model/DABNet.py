@@ -334,11 +334,11 @@ class DABNet(nn.Module):
     def fused_loss(self, input, target, criterion):
         """criterion(self(input), target) -- train.py:351-352 -- with the bilinear head, CrossEntropyLoss2d and both their
         backward passes as ONE launch (esn_bilinear_ce: the full-resolution logits and their gradient are never written).
-        esn.graph.GraphedTrainStep calls this when the model offers it.  Any other criterion, eval mode, or an input size
-        whose 1/8-resolution scores are not an exact 8x down-sampling takes the two-module form."""
+        esn.graph.GraphedTrainStep calls this when the model offers it.  Any other criterion or eval mode takes the
+        two-module form."""
         from esn import train as T
         from model._dabnet_train import dabnet_train_forward
-        return T.fused_bilinear_loss(self, dabnet_train_forward, input, target, criterion, self.classifier[0].conv.out_channels, 8)
+        return T.fused_bilinear_loss(self, dabnet_train_forward, input, target, criterion, self.classifier[0].conv.out_channels)
 
     @torch.no_grad()
     def predict_mask(self, input, with_logits=False):

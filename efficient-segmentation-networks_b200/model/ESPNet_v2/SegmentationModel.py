@@ -115,6 +115,14 @@ class EESPNet_Seg(PrepMixin, nn.Module):
             ops.conv2d(cat1, P["l1"], out=m1)
         return m1, (h, w)
 
+    def fused_loss(self, input, target, criterion):
+        """criterion(self(input), target) (train.py:351-352) with the final bilinear up-sampling (SegmentationModel.py:76,
+        align_corners=True), CrossEntropyLoss2d and both their backward passes as ONE launch (esn_bilinear_ce).
+        esn.graph.GraphedTrainStep calls this; other criteria and eval mode take the two-module form."""
+        from esn import train as T
+        from model.ESPNet_v2._train import espnetv2_train_forward
+        return T.fused_bilinear_loss(self, espnetv2_train_forward, input, target, criterion, self.project_l1[1].conv.out_channels)
+
     def forward(self, input):
         if self.training:
             # batch-statistics BatchNorm + Dropout2d + recorded backward (esn/train.py); one autograd node for the net

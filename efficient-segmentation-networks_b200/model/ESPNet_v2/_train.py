@@ -85,7 +85,7 @@ def _psp(tape, m, x):
     return _cbr(tape, m.project, cat)
 
 
-def espnetv2_train_forward(model, input):
+def espnetv2_train_forward(model, input, loss=None):
     ops.require_cuda(input, "EESPNet_Seg")
     if input.dtype != torch.float32 or not input.is_contiguous():
         input = input.float().contiguous()
@@ -137,5 +137,5 @@ def espnetv2_train_forward(model, input):
     d1 = T.dropout(tape, cat1, model.project_l1[0].p, per_channel=True)
     scores = T.V(ops.new_act(n, classes, l1.t.shape[2], l1.t.shape[3], dt, dev, c_alloc=32))
     _conv(tape, model.project_l1[1].conv, d1, out=scores)
-    logits, holder = T.bilinear_logits(tape, scores, H, W, torch.float32, align_corners=True)
-    return logits, tape, holder
+    # fp32 logits, or the loss sums of the fused close when called from EESPNet_Seg.fused_loss (esn_bilinear_ce)
+    return T.bilinear_close(tape, scores, H, W, loss, align_corners=True)

@@ -291,6 +291,17 @@ class FastSCNN(nn.Module):
         y = self.feature_fusion(higher, y)
         return self.classifier(y), x.shape[2:]
 
+    def fused_loss(self, input, target, criterion):
+        """criterion(self(input), target) (train.py:351-352) with the bilinear head (FastSCNN.py:233, align_corners=True),
+        CrossEntropyLoss2d and both their backward passes as ONE launch (esn_bilinear_ce): the 2.5 GB of fp32 logits of a
+        16 x 1024 x 2048 batch and their gradient are never written.  esn.graph.GraphedTrainStep calls this; other criteria and
+        eval mode take the two-module form."""
+        if self.aux:
+            return criterion(self(input), target)
+        from esn import train as T
+        from model._fastscnn_train import fastscnn_train_forward
+        return T.fused_bilinear_loss(self, fastscnn_train_forward, input, target, criterion, self.classifier.conv[1].out_channels)
+
     def forward(self, x):
         if self.training:
             # batch-statistics BatchNorm + Dropout + recorded backward (esn/train.py); one autograd node for the net

@@ -35,7 +35,7 @@ def _bottleneck(tape, m, x):
     return T.add(tape, x, y) if m.use_shortcut else y
 
 
-def fastscnn_train_forward(model, input):
+def fastscnn_train_forward(model, input, loss=None):
     ops.require_cuda(input, "FastSCNN")
     if input.dtype != torch.float32 or not input.is_contiguous():
         input = input.float().contiguous()
@@ -81,5 +81,5 @@ def fastscnn_train_forward(model, input):
     classes = cl.conv[1].out_channels
     scores = T.V(ops.new_act(n, classes, y.t.shape[2], y.t.shape[3], dt, dev, c_alloc=32))
     _convT(cl.conv[1]).forward(tape, y, out=scores)
-    logits, holder = T.bilinear_logits(tape, scores, H, W, torch.float32, align_corners=True)
-    return logits, tape, holder
+    # fp32 logits, or the loss sums of the fused close when called from FastSCNN.fused_loss (esn_bilinear_ce)
+    return T.bilinear_close(tape, scores, H, W, loss, align_corners=True)

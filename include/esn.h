@@ -524,11 +524,12 @@ int esn_gate_bcast(const EsnTensor* g, const EsnTensor* x, const EsnTensor* b, c
 
 /* Bilinear up-sampling of low-resolution class scores + weighted cross-entropy + the gradient of the scores, in one pass that
  * never writes a full-resolution tensor: the close of a training iteration of the nets whose head is
- * F.interpolate(scores, input.size()[2:], mode='bilinear', align_corners=False) (DABNet.py:181, FastSCNN.py:233, CGNet,
- * ContextNet, EDANet) under CrossEntropyLoss2d (utils/losses/loss.py:15-32; train.py:351-353).  Replaces esn_head_bilinear ->
+ * F.interpolate(scores, input.size()[2:], mode='bilinear', align_corners=False / True) (DABNet.py:181, CGNet.py:332;
+ * FastSCNN.py:233, ESPNet_v2/SegmentationModel.py:76) under CrossEntropyLoss2d (utils/losses/loss.py:15-32; train.py:351-353).  Replaces esn_head_bilinear ->
  * esn_weighted_ce (forward, backward) -> esn_bilinear_bwd.
  *   scores: NHWC (n, h, w, c <= 32), f32 or bf16;  target: int64 (n, out_h, out_w);  weight: [c] f32 or NULL;
- *   out_h = s h, out_w = s w with one even integer s (2 .. 64): anything else answers ESN_ERR_UNSUPPORTED.
+ *   any out_h, out_w >= 1 and both align_corners modes: source coordinates and weights as ATen's upsample_bilinear2d computes
+ *   them in fp32.
  *   sums[0] += sum_p w[t_p] (lse(logits_p) - logits_p[t_p]),  sums[1] += sum_p w[t_p]   over pixels with t_p in [0, c) and
  *   t_p != ignore_label (fp32 atomics; zeroed by the caller);
  *   dscores: f32 NHWC (n, h, w, c), every lane of its pixel stride written (zeros behind the classes):
@@ -541,7 +542,7 @@ typedef struct EsnBilinearCE {
   EsnTensor dscores;
   int32_t out_h, out_w;
   int32_t ignore_label;
-  int32_t _pad;
+  int32_t align_corners;
 } EsnBilinearCE;
 int esn_bilinear_ce(const EsnBilinearCE* p, void* stream);
 

@@ -316,12 +316,11 @@ def esn_bilinear_ce(ref):
     x = tensor(p.scores).float().contiguous().requires_grad_(True)
     n, c, h, w = x.shape
     H, W = p.out_h, p.out_w
-    assert H % h == 0 and W % w == 0 and H // h == W // w and (H // h) % 2 == 0
     tgt = _buf(p.target, n * H * W, torch.int64, 8).view(n, H, W).clone()
     tgt[(tgt < 0) | (tgt >= c)] = p.ignore_label
     wt = vec(p.weight, c)
     with torch.enable_grad():
-        logits = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=False)
+        logits = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=bool(p.align_corners))
         loss = F.cross_entropy(logits, tgt, wt, ignore_index=p.ignore_label, reduction="sum")
         (g,) = torch.autograd.grad(loss, x)
     valid = tgt != p.ignore_label

@@ -287,8 +287,17 @@ def test_bilinear_ce_wrapper_through_the_abi():
         x = ops.new_act(n, c, h, w, torch.float32, "cpu", c_alloc=32)
         x.copy_(torch.randn(n, c, h, w))
         sums, ds = ops.bilinear_ce(x, tgt, wt, 255, s * h, s * w)
-        assert ops.bilinear_ce(x, tgt[:, :, :40], wt, 255, s * h, 40) is None        # anisotropic scale: declined on the host
+        assert ops.bilinear_ce(x, tgt.int(), wt, 255, s * h, s * w) is None          # int32 target: declined on the host
         assert [nm for nm, _ in calls] == ["esn_bilinear_ce"]
+        # align_corners=True at a non-integer scale (Fast-SCNN's / ESPNetv2's close)
+        tgt2 = torch.randint(0, c, (n, 29, 41))
+        sums2, ds2 = ops.bilinear_ce(x, tgt2, None, 255, 29, 41, align_corners=True)
+    xr2 = x.detach().clone().contiguous().requires_grad_(True)
+    loss2 = F.cross_entropy(F.interpolate(xr2, size=(29, 41), mode="bilinear", align_corners=True), tgt2, reduction="sum")
+    loss2.backward()
+    assert abs(sums2[0].item() - loss2.item()) < 1e-4 * abs(loss2.item()) and _rel(ds2, xr2.grad) < 1e-5
+    with emulate_abi(bf16=False):
+        pass
     xr = x.detach().clone().contiguous().requires_grad_(True)
     loss = F.cross_entropy(F.interpolate(xr, scale_factor=s, mode="bilinear", align_corners=False), tgt, wt, ignore_index=255,
                            reduction="sum")

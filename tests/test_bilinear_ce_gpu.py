@@ -16,24 +16,26 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("align", [False, True])
 @pytest.mark.parametrize("n,c,h,w,s,weighted", [(2, 19, 8, 16, 8, True), (1, 19, 5, 18, 8, True), (2, 11, 7, 33, 4, False),
                                                (1, 19, 4, 4, 16, True), (1, 3, 9, 21, 2, True), (1, 32, 4, 17, 8, True),
-                                               (2, 19, 64, 128, 8, True)])
-def test_bilinear_ce_matches_torch_autograd(dt, n, c, h, w, s, weighted):
+                                               (2, 19, 64, 128, 8, True), (1, 19, 5, 7, (33, 50), True), (1, 19, 9, 9, (9, 9), True),
+                                               (1, 19, 1, 1, (6, 5), True), (1, 19, 12, 20, (7, 31), False)])
+def test_bilinear_ce_matches_torch_autograd(dt, align, n, c, h, w, s, weighted):
     from esn import ops
-    g = torch.Generator(device="cuda").manual_seed(n * 1000 + c * 10 + s)
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + c * 10 + h)
     x = ops.new_act(n, c, h, w, dt, "cuda", c_alloc=32)
     x.copy_(torch.randn(n, c, h, w, device="cuda", generator=g) * 3)
-    H, W = s * h, s * w
+    H, W = (s * h, s * w) if isinstance(s, int) else s        # integer scales, or any output size (incl. down-sampling)
     tgt = torch.randint(0, c, (n, H, W), device="cuda", generator=g)
     tgt[torch.rand(n, H, W, device="cuda", generator=g) < 0.15] = 255          # ignored pixels
     tgt[0, :3, :] = 255                                                          # a whole border strip ignored
     wt = (torch.rand(c, device="cuda", generator=g) + 0.5) if weighted else None
-    res = ops.bilinear_ce(x, tgt, wt, 255, H, W)
+    res = ops.bilinear_ce(x, tgt, wt, 255, H, W, align_corners=align)
     assert res is not None
     sums, ds = res
     xr = x.double().detach().contiguous().requires_grad_(True)
-    logits = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False)
+    logits = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=align)
     loss = F.cross_entropy(logits, tgt, None if wt is None else wt.double(), ignore_index=255, reduction="sum")
     (gr,) = torch.autograd.grad(loss, xr)
     valid = tgt != 255
@@ -46,14 +48,14 @@ def test_bilinear_ce_matches_torch_autograd(dt, n, c, h, w, s, weighted):
     assert pad.numel() == 0 or float(pad.abs().max()) == 0.0                     # the padded lanes are written as zeros
 
 
-def test_bilinear_ce_declines_other_geometries():
+def test_bilinear_ce_declines_what_it_does_not_take():
     from esn import ops
     x = ops.new_act(1, 19, 8, 16, torch.float32, "cuda").normal_()
-    for H, W in ((64, 96), (24, 48), (60, 128)):                                 # anisotropic, odd scale, non-integer scale
-        assert ops.bilinear_ce(x, torch.zeros(1, H, W, dtype=torch.int64, device="cuda"), None, 255, H, W) is None
+    assert ops.bilinear_ce(x, torch.zeros(1, 64, 128, dtype=torch.int32, device="cuda"), None, 255, 64, 128) is None
+    assert ops.bilinear_ce(x, torch.zeros(1, 64, 96, dtype=torch.int64, device="cuda"), None, 255, 64, 128) is None
 
 
-@pytest.mark.parametrize("net", ["DABNet", "CGNet"])
+@pytest.mark.parametrize("net", ["DABNet", "CGNet", "FastSCNN", "ESPNet_v2"])
 @pytest.mark.parametrize("dt", [None, torch.bfloat16])
 def test_fused_loss_equals_the_two_module_form(spec, dt, net):
     """loss and parameter gradients of model.fused_loss (one esn_bilinear_ce launch) against criterion(model(x), y)."""
