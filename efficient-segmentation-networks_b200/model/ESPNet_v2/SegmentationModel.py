@@ -115,13 +115,9 @@ class EESPNet_Seg(PrepMixin, nn.Module):
             ops.conv2d(cat1, P["l1"], out=m1)
         return m1, (h, w)
 
-    def fused_loss(self, input, target, criterion):
-        """criterion(self(input), target) (train.py:351-352) with the final bilinear up-sampling (SegmentationModel.py:76,
-        align_corners=True), CrossEntropyLoss2d and both their backward passes as ONE launch (esn_bilinear_ce).
-        esn.graph.GraphedTrainStep calls this; other criteria and eval mode take the two-module form."""
-        from esn import train as T
-        from model.ESPNet_v2._train import espnetv2_train_forward
-        return T.fused_bilinear_loss(self, espnetv2_train_forward, input, target, criterion, self.project_l1[1].conv.out_channels)
+    # No fused_loss here: the scores are at 1/2 resolution, and esn_bilinear_ce maps 8 lanes to the rows of a source cell -- at an
+    # up-sampling factor of 2 a quarter of them work and the fused close takes as long as the launches it replaces (measured:
+    # 160.8 against 161.4 ms per step).  It pays from a factor of 4 (DABNet, CGNet, Fast-SCNN: 8).
 
     def forward(self, input):
         if self.training:
