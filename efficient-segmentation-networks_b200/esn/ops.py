@@ -82,6 +82,12 @@ def _call(fn, name, arg_refs, alg_bytes=0, flops=0, tag="", allow_unsupported=Fa
 def require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError("%s: tensors must live on a CUDA device; this framework has no CPU path" % what)
+    # the C side launches on the CURRENT device and on torch's current stream of it (esn_current_device, stream()): a tensor
+    # on another device would be read through a stale peer mapping or fault -- one process per GPU, or torch.cuda.device(...)
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise RuntimeError("%s: tensor lives on cuda:%d but the current device is cuda:%d; wrap the call in "
+                           "torch.cuda.device(tensor.device) (one process per GPU is the supported form)"
+                           % (what, t.device.index, torch.cuda.current_device()))
 
 
 def widen(t, c):

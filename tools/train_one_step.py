@@ -20,15 +20,16 @@ m = build_model(name, 19)
 m.load_state_dict(bench.fixture_state_dict(name))
 m = m.cuda().train()
 crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
-opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=1e-4, fused=True)
+from esn.optim import Adam  # noqa: E402  (train.py:212-215's torch.optim.Adam as one launch; what bench.py steps)
+opt = Adam(m.parameters(), lr=5e-4, weight_decay=1e-4)
 x = fixture.make_input(batch, H, W).cuda()
 y = fixture.make_labels(batch, H, W, 19).cuda()
 
 
 def step():
     opt.zero_grad(set_to_none=True)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        loss = crit(m(x), y)
+    with torch.autocast("cuda", dtype=torch.bfloat16):     # the iteration esn.graph.GraphedTrainStep captures
+        loss = m.fused_loss(x, y, crit) if hasattr(m, "fused_loss") else crit(m(x), y)
     loss.backward()
     opt.step()
     return loss
