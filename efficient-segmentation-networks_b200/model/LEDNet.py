@@ -209,9 +209,7 @@ class LEDNet(nn.Module):
     def _scores(self, input):
         ops.require_cuda(input, "LEDNet")
         _no_train(self)
-        if (input.shape[2] | input.shape[3]) % 8:
-            raise NotImplementedError("LEDNet: input height and width must be multiples of 8, got %dx%d"
-                                      % (input.shape[2], input.shape[3]))
+        # any input size: the DownsamplerBlock pads like the reference's (LEDNet.py:84-88), the pyramid rounds its levels itself
         output = self.initial_block(input)
         for layer in self.layers:
             output = layer(output)

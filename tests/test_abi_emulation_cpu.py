@@ -308,6 +308,17 @@ def test_bilinear_ce_wrapper_through_the_abi():
 
 
 @pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
+def test_lednet_odd_input_sizes_through_the_abi(size, spec, golden):
+    """LEDNet.py:76-96 + 245-264 on odd sizes, fp32 against the reference's golden (bf16: the attention pyramid is
+    ill-conditioned with random weights, tests/test_zz_widening_gpu.py)."""
+    m = _model("LEDNet", spec)
+    ref = torch.from_numpy(golden("oddsize")["LEDNet_%dx%dx%d_logits" % size])
+    with emulate_abi() as calls, torch.no_grad():
+        y = m(fixture.make_input(*size))
+    assert y.shape == ref.shape and _rel(y.float(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
 @pytest.mark.parametrize("bf16", [False, True])
 def test_esnet_odd_input_sizes_through_the_abi(size, bf16, spec, golden):
     """ESNet.py:22-29: odd heights / widths.  The stride-2 conv of the block takes the direct kernel, the pool kernel writes

@@ -31,15 +31,18 @@ def test_eval_forward_matches_reference(name, spec, golden):
     assert (nets.argmax_mask(y) == g["eval_2x128x256_argmax"]).mean() > 0.9999
 
 
+@pytest.mark.parametrize("name", ["ESNet", "LEDNet"])
 @pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
-def test_esnet_odd_sizes_match_reference(size, spec, golden):
-    """The F.pad path of ESNet's DownsamplerBlock (model/ESNet.py:22-29): inputs that are odd at one or more levels; the logits
-    have 8 * ceil(ceil(ceil(H / 2) / 2) / 2) rows (tools/make_golden_oddsize.py, unmodified reference)."""
+def test_odd_sizes_match_reference(name, size, spec, golden):
+    """The F.pad path of ESNet's / LEDNet's DownsamplerBlock (model/ESNet.py:22-29, LEDNet.py:76-96): inputs that are odd at one or
+    more levels.  ESNet's logits have 8 * ceil(ceil(ceil(H / 2) / 2) / 2) rows, LEDNet interpolates back to the input size
+    (tools/make_golden_oddsize.py, unmodified reference)."""
     n, h, w = size
-    ref = torch.from_numpy(golden("oddsize")["ESNet_%dx%dx%d_logits" % size])
+    ref = torch.from_numpy(golden("oddsize")["%s_%dx%dx%d_logits" % ((name,) + size)])
     with torch.no_grad():
-        y = nets.forward("ESNet", spec_state_dict(spec, "ESNet"), fixture.make_input(n, h, w))
-    assert y.shape == ref.shape == (n, 19, 8 * -(-(-(-(-(-h // 2)) // 2)) // 2), 8 * -(-(-(-(-(-w // 2)) // 2)) // 2))
+        y = nets.forward(name, spec_state_dict(spec, name), fixture.make_input(n, h, w))
+    up = lambda v: 8 * -(-(-(-(-(-v // 2)) // 2)) // 2)
+    assert y.shape == ref.shape == ((n, 19, up(h), up(w)) if name == "ESNet" else (n, 19, h, w))
     assert (y - ref).norm() / ref.norm() < 1e-5
 
 

@@ -239,3 +239,19 @@ def test_esnet_odd_input_sizes(size, spec, golden):
     assert T._rel(y16.float().cpu(), ref) < 5e-2
     assert torch.equal(mask.cpu().long(), y16.float().cpu().argmax(1)) or \
         (mask.cpu().long() == y16.float().cpu().argmax(1)).float().mean().item() > 0.995     # fp32 accumulators vs bf16-rounded logits
+
+
+@pytest.mark.parametrize("size", [(1, 51, 77), (2, 36, 50), (1, 33, 64)])
+def test_lednet_odd_input_sizes(size, spec, golden):
+    """LEDNet on inputs that are odd at one or more levels (LEDNet.py:76-96, 245-264): fp32 logits against the unmodified
+    reference; the bf16 path runs and stays finite (its accuracy is bounded stage by stage above)."""
+    n, h, w = size
+    m = T._model("LEDNet", spec)
+    ref = torch.from_numpy(golden("oddsize")["LEDNet_%dx%dx%d_logits" % size])
+    x = fixture.make_input(n, h, w).cuda()
+    with torch.no_grad():
+        y = m(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            mask = m.predict_mask(x)
+    assert y.shape == ref.shape and T._rel(y.cpu(), ref) < 1e-3
+    assert mask.shape == (n, h, w) and mask.dtype == torch.uint8 and int(mask.max()) < 19
