@@ -26,13 +26,6 @@ class GraphedTrainStep:
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (there is no CPU path)")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
-        # Flat gradient buckets also on ONE GPU (no collective is launched at world size 1): the tape hands out weight gradients in
-        # its kernels' [tap][Cout][Cin] order, and without buckets autograd re-lays every one of them with its own copy kernel
-        # (61 launches, 0.11 ms of a DABNet step); a bucket is packed by one multi-tensor copy and its views are the .grad tensors
-        import os
-        if "_esn_buckets" not in model.__dict__ and os.environ.get("ESN_NO_LOCAL_BUCKETS") != "1":
-            from . import parallel
-            parallel.data_parallel(model)
         self.autocast_dtype = autocast_dtype
         self.fuse_loss = fuse_loss
         self.images = images.clone()
