@@ -824,6 +824,8 @@ int conv_umma_impl(const EsnConv* p, const EsnConvDual* dual, void* stream) {
     KB = Cin;
   else if (Cin % 64 == 0)
     KB = 64;
+  else if (Cin % 32 == 0)
+    KB = 32;       // 96 / 160-channel inputs (Fast-SCNN's 64 -> 96 -> 128 bottlenecks, FastSCNN.py:134): 64-byte swizzled K blocks
   else
     return ESN_ERR_UNSUPPORTED;
   const int nkb = Cin / KB;

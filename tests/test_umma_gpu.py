@@ -30,6 +30,15 @@ CASES = [
     ("convT_128_64", 128, 64, 3, 2, 1, 1, True, 1, 2, 8, 24),
     ("convT_64_16", 64, 16, 3, 2, 1, 1, True, 1, 2, 12, 130),
     ("1x1_64_29", 64, 29, 1, 1, 0, 1, False, 0, 2, 9, 33),
+    # inputs of 96 / 160 channels: three / five 32-channel K blocks (64-byte swizzle)
+    ("1x1_96_256", 96, 256, 1, 1, 0, 1, False, 0, 2, 16, 64),
+    ("1x1_96_128", 96, 128, 1, 1, 0, 1, False, 0, 1, 9, 130),
+    ("1x1_96_64", 96, 64, 1, 1, 0, 1, False, 0, 2, 8, 256),
+    ("3x3_96_32", 96, 32, 3, 1, 1, 1, False, 0, 2, 12, 40),
+    ("1x3_96_96_w256", 96, 96, (1, 3), 1, (0, 1), (1, 1), False, 0, 1, 6, 256),
+    ("3x1_96_96", 96, 96, (3, 1), 1, (1, 0), (1, 1), False, 0, 1, 21, 128),
+    ("1x1_160_48", 160, 48, 1, 1, 0, 1, False, 0, 1, 10, 96),
+    ("3x3s2_96_64", 96, 64, 3, 2, 1, 1, False, 0, 1, 16, 64),
     # tap-reuse modes (row tiles): shifted-window descriptors on 32B / 64B / 128B swizzled tiles
     ("h_1x3_16_w512", 16, 16, (1, 3), 1, (0, 1), (1, 1), False, 0, 2, 6, 512),
     ("h_1x3_16_w640", 16, 16, (1, 3), 1, (0, 1), (1, 1), False, 0, 1, 5, 640),
