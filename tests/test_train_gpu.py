@@ -336,7 +336,7 @@ def test_pool_bilinear_ce_backward():
     assert _rel(lg2.grad, gref) < 1e-5
 
 
-def _train_step(name, spec, dtype):
+def _train_step(name, spec, dtype, batch=2):
     from builders.model_builder import build_model
     from utils.losses.loss import CrossEntropyLoss2d
     m = build_model(name, 19)
@@ -345,8 +345,8 @@ def _train_step(name, spec, dtype):
     for mod in m.modules():           # the golden gradients were produced with dropout off
         if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
             mod.p = 0.0
-    x = fixture.make_input(2, 64, 128).cuda()
-    lab = fixture.make_labels(2, 64, 128, 19).cuda()
+    x = fixture.make_input(batch, 64, 128).cuda()
+    lab = fixture.make_labels(batch, 64, 128, 19).cuda()
     crit = CrossEntropyLoss2d(weight=torch.tensor(fixture.CLASS_WEIGHTS), ignore_label=255).cuda()
     if dtype == torch.bfloat16:
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -441,6 +441,13 @@ def test_training_matches_reference_fp64(spec, golden, dtype, net):
                 print("   full-tensor rel-L2 %-50s %.3e   (torch fp32 autograd: %.3e)" % (k, err, err_t))
                 assert err < max(gtol, 2.0 * err_t), (k, err, err_t)
         return
+    if net == "FastSCNN":
+        # At batch 2 the 1x1 level of Fast-SCNN's pyramid pooling normalises TWO values per channel: its train-mode BatchNorm
+        # is sign(a - b), so a last-bit difference of any upstream rounding (which conv runs on which tensor-core route) flips
+        # channels and moves every gradient of the net by O(1) -- for torch's autocast as for us, a coin toss per build
+        # (DESIGN 4.5).  The gradient distribution is therefore checked at batch 4, where that level is a continuous function,
+        # against the oracle in fp64 on the device (the oracle's train mode is pinned on the golden by the fp32 case above).
+        return _bf16_gradients_vs_oracle_fp64(net, spec, batch=4)
     # bf16: the tolerance is the reference's own bf16 noise.  Run the reference arithmetic (oracle port)
     # under torch bf16 autocast on the same fixture and require our error distribution to be no worse.
     from oracle import nets
@@ -463,6 +470,50 @@ def test_training_matches_reference_fp64(spec, golden, dtype, net):
     print("   torch bf16-autocast on the same graph: median %.3e p90 %.3e worst %.3e" % (r_med, r_p90, ref_errs[-1]))
     assert med < 1.5 * r_med + 1e-3, (med, r_med)
     assert p90 < 1.5 * r_p90 + 1e-3, (p90, r_p90)
+
+
+def _bf16_gradients_vs_oracle_fp64(net, spec, batch):
+    """Per-tensor gradient-norm errors of our bf16 step and of torch's bf16 autocast of the oracle graph, both against the
+    oracle in fp64 on the same batch: ours must be no worse at the median and the 90 % quantile."""
+    from oracle import nets
+    m, _, loss = _train_step(net, spec, torch.bfloat16, batch=batch)
+    x = fixture.make_input(batch, 64, 128).cuda()
+    lab = fixture.make_labels(batch, 64, 128, 19).cuda()
+    wt = torch.tensor(fixture.CLASS_WEIGHTS, device="cuda")
+
+    def oracle(dtype, autocast):
+        sd = {k: ((v.cuda().to(dtype).requires_grad_(True)) if v.is_floating_point() else v.cuda())
+              for k, v in spec_state_dict(spec, net).items()}
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = nets.forward(net, sd, x, train=True)
+                l = F.cross_entropy(y.float(), lab, wt, ignore_index=255)
+        else:
+            y = nets.forward(net, sd, x.to(dtype), train=True)
+            l = F.cross_entropy(y, lab, wt.to(dtype), ignore_index=255)
+        l.backward()
+        return sd, l.item()
+
+    sd64, l64 = oracle(torch.float64, False)
+    sd16, l16 = oracle(torch.float32, True)
+    named = dict(m.named_parameters())
+    ours, theirs = [], []
+    for k, p in named.items():
+        g64 = sd64[k].grad
+        if g64 is None or g64.norm().item() < 1e-10 * max(sd64[k].norm().item(), 1e-30):
+            continue
+        gn = g64.norm().item()
+        ours.append(abs(p.grad.double().norm().item() - gn) / gn)
+        theirs.append(abs(sd16[k].grad.double().norm().item() - gn) / gn)
+    ours.sort()
+    theirs.sort()
+    q = lambda v, f: v[int(f * len(v))]
+    print("%s bf16 at batch %d: loss %.6f (fp64 %.6f, autocast %.6f); per-tensor grad-norm error vs the fp64 oracle: median %.3e p90 "
+          "%.3e | torch bf16-autocast: median %.3e p90 %.3e (%d tensors)"
+          % (net, batch, loss.item(), l64, l16, q(ours, 0.5), q(ours, 0.9), q(theirs, 0.5), q(theirs, 0.9), len(ours)))
+    assert abs(loss.item() - l64) / l64 < max(2e-2, 1.5 * abs(l16 - l64) / l64)
+    assert q(ours, 0.5) < 1.5 * q(theirs, 0.5) + 1e-3, (q(ours, 0.5), q(theirs, 0.5))
+    assert q(ours, 0.9) < 1.5 * q(theirs, 0.9) + 1e-3, (q(ours, 0.9), q(theirs, 0.9))
 
 
 def test_resize_pool_dropout_backward():
