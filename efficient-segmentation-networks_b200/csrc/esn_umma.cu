@@ -826,6 +826,8 @@ int conv_umma_impl(const EsnConv* p, const EsnConvDual* dual, void* stream) {
     KB = 64;
   else if (Cin % 32 == 0)
     KB = 32;       // 96 / 160-channel inputs (Fast-SCNN's 64 -> 96 -> 128 bottlenecks, FastSCNN.py:134): 64-byte swizzled K blocks
+  else if (Cin % 16 == 0)
+    KB = 16;       // 48 / 80 / 112 ...: 32-byte swizzled K blocks (Fast-SCNN's 32 -> 48 -> 64 learning-to-downsample stage)
   else
     return ESN_ERR_UNSUPPORTED;
   const int nkb = Cin / KB;

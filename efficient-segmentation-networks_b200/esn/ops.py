@@ -552,7 +552,7 @@ def conv_pair(x, p1, p2, out=None, residual=None):
 def umma_supported(prep, p):
     """Mirror of esn_conv2d_umma's shape gate (csrc/esn_umma.cu) so routing costs no failed call."""
     cin = prep.cin
-    if not (cin in (16, 32, 64) or cin % 32 == 0) or prep.cout_pad > 256:
+    if cin % 16 or prep.cout_pad > 256:
         return False
     if prep.kh * prep.kw > 9 or prep.stride not in (1, 2):
         return False
@@ -565,7 +565,7 @@ def umma_supported(prep, p):
     if p.ep.residual.ptr and (p.ep.residual.c_stride % 8 or p.ep.residual.ptr % 16 or p.ep.residual.dtype != L.ESN_BF16):
         return False
     taps = prep.kh * prep.kw if not prep.transposed else 4
-    kb = cin if cin in (16, 32, 64) else (64 if cin % 64 == 0 else 32)     # K block of the kernel (esn_umma.cu)
+    kb = 64 if cin % 64 == 0 else (32 if cin % 32 == 0 else 16)            # K block of the kernel (esn_umma.cu)
     mt = 64 // kb
     while mt > 1 and mt * prep.cout_pad > 256:
         mt //= 2

@@ -39,6 +39,12 @@ CASES = [
     ("3x1_96_96", 96, 96, (3, 1), 1, (1, 0), (1, 1), False, 0, 1, 21, 128),
     ("1x1_160_48", 160, 48, 1, 1, 0, 1, False, 0, 1, 10, 96),
     ("3x3s2_96_64", 96, 64, 3, 2, 1, 1, False, 0, 1, 16, 64),
+    # 48 / 80 / 112 channels: 16-channel K blocks (32-byte swizzle)
+    ("1x1_48_64", 48, 64, 1, 1, 0, 1, False, 0, 2, 16, 128),
+    ("1x1_48_32", 48, 32, 1, 1, 0, 1, False, 0, 1, 9, 130),
+    ("3x3_48_48", 48, 48, 3, 1, 1, 1, False, 0, 1, 12, 40),
+    ("1x3_80_80_w256", 80, 80, (1, 3), 1, (0, 1), (1, 1), False, 0, 1, 6, 256),
+    ("1x1_112_16", 112, 16, 1, 1, 0, 1, False, 0, 1, 10, 96),
     # tap-reuse modes (row tiles): shifted-window descriptors on 32B / 64B / 128B swizzled tiles
     ("h_1x3_16_w512", 16, 16, (1, 3), 1, (0, 1), (1, 1), False, 0, 2, 6, 512),
     ("h_1x3_16_w640", 16, 16, (1, 3), 1, (0, 1), (1, 1), False, 0, 1, 5, 640),
