@@ -868,20 +868,21 @@ def _scale_nc(src, mask, residual=None, out=None):
     return out
 
 
-def dropout(tape, x, p, per_channel=False, training=True, residual=None):
+def dropout(tape, x, p, per_channel=False, training=True, residual=None, c_alloc=None):
     """nn.Dropout (element-wise) / nn.Dropout2d (per (n, c) plane); with `residual` (a V) the result is dropout(x) + residual in
     the same pass (ERFNet's `output + input`, ERFNet.py:62-65).  Element-wise: the keep mask is regenerated from the seed in
     backward.  Per plane: the N x C scale factors (0 or 1 / (1 - p)) are drawn once into a small table and forward / backward
     are one per-plane scaling each -- the per-element kernel hashed every element (62 us per ERFNet block on a 17 MB tensor).
     The seed is drawn from torch's CPU generator, so torch.manual_seed makes runs repeatable; the iteration counter lives on
-    the device, so CUDA-graph replays draw new masks."""
+    the device, so CUDA-graph replays draw new masks.  c_alloc: pixel stride of the output buffer, zero behind the channels (for a
+    consumer that reads a zero-padded channel count on the tensor cores); per-element path only."""
     if not training or p <= 0.0:
         return x if residual is None else add(tape, x, residual)
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) + _DROPOUT_CALLS[0]
     _DROPOUT_CALLS[0] += 1
     n, c, h, w = x.t.shape
-    def apply(src):
-        dst = ops.new_act(n, c, h, w, src.dtype, src.device)
+    def apply(src, pad=None):
+        dst = ops.new_act(n, c, h, w, src.dtype, src.device, c_alloc=pad, zero=bool(pad) and pad != c)
         a, b = ops.tdesc(src), ops.tdesc(dst)
         ops._call(L.lib.esn_dropout_step, "esn_dropout", (C.byref(a), C.byref(b), C.c_uint64(seed),
                                                           C.c_void_p(ops.step_counter(src.device).data_ptr()), C.c_float(p),
@@ -914,7 +915,7 @@ def dropout(tape, x, p, per_channel=False, training=True, residual=None):
         tape.push(bwd_nc)
         return y
 
-    y = V(apply(x.t))
+    y = V(apply(x.t, c_alloc))
 
     def bwd():
         g = apply(y.g)

@@ -18,6 +18,21 @@ def _convT(conv):
     return t
 
 
+def _conv_padded(tape, conv, x, cin_pad, classes):
+    """1x1 conv onto `classes` scores over a zero-padded input width, on the tensor cores in all three directions (forward,
+    input gradient, weight gradient): x lives in a buffer cin_pad channels wide with a zero tail, the result in a 32-channel
+    one (zero weight rows) of which the first `classes` are the scores.  The CUDA-core kernel ran these odd-channel convs
+    (147 -> 19, 51 -> 19 and their input gradients at 1/4 and 1/2 resolution) at 1.8-3.9 TFLOP/s: 24 of 161 ms per step."""
+    t = conv.__dict__.get("_esn_T_pad")
+    if t is None or t.cin_pad != cin_pad:
+        t = T.ConvT(conv, cin_pad, 32)
+        conv.__dict__["_esn_T_pad"] = t
+    n, _, h, w = x.t.shape
+    wide = T.V(ops.new_act(n, 32, h, w, x.t.dtype, x.t.device))
+    t.forward(tape, x, out=wide)
+    return wide.slice(0, classes)
+
+
 def _conv(tape, conv, x, out=None, need_dx=True, dtype=None):
     t = _convT(conv)
     if isinstance(t, T.GroupedConvT):
@@ -112,8 +127,13 @@ def espnetv2_train_forward(model, input, loss=None):
     for layer in net.level4:
         l4 = _eesp(tape, layer, l4)
 
-    def cat_buffer(c, like):
-        return T.V(ops.new_act(n, c, like.t.shape[2], like.t.shape[3], dt, dev, c_alloc=(c + 7) // 8 * 8, zero=True))
+    def cat_buffer(c, like, c_alloc=None):
+        return T.V(ops.new_act(n, c, like.t.shape[2], like.t.shape[3], dt, dev, c_alloc=c_alloc or (c + 7) // 8 * 8, zero=True))
+
+    pad16 = lambda c: (c + 15) // 16 * 16
+    # bf16: the two odd-channel 1x1 convs onto the class scores run over zero-padded widths on the tensor cores
+    tc_head = dt == torch.bfloat16 and model.project_l2.conv.bias is None and model.project_l1[1].conv.bias is None \
+        and model.project_l2.conv.kernel_size == (1, 1) and model.project_l1[1].conv.kernel_size == (1, 1)
 
     c3 = l3.t.shape[1]
     cat3 = cat_buffer(2 * c3, l3)
@@ -125,17 +145,26 @@ def espnetv2_train_forward(model, input, loss=None):
     classes = s3.t.shape[1]
 
     c2 = l2.t.shape[1]
-    cat2 = cat_buffer(c2 + classes, l2)
+    tc_head = tc_head and classes <= 32 and model.project_l2.conv.out_channels == classes
+    cat2 = cat_buffer(c2 + classes, l2, pad16(c2 + classes) if tc_head else None)
     T.copy_into(tape, l2, cat2.slice(0, c2))
     T.bilinear(tape, s3, l2.t.shape[2], l2.t.shape[3], True, out=cat2.slice(c2, c2 + classes))
-    m2 = _cbr(tape, model.project_l2, cat2)
+    if tc_head:
+        m2 = _br(tape, model.project_l2, _conv_padded(tape, model.project_l2.conv, cat2, pad16(c2 + classes), classes))
+    else:
+        m2 = _cbr(tape, model.project_l2, cat2)
 
     c1 = l1.t.shape[1]
     cat1 = cat_buffer(c1 + classes, l1)
     T.copy_into(tape, l1, cat1.slice(0, c1))
     T.bilinear(tape, m2, l1.t.shape[2], l1.t.shape[3], True, out=cat1.slice(c1, c1 + classes))
-    d1 = T.dropout(tape, cat1, model.project_l1[0].p, per_channel=True)
-    scores = T.V(ops.new_act(n, classes, l1.t.shape[2], l1.t.shape[3], dt, dev, c_alloc=32))
-    _conv(tape, model.project_l1[1].conv, d1, out=scores)
+    if tc_head and model.project_l1[0].p > 0.0 and (c1 + classes) % 4:
+        # (the per-element dropout path, taken for channel counts that are not multiples of 4, can write a padded buffer)
+        d1 = T.dropout(tape, cat1, model.project_l1[0].p, per_channel=True, c_alloc=pad16(c1 + classes))
+        scores = _conv_padded(tape, model.project_l1[1].conv, d1, pad16(c1 + classes), classes)
+    else:
+        d1 = T.dropout(tape, cat1, model.project_l1[0].p, per_channel=True)
+        scores = T.V(ops.new_act(n, classes, l1.t.shape[2], l1.t.shape[3], dt, dev, c_alloc=32))
+        _conv(tape, model.project_l1[1].conv, d1, out=scores)
     # fp32 logits, or the loss sums of the fused close when called from EESPNet_Seg.fused_loss (esn_bilinear_ce)
     return T.bilinear_close(tape, scores, H, W, loss, align_corners=True)
