@@ -114,6 +114,38 @@ __global__ void __launch_bounds__(128) avgpool3x3s2_bwd_kernel(const T* __restri
   st1<T>(p, acc);
 }
 
+// the same for bf16 tensors on 16-byte channel vectors: a thread owns eight channels of one input pixel and gathers the (up to
+// four) windows that contain it with 16-byte loads.  The scalar kernel above ran ESPNetv2's seven down-sampler gradients at
+// 0.2 TB/s (9.9 ms of its training step).
+__global__ void __launch_bounds__(256) avgpool3x3s2_bwd_v8_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                                  long long total, int C8, int H, int W, int Ho, int Wo, int dy_cs,
+                                                                  int dx_cs, int accumulate) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % C8);
+  const long long pix = idx / C8;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const long long n = pix / ((long long)W * H);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {          // windows [2ho-1, 2ho+1] containing h
+    if (ho >= Ho) continue;
+    for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+      if (wo >= Wo) continue;
+      float t[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(dy + ((size_t)(n * Ho + ho) * Wo + wo) * dy_cs) + cv), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
+  }
+  uint4* p = reinterpret_cast<uint4*>(dx + (size_t)pix * dx_cs) + cv;
+  float prev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (accumulate) bf16x8_to_float(*p, prev);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = acc[j] * (1.f / 9.f) + prev[j];
+  *p = float_to_bf16x8(acc);
+}
+
 // ---- dropout (element-wise nn.Dropout or per-(n, c) nn.Dropout2d): counter-based hash, so the backward
 // pass regenerates the mask from the seed instead of storing it
 __device__ __forceinline__ uint32_t mix32(uint64_t x) {
@@ -218,6 +250,15 @@ extern "C" int esn_avgpool3x3s2_bwd(const EsnTensor* dy, const EsnTensor* dx, in
   const long long total = (long long)dx->n * dx->h * dx->w * dx->c;
   const int grid = esn_cdiv(total, 128);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dx->dtype == ESN_BF16 && dx->c % 8 == 0 && dx->c_stride % 8 == 0 && dy->c_stride % 8 == 0 &&
+      ((uintptr_t)dx->ptr % 16) == 0 && ((uintptr_t)dy->ptr % 16) == 0 && total / 8 < 0x7fffffffLL * 256) {
+    const long long tv = total / 8;
+    avgpool3x3s2_bwd_v8_kernel<<<esn_cdiv(tv, 256), 256, 0, st>>>((const __nv_bfloat16*)dy->ptr, (__nv_bfloat16*)dx->ptr, tv,
+                                                                  dx->c / 8, dx->h, dx->w, dy->h, dy->w, dy->c_stride, dx->c_stride,
+                                                                  accumulate);
+    ESN_CHECK_LAUNCH();
+    return ESN_OK;
+  }
   if (dx->dtype == ESN_F32)
     avgpool3x3s2_bwd_kernel<float><<<grid, 128, 0, st>>>((const float*)dy->ptr, (float*)dx->ptr, dx->n, dx->c, dx->h, dx->w, dy->h,
                                                          dy->w, dy->c_stride, dx->c_stride, accumulate);

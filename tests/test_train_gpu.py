@@ -593,6 +593,23 @@ def test_grouped_conv_and_avgpool_backward():
         y._g = _nhwc(gy, torch.float32, ops)
         tape.backward()
         assert _rel(xv.g, gx) < 1e-5, (h, w)
+    # bf16 on 16-byte channel vectors (the vector kernel), written and accumulated into an existing gradient
+    import ctypes as C
+    from esn import _lib as L
+    for (n_, c_, h, w) in ((2, 32, 9, 14), (1, 64, 16, 16), (3, 8, 1, 5)):
+        x = torch.randn(n_, c_, h, w, device="cuda", requires_grad=True)
+        ref = F.avg_pool2d(x, 3, 2, 1)
+        gy = torch.randn_like(ref).to(torch.bfloat16).float()
+        gx, = torch.autograd.grad(ref, x, gy)
+        dy = _nhwc(gy, torch.bfloat16, ops)
+        for acc in (0, 1):
+            dx = ops.new_act(n_, c_, h, w, torch.bfloat16, "cuda")
+            prev = torch.randn(n_, c_, h, w, device="cuda").to(torch.bfloat16)
+            dx.copy_(prev)
+            a, b = ops.tdesc(dy), ops.tdesc(dx)
+            ops._call(L.lib.esn_avgpool3x3s2_bwd, "esn_avgpool3x3s2_bwd", (C.byref(a), C.byref(b), acc))
+            want = gx + (prev.float() if acc else 0.0)
+            assert (dx.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item(), (n_, c_, h, w, acc)
 
 
 @pytest.mark.parametrize("net", ["DABNet", "FastSCNN"])
