@@ -533,6 +533,24 @@ def test_resize_pool_dropout_backward():
         y._g = _nhwc(gy, torch.float32, ops)
         tape.backward()
         assert _rel(xv.g, gx) < 1e-5, (align, hi, wi)
+    # the same gradients in bf16 on 16-byte channel vectors (the vector kernel), written and accumulated
+    import ctypes as C
+    from esn import _lib as L
+    for align, (hi, wi, ho, wo) in ((True, (4, 8, 16, 32)), (False, (5, 7, 13, 20)), (True, (1, 1, 4, 8)), (True, (16, 32, 32, 64)),
+                                    (False, (9, 9, 18, 18))):
+        x = torch.randn(2, 24, hi, wi, device="cuda").requires_grad_(True)
+        ref = F.interpolate(x, (ho, wo), mode="bilinear", align_corners=align)
+        gy = torch.randn_like(ref).to(torch.bfloat16).float()
+        gx, = torch.autograd.grad(ref, x, gy)
+        dy = _nhwc(gy, torch.bfloat16, ops)
+        for acc in (0, 1):
+            dx = ops.new_act(2, 24, hi, wi, torch.bfloat16, "cuda")
+            prev = torch.randn(2, 24, hi, wi, device="cuda").to(torch.bfloat16)
+            dx.copy_(prev)
+            a, b = ops.tdesc(dy), ops.tdesc(dx)
+            ops._call(L.lib.esn_bilinear_bwd_nhwc, "esn_bilinear_bwd_nhwc", (C.byref(a), C.byref(b), int(align), acc))
+            want = gx + (prev.float() if acc else 0.0)
+            assert (dx.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item(), (align, hi, wi, acc)
     for size, (h, w) in ((1, (4, 8)), (2, (4, 8)), (3, (4, 8)), (6, (4, 8)), (3, (7, 10))):
         x = torch.randn(2, 16, h, w, device="cuda").requires_grad_(True)
         ref = F.adaptive_avg_pool2d(x, size)
