@@ -67,3 +67,43 @@ def test_tables_cover_every_element_once_and_reproduce_torch_adam():
     for i, p in enumerate(ours):
         assert offs[i] % 4 == 0
         assert torch.allclose(m[offs[i]:offs[i] + p.numel()].view_as(p), opt.state[theirs[i]]["exp_avg"], atol=1e-6)
+
+
+def test_adam_constructor_mirrors_torch_and_has_no_cpu_path():
+    """Same argument checks as torch.optim.Adam (train.py:212-215 builds it with lr, betas, eps, weight_decay); amsgrad /
+    maximize are not on the path; stepping CPU parameters raises (the product has no CPU path)."""
+    import pytest
+    from esn.optim import Adam
+    p = [torch.nn.Parameter(torch.randn(4, 3))]
+    opt = Adam(p, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    g = opt.param_groups[0]
+    assert (g["lr"], g["betas"], g["eps"], g["weight_decay"]) == (5e-4, (0.9, 0.999), 1e-8, 1e-4)
+    assert isinstance(opt, torch.optim.Optimizer) and opt.state_dict()["state"] == {}
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda i: 0.5 ** i)      # the reference's per-iteration schedulers attach
+    assert sched.get_last_lr() == [5e-4]
+    for bad in (dict(lr=-1.0), dict(eps=-1.0), dict(betas=(1.0, 0.999)), dict(betas=(0.9, -0.1)), dict(weight_decay=-1.0)):
+        with pytest.raises(ValueError):
+            Adam(p, **bad)
+    for unsupported in (dict(amsgrad=True), dict(maximize=True)):
+        with pytest.raises(NotImplementedError):
+            Adam(p, **unsupported)
+    p[0].grad = torch.randn(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        opt.step()
+
+
+def test_fused_head_spec_only_for_the_plain_weighted_ce():
+    """model.fused_loss takes the fused close only for CrossEntropyLoss2d itself; focal / OHEM criteria keep the two-module
+    form (utils/losses/loss.py)."""
+    from utils.losses.loss import CrossEntropyLoss2d, FocalLoss2d, ProbOhemCrossEntropy2d, fused_head_spec
+    tgt = torch.randint(0, 19, (1, 8, 8)).to(torch.uint8)
+    w = torch.rand(19)
+    spec = fused_head_spec(CrossEntropyLoss2d(weight=w, ignore_label=255, reduction="sum", distributed=False), torch.device("cpu"), tgt, 19)
+    t, wt, ignore, reduction, distributed = spec
+    assert t.dtype == torch.int64 and torch.equal(wt, w) and (ignore, reduction, distributed) == (255, "sum", False)
+    assert fused_head_spec(FocalLoss2d(), torch.device("cpu"), tgt, 19) is None
+    assert fused_head_spec(ProbOhemCrossEntropy2d(), torch.device("cpu"), tgt, 19) is None
+
+    class Sub(CrossEntropyLoss2d):      # a subclass may change forward: no fused form is assumed for it
+        pass
+    assert fused_head_spec(Sub(), torch.device("cpu"), tgt, 19) is None
